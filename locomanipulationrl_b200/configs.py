@@ -1,0 +1,219 @@
+"""Task constants for every hot-path task variant.
+
+The reference keeps these as class attributes (not yaml), one copy per task file.  Here they are
+one dataclass; each named constructor cites the reference class it restates.  The dataclass maps
+1:1 onto the C struct ``LmTaskParams`` (include/lm_b200.h) consumed by the CUDA kernels.
+
+Reference shorthand (all under /root/reference/RobotLearning/omniisaacgymenvs/):
+  QPC  tasks/quadruped_pose_control_tasks/quadruped_pose_control.py
+  QPCV tasks/quadruped_pose_control_tasks/quadruped_pose_control_vertical.py
+  QMP  tasks/quadruped_manipulate_plate/quadruped_manipulate_plate.py
+  QMPV tasks/quadruped_manipulate_plate/quadruped_manipulate_plate_vertical.py
+  JL   tasks/joint_train_locomanipulation/joint_locomanipulation.py
+  JLV  tasks/joint_train_locomanipulation/joint_locomanipulation_vertical.py
+  *_PC the ``_position_control.py`` sibling of QPC / QMP / JL
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field, replace
+from typing import Dict, List, Tuple
+
+KIND_LOCO = 0
+KIND_MANI = 1
+KIND_COTRAIN = 2
+
+CONTROL_VELOCITY = 0   # robot.py:452-454  (default of all six robot configs, quadruped_robot.py:12,42,77,...)
+CONTROL_POSITION = 1   # robot.py:449-451
+CONTROL_EFFORT = 2     # robot.py:455-459
+CONTROL_PD = 3         # *_PC explicit PD torque loop (quadruped_pose_control_position_control.py:275-313)
+
+# robot/quadruped_robot.py:45-52 (QuadrupedRobotOVOmni / OVFixedBaseOmni)
+_HORIZONTAL_ROBOT_INIT = [-1.2, 1.2, 1.2, -1.2,
+                          -1.22, -1.92, 1.92, 1.22, 1.92, 1.22, -1.22, -1.92,
+                          0.953, -0.953, 0.953, -0.953, 0.953, -0.953, 0.953, -0.953]
+# QPC:94-102 / QMP:94-102 override
+_HORIZONTAL_TASK_INIT = [-1.57, 1.57, 1.57, -1.57,
+                         -1.04, -2.09, 2.09, 1.04, 2.09, 1.04, -1.04, -2.09,
+                         1.37, -1.37, 1.37, -1.37, 1.37, -1.37, 1.37, -1.37]
+# robot/quadruped_robot.py:80-87 (QuadrupedRobotVerticalOVOmni / VerticalOVFixedOmni)
+_VERTICAL_INIT = [0.0, 0.0, 0.0, 0.0,
+                  0.35, -0.35, 0.35, -0.35, 0.35, -0.35, 0.35, -0.35,
+                  0.95, -0.95, 0.95, -0.95, 0.95, -0.95, 0.95, -0.95]
+
+# QPC:132-137
+_HORIZONTAL_CORNERS = [[0.075, 0.1835, -0.04], [-0.075, 0.1835, -0.04],
+                       [0.075, -0.1835, -0.04], [-0.075, -0.1835, -0.04]]
+# JLV:147-152
+_VERTICAL_CORNERS = [[0.0, -0.115, -0.1853], [0.0, 0.115, -0.1853],
+                     [-0.115, 0.0, -0.1853], [0.115, 0.0, -0.1853]]
+
+# QPC:127-130 (same in every task file)
+DEFAULT_BASE_TIP_POSITIONS = [[-0.0937, 0.1223, -0.1774], [0.0937, 0.1408, -0.1773],
+                              [-0.0937, -0.1408, -0.1773], [0.0937, -0.1223, -0.1774]]
+
+# *_PC: quadruped_pose_control_position_control.py:32-52,186-190
+_PC_MIN_SE = [-2.35, -0.78, -0.78, -2.35, -2.09, 0.52, 1.05, 0.52, 1.05, 0.52, -2.09, 0.52]
+_PC_MAX_SE = [0.78, 2.35, 2.35, 0.78, -1.05, 2.09, 2.09, 2.09, 2.09, 2.09, -1.05, 2.09]
+_PC_INIT_SE = [-1.57, 1.57, 1.57, -1.57, -1.57, 1.05, 1.57, 1.05, 1.57, 1.05, -1.57, 1.05]
+
+
+@dataclass
+class TaskConfig:
+    name: str
+    kind: int
+    vertical: bool
+    # --- goal sampling (rand_quaternions ranges) QPC:38-43
+    min_roll: float = -0.4
+    max_roll: float = 0.4
+    min_pitch: float = -0.4
+    max_pitch: float = 0.4
+    min_yaw: float = -1.57
+    max_yaw: float = 1.57
+    # --- observation scales QPC:27-34
+    position_scale: float = 5.0
+    quaternion_obs_scale: float = 1.0
+    linear_vel_scale: float = 2.0
+    angular_vel_scale: float = 0.25
+    tip_position_scale: float = 1.0
+    joint_position_scale: float = 0.3
+    joint_velocity_scale: float = 0.3
+    # --- reward QPC:54-61,457
+    quaternion_scale: float = 0.5
+    rot_eps: float = 0.1
+    translation_scale: float = -2.5
+    joint_acc_scale: float = -0.0005
+    action_rate_scale: float = -0.02
+    consecutive_success_reward: float = 600.0
+    fall_penalty: float = 0.0
+    joint_limit_penalty: float = -5.0
+    # --- thresholds QPC:64-87
+    baseline_knee_height: float = 0.04
+    baseline_height: float = 0.05
+    baseline_corner_height: float = 0.01
+    success_thresh: float = 0.15
+    max_consecutive_successes: int = 15
+    min_joint_23_diff: float = 0.43
+    max_joint_23_diff: float = 2.53
+    reset_min_joint_23_diff: float = 0.384
+    reset_max_joint_23_diff: float = 2.61
+    min_joint_1_pos: float = -2.35
+    max_joint_1_pos: float = 0.78
+    reset_min_joint_1_pos: float = -2.44
+    reset_max_joint_1_pos: float = 0.87
+    joint1_mirrored: bool = True   # horizontal: a2,a3 use (-max,-min) (QPC:482-503); vertical: all four share one range (JLV:589-596)
+    corners: List[List[float]] = field(default_factory=lambda: [list(c) for c in _HORIZONTAL_CORNERS])
+    # --- defaults written by reset_idx
+    loco_init_joint_pos: List[float] = field(default_factory=lambda: list(_HORIZONTAL_TASK_INIT))
+    loco_default_position: List[float] = field(default_factory=lambda: [0.0, 0.0, 0.14])
+    loco_default_quaternion: List[float] = field(default_factory=lambda: [1.0, 0.0, 0.0, 0.0])
+    mani_init_joint_pos: List[float] = field(default_factory=lambda: list(_HORIZONTAL_TASK_INIT))
+    mani_default_position: List[float] = field(default_factory=lambda: [0.0, 0.0, 0.0])
+    mani_default_quaternion: List[float] = field(default_factory=lambda: [0.0, 1.0, 0.0, 0.0])
+    obj_default_position: List[float] = field(default_factory=lambda: [0.0, 0.0, 0.14])
+    indicator_loco_position: List[float] = field(default_factory=lambda: [0.0, 0.0, 0.3])
+    indicator_mani_position: List[float] = field(default_factory=lambda: [0.0, 0.0, 0.3])
+    # --- buffers / surface
+    num_observations: int = 64
+    num_states: int = 93           # 93-wide states_buf in single-task horizontal/vertical files (QPC:119,406-423); 64 (alias of obs) in co-train (JLV:130,515)
+    num_actions: int = 12
+    zero_actions: bool = False     # debug leftover ``actions[:] = 0`` shipped live in JLV:258-259, QPCV:204, QMPV:214, *_PC
+    # --- control
+    control_mode: int = CONTROL_VELOCITY
+    velocity_limit: float = 3.0    # quadruped_robot.py:55
+    torque_limit: float = 1.5      # quadruped_robot.py:56
+    # --- sim cfg (cfg/task/*.yaml)
+    dt: float = 0.0083
+    control_frequency_inv: int = 4
+    max_episode_length: int = 300
+    clip_observations: float = 5.0
+    clip_actions: float = 1.0
+    env_spacing: float = 1.0
+    max_reset_counts: int = 2048   # QPC:151
+    # --- *_PC explicit PD (quadruped_pose_control_position_control.py:25-52)
+    pd_kp: float = 4.5
+    pd_kd: float = 0.2
+    pd_max_effort: float = 1.5
+    pd_action_scale: float = 0.1
+    pd_control_decimal: int = 4
+    pd_torque_divisor: float = 4.0   # single-task: /control_decimal (:313); co-train: /(control_decimal+1) (JL_PC:408)
+    pd_min_se: List[float] = field(default_factory=lambda: list(_PC_MIN_SE))
+    pd_max_se: List[float] = field(default_factory=lambda: list(_PC_MAX_SE))
+    pd_init_se: List[float] = field(default_factory=lambda: list(_PC_INIT_SE))
+
+    @property
+    def time_interval(self) -> float:
+        """Finite-difference Δt for joint acceleration (QPC:156; *_PC: dt*(control_decimal+1), :199)."""
+        if self.control_mode == CONTROL_PD:
+            return self.dt * (self.pd_control_decimal + 1)
+        return self.dt * self.control_frequency_inv
+
+    def with_(self, **kw) -> "TaskConfig":
+        return replace(self, **kw)
+
+
+def _vertical_limits() -> Dict[str, object]:
+    # JLV:96-99 / QPCV:84-87
+    return dict(min_joint_1_pos=-2.09, max_joint_1_pos=2.09, reset_min_joint_1_pos=-2.26,
+                reset_max_joint_1_pos=2.26, joint1_mirrored=False,
+                corners=[list(c) for c in _VERTICAL_CORNERS])
+
+
+def quadruped_pose_control() -> TaskConfig:
+    """QPC:20-158."""
+    return TaskConfig(name="QuadrupedPoseControl", kind=KIND_LOCO, vertical=False)
+
+
+def quadruped_pose_control_vertical() -> TaskConfig:
+    """QPCV: robot defaults from QuadrupedRobotVerticalOVOmni (quadruped_robot.py:70-103); ``actions[:] = 0`` live at :204."""
+    return TaskConfig(name="QuadrupedPoseControlVertical", kind=KIND_LOCO, vertical=True,
+                      loco_init_joint_pos=list(_VERTICAL_INIT), loco_default_position=[0.0, 0.0, 0.35],
+                      indicator_loco_position=[0.0, 0.0, 0.4], zero_actions=True, **_vertical_limits())
+
+
+def quadruped_manipulate_plate() -> TaskConfig:
+    """QMP:21-168."""
+    return TaskConfig(name="QuadrupedManipulatePlate", kind=KIND_MANI, vertical=False)
+
+
+def quadruped_manipulate_plate_vertical() -> TaskConfig:
+    """QMPV:91-93,141-143; ``actions[:] = 0`` live at :214."""
+    return TaskConfig(name="QuadrupedManipulatePlateVertical", kind=KIND_MANI, vertical=True,
+                      mani_init_joint_pos=list(_VERTICAL_INIT), obj_default_position=[0.0, 0.0, 0.35],
+                      indicator_mani_position=[0.0, 0.0, 0.4], zero_actions=True, **_vertical_limits())
+
+
+def joint_locomanipulation() -> TaskConfig:
+    """JL:21-227.  Ships fixed goal angles (JL:61-66) and the robot-file default poses (overrides commented out, JL:114-137)."""
+    return TaskConfig(name="JointLocomanipulation", kind=KIND_COTRAIN, vertical=False,
+                      min_roll=0.2, max_roll=0.2, min_pitch=0.2, max_pitch=0.2, min_yaw=0.785, max_yaw=0.785,
+                      loco_init_joint_pos=list(_HORIZONTAL_ROBOT_INIT), loco_default_position=[0.0, 0.0, 0.18],
+                      mani_init_joint_pos=list(_HORIZONTAL_ROBOT_INIT), mani_default_position=[0.0, 0.0, 0.5],
+                      obj_default_position=[0.0, 0.0, 0.68], indicator_loco_position=[0.0, 0.0, 0.3],
+                      indicator_mani_position=[0.0, 0.0, 0.8], num_states=64, env_spacing=0.5)
+
+
+def joint_locomanipulation_vertical() -> TaskConfig:
+    """JLV:21-195; ``actions[...] = 0`` live at JLV:258-259."""
+    return TaskConfig(name="JointLocomanipulationVertical", kind=KIND_COTRAIN, vertical=True,
+                      loco_init_joint_pos=list(_VERTICAL_INIT), loco_default_position=[0.0, 0.0, 0.35],
+                      mani_init_joint_pos=list(_VERTICAL_INIT), mani_default_position=[0.0, 0.0, 0.6],
+                      obj_default_position=[0.0, 0.0, 0.95], indicator_loco_position=[0.0, 0.0, 0.5],
+                      indicator_mani_position=[0.0, 0.0, 1.1], num_states=64, zero_actions=True,
+                      **_vertical_limits())
+
+
+TASK_CONFIGS = {
+    "QuadrupedPoseControl": quadruped_pose_control,
+    "QuadrupedPoseControlVertical": quadruped_pose_control_vertical,
+    "QuadrupedManipulatePlate": quadruped_manipulate_plate,
+    "QuadrupedManipulatePlateVertical": quadruped_manipulate_plate_vertical,
+    "JointLocomanipulation": joint_locomanipulation,
+    "JointLocomanipulationVertical": joint_locomanipulation_vertical,
+}
+
+
+def get_task_config(name: str) -> TaskConfig:
+    """Same role as the reference's ``task_map`` lookup (utils/task_util.py:60-90)."""
+    if name not in TASK_CONFIGS:
+        raise KeyError(f"unknown task {name!r}; known: {sorted(TASK_CONFIGS)}")
+    return TASK_CONFIGS[name]()
