@@ -1,0 +1,245 @@
+/*
+ * lm_b200.h — C ABI of the B200-native LocoManipulationRL task / policy hot path.
+ *
+ * Drop-in boundary for the reference's per-environment task math.  Every entry point cites the
+ * reference interface it replaces (paths under /root/reference/RobotLearning/omniisaacgymenvs/).
+ * All pointers are DEVICE pointers unless a name ends in _host; all tensors are contiguous,
+ * row-major, 16-byte aligned, in the reference's own dtypes (fp32 data, int64 flags).  `stream`
+ * is a cudaStream_t passed as void* (torch.cuda.current_stream().cuda_stream).  Calls never
+ * allocate, never synchronise the host (except the *_host entry points), and never throw:
+ * they return 0 on success or a negative LM_ERR_* / positive cudaError_t code;
+ * lm_last_error() returns a thread-local message.
+ */
+#ifndef LM_B200_H
+#define LM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LM_ABI_VERSION 1
+
+#define LM_NUM_DOF 20        /* articulation DOFs: 12 actuated + 8 passive (robot/base/robot.py:437) */
+#define LM_NUM_ACT 12        /* actions / actuated DOFs (quadruped_pose_control.py:117)              */
+#define LM_NUM_OBS 64        /* observation row (quadruped_pose_control.py:118,358-371)              */
+#define LM_NUM_STATES_FULL 93 /* single-task states row (quadruped_pose_control.py:119,406-423)      */
+
+enum { LM_KIND_LOCO = 0, LM_KIND_MANI = 1, LM_KIND_COTRAIN = 2 };
+enum { LM_CONTROL_VELOCITY = 0, LM_CONTROL_POSITION = 1, LM_CONTROL_EFFORT = 2, LM_CONTROL_PD = 3 };
+enum { LM_GAE_RLGAMES = 0, LM_GAE_SKRL = 1 };
+
+enum {
+  LM_OK = 0,
+  LM_ERR_BAD_ARG = -1,     /* null pointer / inconsistent sizes */
+  LM_ERR_ALIGNMENT = -2,   /* a tensor is not 16-byte aligned   */
+  LM_ERR_NO_DEVICE = -3,   /* no sm_100 device / wrong arch     */
+  LM_ERR_UNSUPPORTED = -4
+};
+
+/* Task constants: mirror of the reference's class attributes
+ * (quadruped_pose_control.py:27-87, quadruped_manipulate_plate.py:28-88,
+ *  joint_locomanipulation_vertical.py:39-99) plus the yaml values the tasks read
+ *  (cfg/task/*.yaml: dt, controlFrequencyInv, max_episode_length, clipObservations, clipActions). */
+typedef struct LmTaskParams {
+  int32_t kind;                 /* LM_KIND_*                                                         */
+  int32_t num_envs;             /* N; co-train: first N/2 locomotion, last N/2 manipulation (JL:22-35) */
+  int32_t num_states;           /* 93 (single task) or 64 (co-train: states alias obs, JLV:515)      */
+  int32_t control_mode;         /* LM_CONTROL_*                                                      */
+  int32_t zero_actions;         /* debug leftover `actions[:] = 0` shipped live (JLV:258-259)        */
+  int32_t joint1_mirrored;      /* 1: a2,a3 use (-max,-min) (QPC:482-503); 0: one range (JLV:589-596) */
+  int32_t max_consecutive_successes;
+  int32_t max_episode_length;
+  int32_t max_reset_counts;     /* 2048 (QPC:151)                                                    */
+  int32_t clamp_actions;        /* 1: fuse VecEnvRLGames.step's clamp (envs/vec_env_rlgames.py:60)   */
+  int32_t dof_index[LM_NUM_ACT];/* articulation column of each actuated DOF (robot.py:174-190)       */
+  /* goal sampling (utils/math.py:176-193): angle = min + range * u, range = (max - min) in double    */
+  float min_roll, roll_range, min_pitch, pitch_range, min_yaw, yaw_range;
+  /* observation scales (QPC:27-34) */
+  float position_scale, quaternion_obs_scale, linear_vel_scale, angular_vel_scale, tip_position_scale,
+      joint_position_scale, joint_velocity_scale;
+  /* reward (QPC:54-61,432-457) */
+  float quaternion_scale, rot_eps, translation_scale, joint_acc_scale, action_rate_scale,
+      consecutive_success_reward, fall_penalty, joint_limit_penalty;
+  /* thresholds (QPC:64-87) */
+  float baseline_knee_height, baseline_height, baseline_corner_height, success_thresh;
+  float min_joint_23_diff, max_joint_23_diff, reset_min_joint_23_diff, reset_max_joint_23_diff;
+  float min_joint_1_pos, max_joint_1_pos, reset_min_joint_1_pos, reset_max_joint_1_pos;
+  float time_interval;          /* dt * controlFrequencyInv (QPC:156)                                 */
+  float clip_actions, clip_observations;
+  float action_limit;           /* velocity ±3 rad/s, position ±pi, effort ±1.5 N·m (robot.py:195-231) */
+  float corners[4][3];          /* body corners in the robot frame (QPC:132-137, JLV:147-152)         */
+  float default_base_tip[4][3]; /* QPC:127-130                                                        */
+  float loco_init_joint_pos[LM_NUM_DOF], loco_default_position[3], loco_default_quaternion[4];
+  float mani_init_joint_pos[LM_NUM_DOF], mani_default_position[3], mani_default_quaternion[4];
+  float obj_default_position[3];
+  float indicator_loco_position[3], indicator_mani_position[3];
+} LmTaskParams;
+
+/* One articulation + its auxiliary rigid views, as PhysX exposes them through
+ * ArticulationView / RigidPrimView (robot/base/robot.py:288-321; objects/base/rigid_object.py:52-58).
+ * Read by lm_task_post_step; written for reset envs by lm_task_pre_step
+ * (the set_* calls of reset_idx, QPC:244-284 / QMP:252-294).  n = N (single task) or N/2. */
+typedef struct LmRobotViews {
+  float* dof_pos;        /* [n,20] */
+  float* dof_vel;        /* [n,20] */
+  float* root_pos;       /* [n,3] world (locomotion robot only; NULL for the fixed-base robot) */
+  float* root_quat;      /* [n,4] wxyz  */
+  float* root_lin_vel;   /* [n,3] */
+  float* root_ang_vel;   /* [n,3] */
+  float* tip_pos;        /* [n*4,3] world */
+  float* knee_pos;       /* [n*8,3] world */
+  float* indicator_pos;  /* [n,3] world  (pose indicator, objects/pose_indicator.py) */
+  float* indicator_quat; /* [n,4] */
+  float* plate_pos;      /* [n,3] world  (manipulation only; objects/plate.py) */
+  float* plate_quat;     /* [n,4] */
+  float* plate_lin_vel;  /* [n,3] */
+  float* plate_ang_vel;  /* [n,3] */
+  float* targets;        /* [n,12] joint velocity/position targets, or [n,20] efforts (robot.py:444-461) */
+} LmRobotViews;
+
+/* Task-owned RL buffers (tasks/base/rl_task.py:104-113; quadruped_pose_control.py:123-154). */
+typedef struct LmTaskBuffers {
+  float* obs_buf;                  /* [N,64]                                     */
+  float* states_buf;               /* [N,93] or NULL when states alias obs       */
+  float* rew_buf;                  /* [N]                                        */
+  int64_t* reset_buf;              /* [N] (initialised to ones, rl_task.py:111)  */
+  int64_t* progress_buf;           /* [N]                                        */
+  int64_t* successes;              /* [N]                                        */
+  int64_t* consecutive_successes;  /* [N]                                        */
+  int64_t* goal_reset_buf;         /* [N]                                        */
+  float* actions_ring;             /* [2,N,12]: slot (step&1) = current_actions, other = last_actions */
+  float* last_joint_vel;           /* [N,12] (robot.py:263,291)                  */
+  float* last_base_tip;            /* [N,4,3] (QPC:126,426)                      */
+  float* goal_quaternions;         /* [N,4]                                      */
+  int64_t* reset_env_ids;          /* [N] out: ascending ids reset by the last pre_step (QPC:206)      */
+  int32_t* num_reset;              /* [2] out: {count, count in locomotion half}                        */
+  float* extras;                   /* [LM_NUM_EXTRAS] out, see LM_EXTRA_*                               */
+  int64_t* counters;               /* [6] num_successes,num_resets,{_loco},{_mani} (QPC:152-153, JLV:173-184) */
+} LmTaskBuffers;
+
+enum {
+  LM_EXTRA_ORIENTATION_REW = 0, LM_EXTRA_TRANSLATION_PENALTY, LM_EXTRA_JOINT_ACC_PENALTY,
+  LM_EXTRA_ACTION_RATE_PENALTY, LM_EXTRA_CONSECUTIVE_SUCCESSES_REW, LM_EXTRA_JOINT_LIMIT_PENALTY,
+  LM_EXTRA_FALL_PENALTY, LM_EXTRA_SUCCESS_RATE, LM_EXTRA_SUCCESS_RATE_LOCO, LM_EXTRA_SUCCESS_RATE_MANI,
+  LM_EXTRA_NAN_COUNT, LM_EXTRA_BELOW_M50_COUNT, /* device-side form of the guards at QPC:550-558 */
+  LM_NUM_EXTRAS = 16
+};
+
+typedef struct LmTask LmTask; /* opaque */
+
+int lm_abi_version(void);
+const char* lm_last_error(void);
+/* number of SMs / name of the device the library will launch on (-1 / "" if none) */
+int lm_device_sm_count(int device);
+/* sizeof() of the ABI structs as compiled (0 LmTaskParams, 1 LmRobotViews, 2 LmTaskBuffers, 3 LmHostStep):
+ * bindings assert their mirror structs agree. */
+int lm_struct_size(int which);
+
+/* Replaces the constructor + cleanup() of RLTask/JointRLTask (rl_task.py:55-113): validates
+ * params, sizes the launch grids, allocates the few KB of device scratch (tile reset counts,
+ * block partials).  The only allocating call. */
+LmTask* lm_task_create(const LmTaskParams* params, int device);
+void lm_task_destroy(LmTask* task);
+/* Current step parity (which actions_ring slot holds current_actions). */
+int lm_task_step_parity(const LmTask* task);
+/* When on, post_step stores clamp(obs, ±clip_observations) — the adapter's _process_data clamp
+ * (envs/vec_env_rlgames.py:42) fused into the producing kernel.  Off by default (obs_buf then holds
+ * the reference task's unclamped values). */
+int lm_task_set_clamp_observations(LmTask* task, int on);
+
+/* pre_physics_step (QPC:200-228 / QMP:213-236 / JLV:248-270) including reset_idx
+ * (QPC:230-299 / JLV:272-377), rand_quaternions (utils/math.py:176-193) and take_action
+ * (robot.py:444-461).  `actions` [N,12]; `uniforms` [N,3] = the torch.rand draw, row k is consumed
+ * by the k-th reset env in ascending id order (its reset rank / goal index).  `loco` / `mani`
+ * may be NULL when the task kind has no such half. */
+int lm_task_pre_step(LmTask* task, const LmRobotViews* loco, const LmRobotViews* mani,
+                     const float* env_pos, const LmTaskBuffers* buf, const float* actions,
+                     const float* uniforms, void* stream);
+
+/* reset_idx(env_ids) called directly (QPC:230-299): env_ids [count] int64 (device), entry k consumes
+ * uniform row k.  In co-train the caller orders ids locomotion-first, as nonzero() does. */
+int lm_task_reset_idx(LmTask* task, const LmRobotViews* loco, const LmRobotViews* mani,
+                      const float* env_pos, const LmTaskBuffers* buf, const int64_t* env_ids,
+                      int32_t count, const float* uniforms, void* stream);
+
+/* post_physics_step (rl_task.py:240-260): progress += 1, update_all_states (robot.py:276-321),
+ * get_observations (QPC:301-426 / QMP:311-435 / JLV:379-521), calculate_metrics
+ * (QPC:428-560), is_done (QPC:562-633) and the extras means / success-rate bookkeeping. */
+int lm_task_post_step(LmTask* task, const LmRobotViews* loco, const LmRobotViews* mani,
+                      const float* env_pos, const LmTaskBuffers* buf, void* stream);
+
+/* _process_data of the vec-env adapter (envs/vec_env_rlgames.py:41-46): out = clamp(in, ±clip). */
+int lm_clamp_copy(const float* in, float* out, int64_t count, float clip, void* stream);
+
+/* One sub-step of the *_PC explicit PD loop
+ * (quadruped_pose_control_position_control.py:295-311): torque = clamp(kp (target - q) - kd qd, ±max),
+ * torque_sum += torque.  q/qd are [n,20] articulation rows gathered through dof_index. */
+int lm_pd_substep(const float* dof_pos, const float* dof_vel, const float* targets, float* torque,
+                  float* torque_sum, const int32_t* dof_index_host, int32_t n, float kp, float kd,
+                  float max_effort, void* stream);
+/* Swing/extension target integration of the *_PC variants (…position_control.py:275-287). */
+int lm_pd_integrate_targets(const float* actions, float* targets_se, float* targets,
+                            const float* se_lower_host, const float* se_upper_host, int32_t n,
+                            float action_scale, int32_t zero_actions, void* stream);
+
+/* MLP actor-critic forward: Linear(64,256)-ELU-Linear(256,128)-ELU-Linear(128,64)-ELU, heads
+ * mean Linear(64,12) and value Linear(64,1) (scripts/skrl_ppo_locomanipulation.py:33-42,57-61;
+ * cfg/train/JointLocomanipulationPPO.yaml:10-32).  bf16 operands, fp32 accumulate, tcgen05.
+ * lm_mlp_pack converts nn.Linear [out,in] fp32 weights (device) into the kernel's resident layout. */
+typedef struct LmMlp LmMlp;
+LmMlp* lm_mlp_create(int device);
+void lm_mlp_destroy(LmMlp* mlp);
+int lm_mlp_pack(LmMlp* mlp, const float* w1, const float* b1, const float* w2, const float* b2,
+                const float* w3, const float* b3, const float* w_mu, const float* b_mu,
+                const float* w_value, const float* b_value, void* stream);
+/* obs [N,64] fp32.  Optional input standardisation fused in the prologue: when norm_mean != NULL,
+ * x = clamp((obs - norm_mean) * norm_inv_std, ±norm_clip) with norm_inv_std supplied by the caller in
+ * its library's form (rl_games RunningMeanStd: 1/sqrt(var + 1e-5), clamp 5; skrl RunningStandardScaler:
+ * 1/(sqrt(var) + 1e-8), clamp 5).  Outputs mu [N,12], value [N] fp32. */
+int lm_mlp_forward(LmMlp* mlp, const float* obs, const float* norm_mean, const float* norm_inv_std,
+                   float norm_clip, float* mu, float* value, int32_t n, void* stream);
+
+/* GNN limb-graph policy forward (scripts/graph_model_orebot_ov.py:11-241; wired at
+ * scripts/skrl_ppo_locomanipulation.py:44-49 with hidden 32).  fp32.  Weights are the module's
+ * own tensors in nn.Linear layout, concatenated by lm_gnn_pack in a fixed order. */
+typedef struct LmGnn LmGnn;
+LmGnn* lm_gnn_create(int device);
+void lm_gnn_destroy(LmGnn* gnn);
+int lm_gnn_pack(LmGnn* gnn, const float* const* weights, int32_t num_tensors, void* stream);
+int lm_gnn_forward(LmGnn* gnn, const float* obs, float* mu, float* value, int32_t n, void* stream);
+
+/* PPO generalised advantage estimation over a time-major [T,N] rollout.
+ * LM_GAE_RLGAMES: rl_games 1.6.0 A2CBase.discount_values (next-step done mask; last step uses
+ *   `last_dones`/`last_values`).  LM_GAE_SKRL: skrl PPO compute_gae (current-step done mask;
+ *   returns = adv + values; optional normalisation is a separate call).
+ * dones is fp32 (0/1) as both libraries store it.  advantages/returns [T,N]. */
+int lm_gae(const float* rewards, const float* values, const float* dones, const float* last_values,
+           const float* last_dones, float* advantages, float* returns, int32_t T, int32_t N,
+           float gamma, float lambda, int32_t variant, void* stream);
+/* Same recurrence over an env-major [N,T] buffer: one warp per env, warp-shuffle scan of the affine
+ * maps A -> delta_t + c_t A (32 time steps per scan).  Agrees with lm_gae to fp32 round-off. */
+int lm_gae_env_major(const float* rewards, const float* values, const float* dones,
+                     const float* last_values, const float* last_dones, float* advantages,
+                     float* returns, int32_t T, int32_t N, float gamma, float lambda, int32_t variant,
+                     void* stream);
+
+/* End-to-end host-buffer entry used by bench.py's e2e leg: one env step with inputs in pinned
+ * host memory (state of both robots packed as the LmRobotViews fields, actions, uniforms) and
+ * outputs (obs, rew, reset) read back.  Copies run on `stream`; returns after synchronising it. */
+typedef struct LmHostStep {
+  const float* actions_host;   /* [N,12] */
+  const float* uniforms_host;  /* [N,3]  */
+  const float* loco_state_host; int64_t loco_state_floats; float* loco_state_dev;
+  const float* mani_state_host; int64_t mani_state_floats; float* mani_state_dev;
+  float* actions_dev; float* uniforms_dev;
+  float* obs_host; float* rew_host; int64_t* reset_host;
+} LmHostStep;
+int lm_task_step_host(LmTask* task, const LmRobotViews* loco, const LmRobotViews* mani,
+                      const float* env_pos, const LmTaskBuffers* buf, const LmHostStep* io, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LM_B200_H */

@@ -1,0 +1,182 @@
+"""ctypes binding of liblm_b200.so (include/lm_b200.h).  The structures below mirror the C structs
+field by field; tests/test_cabi.py checks sizes and that every declared symbol is exported.
+
+There is NO fallback: if the library is missing or a call fails, an exception is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+from .configs import TaskConfig, DEFAULT_BASE_TIP_POSITIONS, CONTROL_EFFORT, CONTROL_POSITION, CONTROL_VELOCITY
+
+NUM_DOF, NUM_ACT, NUM_OBS, NUM_STATES_FULL, NUM_EXTRAS = 20, 12, 64, 93, 16
+_f, _i32, _i64, _fp = C.c_float, C.c_int32, C.c_int64, C.POINTER(C.c_float)
+_i64p, _i32p = C.POINTER(C.c_int64), C.POINTER(C.c_int32)
+
+EXTRA_NAMES = ["orientation_rew", "translation_penalty", "joint_acc_penalty", "action_rate_penalty",
+               "consecutive_successes_rew", "joint_limit_panelty", "fall_penalty"]
+EXTRA_SUCCESS_RATE, EXTRA_NAN_COUNT, EXTRA_BELOW_M50 = 7, 10, 11
+
+
+class LmTaskParams(C.Structure):
+    _fields_ = [
+        ("kind", _i32), ("num_envs", _i32), ("num_states", _i32), ("control_mode", _i32), ("zero_actions", _i32),
+        ("joint1_mirrored", _i32), ("max_consecutive_successes", _i32), ("max_episode_length", _i32),
+        ("max_reset_counts", _i32), ("clamp_actions", _i32), ("dof_index", _i32 * NUM_ACT),
+        ("min_roll", _f), ("roll_range", _f), ("min_pitch", _f), ("pitch_range", _f), ("min_yaw", _f), ("yaw_range", _f),
+        ("position_scale", _f), ("quaternion_obs_scale", _f), ("linear_vel_scale", _f), ("angular_vel_scale", _f),
+        ("tip_position_scale", _f), ("joint_position_scale", _f), ("joint_velocity_scale", _f),
+        ("quaternion_scale", _f), ("rot_eps", _f), ("translation_scale", _f), ("joint_acc_scale", _f),
+        ("action_rate_scale", _f), ("consecutive_success_reward", _f), ("fall_penalty", _f), ("joint_limit_penalty", _f),
+        ("baseline_knee_height", _f), ("baseline_height", _f), ("baseline_corner_height", _f), ("success_thresh", _f),
+        ("min_joint_23_diff", _f), ("max_joint_23_diff", _f), ("reset_min_joint_23_diff", _f), ("reset_max_joint_23_diff", _f),
+        ("min_joint_1_pos", _f), ("max_joint_1_pos", _f), ("reset_min_joint_1_pos", _f), ("reset_max_joint_1_pos", _f),
+        ("time_interval", _f), ("clip_actions", _f), ("clip_observations", _f), ("action_limit", _f),
+        ("corners", (_f * 3) * 4), ("default_base_tip", (_f * 3) * 4),
+        ("loco_init_joint_pos", _f * NUM_DOF), ("loco_default_position", _f * 3), ("loco_default_quaternion", _f * 4),
+        ("mani_init_joint_pos", _f * NUM_DOF), ("mani_default_position", _f * 3), ("mani_default_quaternion", _f * 4),
+        ("obj_default_position", _f * 3), ("indicator_loco_position", _f * 3), ("indicator_mani_position", _f * 3),
+    ]
+
+
+class LmRobotViews(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "dof_pos", "dof_vel", "root_pos", "root_quat", "root_lin_vel", "root_ang_vel", "tip_pos", "knee_pos",
+        "indicator_pos", "indicator_quat", "plate_pos", "plate_quat", "plate_lin_vel", "plate_ang_vel", "targets")]
+
+
+class LmTaskBuffers(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "obs_buf", "states_buf", "rew_buf", "reset_buf", "progress_buf", "successes", "consecutive_successes",
+        "goal_reset_buf", "actions_ring", "last_joint_vel", "last_base_tip", "goal_quaternions", "reset_env_ids",
+        "num_reset", "extras", "counters")]
+
+
+class LmHostStep(C.Structure):
+    _fields_ = [("actions_host", C.c_void_p), ("uniforms_host", C.c_void_p),
+                ("loco_state_host", C.c_void_p), ("loco_state_floats", _i64), ("loco_state_dev", C.c_void_p),
+                ("mani_state_host", C.c_void_p), ("mani_state_floats", _i64), ("mani_state_dev", C.c_void_p),
+                ("actions_dev", C.c_void_p), ("uniforms_dev", C.c_void_p),
+                ("obs_host", C.c_void_p), ("rew_host", C.c_void_p), ("reset_host", C.c_void_p)]
+
+
+# name -> (restype, argtypes); every symbol include/lm_b200.h declares
+_vp = C.c_void_p
+SYMBOLS = {
+    "lm_abi_version": (C.c_int, []),
+    "lm_last_error": (C.c_char_p, []),
+    "lm_device_sm_count": (C.c_int, [C.c_int]),
+    "lm_struct_size": (C.c_int, [C.c_int]),
+    "lm_task_create": (_vp, [C.POINTER(LmTaskParams), C.c_int]),
+    "lm_task_destroy": (None, [_vp]),
+    "lm_task_step_parity": (C.c_int, [_vp]),
+    "lm_task_set_clamp_observations": (C.c_int, [_vp, C.c_int]),
+    "lm_task_pre_step": (C.c_int, [_vp, C.POINTER(LmRobotViews), C.POINTER(LmRobotViews), _vp, C.POINTER(LmTaskBuffers), _vp, _vp, _vp]),
+    "lm_task_reset_idx": (C.c_int, [_vp, C.POINTER(LmRobotViews), C.POINTER(LmRobotViews), _vp, C.POINTER(LmTaskBuffers), _vp, _i32, _vp, _vp]),
+    "lm_task_post_step": (C.c_int, [_vp, C.POINTER(LmRobotViews), C.POINTER(LmRobotViews), _vp, C.POINTER(LmTaskBuffers), _vp]),
+    "lm_clamp_copy": (C.c_int, [_vp, _vp, _i64, _f, _vp]),
+    "lm_pd_substep": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.POINTER(_i32), _i32, _f, _f, _f, _vp]),
+    "lm_pd_integrate_targets": (C.c_int, [_vp, _vp, _vp, C.POINTER(_f), C.POINTER(_f), _i32, _f, _i32, _vp]),
+    "lm_mlp_create": (_vp, [C.c_int]),
+    "lm_mlp_destroy": (None, [_vp]),
+    "lm_mlp_pack": (C.c_int, [_vp] * 11 + [_vp]),
+    "lm_mlp_forward": (C.c_int, [_vp, _vp, _vp, _vp, _f, _vp, _vp, _i32, _vp]),
+    "lm_gnn_create": (_vp, [C.c_int]),
+    "lm_gnn_destroy": (None, [_vp]),
+    "lm_gnn_pack": (C.c_int, [_vp, C.POINTER(_vp), _i32, _vp]),
+    "lm_gnn_forward": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _vp]),
+    "lm_gae": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _f, _f, _i32, _vp]),
+    "lm_gae_env_major": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _f, _f, _i32, _vp]),
+    "lm_task_step_host": (C.c_int, [_vp, C.POINTER(LmRobotViews), C.POINTER(LmRobotViews), _vp, C.POINTER(LmTaskBuffers), C.POINTER(LmHostStep), _vp]),
+}
+
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "liblm_b200.so")
+_lib: Optional[C.CDLL] = None
+
+
+class LmError(RuntimeError):
+    pass
+
+
+def load(path: Optional[str] = None) -> C.CDLL:
+    """Load the C-ABI library; raises if it is missing (no CPU / eager fallback exists)."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    path = path or LIB_PATH
+    if not os.path.exists(path):
+        raise LmError(f"{path} not found: build it with `python -m locomanipulationrl_b200.build` "
+                      "(there is no fallback path)")
+    lib = C.CDLL(path)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)   # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    if lib.lm_abi_version() != 1:
+        raise LmError("liblm_b200.so ABI version mismatch")
+    for which, struct in enumerate((LmTaskParams, LmRobotViews, LmTaskBuffers, LmHostStep)):
+        if lib.lm_struct_size(which) != C.sizeof(struct):
+            raise LmError(f"struct layout mismatch for {struct.__name__}: C {lib.lm_struct_size(which)} vs ctypes {C.sizeof(struct)}")
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = load().lm_last_error()
+        raise LmError(f"{what} failed (code {rc}): {msg.decode() if msg else ''}")
+
+
+def ptr(t) -> Optional[int]:
+    """Device pointer of a torch tensor (None -> NULL)."""
+    if t is None:
+        return None
+    assert t.is_contiguous(), "tensors passed to the C ABI must be contiguous"
+    return t.data_ptr()
+
+
+def task_params(cfg: TaskConfig, num_envs: int, clamp_actions: bool = True, dof_index=None) -> LmTaskParams:
+    """TaskConfig -> LmTaskParams.  Range terms are formed in double like the reference's Python floats
+    (utils/math.py:187-189: ``(max_roll-min_roll) * rand``), then rounded to fp32 by ctypes."""
+    import math
+    p = LmTaskParams()
+    p.kind, p.num_envs, p.num_states = cfg.kind, num_envs, cfg.num_states
+    p.control_mode, p.zero_actions = cfg.control_mode, int(cfg.zero_actions)
+    p.joint1_mirrored = int(cfg.joint1_mirrored)
+    p.max_consecutive_successes, p.max_episode_length = cfg.max_consecutive_successes, cfg.max_episode_length
+    p.max_reset_counts, p.clamp_actions = cfg.max_reset_counts, int(clamp_actions)
+    for j, v in enumerate(dof_index if dof_index is not None else range(NUM_ACT)):
+        p.dof_index[j] = int(v)
+    p.min_roll, p.roll_range = cfg.min_roll, cfg.max_roll - cfg.min_roll
+    p.min_pitch, p.pitch_range = cfg.min_pitch, cfg.max_pitch - cfg.min_pitch
+    p.min_yaw, p.yaw_range = cfg.min_yaw, cfg.max_yaw - cfg.min_yaw
+    for name in ("position_scale", "quaternion_obs_scale", "linear_vel_scale", "angular_vel_scale", "tip_position_scale",
+                 "joint_position_scale", "joint_velocity_scale", "quaternion_scale", "rot_eps", "translation_scale",
+                 "joint_acc_scale", "action_rate_scale", "consecutive_success_reward", "fall_penalty", "joint_limit_penalty",
+                 "baseline_knee_height", "baseline_height", "baseline_corner_height", "success_thresh",
+                 "min_joint_23_diff", "max_joint_23_diff", "reset_min_joint_23_diff", "reset_max_joint_23_diff",
+                 "min_joint_1_pos", "max_joint_1_pos", "reset_min_joint_1_pos", "reset_max_joint_1_pos",
+                 "clip_actions", "clip_observations"):
+        setattr(p, name, getattr(cfg, name))
+    p.time_interval = cfg.time_interval
+    p.action_limit = {CONTROL_VELOCITY: cfg.velocity_limit, CONTROL_POSITION: math.pi,
+                      CONTROL_EFFORT: cfg.torque_limit}.get(cfg.control_mode, cfg.velocity_limit)
+    for k in range(4):
+        for i in range(3):
+            p.corners[k][i] = cfg.corners[k][i]
+            p.default_base_tip[k][i] = DEFAULT_BASE_TIP_POSITIONS[k][i]
+    for j in range(NUM_DOF):
+        p.loco_init_joint_pos[j] = cfg.loco_init_joint_pos[j]
+        p.mani_init_joint_pos[j] = cfg.mani_init_joint_pos[j]
+    for i in range(3):
+        p.loco_default_position[i] = cfg.loco_default_position[i]
+        p.mani_default_position[i] = cfg.mani_default_position[i]
+        p.obj_default_position[i] = cfg.obj_default_position[i]
+        p.indicator_loco_position[i] = cfg.indicator_loco_position[i]
+        p.indicator_mani_position[i] = cfg.indicator_mani_position[i]
+    for i in range(4):
+        p.loco_default_quaternion[i] = cfg.loco_default_quaternion[i]
+        p.mani_default_quaternion[i] = cfg.mani_default_quaternion[i]
+    return p

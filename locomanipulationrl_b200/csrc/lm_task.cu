@@ -1,0 +1,915 @@
+// Task hot path for sm_100a: reset rank scan, pre_physics_step (+reset_idx scatter, goal resample,
+// action -> target) and post_physics_step (state read-back, observation assembly, rot-distance
+// reward, termination, success bookkeeping) — one env per thread, one 128-env tile per CTA, every
+// per-env array staged through shared memory by 1-D TMA bulk copies (the rows of a tile are one
+// contiguous span of the row-major [N,k] tensors the reference's API fixes).
+//
+// Reference restated (paths under /root/reference/RobotLearning/omniisaacgymenvs/):
+//   tasks/quadruped_pose_control_tasks/quadruped_pose_control.py:200-633        (QPC)
+//   tasks/quadruped_manipulate_plate/quadruped_manipulate_plate.py:213-652      (QMP)
+//   tasks/joint_train_locomanipulation/joint_locomanipulation_vertical.py:248-802 (JLV)
+//   robot/base/robot.py:276-321,444-461; objects/base/rigid_object.py:36-58; utils/math.py:7-193
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "lm_common.cuh"
+#include "lm_host.h"
+
+namespace lm {
+
+constexpr int T = 128;            // envs per tile == threads per CTA
+constexpr int OBS_PAD = 68;       // padded obs row (floats): 272 B stride -> conflict-free 128-bit smem access
+constexpr int STATS = 16;         // per-CTA partials: 7 reward terms, nan, below -50, goal_reset, reset, pad
+
+struct Derived {                  // host-computed constants (lm_task_create)
+  float R0[9];                    // rot_matrices_from_quat(mani default quaternion)  (QMP:149, math.py:7-19)
+  float p0inv[3];                 // bmm(R0^T, -p0)                                   (math.py:165-166)
+  float corners_world[4][3];      // transform_vectors(q0, p0, corners)               (QMP:162-165)
+  int32_t half;                   // envs per half (N for single-task kinds)
+  int32_t tiles_per_half;
+  int32_t num_tiles;
+  int32_t dof_identity;           // dof_index == 0..11
+};
+
+struct KernelParams {
+  LmTaskParams p;
+  Derived d;
+};
+
+// ------------------------------------------------------------------------------------------------
+// tile geometry: tiles never straddle the locomotion / manipulation boundary
+// ------------------------------------------------------------------------------------------------
+struct Tile {
+  int is_mani;      // which robot's views this tile reads
+  int hr0;          // first row in the half-arrays
+  int e0;           // first global env id
+  int n;            // valid envs in this tile
+};
+__device__ __forceinline__ Tile tile_of(const KernelParams& kp, int t) {
+  Tile tl;
+  int second = t >= kp.d.tiles_per_half && kp.p.kind == LM_KIND_COTRAIN;
+  int lt = second ? t - kp.d.tiles_per_half : t;
+  tl.is_mani = (kp.p.kind == LM_KIND_MANI) || second;
+  tl.hr0 = lt * T;
+  tl.e0 = (second ? kp.d.half : 0) + tl.hr0;
+  tl.n = min(T, kp.d.half - tl.hr0);
+  return tl;
+}
+
+// staged load of `nfloats` contiguous floats: TMA when the span is a multiple of 16 B, else cooperative.
+struct Stager {
+  uint64_t* bar;
+  uint32_t bytes;
+  bool use_tma;
+  __device__ __forceinline__ void load(float* dst, const float* src, int nfloats) {
+    if (use_tma) {
+      if (threadIdx.x == 0) {
+        tma_load_1d(dst, src, (uint32_t)nfloats * 4u, bar);
+        bytes += (uint32_t)nfloats * 4u;
+      }
+    } else {
+      for (int i = threadIdx.x; i < nfloats; i += blockDim.x) dst[i] = __ldg(src + i);
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// K_scan: per-tile reset counts + exclusive offsets (the reset rank = goal index of QPC:206 / math.py:184)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(T) k_reset_count(const KernelParams kp, const int64_t* __restrict__ reset_buf,
+                                                   int32_t* __restrict__ tile_counts, int32_t* __restrict__ tile_offsets,
+                                                   int32_t* __restrict__ num_reset, unsigned int* __restrict__ ticket) {
+  __shared__ int warp_counts[T / 32];
+  __shared__ int is_last;
+  __shared__ int scan_s[T];
+  const Tile tl = tile_of(kp, blockIdx.x);
+  const int r = threadIdx.x;
+  int flag = 0;
+  if (r < tl.n) flag = reset_buf[tl.e0 + r] != 0;
+  unsigned b = __ballot_sync(0xffffffffu, flag);
+  if ((r & 31) == 0) warp_counts[r >> 5] = __popc(b);
+  __syncthreads();
+  if (r == 0) {
+    int c = 0;
+#pragma unroll
+    for (int w = 0; w < T / 32; ++w) c += warp_counts[w];
+    tile_counts[blockIdx.x] = c;
+    __threadfence();
+    is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  // last CTA: exclusive scan over all tile counts, chunked per thread
+  const int nt = kp.d.num_tiles;
+  const int per = (nt + T - 1) / T;
+  int lo = r * per, hi = min(nt, lo + per), s = 0;
+  for (int i = lo; i < hi; ++i) s += __ldcg(tile_counts + i);
+  scan_s[r] = s;
+  __syncthreads();
+  if (r == 0) {
+    int acc = 0;
+    for (int i = 0; i < T; ++i) { int v = scan_s[i]; scan_s[i] = acc; acc += v; }
+    num_reset[0] = acc;
+    if (kp.p.kind == LM_KIND_LOCO) num_reset[1] = acc;
+    if (kp.p.kind == LM_KIND_MANI) num_reset[1] = 0;
+    *ticket = 0;
+  }
+  __syncthreads();
+  int acc = scan_s[r];
+  for (int i = lo; i < hi; ++i) {
+    if (kp.p.kind == LM_KIND_COTRAIN && i == kp.d.tiles_per_half) num_reset[1] = acc;   // resets in the locomotion half
+    tile_offsets[i] = acc;
+    acc += __ldcg(tile_counts + i);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K_pre: clamp + stash actions, action -> target, reset_idx scatter + goal resample
+// ------------------------------------------------------------------------------------------------
+struct PreArgs {
+  LmRobotViews loco, mani;
+  const float* env_pos;
+  LmTaskBuffers buf;
+  const float* actions;
+  const float* uniforms;
+  const int32_t* tile_offsets;
+  int parity;                      // actions_ring slot that receives current_actions
+};
+
+__device__ __forceinline__ void store3(float* p, float a, float b, float c) { p[0] = a; p[1] = b; p[2] = c; }
+
+// reset_idx for one env (QPC:230-299 / QMP:238-309 / JLV:272-377): defaults into the PhysX views,
+// goal resample from uniform row `rank`, history buffers cleared.
+__device__ __forceinline__ void reset_one_env(const KernelParams& kp, const PreArgs& a, const LmRobotViews& V, float* ring_last,
+                                              int is_mani, int e, int hr, int rank) {
+  const LmTaskParams& P = kp.p;
+  Tile tl; tl.is_mani = is_mani;
+
+    const float* u = a.uniforms + (size_t)rank * 3;
+    const Quat g = goal_from_uniforms(P, u[0], u[1], u[2]);
+    float* gq = a.buf.goal_quaternions + (size_t)e * 4;
+    gq[0] = g.w; gq[1] = g.x; gq[2] = g.y; gq[3] = g.z;
+    const float ox = a.env_pos[hr * 3 + 0], oy = a.env_pos[hr * 3 + 1], oz = a.env_pos[hr * 3 + 2];
+    float* jp = V.dof_pos + (size_t)hr * LM_NUM_DOF;
+    float* jv = V.dof_vel + (size_t)hr * LM_NUM_DOF;
+#pragma unroll
+    for (int j = 0; j < LM_NUM_DOF; ++j) { jp[j] = tl.is_mani ? P.mani_init_joint_pos[j] : P.loco_init_joint_pos[j]; jv[j] = 0.0f; }
+    if (!tl.is_mani) {
+      store3(V.root_pos + hr * 3, add(P.loco_default_position[0], ox), add(P.loco_default_position[1], oy),
+             add(P.loco_default_position[2], oz));                                  // robot.py:420
+      float* q = V.root_quat + hr * 4;
+      q[0] = P.loco_default_quaternion[0]; q[1] = P.loco_default_quaternion[1];
+      q[2] = P.loco_default_quaternion[2]; q[3] = P.loco_default_quaternion[3];
+      store3(V.root_lin_vel + hr * 3, 0.f, 0.f, 0.f);
+      store3(V.root_ang_vel + hr * 3, 0.f, 0.f, 0.f);
+      float* iq = V.indicator_quat + hr * 4;                                        // conj(goal), QPC:282
+      iq[0] = g.w; iq[1] = -g.x; iq[2] = -g.y; iq[3] = -g.z;
+      store3(V.indicator_pos + hr * 3, add(ox, P.indicator_loco_position[0]), add(oy, P.indicator_loco_position[1]),
+             add(oz, P.indicator_loco_position[2]));                                // rigid_object.py:45
+    } else {
+      store3(V.plate_pos + hr * 3, add(ox, P.obj_default_position[0]), add(oy, P.obj_default_position[1]),
+             add(oz, P.obj_default_position[2]));
+      float* q = V.plate_quat + hr * 4;
+      q[0] = P.mani_default_quaternion[0]; q[1] = P.mani_default_quaternion[1];
+      q[2] = P.mani_default_quaternion[2]; q[3] = P.mani_default_quaternion[3];
+      store3(V.plate_lin_vel + hr * 3, 0.f, 0.f, 0.f);
+      store3(V.plate_ang_vel + hr * 3, 0.f, 0.f, 0.f);
+      float Rg[9], M[9], R0[9];                                                     // rotate_orientations(q0, goal), QMP:291
+#pragma unroll
+      for (int i = 0; i < 9; ++i) R0[i] = kp.d.R0[i];
+      rot_from_quat_scipy(g, Rg);
+      mat3_mul<false>(R0, Rg, M);
+      const Quat iqv = quat_from_rot_scipy(M);
+      float* iq = V.indicator_quat + hr * 4;
+      iq[0] = iqv.w; iq[1] = iqv.x; iq[2] = iqv.y; iq[3] = iqv.z;
+      store3(V.indicator_pos + hr * 3, add(ox, P.indicator_mani_position[0]), add(oy, P.indicator_mani_position[1]),
+             add(oz, P.indicator_mani_position[2]));
+    }
+    float* ljv = a.buf.last_joint_vel + (size_t)e * LM_NUM_ACT;
+    float* la = ring_last + (size_t)e * LM_NUM_ACT;
+    float* lt = a.buf.last_base_tip + (size_t)e * 12;
+#pragma unroll
+    for (int j = 0; j < LM_NUM_ACT; ++j) { ljv[j] = 0.0f; la[j] = 0.0f; lt[j] = P.default_base_tip[j / 3][j % 3]; }
+    a.buf.reset_buf[e] = 0; a.buf.progress_buf[e] = 0; a.buf.successes[e] = 0;
+    a.buf.consecutive_successes[e] = 0; a.buf.goal_reset_buf[e] = 0;
+    a.buf.reset_env_ids[rank] = e;
+  }
+
+__global__ void __launch_bounds__(T) k_pre(const KernelParams kp, const PreArgs a) {
+  const LmTaskParams& P = kp.p;
+  const Tile tl = tile_of(kp, blockIdx.x);
+  const int r = threadIdx.x;
+  const int N = P.num_envs;
+  float* ring_cur = a.buf.actions_ring + (size_t)a.parity * N * LM_NUM_ACT;
+  float* ring_last = a.buf.actions_ring + (size_t)(a.parity ^ 1) * N * LM_NUM_ACT;
+  const LmRobotViews& V = tl.is_mani ? a.mani : a.loco;
+
+  // ---- reset mask + rank inside the tile
+  __shared__ int warp_base[T / 32];
+  int flag = 0;
+  const int e = tl.e0 + r, hr = tl.hr0 + r;
+  if (r < tl.n) flag = a.buf.reset_buf[e] != 0;
+  unsigned b = __ballot_sync(0xffffffffu, flag);
+  if ((r & 31) == 0) warp_base[r >> 5] = __popc(b);
+  __syncthreads();
+  int base = a.tile_offsets[blockIdx.x];
+  for (int w = 0; w < (r >> 5); ++w) base += warp_base[w];
+  const int rank = base + __popc(b & ((1u << (r & 31)) - 1u));
+
+  // ---- reset_idx for flagged envs
+  if (flag) reset_one_env(kp, a, V, ring_last, tl.is_mani, e, hr, rank);
+
+  // ---- actions: clamp (vec_env_rlgames.py:60), stash as current_actions, take_action (robot.py:444-461)
+  const int nflat = tl.n * LM_NUM_ACT;
+  const float* act_g = a.actions + (size_t)tl.e0 * LM_NUM_ACT;
+  float* cur_g = ring_cur + (size_t)tl.e0 * LM_NUM_ACT;
+  const float range = sub(P.action_limit, -P.action_limit);
+  const float offset = mul(add(-P.action_limit, P.action_limit), 0.5f);
+  const bool write_targets = (P.control_mode == LM_CONTROL_VELOCITY || P.control_mode == LM_CONTROL_POSITION) && V.targets;
+  float* tgt_g = write_targets ? V.targets + (size_t)tl.hr0 * LM_NUM_ACT : nullptr;
+  for (int i = r; i < nflat / 4; i += T) {
+    float4 v = ld_nc_f4(act_g + 4 * i);
+    if (P.clamp_actions) {
+      v.x = fminf(fmaxf(v.x, -P.clip_actions), P.clip_actions); v.y = fminf(fmaxf(v.y, -P.clip_actions), P.clip_actions);
+      v.z = fminf(fmaxf(v.z, -P.clip_actions), P.clip_actions); v.w = fminf(fmaxf(v.w, -P.clip_actions), P.clip_actions);
+    }
+    reinterpret_cast<float4*>(cur_g)[i] = v;
+    if (write_targets) {
+      if (P.zero_actions) v = make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 t;
+      t.x = add(mul(mul(v.x, range), 0.5f), offset); t.y = add(mul(mul(v.y, range), 0.5f), offset);
+      t.z = add(mul(mul(v.z, range), 0.5f), offset); t.w = add(mul(mul(v.w, range), 0.5f), offset);
+      reinterpret_cast<float4*>(tgt_g)[i] = t;
+    }
+  }
+  if (P.control_mode == LM_CONTROL_EFFORT && V.targets && r < tl.n) {                // robot.py:455-459
+    float* eff = V.targets + (size_t)hr * LM_NUM_DOF;
+    const float* av = a.actions + (size_t)e * LM_NUM_ACT;
+#pragma unroll
+    for (int j = 0; j < LM_NUM_DOF; ++j) eff[j] = 0.0f;
+#pragma unroll
+    for (int j = 0; j < LM_NUM_ACT; ++j) {
+      float v = av[j];
+      if (P.clamp_actions) v = fminf(fmaxf(v, -P.clip_actions), P.clip_actions);
+      if (P.zero_actions) v = 0.0f;
+      eff[P.dof_index[j]] = add(mul(mul(v, range), 0.5f), offset);
+    }
+  }
+}
+
+// direct reset_idx(env_ids) call (random_policy.py-style drivers): env k of the list consumes uniform row k
+__global__ void k_reset_idx(const KernelParams kp, const PreArgs a, const int64_t* __restrict__ env_ids, int count) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= count) return;
+  const int e = (int)env_ids[k];
+  if (e < 0 || e >= kp.p.num_envs) return;
+  const int second = (kp.p.kind == LM_KIND_COTRAIN) && e >= kp.d.half;
+  const int is_mani = (kp.p.kind == LM_KIND_MANI) || second;
+  const int hr = second ? e - kp.d.half : e;
+  float* ring_last = a.buf.actions_ring + (size_t)(a.parity ^ 1) * kp.p.num_envs * LM_NUM_ACT;
+  reset_one_env(kp, a, is_mani ? a.mani : a.loco, ring_last, is_mani, e, hr, k);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K_post
+// ------------------------------------------------------------------------------------------------
+struct PostArgs {
+  LmRobotViews loco, mani;
+  const float* env_pos;
+  LmTaskBuffers buf;
+  float* partials;                 // [num_tiles, STATS] fp32 + int32 mix (see below)
+  unsigned int* ticket;
+  int parity;
+  int clamp_observations;          // store clamp(obs, ±clip_observations) (fused _process_data)
+};
+
+// smem carve (floats)
+struct PostSmem {
+  static constexpr int kDofPos = 0;
+  static constexpr int kDofVel = kDofPos + T * 20;
+  static constexpr int kPos = kDofVel + T * 20;      // root_pos | plate_pos
+  static constexpr int kQuat = kPos + T * 3 + (T * 3) % 4;
+  static constexpr int kLin = kQuat + T * 4;
+  static constexpr int kAng = kLin + T * 3;
+  static constexpr int kTips = kAng + T * 3;
+  static constexpr int kKnees = kTips + T * 12;
+  static constexpr int kEnvPos = kKnees + T * 24;
+  static constexpr int kGoal = kEnvPos + T * 3;
+  static constexpr int kCur = kGoal + T * 4;
+  static constexpr int kLast = kCur + T * 12;
+  static constexpr int kLastJv = kLast + T * 12;
+  static constexpr int kLastTip = kLastJv + T * 12;
+  static constexpr int kCurQ = kLastTip + T * 12;
+  static constexpr int kObs = kCurQ + T * 4;
+  static constexpr int kEnd = kObs + T * OBS_PAD;
+  static constexpr int kBytes = kEnd * 4 + 64;
+};
+static_assert(T % 4 == 0, "tile spans must stay 16-byte aligned");
+
+// column c of the 93-wide states row -> (smem region, row stride, column, scale id)   QPC:406-423
+__device__ __forceinline__ float states_elem(const LmTaskParams& P, const float* sm, int r, int c) {
+  const float* obs = sm + PostSmem::kObs + r * OBS_PAD;
+  if (c < 3) return obs[c];                                   // scaled position
+  if (c < 6) return obs[10 + (c - 3)];                        // scaled linear velocity
+  if (c < 10) return mul(P.quaternion_obs_scale, sm[PostSmem::kCurQ + r * 4 + (c - 6)]);
+  if (c < 13) return obs[13 + (c - 10)];                      // scaled angular velocity
+  if (c < 37) return obs[16 + (c - 13)];                      // joint positions, velocities
+  if (c < 41) return mul(P.quaternion_obs_scale, sm[PostSmem::kGoal + r * 4 + (c - 37)]);
+  if (c < 45) return obs[6 + (c - 41)];                       // quat diff
+  if (c < 57) return mul(P.tip_position_scale, sm[PostSmem::kTips + r * 12 + (c - 45)]);      // tips now (base frame)
+  if (c < 69) return mul(P.tip_position_scale, sm[PostSmem::kLastTip + r * 12 + (c - 57)]);   // tips previous step
+  return obs[40 + (c - 69)];                                  // current, last actions
+}
+
+__global__ void __launch_bounds__(T, 2) k_post(const KernelParams kp, const PostArgs a) {
+  extern __shared__ __align__(128) float sm[];
+  __shared__ uint64_t bar;
+  __shared__ float red_f[T / 32][STATS];
+  __shared__ int is_last;
+  const LmTaskParams& P = kp.p;
+  const Tile tl = tile_of(kp, blockIdx.x);
+  const int r = threadIdx.x;
+  const int N = P.num_envs;
+  const LmRobotViews& V = tl.is_mani ? a.mani : a.loco;
+  const float* ring_cur = a.buf.actions_ring + (size_t)a.parity * N * LM_NUM_ACT;
+  const float* ring_last = a.buf.actions_ring + (size_t)(a.parity ^ 1) * N * LM_NUM_ACT;
+  const bool full_states = (P.num_states == LM_NUM_STATES_FULL) && a.buf.states_buf != nullptr;
+
+  // ---- stage the tile (TMA bulk loads, one mbarrier)
+  if (r == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+  __syncthreads();
+  Stager st{&bar, 0u, (tl.n % 4) == 0};
+  const int n = tl.n, h0 = tl.hr0, e0 = tl.e0;
+  st.load(sm + PostSmem::kDofPos, V.dof_pos + (size_t)h0 * 20, n * 20);
+  st.load(sm + PostSmem::kDofVel, V.dof_vel + (size_t)h0 * 20, n * 20);
+  st.load(sm + PostSmem::kPos, (tl.is_mani ? V.plate_pos : V.root_pos) + (size_t)h0 * 3, n * 3);
+  st.load(sm + PostSmem::kQuat, (tl.is_mani ? V.plate_quat : V.root_quat) + (size_t)h0 * 4, n * 4);
+  st.load(sm + PostSmem::kLin, (tl.is_mani ? V.plate_lin_vel : V.root_lin_vel) + (size_t)h0 * 3, n * 3);
+  st.load(sm + PostSmem::kAng, (tl.is_mani ? V.plate_ang_vel : V.root_ang_vel) + (size_t)h0 * 3, n * 3);
+  st.load(sm + PostSmem::kTips, V.tip_pos + (size_t)h0 * 12, n * 12);
+  st.load(sm + PostSmem::kKnees, V.knee_pos + (size_t)h0 * 24, n * 24);
+  st.load(sm + PostSmem::kEnvPos, a.env_pos + (size_t)h0 * 3, n * 3);
+  st.load(sm + PostSmem::kGoal, a.buf.goal_quaternions + (size_t)e0 * 4, n * 4);
+  st.load(sm + PostSmem::kCur, ring_cur + (size_t)e0 * 12, n * 12);
+  st.load(sm + PostSmem::kLast, ring_last + (size_t)e0 * 12, n * 12);
+  st.load(sm + PostSmem::kLastJv, a.buf.last_joint_vel + (size_t)e0 * 12, n * 12);
+  if (full_states) st.load(sm + PostSmem::kLastTip, a.buf.last_base_tip + (size_t)e0 * 12, n * 12);
+  if (st.use_tma) {
+    if (r == 0) mbar_expect_tx(&bar, st.bytes);
+  }
+  // int64 flags straight from global while the bulk copies fly
+  int64_t progress = 0, reset = 0, succ_prev = 0, consec = 0;
+  if (r < n) {
+    progress = a.buf.progress_buf[e0 + r];
+    reset = a.buf.reset_buf[e0 + r];
+    succ_prev = a.buf.successes[e0 + r];
+    consec = a.buf.consecutive_successes[e0 + r];
+  }
+  if (st.use_tma) mbar_wait(&bar, 0); else __syncthreads();
+
+  float stats[STATS];
+#pragma unroll
+  for (int i = 0; i < STATS; ++i) stats[i] = 0.0f;
+
+  if (r < n) {
+    // ---- joint state: gather 12 actuated DOFs, finite-difference acceleration (robot.py:288-291)
+    float jp[12], jv[12];
+    if (kp.d.dof_identity) {
+      const float4* p4 = reinterpret_cast<const float4*>(sm + PostSmem::kDofPos + r * 20);
+      const float4* v4 = reinterpret_cast<const float4*>(sm + PostSmem::kDofVel + r * 20);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        float4 x = p4[k], y = v4[k];
+        jp[4 * k] = x.x; jp[4 * k + 1] = x.y; jp[4 * k + 2] = x.z; jp[4 * k + 3] = x.w;
+        jv[4 * k] = y.x; jv[4 * k + 1] = y.y; jv[4 * k + 2] = y.z; jv[4 * k + 3] = y.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 12; ++j) {
+        jp[j] = sm[PostSmem::kDofPos + r * 20 + P.dof_index[j]];
+        jv[j] = sm[PostSmem::kDofVel + r * 20 + P.dof_index[j]];
+      }
+    }
+    float cur[12], last[12];
+    {
+      const float4* c4 = reinterpret_cast<const float4*>(sm + PostSmem::kCur + r * 12);
+      const float4* l4 = reinterpret_cast<const float4*>(sm + PostSmem::kLast + r * 12);
+      float4* j4 = reinterpret_cast<float4*>(sm + PostSmem::kLastJv + r * 12);
+      float acc_sum = 0.0f, rate_sum = 0.0f;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        float4 c = c4[k], l = l4[k], pv = j4[k];
+        cur[4 * k] = c.x; cur[4 * k + 1] = c.y; cur[4 * k + 2] = c.z; cur[4 * k + 3] = c.w;
+        last[4 * k] = l.x; last[4 * k + 1] = l.y; last[4 * k + 2] = l.z; last[4 * k + 3] = l.w;
+        const float prev[4] = {pv.x, pv.y, pv.z, pv.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int j = 4 * k + q;
+          const float acc = fdiv(sub(jv[j], prev[q]), P.time_interval);
+          acc_sum = add(acc_sum, mul(fabsf(acc), P.joint_acc_scale));                    // QPC:443
+          rate_sum = add(rate_sum, fabsf(sub(last[j], cur[j])));                        // QPC:446
+        }
+        j4[k] = make_float4(jv[4 * k], jv[4 * k + 1], jv[4 * k + 2], jv[4 * k + 3]);    // last_joint_vel <- jv (robot.py:291)
+      }
+      stats[2] = acc_sum;
+      stats[3] = mul(rate_sum, P.action_rate_scale);
+    }
+
+    // ---- frame quantities per kind
+    const Vec3 O{sm[PostSmem::kEnvPos + r * 3], sm[PostSmem::kEnvPos + r * 3 + 1], sm[PostSmem::kEnvPos + r * 3 + 2]};
+    const Vec3 Pw{sm[PostSmem::kPos + r * 3], sm[PostSmem::kPos + r * 3 + 1], sm[PostSmem::kPos + r * 3 + 2]};
+    const float4 qv = *reinterpret_cast<const float4*>(sm + PostSmem::kQuat + r * 4);
+    const Quat q{qv.x, qv.y, qv.z, qv.w};
+    const Vec3 lin{sm[PostSmem::kLin + r * 3], sm[PostSmem::kLin + r * 3 + 1], sm[PostSmem::kLin + r * 3 + 2]};
+    const Vec3 ang{sm[PostSmem::kAng + r * 3], sm[PostSmem::kAng + r * 3 + 1], sm[PostSmem::kAng + r * 3 + 2]};
+    const Vec3 pl{sub(Pw.x, O.x), sub(Pw.y, O.y), sub(Pw.z, O.z)};      // local pose (robot.py:295 / rigid_object.py:54)
+    float* tips = sm + PostSmem::kTips + r * 12;
+    const float* knees = sm + PostSmem::kKnees + r * 24;
+    Vec3 pos, lin_o, ang_o;
+    Quat cur_q;
+    float body_height;
+    int corner_low = 0, knee_low = 0;
+    float R[9];
+    rot_from_quat_scipy(q, R);
+    if (!tl.is_mani) {
+      pos = quat_rotate_t<true>(q, Vec3{-pl.x, -pl.y, -pl.z});                            // QPC:319
+      cur_q = quat_conj(q);                                                              // QPC:322
+      lin_o = quat_rotate_t<true>(q, Vec3{-lin.x, -lin.y, -lin.z});                      // QPC:326
+      ang_o = quat_rotate_t<true>(q, Vec3{-ang.x, -ang.y, -ang.z});                      // QPC:329
+      const Vec3 pinv = tf_inverse_translation(R, pl);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {                                                       // QPC:332-335
+        const Vec3 t = tf_inverse_apply(R, pinv, Vec3{sub(tips[3 * k], O.x), sub(tips[3 * k + 1], O.y), sub(tips[3 * k + 2], O.z)});
+        tips[3 * k] = t.x; tips[3 * k + 1] = t.y; tips[3 * k + 2] = t.z;
+        const float cz = add(row_dot(R + 6, 1, Vec3{P.corners[k][0], P.corners[k][1], P.corners[k][2]}), pl.z);   // QPC:574-579
+        corner_low |= cz < P.baseline_corner_height;
+      }
+      body_height = pl.z;                                                                 // QPC:569
+#pragma unroll
+      for (int k = 0; k < 8; ++k) knee_low |= sub(sub(knees[3 * k + 2], O.z), P.baseline_knee_height) <= 0.0f;   // QPC:585-587
+    } else {
+      const Vec3 p0inv{kp.d.p0inv[0], kp.d.p0inv[1], kp.d.p0inv[2]};
+      float R0[9];
+#pragma unroll
+      for (int i = 0; i < 9; ++i) R0[i] = kp.d.R0[i];
+      pos = tf_inverse_apply(R0, p0inv, pl);                                              // QMP:326-329
+      float M[9];
+      mat3_mul<true>(R0, R, M);                                                      // QMP:332 (math.py:70-74)
+      cur_q = quat_from_rot_scipy(M);
+      const Quat q0{P.mani_default_quaternion[0], P.mani_default_quaternion[1], P.mani_default_quaternion[2], P.mani_default_quaternion[3]};
+      lin_o = quat_rotate_t<true>(q0, lin);                                               // QMP:338
+      ang_o = quat_rotate_t<true>(q0, ang);
+      const Vec3 pinv = tf_inverse_translation(R, pl);                                    // plate frame (QMP:576-603)
+      body_height = tf_inverse_apply_z(R, pinv.z, Vec3{P.mani_default_position[0], P.mani_default_position[1], P.mani_default_position[2]});
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const Vec3 t = tf_inverse_apply(R0, p0inv, Vec3{sub(tips[3 * k], O.x), sub(tips[3 * k + 1], O.y), sub(tips[3 * k + 2], O.z)});   // QMP:343
+        tips[3 * k] = t.x; tips[3 * k + 1] = t.y; tips[3 * k + 2] = t.z;
+        const float cz = tf_inverse_apply_z(R, pinv.z, Vec3{kp.d.corners_world[k][0], kp.d.corners_world[k][1], kp.d.corners_world[k][2]});
+        corner_low |= cz < P.baseline_corner_height;
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float kz = tf_inverse_apply_z(R, pinv.z, Vec3{sub(knees[3 * k], O.x), sub(knees[3 * k + 1], O.y), sub(knees[3 * k + 2], O.z)});
+        knee_low |= sub(kz, P.baseline_knee_height) <= 0.0f;
+      }
+    }
+
+    // ---- orientation error (QPC:345-350,430-432)
+    const float4 gv = *reinterpret_cast<const float4*>(sm + PostSmem::kGoal + r * 4);
+    const Quat goal{gv.x, gv.y, gv.z, gv.w};
+    Quat diff = quat_mul(cur_q, quat_conj(goal));
+    const float nrm = norm3_torch(diff.x, diff.y, diff.z);
+    const float rot_dist = mul(2.0f, (float)asin((double)fminf(nrm, 1.0f)));
+    if (diff.w < 0.0f) { diff.w = -diff.w; diff.x = -diff.x; diff.y = -diff.y; diff.z = -diff.z; }
+    const Vec3 up = quat_rotate_t<false>(cur_q, Vec3{0.0f, 0.0f, 1.0f});                  // quat_axis(q, 2)
+
+    // ---- observation row (QPC:358-371)
+    float o[64];
+    o[0] = mul(P.position_scale, pos.x); o[1] = mul(P.position_scale, pos.y); o[2] = mul(P.position_scale, pos.z);
+    o[3] = up.x; o[4] = up.y; o[5] = up.z;
+    o[6] = diff.w; o[7] = diff.x; o[8] = diff.y; o[9] = diff.z;
+    o[10] = mul(P.linear_vel_scale, lin_o.x); o[11] = mul(P.linear_vel_scale, lin_o.y); o[12] = mul(P.linear_vel_scale, lin_o.z);
+    o[13] = mul(P.angular_vel_scale, ang_o.x); o[14] = mul(P.angular_vel_scale, ang_o.y); o[15] = mul(P.angular_vel_scale, ang_o.z);
+#pragma unroll
+    for (int j = 0; j < 12; ++j) {
+      o[16 + j] = mul(P.joint_position_scale, jp[j]);
+      o[28 + j] = mul(P.joint_velocity_scale, jv[j]);
+      o[40 + j] = cur[j];
+      o[52 + j] = last[j];
+    }
+    if (a.clamp_observations) {
+#pragma unroll
+      for (int j = 0; j < 64; ++j) o[j] = fminf(fmaxf(o[j], -P.clip_observations), P.clip_observations);
+    }
+    float4* orow = reinterpret_cast<float4*>(sm + PostSmem::kObs + r * OBS_PAD);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) orow[k] = make_float4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
+    if (full_states) {
+      float* cq = sm + PostSmem::kCurQ + r * 4;
+      cq[0] = cur_q.w; cq[1] = cur_q.x; cq[2] = cur_q.y; cq[3] = cur_q.z;
+    }
+
+    // ---- reward (QPC:432-457,506-515)
+    const float rot_rew = mul(fdiv(1.0f, add(fabsf(rot_dist), P.rot_eps)), P.quaternion_scale);
+    const float trans = mul(norm2_torch(pos.x, pos.y), P.translation_scale);
+    const int goal_reset = consec > (int64_t)P.max_consecutive_successes;                 // counter BEFORE update (QPC:449)
+    const float bonus = mul(P.consecutive_success_reward, (float)goal_reset);
+    const int success = fabsf(rot_dist) <= P.success_thresh;
+    int brk = 0, rst = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {                                                         // QPC:466-504 / JLV:574-597
+      const float d = fabsf(sub(jp[5 + 2 * k], jp[4 + 2 * k]));
+      brk |= (d < P.min_joint_23_diff) | (d > P.max_joint_23_diff);
+      rst |= (d < P.reset_min_joint_23_diff) | (d > P.reset_max_joint_23_diff);
+      const bool mirrored = P.joint1_mirrored && (k == 1 || k == 2);
+      const float lo = mirrored ? -P.max_joint_1_pos : P.min_joint_1_pos, hi = mirrored ? -P.min_joint_1_pos : P.max_joint_1_pos;
+      const float rlo = mirrored ? -P.reset_max_joint_1_pos : P.reset_min_joint_1_pos;
+      const float rhi = mirrored ? -P.reset_min_joint_1_pos : P.reset_max_joint_1_pos;
+      brk |= (jp[k] < lo) | (jp[k] > hi);
+      rst |= (jp[k] < rlo) | (jp[k] > rhi);
+    }
+    const float limit_pen = mul(P.joint_limit_penalty, (float)brk);
+    float total = add(add(add(add(add(rot_rew, trans), stats[2]), stats[3]), bonus), limit_pen);
+
+    // ---- consecutive-success state machine (QPC:534-545)
+    const int both = success && (succ_prev != 0);
+    if (!both) consec = 0;
+    if (both) consec += 1;
+    if (succ_prev == 0 && success) consec = 1;
+
+    // ---- termination (QPC:562-616)
+    int rs = reset != 0;
+    rs |= pos.z > 0.0f;
+    rs |= body_height <= P.baseline_height;
+    rs |= corner_low | knee_low | rst;
+    const float fall = mul(P.fall_penalty, (float)rs);
+    total = add(total, fall);
+    rs |= goal_reset;
+    progress += 1;                                                                        // rl_task.py:251
+    rs |= progress >= (int64_t)(P.max_episode_length - 1);
+
+    const int e = e0 + r;
+    a.buf.rew_buf[e] = total;
+    a.buf.progress_buf[e] = progress;
+    a.buf.reset_buf[e] = rs;
+    a.buf.successes[e] = success;
+    a.buf.consecutive_successes[e] = consec;
+    a.buf.goal_reset_buf[e] = goal_reset;
+
+    stats[0] = rot_rew; stats[1] = trans; stats[4] = bonus; stats[5] = limit_pen; stats[6] = fall;
+    stats[7] = isnan(total) ? 1.0f : 0.0f;
+    stats[8] = total < -50.0f ? 1.0f : 0.0f;
+    stats[9] = (float)goal_reset;
+    stats[10] = (float)rs;
+  }
+
+  // ---- per-CTA partial sums for extras (QPC:560,610,630-631)
+#pragma unroll
+  for (int i = 0; i < STATS; ++i) {
+    float v = stats[i];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    if ((r & 31) == 0) red_f[r >> 5][i] = v;
+  }
+  fence_proxy_async();
+  __syncthreads();
+  if (r < STATS) {
+    float v = 0.0f;
+#pragma unroll
+    for (int w = 0; w < T / 32; ++w) v += red_f[w][r];
+    a.partials[(size_t)blockIdx.x * STATS + r] = v;
+  }
+
+  // ---- write back: obs rows (coalesced 128-bit), states gather, last_joint_vel / last_base_tip (TMA bulk store)
+  {
+    float* obs_g = a.buf.obs_buf + (size_t)e0 * LM_NUM_OBS;
+    for (int i = r; i < n * 16; i += T) {
+      const int row = i >> 4, c4 = i & 15;
+      reinterpret_cast<float4*>(obs_g)[i] = *reinterpret_cast<const float4*>(sm + PostSmem::kObs + row * OBS_PAD + c4 * 4);
+    }
+    if (full_states) {
+      float* st_g = a.buf.states_buf + (size_t)e0 * LM_NUM_STATES_FULL;
+      const int total_el = n * LM_NUM_STATES_FULL;
+      for (int i = r; i < total_el; i += T) {
+        const int row = i / LM_NUM_STATES_FULL, c = i - row * LM_NUM_STATES_FULL;
+        float v = states_elem(P, sm, row, c);
+        if (a.clamp_observations) v = fminf(fmaxf(v, -P.clip_observations), P.clip_observations);
+        st_g[i] = v;
+      }
+    }
+    if (st.use_tma) {
+      if (r == 0) {
+        tma_store_1d(a.buf.last_joint_vel + (size_t)e0 * 12, sm + PostSmem::kLastJv, (uint32_t)n * 48u);
+        tma_store_1d(a.buf.last_base_tip + (size_t)e0 * 12, sm + PostSmem::kTips, (uint32_t)n * 48u);
+        tma_store_commit();
+      }
+    } else {
+      for (int i = r; i < n * 12; i += T) {
+        a.buf.last_joint_vel[(size_t)e0 * 12 + i] = sm[PostSmem::kLastJv + i];
+        a.buf.last_base_tip[(size_t)e0 * 12 + i] = sm[PostSmem::kTips + i];
+      }
+    }
+  }
+
+  // ---- last CTA: extras means + success-rate bookkeeping (QPC:560,619-633 / JLV:758-802)
+  __threadfence();
+  if (r == 0) is_last = atomicAdd(a.ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    __shared__ double part[2][T / STATS][STATS];   // [loco|mani][thread group][stat]
+    __shared__ double tot[3][STATS];                // [all, loco, mani]
+    {
+      const int i = r % STATS, g = r / STATS;
+      double s_l = 0.0, s_m = 0.0;
+      const int tph = kp.d.tiles_per_half;
+      for (int t = g; t < kp.d.num_tiles; t += T / STATS) {
+        const double v = (double)__ldcg(a.partials + (size_t)t * STATS + i);
+        const bool second = (P.kind == LM_KIND_COTRAIN) && t >= tph;
+        if (second) s_m += v; else s_l += v;
+      }
+      part[0][g][i] = s_l; part[1][g][i] = s_m;
+    }
+    __syncthreads();
+    if (r < STATS) {
+      double s_l = 0.0, s_m = 0.0;
+      for (int g = 0; g < T / STATS; ++g) { s_l += part[0][g][r]; s_m += part[1][g][r]; }
+      tot[0][r] = s_l + s_m; tot[1][r] = s_l; tot[2][r] = s_m;
+    }
+    __syncthreads();
+    if (r == 0) {
+      float* ex = a.buf.extras;
+      const double inv_n = 1.0 / (double)N;
+      for (int i = 0; i < 7; ++i) ex[i] = (float)(tot[0][i] * inv_n);
+      ex[LM_EXTRA_NAN_COUNT] = (float)tot[0][7];
+      ex[LM_EXTRA_BELOW_M50_COUNT] = (float)tot[0][8];
+      int64_t* c = a.buf.counters;
+      const int groups = (P.kind == LM_KIND_COTRAIN) ? 3 : 1;
+      for (int g = 0; g < groups; ++g) {
+        int64_t& ns = c[2 * g];
+        int64_t& nr = c[2 * g + 1];
+        if (nr > (int64_t)P.max_reset_counts) {
+          ex[LM_EXTRA_SUCCESS_RATE + g] = (float)ns / (float)nr;
+          ns = 0; nr = 0;
+        }
+      }
+      for (int g = 0; g < groups; ++g) {
+        c[2 * g] += (int64_t)llrint(tot[g][9]);
+        c[2 * g + 1] += (int64_t)llrint(tot[g][10]);
+      }
+      *a.ticket = 0;
+    }
+  }
+  if (st.use_tma && r == 0) tma_store_wait_all();
+}
+
+// clamp + copy (_process_data, envs/vec_env_rlgames.py:41-46)
+__global__ void k_clamp_copy(const float* __restrict__ in, float* __restrict__ out, int64_t count, float clip) {
+  const int64_t n4 = count >> 2;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 v = reinterpret_cast<const float4*>(in)[i];
+    v.x = fminf(fmaxf(v.x, -clip), clip); v.y = fminf(fmaxf(v.y, -clip), clip);
+    v.z = fminf(fmaxf(v.z, -clip), clip); v.w = fminf(fmaxf(v.w, -clip), clip);
+    reinterpret_cast<float4*>(out)[i] = v;
+  }
+  for (int64_t i = (n4 << 2) + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = fminf(fmaxf(in[i], -clip), clip);
+}
+
+}  // namespace lm
+
+// =================================================================================================
+// host side
+// =================================================================================================
+using namespace lm;
+
+struct LmTask {
+  KernelParams kp;
+  int device;
+  int parity;
+  int sm_count;
+  int32_t* tile_counts;
+  int32_t* tile_offsets;
+  float* partials;
+  unsigned int* tickets;     // [2]: scan, post
+  int clamp_observations;
+};
+
+static void host_rot_from_quat(const float q[4], float m[9]) {   // same formulas as lm::rot_from_quat_scipy
+  double w = q[0], x = q[1], y = q[2], z = q[3];
+  double n = sqrt(x * x + y * y + z * z + w * w);
+  x /= n; y /= n; z /= n; w /= n;
+  double x2 = x * x, y2 = y * y, z2 = z * z, w2 = w * w, xy = x * y, zw = z * w, xz = x * z, yw = y * w, yz = y * z, xw = x * w;
+  m[0] = (float)(x2 - y2 - z2 + w2); m[1] = (float)(2.0 * (xy - zw)); m[2] = (float)(2.0 * (xz + yw));
+  m[3] = (float)(2.0 * (xy + zw)); m[4] = (float)(-x2 + y2 - z2 + w2); m[5] = (float)(2.0 * (yz - xw));
+  m[6] = (float)(2.0 * (xz - yw)); m[7] = (float)(2.0 * (yz + xw)); m[8] = (float)(-x2 - y2 + z2 + w2);
+}
+// volatile keeps the host compiler from contracting a*b+c into an FMA: the fp32 values must equal torch.bmm's
+static float seq_dot3(float a0, float b0, float a1, float b1, float a2, float b2) {
+  volatile float p0 = a0 * b0, p1 = a1 * b1, p2 = a2 * b2;
+  volatile float s = p0 + p1;
+  volatile float s2 = s + p2;
+  return s2;
+}
+
+extern "C" {
+
+int lm_abi_version(void) { return LM_ABI_VERSION; }
+const char* lm_last_error(void) { return lm_error_buffer(); }
+
+int lm_struct_size(int which) {
+  switch (which) {
+    case 0: return (int)sizeof(LmTaskParams);
+    case 1: return (int)sizeof(LmRobotViews);
+    case 2: return (int)sizeof(LmTaskBuffers);
+    case 3: return (int)sizeof(LmHostStep);
+    default: return -1;
+  }
+}
+
+int lm_device_sm_count(int device) {
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return -1;
+  return prop.multiProcessorCount;
+}
+
+LmTask* lm_task_create(const LmTaskParams* params, int device) {
+  if (!params) { lm_set_error("lm_task_create: params is NULL"); return nullptr; }
+  const LmTaskParams& p = *params;
+  if (p.num_envs <= 0 || p.kind < 0 || p.kind > 2) { lm_set_error("lm_task_create: bad num_envs/kind"); return nullptr; }
+  if (p.kind == LM_KIND_COTRAIN && (p.num_envs % 2)) { lm_set_error("Number of envs must be a multiplier of 2."); return nullptr; }
+  if (p.num_states != LM_NUM_OBS && p.num_states != LM_NUM_STATES_FULL) { lm_set_error("num_states must be 64 or 93"); return nullptr; }
+  cudaDeviceProp prop;
+  cudaError_t err = cudaGetDeviceProperties(&prop, device);
+  if (err != cudaSuccess) { lm_set_error("lm_task_create: no CUDA device (%s)", cudaGetErrorString(err)); return nullptr; }
+  if (prop.major != 10) { lm_set_error("lm_task_create: device %d is sm_%d%d; this library is sm_100a only", device, prop.major, prop.minor); return nullptr; }
+  if ((err = cudaSetDevice(device)) != cudaSuccess) { lm_set_error("cudaSetDevice: %s", cudaGetErrorString(err)); return nullptr; }
+  LmTask* t = new LmTask();
+  memset(t, 0, sizeof(*t));
+  t->kp.p = p;
+  t->device = device;
+  t->sm_count = prop.multiProcessorCount;
+  Derived& d = t->kp.d;
+  d.half = (p.kind == LM_KIND_COTRAIN) ? p.num_envs / 2 : p.num_envs;
+  d.tiles_per_half = (d.half + T - 1) / T;
+  d.num_tiles = d.tiles_per_half * ((p.kind == LM_KIND_COTRAIN) ? 2 : 1);
+  d.dof_identity = 1;
+  for (int j = 0; j < LM_NUM_ACT; ++j) {
+    if (p.dof_index[j] < 0 || p.dof_index[j] >= LM_NUM_DOF) { lm_set_error("dof_index[%d] out of range", j); delete t; return nullptr; }
+    d.dof_identity &= (p.dof_index[j] == j);
+  }
+  host_rot_from_quat(p.mani_default_quaternion, d.R0);
+  const float* p0 = p.mani_default_position;
+  for (int i = 0; i < 3; ++i)   // bmm(R0^T, -p0)
+    d.p0inv[i] = seq_dot3(d.R0[0 + i], -p0[0], d.R0[3 + i], -p0[1], d.R0[6 + i], -p0[2]);
+  for (int k = 0; k < 4; ++k)
+    for (int i = 0; i < 3; ++i) {
+      volatile float s = seq_dot3(d.R0[3 * i], p.corners[k][0], d.R0[3 * i + 1], p.corners[k][1], d.R0[3 * i + 2], p.corners[k][2]);
+      volatile float v = s + p0[i];
+      d.corners_world[k][i] = v;
+    }
+  bool ok = cudaMalloc(&t->tile_counts, sizeof(int32_t) * d.num_tiles) == cudaSuccess &&
+            cudaMalloc(&t->tile_offsets, sizeof(int32_t) * d.num_tiles) == cudaSuccess &&
+            cudaMalloc(&t->partials, sizeof(float) * STATS * d.num_tiles) == cudaSuccess &&
+            cudaMalloc(&t->tickets, sizeof(unsigned int) * 2) == cudaSuccess;
+  if (!ok) { lm_set_error("lm_task_create: cudaMalloc failed"); lm_task_destroy(t); return nullptr; }
+  cudaMemset(t->tickets, 0, sizeof(unsigned int) * 2);
+  err = cudaFuncSetAttribute(k_post, cudaFuncAttributeMaxDynamicSharedMemorySize, PostSmem::kBytes);
+  if (err != cudaSuccess) { lm_set_error("cudaFuncSetAttribute(k_post): %s", cudaGetErrorString(err)); lm_task_destroy(t); return nullptr; }
+  return t;
+}
+
+void lm_task_destroy(LmTask* t) {
+  if (!t) return;
+  cudaFree(t->tile_counts); cudaFree(t->tile_offsets); cudaFree(t->partials); cudaFree(t->tickets);
+  delete t;
+}
+
+int lm_task_step_parity(const LmTask* t) { return t ? t->parity : -1; }
+
+int lm_task_set_clamp_observations(LmTask* t, int on) { if (!t) return LM_ERR_BAD_ARG; t->clamp_observations = on; return LM_OK; }
+
+static int check_views(const LmTask* t, const LmRobotViews* loco, const LmRobotViews* mani, const float* env_pos,
+                       const LmTaskBuffers* buf) {
+  const int kind = t->kp.p.kind;
+  if (!buf || !env_pos) return lm_fail(LM_ERR_BAD_ARG, "buffers/env_pos NULL");
+  if ((kind != LM_KIND_MANI) && !loco) return lm_fail(LM_ERR_BAD_ARG, "locomotion views required");
+  if ((kind != LM_KIND_LOCO) && !mani) return lm_fail(LM_ERR_BAD_ARG, "manipulation views required");
+#define LM_CHK(ptr)                                                                                   \
+  do {                                                                                                \
+    if (!(ptr)) return lm_fail(LM_ERR_BAD_ARG, #ptr " is NULL");                                      \
+    if (((uintptr_t)(ptr)) & 15) return lm_fail(LM_ERR_ALIGNMENT, #ptr " is not 16-byte aligned");    \
+  } while (0)
+  LM_CHK(env_pos);
+  LM_CHK(buf->obs_buf); LM_CHK(buf->rew_buf); LM_CHK(buf->reset_buf); LM_CHK(buf->progress_buf); LM_CHK(buf->successes);
+  LM_CHK(buf->consecutive_successes); LM_CHK(buf->goal_reset_buf); LM_CHK(buf->actions_ring); LM_CHK(buf->last_joint_vel);
+  LM_CHK(buf->last_base_tip); LM_CHK(buf->goal_quaternions); LM_CHK(buf->reset_env_ids); LM_CHK(buf->num_reset);
+  LM_CHK(buf->extras); LM_CHK(buf->counters);
+  if (t->kp.p.num_states == LM_NUM_STATES_FULL) LM_CHK(buf->states_buf);
+  if (loco && kind != LM_KIND_MANI) {
+    LM_CHK(loco->dof_pos); LM_CHK(loco->dof_vel); LM_CHK(loco->root_pos); LM_CHK(loco->root_quat); LM_CHK(loco->root_lin_vel);
+    LM_CHK(loco->root_ang_vel); LM_CHK(loco->tip_pos); LM_CHK(loco->knee_pos); LM_CHK(loco->indicator_pos); LM_CHK(loco->indicator_quat);
+  }
+  if (mani && kind != LM_KIND_LOCO) {
+    LM_CHK(mani->dof_pos); LM_CHK(mani->dof_vel); LM_CHK(mani->tip_pos); LM_CHK(mani->knee_pos); LM_CHK(mani->plate_pos);
+    LM_CHK(mani->plate_quat); LM_CHK(mani->plate_lin_vel); LM_CHK(mani->plate_ang_vel); LM_CHK(mani->indicator_pos); LM_CHK(mani->indicator_quat);
+  }
+#undef LM_CHK
+  return LM_OK;
+}
+
+int lm_task_pre_step(LmTask* t, const LmRobotViews* loco, const LmRobotViews* mani, const float* env_pos,
+                     const LmTaskBuffers* buf, const float* actions, const float* uniforms, void* stream) {
+  if (!t || !actions || !uniforms) return lm_fail(LM_ERR_BAD_ARG, "lm_task_pre_step: NULL argument");
+  if (((uintptr_t)actions) & 15) return lm_fail(LM_ERR_ALIGNMENT, "actions is not 16-byte aligned");
+  int rc = check_views(t, loco, mani, env_pos, buf);
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  const Derived& d = t->kp.d;
+  t->parity ^= 1;
+  k_reset_count<<<d.num_tiles, T, 0, s>>>(t->kp, buf->reset_buf, t->tile_counts, t->tile_offsets, buf->num_reset, t->tickets + 0);
+  PreArgs a;
+  memset(&a, 0, sizeof(a));
+  if (loco) a.loco = *loco;
+  if (mani) a.mani = *mani;
+  a.env_pos = env_pos; a.buf = *buf; a.actions = actions; a.uniforms = uniforms;
+  a.tile_offsets = t->tile_offsets; a.parity = t->parity;
+  k_pre<<<d.num_tiles, T, 0, s>>>(t->kp, a);
+  return lm_check_launch("lm_task_pre_step");
+}
+
+int lm_task_reset_idx(LmTask* t, const LmRobotViews* loco, const LmRobotViews* mani, const float* env_pos,
+                      const LmTaskBuffers* buf, const int64_t* env_ids, int32_t count, const float* uniforms, void* stream) {
+  if (!t || !env_ids || !uniforms || count < 0) return lm_fail(LM_ERR_BAD_ARG, "lm_task_reset_idx: bad argument");
+  int rc = check_views(t, loco, mani, env_pos, buf);
+  if (rc) return rc;
+  if (count == 0) return LM_OK;
+  PreArgs a;
+  memset(&a, 0, sizeof(a));
+  if (loco) a.loco = *loco;
+  if (mani) a.mani = *mani;
+  a.env_pos = env_pos; a.buf = *buf; a.uniforms = uniforms; a.parity = t->parity ^ 1;   // "last" slot = current one before the next pre_step
+  k_reset_idx<<<(count + 127) / 128, 128, 0, (cudaStream_t)stream>>>(t->kp, a, env_ids, count);
+  return lm_check_launch("lm_task_reset_idx");
+}
+
+int lm_task_post_step(LmTask* t, const LmRobotViews* loco, const LmRobotViews* mani, const float* env_pos,
+                      const LmTaskBuffers* buf, void* stream) {
+  if (!t) return lm_fail(LM_ERR_BAD_ARG, "lm_task_post_step: task is NULL");
+  int rc = check_views(t, loco, mani, env_pos, buf);
+  if (rc) return rc;
+  PostArgs a;
+  memset(&a, 0, sizeof(a));
+  if (loco) a.loco = *loco;
+  if (mani) a.mani = *mani;
+  a.env_pos = env_pos; a.buf = *buf; a.partials = t->partials; a.ticket = t->tickets + 1;
+  a.parity = t->parity; a.clamp_observations = t->clamp_observations;
+  k_post<<<t->kp.d.num_tiles, T, PostSmem::kBytes, (cudaStream_t)stream>>>(t->kp, a);
+  return lm_check_launch("lm_task_post_step");
+}
+
+int lm_clamp_copy(const float* in, float* out, int64_t count, float clip, void* stream) {
+  if (!in || !out || count < 0) return lm_fail(LM_ERR_BAD_ARG, "lm_clamp_copy: bad argument");
+  if ((((uintptr_t)in) | ((uintptr_t)out)) & 15) return lm_fail(LM_ERR_ALIGNMENT, "lm_clamp_copy: unaligned");
+  if (count == 0) return LM_OK;
+  int blocks = (int)((count / 4 + 255) / 256);
+  if (blocks < 1) blocks = 1;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  k_clamp_copy<<<blocks, 256, 0, (cudaStream_t)stream>>>(in, out, count, clip);
+  return lm_check_launch("lm_clamp_copy");
+}
+
+int lm_task_step_host(LmTask* t, const LmRobotViews* loco, const LmRobotViews* mani, const float* env_pos,
+                      const LmTaskBuffers* buf, const LmHostStep* io, void* stream) {
+  if (!t || !io) return lm_fail(LM_ERR_BAD_ARG, "lm_task_step_host: NULL argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int N = t->kp.p.num_envs;
+  cudaError_t e;
+  // pre_physics_step on the previous state, then the "physics" arrives from the host, then post_physics_step
+  if ((e = cudaMemcpyAsync(io->actions_dev, io->actions_host, sizeof(float) * N * LM_NUM_ACT, cudaMemcpyHostToDevice, s)) != cudaSuccess) goto fail;
+  if ((e = cudaMemcpyAsync(io->uniforms_dev, io->uniforms_host, sizeof(float) * N * 3, cudaMemcpyHostToDevice, s)) != cudaSuccess) goto fail;
+  {
+    int rc = lm_task_pre_step(t, loco, mani, env_pos, buf, io->actions_dev, io->uniforms_dev, stream);
+    if (rc) return rc;
+  }
+  if (io->loco_state_host && io->loco_state_floats > 0)
+    if ((e = cudaMemcpyAsync(io->loco_state_dev, io->loco_state_host, sizeof(float) * io->loco_state_floats, cudaMemcpyHostToDevice, s)) != cudaSuccess) goto fail;
+  if (io->mani_state_host && io->mani_state_floats > 0)
+    if ((e = cudaMemcpyAsync(io->mani_state_dev, io->mani_state_host, sizeof(float) * io->mani_state_floats, cudaMemcpyHostToDevice, s)) != cudaSuccess) goto fail;
+  {
+    int rc = lm_task_post_step(t, loco, mani, env_pos, buf, stream);
+    if (rc) return rc;
+  }
+  if (io->obs_host && (e = cudaMemcpyAsync(io->obs_host, buf->obs_buf, sizeof(float) * (size_t)N * LM_NUM_OBS, cudaMemcpyDeviceToHost, s)) != cudaSuccess) goto fail;
+  if (io->rew_host && (e = cudaMemcpyAsync(io->rew_host, buf->rew_buf, sizeof(float) * N, cudaMemcpyDeviceToHost, s)) != cudaSuccess) goto fail;
+  if (io->reset_host && (e = cudaMemcpyAsync(io->reset_host, buf->reset_buf, sizeof(int64_t) * N, cudaMemcpyDeviceToHost, s)) != cudaSuccess) goto fail;
+  if ((e = cudaStreamSynchronize(s)) != cudaSuccess) goto fail;
+  return LM_OK;
+fail:
+  return lm_fail((int)e, "lm_task_step_host: %s", cudaGetErrorString(e));
+}
+
+}  // extern "C"

@@ -1,0 +1,108 @@
+"""GNN limb-graph actor-critic with the forward pass on the fused fp32 kernel (csrc/lm_gnn.cu).
+
+Module / parameter names follow the reference (scripts/graph_model_orebot_ov.py:82-241 and the ``Shared``
+wrapper at scripts/skrl_ppo_locomanipulation.py:44-49) so its checkpoints load unchanged.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from .. import _lib
+
+HIDDEN = 32
+
+
+class _GraphLayer(nn.Module):
+    def __init__(self, in_features, hidden_features, out_features):
+        super().__init__()
+        self.linear1 = nn.Linear(in_features * 2, hidden_features)
+        self.linear2 = nn.Linear(hidden_features, out_features)
+
+
+class _GraphNet(nn.Module):
+    def __init__(self, hidden_features=HIDDEN, out_features=HIDDEN):
+        super().__init__()
+        self.input_layer1 = nn.Linear(16, hidden_features)
+        self.input_layer2 = nn.Linear(4, hidden_features)
+        self.graph_layer1 = _GraphLayer(hidden_features, hidden_features, hidden_features)
+        self.graph_layer2 = _GraphLayer(hidden_features, hidden_features, hidden_features)
+        self.graph_layer3 = _GraphLayer(hidden_features, hidden_features, out_features)
+
+
+class _Head(nn.Module):
+    def __init__(self, hidden_features):
+        super().__init__()
+        self.action_layer = nn.Linear(hidden_features, 1)
+
+
+class GnnActorCritic(nn.Module):
+    def __init__(self, num_actions: int = 12, device="cuda:0"):
+        super().__init__()
+        self.net = _GraphNet()
+        self.mean_layer = _Head(HIDDEN)
+        self.log_std_parameter = nn.Parameter(torch.zeros(num_actions))
+        self.value_layer = _Head(HIDDEN)
+        self.to(device)
+        self._device = torch.device(device)
+        self._lib = None
+        self._handle = None
+        self._packed_version = None
+
+    def _ensure(self):
+        if self._handle is None:
+            if self._device.type != "cuda" or not torch.cuda.is_available():
+                raise _lib.LmError("GnnActorCritic.forward needs a CUDA device (no CPU fallback)")
+            self._lib = _lib.load()
+            idx = self._device.index if self._device.index is not None else torch.cuda.current_device()
+            self._handle = self._lib.lm_gnn_create(idx)
+            if not self._handle:
+                raise _lib.LmError(f"lm_gnn_create failed: {self._lib.lm_last_error().decode()}")
+
+    def ordered_parameters(self):
+        n = self.net
+        ps = [n.input_layer1.weight, n.input_layer1.bias, n.input_layer2.weight, n.input_layer2.bias]
+        for g in (n.graph_layer1, n.graph_layer2, n.graph_layer3):
+            ps += [g.linear1.weight, g.linear1.bias, g.linear2.weight, g.linear2.bias]
+        ps += [self.mean_layer.action_layer.weight, self.mean_layer.action_layer.bias,
+               self.value_layer.action_layer.weight, self.value_layer.action_layer.bias]
+        return ps
+
+    def _param_version(self):
+        return tuple(p._version for p in self.parameters()) + tuple(p.data_ptr() for p in self.parameters())
+
+    def pack(self) -> None:
+        self._ensure()
+        ts = [p.detach().float().contiguous() for p in self.ordered_parameters()]
+        arr = (C.c_void_p * len(ts))(*[t.data_ptr() for t in ts])
+        stream = torch.cuda.current_stream(self._device).cuda_stream
+        _lib.check(self._lib.lm_gnn_pack(self._handle, arr, len(ts), stream), "lm_gnn_pack")
+        self._keep = ts
+        self._packed_version = self._param_version()
+
+    @torch.no_grad()
+    def forward(self, obs: torch.Tensor, out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None):
+        self._ensure()
+        if self._packed_version != self._param_version():
+            self.pack()
+        obs = obs.to(self._device, dtype=torch.float32).contiguous()
+        n = obs.shape[0]
+        if out is None:
+            mu = torch.empty((n, 12), device=self._device, dtype=torch.float32)
+            value = torch.empty((n, 1), device=self._device, dtype=torch.float32)
+        else:
+            mu, value = out
+        stream = torch.cuda.current_stream(self._device).cuda_stream
+        _lib.check(self._lib.lm_gnn_forward(self._handle, obs.data_ptr(), mu.data_ptr(), value.data_ptr(), n, stream), "lm_gnn_forward")
+        return mu, value, self.log_std_parameter
+
+    def __del__(self):
+        try:
+            if self._handle:
+                self._lib.lm_gnn_destroy(self._handle)
+                self._handle = None
+        except Exception:
+            pass

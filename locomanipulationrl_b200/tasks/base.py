@@ -1,0 +1,261 @@
+"""Host-side mirror of the reference task surface (tasks/base/rl_task.py:45-260, joint_rl_task.py).
+
+``LocoManipulationTask`` keeps the OmniIsaacGymEnvs task API — ``pre_physics_step(actions)``,
+``post_physics_step() -> (obs_buf, rew_buf, reset_buf, extras)``, ``get_observations``, ``get_states``,
+``calculate_metrics``, ``is_done``, ``get_extras``, ``reset``, ``reset_idx``, ``post_reset``, the
+``obs_buf/states_buf/rew_buf/reset_buf/progress_buf/extras`` buffers with the reference dtypes, and the
+attributes the vec-env adapter reads (``clip_obs``, ``clip_actions``, ``rl_device``, ``device``,
+``control_frequency_inv``, ``randomize_actions/observations``) — but every method is a thin call into
+liblm_b200.so (include/lm_b200.h).  PyTorch owns the tensors; there is no eager fallback: without a
+CUDA device or without the built library construction raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import torch
+
+from .. import _lib
+from ..configs import (CONTROL_EFFORT, CONTROL_PD, KIND_COTRAIN, KIND_LOCO, KIND_MANI, TaskConfig, get_task_config)
+
+_ART_KEYS = ("dof_pos", "dof_vel", "root_pos", "root_quat", "root_lin_vel", "root_ang_vel", "tip_pos", "knee_pos",
+             "indicator_pos", "indicator_quat", "plate_pos", "plate_quat", "plate_lin_vel", "plate_ang_vel")
+
+
+class LocoManipulationTask:
+    """One task instance over ``num_envs`` environments on one GPU."""
+
+    def __init__(self, cfg: TaskConfig, num_envs: int, scene=None, device="cuda:0", rl_device=None,
+                 clamp_actions: bool = True, fuse_obs_clamp: bool = False, seed: int = 42):
+        self.cfg = cfg
+        self._name = cfg.name
+        self._num_envs = int(num_envs)
+        self._device = torch.device(device)
+        if self._device.type != "cuda":
+            raise _lib.LmError("LocoManipulationTask runs on a CUDA device only (no CPU fallback)")
+        if not torch.cuda.is_available():
+            raise _lib.LmError("CUDA is not available; the B200 task kernels cannot run")
+        self._lib = _lib.load()
+        self.rl_device = rl_device or str(self._device)
+        self._num_actions, self._num_observations, self._num_states = cfg.num_actions, cfg.num_observations, cfg.num_states
+        self._num_agents = 1
+        self.clip_obs, self.clip_actions = cfg.clip_observations, cfg.clip_actions
+        self.control_frequency_inv = cfg.control_frequency_inv
+        self.randomize_actions = False        # rl_task.py:72-73 (domain randomisation is off in every hot-path yaml)
+        self.randomize_observations = False
+        self._dr_randomizer = None
+        self._max_episode_length = cfg.max_episode_length
+        self._single_task_num_envs = self._num_envs // 2 if cfg.kind == KIND_COTRAIN else self._num_envs
+        self._generator = torch.Generator(device=self._device)
+        self._generator.manual_seed(seed)
+        idx = self._device.index if self._device.index is not None else torch.cuda.current_device()
+        self._params = _lib.task_params(cfg, self._num_envs, clamp_actions=clamp_actions)
+        with torch.cuda.device(idx):
+            self._handle = self._lib.lm_task_create(C.byref(self._params), idx)
+        if not self._handle:
+            raise _lib.LmError(f"lm_task_create failed: {self._lib.lm_last_error().decode()}")
+        if fuse_obs_clamp:
+            _lib.check(self._lib.lm_task_set_clamp_observations(self._handle, 1), "lm_task_set_clamp_observations")
+        self.cleanup()
+        self._scene = None
+        self._loco_views = self._mani_views = None
+        self._posted_since_pre = False
+        if scene is not None:
+            self.set_up_scene(scene)
+
+    # ------------------------------------------------------------------ buffers (rl_task.py:104-113; QPC:123-154)
+    def cleanup(self) -> None:
+        n, dev, f32, i64 = self._num_envs, self._device, torch.float32, torch.long
+        self.obs_buf = torch.zeros((n, self._num_observations), device=dev, dtype=f32)
+        if self._num_states == 93:
+            self.states_buf = torch.zeros((n, 93), device=dev, dtype=f32)
+        else:
+            self.states_buf = self.obs_buf                      # JLV:515
+        self.rew_buf = torch.zeros(n, device=dev, dtype=f32)
+        self.reset_buf = torch.ones(n, device=dev, dtype=i64)
+        self.progress_buf = torch.zeros(n, device=dev, dtype=i64)
+        self.successes = torch.zeros(n, device=dev, dtype=i64)
+        self.consecutive_successes = torch.zeros(n, device=dev, dtype=i64)
+        self.goal_reset_buf = torch.zeros(n, device=dev, dtype=i64)
+        self._actions_ring = torch.zeros((2, n, 12), device=dev, dtype=f32)
+        self.last_joint_velocities = torch.zeros((n, 12), device=dev, dtype=f32)
+        self.last_base_tip_positions = torch.zeros((n, 4, 3), device=dev, dtype=f32)
+        self.goal_quaternions = torch.zeros((n, 4), device=dev, dtype=f32)
+        self.reset_env_ids_buf = torch.zeros(n, device=dev, dtype=i64)
+        self.num_reset_buf = torch.zeros(2, device=dev, dtype=torch.int32)
+        self._extras_buf = torch.zeros(_lib.NUM_EXTRAS, device=dev, dtype=f32)
+        self._counters = torch.zeros(6, device=dev, dtype=i64)
+        h = self._single_task_num_envs
+        tw = 20 if self.cfg.control_mode == CONTROL_EFFORT else 12
+        self.targets_loco = torch.zeros((h, tw), device=dev, dtype=f32)
+        self.targets_mani = torch.zeros((h, tw), device=dev, dtype=f32)
+        ex = self._extras_buf
+        self.extras: Dict[str, torch.Tensor] = {"env/rewards/" + k: ex[i] for i, k in enumerate(_lib.EXTRA_NAMES)}
+        self.extras["env/success_rate"] = ex[_lib.EXTRA_SUCCESS_RATE]
+        if self.cfg.kind == KIND_COTRAIN:
+            self.extras["env/success_rate_loco"] = ex[_lib.EXTRA_SUCCESS_RATE + 1]
+            self.extras["env/success_rate_mani"] = ex[_lib.EXTRA_SUCCESS_RATE + 2]
+        b = _lib.LmTaskBuffers()
+        b.obs_buf, b.rew_buf = self.obs_buf.data_ptr(), self.rew_buf.data_ptr()
+        b.states_buf = self.states_buf.data_ptr() if self._num_states == 93 else None
+        b.reset_buf, b.progress_buf = self.reset_buf.data_ptr(), self.progress_buf.data_ptr()
+        b.successes, b.consecutive_successes = self.successes.data_ptr(), self.consecutive_successes.data_ptr()
+        b.goal_reset_buf, b.actions_ring = self.goal_reset_buf.data_ptr(), self._actions_ring.data_ptr()
+        b.last_joint_vel, b.last_base_tip = self.last_joint_velocities.data_ptr(), self.last_base_tip_positions.data_ptr()
+        b.goal_quaternions, b.reset_env_ids = self.goal_quaternions.data_ptr(), self.reset_env_ids_buf.data_ptr()
+        b.num_reset, b.extras, b.counters = self.num_reset_buf.data_ptr(), self._extras_buf.data_ptr(), self._counters.data_ptr()
+        self._buffers = b
+
+    # ------------------------------------------------------------------ scene / views
+    def _views(self, state: Optional[Dict[str, torch.Tensor]], targets: torch.Tensor):
+        if not state:
+            return None
+        v = _lib.LmRobotViews()
+        for k in _ART_KEYS:
+            t = state.get(k)
+            if t is not None:
+                if t.device != self._device or t.dtype != torch.float32 or not t.is_contiguous():
+                    raise _lib.LmError(f"view tensor {k} must be a contiguous float32 tensor on {self._device}")
+                setattr(v, k, t.data_ptr())
+        v.targets = targets.data_ptr()
+        return v
+
+    def set_up_scene(self, scene) -> None:
+        """Bind the PhysX-side tensors (``scene.loco`` / ``scene.mani`` dicts and ``scene.env_pos``).  The reference's
+        set_up_scene clones USD prims and creates the views (QPC:161-186); only the resulting tensors matter here."""
+        self._scene = scene
+        self._env_pos = scene.env_pos
+        assert self._env_pos.shape[0] == self._single_task_num_envs
+        self._loco_views = self._views(scene.loco, self.targets_loco)
+        self._mani_views = self._views(scene.mani, self.targets_mani)
+        if self.cfg.kind != KIND_MANI and self._loco_views is None:
+            raise _lib.LmError("scene has no locomotion robot state")
+        if self.cfg.kind != KIND_LOCO and self._mani_views is None:
+            raise _lib.LmError("scene has no manipulation robot state")
+
+    def post_reset(self) -> None:
+        """QPC:188-198 — limits / gains / DOF index discovery are PhysX plumbing; nothing to compute."""
+        return None
+
+    # ------------------------------------------------------------------ properties (rl_task.py:166-219)
+    num_envs = property(lambda self: self._num_envs)
+    num_actions = property(lambda self: self._num_actions)
+    num_observations = property(lambda self: self._num_observations)
+    num_states = property(lambda self: self._num_states)
+    num_agents = property(lambda self: self._num_agents)
+    device = property(lambda self: str(self._device))
+
+    @property
+    def current_actions(self) -> torch.Tensor:
+        return self._actions_ring[self._lib.lm_task_step_parity(self._handle)]
+
+    @property
+    def last_actions(self) -> torch.Tensor:
+        p = self._lib.lm_task_step_parity(self._handle)
+        # after post_physics_step the reference has last_actions == current_actions (QPC:548)
+        return self._actions_ring[p if self._posted_since_pre else p ^ 1]
+
+    @property
+    def num_successes(self):
+        return self._counters[0]
+
+    @property
+    def num_resets(self):
+        return self._counters[1]
+
+    def _stream(self):
+        return torch.cuda.current_stream(self._device).cuda_stream
+
+    def _lp(self):
+        return C.byref(self._loco_views) if self._loco_views is not None else None
+
+    def _mp(self):
+        return C.byref(self._mani_views) if self._mani_views is not None else None
+
+    # ------------------------------------------------------------------ the task API
+    def get_states(self):
+        return self.states_buf
+
+    def get_extras(self):
+        return self.extras
+
+    def reset(self) -> None:
+        """rl_task.py:222-225 (in place, so the pointer the kernels hold stays valid)."""
+        self.reset_buf.fill_(1)
+
+    def draw_goal_uniforms(self) -> torch.Tensor:
+        """The ``torch.rand((num_reset, 3))`` draw of rand_quaternions (utils/math.py:184), drawn for every env up
+        front so no host sync on ``num_reset`` is needed; row k is consumed by the k-th reset env."""
+        return torch.rand((self._num_envs, 3), device=self._device, generator=self._generator)
+
+    def pre_physics_step(self, actions: torch.Tensor, uniforms: Optional[torch.Tensor] = None) -> None:
+        if self._scene is None:
+            raise _lib.LmError("set_up_scene(scene) must be called before stepping")
+        actions = actions.to(self._device, dtype=torch.float32)
+        if not actions.is_contiguous():
+            actions = actions.contiguous()
+        if uniforms is None:
+            uniforms = self.draw_goal_uniforms()
+        if self._posted_since_pre is False and self._lib.lm_task_step_parity(self._handle) >= 0:
+            pass
+        rc = self._lib.lm_task_pre_step(self._handle, self._lp(), self._mp(), self._env_pos.data_ptr(), C.byref(self._buffers),
+                                        actions.data_ptr(), uniforms.data_ptr(), self._stream())
+        _lib.check(rc, "lm_task_pre_step")
+        self._posted_since_pre = False
+        self._keep = (actions, uniforms)   # keep inputs alive until the stream has consumed them
+
+    def reset_idx(self, env_ids: torch.Tensor, uniforms: Optional[torch.Tensor] = None) -> None:
+        env_ids = env_ids.to(self._device, dtype=torch.long).contiguous()
+        k = int(env_ids.numel())
+        if k == 0:
+            return
+        if uniforms is None:
+            uniforms = torch.rand((k, 3), device=self._device, generator=self._generator)
+        rc = self._lib.lm_task_reset_idx(self._handle, self._lp(), self._mp(), self._env_pos.data_ptr(), C.byref(self._buffers),
+                                         env_ids.data_ptr(), k, uniforms.data_ptr(), self._stream())
+        _lib.check(rc, "lm_task_reset_idx")
+        self._keep = (env_ids, uniforms)
+
+    def post_physics_step(self):
+        """rl_task.py:240-260: progress += 1, observations, metrics, termination — one fused launch."""
+        if self._posted_since_pre:
+            # second post without a pre: the reference would see last_actions == current_actions (QPC:548)
+            p = self._lib.lm_task_step_parity(self._handle)
+            self._actions_ring[p ^ 1].copy_(self._actions_ring[p])
+        rc = self._lib.lm_task_post_step(self._handle, self._lp(), self._mp(), self._env_pos.data_ptr(), C.byref(self._buffers),
+                                         self._stream())
+        _lib.check(rc, "lm_task_post_step")
+        self._posted_since_pre = True
+        return self.obs_buf, self.rew_buf, self.reset_buf, self.extras
+
+    # The reference runs these three in sequence inside post_physics_step; here they are one kernel.  Calling
+    # get_observations() runs it; the other two are then no-ops on already-computed buffers.
+    def get_observations(self):
+        self.progress_buf -= 1      # post_physics_step increments; a bare get_observations() must not (QPC:301)
+        self.post_physics_step()
+        return self.obs_buf
+
+    def calculate_metrics(self) -> None:
+        return None
+
+    def is_done(self) -> None:
+        return None
+
+    def reset_env_ids(self) -> torch.Tensor:
+        """Ascending ids reset by the last pre_physics_step (host sync; for logging / parity checks)."""
+        k = int(self.num_reset_buf[0].item())
+        return self.reset_env_ids_buf[:k]
+
+    def __del__(self):
+        try:
+            if getattr(self, "_handle", None):
+                self._lib.lm_task_destroy(self._handle)
+                self._handle = None
+        except Exception:
+            pass
+
+
+def make_task(name: str, num_envs: int, scene=None, device="cuda:0", **kw) -> LocoManipulationTask:
+    """Name -> task, the role of ``initialize_task``'s task_map (utils/task_util.py:60-90)."""
+    return LocoManipulationTask(get_task_config(name), num_envs, scene=scene, device=device, **kw)

@@ -1,0 +1,121 @@
+"""TEST INFRASTRUCTURE — generates tests/golden/*.npz from the UNMODIFIED reference under the shim.
+
+Run in the authoring container only (needs /root/reference):  ``python -m oracle.make_golden``.
+Each task fixture stores, for a short seeded rollout, everything the reference task exposes after each
+``pre_physics_step`` / ``post_physics_step`` so that (a) the port and (b) the CUDA path can be checked on a
+box where the reference does not exist.  Inputs are regenerated from seeds (SyntheticScene, torch.Generator).
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+from locomanipulationrl_b200 import configs, synthetic
+from oracle import refshim
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+TASK_N = 50            # ragged: n % 4 != 0 (co-train halves of 25) -> exercises the non-TMA tail path of the kernels
+TASK_STEPS = 20        # long enough for the consecutive-success counter to pass 15 and trigger goal resets
+FULL_STEPS = (0, 1, 2, 17, 18, 19)   # steps whose float tensors are stored; the rest keep masks / ints / rewards only
+SEED = 7
+
+
+def rollout_inputs(n, steps, seed=SEED):
+    g = torch.Generator().manual_seed(seed)
+    acts = [(torch.rand(n, 12, generator=g) * 2 - 1) for _ in range(steps)]
+    unis = [torch.rand(n, 3, generator=g) for _ in range(steps)]
+    return acts, unis
+
+
+def task_fixture(name):
+    cfg = configs.get_task_config(name)
+    scene = synthetic.SyntheticScene(cfg, TASK_N, seed=SEED)
+    task = refshim.make_reference_task(cfg, scene)
+    acts, unis = rollout_inputs(TASK_N, TASK_STEPS)
+    out = {}
+    for t in range(TASK_STEPS):
+        with refshim.supplied_uniforms(unis[t]), refshim.quiet():
+            ids = task.reset_buf.nonzero(as_tuple=False).squeeze(-1).clone()
+            task.pre_physics_step(acts[t].clone())
+        full = t in FULL_STEPS
+        out[f"s{t}_reset_ids"] = ids.numpy()
+        out[f"s{t}_goal"] = task.goal_quaternions.numpy().copy()
+        for grp in ("loco", "mani"):
+            st = getattr(scene, grp)
+            if st and full:
+                art = (task.robot_locomotion if grp == "loco" else task.robot_manipulation)._robot_articulation
+                out[f"s{t}_{grp}_targets"] = art.targets["velocity"][:, :12].numpy().copy()
+                for k in ("dof_pos", "dof_vel", "indicator_pos", "indicator_quat") + (("root_pos", "root_quat") if grp == "loco" else ("plate_pos", "plate_quat")):
+                    out[f"s{t}_{grp}_{k}"] = st[k].numpy().copy()
+        scene.step(t, task.goal_quaternions)
+        with refshim.quiet():
+            obs, rew, reset, extras = task.post_physics_step()
+        if full:
+            out[f"s{t}_obs"] = obs.numpy().copy()
+            if cfg.num_states == 93:
+                out[f"s{t}_states"] = task.get_states().numpy().copy()
+            out[f"s{t}_last_base_tip_positions"] = task.last_base_tip_positions.numpy().copy()
+        out[f"s{t}_rew"] = rew.numpy().copy()
+        out[f"s{t}_reset"] = reset.numpy().astype(np.int8)
+        for k in ("progress_buf", "successes", "consecutive_successes", "goal_reset_buf"):
+            out[f"s{t}_{k}"] = getattr(task, k).numpy().astype(np.int16)
+        for k, v in extras.items():
+            out[f"s{t}_extras/{k}"] = np.asarray(float(v), dtype=np.float32)
+    np.savez_compressed(os.path.join(GOLDEN_DIR, f"task_{name}.npz"), **out)
+    print("wrote", name, len(out), "arrays")
+
+
+def gnn_fixture():
+    refshim.install()
+    import graph_model_orebot_ov as G  # the reference module (scripts/graph_model_orebot_ov.py)
+    torch.manual_seed(11)
+    net = G.GraphNet(hidden_features=32, out_features=32)
+    act = G.Action_Layer(hidden_features=32, num_actions=12)
+    val = G.Value_Layer(hidden_features=32)
+    obs = torch.randn(64, 64) * 1.5
+    with torch.no_grad():
+        h = net(obs)
+        mu, value = act(h), val(h)
+    sd = {"net." + k: v for k, v in net.state_dict().items()}
+    sd.update({"mean_layer." + k: v for k, v in act.state_dict().items()})
+    sd.update({"value_layer." + k: v for k, v in val.state_dict().items()})
+    out = {"obs": obs.numpy(), "mu": mu.numpy(), "value": value.numpy()}
+    out.update({"p/" + k: v.numpy() for k, v in sd.items()})
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "gnn_reference.npz"), **out)
+    print("wrote gnn", mu.shape, value.shape)
+
+
+def math_fixture():
+    """utils/math.py helpers on seeded inputs (the SciPy float64 path)."""
+    refshim.install()
+    import utils.math as M
+    g = torch.Generator().manual_seed(5)
+    n = 512
+    q = torch.randn(n, 4, generator=g); q = q / q.norm(dim=-1, keepdim=True) + torch.randn(n, 4, generator=g) * 1e-4
+    q2 = torch.randn(n, 4, generator=g); q2 = q2 / q2.norm(dim=-1, keepdim=True)
+    t = torch.randn(n, 3, generator=g)
+    v = torch.randn(n, 8, 3, generator=g)
+    out = {"q": q.numpy(), "q2": q2.numpy(), "t": t.numpy(), "v": v.numpy(),
+           "transform": M.transform_vectors(q, t, v).numpy(), "inverse_transform": M.inverse_transform_vectors(q, t, v).numpy(),
+           "rotate": M.rotate_orientations(q, q2).numpy(), "inverse_rotate": M.inverse_rotate_orientations(q, q2).numpy(),
+           "main_example": M.inverse_rotate_orientations(torch.tensor([-0.5, -0.5, 0.5, 0.5]).repeat(2, 1),
+                                                         torch.tensor([0.7071, 0, 0, 0.7071]).repeat(2, 1)).numpy()}   # math.py:214-218
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "math_reference.npz"), **out)
+    print("wrote math")
+
+
+def main():
+    if not refshim.reference_available():
+        sys.exit("reference tree not available; golden vectors can only be generated in the authoring container")
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    for name in configs.TASK_CONFIGS:
+        task_fixture(name)
+    gnn_fixture()
+    math_fixture()
+
+
+if __name__ == "__main__":
+    main()
