@@ -1,0 +1,463 @@
+#!/usr/bin/env python
+"""Benchmark of the task + policy hot path (BASELINE.json metric: env-steps/s, obs+reward+PD/targets+reset+policy).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one rank per GPU under torchrun)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU torch path (oracle port) on the host cores
+
+Workload (config.workload): JointLocomanipulationVertical co-train (half locomotion, half manipulation envs) +
+MLP actor-critic, 65,536 envs PER GPU — BASELINE.json configs[2] at N=1 and configs[4] (524,288 envs on 8 GPUs) at
+N=8, i.e. weak scaling.  One "step" = pre_physics_step(actions) [reset scan, reset scatter + goal resample, action ->
+targets] -> synthetic physics state swap -> post_physics_step [obs, reward, termination, stats] -> MLP forward.
+Other workloads: --workload manip16k (configs[1]), gnn_gae (configs[3]).
+
+Prints ONE JSON line (rank 0).  `value` = device-resident throughput; `e2e` = the same step driven through the
+C-ABI host entry (lm_task_step_host) with pinned-host inputs/outputs copied every step.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+ENVS_PER_GPU = 65536
+STATE_SETS = 6            # distinct synthetic state sets rotated through: 6 x ~23 MB state + buffers > 126 MB L2
+B_TASK = 1036             # algorithmic bytes / env-step, task path
+B_POST = 892              # of which the post_physics_step kernel moves (DESIGN.md "k_post bytes")
+MLP_FLOPS = 116352        # FLOP / env
+HORIZON = 16              # stats / gradient all-reduce cadence (rollout horizon of BASELINE configs[3])
+
+WORKLOADS = {
+    "cotrain64k": dict(task="JointLocomanipulationVertical", envs=ENVS_PER_GPU, policy="mlp",
+                       desc="JointLocomanipulationVertical co-train + MLP actor-critic, 65,536 envs per GPU"),
+    "manip16k": dict(task="QuadrupedManipulatePlate", envs=16384, policy="mlp",
+                     desc="QuadrupedManipulatePlate + MLP actor-critic, 16,384 envs per GPU"),
+    "gnn_gae": dict(task="JointLocomanipulationVertical", envs=ENVS_PER_GPU, policy="gnn",
+                    desc="JointLocomanipulationVertical co-train + GNN policy + GAE over 16-step rollouts, 65,536 envs per GPU"),
+}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return float(d.get("hbm_gbs", 6650.0)), float(d.get("bf16_tflops", 1590.0)), "measured"
+    return 6650.0, 1590.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi SM clocks / throttle reasons while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.1)
+
+    def summary(self):
+        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        reasons = set()
+        for s in self.samples:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        mx = max((int(s[1]) for s in self.samples if s[1].isdigit()), default=None)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(self.samples)}
+
+
+# ----------------------------------------------------------------------------------------------- reference / CPU arm
+def run_cpu_port(workload, steps, warmup, envs):
+    """The reference's CPU torch path (oracle port: same scipy/torch calls as the reference classes) + torch policy."""
+    from locomanipulationrl_b200 import configs, synthetic
+    from oracle import port, port_policy
+    torch.set_num_threads(os.cpu_count() or 1)
+    w = WORKLOADS[workload]
+    cfg = configs.get_task_config(w["task"])
+    scene = synthetic.SyntheticScene(cfg, envs)
+    task = port.TaskPort(cfg, scene)
+    torch.manual_seed(0)
+    if w["policy"] == "mlp":
+        net = torch.nn.Sequential(torch.nn.Linear(64, 256), torch.nn.ELU(), torch.nn.Linear(256, 128), torch.nn.ELU(),
+                                  torch.nn.Linear(128, 64), torch.nn.ELU())
+        mean, val = torch.nn.Linear(64, 12), torch.nn.Linear(64, 1)
+        def policy(obs):
+            h = net(obs)
+            return mean(h), val(h)
+    else:
+        import numpy as np
+        g = np.load(os.path.join(ROOT, "tests", "golden", "gnn_reference.npz"))
+        sd = {k[2:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("p/")}
+        def policy(obs):
+            return port_policy.gnn_forward(sd, obs)
+    states = [scene.generate(i) for i in range(STATE_SETS)]
+    gen = torch.Generator().manual_seed(1)
+    unis = [torch.rand(envs, 3, generator=gen) for _ in range(STATE_SETS)]
+    actions = torch.zeros(envs, 12)
+    times = []
+    rollout = []
+    with torch.no_grad():
+        for t in range(warmup + steps):
+            t0 = time.perf_counter()
+            task.pre_physics_step(torch.clamp(actions, -1.0, 1.0), unis[t % STATE_SETS])
+            scene.load(states[t % STATE_SETS])
+            obs, rew, reset, _ = task.post_physics_step()
+            mu, value = policy(torch.clamp(obs, -5.0, 5.0))
+            actions = mu
+            if w["policy"] == "gnn":
+                rollout.append((rew.clone(), value.view(-1).clone(), reset.float()))
+                if len(rollout) == HORIZON:
+                    r, v, d = (torch.stack(x) for x in zip(*rollout))
+                    port_policy.gae_rlgames(r, v, d, v[-1], d[-1])
+                    rollout = []
+            dt = time.perf_counter() - t0
+            if t >= warmup:
+                times.append(dt)
+    total = sum(times)
+    return envs * len(times) / total, total / len(times), torch.get_num_threads()
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    w = WORKLOADS[args.workload]
+    envs = w["envs"]
+    # bound the run: calibrate one step at full size, shrink the env sample if K steps would take too long
+    v1, t1, cores = run_cpu_port(args.workload, 1, 1, envs)
+    budget = 150.0
+    while (args.steps + args.warmup) * t1 * (envs / w["envs"]) > budget and envs > 2048:
+        envs //= 2
+    value, per_step, cores = run_cpu_port(args.workload, args.steps, args.warmup, envs)
+    sample = f"{args.steps} steps x {envs} envs of the {w['envs']}-env workload (oracle port: the reference's scipy/torch CPU path)"
+    line = {"impl": "reference", "metric": "env-steps/s (obs+reward+PD+reset+policy)", "value": value, "unit": "env-steps/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": w["desc"], "envs_per_step": envs},
+            "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------- CUDA arm
+class Pipeline:
+    """Device-resident step loop: S state sets, one CUDA graph per set (count + pre + post + policy = 4 launches)."""
+
+    def __init__(self, workload, device, rank):
+        from locomanipulationrl_b200 import _lib, configs, synthetic
+        from locomanipulationrl_b200.tasks.base import LocoManipulationTask
+        from locomanipulationrl_b200.policy.mlp import MlpActorCritic
+        from locomanipulationrl_b200.policy.gnn import GnnActorCritic
+        self.w = WORKLOADS[workload]
+        self.device = device
+        self.n = n = self.w["envs"]
+        self.lib = _lib.load()
+        self._lib_mod = _lib
+        cfg = configs.get_task_config(self.w["task"])
+        self.cfg = cfg
+        self.scenes = [synthetic.SyntheticScene(cfg, n, device=device, seed=1000 * rank + 42, env_id_offset=rank * n) for _ in range(STATE_SETS)]
+        self.host_states = []
+        for i, sc in enumerate(self.scenes):
+            st = sc.generate(i)
+            sc.load(st)
+            self.host_states.append(sc.pack_host(st))
+        self.task = LocoManipulationTask(cfg, n, scene=self.scenes[0], device=device, fuse_obs_clamp=True, seed=rank)
+        torch.manual_seed(0)          # identical weights on every rank (data parallel)
+        if self.w["policy"] == "mlp":
+            self.policy = MlpActorCritic(device=device)
+        else:
+            self.policy = GnnActorCritic(device=device)
+        self.policy.pack()
+        g = torch.Generator(device=device).manual_seed(7 + rank)
+        self.uniforms = [torch.rand(n, 3, device=device, generator=g) for _ in range(STATE_SETS)]
+        self.mu = torch.zeros(n, 12, device=device)
+        self.value = torch.zeros(n, 1, device=device)
+        self.norm_mean = torch.zeros(64, device=device)
+        self.norm_inv_std = torch.ones(64, device=device)
+        self.graphs = None
+        self.gae_buf = None
+        if self.w["policy"] == "gnn":
+            T = HORIZON
+            self.gae_buf = dict(r=torch.zeros(T, n, device=device), v=torch.zeros(T, n, device=device), d=torch.zeros(T, n, device=device),
+                                adv=torch.zeros(T, n, device=device), ret=torch.zeros(T, n, device=device))
+        self.launches_per_step = 4
+
+    def step_eager(self, i, t=0):
+        task = self.task
+        task.pre_physics_step(self.mu, self.uniforms[i])
+        task.set_up_scene(self.scenes[i])               # "physics": the next state set becomes the live views
+        task.post_physics_step()
+        if self.w["policy"] == "mlp":
+            self.policy(task.obs_buf, norm_mean=self.norm_mean, norm_inv_std=self.norm_inv_std, out=(self.mu, self.value))
+        else:
+            self.policy(task.obs_buf, out=(self.mu, self.value))
+            b = self.gae_buf
+            k = t % HORIZON
+            b["r"][k].copy_(task.rew_buf); b["v"][k].copy_(self.value.view(-1)); b["d"][k].copy_(task.reset_buf)
+            if k == HORIZON - 1:
+                s = torch.cuda.current_stream().cuda_stream
+                self._lib_mod.check(self.lib.lm_gae(b["r"].data_ptr(), b["v"].data_ptr(), b["d"].data_ptr(), b["v"][-1].data_ptr(),
+                                                    b["d"][-1].data_ptr(), b["adv"].data_ptr(), b["ret"].data_ptr(), HORIZON, self.n,
+                                                    0.99, 0.95, 0, s), "lm_gae")
+
+    def capture(self):
+        """One CUDA graph per state set (parity of the action ring alternates, STATE_SETS is even)."""
+        assert STATE_SETS % 2 == 0
+        if self.w["policy"] != "mlp":
+            return                                      # the GAE cadence needs a host-side counter: stay eager
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for i in range(STATE_SETS):
+                self.step_eager(i)                      # warm everything on the capture stream
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graphs = []
+        for i in range(STATE_SETS):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.step_eager(i)
+            self.graphs.append(g)
+        torch.cuda.synchronize()
+
+    def step(self, t):
+        if self.graphs is not None:
+            self.graphs[t % STATE_SETS].replay()
+        else:
+            self.step_eager(t % STATE_SETS, t)
+
+
+def time_kernel(fn, iters):
+    """Average device time of one call sequence (CUDA events on the launching stream)."""
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+    for i, (a, b) in enumerate(ev):
+        a.record()
+        fn(i)
+        b.record()
+    torch.cuda.synchronize()
+    ts = [a.elapsed_time(b) for a, b in ev]
+    return sum(ts) / len(ts)
+
+
+def cuda_arm(args):
+    from locomanipulationrl_b200 import dist as lmdist
+    import torch.distributed as tdist
+    rank, world, local_rank = lmdist.init_from_env("nccl")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback (use --impl reference for the CPU baseline)")
+    device = torch.device(f"cuda:{local_rank}")
+    torch.cuda.set_device(device)
+    pipe = Pipeline(args.workload, device, rank)
+    n = pipe.n
+    stats = lmdist.StatReducer(n, device)
+    arena = lmdist.GradArena(pipe.policy.parameters())
+    comm_stream = torch.cuda.Stream(device=device)
+
+    def comm():
+        """Episode-stat reduction + PPO gradient all-reduce, once per rollout horizon, on a side stream."""
+        if world == 1:
+            return
+        comm_stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(comm_stream):
+            stats.reduce(pipe.task._extras_buf, pipe.task._counters)
+            arena.allreduce_mean()
+
+    pipe.capture()
+    for t in range(max(args.warmup, 3)):
+        pipe.step(t)
+    torch.cuda.synchronize()
+    if world > 1:
+        tdist.barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.25)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for t in range(args.steps):
+        pipe.step(t)
+        if (t + 1) % HORIZON == 0:
+            comm()
+    torch.cuda.current_stream().wait_stream(comm_stream)
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        tdist.barrier()
+    ms_total = e0.elapsed_time(e1)
+    sampler.stop_flag.set()
+    sampler.join(timeout=2)
+    t_ms = torch.tensor([ms_total], device=device, dtype=torch.float64)
+    if world > 1:
+        tdist.all_reduce(t_ms, op=tdist.ReduceOp.MAX)
+    ms_total = float(t_ms.item())
+    value = n * world * args.steps / (ms_total * 1e-3)
+
+    # ---- per-kernel timing (rank 0; eager launches bracketed by events, same state rotation)
+    line_extra = {}
+    if rank == 0:
+        task = pipe.task
+        iters = max(12, min(args.steps, 60))
+
+        def post_only(i):
+            task.set_up_scene(pipe.scenes[i % STATE_SETS])
+            task._posted_since_pre = False     # time the kernel alone (no double-post fix-up copy)
+            task.post_physics_step()
+
+        def pre_only(i):
+            task.pre_physics_step(pipe.mu, pipe.uniforms[i % STATE_SETS])
+
+        def policy_only(i):
+            if pipe.w["policy"] == "mlp":
+                pipe.policy(task.obs_buf, norm_mean=pipe.norm_mean, norm_inv_std=pipe.norm_inv_std, out=(pipe.mu, pipe.value))
+            else:
+                pipe.policy(task.obs_buf, out=(pipe.mu, pipe.value))
+
+        for f in (pre_only, post_only, policy_only):
+            for i in range(3):
+                f(i)
+        ms_post = time_kernel(post_only, iters)
+        ms_pre = time_kernel(pre_only, iters)
+        ms_pol = time_kernel(policy_only, iters)
+        hbm, tf, src = measured_peaks()
+        ach = n * B_POST / (ms_post * 1e-3) / 1e9
+        ach_task = n * B_TASK / ((ms_post + ms_pre) * 1e-3) / 1e9
+        line_extra["roofline"] = {"kernel": "k_post (post_physics_step)", "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s",
+                                  "frac": ach / hbm, "traffic": None, "peak_source": src, "bytes_per_env": B_POST, "ms": ms_post}
+        line_extra["roofline_task"] = {"kernels": "k_reset_count + k_pre + k_post", "bound": "hbm", "achieved": ach_task, "peak": hbm,
+                                       "unit": "GB/s", "frac": ach_task / hbm, "bytes_per_env": B_TASK, "ms": ms_post + ms_pre}
+        if pipe.w["policy"] == "mlp":
+            tfl = n * MLP_FLOPS / (ms_pol * 1e-3) / 1e12
+            line_extra["roofline_policy"] = {"kernel": "k_mlp_forward (tcgen05)", "bound": "tensor", "achieved": tfl, "peak": tf, "unit": "TFLOP/s",
+                                             "frac": tfl / tf, "ms": ms_pol, "hbm_gbs": n * 308 / (ms_pol * 1e-3) / 1e9}
+        else:
+            line_extra["roofline_policy"] = {"kernel": "k_gnn_forward", "bound": "fp32", "achieved": n * 447296 / (ms_pol * 1e-3) / 1e12,
+                                             "unit": "TFLOP/s (naive FLOP count)", "ms": ms_pol}
+        line_extra["kernel_ms"] = {"pre": ms_pre, "post": ms_post, "policy": ms_pol}
+
+    # ---- e2e: C-ABI host entry, pinned host buffers in, results out, every step
+    e2e = e2e_arm(pipe, args, world, device)
+
+    # ---- CPU baseline (rank 0, N=1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        w = WORKLOADS[args.workload]
+        cpu_steps = 12 if w["policy"] == "mlp" else 6
+        cpu_envs = w["envs"] if w["policy"] == "mlp" else 8192
+        v, per_step, cores = run_cpu_port(args.workload, cpu_steps, 2, cpu_envs)
+        cpu = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
+               "sample": f"{cpu_steps} steps x {cpu_envs} envs of the same workload (oracle port = the reference's scipy/torch CPU path), {per_step * 1e3:.0f} ms/step"}
+    if rank == 0:
+        clocks = sampler.summary()
+        line = {"metric": "env-steps/s (obs+reward+PD+reset+policy)", "value": value, "unit": "env-steps/s", "n_gpus": world,
+                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32 task math, bf16 x bf16 -> f32 policy GEMMs",
+                "data": "synthetic",
+                "config": {"workload": pipe.w["desc"], "envs_per_gpu": n, "global_envs": n * world, "parallelism": f"env-shard x{world}",
+                           "l2": f"{STATE_SETS} rotating synthetic state sets (> L2) - inputs larger than L2",
+                           "cuda_graphs": pipe.graphs is not None, "comm": f"stat + grad all-reduce every {HORIZON} steps" if world > 1 else "none"},
+                "gpu_launches": pipe.launches_per_step * args.steps, "clocks": clocks, "e2e": e2e, "cpu_baseline": cpu}
+        line.update(line_extra)
+        print(json.dumps(line))
+    if world > 1:
+        tdist.barrier()
+        tdist.destroy_process_group()
+
+
+def e2e_arm(pipe, args, world, device):
+    """Same step through lm_task_step_host: H2D of actions / uniforms / physics state from pinned memory, kernels,
+    D2H of obs / rew / reset, then the policy forward and D2H of its outputs.  Max over ranks."""
+    import torch.distributed as tdist
+    from locomanipulationrl_b200 import _lib
+    task, n, lib = pipe.task, pipe.n, pipe.lib
+    sc = pipe.scenes[0]
+    task.set_up_scene(sc)
+    pin = lambda *shape, dtype=torch.float32: torch.zeros(*shape, dtype=dtype).pin_memory()
+    actions_h, uniforms_h = pin(n, 12), pin(n, 3)
+    obs_h, rew_h, reset_h = pin(n, 64), pin(n), pin(n, dtype=torch.long)
+    mu_h, value_h = pin(n, 12), pin(n, 1)
+    actions_d, uniforms_d = torch.zeros(n, 12, device=device), torch.zeros(n, 3, device=device)
+    uniforms_h.copy_(pipe.uniforms[0].cpu())
+    io = _lib.LmHostStep()
+    io.actions_host, io.uniforms_host = actions_h.data_ptr(), uniforms_h.data_ptr()
+    io.actions_dev, io.uniforms_dev = actions_d.data_ptr(), uniforms_d.data_ptr()
+    io.obs_host, io.rew_host, io.reset_host = obs_h.data_ptr(), rew_h.data_ptr(), reset_h.data_ptr()
+    h2d = actions_h.numel() * 4 + uniforms_h.numel() * 4
+    for grp in ("loco", "mani"):
+        if grp in pipe.host_states[0]:
+            h2d += pipe.host_states[0][grp].numel() * 4
+    d2h = (obs_h.numel() + rew_h.numel() + mu_h.numel() + value_h.numel()) * 4 + reset_h.numel() * 8
+    stream = torch.cuda.current_stream()
+
+    def one(t):
+        hs = pipe.host_states[t % STATE_SETS]
+        if "loco" in hs:
+            io.loco_state_host, io.loco_state_floats, io.loco_state_dev = hs["loco"].data_ptr(), hs["loco"].numel(), sc.arena["loco"].data_ptr()
+        if "mani" in hs:
+            io.mani_state_host, io.mani_state_floats, io.mani_state_dev = hs["mani"].data_ptr(), hs["mani"].numel(), sc.arena["mani"].data_ptr()
+        rc = lib.lm_task_step_host(task._handle, task._lp(), task._mp(), task._env_pos.data_ptr(), C.byref(task._buffers), C.byref(io),
+                                   stream.cuda_stream)
+        _lib.check(rc, "lm_task_step_host")
+        if pipe.w["policy"] == "mlp":
+            pipe.policy(task.obs_buf, norm_mean=pipe.norm_mean, norm_inv_std=pipe.norm_inv_std, out=(pipe.mu, pipe.value))
+        else:
+            pipe.policy(task.obs_buf, out=(pipe.mu, pipe.value))
+        mu_h.copy_(pipe.mu, non_blocking=True)
+        value_h.copy_(pipe.value, non_blocking=True)
+        stream.synchronize()
+        actions_h.copy_(mu_h)           # the host hands the policy output back as the next step's actions
+
+    steps = max(4, min(args.steps, 40))
+    for t in range(3):
+        one(t)
+    torch.cuda.synchronize()
+    if world > 1:
+        tdist.barrier()
+    t0 = time.perf_counter()
+    for t in range(steps):
+        one(t)
+    torch.cuda.synchronize()
+    dt = torch.tensor([time.perf_counter() - t0], device=device, dtype=torch.float64)
+    if world > 1:
+        tdist.all_reduce(dt, op=tdist.ReduceOp.MAX)
+    return {"value": n * world * steps / float(dt.item()), "unit": "env-steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+            "steps": steps, "api": "lm_task_step_host (C ABI, pinned host buffers) + lm_mlp_forward"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=192)
+    ap.add_argument("--warmup", type=int, default=12)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cotrain64k", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        cuda_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,112 @@
+"""Multi-GPU plumbing: one process per GPU, environments block-sharded, NCCL used for exactly two things —
+the PPO gradient all-reduce and the episode-stat reduction (the reference only passes the
+``multi_gpu`` flag through to rl_games, cfg/config.yaml:29, scripts/rlgames_train.py:93-96).
+
+Environments never exchange data, so there is no data-path collective.  Each rank keeps its own
+locomotion/manipulation halves (N_r/2 + N_r/2); ``EnvSharding.global_ids`` gives the fixed permutation back to
+the reference's global ``[all loco ; all mani]`` order for parity checks.
+"""
+from __future__ import annotations
+
+import os
+from dataclasses import dataclass
+from typing import Dict, Iterable, List, Optional
+
+import torch
+import torch.distributed as dist
+
+
+def init_from_env(backend: Optional[str] = None) -> "tuple[int, int, int]":
+    """Join the torchrun rendezvous if WORLD_SIZE > 1.  Returns (rank, world_size, local_rank)."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        backend = backend or ("nccl" if torch.cuda.is_available() else "gloo")
+        if backend == "nccl":
+            torch.cuda.set_device(local_rank)
+        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+    return rank, world, local_rank
+
+
+@dataclass
+class EnvSharding:
+    """Block sharding of ``global_envs`` environments over ``world`` ranks."""
+    global_envs: int
+    world: int
+    rank: int
+    cotrain: bool = True
+
+    def __post_init__(self):
+        unit = 2 * self.world if self.cotrain else self.world
+        if self.global_envs % unit:
+            raise ValueError(f"global env count {self.global_envs} must be a multiple of {unit}")
+
+    @property
+    def local_envs(self) -> int:
+        return self.global_envs // self.world
+
+    def global_ids(self) -> torch.Tensor:
+        """Global env id (reference order) of every local env of this rank."""
+        n = self.local_envs
+        if not self.cotrain:
+            return torch.arange(n) + self.rank * n
+        h_local, h_global = n // 2, self.global_envs // 2
+        loco = torch.arange(h_local) + self.rank * h_local
+        return torch.cat([loco, loco + h_global])
+
+    def scatter_global(self, tensor_global: torch.Tensor) -> torch.Tensor:
+        return tensor_global[self.global_ids().to(tensor_global.device)]
+
+
+class StatReducer:
+    """Sum-reduces the per-rank reward-term means (weighted by env count) and the success / reset counters, then applies the
+    reference's success-rate bookkeeping on the global counts (QPC:619-633 / JLV:758-802).  One small all-reduce."""
+
+    def __init__(self, num_local_envs: int, device, group=None):
+        self.n = num_local_envs
+        self.group = group
+        self.buf = torch.zeros(7 + 6 + 1, dtype=torch.float64, device=device)
+
+    def reduce(self, extras_buf: torch.Tensor, counters: torch.Tensor) -> Dict[str, torch.Tensor]:
+        self.buf[0:7] = extras_buf[0:7].double() * self.n
+        self.buf[7:13] = counters.double()
+        self.buf[13] = float(self.n)
+        if dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            dist.all_reduce(self.buf, op=dist.ReduceOp.SUM, group=self.group)
+        total = self.buf[13]
+        return {"reward_means": (self.buf[0:7] / total).float(), "counters": self.buf[7:13].round().long(), "num_envs": total.long()}
+
+
+class GradArena:
+    """Pre-flattened fp32 gradient buffer: parameters' ``.grad`` are views into one arena, so the PPO gradient all-reduce
+    (rl_games ``multi_gpu``: all_reduce of the concatenated grads / world) is ONE NCCL call with no ``torch.cat``."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter], group=None):
+        self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
+        n = sum(p.numel() for p in self.params)
+        dev = self.params[0].device
+        self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.group = group
+        off = 0
+        for p in self.params:
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+
+    @property
+    def numel(self) -> int:
+        return self.flat.numel()
+
+    def zero_(self) -> None:
+        self.flat.zero_()
+
+    def allreduce_mean(self, async_op: bool = False):
+        if not (dist.is_initialized() and dist.get_world_size(self.group) > 1):
+            return None
+        work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group, async_op=async_op)
+        if async_op:
+            return work
+        self.flat.div_(dist.get_world_size(self.group))
+        return None

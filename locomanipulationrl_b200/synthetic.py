@@ -233,16 +233,29 @@ class SyntheticScene:
         self.env_pos = grid_env_origins(self.num_scenes, cfg.env_spacing).to(self.device)
         self.loco: Dict[str, torch.Tensor] = {}
         self.mani: Dict[str, torch.Tensor] = {}
+        self.arena: Dict[str, torch.Tensor] = {}        # one flat fp32 buffer per robot: all view tensors are slices of it
+        self.physics_floats: Dict[str, int] = {}        # leading floats of the arena that "physics" rewrites every step
         n = self.num_scenes
         if cfg.kind in (KIND_LOCO, KIND_COTRAIN):
-            self.loco = {k: torch.zeros(s, device=self.device) for k, s in self._art_shapes(n).items()}
-            self.loco["indicator_pos"] = torch.zeros(n, 3, device=self.device)
-            self.loco["indicator_quat"] = torch.zeros(n, 4, device=self.device)
+            self.loco = self._carve("loco", self._art_shapes(n), {"indicator_pos": (n, 3), "indicator_quat": (n, 4)})
         if cfg.kind in (KIND_MANI, KIND_COTRAIN):
-            self.mani = {k: torch.zeros(s, device=self.device) for k, s in self._art_shapes(n).items()}
-            for k, s in {"plate_pos": (n, 3), "plate_quat": (n, 4), "plate_lin_vel": (n, 3),
-                         "plate_ang_vel": (n, 3), "indicator_pos": (n, 3), "indicator_quat": (n, 4)}.items():
-                self.mani[k] = torch.zeros(s, device=self.device)
+            shapes = dict(self._art_shapes(n))
+            shapes.update({"plate_pos": (n, 3), "plate_quat": (n, 4), "plate_lin_vel": (n, 3), "plate_ang_vel": (n, 3)})
+            self.mani = self._carve("mani", shapes, {"indicator_pos": (n, 3), "indicator_quat": (n, 4)})
+
+    def _carve(self, group, physics_shapes, extra_shapes):
+        """Allocate one flat buffer and slice 16-byte-aligned tensors out of it (so a step's state is ONE host->device copy)."""
+        def pad4(x):
+            return (x + 3) // 4 * 4
+        offs, total = {}, 0
+        for k, shp in list(physics_shapes.items()) + list(extra_shapes.items()):
+            if k == next(iter(extra_shapes)):
+                self.physics_floats[group] = total
+            offs[k] = (total, shp)
+            total += pad4(shp[0] * shp[1])
+        flat = torch.zeros(total, device=self.device, dtype=torch.float32)
+        self.arena[group] = flat
+        return {k: flat[o:o + shp[0] * shp[1]].view(shp) for k, (o, shp) in offs.items()}
 
     @staticmethod
     def _art_shapes(n):
@@ -273,6 +286,21 @@ class SyntheticScene:
         for group, dst in (("loco", self.loco), ("mani", self.mani)):
             for k, v in states.get(group, {}).items():
                 dst[k].copy_(v, non_blocking=non_blocking)
+
+    def pack_host(self, states: Dict[str, Dict[str, torch.Tensor]], pin: bool = True) -> Dict[str, torch.Tensor]:
+        """Lay a generated state out exactly like the device arenas (physics part only) in pinned host memory."""
+        out = {}
+        for group, views in (("loco", self.loco), ("mani", self.mani)):
+            if not views:
+                continue
+            nfl = self.physics_floats[group]
+            host = torch.zeros(nfl, dtype=torch.float32)
+            base = self.arena[group].data_ptr()
+            for k, v in states[group].items():
+                off = (views[k].data_ptr() - base) // 4
+                host[off:off + v.numel()] = v.reshape(-1)
+            out[group] = host.pin_memory() if pin and torch.cuda.is_available() else host
+        return out
 
     def step(self, step: int, goal_quaternions: Optional[torch.Tensor] = None) -> None:
         self.load(self.generate(step, goal_quaternions))

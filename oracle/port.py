@@ -362,6 +362,8 @@ class TaskPort:
         self.extras.update({"env/rewards/" + k: v.mean() for k, v in terms.items()})
         self.inter["rot_dist"] = rot_dist
         self.inter["d23"] = d23
+        # magnitude of the summed terms: the natural scale for a relative tolerance on a reward that cancels to ~0
+        self.inter["rew_scale"] = sum(v.abs() for v in terms.values())
 
     # ------------------------------------------------------------------ is_done  (QPC:562-633, JLV:655-802)
     def is_done(self) -> None:

@@ -27,14 +27,18 @@ def rollout_inputs(n, steps, seed=GOLDEN_SEED):
     return acts, unis
 
 
-def assert_close(name, got, ref, rtol=RTOL, atol=ATOL, rows=None):
+def assert_close(name, got, ref, rtol=RTOL, atol=ATOL, rows=None, scale=None):
+    """|got - ref| <= atol + rtol * max(|ref|, scale).  ``scale`` (per element) is the magnitude of the terms a value was
+    summed from: the reward is rot_rew (up to 5) minus penalties and often cancels to ~0, so its fp32 error is relative
+    to the terms, not to the total."""
     got = torch.as_tensor(got).detach().cpu().double()
     ref = torch.as_tensor(ref).detach().cpu().double()
     assert got.shape == ref.shape, f"{name}: shape {tuple(got.shape)} vs {tuple(ref.shape)}"
+    mag = ref.abs() if scale is None else torch.maximum(ref.abs(), torch.as_tensor(scale).detach().cpu().double())
     if rows is not None:
-        got, ref = got[rows], ref[rows]
+        got, ref, mag = got[rows], ref[rows], mag[rows]
     err = (got - ref).abs()
-    tol = atol + rtol * ref.abs()
+    tol = atol + rtol * mag
     bad = err > tol
     if bad.any():
         i = torch.nonzero(bad)[0].tolist()
@@ -117,7 +121,7 @@ class CudaRollout:
         self._track("obs", assert_close(f"step {t} obs_buf", task.obs_buf, p.obs_buf))
         if self.cfg.num_states == 93:
             self._track("states", assert_close(f"step {t} states_buf", task.states_buf, p.states_buf))
-        self._track("rew", assert_close(f"step {t} rew_buf", task.rew_buf, p.rew_buf, rows=ok))
+        self._track("rew", assert_close(f"step {t} rew_buf", task.rew_buf, p.rew_buf, rows=ok, scale=p.inter["rew_scale"]))
         self._track("last_tip", assert_close(f"step {t} last_base_tip", task.last_base_tip_positions, p.last_base_tip_positions))
         self._track("last_jv", assert_close(f"step {t} last_joint_vel", task.last_joint_velocities,
                                             torch.cat([p.last_joint_velocities[g] for g in ("loco", "mani") if getattr(self.scene_cpu, g)], dim=0)))
