@@ -283,7 +283,8 @@ def cuda_arm(args):
             stats.reduce(pipe.task._extras_buf, pipe.task._counters)
             arena.allreduce_mean()
 
-    pipe.capture()
+    if not args.no_graphs:
+        pipe.capture()
     for t in range(max(args.warmup, 3)):
         pipe.step(t)
     torch.cuda.synchronize()
@@ -356,7 +357,7 @@ def cuda_arm(args):
         line_extra["kernel_ms"] = {"pre": ms_pre, "post": ms_post, "policy": ms_pol}
 
     # ---- e2e: C-ABI host entry, pinned host buffers in, results out, every step
-    e2e = e2e_arm(pipe, args, world, device)
+    e2e = None if args.no_e2e else e2e_arm(pipe, args, world, device)
 
     # ---- CPU baseline (rank 0, N=1 only)
     cpu = None
@@ -452,6 +453,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cotrain64k", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graphs", action="store_true", help="launch eagerly (for ncu captures)")
+    ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)

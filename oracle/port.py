@@ -361,6 +361,7 @@ class TaskPort:
                  "joint_limit_panelty": joint_limit_penalty}
         self.extras.update({"env/rewards/" + k: v.mean() for k, v in terms.items()})
         self.inter["rot_dist"] = rot_dist
+        self.inter["quat_diff_norm"] = torch.norm(quat_diff[:, 1:4], p=2, dim=-1)
         self.inter["d23"] = d23
         # magnitude of the summed terms: the natural scale for a relative tolerance on a reward that cancels to ~0
         self.inter["rew_scale"] = sum(v.abs() for v in terms.values())

@@ -27,7 +27,18 @@ def rollout_inputs(n, steps, seed=GOLDEN_SEED):
     return acts, unis
 
 
-def assert_close(name, got, ref, rtol=RTOL, atol=ATOL, rows=None, scale=None):
+def rot_reward_conditioning(p):
+    """Forward-error allowance for the orientation reward 0.5 / (2 asin(min(x, 1)) + 0.1) of the reference (QPC:431-432):
+    d asin / dx = 1 / sqrt(1 - x^2) is unbounded as x -> 1 (180-degree orientation error), so a 2-ulp perturbation of
+    x = |quat_diff.xyz| (goal quaternions differ by <= 1 ulp between libm implementations) moves rot_dist by
+    2 * 2.4e-7 / sqrt(1 - x^2).  Away from x ~ 1 this term is < 1e-7 and irrelevant."""
+    x = torch.clamp(p.inter["quat_diff_norm"].double(), max=1.0)
+    d_rd = 2.0 * 2.4e-7 / torch.sqrt(torch.clamp(1.0 - x * x, min=1.2e-7))
+    d_rew = 0.5 / (p.inter["rot_dist"].double().abs() + p.cfg.rot_eps) ** 2
+    return d_rew * d_rd
+
+
+def assert_close(name, got, ref, rtol=RTOL, atol=ATOL, rows=None, scale=None, extra_atol=None):
     """|got - ref| <= atol + rtol * max(|ref|, scale).  ``scale`` (per element) is the magnitude of the terms a value was
     summed from: the reward is rot_rew (up to 5) minus penalties and often cancels to ~0, so its fp32 error is relative
     to the terms, not to the total."""
@@ -39,6 +50,9 @@ def assert_close(name, got, ref, rtol=RTOL, atol=ATOL, rows=None, scale=None):
         got, ref, mag = got[rows], ref[rows], mag[rows]
     err = (got - ref).abs()
     tol = atol + rtol * mag
+    if extra_atol is not None:
+        ex = torch.as_tensor(extra_atol).detach().cpu().double()
+        tol = tol + (ex[rows] if rows is not None else ex)
     bad = err > tol
     if bad.any():
         i = torch.nonzero(bad)[0].tolist()
@@ -121,7 +135,8 @@ class CudaRollout:
         self._track("obs", assert_close(f"step {t} obs_buf", task.obs_buf, p.obs_buf))
         if self.cfg.num_states == 93:
             self._track("states", assert_close(f"step {t} states_buf", task.states_buf, p.states_buf))
-        self._track("rew", assert_close(f"step {t} rew_buf", task.rew_buf, p.rew_buf, rows=ok, scale=p.inter["rew_scale"]))
+        self._track("rew", assert_close(f"step {t} rew_buf", task.rew_buf, p.rew_buf, rows=ok, scale=p.inter["rew_scale"],
+                                        extra_atol=rot_reward_conditioning(p)))
         self._track("last_tip", assert_close(f"step {t} last_base_tip", task.last_base_tip_positions, p.last_base_tip_positions))
         self._track("last_jv", assert_close(f"step {t} last_joint_vel", task.last_joint_velocities,
                                             torch.cat([p.last_joint_velocities[g] for g in ("loco", "mani") if getattr(self.scene_cpu, g)], dim=0)))

