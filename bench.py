@@ -334,12 +334,16 @@ def cuda_arm(args):
             else:
                 pipe.policy(task.obs_buf, out=(pipe.mu, pipe.value))
 
-        for f in (pre_only, post_only, policy_only):
-            for i in range(3):
-                f(i)
-        ms_post = time_kernel(post_only, iters)
-        ms_pre = time_kernel(pre_only, iters)
-        ms_pol = time_kernel(policy_only, iters)
+        for i in range(3):
+            pre_only(i); post_only(i); policy_only(i)
+        # one full step per iteration, four events: pre | post | policy durations of the SAME sequence the step loop runs
+        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(iters)]
+        for i, (a0, a1, a2, a3) in enumerate(evs):
+            a0.record(); pre_only(i); a1.record(); post_only(i); a2.record(); policy_only(i); a3.record()
+        torch.cuda.synchronize()
+        ms_pre = sum(e[0].elapsed_time(e[1]) for e in evs) / iters
+        ms_post = sum(e[1].elapsed_time(e[2]) for e in evs) / iters
+        ms_pol = sum(e[2].elapsed_time(e[3]) for e in evs) / iters
         hbm, tf, src = measured_peaks()
         ach = n * B_POST / (ms_post * 1e-3) / 1e9
         ach_task = n * B_TASK / ((ms_post + ms_pre) * 1e-3) / 1e9

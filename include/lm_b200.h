@@ -148,6 +148,10 @@ int lm_task_step_parity(const LmTask* task);
  * (envs/vec_env_rlgames.py:42) fused into the producing kernel.  Off by default (obs_buf then holds
  * the reference task's unclamped values). */
 int lm_task_set_clamp_observations(LmTask* task, int on);
+/* post_step leaves behind the exclusive scan of the reset mask it just produced, so the next pre_step needs no
+ * extra pass over reset_buf.  Call this after writing reset_buf from outside the library (e.g. RLTask.reset(),
+ * rl_task.py:222-225): the next pre_step then rescans reset_buf first. */
+int lm_task_invalidate_reset_scan(LmTask* task);
 
 /* pre_physics_step (QPC:200-228 / QMP:213-236 / JLV:248-270) including reset_idx
  * (QPC:230-299 / JLV:272-377), rand_quaternions (utils/math.py:176-193) and take_action

@@ -73,6 +73,7 @@ SYMBOLS = {
     "lm_task_destroy": (None, [_vp]),
     "lm_task_step_parity": (C.c_int, [_vp]),
     "lm_task_set_clamp_observations": (C.c_int, [_vp, C.c_int]),
+    "lm_task_invalidate_reset_scan": (C.c_int, [_vp]),
     "lm_task_pre_step": (C.c_int, [_vp, C.POINTER(LmRobotViews), C.POINTER(LmRobotViews), _vp, C.POINTER(LmTaskBuffers), _vp, _vp, _vp]),
     "lm_task_reset_idx": (C.c_int, [_vp, C.POINTER(LmRobotViews), C.POINTER(LmRobotViews), _vp, C.POINTER(LmTaskBuffers), _vp, _i32, _vp, _vp]),
     "lm_task_post_step": (C.c_int, [_vp, C.POINTER(LmRobotViews), C.POINTER(LmRobotViews), _vp, C.POINTER(LmTaskBuffers), _vp]),

@@ -83,8 +83,9 @@ __device__ __forceinline__ float norm3_torch(float a, float b, float c) {
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void rot_from_quat_scipy(const Quat& q, float m[9]) {
   double w = q.w, x = q.x, y = q.y, z = q.z;
-  double n = sqrt(x * x + y * y + z * z + w * w);
-  x /= n; y /= n; z /= n; w /= n;
+  // SciPy divides by the norm; multiplying by rsqrt differs by <= 1 ulp of double, far below the fp32 cast
+  const double inv_n = rsqrt(x * x + y * y + z * z + w * w);
+  x *= inv_n; y *= inv_n; z *= inv_n; w *= inv_n;
   double x2 = x * x, y2 = y * y, z2 = z * z, w2 = w * w;
   double xy = x * y, zw = z * w, xz = x * z, yw = y * w, yz = y * z, xw = x * w;
   m[0] = (float)(x2 - y2 - z2 + w2); m[1] = (float)(2.0 * (xy - zw)); m[2] = (float)(2.0 * (xz + yw));
@@ -132,19 +133,19 @@ __device__ __forceinline__ void mat3_mul(const float a[9], const float b[9], flo
 // (1.18, cython backend) replaces a not-exactly-orthogonal input by its polar factor U V^T (SVD),
 // then applies the largest-of-(diag, trace) branch and normalises.  The polar factor is obtained
 // here by Newton iteration X <- (X + X^-T)/2, which converges quadratically from a matrix that is
-// orthogonal to ~1e-7 (three steps reach double round-off).  Returns wxyz with w >= 0
+// orthogonal to ~1e-7 (error 1e-7 -> 1e-14 -> 1e-28: two steps reach double round-off).  Returns wxyz with w >= 0
 // (math.py:52-54,78-80).
 __device__ __forceinline__ Quat quat_from_rot_scipy(const float m32[9]) {
   double a[9];
 #pragma unroll
   for (int i = 0; i < 9; ++i) a[i] = (double)m32[i];
 #pragma unroll 1
-  for (int it = 0; it < 3; ++it) {
+  for (int it = 0; it < 2; ++it) {
     double c[9];
     c[0] = a[4] * a[8] - a[5] * a[7]; c[1] = a[5] * a[6] - a[3] * a[8]; c[2] = a[3] * a[7] - a[4] * a[6];
     c[3] = a[2] * a[7] - a[1] * a[8]; c[4] = a[0] * a[8] - a[2] * a[6]; c[5] = a[1] * a[6] - a[0] * a[7];
     c[6] = a[1] * a[5] - a[2] * a[4]; c[7] = a[2] * a[3] - a[0] * a[5]; c[8] = a[0] * a[4] - a[1] * a[3];
-    double inv_det = 1.0 / (a[0] * c[0] + a[1] * c[1] + a[2] * c[2]);
+    const double inv_det = __drcp_rn(a[0] * c[0] + a[1] * c[1] + a[2] * c[2]);
 #pragma unroll
     for (int i = 0; i < 9; ++i) a[i] = 0.5 * (a[i] + c[i] * inv_det);
   }
@@ -165,8 +166,8 @@ __device__ __forceinline__ Quat quat_from_rot_scipy(const float m32[9]) {
   } else {
     qx = a[7] - a[5]; qy = a[2] - a[6]; qz = a[3] - a[1]; qw = 1.0 + tr;
   }
-  double n = sqrt(qx * qx + qy * qy + qz * qz + qw * qw);
-  Quat q{(float)(qw / n), (float)(qx / n), (float)(qy / n), (float)(qz / n)};
+  const double inv_n = rsqrt(qx * qx + qy * qy + qz * qz + qw * qw);
+  Quat q{(float)(qw * inv_n), (float)(qx * inv_n), (float)(qy * inv_n), (float)(qz * inv_n)};
   if (q.w < 0.0f) { q.w = -q.w; q.x = -q.x; q.y = -q.y; q.z = -q.z; }
   return q;
 }

@@ -197,16 +197,17 @@ __device__ __forceinline__ void reset_one_env(const KernelParams& kp, const PreA
     a.buf.reset_env_ids[rank] = e;
   }
 
+// K_pre: (1) reset mask -> rank -> compacted ascending id list (the `nonzero()` of QPC:206); (2) clamp + stash
+// actions, take_action.  The reset bodies themselves run in k_reset_apply over the compacted list, so the ~3 % of
+// envs that reset do not drag every warp through the (double-precision) goal resampling path.
 __global__ void __launch_bounds__(T) k_pre(const KernelParams kp, const PreArgs a) {
   const LmTaskParams& P = kp.p;
   const Tile tl = tile_of(kp, blockIdx.x);
   const int r = threadIdx.x;
   const int N = P.num_envs;
   float* ring_cur = a.buf.actions_ring + (size_t)a.parity * N * LM_NUM_ACT;
-  float* ring_last = a.buf.actions_ring + (size_t)(a.parity ^ 1) * N * LM_NUM_ACT;
   const LmRobotViews& V = tl.is_mani ? a.mani : a.loco;
 
-  // ---- reset mask + rank inside the tile
   __shared__ int warp_base[T / 32];
   int flag = 0;
   const int e = tl.e0 + r, hr = tl.hr0 + r;
@@ -214,12 +215,11 @@ __global__ void __launch_bounds__(T) k_pre(const KernelParams kp, const PreArgs 
   unsigned b = __ballot_sync(0xffffffffu, flag);
   if ((r & 31) == 0) warp_base[r >> 5] = __popc(b);
   __syncthreads();
-  int base = a.tile_offsets[blockIdx.x];
-  for (int w = 0; w < (r >> 5); ++w) base += warp_base[w];
-  const int rank = base + __popc(b & ((1u << (r & 31)) - 1u));
-
-  // ---- reset_idx for flagged envs
-  if (flag) reset_one_env(kp, a, V, ring_last, tl.is_mani, e, hr, rank);
+  if (flag) {
+    int base = a.tile_offsets[blockIdx.x];
+    for (int w = 0; w < (r >> 5); ++w) base += warp_base[w];
+    a.buf.reset_env_ids[base + __popc(b & ((1u << (r & 31)) - 1u))] = e;
+  }
 
   // ---- actions: clamp (vec_env_rlgames.py:60), stash as current_actions, take_action (robot.py:444-461)
   const int nflat = tl.n * LM_NUM_ACT;
@@ -259,6 +259,19 @@ __global__ void __launch_bounds__(T) k_pre(const KernelParams kp, const PreArgs 
   }
 }
 
+// reset_idx over the compacted list: thread k resets env reset_env_ids[k] with uniform row k (its goal index).
+// The grid is sized for the worst case (every env resets); blocks beyond num_reset exit immediately.
+__global__ void __launch_bounds__(T) k_reset_apply(const KernelParams kp, const PreArgs a) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= a.buf.num_reset[0]) return;
+  const int e = (int)a.buf.reset_env_ids[k];
+  const int second = (kp.p.kind == LM_KIND_COTRAIN) && e >= kp.d.half;
+  const int is_mani = (kp.p.kind == LM_KIND_MANI) || second;
+  const int hr = second ? e - kp.d.half : e;
+  float* ring_last = a.buf.actions_ring + (size_t)(a.parity ^ 1) * kp.p.num_envs * LM_NUM_ACT;
+  reset_one_env(kp, a, is_mani ? a.mani : a.loco, ring_last, is_mani, e, hr, k);
+}
+
 // direct reset_idx(env_ids) call (random_policy.py-style drivers): env k of the list consumes uniform row k
 __global__ void k_reset_idx(const KernelParams kp, const PreArgs a, const int64_t* __restrict__ env_ids, int count) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -273,24 +286,396 @@ __global__ void k_reset_idx(const KernelParams kp, const PreArgs a, const int64_
 }
 
 // ------------------------------------------------------------------------------------------------
-// K_post
+// K_post: per-env math shared by both tilings
 // ------------------------------------------------------------------------------------------------
 struct PostArgs {
   LmRobotViews loco, mani;
   const float* env_pos;
   LmTaskBuffers buf;
-  float* partials;                 // [num_tiles, STATS] fp32 + int32 mix (see below)
+  float* partials;                 // [num_tiles, STATS] fp32 per-CTA partial sums
   unsigned int* ticket;
+  int32_t* tile_offsets;           // by-product: exclusive scan of per-tile reset counts for the next pre_step
   int parity;
   int clamp_observations;          // store clamp(obs, ±clip_observations) (fused _process_data)
 };
 
-// smem carve (floats)
+struct EnvIn {
+  float jp[12], jv[12], last_jv[12], cur[12], last[12];
+  Vec3 O, Pw, lin, ang;            // env origin, world position of base | plate, velocities
+  Quat q, goal;                    // orientation of base | plate, goal
+  int64_t progress, reset, succ_prev, consec;
+};
+struct EnvOut {
+  float o[64];                     // observation row
+  Quat cur_q;                      // ground | plate quaternion in the robot frame (states row)
+  float rew;
+  int64_t progress, consec;
+  int reset, success, goal_reset;
+  float stats[STATS];
+};
+
+// tips: 4x3 world positions in, base-frame positions out (in place); knees: 8x3 world positions
+template <typename TipPtr>
+__device__ __forceinline__ void env_math(const KernelParams& kp, const int is_mani, const int clamp_obs, const EnvIn& in, TipPtr tips,
+                                         const float* knees, EnvOut& out) {
+  const LmTaskParams& P = kp.p;
+#pragma unroll
+  for (int i = 0; i < STATS; ++i) out.stats[i] = 0.0f;
+  // ---- finite-difference joint acceleration, action rate (robot.py:290; QPC:443,446)
+  float acc_sum = 0.0f, rate_sum = 0.0f;
+#pragma unroll
+  for (int j = 0; j < 12; ++j) {
+    const float acc = fdiv(sub(in.jv[j], in.last_jv[j]), P.time_interval);
+    acc_sum = add(acc_sum, mul(fabsf(acc), P.joint_acc_scale));
+    rate_sum = add(rate_sum, fabsf(sub(in.last[j], in.cur[j])));
+  }
+  const float jacc = acc_sum, arate = mul(rate_sum, P.action_rate_scale);
+
+  // ---- frame quantities per kind
+  const Vec3 O = in.O;
+  const Vec3 pl{sub(in.Pw.x, O.x), sub(in.Pw.y, O.y), sub(in.Pw.z, O.z)};      // local pose (robot.py:295 / rigid_object.py:54)
+  Vec3 pos, lin_o, ang_o;
+  Quat cur_q;
+  float body_height;
+  int corner_low = 0, knee_low = 0;
+  float R[9];
+  rot_from_quat_scipy(in.q, R);
+  if (!is_mani) {
+    pos = quat_rotate_t<true>(in.q, Vec3{-pl.x, -pl.y, -pl.z});                          // QPC:319
+    cur_q = quat_conj(in.q);                                                            // QPC:322
+    lin_o = quat_rotate_t<true>(in.q, Vec3{-in.lin.x, -in.lin.y, -in.lin.z});           // QPC:326
+    ang_o = quat_rotate_t<true>(in.q, Vec3{-in.ang.x, -in.ang.y, -in.ang.z});           // QPC:329
+    const Vec3 pinv = tf_inverse_translation(R, pl);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {                                                       // QPC:332-335
+      const Vec3 t = tf_inverse_apply(R, pinv, Vec3{sub(tips[3 * k], O.x), sub(tips[3 * k + 1], O.y), sub(tips[3 * k + 2], O.z)});
+      tips[3 * k] = t.x; tips[3 * k + 1] = t.y; tips[3 * k + 2] = t.z;
+      const float cz = add(row_dot(R + 6, 1, Vec3{P.corners[k][0], P.corners[k][1], P.corners[k][2]}), pl.z);   // QPC:574-579
+      corner_low |= cz < P.baseline_corner_height;
+    }
+    body_height = pl.z;                                                                 // QPC:569
+#pragma unroll
+    for (int k = 0; k < 8; ++k) knee_low |= sub(sub(knees[3 * k + 2], O.z), P.baseline_knee_height) <= 0.0f;   // QPC:585-587
+  } else {
+    const Vec3 p0inv{kp.d.p0inv[0], kp.d.p0inv[1], kp.d.p0inv[2]};
+    float R0[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) R0[i] = kp.d.R0[i];
+    pos = tf_inverse_apply(R0, p0inv, pl);                                              // QMP:326-329
+    float M[9];
+    mat3_mul<true>(R0, R, M);                                                           // QMP:332 (math.py:70-74)
+    cur_q = quat_from_rot_scipy(M);
+    const Quat q0{P.mani_default_quaternion[0], P.mani_default_quaternion[1], P.mani_default_quaternion[2], P.mani_default_quaternion[3]};
+    lin_o = quat_rotate_t<true>(q0, in.lin);                                            // QMP:338
+    ang_o = quat_rotate_t<true>(q0, in.ang);
+    const Vec3 pinv = tf_inverse_translation(R, pl);                                    // plate frame (QMP:576-603)
+    body_height = tf_inverse_apply_z(R, pinv.z, Vec3{P.mani_default_position[0], P.mani_default_position[1], P.mani_default_position[2]});
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const Vec3 t = tf_inverse_apply(R0, p0inv, Vec3{sub(tips[3 * k], O.x), sub(tips[3 * k + 1], O.y), sub(tips[3 * k + 2], O.z)});   // QMP:343
+      tips[3 * k] = t.x; tips[3 * k + 1] = t.y; tips[3 * k + 2] = t.z;
+      const float cz = tf_inverse_apply_z(R, pinv.z, Vec3{kp.d.corners_world[k][0], kp.d.corners_world[k][1], kp.d.corners_world[k][2]});
+      corner_low |= cz < P.baseline_corner_height;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float kz = tf_inverse_apply_z(R, pinv.z, Vec3{sub(knees[3 * k], O.x), sub(knees[3 * k + 1], O.y), sub(knees[3 * k + 2], O.z)});
+      knee_low |= sub(kz, P.baseline_knee_height) <= 0.0f;
+    }
+  }
+
+  // ---- orientation error (QPC:345-350,430-432)
+  Quat diff = quat_mul(cur_q, quat_conj(in.goal));
+  const float nrm = norm3_torch(diff.x, diff.y, diff.z);
+  const float rot_dist = mul(2.0f, (float)asin((double)fminf(nrm, 1.0f)));
+  if (diff.w < 0.0f) { diff.w = -diff.w; diff.x = -diff.x; diff.y = -diff.y; diff.z = -diff.z; }
+  const Vec3 up = quat_rotate_t<false>(cur_q, Vec3{0.0f, 0.0f, 1.0f});                  // quat_axis(q, 2)
+
+  // ---- observation row (QPC:358-371)
+  float* o = out.o;
+  o[0] = mul(P.position_scale, pos.x); o[1] = mul(P.position_scale, pos.y); o[2] = mul(P.position_scale, pos.z);
+  o[3] = up.x; o[4] = up.y; o[5] = up.z;
+  o[6] = diff.w; o[7] = diff.x; o[8] = diff.y; o[9] = diff.z;
+  o[10] = mul(P.linear_vel_scale, lin_o.x); o[11] = mul(P.linear_vel_scale, lin_o.y); o[12] = mul(P.linear_vel_scale, lin_o.z);
+  o[13] = mul(P.angular_vel_scale, ang_o.x); o[14] = mul(P.angular_vel_scale, ang_o.y); o[15] = mul(P.angular_vel_scale, ang_o.z);
+#pragma unroll
+  for (int j = 0; j < 12; ++j) {
+    o[16 + j] = mul(P.joint_position_scale, in.jp[j]);
+    o[28 + j] = mul(P.joint_velocity_scale, in.jv[j]);
+    o[40 + j] = in.cur[j];
+    o[52 + j] = in.last[j];
+  }
+  if (clamp_obs) {
+#pragma unroll
+    for (int j = 0; j < 64; ++j) o[j] = fminf(fmaxf(o[j], -P.clip_observations), P.clip_observations);
+  }
+  out.cur_q = cur_q;
+
+  // ---- reward (QPC:432-457,506-515)
+  const float rot_rew = mul(fdiv(1.0f, add(fabsf(rot_dist), P.rot_eps)), P.quaternion_scale);
+  const float trans = mul(norm2_torch(pos.x, pos.y), P.translation_scale);
+  const int goal_reset = in.consec > (int64_t)P.max_consecutive_successes;               // counter BEFORE update (QPC:449)
+  const float bonus = mul(P.consecutive_success_reward, (float)goal_reset);
+  const int success = fabsf(rot_dist) <= P.success_thresh;
+  int brk = 0, rst = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {                                                         // QPC:466-504 / JLV:574-597
+    const float d = fabsf(sub(in.jp[5 + 2 * k], in.jp[4 + 2 * k]));
+    brk |= (d < P.min_joint_23_diff) | (d > P.max_joint_23_diff);
+    rst |= (d < P.reset_min_joint_23_diff) | (d > P.reset_max_joint_23_diff);
+    const bool mirrored = P.joint1_mirrored && (k == 1 || k == 2);
+    const float lo = mirrored ? -P.max_joint_1_pos : P.min_joint_1_pos, hi = mirrored ? -P.min_joint_1_pos : P.max_joint_1_pos;
+    const float rlo = mirrored ? -P.reset_max_joint_1_pos : P.reset_min_joint_1_pos;
+    const float rhi = mirrored ? -P.reset_min_joint_1_pos : P.reset_max_joint_1_pos;
+    brk |= (in.jp[k] < lo) | (in.jp[k] > hi);
+    rst |= (in.jp[k] < rlo) | (in.jp[k] > rhi);
+  }
+  const float limit_pen = mul(P.joint_limit_penalty, (float)brk);
+  float total = add(add(add(add(add(rot_rew, trans), jacc), arate), bonus), limit_pen);
+
+  // ---- consecutive-success state machine (QPC:534-545)
+  int64_t consec = in.consec;
+  const int both = success && (in.succ_prev != 0);
+  if (!both) consec = 0;
+  if (both) consec += 1;
+  if (in.succ_prev == 0 && success) consec = 1;
+
+  // ---- termination (QPC:562-616)
+  int rs = in.reset != 0;
+  rs |= pos.z > 0.0f;
+  rs |= body_height <= P.baseline_height;
+  rs |= corner_low | knee_low | rst;
+  const float fall = mul(P.fall_penalty, (float)rs);
+  total = add(total, fall);
+  rs |= goal_reset;
+  const int64_t progress = in.progress + 1;                                             // rl_task.py:251
+  rs |= progress >= (int64_t)(P.max_episode_length - 1);
+
+  out.rew = total; out.progress = progress; out.consec = consec; out.reset = rs; out.success = success; out.goal_reset = goal_reset;
+  out.stats[0] = rot_rew; out.stats[1] = trans; out.stats[2] = jacc; out.stats[3] = arate; out.stats[4] = bonus;
+  out.stats[5] = limit_pen; out.stats[6] = fall;
+  out.stats[7] = isnan(total) ? 1.0f : 0.0f;
+  out.stats[8] = total < -50.0f ? 1.0f : 0.0f;
+  out.stats[9] = (float)goal_reset;
+  out.stats[10] = (float)rs;
+}
+
+__device__ __forceinline__ void store_flags(const LmTaskBuffers& b, int e, const EnvOut& out) {
+  b.rew_buf[e] = out.rew;
+  b.progress_buf[e] = out.progress;
+  b.reset_buf[e] = out.reset;
+  b.successes[e] = out.success;
+  b.consecutive_successes[e] = out.consec;
+  b.goal_reset_buf[e] = out.goal_reset;
+}
+
+// per-CTA partial sums -> partials[tile]; the last CTA turns them into extras / counters / the next reset scan
+// (QPC:560,610,619-633 / JLV:758-802)
+template <int kThreads>
+__device__ __forceinline__ void finish_stats(const KernelParams& kp, const PostArgs& a, const float stats[STATS],
+                                             float (*red_f)[STATS], int* is_last, double (*part)[kThreads / STATS][STATS],
+                                             double (*tot)[STATS], int* scan_s) {
+  const LmTaskParams& P = kp.p;
+  const int r = threadIdx.x, N = P.num_envs;
+#pragma unroll
+  for (int i = 0; i < 11; ++i) {
+    float v = stats[i];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    if ((r & 31) == 0) red_f[r >> 5][i] = v;
+  }
+  __syncthreads();
+  if (r < STATS) {
+    float v = 0.0f;
+    if (r < 11) {
+#pragma unroll
+      for (int w = 0; w < kThreads / 32; ++w) v += red_f[w][r];
+    }
+    a.partials[(size_t)blockIdx.x * STATS + r] = v;
+  }
+  __threadfence();
+  __syncthreads();
+  if (r == 0) *is_last = atomicAdd(a.ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!*is_last) return;
+  __threadfence();
+  {
+    const int i = r % STATS, g = r / STATS;
+    double s_l = 0.0, s_m = 0.0;
+    const int tph = kp.d.tiles_per_half;
+    for (int t = g; t < kp.d.num_tiles; t += kThreads / STATS) {
+      const double v = (double)__ldcg(a.partials + (size_t)t * STATS + i);
+      const bool second = (P.kind == LM_KIND_COTRAIN) && t >= tph;
+      if (second) s_m += v; else s_l += v;
+    }
+    part[0][g][i] = s_l; part[1][g][i] = s_m;
+  }
+  __syncthreads();
+  if (r < STATS) {
+    double s_l = 0.0, s_m = 0.0;
+    for (int g = 0; g < kThreads / STATS; ++g) { s_l += part[0][g][r]; s_m += part[1][g][r]; }
+    tot[0][r] = s_l + s_m; tot[1][r] = s_l; tot[2][r] = s_m;
+  }
+  // exclusive scan of per-tile reset counts (partials[t][10]) -> tile_offsets, num_reset: the next pre_step's reset ranks
+  const int nt = kp.d.num_tiles;
+  const int per = (nt + kThreads - 1) / kThreads;
+  const int lo = r * per, hi = min(nt, lo + per);
+  int s = 0;
+  for (int i = lo; i < hi; ++i) s += (int)__ldcg(a.partials + (size_t)i * STATS + 10);
+  scan_s[r] = s;
+  __syncthreads();
+  if (r == 0) {
+    int acc = 0;
+    for (int i = 0; i < kThreads; ++i) { const int v = scan_s[i]; scan_s[i] = acc; acc += v; }
+    a.buf.num_reset[0] = acc;
+    if (P.kind == LM_KIND_LOCO) a.buf.num_reset[1] = acc;
+    if (P.kind == LM_KIND_MANI) a.buf.num_reset[1] = 0;
+    float* ex = a.buf.extras;
+    const double inv_n = 1.0 / (double)N;
+    for (int i = 0; i < 7; ++i) ex[i] = (float)(tot[0][i] * inv_n);
+    ex[LM_EXTRA_NAN_COUNT] = (float)tot[0][7];
+    ex[LM_EXTRA_BELOW_M50_COUNT] = (float)tot[0][8];
+    int64_t* c = a.buf.counters;
+    const int groups = (P.kind == LM_KIND_COTRAIN) ? 3 : 1;
+    for (int g = 0; g < groups; ++g) {
+      int64_t& ns = c[2 * g];
+      int64_t& nr = c[2 * g + 1];
+      if (nr > (int64_t)P.max_reset_counts) {
+        ex[LM_EXTRA_SUCCESS_RATE + g] = (float)ns / (float)nr;
+        ns = 0; nr = 0;
+      }
+    }
+    for (int g = 0; g < groups; ++g) {
+      c[2 * g] += (int64_t)llrint(tot[g][9]);
+      c[2 * g + 1] += (int64_t)llrint(tot[g][10]);
+    }
+    *a.ticket = 0;
+  }
+  __syncthreads();
+  int acc = scan_s[r];
+  for (int i = lo; i < hi; ++i) {
+    if (P.kind == LM_KIND_COTRAIN && i == kp.d.tiles_per_half) a.buf.num_reset[1] = acc;
+    a.tile_offsets[i] = acc;
+    acc += (int)__ldcg(a.partials + (size_t)i * STATS + 10);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K_post, lean tiling (states alias obs: every co-train task).  Only the arrays whose row stride defeats
+// coalescing (20-wide DOF rows, 12-wide tip rows, 24-wide knee rows) are staged through shared memory by
+// TMA; 16-byte-friendly rows are loaded straight into registers while the bulk copies fly.  39 KB of
+// shared memory per CTA -> 4 resident CTAs (16 warps) per SM to hide the double-precision latency chains.
+// ------------------------------------------------------------------------------------------------
+struct LeanSmem {
+  static constexpr int kDofPos = 0;
+  static constexpr int kDofVel = kDofPos + T * 20;
+  static constexpr int kTips = kDofVel + T * 20;
+  static constexpr int kKnees = kTips + T * 12;
+  static constexpr int kEnd = kKnees + T * 24;
+  static constexpr int kBytes = kEnd * 4 + 64;
+};
+
+__device__ __forceinline__ void ld12(const float* p, float v[12]) {
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const float4 x = reinterpret_cast<const float4*>(p)[k];
+    v[4 * k] = x.x; v[4 * k + 1] = x.y; v[4 * k + 2] = x.z; v[4 * k + 3] = x.w;
+  }
+}
+__device__ __forceinline__ void st12(float* p, const float v[12]) {
+#pragma unroll
+  for (int k = 0; k < 3; ++k) reinterpret_cast<float4*>(p)[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+}
+__device__ __forceinline__ Vec3 ld3(const float* p) { return Vec3{p[0], p[1], p[2]}; }
+
+__global__ void __launch_bounds__(T, 4) k_post_lean(const KernelParams kp, const PostArgs a) {
+  extern __shared__ __align__(128) float sm[];
+  __shared__ uint64_t bar;
+  __shared__ float red_f[T / 32][STATS];
+  __shared__ int is_last;
+  __shared__ double part[2][T / STATS][STATS];
+  __shared__ double tot[3][STATS];
+  __shared__ int scan_s[T];
+  const LmTaskParams& P = kp.p;
+  const Tile tl = tile_of(kp, blockIdx.x);
+  const int r = threadIdx.x;
+  const int N = P.num_envs;
+  const LmRobotViews& V = tl.is_mani ? a.mani : a.loco;
+  const float* ring_cur = a.buf.actions_ring + (size_t)a.parity * N * LM_NUM_ACT;
+  const float* ring_last = a.buf.actions_ring + (size_t)(a.parity ^ 1) * N * LM_NUM_ACT;
+  const int n = tl.n, h0 = tl.hr0, e0 = tl.e0;
+
+  if (r == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+  __syncthreads();
+  Stager st{&bar, 0u, (n % 4) == 0};
+  st.load(sm + LeanSmem::kDofPos, V.dof_pos + (size_t)h0 * 20, n * 20);
+  st.load(sm + LeanSmem::kDofVel, V.dof_vel + (size_t)h0 * 20, n * 20);
+  st.load(sm + LeanSmem::kTips, V.tip_pos + (size_t)h0 * 12, n * 12);
+  st.load(sm + LeanSmem::kKnees, V.knee_pos + (size_t)h0 * 24, n * 24);
+  if (st.use_tma && r == 0) mbar_expect_tx(&bar, st.bytes);
+
+  EnvIn in;
+  EnvOut out;
+  const bool valid = r < n;
+  const int e = e0 + (valid ? r : 0), hr = h0 + (valid ? r : 0);
+  {
+    // register loads overlap the bulk copies
+    ld12(ring_cur + (size_t)e * 12, in.cur);
+    ld12(ring_last + (size_t)e * 12, in.last);
+    ld12(a.buf.last_joint_vel + (size_t)e * 12, in.last_jv);
+    const float4 g4 = *reinterpret_cast<const float4*>(a.buf.goal_quaternions + (size_t)e * 4);
+    const float4 q4 = *reinterpret_cast<const float4*>((tl.is_mani ? V.plate_quat : V.root_quat) + (size_t)hr * 4);
+    in.goal = Quat{g4.x, g4.y, g4.z, g4.w};
+    in.q = Quat{q4.x, q4.y, q4.z, q4.w};
+    in.O = ld3(a.env_pos + (size_t)hr * 3);
+    in.Pw = ld3((tl.is_mani ? V.plate_pos : V.root_pos) + (size_t)hr * 3);
+    in.lin = ld3((tl.is_mani ? V.plate_lin_vel : V.root_lin_vel) + (size_t)hr * 3);
+    in.ang = ld3((tl.is_mani ? V.plate_ang_vel : V.root_ang_vel) + (size_t)hr * 3);
+    in.progress = a.buf.progress_buf[e];
+    in.reset = a.buf.reset_buf[e];
+    in.succ_prev = a.buf.successes[e];
+    in.consec = a.buf.consecutive_successes[e];
+  }
+  if (st.use_tma) mbar_wait(&bar, 0); else __syncthreads();
+  {
+    const int rr = valid ? r : 0;
+    if (kp.d.dof_identity) {
+      ld12(sm + LeanSmem::kDofPos + rr * 20, in.jp);
+      ld12(sm + LeanSmem::kDofVel + rr * 20, in.jv);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 12; ++j) {
+        in.jp[j] = sm[LeanSmem::kDofPos + rr * 20 + P.dof_index[j]];
+        in.jv[j] = sm[LeanSmem::kDofVel + rr * 20 + P.dof_index[j]];
+      }
+    }
+    float tips[12];
+    ld12(sm + LeanSmem::kTips + rr * 12, tips);
+    env_math(kp, tl.is_mani, a.clamp_observations, in, tips, sm + LeanSmem::kKnees + rr * 24, out);
+    if (valid) {
+      float4* og = reinterpret_cast<float4*>(a.buf.obs_buf + (size_t)e * LM_NUM_OBS);
+#pragma unroll
+      for (int k = 0; k < 16; ++k) og[k] = make_float4(out.o[4 * k], out.o[4 * k + 1], out.o[4 * k + 2], out.o[4 * k + 3]);
+      st12(a.buf.last_joint_vel + (size_t)e * 12, in.jv);                               // robot.py:291
+      st12(a.buf.last_base_tip + (size_t)e * 12, tips);                                 // QPC:426
+      store_flags(a.buf, e, out);
+    } else {
+#pragma unroll
+      for (int i = 0; i < STATS; ++i) out.stats[i] = 0.0f;
+    }
+  }
+  finish_stats<T>(kp, a, out.stats, red_f, &is_last, part, tot, scan_s);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K_post, full tiling (single-task files with the 93-wide states_buf, QPC:406-423): everything staged in
+// shared memory so the 93-wide rows can be gathered and stored coalesced.
+// ------------------------------------------------------------------------------------------------
 struct PostSmem {
   static constexpr int kDofPos = 0;
   static constexpr int kDofVel = kDofPos + T * 20;
   static constexpr int kPos = kDofVel + T * 20;      // root_pos | plate_pos
-  static constexpr int kQuat = kPos + T * 3 + (T * 3) % 4;
+  static constexpr int kQuat = kPos + T * 3;
   static constexpr int kLin = kQuat + T * 4;
   static constexpr int kAng = kLin + T * 3;
   static constexpr int kTips = kAng + T * 3;
@@ -308,7 +693,7 @@ struct PostSmem {
 };
 static_assert(T % 4 == 0, "tile spans must stay 16-byte aligned");
 
-// column c of the 93-wide states row -> (smem region, row stride, column, scale id)   QPC:406-423
+// column c of the 93-wide states row                                                         QPC:406-423
 __device__ __forceinline__ float states_elem(const LmTaskParams& P, const float* sm, int r, int c) {
   const float* obs = sm + PostSmem::kObs + r * OBS_PAD;
   if (c < 3) return obs[c];                                   // scaled position
@@ -328,6 +713,9 @@ __global__ void __launch_bounds__(T, 2) k_post(const KernelParams kp, const Post
   __shared__ uint64_t bar;
   __shared__ float red_f[T / 32][STATS];
   __shared__ int is_last;
+  __shared__ double part[2][T / STATS][STATS];
+  __shared__ double tot[3][STATS];
+  __shared__ int scan_s[T];
   const LmTaskParams& P = kp.p;
   const Tile tl = tile_of(kp, blockIdx.x);
   const int r = threadIdx.x;
@@ -337,7 +725,6 @@ __global__ void __launch_bounds__(T, 2) k_post(const KernelParams kp, const Post
   const float* ring_last = a.buf.actions_ring + (size_t)(a.parity ^ 1) * N * LM_NUM_ACT;
   const bool full_states = (P.num_states == LM_NUM_STATES_FULL) && a.buf.states_buf != nullptr;
 
-  // ---- stage the tile (TMA bulk loads, one mbarrier)
   if (r == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
   __syncthreads();
   Stager st{&bar, 0u, (tl.n % 4) == 0};
@@ -356,233 +743,53 @@ __global__ void __launch_bounds__(T, 2) k_post(const KernelParams kp, const Post
   st.load(sm + PostSmem::kLast, ring_last + (size_t)e0 * 12, n * 12);
   st.load(sm + PostSmem::kLastJv, a.buf.last_joint_vel + (size_t)e0 * 12, n * 12);
   if (full_states) st.load(sm + PostSmem::kLastTip, a.buf.last_base_tip + (size_t)e0 * 12, n * 12);
-  if (st.use_tma) {
-    if (r == 0) mbar_expect_tx(&bar, st.bytes);
-  }
-  // int64 flags straight from global while the bulk copies fly
-  int64_t progress = 0, reset = 0, succ_prev = 0, consec = 0;
-  if (r < n) {
-    progress = a.buf.progress_buf[e0 + r];
-    reset = a.buf.reset_buf[e0 + r];
-    succ_prev = a.buf.successes[e0 + r];
-    consec = a.buf.consecutive_successes[e0 + r];
+  if (st.use_tma && r == 0) mbar_expect_tx(&bar, st.bytes);
+  EnvIn in;
+  EnvOut out;
+  in.progress = in.reset = in.succ_prev = in.consec = 0;
+  if (r < n) {   // int64 flags straight from global while the bulk copies fly
+    in.progress = a.buf.progress_buf[e0 + r];
+    in.reset = a.buf.reset_buf[e0 + r];
+    in.succ_prev = a.buf.successes[e0 + r];
+    in.consec = a.buf.consecutive_successes[e0 + r];
   }
   if (st.use_tma) mbar_wait(&bar, 0); else __syncthreads();
 
-  float stats[STATS];
 #pragma unroll
-  for (int i = 0; i < STATS; ++i) stats[i] = 0.0f;
-
+  for (int i = 0; i < STATS; ++i) out.stats[i] = 0.0f;
   if (r < n) {
-    // ---- joint state: gather 12 actuated DOFs, finite-difference acceleration (robot.py:288-291)
-    float jp[12], jv[12];
     if (kp.d.dof_identity) {
-      const float4* p4 = reinterpret_cast<const float4*>(sm + PostSmem::kDofPos + r * 20);
-      const float4* v4 = reinterpret_cast<const float4*>(sm + PostSmem::kDofVel + r * 20);
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        float4 x = p4[k], y = v4[k];
-        jp[4 * k] = x.x; jp[4 * k + 1] = x.y; jp[4 * k + 2] = x.z; jp[4 * k + 3] = x.w;
-        jv[4 * k] = y.x; jv[4 * k + 1] = y.y; jv[4 * k + 2] = y.z; jv[4 * k + 3] = y.w;
-      }
+      ld12(sm + PostSmem::kDofPos + r * 20, in.jp);
+      ld12(sm + PostSmem::kDofVel + r * 20, in.jv);
     } else {
 #pragma unroll
       for (int j = 0; j < 12; ++j) {
-        jp[j] = sm[PostSmem::kDofPos + r * 20 + P.dof_index[j]];
-        jv[j] = sm[PostSmem::kDofVel + r * 20 + P.dof_index[j]];
+        in.jp[j] = sm[PostSmem::kDofPos + r * 20 + P.dof_index[j]];
+        in.jv[j] = sm[PostSmem::kDofVel + r * 20 + P.dof_index[j]];
       }
     }
-    float cur[12], last[12];
-    {
-      const float4* c4 = reinterpret_cast<const float4*>(sm + PostSmem::kCur + r * 12);
-      const float4* l4 = reinterpret_cast<const float4*>(sm + PostSmem::kLast + r * 12);
-      float4* j4 = reinterpret_cast<float4*>(sm + PostSmem::kLastJv + r * 12);
-      float acc_sum = 0.0f, rate_sum = 0.0f;
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        float4 c = c4[k], l = l4[k], pv = j4[k];
-        cur[4 * k] = c.x; cur[4 * k + 1] = c.y; cur[4 * k + 2] = c.z; cur[4 * k + 3] = c.w;
-        last[4 * k] = l.x; last[4 * k + 1] = l.y; last[4 * k + 2] = l.z; last[4 * k + 3] = l.w;
-        const float prev[4] = {pv.x, pv.y, pv.z, pv.w};
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int j = 4 * k + q;
-          const float acc = fdiv(sub(jv[j], prev[q]), P.time_interval);
-          acc_sum = add(acc_sum, mul(fabsf(acc), P.joint_acc_scale));                    // QPC:443
-          rate_sum = add(rate_sum, fabsf(sub(last[j], cur[j])));                        // QPC:446
-        }
-        j4[k] = make_float4(jv[4 * k], jv[4 * k + 1], jv[4 * k + 2], jv[4 * k + 3]);    // last_joint_vel <- jv (robot.py:291)
-      }
-      stats[2] = acc_sum;
-      stats[3] = mul(rate_sum, P.action_rate_scale);
-    }
-
-    // ---- frame quantities per kind
-    const Vec3 O{sm[PostSmem::kEnvPos + r * 3], sm[PostSmem::kEnvPos + r * 3 + 1], sm[PostSmem::kEnvPos + r * 3 + 2]};
-    const Vec3 Pw{sm[PostSmem::kPos + r * 3], sm[PostSmem::kPos + r * 3 + 1], sm[PostSmem::kPos + r * 3 + 2]};
+    ld12(sm + PostSmem::kCur + r * 12, in.cur);
+    ld12(sm + PostSmem::kLast + r * 12, in.last);
+    ld12(sm + PostSmem::kLastJv + r * 12, in.last_jv);
+    in.O = ld3(sm + PostSmem::kEnvPos + r * 3);
+    in.Pw = ld3(sm + PostSmem::kPos + r * 3);
+    in.lin = ld3(sm + PostSmem::kLin + r * 3);
+    in.ang = ld3(sm + PostSmem::kAng + r * 3);
     const float4 qv = *reinterpret_cast<const float4*>(sm + PostSmem::kQuat + r * 4);
-    const Quat q{qv.x, qv.y, qv.z, qv.w};
-    const Vec3 lin{sm[PostSmem::kLin + r * 3], sm[PostSmem::kLin + r * 3 + 1], sm[PostSmem::kLin + r * 3 + 2]};
-    const Vec3 ang{sm[PostSmem::kAng + r * 3], sm[PostSmem::kAng + r * 3 + 1], sm[PostSmem::kAng + r * 3 + 2]};
-    const Vec3 pl{sub(Pw.x, O.x), sub(Pw.y, O.y), sub(Pw.z, O.z)};      // local pose (robot.py:295 / rigid_object.py:54)
-    float* tips = sm + PostSmem::kTips + r * 12;
-    const float* knees = sm + PostSmem::kKnees + r * 24;
-    Vec3 pos, lin_o, ang_o;
-    Quat cur_q;
-    float body_height;
-    int corner_low = 0, knee_low = 0;
-    float R[9];
-    rot_from_quat_scipy(q, R);
-    if (!tl.is_mani) {
-      pos = quat_rotate_t<true>(q, Vec3{-pl.x, -pl.y, -pl.z});                            // QPC:319
-      cur_q = quat_conj(q);                                                              // QPC:322
-      lin_o = quat_rotate_t<true>(q, Vec3{-lin.x, -lin.y, -lin.z});                      // QPC:326
-      ang_o = quat_rotate_t<true>(q, Vec3{-ang.x, -ang.y, -ang.z});                      // QPC:329
-      const Vec3 pinv = tf_inverse_translation(R, pl);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {                                                       // QPC:332-335
-        const Vec3 t = tf_inverse_apply(R, pinv, Vec3{sub(tips[3 * k], O.x), sub(tips[3 * k + 1], O.y), sub(tips[3 * k + 2], O.z)});
-        tips[3 * k] = t.x; tips[3 * k + 1] = t.y; tips[3 * k + 2] = t.z;
-        const float cz = add(row_dot(R + 6, 1, Vec3{P.corners[k][0], P.corners[k][1], P.corners[k][2]}), pl.z);   // QPC:574-579
-        corner_low |= cz < P.baseline_corner_height;
-      }
-      body_height = pl.z;                                                                 // QPC:569
-#pragma unroll
-      for (int k = 0; k < 8; ++k) knee_low |= sub(sub(knees[3 * k + 2], O.z), P.baseline_knee_height) <= 0.0f;   // QPC:585-587
-    } else {
-      const Vec3 p0inv{kp.d.p0inv[0], kp.d.p0inv[1], kp.d.p0inv[2]};
-      float R0[9];
-#pragma unroll
-      for (int i = 0; i < 9; ++i) R0[i] = kp.d.R0[i];
-      pos = tf_inverse_apply(R0, p0inv, pl);                                              // QMP:326-329
-      float M[9];
-      mat3_mul<true>(R0, R, M);                                                      // QMP:332 (math.py:70-74)
-      cur_q = quat_from_rot_scipy(M);
-      const Quat q0{P.mani_default_quaternion[0], P.mani_default_quaternion[1], P.mani_default_quaternion[2], P.mani_default_quaternion[3]};
-      lin_o = quat_rotate_t<true>(q0, lin);                                               // QMP:338
-      ang_o = quat_rotate_t<true>(q0, ang);
-      const Vec3 pinv = tf_inverse_translation(R, pl);                                    // plate frame (QMP:576-603)
-      body_height = tf_inverse_apply_z(R, pinv.z, Vec3{P.mani_default_position[0], P.mani_default_position[1], P.mani_default_position[2]});
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const Vec3 t = tf_inverse_apply(R0, p0inv, Vec3{sub(tips[3 * k], O.x), sub(tips[3 * k + 1], O.y), sub(tips[3 * k + 2], O.z)});   // QMP:343
-        tips[3 * k] = t.x; tips[3 * k + 1] = t.y; tips[3 * k + 2] = t.z;
-        const float cz = tf_inverse_apply_z(R, pinv.z, Vec3{kp.d.corners_world[k][0], kp.d.corners_world[k][1], kp.d.corners_world[k][2]});
-        corner_low |= cz < P.baseline_corner_height;
-      }
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const float kz = tf_inverse_apply_z(R, pinv.z, Vec3{sub(knees[3 * k], O.x), sub(knees[3 * k + 1], O.y), sub(knees[3 * k + 2], O.z)});
-        knee_low |= sub(kz, P.baseline_knee_height) <= 0.0f;
-      }
-    }
-
-    // ---- orientation error (QPC:345-350,430-432)
     const float4 gv = *reinterpret_cast<const float4*>(sm + PostSmem::kGoal + r * 4);
-    const Quat goal{gv.x, gv.y, gv.z, gv.w};
-    Quat diff = quat_mul(cur_q, quat_conj(goal));
-    const float nrm = norm3_torch(diff.x, diff.y, diff.z);
-    const float rot_dist = mul(2.0f, (float)asin((double)fminf(nrm, 1.0f)));
-    if (diff.w < 0.0f) { diff.w = -diff.w; diff.x = -diff.x; diff.y = -diff.y; diff.z = -diff.z; }
-    const Vec3 up = quat_rotate_t<false>(cur_q, Vec3{0.0f, 0.0f, 1.0f});                  // quat_axis(q, 2)
-
-    // ---- observation row (QPC:358-371)
-    float o[64];
-    o[0] = mul(P.position_scale, pos.x); o[1] = mul(P.position_scale, pos.y); o[2] = mul(P.position_scale, pos.z);
-    o[3] = up.x; o[4] = up.y; o[5] = up.z;
-    o[6] = diff.w; o[7] = diff.x; o[8] = diff.y; o[9] = diff.z;
-    o[10] = mul(P.linear_vel_scale, lin_o.x); o[11] = mul(P.linear_vel_scale, lin_o.y); o[12] = mul(P.linear_vel_scale, lin_o.z);
-    o[13] = mul(P.angular_vel_scale, ang_o.x); o[14] = mul(P.angular_vel_scale, ang_o.y); o[15] = mul(P.angular_vel_scale, ang_o.z);
-#pragma unroll
-    for (int j = 0; j < 12; ++j) {
-      o[16 + j] = mul(P.joint_position_scale, jp[j]);
-      o[28 + j] = mul(P.joint_velocity_scale, jv[j]);
-      o[40 + j] = cur[j];
-      o[52 + j] = last[j];
-    }
-    if (a.clamp_observations) {
-#pragma unroll
-      for (int j = 0; j < 64; ++j) o[j] = fminf(fmaxf(o[j], -P.clip_observations), P.clip_observations);
-    }
+    in.q = Quat{qv.x, qv.y, qv.z, qv.w};
+    in.goal = Quat{gv.x, gv.y, gv.z, gv.w};
+    env_math(kp, tl.is_mani, a.clamp_observations, in, sm + PostSmem::kTips + r * 12, sm + PostSmem::kKnees + r * 24, out);
+    st12(sm + PostSmem::kLastJv + r * 12, in.jv);                                        // last_joint_vel <- jv (robot.py:291)
     float4* orow = reinterpret_cast<float4*>(sm + PostSmem::kObs + r * OBS_PAD);
 #pragma unroll
-    for (int k = 0; k < 16; ++k) orow[k] = make_float4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
-    if (full_states) {
-      float* cq = sm + PostSmem::kCurQ + r * 4;
-      cq[0] = cur_q.w; cq[1] = cur_q.x; cq[2] = cur_q.y; cq[3] = cur_q.z;
-    }
-
-    // ---- reward (QPC:432-457,506-515)
-    const float rot_rew = mul(fdiv(1.0f, add(fabsf(rot_dist), P.rot_eps)), P.quaternion_scale);
-    const float trans = mul(norm2_torch(pos.x, pos.y), P.translation_scale);
-    const int goal_reset = consec > (int64_t)P.max_consecutive_successes;                 // counter BEFORE update (QPC:449)
-    const float bonus = mul(P.consecutive_success_reward, (float)goal_reset);
-    const int success = fabsf(rot_dist) <= P.success_thresh;
-    int brk = 0, rst = 0;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {                                                         // QPC:466-504 / JLV:574-597
-      const float d = fabsf(sub(jp[5 + 2 * k], jp[4 + 2 * k]));
-      brk |= (d < P.min_joint_23_diff) | (d > P.max_joint_23_diff);
-      rst |= (d < P.reset_min_joint_23_diff) | (d > P.reset_max_joint_23_diff);
-      const bool mirrored = P.joint1_mirrored && (k == 1 || k == 2);
-      const float lo = mirrored ? -P.max_joint_1_pos : P.min_joint_1_pos, hi = mirrored ? -P.min_joint_1_pos : P.max_joint_1_pos;
-      const float rlo = mirrored ? -P.reset_max_joint_1_pos : P.reset_min_joint_1_pos;
-      const float rhi = mirrored ? -P.reset_min_joint_1_pos : P.reset_max_joint_1_pos;
-      brk |= (jp[k] < lo) | (jp[k] > hi);
-      rst |= (jp[k] < rlo) | (jp[k] > rhi);
-    }
-    const float limit_pen = mul(P.joint_limit_penalty, (float)brk);
-    float total = add(add(add(add(add(rot_rew, trans), stats[2]), stats[3]), bonus), limit_pen);
-
-    // ---- consecutive-success state machine (QPC:534-545)
-    const int both = success && (succ_prev != 0);
-    if (!both) consec = 0;
-    if (both) consec += 1;
-    if (succ_prev == 0 && success) consec = 1;
-
-    // ---- termination (QPC:562-616)
-    int rs = reset != 0;
-    rs |= pos.z > 0.0f;
-    rs |= body_height <= P.baseline_height;
-    rs |= corner_low | knee_low | rst;
-    const float fall = mul(P.fall_penalty, (float)rs);
-    total = add(total, fall);
-    rs |= goal_reset;
-    progress += 1;                                                                        // rl_task.py:251
-    rs |= progress >= (int64_t)(P.max_episode_length - 1);
-
-    const int e = e0 + r;
-    a.buf.rew_buf[e] = total;
-    a.buf.progress_buf[e] = progress;
-    a.buf.reset_buf[e] = rs;
-    a.buf.successes[e] = success;
-    a.buf.consecutive_successes[e] = consec;
-    a.buf.goal_reset_buf[e] = goal_reset;
-
-    stats[0] = rot_rew; stats[1] = trans; stats[4] = bonus; stats[5] = limit_pen; stats[6] = fall;
-    stats[7] = isnan(total) ? 1.0f : 0.0f;
-    stats[8] = total < -50.0f ? 1.0f : 0.0f;
-    stats[9] = (float)goal_reset;
-    stats[10] = (float)rs;
-  }
-
-  // ---- per-CTA partial sums for extras (QPC:560,610,630-631)
-#pragma unroll
-  for (int i = 0; i < STATS; ++i) {
-    float v = stats[i];
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-    if ((r & 31) == 0) red_f[r >> 5][i] = v;
+    for (int k = 0; k < 16; ++k) orow[k] = make_float4(out.o[4 * k], out.o[4 * k + 1], out.o[4 * k + 2], out.o[4 * k + 3]);
+    float* cq = sm + PostSmem::kCurQ + r * 4;
+    cq[0] = out.cur_q.w; cq[1] = out.cur_q.x; cq[2] = out.cur_q.y; cq[3] = out.cur_q.z;
+    store_flags(a.buf, e0 + r, out);
   }
   fence_proxy_async();
   __syncthreads();
-  if (r < STATS) {
-    float v = 0.0f;
-#pragma unroll
-    for (int w = 0; w < T / 32; ++w) v += red_f[w][r];
-    a.partials[(size_t)blockIdx.x * STATS + r] = v;
-  }
-
   // ---- write back: obs rows (coalesced 128-bit), states gather, last_joint_vel / last_base_tip (TMA bulk store)
   {
     float* obs_g = a.buf.obs_buf + (size_t)e0 * LM_NUM_OBS;
@@ -613,56 +820,7 @@ __global__ void __launch_bounds__(T, 2) k_post(const KernelParams kp, const Post
       }
     }
   }
-
-  // ---- last CTA: extras means + success-rate bookkeeping (QPC:560,619-633 / JLV:758-802)
-  __threadfence();
-  if (r == 0) is_last = atomicAdd(a.ticket, 1u) == gridDim.x - 1;
-  __syncthreads();
-  if (is_last) {
-    __threadfence();
-    __shared__ double part[2][T / STATS][STATS];   // [loco|mani][thread group][stat]
-    __shared__ double tot[3][STATS];                // [all, loco, mani]
-    {
-      const int i = r % STATS, g = r / STATS;
-      double s_l = 0.0, s_m = 0.0;
-      const int tph = kp.d.tiles_per_half;
-      for (int t = g; t < kp.d.num_tiles; t += T / STATS) {
-        const double v = (double)__ldcg(a.partials + (size_t)t * STATS + i);
-        const bool second = (P.kind == LM_KIND_COTRAIN) && t >= tph;
-        if (second) s_m += v; else s_l += v;
-      }
-      part[0][g][i] = s_l; part[1][g][i] = s_m;
-    }
-    __syncthreads();
-    if (r < STATS) {
-      double s_l = 0.0, s_m = 0.0;
-      for (int g = 0; g < T / STATS; ++g) { s_l += part[0][g][r]; s_m += part[1][g][r]; }
-      tot[0][r] = s_l + s_m; tot[1][r] = s_l; tot[2][r] = s_m;
-    }
-    __syncthreads();
-    if (r == 0) {
-      float* ex = a.buf.extras;
-      const double inv_n = 1.0 / (double)N;
-      for (int i = 0; i < 7; ++i) ex[i] = (float)(tot[0][i] * inv_n);
-      ex[LM_EXTRA_NAN_COUNT] = (float)tot[0][7];
-      ex[LM_EXTRA_BELOW_M50_COUNT] = (float)tot[0][8];
-      int64_t* c = a.buf.counters;
-      const int groups = (P.kind == LM_KIND_COTRAIN) ? 3 : 1;
-      for (int g = 0; g < groups; ++g) {
-        int64_t& ns = c[2 * g];
-        int64_t& nr = c[2 * g + 1];
-        if (nr > (int64_t)P.max_reset_counts) {
-          ex[LM_EXTRA_SUCCESS_RATE + g] = (float)ns / (float)nr;
-          ns = 0; nr = 0;
-        }
-      }
-      for (int g = 0; g < groups; ++g) {
-        c[2 * g] += (int64_t)llrint(tot[g][9]);
-        c[2 * g + 1] += (int64_t)llrint(tot[g][10]);
-      }
-      *a.ticket = 0;
-    }
-  }
+  finish_stats<T>(kp, a, out.stats, red_f, &is_last, part, tot, scan_s);
   if (st.use_tma && r == 0) tma_store_wait_all();
 }
 
@@ -696,6 +854,7 @@ struct LmTask {
   float* partials;
   unsigned int* tickets;     // [2]: scan, post
   int clamp_observations;
+  int scan_valid;            // tile_offsets / num_reset were produced by the last post_step and reset_buf is untouched since
 };
 
 static void host_rot_from_quat(const float q[4], float m[9]) {   // same formulas as lm::rot_from_quat_scipy
@@ -777,7 +936,8 @@ LmTask* lm_task_create(const LmTaskParams* params, int device) {
             cudaMalloc(&t->tickets, sizeof(unsigned int) * 2) == cudaSuccess;
   if (!ok) { lm_set_error("lm_task_create: cudaMalloc failed"); lm_task_destroy(t); return nullptr; }
   cudaMemset(t->tickets, 0, sizeof(unsigned int) * 2);
-  err = cudaFuncSetAttribute(k_post, cudaFuncAttributeMaxDynamicSharedMemorySize, PostSmem::kBytes);
+  err = cudaFuncSetAttribute(k_post_lean, cudaFuncAttributeMaxDynamicSharedMemorySize, LeanSmem::kBytes);
+  if (err == cudaSuccess) err = cudaFuncSetAttribute(k_post, cudaFuncAttributeMaxDynamicSharedMemorySize, PostSmem::kBytes);
   if (err != cudaSuccess) { lm_set_error("cudaFuncSetAttribute(k_post): %s", cudaGetErrorString(err)); lm_task_destroy(t); return nullptr; }
   return t;
 }
@@ -791,6 +951,8 @@ void lm_task_destroy(LmTask* t) {
 int lm_task_step_parity(const LmTask* t) { return t ? t->parity : -1; }
 
 int lm_task_set_clamp_observations(LmTask* t, int on) { if (!t) return LM_ERR_BAD_ARG; t->clamp_observations = on; return LM_OK; }
+
+int lm_task_invalidate_reset_scan(LmTask* t) { if (!t) return LM_ERR_BAD_ARG; t->scan_valid = 0; return LM_OK; }
 
 static int check_views(const LmTask* t, const LmRobotViews* loco, const LmRobotViews* mani, const float* env_pos,
                        const LmTaskBuffers* buf) {
@@ -830,7 +992,9 @@ int lm_task_pre_step(LmTask* t, const LmRobotViews* loco, const LmRobotViews* ma
   cudaStream_t s = (cudaStream_t)stream;
   const Derived& d = t->kp.d;
   t->parity ^= 1;
-  k_reset_count<<<d.num_tiles, T, 0, s>>>(t->kp, buf->reset_buf, t->tile_counts, t->tile_offsets, buf->num_reset, t->tickets + 0);
+  if (!t->scan_valid)   // first step, or reset_buf was written from outside (task.reset(), lm_task_invalidate_reset_scan)
+    k_reset_count<<<d.num_tiles, T, 0, s>>>(t->kp, buf->reset_buf, t->tile_counts, t->tile_offsets, buf->num_reset, t->tickets + 0);
+  t->scan_valid = 0;
   PreArgs a;
   memset(&a, 0, sizeof(a));
   if (loco) a.loco = *loco;
@@ -838,6 +1002,7 @@ int lm_task_pre_step(LmTask* t, const LmRobotViews* loco, const LmRobotViews* ma
   a.env_pos = env_pos; a.buf = *buf; a.actions = actions; a.uniforms = uniforms;
   a.tile_offsets = t->tile_offsets; a.parity = t->parity;
   k_pre<<<d.num_tiles, T, 0, s>>>(t->kp, a);
+  k_reset_apply<<<d.num_tiles, T, 0, s>>>(t->kp, a);
   return lm_check_launch("lm_task_pre_step");
 }
 
@@ -853,6 +1018,7 @@ int lm_task_reset_idx(LmTask* t, const LmRobotViews* loco, const LmRobotViews* m
   if (mani) a.mani = *mani;
   a.env_pos = env_pos; a.buf = *buf; a.uniforms = uniforms; a.parity = t->parity ^ 1;   // "last" slot = current one before the next pre_step
   k_reset_idx<<<(count + 127) / 128, 128, 0, (cudaStream_t)stream>>>(t->kp, a, env_ids, count);
+  t->scan_valid = 0;   // reset_buf entries were cleared: the by-product scan of the last post_step is stale
   return lm_check_launch("lm_task_reset_idx");
 }
 
@@ -865,9 +1031,13 @@ int lm_task_post_step(LmTask* t, const LmRobotViews* loco, const LmRobotViews* m
   memset(&a, 0, sizeof(a));
   if (loco) a.loco = *loco;
   if (mani) a.mani = *mani;
-  a.env_pos = env_pos; a.buf = *buf; a.partials = t->partials; a.ticket = t->tickets + 1;
+  a.env_pos = env_pos; a.buf = *buf; a.partials = t->partials; a.ticket = t->tickets + 1; a.tile_offsets = t->tile_offsets;
   a.parity = t->parity; a.clamp_observations = t->clamp_observations;
-  k_post<<<t->kp.d.num_tiles, T, PostSmem::kBytes, (cudaStream_t)stream>>>(t->kp, a);
+  if (t->kp.p.num_states == LM_NUM_STATES_FULL)
+    k_post<<<t->kp.d.num_tiles, T, PostSmem::kBytes, (cudaStream_t)stream>>>(t->kp, a);
+  else
+    k_post_lean<<<t->kp.d.num_tiles, T, LeanSmem::kBytes, (cudaStream_t)stream>>>(t->kp, a);
+  t->scan_valid = 1;
   return lm_check_launch("lm_task_post_step");
 }
 

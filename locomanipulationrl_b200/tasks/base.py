@@ -61,6 +61,7 @@ class LocoManipulationTask:
         self._scene = None
         self._loco_views = self._mani_views = None
         self._posted_since_pre = False
+        self._reset_version = -1
         if scene is not None:
             self.set_up_scene(scene)
 
@@ -197,8 +198,9 @@ class LocoManipulationTask:
             actions = actions.contiguous()
         if uniforms is None:
             uniforms = self.draw_goal_uniforms()
-        if self._posted_since_pre is False and self._lib.lm_task_step_parity(self._handle) >= 0:
-            pass
+        if self.reset_buf._version != self._reset_version:
+            # reset_buf was written through torch since the last post step (task.reset(), user code): rescan it
+            self._lib.lm_task_invalidate_reset_scan(self._handle)
         rc = self._lib.lm_task_pre_step(self._handle, self._lp(), self._mp(), self._env_pos.data_ptr(), C.byref(self._buffers),
                                         actions.data_ptr(), uniforms.data_ptr(), self._stream())
         _lib.check(rc, "lm_task_pre_step")
@@ -227,6 +229,7 @@ class LocoManipulationTask:
                                          self._stream())
         _lib.check(rc, "lm_task_post_step")
         self._posted_since_pre = True
+        self._reset_version = self.reset_buf._version
         return self.obs_buf, self.rew_buf, self.reset_buf, self.extras
 
     # The reference runs these three in sequence inside post_physics_step; here they are one kernel.  Calling
