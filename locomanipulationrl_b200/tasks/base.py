@@ -246,7 +246,8 @@ class LocoManipulationTask:
         return None
 
     def reset_env_ids(self) -> torch.Tensor:
-        """Ascending ids reset by the last pre_physics_step (host sync; for logging / parity checks)."""
+        """Ascending ids reset by the last pre_physics_step (host sync; for logging / parity checks).  Valid between
+        pre_physics_step and post_physics_step: the post step overwrites the count with the NEXT step's reset count."""
         k = int(self.num_reset_buf[0].item())
         return self.reset_env_ids_buf[:k]
 

@@ -85,12 +85,12 @@ def test_edge_cases_termination_and_timeout():
     assert int(survivors.sum()) > 0 and bool((ro.task.reset_buf[survivors] == 1).all())
     ro.port.reset_buf[:] = 1                         # then flag everyone
     ro.task.reset_buf.fill_(1)
-    ro.step(5, acts[5], unis[5])                     # everyone resets (storm)
-    assert ro.task.reset_env_ids().numel() == n
+    ro.step(5, acts[5], unis[5])                     # everyone resets (storm); id lists are compared inside step()
+    assert ro.port.reset_env_ids.numel() == n
     ro.port.reset_buf = torch.ones_like(ro.port.reset_buf)   # rl_task.py:222-225
     ro.task.reset()
     ro.step(6, acts[6], unis[6])
-    assert ro.task.reset_env_ids().numel() == n
+    assert ro.port.reset_env_ids.numel() == n
     ro.step(7, acts[7], unis[7])
 
 
