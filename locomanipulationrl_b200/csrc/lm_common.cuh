@@ -172,17 +172,16 @@ __device__ __forceinline__ Quat quat_from_rot_scipy(const float m32[9]) {
   return q;
 }
 
-// quat_from_euler_xyz (Isaac) with the reference's angle draw (utils/math.py:187-191).  sin/cos are
-// evaluated in double and rounded once (<= 0.5 ulp; torch-CPU's SLEEF float kernels are <= 1 ulp).
+// quat_from_euler_xyz (Isaac) with the reference's angle draw (utils/math.py:187-191).  sinf/cosf (<= 1 ulp, like
+// torch-CPU's SLEEF kernels; the two libms agree bit-for-bit in ~95 % of draws and differ by 1 ulp otherwise).
 __device__ __forceinline__ Quat goal_from_uniforms(const LmTaskParams& p, float u0, float u1, float u2) {
   float roll = add(p.min_roll, mul(p.roll_range, u0));
   float pitch = add(p.min_pitch, mul(p.pitch_range, u1));
   float yaw = add(p.min_yaw, mul(p.yaw_range, u2));
-  double sy_, cy_, sr_, cr_, sp_, cp_;
-  sincos((double)mul(yaw, 0.5f), &sy_, &cy_);
-  sincos((double)mul(roll, 0.5f), &sr_, &cr_);
-  sincos((double)mul(pitch, 0.5f), &sp_, &cp_);
-  float sy = (float)sy_, cy = (float)cy_, sr = (float)sr_, cr = (float)cr_, sp = (float)sp_, cp = (float)cp_;
+  float sy, cy, sr, cr, sp, cp;
+  sincosf(mul(yaw, 0.5f), &sy, &cy);
+  sincosf(mul(roll, 0.5f), &sr, &cr);
+  sincosf(mul(pitch, 0.5f), &sp, &cp);
   Quat q;
   q.w = add(mul(mul(cy, cr), cp), mul(mul(sy, sr), sp));
   q.x = sub(mul(mul(cy, sr), cp), mul(mul(sy, cr), sp));

@@ -140,62 +140,74 @@ struct PreArgs {
 
 __device__ __forceinline__ void store3(float* p, float a, float b, float c) { p[0] = a; p[1] = b; p[2] = c; }
 
-// reset_idx for one env (QPC:230-299 / QMP:238-309 / JLV:272-377): defaults into the PhysX views,
-// goal resample from uniform row `rank`, history buffers cleared.
+// reset_idx for one env (QPC:230-299 / QMP:238-309 / JLV:272-377): defaults into the PhysX views, goal resample from
+// uniform row `rank`, history buffers cleared.  `role` splits the work over two lanes: 0 = goal quaternion + pose
+// indicator (the long double-precision chain), 1 = joint / root / plate defaults and history; -1 = both.
 __device__ __forceinline__ void reset_one_env(const KernelParams& kp, const PreArgs& a, const LmRobotViews& V, float* ring_last,
-                                              int is_mani, int e, int hr, int rank) {
+                                              int is_mani, int e, int hr, int rank, int role) {
   const LmTaskParams& P = kp.p;
-  Tile tl; tl.is_mani = is_mani;
-
+  const float ox = a.env_pos[hr * 3 + 0], oy = a.env_pos[hr * 3 + 1], oz = a.env_pos[hr * 3 + 2];
+  if (role != 1) {
     const float* u = a.uniforms + (size_t)rank * 3;
     const Quat g = goal_from_uniforms(P, u[0], u[1], u[2]);
     float* gq = a.buf.goal_quaternions + (size_t)e * 4;
     gq[0] = g.w; gq[1] = g.x; gq[2] = g.y; gq[3] = g.z;
-    const float ox = a.env_pos[hr * 3 + 0], oy = a.env_pos[hr * 3 + 1], oz = a.env_pos[hr * 3 + 2];
-    float* jp = V.dof_pos + (size_t)hr * LM_NUM_DOF;
-    float* jv = V.dof_vel + (size_t)hr * LM_NUM_DOF;
-#pragma unroll
-    for (int j = 0; j < LM_NUM_DOF; ++j) { jp[j] = tl.is_mani ? P.mani_init_joint_pos[j] : P.loco_init_joint_pos[j]; jv[j] = 0.0f; }
-    if (!tl.is_mani) {
-      store3(V.root_pos + hr * 3, add(P.loco_default_position[0], ox), add(P.loco_default_position[1], oy),
-             add(P.loco_default_position[2], oz));                                  // robot.py:420
-      float* q = V.root_quat + hr * 4;
-      q[0] = P.loco_default_quaternion[0]; q[1] = P.loco_default_quaternion[1];
-      q[2] = P.loco_default_quaternion[2]; q[3] = P.loco_default_quaternion[3];
-      store3(V.root_lin_vel + hr * 3, 0.f, 0.f, 0.f);
-      store3(V.root_ang_vel + hr * 3, 0.f, 0.f, 0.f);
-      float* iq = V.indicator_quat + hr * 4;                                        // conj(goal), QPC:282
-      iq[0] = g.w; iq[1] = -g.x; iq[2] = -g.y; iq[3] = -g.z;
+    a.buf.reset_env_ids[rank] = e;
+    float* iq = V.indicator_quat + hr * 4;
+    if (!is_mani) {
+      iq[0] = g.w; iq[1] = -g.x; iq[2] = -g.y; iq[3] = -g.z;                             // conj(goal), QPC:282
       store3(V.indicator_pos + hr * 3, add(ox, P.indicator_loco_position[0]), add(oy, P.indicator_loco_position[1]),
-             add(oz, P.indicator_loco_position[2]));                                // rigid_object.py:45
+             add(oz, P.indicator_loco_position[2]));                                    // rigid_object.py:45
     } else {
-      store3(V.plate_pos + hr * 3, add(ox, P.obj_default_position[0]), add(oy, P.obj_default_position[1]),
-             add(oz, P.obj_default_position[2]));
-      float* q = V.plate_quat + hr * 4;
-      q[0] = P.mani_default_quaternion[0]; q[1] = P.mani_default_quaternion[1];
-      q[2] = P.mani_default_quaternion[2]; q[3] = P.mani_default_quaternion[3];
-      store3(V.plate_lin_vel + hr * 3, 0.f, 0.f, 0.f);
-      store3(V.plate_ang_vel + hr * 3, 0.f, 0.f, 0.f);
-      float Rg[9], M[9], R0[9];                                                     // rotate_orientations(q0, goal), QMP:291
+      float Rg[9], M[9], R0[9];                                                         // rotate_orientations(q0, goal), QMP:291
 #pragma unroll
       for (int i = 0; i < 9; ++i) R0[i] = kp.d.R0[i];
       rot_from_quat_scipy(g, Rg);
       mat3_mul<false>(R0, Rg, M);
       const Quat iqv = quat_from_rot_scipy(M);
-      float* iq = V.indicator_quat + hr * 4;
       iq[0] = iqv.w; iq[1] = iqv.x; iq[2] = iqv.y; iq[3] = iqv.z;
       store3(V.indicator_pos + hr * 3, add(ox, P.indicator_mani_position[0]), add(oy, P.indicator_mani_position[1]),
              add(oz, P.indicator_mani_position[2]));
     }
-    float* ljv = a.buf.last_joint_vel + (size_t)e * LM_NUM_ACT;
-    float* la = ring_last + (size_t)e * LM_NUM_ACT;
-    float* lt = a.buf.last_base_tip + (size_t)e * 12;
+  }
+  if (role != 0) {
+    float4* jp = reinterpret_cast<float4*>(V.dof_pos + (size_t)hr * LM_NUM_DOF);
+    float4* jv = reinterpret_cast<float4*>(V.dof_vel + (size_t)hr * LM_NUM_DOF);
 #pragma unroll
-    for (int j = 0; j < LM_NUM_ACT; ++j) { ljv[j] = 0.0f; la[j] = 0.0f; lt[j] = P.default_base_tip[j / 3][j % 3]; }
+    for (int k = 0; k < LM_NUM_DOF / 4; ++k) {
+      jp[k] = is_mani ? make_float4(P.mani_init_joint_pos[4 * k], P.mani_init_joint_pos[4 * k + 1], P.mani_init_joint_pos[4 * k + 2], P.mani_init_joint_pos[4 * k + 3])
+                      : make_float4(P.loco_init_joint_pos[4 * k], P.loco_init_joint_pos[4 * k + 1], P.loco_init_joint_pos[4 * k + 2], P.loco_init_joint_pos[4 * k + 3]);
+      jv[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (!is_mani) {
+      store3(V.root_pos + hr * 3, add(P.loco_default_position[0], ox), add(P.loco_default_position[1], oy),
+             add(P.loco_default_position[2], oz));                                      // robot.py:420
+      *reinterpret_cast<float4*>(V.root_quat + hr * 4) = make_float4(P.loco_default_quaternion[0], P.loco_default_quaternion[1],
+                                                                    P.loco_default_quaternion[2], P.loco_default_quaternion[3]);
+      store3(V.root_lin_vel + hr * 3, 0.f, 0.f, 0.f);
+      store3(V.root_ang_vel + hr * 3, 0.f, 0.f, 0.f);
+    } else {
+      store3(V.plate_pos + hr * 3, add(ox, P.obj_default_position[0]), add(oy, P.obj_default_position[1]),
+             add(oz, P.obj_default_position[2]));
+      *reinterpret_cast<float4*>(V.plate_quat + hr * 4) = make_float4(P.mani_default_quaternion[0], P.mani_default_quaternion[1],
+                                                                     P.mani_default_quaternion[2], P.mani_default_quaternion[3]);
+      store3(V.plate_lin_vel + hr * 3, 0.f, 0.f, 0.f);
+      store3(V.plate_ang_vel + hr * 3, 0.f, 0.f, 0.f);
+    }
+    float4* ljv = reinterpret_cast<float4*>(a.buf.last_joint_vel + (size_t)e * LM_NUM_ACT);
+    float4* la = reinterpret_cast<float4*>(ring_last + (size_t)e * LM_NUM_ACT);
+    float4* lt = reinterpret_cast<float4*>(a.buf.last_base_tip + (size_t)e * 12);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      ljv[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      la[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      lt[k] = make_float4(P.default_base_tip[(4 * k) / 3][(4 * k) % 3], P.default_base_tip[(4 * k + 1) / 3][(4 * k + 1) % 3],
+                          P.default_base_tip[(4 * k + 2) / 3][(4 * k + 2) % 3], P.default_base_tip[(4 * k + 3) / 3][(4 * k + 3) % 3]);
+    }
     a.buf.reset_buf[e] = 0; a.buf.progress_buf[e] = 0; a.buf.successes[e] = 0;
     a.buf.consecutive_successes[e] = 0; a.buf.goal_reset_buf[e] = 0;
-    a.buf.reset_env_ids[rank] = e;
   }
+}
 
 // K_pre: (1) reset mask -> rank -> compacted ascending id list (the `nonzero()` of QPC:206); (2) clamp + stash
 // actions, take_action.  The reset bodies themselves run in k_reset_apply over the compacted list, so the ~3 % of
@@ -209,16 +221,29 @@ __global__ void __launch_bounds__(T) k_pre(const KernelParams kp, const PreArgs 
   const LmRobotViews& V = tl.is_mani ? a.mani : a.loco;
 
   __shared__ int warp_base[T / 32];
+  __shared__ int list[T];
   int flag = 0;
   const int e = tl.e0 + r, hr = tl.hr0 + r;
   if (r < tl.n) flag = a.buf.reset_buf[e] != 0;
   unsigned b = __ballot_sync(0xffffffffu, flag);
   if ((r & 31) == 0) warp_base[r >> 5] = __popc(b);
   __syncthreads();
-  if (flag) {
-    int base = a.tile_offsets[blockIdx.x];
-    for (int w = 0; w < (r >> 5); ++w) base += warp_base[w];
-    a.buf.reset_env_ids[base + __popc(b & ((1u << (r & 31)) - 1u))] = e;
+  int local_rank = __popc(b & ((1u << (r & 31)) - 1u)), count = 0;
+#pragma unroll
+  for (int w = 0; w < T / 32; ++w) {
+    if (w < (r >> 5)) local_rank += warp_base[w];
+    count += warp_base[w];
+  }
+  if (flag) list[local_rank] = r;          // tile-local compaction: the reset bodies run on the first lanes only
+  __syncthreads();
+  if (count > 0) {
+    // two lanes per reset env: role 0 = goal + indicator pose (the double-precision chain), role 1 = defaults + history
+    const int tile_base = a.tile_offsets[blockIdx.x];
+    float* ring_last = a.buf.actions_ring + (size_t)(a.parity ^ 1) * N * LM_NUM_ACT;
+    for (int idx = r; idx < 2 * count; idx += T) {
+      const int lr = list[idx >> 1];
+      reset_one_env(kp, a, V, ring_last, tl.is_mani, tl.e0 + lr, tl.hr0 + lr, tile_base + (idx >> 1), idx & 1);
+    }
   }
 
   // ---- actions: clamp (vec_env_rlgames.py:60), stash as current_actions, take_action (robot.py:444-461)
@@ -259,19 +284,6 @@ __global__ void __launch_bounds__(T) k_pre(const KernelParams kp, const PreArgs 
   }
 }
 
-// reset_idx over the compacted list: thread k resets env reset_env_ids[k] with uniform row k (its goal index).
-// The grid is sized for the worst case (every env resets); blocks beyond num_reset exit immediately.
-__global__ void __launch_bounds__(T) k_reset_apply(const KernelParams kp, const PreArgs a) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= a.buf.num_reset[0]) return;
-  const int e = (int)a.buf.reset_env_ids[k];
-  const int second = (kp.p.kind == LM_KIND_COTRAIN) && e >= kp.d.half;
-  const int is_mani = (kp.p.kind == LM_KIND_MANI) || second;
-  const int hr = second ? e - kp.d.half : e;
-  float* ring_last = a.buf.actions_ring + (size_t)(a.parity ^ 1) * kp.p.num_envs * LM_NUM_ACT;
-  reset_one_env(kp, a, is_mani ? a.mani : a.loco, ring_last, is_mani, e, hr, k);
-}
-
 // direct reset_idx(env_ids) call (random_policy.py-style drivers): env k of the list consumes uniform row k
 __global__ void k_reset_idx(const KernelParams kp, const PreArgs a, const int64_t* __restrict__ env_ids, int count) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -282,7 +294,7 @@ __global__ void k_reset_idx(const KernelParams kp, const PreArgs a, const int64_
   const int is_mani = (kp.p.kind == LM_KIND_MANI) || second;
   const int hr = second ? e - kp.d.half : e;
   float* ring_last = a.buf.actions_ring + (size_t)(a.parity ^ 1) * kp.p.num_envs * LM_NUM_ACT;
-  reset_one_env(kp, a, is_mani ? a.mani : a.loco, ring_last, is_mani, e, hr, k);
+  reset_one_env(kp, a, is_mani ? a.mani : a.loco, ring_last, is_mani, e, hr, k, -1);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -303,25 +315,37 @@ struct EnvIn {
   float jp[12], jv[12], last_jv[12], cur[12], last[12];
   Vec3 O, Pw, lin, ang;            // env origin, world position of base | plate, velocities
   Quat q, goal;                    // orientation of base | plate, goal
-  int64_t progress, reset, succ_prev, consec;
+  int progress, reset, succ_prev, consec;   // int64 at the boundary; values are small
 };
 struct EnvOut {
-  float o[64];                     // observation row
   Quat cur_q;                      // ground | plate quaternion in the robot frame (states row)
   float rew;
-  int64_t progress, consec;
+  int progress, consec;
   int reset, success, goal_reset;
   float stats[STATS];
 };
 
+// Emits one 16-byte chunk k (0..15) of the 64-float observation row.
+struct ObsToGlobal {
+  float4* row; float clip; int clamp;
+  __device__ __forceinline__ void operator()(int k, float a, float b, float c, float d) const {
+    if (clamp) {
+      a = fminf(fmaxf(a, -clip), clip); b = fminf(fmaxf(b, -clip), clip);
+      c = fminf(fmaxf(c, -clip), clip); d = fminf(fmaxf(d, -clip), clip);
+    }
+    row[k] = make_float4(a, b, c, d);
+  }
+};
+
 // tips: 4x3 world positions in, base-frame positions out (in place); knees: 8x3 world positions
-template <typename TipPtr>
-__device__ __forceinline__ void env_math(const KernelParams& kp, const int is_mani, const int clamp_obs, const EnvIn& in, TipPtr tips,
-                                         const float* knees, EnvOut& out) {
+template <typename Sink>
+__device__ __forceinline__ void env_math(const KernelParams& kp, const int is_mani, const EnvIn& in, float* tips,
+                                         const float* knees, const Sink& sink, EnvOut& out) {
   const LmTaskParams& P = kp.p;
 #pragma unroll
   for (int i = 0; i < STATS; ++i) out.stats[i] = 0.0f;
-  // ---- finite-difference joint acceleration, action rate (robot.py:290; QPC:443,446)
+  // ---- joint part first (its inputs die early): acceleration / action-rate sums (robot.py:290; QPC:443,446),
+  //      joint-limit flags (QPC:466-504 / JLV:574-597) and obs[16:64] (QPC:367-370)
   float acc_sum = 0.0f, rate_sum = 0.0f;
 #pragma unroll
   for (int j = 0; j < 12; ++j) {
@@ -330,6 +354,28 @@ __device__ __forceinline__ void env_math(const KernelParams& kp, const int is_ma
     rate_sum = add(rate_sum, fabsf(sub(in.last[j], in.cur[j])));
   }
   const float jacc = acc_sum, arate = mul(rate_sum, P.action_rate_scale);
+  int brk = 0, rst = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float d = fabsf(sub(in.jp[5 + 2 * k], in.jp[4 + 2 * k]));
+    brk |= (d < P.min_joint_23_diff) | (d > P.max_joint_23_diff);
+    rst |= (d < P.reset_min_joint_23_diff) | (d > P.reset_max_joint_23_diff);
+    const bool mirrored = P.joint1_mirrored && (k == 1 || k == 2);
+    const float lo = mirrored ? -P.max_joint_1_pos : P.min_joint_1_pos, hi = mirrored ? -P.min_joint_1_pos : P.max_joint_1_pos;
+    const float rlo = mirrored ? -P.reset_max_joint_1_pos : P.reset_min_joint_1_pos;
+    const float rhi = mirrored ? -P.reset_min_joint_1_pos : P.reset_max_joint_1_pos;
+    brk |= (in.jp[k] < lo) | (in.jp[k] > hi);
+    rst |= (in.jp[k] < rlo) | (in.jp[k] > rhi);
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    sink(4 + k, mul(P.joint_position_scale, in.jp[4 * k]), mul(P.joint_position_scale, in.jp[4 * k + 1]),
+         mul(P.joint_position_scale, in.jp[4 * k + 2]), mul(P.joint_position_scale, in.jp[4 * k + 3]));
+    sink(7 + k, mul(P.joint_velocity_scale, in.jv[4 * k]), mul(P.joint_velocity_scale, in.jv[4 * k + 1]),
+         mul(P.joint_velocity_scale, in.jv[4 * k + 2]), mul(P.joint_velocity_scale, in.jv[4 * k + 3]));
+    sink(10 + k, in.cur[4 * k], in.cur[4 * k + 1], in.cur[4 * k + 2], in.cur[4 * k + 3]);
+    sink(13 + k, in.last[4 * k], in.last[4 * k + 1], in.last[4 * k + 2], in.last[4 * k + 3]);
+  }
 
   // ---- frame quantities per kind
   const Vec3 O = in.O;
@@ -391,50 +437,25 @@ __device__ __forceinline__ void env_math(const KernelParams& kp, const int is_ma
   if (diff.w < 0.0f) { diff.w = -diff.w; diff.x = -diff.x; diff.y = -diff.y; diff.z = -diff.z; }
   const Vec3 up = quat_rotate_t<false>(cur_q, Vec3{0.0f, 0.0f, 1.0f});                  // quat_axis(q, 2)
 
-  // ---- observation row (QPC:358-371)
-  float* o = out.o;
-  o[0] = mul(P.position_scale, pos.x); o[1] = mul(P.position_scale, pos.y); o[2] = mul(P.position_scale, pos.z);
-  o[3] = up.x; o[4] = up.y; o[5] = up.z;
-  o[6] = diff.w; o[7] = diff.x; o[8] = diff.y; o[9] = diff.z;
-  o[10] = mul(P.linear_vel_scale, lin_o.x); o[11] = mul(P.linear_vel_scale, lin_o.y); o[12] = mul(P.linear_vel_scale, lin_o.z);
-  o[13] = mul(P.angular_vel_scale, ang_o.x); o[14] = mul(P.angular_vel_scale, ang_o.y); o[15] = mul(P.angular_vel_scale, ang_o.z);
-#pragma unroll
-  for (int j = 0; j < 12; ++j) {
-    o[16 + j] = mul(P.joint_position_scale, in.jp[j]);
-    o[28 + j] = mul(P.joint_velocity_scale, in.jv[j]);
-    o[40 + j] = in.cur[j];
-    o[52 + j] = in.last[j];
-  }
-  if (clamp_obs) {
-#pragma unroll
-    for (int j = 0; j < 64; ++j) o[j] = fminf(fmaxf(o[j], -P.clip_observations), P.clip_observations);
-  }
+  // ---- obs[0:16] (QPC:358-366)
+  sink(0, mul(P.position_scale, pos.x), mul(P.position_scale, pos.y), mul(P.position_scale, pos.z), up.x);
+  sink(1, up.y, up.z, diff.w, diff.x);
+  sink(2, diff.y, diff.z, mul(P.linear_vel_scale, lin_o.x), mul(P.linear_vel_scale, lin_o.y));
+  sink(3, mul(P.linear_vel_scale, lin_o.z), mul(P.angular_vel_scale, ang_o.x), mul(P.angular_vel_scale, ang_o.y),
+       mul(P.angular_vel_scale, ang_o.z));
   out.cur_q = cur_q;
 
   // ---- reward (QPC:432-457,506-515)
   const float rot_rew = mul(fdiv(1.0f, add(fabsf(rot_dist), P.rot_eps)), P.quaternion_scale);
   const float trans = mul(norm2_torch(pos.x, pos.y), P.translation_scale);
-  const int goal_reset = in.consec > (int64_t)P.max_consecutive_successes;               // counter BEFORE update (QPC:449)
+  const int goal_reset = in.consec > P.max_consecutive_successes;                       // counter BEFORE update (QPC:449)
   const float bonus = mul(P.consecutive_success_reward, (float)goal_reset);
   const int success = fabsf(rot_dist) <= P.success_thresh;
-  int brk = 0, rst = 0;
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {                                                         // QPC:466-504 / JLV:574-597
-    const float d = fabsf(sub(in.jp[5 + 2 * k], in.jp[4 + 2 * k]));
-    brk |= (d < P.min_joint_23_diff) | (d > P.max_joint_23_diff);
-    rst |= (d < P.reset_min_joint_23_diff) | (d > P.reset_max_joint_23_diff);
-    const bool mirrored = P.joint1_mirrored && (k == 1 || k == 2);
-    const float lo = mirrored ? -P.max_joint_1_pos : P.min_joint_1_pos, hi = mirrored ? -P.min_joint_1_pos : P.max_joint_1_pos;
-    const float rlo = mirrored ? -P.reset_max_joint_1_pos : P.reset_min_joint_1_pos;
-    const float rhi = mirrored ? -P.reset_min_joint_1_pos : P.reset_max_joint_1_pos;
-    brk |= (in.jp[k] < lo) | (in.jp[k] > hi);
-    rst |= (in.jp[k] < rlo) | (in.jp[k] > rhi);
-  }
   const float limit_pen = mul(P.joint_limit_penalty, (float)brk);
   float total = add(add(add(add(add(rot_rew, trans), jacc), arate), bonus), limit_pen);
 
   // ---- consecutive-success state machine (QPC:534-545)
-  int64_t consec = in.consec;
+  int consec = in.consec;
   const int both = success && (in.succ_prev != 0);
   if (!both) consec = 0;
   if (both) consec += 1;
@@ -448,8 +469,8 @@ __device__ __forceinline__ void env_math(const KernelParams& kp, const int is_ma
   const float fall = mul(P.fall_penalty, (float)rs);
   total = add(total, fall);
   rs |= goal_reset;
-  const int64_t progress = in.progress + 1;                                             // rl_task.py:251
-  rs |= progress >= (int64_t)(P.max_episode_length - 1);
+  const int progress = in.progress + 1;                                                 // rl_task.py:251
+  rs |= progress >= (P.max_episode_length - 1);
 
   out.rew = total; out.progress = progress; out.consec = consec; out.reset = rs; out.success = success; out.goal_reset = goal_reset;
   out.stats[0] = rot_rew; out.stats[1] = trans; out.stats[2] = jacc; out.stats[3] = arate; out.stats[4] = bonus;
@@ -462,11 +483,11 @@ __device__ __forceinline__ void env_math(const KernelParams& kp, const int is_ma
 
 __device__ __forceinline__ void store_flags(const LmTaskBuffers& b, int e, const EnvOut& out) {
   b.rew_buf[e] = out.rew;
-  b.progress_buf[e] = out.progress;
-  b.reset_buf[e] = out.reset;
-  b.successes[e] = out.success;
-  b.consecutive_successes[e] = out.consec;
-  b.goal_reset_buf[e] = out.goal_reset;
+  b.progress_buf[e] = (int64_t)out.progress;
+  b.reset_buf[e] = (int64_t)out.reset;
+  b.successes[e] = (int64_t)out.success;
+  b.consecutive_successes[e] = (int64_t)out.consec;
+  b.goal_reset_buf[e] = (int64_t)out.goal_reset;
 }
 
 // per-CTA partial sums -> partials[tile]; the last CTA turns them into extras / counters / the next reset scan
@@ -485,17 +506,24 @@ __device__ __forceinline__ void finish_stats(const KernelParams& kp, const PostA
     if ((r & 31) == 0) red_f[r >> 5][i] = v;
   }
   __syncthreads();
-  if (r < STATS) {
-    float v = 0.0f;
-    if (r < 11) {
+  if (r == 0) {
+    // one thread publishes the CTA's partial sums, fences them and takes the ticket: the other threads' pending stores
+    // (obs rows etc.) stay off the fence's critical path
+    float4* dst = reinterpret_cast<float4*>(a.partials + (size_t)blockIdx.x * STATS);
+    float v[STATS];
 #pragma unroll
-      for (int w = 0; w < kThreads / 32; ++w) v += red_f[w][r];
+    for (int i = 0; i < STATS; ++i) {
+      v[i] = 0.0f;
+      if (i < 11) {
+#pragma unroll
+        for (int w = 0; w < kThreads / 32; ++w) v[i] += red_f[w][i];
+      }
     }
-    a.partials[(size_t)blockIdx.x * STATS + r] = v;
+#pragma unroll
+    for (int k = 0; k < STATS / 4; ++k) __stcg(dst + k, make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]));
+    __threadfence();
+    *is_last = atomicAdd(a.ticket, 1u) == gridDim.x - 1;
   }
-  __threadfence();
-  __syncthreads();
-  if (r == 0) *is_last = atomicAdd(a.ticket, 1u) == gridDim.x - 1;
   __syncthreads();
   if (!*is_last) return;
   __threadfence();
@@ -631,10 +659,10 @@ __global__ void __launch_bounds__(T, 4) k_post_lean(const KernelParams kp, const
     in.Pw = ld3((tl.is_mani ? V.plate_pos : V.root_pos) + (size_t)hr * 3);
     in.lin = ld3((tl.is_mani ? V.plate_lin_vel : V.root_lin_vel) + (size_t)hr * 3);
     in.ang = ld3((tl.is_mani ? V.plate_ang_vel : V.root_ang_vel) + (size_t)hr * 3);
-    in.progress = a.buf.progress_buf[e];
-    in.reset = a.buf.reset_buf[e];
-    in.succ_prev = a.buf.successes[e];
-    in.consec = a.buf.consecutive_successes[e];
+    in.progress = (int)a.buf.progress_buf[e];
+    in.reset = (int)a.buf.reset_buf[e];
+    in.succ_prev = (int)a.buf.successes[e];
+    in.consec = (int)a.buf.consecutive_successes[e];
   }
   if (st.use_tma) mbar_wait(&bar, 0); else __syncthreads();
   {
@@ -651,12 +679,12 @@ __global__ void __launch_bounds__(T, 4) k_post_lean(const KernelParams kp, const
     }
     float tips[12];
     ld12(sm + LeanSmem::kTips + rr * 12, tips);
-    env_math(kp, tl.is_mani, a.clamp_observations, in, tips, sm + LeanSmem::kKnees + rr * 24, out);
+    // padding lanes of a ragged tile write their (meaningless) obs row into a scratch row of shared memory
+    float4* orow = valid ? reinterpret_cast<float4*>(a.buf.obs_buf + (size_t)e * LM_NUM_OBS)
+                         : reinterpret_cast<float4*>(sm + LeanSmem::kDofPos + rr * 20);
+    if (valid) st12(a.buf.last_joint_vel + (size_t)e * 12, in.jv);                      // robot.py:291
+    env_math(kp, tl.is_mani, in, tips, sm + LeanSmem::kKnees + rr * 24, ObsToGlobal{orow, P.clip_observations, a.clamp_observations}, out);
     if (valid) {
-      float4* og = reinterpret_cast<float4*>(a.buf.obs_buf + (size_t)e * LM_NUM_OBS);
-#pragma unroll
-      for (int k = 0; k < 16; ++k) og[k] = make_float4(out.o[4 * k], out.o[4 * k + 1], out.o[4 * k + 2], out.o[4 * k + 3]);
-      st12(a.buf.last_joint_vel + (size_t)e * 12, in.jv);                               // robot.py:291
       st12(a.buf.last_base_tip + (size_t)e * 12, tips);                                 // QPC:426
       store_flags(a.buf, e, out);
     } else {
@@ -748,10 +776,10 @@ __global__ void __launch_bounds__(T, 2) k_post(const KernelParams kp, const Post
   EnvOut out;
   in.progress = in.reset = in.succ_prev = in.consec = 0;
   if (r < n) {   // int64 flags straight from global while the bulk copies fly
-    in.progress = a.buf.progress_buf[e0 + r];
-    in.reset = a.buf.reset_buf[e0 + r];
-    in.succ_prev = a.buf.successes[e0 + r];
-    in.consec = a.buf.consecutive_successes[e0 + r];
+    in.progress = (int)a.buf.progress_buf[e0 + r];
+    in.reset = (int)a.buf.reset_buf[e0 + r];
+    in.succ_prev = (int)a.buf.successes[e0 + r];
+    in.consec = (int)a.buf.consecutive_successes[e0 + r];
   }
   if (st.use_tma) mbar_wait(&bar, 0); else __syncthreads();
 
@@ -779,11 +807,9 @@ __global__ void __launch_bounds__(T, 2) k_post(const KernelParams kp, const Post
     const float4 gv = *reinterpret_cast<const float4*>(sm + PostSmem::kGoal + r * 4);
     in.q = Quat{qv.x, qv.y, qv.z, qv.w};
     in.goal = Quat{gv.x, gv.y, gv.z, gv.w};
-    env_math(kp, tl.is_mani, a.clamp_observations, in, sm + PostSmem::kTips + r * 12, sm + PostSmem::kKnees + r * 24, out);
     st12(sm + PostSmem::kLastJv + r * 12, in.jv);                                        // last_joint_vel <- jv (robot.py:291)
-    float4* orow = reinterpret_cast<float4*>(sm + PostSmem::kObs + r * OBS_PAD);
-#pragma unroll
-    for (int k = 0; k < 16; ++k) orow[k] = make_float4(out.o[4 * k], out.o[4 * k + 1], out.o[4 * k + 2], out.o[4 * k + 3]);
+    env_math(kp, tl.is_mani, in, sm + PostSmem::kTips + r * 12, sm + PostSmem::kKnees + r * 24,
+             ObsToGlobal{reinterpret_cast<float4*>(sm + PostSmem::kObs + r * OBS_PAD), P.clip_observations, a.clamp_observations}, out);
     float* cq = sm + PostSmem::kCurQ + r * 4;
     cq[0] = out.cur_q.w; cq[1] = out.cur_q.x; cq[2] = out.cur_q.y; cq[3] = out.cur_q.z;
     store_flags(a.buf, e0 + r, out);
@@ -1002,7 +1028,6 @@ int lm_task_pre_step(LmTask* t, const LmRobotViews* loco, const LmRobotViews* ma
   a.env_pos = env_pos; a.buf = *buf; a.actions = actions; a.uniforms = uniforms;
   a.tile_offsets = t->tile_offsets; a.parity = t->parity;
   k_pre<<<d.num_tiles, T, 0, s>>>(t->kp, a);
-  k_reset_apply<<<d.num_tiles, T, 0, s>>>(t->kp, a);
   return lm_check_launch("lm_task_pre_step");
 }
 
