@@ -336,14 +336,31 @@ def cuda_arm(args):
 
         for i in range(3):
             pre_only(i); post_only(i); policy_only(i)
-        # one full step per iteration, four events: pre | post | policy durations of the SAME sequence the step loop runs
-        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(iters)]
-        for i, (a0, a1, a2, a3) in enumerate(evs):
-            a0.record(); pre_only(i); a1.record(); post_only(i); a2.record(); policy_only(i); a3.record()
         torch.cuda.synchronize()
-        ms_pre = sum(e[0].elapsed_time(e[1]) for e in evs) / iters
-        ms_post = sum(e[1].elapsed_time(e[2]) for e in evs) / iters
-        ms_pol = sum(e[2].elapsed_time(e[3]) for e in evs) / iters
+
+        def graph_time(fn, reps=20):
+            """Average device time of one call: STATE_SETS calls captured back-to-back in a CUDA graph (no host launch gaps),
+            replayed `reps` times between two CUDA events on the launching stream."""
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                for i in range(STATE_SETS):
+                    fn(i)
+            g.replay()
+            torch.cuda.synchronize()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            for _ in range(reps):
+                g.replay()
+            a1.record()
+            torch.cuda.synchronize()
+            return a0.elapsed_time(a1) / (reps * STATE_SETS)
+
+        def pre_post(i):
+            pre_only(i); post_only(i)
+
+        ms_post = graph_time(post_only)
+        ms_pre = max(graph_time(pre_post) - ms_post, 1e-6)      # pre needs a preceding post (its reset scan is post's by-product)
+        ms_pol = graph_time(policy_only)
         hbm, tf, src = measured_peaks()
         ach = n * B_POST / (ms_post * 1e-3) / 1e9
         ach_task = n * B_TASK / ((ms_post + ms_pre) * 1e-3) / 1e9
@@ -359,6 +376,8 @@ def cuda_arm(args):
             line_extra["roofline_policy"] = {"kernel": "k_gnn_forward", "bound": "fp32", "achieved": n * 447296 / (ms_pol * 1e-3) / 1e12,
                                              "unit": "TFLOP/s (naive FLOP count)", "ms": ms_pol}
         line_extra["kernel_ms"] = {"pre": ms_pre, "post": ms_post, "policy": ms_pol}
+        if world == 1 and not args.no_large:
+            line_extra["roofline_large"] = large_roofline(device, graph_time, hbm)
 
     # ---- e2e: C-ABI host entry, pinned host buffers in, results out, every step
     e2e = None if args.no_e2e else e2e_arm(pipe, args, world, device)
@@ -387,6 +406,36 @@ def cuda_arm(args):
     if world > 1:
         tdist.barrier()
         tdist.destroy_process_group()
+
+
+def large_roofline(device, graph_time, hbm, n=524288):
+    """k_post at 524,288 envs on ONE GPU (BASELINE configs[4]'s global batch): several waves of CTAs, so the figure shows
+    the kernel's steady-state quality rather than the launch/latency floor that dominates at 65,536 envs."""
+    from locomanipulationrl_b200 import configs, synthetic
+    from locomanipulationrl_b200.tasks.base import LocoManipulationTask
+    cfg = configs.get_task_config("JointLocomanipulationVertical")
+    scenes = [synthetic.SyntheticScene(cfg, n, device=device, seed=77) for _ in range(2)]      # 2 x ~190 MB of state > L2
+    small = synthetic.SyntheticScene(cfg, 65536, seed=77)
+    st = small.generate(0)
+    for sc in scenes:                          # tile the 65,536-env synthetic state 8x (generation cost, not content, matters here)
+        for grp, dst in (("loco", sc.loco), ("mani", sc.mani)):
+            for k, v in st[grp].items():
+                reps = dst[k].shape[0] // v.shape[0]
+                dst[k].copy_(v.repeat(reps, 1))
+    task = LocoManipulationTask(cfg, n, scene=scenes[0], device=device, fuse_obs_clamp=True)
+    task.pre_physics_step(torch.zeros(n, 12, device=device), torch.rand(n, 3, device=device))
+
+    def post_only(i):
+        task.set_up_scene(scenes[i % 2])
+        task._posted_since_pre = False
+        task.post_physics_step()
+
+    for i in range(3):
+        post_only(i)
+    ms = graph_time(post_only, reps=10)
+    ach = n * B_POST / (ms * 1e-3) / 1e9
+    return {"kernel": "k_post_lean", "envs": n, "ms": ms, "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
+            "bytes_per_env": B_POST}
 
 
 def e2e_arm(pipe, args, world, device):
@@ -459,6 +508,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graphs", action="store_true", help="launch eagerly (for ncu captures)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-large", action="store_true", help="skip the 524,288-env k_post roofline line")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)

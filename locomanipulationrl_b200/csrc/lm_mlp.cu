@@ -4,7 +4,7 @@
 // cfg/train/JointLocomanipulationPPO.yaml:10-32):
 //   x[64] -> Linear(64,256) ELU -> Linear(256,128) ELU -> Linear(128,64) ELU -> { mean Linear(64,12), value Linear(64,1) }
 //
-// One CTA per SM, 256 threads.  All four weight matrices (bf16, 115 KB) are pulled into shared memory
+// One CTA per SM, 512 threads (16 epilogue warps: 4 TMEM lane groups x 4 column quarters).  All four weight matrices (bf16, 115 KB) are pulled into shared memory
 // once per CTA by a TMA bulk copy and stay there; the CTA then walks 128-env tiles:
 //   TMA bulk load of the fp32 obs tile -> normalise/clamp -> bf16 A operand in the UMMA canonical
 //   K-major layout -> tcgen05.mma (M=128, N=256/128/64/16, fp32 accumulators in TMEM) ->
@@ -21,7 +21,7 @@ namespace lm {
 namespace mlp {
 
 constexpr int TM = 128;                 // rows (envs) per tile == UMMA M
-constexpr int THREADS = 256;
+constexpr int THREADS = 512;              // 16 warps: 4 TMEM lane groups x 4 column quarters
 constexpr int D0 = 64, D1 = 256, D2 = 128, D3 = 64, DH = 16;   // head: 12 mean + 1 value + 3 pad
 
 // UMMA canonical K-major, no swizzle: core matrix = 8 rows x 16 B, rows 16 B apart; core matrices
@@ -83,19 +83,28 @@ __device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t cols) {
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
 }
-// 32 lanes x 16 consecutive fp32 columns: thread i of the warp receives row (lane base + i)
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float v[16]) {
-  uint32_t r[16];
+// 32 lanes x 16 / 32 consecutive fp32 columns: thread i of the warp receives row (lane base + i).  The loads are
+// asynchronous; tmem_wait() must precede the first use of the registers.
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t r[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
         "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr)
       : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t r[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,"
+      "%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ float elu(float x) { return x > 0.0f ? x : __expf(x) - 1.0f; }   // nn.ELU(alpha=1)
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
@@ -117,24 +126,46 @@ __device__ __forceinline__ void issue_layer(uint32_t tmem_d, uint32_t a_saddr, u
   umma_commit(bar);
 }
 
-// hidden-layer epilogue: TMEM fp32 [128 x kN] -> +bias, ELU, bf16 -> next A operand (K = kN) in `dst`
+// 8 accumulator columns -> +bias, ELU, bf16 -> one 16-byte K chunk of the next A operand
+__device__ __forceinline__ void emit_chunk(const uint32_t* acc, const float* __restrict__ bias, uint8_t* dst) {
+  const float4 b0 = *reinterpret_cast<const float4*>(bias), b1 = *reinterpret_cast<const float4*>(bias + 4);
+  const float e0 = elu(__uint_as_float(acc[0]) + b0.x), e1 = elu(__uint_as_float(acc[1]) + b0.y);
+  const float e2 = elu(__uint_as_float(acc[2]) + b0.z), e3 = elu(__uint_as_float(acc[3]) + b0.w);
+  const float e4 = elu(__uint_as_float(acc[4]) + b1.x), e5 = elu(__uint_as_float(acc[5]) + b1.y);
+  const float e6 = elu(__uint_as_float(acc[6]) + b1.z), e7 = elu(__uint_as_float(acc[7]) + b1.w);
+  *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16(e0, e1), pack_bf16(e2, e3), pack_bf16(e4, e5), pack_bf16(e6, e7));
+}
+
+// hidden-layer epilogue: TMEM fp32 [128 x kN] -> +bias, ELU, bf16 -> next A operand (K = kN) in `dst`.
+// Warp w owns TMEM lanes 32*(w&3).. and the column quarter (w>>2); all of its columns are fetched with one or two
+// asynchronous tcgen05.ld before the single wait, so the TMEM latency is paid once per layer.
 template <int kN>
 __device__ __forceinline__ void epilogue_hidden(uint32_t tmem_base, const float* __restrict__ bias, uint8_t* dst, int warp, int lane) {
+  constexpr int PER = kN / 4;                       // columns per warp: 64, 32 or 16
   const int row = (warp & 3) * 32 + lane;
-  const int col_begin = (warp >> 2) * (kN / 2), col_end = col_begin + kN / 2;
-  const uint32_t taddr_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-#pragma unroll 1
-  for (int c0 = col_begin; c0 < col_end; c0 += 16) {
-    float v[16];
-    tmem_ld16(taddr_row + (uint32_t)c0, v);
+  const int c0 = (warp >> 2) * PER;
+  const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)c0;
+  if constexpr (PER == 64) {
+    uint32_t a[32], b[32];
+    tmem_ld32(taddr, a);
+    tmem_ld32(taddr + 32, b);
+    tmem_wait();
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      float e[8];
+    for (int k = 0; k < 4; ++k) emit_chunk(a + 8 * k, bias + c0 + 8 * k, dst + elem_offset(TM, row, c0 + 8 * k));
 #pragma unroll
-      for (int i = 0; i < 8; ++i) e[i] = elu(v[8 * h + i] + bias[c0 + 8 * h + i]);
-      uint4 pk = make_uint4(pack_bf16(e[0], e[1]), pack_bf16(e[2], e[3]), pack_bf16(e[4], e[5]), pack_bf16(e[6], e[7]));
-      *reinterpret_cast<uint4*>(dst + elem_offset(TM, row, c0 + 8 * h)) = pk;
-    }
+    for (int k = 0; k < 4; ++k) emit_chunk(b + 8 * k, bias + c0 + 32 + 8 * k, dst + elem_offset(TM, row, c0 + 32 + 8 * k));
+  } else if constexpr (PER == 32) {
+    uint32_t a[32];
+    tmem_ld32(taddr, a);
+    tmem_wait();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) emit_chunk(a + 8 * k, bias + c0 + 8 * k, dst + elem_offset(TM, row, c0 + 8 * k));
+  } else {
+    uint32_t a[16];
+    tmem_ld16(taddr, a);
+    tmem_wait();
+#pragma unroll
+    for (int k = 0; k < 2; ++k) emit_chunk(a + 8 * k, bias + c0 + 8 * k, dst + elem_offset(TM, row, c0 + 8 * k));
   }
 }
 
@@ -257,8 +288,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_mlp_forward(const Args a) {
     mbar_wait(&bar_mma, ph_mma); ph_mma ^= 1;
     tc_fence_after();
     if (warp < 4) {
+      uint32_t acc[16];
+      tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16), acc);
+      tmem_wait();
       float v[16];
-      tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16), v);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[j]);
       const int row = warp * 32 + lane;
       if (row < rows) {
         float* m = a.mu + (size_t)(row0 + row) * 12;
