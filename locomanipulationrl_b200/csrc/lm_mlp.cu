@@ -4,14 +4,17 @@
 // cfg/train/JointLocomanipulationPPO.yaml:10-32):
 //   x[64] -> Linear(64,256) ELU -> Linear(256,128) ELU -> Linear(128,64) ELU -> { mean Linear(64,12), value Linear(64,1) }
 //
-// One CTA per SM, 512 threads (16 epilogue warps: 4 TMEM lane groups x 4 column quarters).  All four weight matrices (bf16, 115 KB) are pulled into shared memory
-// once per CTA by a TMA bulk copy and stay there; the CTA then walks 128-env tiles:
-//   TMA bulk load of the fp32 obs tile -> normalise/clamp -> bf16 A operand in the UMMA canonical
-//   K-major layout -> tcgen05.mma (M=128, N=256/128/64/16, fp32 accumulators in TMEM) ->
-//   tcgen05.ld epilogue (+bias, ELU, bf16) writes the next layer's A operand straight back to shared
-//   memory.  Activations never touch HBM; per env the kernel reads 256 B and writes 52 B.
-// The next tile's obs load is issued as soon as its staging region is free, so it overlaps the
-// last two layers of the current tile.
+// One CTA per SM: 16 epilogue warps (4 TMEM lane groups x 4 column quarters) + 1 control warp whose lane 0 issues
+// every tcgen05.mma.  All four weight matrices (bf16, 115 KB) are pulled into shared memory once per CTA by a TMA
+// bulk copy and stay there; the CTA then walks 128-env tiles as a chunk-level pipeline:
+//   * the epilogue of layer L (tcgen05.ld -> +bias, ELU, bf16 -> next A operand in shared memory) proceeds in 64-column
+//     sub-steps; each finished sub-step is one K chunk of layer L+1, whose MMAs are issued at once, so the tensor
+//     pipe runs underneath the epilogue instead of after it;
+//   * every layer has its own TMEM accumulator columns (256 + 128 + 64 + 16 of the 512), so the next tile's layer-1
+//     MMA is issued while the current tile is still in layers 2-4;
+//   * the next tile's observations are fetched into registers one tile ahead (coalesced 128-bit loads),
+//     normalised/clamped and written as the bf16 A0 operand in the bubble between the layer-1 and layer-2 epilogues.
+// Activations never touch HBM; per env the kernel reads 256 B and writes 52 B.
 #include <cuda_bf16.h>
 
 #include "lm_common.cuh"
@@ -21,7 +24,9 @@ namespace lm {
 namespace mlp {
 
 constexpr int TM = 128;                 // rows (envs) per tile == UMMA M
-constexpr int THREADS = 512;              // 16 warps: 4 TMEM lane groups x 4 column quarters
+constexpr int E_WARPS = 16;               // epilogue warps: 4 TMEM lane groups x 4 column quarters
+constexpr int E_THREADS = E_WARPS * 32;
+constexpr int THREADS = E_THREADS + 32;   // + the control warp (MMA issue, weight TMA)
 constexpr int D0 = 64, D1 = 256, D2 = 128, D3 = 64, DH = 16;   // head: 12 mean + 1 value + 3 pad
 
 // UMMA canonical K-major, no swizzle: core matrix = 8 rows x 16 B, rows 16 B apart; core matrices
@@ -42,15 +47,16 @@ constexpr int BIAS_OFF = WH_OFF + operand_bytes(DH, D3);          // fp32 biases
 constexpr int BLOB_BYTES = BIAS_OFF + (D1 + D2 + D3 + DH) * 4;
 static_assert(BLOB_BYTES % 16 == 0 && W2_OFF % 16 == 0 && W3_OFF % 16 == 0 && WH_OFF % 16 == 0 && BIAS_OFF % 16 == 0, "align");
 
-// activation regions
-constexpr int RA_BYTES = operand_bytes(TM, D2);                   // A2 [128 x 128]; also the fp32 obs stage (32 KB)
-constexpr int RB_BYTES = operand_bytes(TM, D1);                   // A1 [128 x 256]; also A0, A3
-static_assert(RA_BYTES >= TM * D0 * 4, "obs stage must fit region A");
-constexpr int RA_OFF = BLOB_BYTES;
-constexpr int RB_OFF = RA_OFF + RA_BYTES;
-constexpr int NORM_OFF = RB_OFF + RB_BYTES;                       // mean[64], inv_std[64] fp32
-constexpr int SMEM_BYTES = NORM_OFF + 2 * D0 * 4 + 64;
+// activation regions (bf16 A operands).  A2 aliases A1: layer 2 has finished reading A1 when the layer-2 epilogue starts.
+constexpr int ACT_OFF = BLOB_BYTES;                               // A1 [128 x 256]; A2 [128 x 128] at +0
+constexpr int ACT_BYTES = operand_bytes(TM, D1);
+constexpr int A0_OFF = ACT_OFF + ACT_BYTES;                       // A0 [128 x 64]
+constexpr int A3_OFF = A0_OFF + operand_bytes(TM, D0);            // A3 [128 x 64]
+constexpr int SMEM_BYTES = A3_OFF + operand_bytes(TM, D3) + 64;
 static_assert(SMEM_BYTES <= 232448, "exceeds 227 KB");
+static_assert(ACT_OFF % 16 == 0 && A0_OFF % 16 == 0 && A3_OFF % 16 == 0, "align");
+// TMEM accumulator columns
+constexpr uint32_t ACC1_COL = 0, ACC2_COL = 256, ACC3_COL = 384, ACCH_COL = 448, TMEM_COLS = 512;
 
 // ---------------------------------------------------------------- tcgen05 wrappers
 __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, int lbo) {
@@ -106,66 +112,70 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t r[32]) {
 }
 __device__ __forceinline__ void tmem_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-__device__ __forceinline__ float elu(float x) { return x > 0.0f ? x : __expf(x) - 1.0f; }   // nn.ELU(alpha=1)
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// nn.ELU(alpha=1) = max(x, min(exp(x) - 1, 0)): exp(x) - 1 >= x everywhere, and it is > 0 exactly when x > 0
+__device__ __forceinline__ float elu(float x) {
+  return fmaxf(x, fminf(ex2_approx(x * 1.4426950408889634f) - 1.0f, 0.0f));
+}
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-// issue the K/16 MMAs of one layer (single thread) and commit to `bar`
-template <int kN, int kK>
-__device__ __forceinline__ void issue_layer(uint32_t tmem_d, uint32_t a_saddr, uint32_t b_saddr, uint64_t* bar) {
-  tc_fence_after();
+// the K/16 MMAs [ks0, ks0 + nks) of one layer (single thread)
+template <int kN>
+__device__ __forceinline__ void issue_ksteps(uint32_t tmem_d, uint32_t a_saddr, uint32_t b_saddr, int ks0, int nks) {
   constexpr uint32_t idesc = instr_desc(TM, kN);
 #pragma unroll
-  for (int ks = 0; ks < kK / 16; ++ks) {
-    const uint64_t ad = smem_desc(a_saddr + ks * 2 * lbo_bytes(TM), lbo_bytes(TM));
-    const uint64_t bd = smem_desc(b_saddr + ks * 2 * lbo_bytes(kN), lbo_bytes(kN));
-    umma_bf16(tmem_d, ad, bd, idesc, ks > 0 ? 1u : 0u);
+  for (int i = 0; i < 4; ++i) {
+    if (i < nks) {
+      const int ks = ks0 + i;
+      const uint64_t ad = smem_desc(a_saddr + ks * 2 * lbo_bytes(TM), lbo_bytes(TM));
+      const uint64_t bd = smem_desc(b_saddr + ks * 2 * lbo_bytes(kN), lbo_bytes(kN));
+      umma_bf16(tmem_d, ad, bd, idesc, ks > 0 ? 1u : 0u);
+    }
   }
-  umma_commit(bar);
 }
 
-// 8 accumulator columns -> +bias, ELU, bf16 -> one 16-byte K chunk of the next A operand
-__device__ __forceinline__ void emit_chunk(const uint32_t* acc, const float* __restrict__ bias, uint8_t* dst) {
-  const float4 b0 = *reinterpret_cast<const float4*>(bias), b1 = *reinterpret_cast<const float4*>(bias + 4);
-  const float e0 = elu(__uint_as_float(acc[0]) + b0.x), e1 = elu(__uint_as_float(acc[1]) + b0.y);
-  const float e2 = elu(__uint_as_float(acc[2]) + b0.z), e3 = elu(__uint_as_float(acc[3]) + b0.w);
-  const float e4 = elu(__uint_as_float(acc[4]) + b1.x), e5 = elu(__uint_as_float(acc[5]) + b1.y);
-  const float e6 = elu(__uint_as_float(acc[6]) + b1.z), e7 = elu(__uint_as_float(acc[7]) + b1.w);
-  *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16(e0, e1), pack_bf16(e2, e3), pack_bf16(e4, e5), pack_bf16(e6, e7));
+// 16 accumulator columns [c0, c0+16) of row `row` -> +bias, ELU, bf16 -> two 16-byte K chunks of the next A operand
+__device__ __forceinline__ void emit16(const uint32_t* acc, const float* __restrict__ bias, uint8_t* dst, int row, int c0) {
+  uint32_t w[8];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float4 b = *reinterpret_cast<const float4*>(bias + c0 + 4 * k);
+    w[2 * k] = pack_bf16(elu(__uint_as_float(acc[4 * k]) + b.x), elu(__uint_as_float(acc[4 * k + 1]) + b.y));
+    w[2 * k + 1] = pack_bf16(elu(__uint_as_float(acc[4 * k + 2]) + b.z), elu(__uint_as_float(acc[4 * k + 3]) + b.w));
+  }
+  *reinterpret_cast<uint4*>(dst + elem_offset(TM, row, c0)) = make_uint4(w[0], w[1], w[2], w[3]);
+  *reinterpret_cast<uint4*>(dst + elem_offset(TM, row, c0 + 8)) = make_uint4(w[4], w[5], w[6], w[7]);
 }
 
-// hidden-layer epilogue: TMEM fp32 [128 x kN] -> +bias, ELU, bf16 -> next A operand (K = kN) in `dst`.
-// Warp w owns TMEM lanes 32*(w&3).. and the column quarter (w>>2); all of its columns are fetched with one or two
-// asynchronous tcgen05.ld before the single wait, so the TMEM latency is paid once per layer.
-template <int kN>
-__device__ __forceinline__ void epilogue_hidden(uint32_t tmem_base, const float* __restrict__ bias, uint8_t* dst, int warp, int lane) {
-  constexpr int PER = kN / 4;                       // columns per warp: 64, 32 or 16
-  const int row = (warp & 3) * 32 + lane;
-  const int c0 = (warp >> 2) * PER;
-  const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)c0;
-  if constexpr (PER == 64) {
-    uint32_t a[32], b[32];
-    tmem_ld32(taddr, a);
-    tmem_ld32(taddr + 32, b);
-    tmem_wait();
+// Hidden-layer epilogue of one warp: kSub sub-steps; in sub-step s the 16 warps together cover accumulator columns
+// [64 s, 64 s + 64) (this warp: 16 of them), i.e. K chunk s of the next layer, and signal `bars[s]`.  The TMEM load
+// of sub-step s+1 is in flight while sub-step s is being processed.
+template <int kSub>
+__device__ __forceinline__ void epilogue_hidden(uint32_t tmem_acc, const float* __restrict__ bias, uint8_t* dst, uint64_t* bars,
+                                                int g, int q, int lane) {
+  const int row = g * 32 + lane;
+  const uint32_t taddr = tmem_acc + ((uint32_t)(g * 32) << 16) + (uint32_t)(q * 16);
+  uint32_t a[16], b[16];
+  tmem_ld16(taddr, a);
+  tmem_wait();
 #pragma unroll
-    for (int k = 0; k < 4; ++k) emit_chunk(a + 8 * k, bias + c0 + 8 * k, dst + elem_offset(TM, row, c0 + 8 * k));
-#pragma unroll
-    for (int k = 0; k < 4; ++k) emit_chunk(b + 8 * k, bias + c0 + 32 + 8 * k, dst + elem_offset(TM, row, c0 + 32 + 8 * k));
-  } else if constexpr (PER == 32) {
-    uint32_t a[32];
-    tmem_ld32(taddr, a);
-    tmem_wait();
-#pragma unroll
-    for (int k = 0; k < 4; ++k) emit_chunk(a + 8 * k, bias + c0 + 8 * k, dst + elem_offset(TM, row, c0 + 8 * k));
-  } else {
-    uint32_t a[16];
-    tmem_ld16(taddr, a);
-    tmem_wait();
-#pragma unroll
-    for (int k = 0; k < 2; ++k) emit_chunk(a + 8 * k, bias + c0 + 8 * k, dst + elem_offset(TM, row, c0 + 8 * k));
+  for (int s = 0; s < kSub; ++s) {
+    uint32_t* cur = (s & 1) ? b : a;
+    uint32_t* nxt = (s & 1) ? a : b;
+    if (s + 1 < kSub) tmem_ld16(taddr + 64 * (s + 1), nxt);
+    emit16(cur, bias, dst, row, 64 * s + q * 16);
+    fence_proxy_async();                       // generic-proxy A operand writes -> visible to the tensor core's async proxy
+    if (s + 1 < kSub) tmem_wait();
+    tc_fence_before();                         // orders this warp's tcgen05.ld before the MMA that reuses the accumulator
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&bars[s]);
   }
 }
 
@@ -181,136 +191,194 @@ struct Args {
   int num_tiles;
 };
 
+struct ObsRegs { float4 v[4]; };
+
+// thread tid of the 512 epilogue threads owns float4 (j*512 + tid) of the [128 x 64] fp32 tile: row j*32 + tid/16, columns 4*(tid%16)..
+__device__ __forceinline__ void obs_fetch(const Args& a, int tile, int tid, ObsRegs& r) {
+  const int rows = min(TM, a.n - tile * TM);
+  const float* base = a.obs + (size_t)tile * TM * D0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int row = j * 32 + (tid >> 4);
+    r.v[j] = row < rows ? ld_nc_f4(base + (size_t)(j * E_THREADS + tid) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+__device__ __forceinline__ void obs_convert(const Args& a, int tile, int tid, const ObsRegs& r, const float4& mean, const float4& inv_std,
+                                            bool has_norm, uint8_t* A0) {
+  const int rows = min(TM, a.n - tile * TM);
+  const int c4 = tid & 15;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int row = j * 32 + (tid >> 4);
+    float4 x = r.v[j];
+    if (has_norm && row < rows) {
+      x.x = fminf(fmaxf((x.x - mean.x) * inv_std.x, -a.norm_clip), a.norm_clip);
+      x.y = fminf(fmaxf((x.y - mean.y) * inv_std.y, -a.norm_clip), a.norm_clip);
+      x.z = fminf(fmaxf((x.z - mean.z) * inv_std.z, -a.norm_clip), a.norm_clip);
+      x.w = fminf(fmaxf((x.w - mean.w) * inv_std.w, -a.norm_clip), a.norm_clip);
+    }
+    *reinterpret_cast<uint2*>(A0 + elem_offset(TM, row, 4 * c4)) = make_uint2(pack_bf16(x.x, x.y), pack_bf16(x.z, x.w));
+  }
+}
+
+// head epilogue of one lane-group warp: 16 accumulator columns -> +bias -> mu[12], value
+__device__ __forceinline__ void epilogue_head(const Args& a, uint32_t tmem_acc, const float* __restrict__ biash, int tile, int g, int lane) {
+  uint32_t acc[16];
+  tmem_ld16(tmem_acc + ((uint32_t)(g * 32) << 16), acc);
+  tmem_wait();
+  tc_fence_before();
+  const int row0 = tile * TM, rows = min(TM, a.n - row0);
+  const int row = g * 32 + lane;
+  if (row < rows) {
+    float o[13];
+#pragma unroll
+    for (int j = 0; j < 13; ++j) o[j] = __uint_as_float(acc[j]) + biash[j];
+    float4* m = reinterpret_cast<float4*>(a.mu + (size_t)(row0 + row) * 12);
+    m[0] = make_float4(o[0], o[1], o[2], o[3]);
+    m[1] = make_float4(o[4], o[5], o[6], o[7]);
+    m[2] = make_float4(o[8], o[9], o[10], o[11]);
+    a.value[row0 + row] = o[12];
+  }
+}
+
 __global__ void __launch_bounds__(THREADS, 1) k_mlp_forward(const Args a) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ uint64_t bar_w, bar_obs, bar_mma;
+  // mbarriers.  count 1: bar_w (weight TMA), bar_acc* (tcgen05.commit).  count 16 (one arrive per epilogue warp):
+  // bar_a0 (A0 operand written), bar_act1[s] / bar_act2[s] / bar_act3 (K chunk s of the next layer's A operand written
+  // and, for the last sub-step, the accumulator fully read).  Every barrier completes exactly once per tile.
+  __shared__ uint64_t bar_w, bar_a0, bar_acc1, bar_acc2, bar_acc3, bar_acch, bar_act1[4], bar_act2[2], bar_act3[1];
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  uint8_t* RA = smem + RA_OFF;
-  uint8_t* RB = smem + RB_OFF;
-  float* norm = reinterpret_cast<float*>(smem + NORM_OFF);
+  uint8_t* ACT = smem + ACT_OFF;
+  uint8_t* A0 = smem + A0_OFF;
+  uint8_t* A3 = smem + A3_OFF;
   const float* bias1 = reinterpret_cast<const float*>(smem + BIAS_OFF);
   const float* bias2 = bias1 + D1;
   const float* bias3 = bias2 + D2;
   const float* biash = bias3 + D3;
 
   if (tid == 0) {
-    mbar_init(&bar_w, 1); mbar_init(&bar_obs, 1); mbar_init(&bar_mma, 1);
+    mbar_init(&bar_w, 1); mbar_init(&bar_a0, E_WARPS);
+    mbar_init(&bar_acc1, 1); mbar_init(&bar_acc2, 1); mbar_init(&bar_acc3, 1); mbar_init(&bar_acch, 1);
+    for (int s = 0; s < 4; ++s) mbar_init(&bar_act1[s], E_WARPS);
+    for (int s = 0; s < 2; ++s) mbar_init(&bar_act2[s], E_WARPS);
+    mbar_init(&bar_act3[0], E_WARPS);
     fence_mbar_init();
   }
-  if (warp == 0) tmem_alloc(&tmem_slot, 256);
-  if (tid < D0) {
-    norm[tid] = a.norm_mean ? a.norm_mean[tid] : 0.0f;
-    norm[D0 + tid] = a.norm_inv_std ? a.norm_inv_std[tid] : 1.0f;
-  }
+  if (warp == E_WARPS) tmem_alloc(&tmem_slot, TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
+  const int tile0 = blockIdx.x, stride = gridDim.x;
 
-  int tile = blockIdx.x;
-  if (tid == 0) {
-    // resident weights + biases: one bulk copy per CTA
-    mbar_expect_tx(&bar_w, BLOB_BYTES);
-    tma_load_1d(smem, a.blob, BLOB_BYTES, &bar_w);
-    if (tile < a.num_tiles) {
-      const int rows = min(TM, a.n - tile * TM);
-      mbar_expect_tx(&bar_obs, (uint32_t)rows * D0 * 4);
-      tma_load_1d(RA, a.obs + (size_t)tile * TM * D0, (uint32_t)rows * D0 * 4, &bar_obs);
-    }
-  }
-  mbar_wait(&bar_w, 0);
-  uint32_t ph_obs = 0, ph_mma = 0;
-  const bool has_norm = a.norm_mean != nullptr;
-
-  for (; tile < a.num_tiles; tile += gridDim.x) {
-    const int row0 = tile * TM;
-    const int rows = min(TM, a.n - row0);
-    // ---- obs tile fp32 (region A) -> normalise/clamp -> bf16 A0 (region B)
-    mbar_wait(&bar_obs, ph_obs); ph_obs ^= 1;
-    for (int i = tid; i < TM * (D0 / 8); i += THREADS) {
-      const int row = i >> 3, c = i & 7;
-      float x[8];
-      if (row < rows) {
-        const float4 p = *reinterpret_cast<const float4*>(RA + row * (D0 * 4) + c * 32);
-        const float4 q = *reinterpret_cast<const float4*>(RA + row * (D0 * 4) + c * 32 + 16);
-        x[0] = p.x; x[1] = p.y; x[2] = p.z; x[3] = p.w; x[4] = q.x; x[5] = q.y; x[6] = q.z; x[7] = q.w;
-        if (has_norm) {
+  if (warp == E_WARPS) {
+    // ================================================================== control warp: one thread issues TMA + every MMA
+    if (lane == 0) {
+      mbar_expect_tx(&bar_w, BLOB_BYTES);
+      tma_load_1d(smem, a.blob, BLOB_BYTES, &bar_w);      // resident weights + biases: one bulk copy per CTA
+      mbar_wait(&bar_w, 0);
+      const uint32_t sW1 = smem_u32(smem + W1_OFF), sW2 = smem_u32(smem + W2_OFF), sW3 = smem_u32(smem + W3_OFF), sWH = smem_u32(smem + WH_OFF);
+      const uint32_t sACT = smem_u32(ACT), sA0 = smem_u32(A0), sA3 = smem_u32(A3);
+      if (tile0 < a.num_tiles) {
+        mbar_wait(&bar_a0, 0);
+        tc_fence_after();
+        issue_ksteps<D1>(tmem + ACC1_COL, sA0, sW1, 0, 4);
+        umma_commit(&bar_acc1);
+      }
+      uint32_t it = 0;
+      for (int tile = tile0; tile < a.num_tiles; tile += stride, ++it) {
+        const uint32_t ph = it & 1;
+        // layer 2: K chunk s as soon as the layer-1 epilogue has produced it
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float y = (x[j] - norm[c * 8 + j]) * norm[D0 + c * 8 + j];
-            x[j] = fminf(fmaxf(y, -a.norm_clip), a.norm_clip);
-          }
+        for (int s = 0; s < 4; ++s) {
+          mbar_wait(&bar_act1[s], ph);
+          tc_fence_after();
+          issue_ksteps<D2>(tmem + ACC2_COL, sACT, sW2, 4 * s, 4);
         }
-      } else {
+        umma_commit(&bar_acc2);
+        // next tile's layer 1 (its accumulator columns were released by the last layer-1 sub-step above)
+        if (tile + stride < a.num_tiles) {
+          mbar_wait(&bar_a0, ph ^ 1);
+          tc_fence_after();
+          issue_ksteps<D1>(tmem + ACC1_COL, sA0, sW1, 0, 4);
+          umma_commit(&bar_acc1);
+        }
+        // layer 3
 #pragma unroll
-        for (int j = 0; j < 8; ++j) x[j] = 0.0f;
-      }
-      *reinterpret_cast<uint4*>(RB + elem_offset(TM, row, c * 8)) =
-          make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]), pack_bf16(x[6], x[7]));
-    }
-    fence_proxy_async();
-    tc_fence_before();
-    __syncthreads();
-    // ---- layer 1: [128x64] x W1^T -> TMEM[128x256]
-    if (tid == 0) issue_layer<D1, D0>(tmem, smem_u32(RB), smem_u32(smem + W1_OFF), &bar_mma);
-    mbar_wait(&bar_mma, ph_mma); ph_mma ^= 1;
-    tc_fence_after();
-    epilogue_hidden<D1>(tmem, bias1, RB, warp, lane);          // A1 overwrites A0 (layer-1 MMA has completed)
-    fence_proxy_async();
-    tc_fence_before();
-    __syncthreads();
-    // ---- layer 2: [128x256] x W2^T -> TMEM[128x128]
-    if (tid == 0) issue_layer<D2, D1>(tmem, smem_u32(RB), smem_u32(smem + W2_OFF), &bar_mma);
-    mbar_wait(&bar_mma, ph_mma); ph_mma ^= 1;
-    tc_fence_after();
-    epilogue_hidden<D2>(tmem, bias2, RA, warp, lane);          // A2 -> region A (obs stage already consumed)
-    fence_proxy_async();
-    tc_fence_before();
-    __syncthreads();
-    // ---- layer 3: [128x128] x W3^T -> TMEM[128x64]
-    if (tid == 0) issue_layer<D3, D2>(tmem, smem_u32(RA), smem_u32(smem + W3_OFF), &bar_mma);
-    mbar_wait(&bar_mma, ph_mma); ph_mma ^= 1;
-    tc_fence_after();
-    // region A is free again: prefetch the next tile's obs while layers 3-4 finish
-    const int next = tile + gridDim.x;
-    if (tid == 0 && next < a.num_tiles) {
-      const int nrows = min(TM, a.n - next * TM);
-      mbar_expect_tx(&bar_obs, (uint32_t)nrows * D0 * 4);
-      tma_load_1d(RA, a.obs + (size_t)next * TM * D0, (uint32_t)nrows * D0 * 4, &bar_obs);
-    }
-    epilogue_hidden<D3>(tmem, bias3, RB, warp, lane);          // A3 -> region B
-    fence_proxy_async();
-    tc_fence_before();
-    __syncthreads();
-    // ---- heads: [128x64] x Wh^T -> TMEM[128x16]  (cols 0..11 mean, 12 value)
-    if (tid == 0) issue_layer<DH, D3>(tmem, smem_u32(RB), smem_u32(smem + WH_OFF), &bar_mma);
-    mbar_wait(&bar_mma, ph_mma); ph_mma ^= 1;
-    tc_fence_after();
-    if (warp < 4) {
-      uint32_t acc[16];
-      tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16), acc);
-      tmem_wait();
-      float v[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[j]);
-      const int row = warp * 32 + lane;
-      if (row < rows) {
-        float* m = a.mu + (size_t)(row0 + row) * 12;
-        float o[13];
-#pragma unroll
-        for (int j = 0; j < 13; ++j) o[j] = v[j] + biash[j];
-        reinterpret_cast<float4*>(m)[0] = make_float4(o[0], o[1], o[2], o[3]);
-        reinterpret_cast<float4*>(m)[1] = make_float4(o[4], o[5], o[6], o[7]);
-        reinterpret_cast<float4*>(m)[2] = make_float4(o[8], o[9], o[10], o[11]);
-        a.value[row0 + row] = o[12];
+        for (int s = 0; s < 2; ++s) {
+          mbar_wait(&bar_act2[s], ph);
+          tc_fence_after();
+          issue_ksteps<D3>(tmem + ACC3_COL, sACT, sW3, 4 * s, 4);
+        }
+        umma_commit(&bar_acc3);
+        // heads
+        mbar_wait(&bar_act3[0], ph);
+        tc_fence_after();
+        issue_ksteps<DH>(tmem + ACCH_COL, sA3, sWH, 0, 4);
+        umma_commit(&bar_acch);
       }
     }
-    tc_fence_before();
-    __syncthreads();   // all TMEM reads done before the next tile's layer-1 MMA overwrites the accumulator
+  } else {
+    // ================================================================== epilogue warps
+    const int g = warp & 3, q = warp >> 2;
+    const bool has_norm = a.norm_mean != nullptr;
+    float4 mean = make_float4(0.f, 0.f, 0.f, 0.f), inv_std = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (has_norm) {
+      mean = *reinterpret_cast<const float4*>(a.norm_mean + 4 * (tid & 15));
+      inv_std = *reinterpret_cast<const float4*>(a.norm_inv_std + 4 * (tid & 15));
+    }
+    ObsRegs regs;
+    if (tile0 < a.num_tiles) {
+      obs_fetch(a, tile0, tid, regs);
+      obs_convert(a, tile0, tid, regs, mean, inv_std, has_norm, A0);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_a0);
+      if (tile0 + stride < a.num_tiles) obs_fetch(a, tile0 + stride, tid, regs);
+    }
+    mbar_wait(&bar_w, 0);                                  // biases live in the weight blob
+    uint32_t it = 0;
+    for (int tile = tile0; tile < a.num_tiles; tile += stride, ++it) {
+      const uint32_t ph = it & 1;
+      const int next = tile + stride;
+      // ---- layer-1 epilogue: TMEM[128 x 256] -> A1 (4 K chunks for layer 2)
+      mbar_wait(&bar_acc1, ph);
+      tc_fence_after();
+      epilogue_hidden<4>(tmem + ACC1_COL, bias1, ACT, bar_act1, g, q, lane);
+      // ---- next tile's observations -> A0 (layer 1 of this tile has consumed A0), then fetch the tile after it
+      if (next < a.num_tiles) {
+        obs_convert(a, next, tid, regs, mean, inv_std, has_norm, A0);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_a0);
+        if (next + stride < a.num_tiles) obs_fetch(a, next + stride, tid, regs);
+      }
+      // ---- previous tile's heads (its MMA finished long ago)
+      if (q == 0 && it > 0) {
+        mbar_wait(&bar_acch, ph ^ 1);
+        tc_fence_after();
+        epilogue_head(a, tmem + ACCH_COL, biash, tile - stride, g, lane);
+      }
+      // ---- layer-2 epilogue: TMEM[128 x 128] -> A2 (aliases A1: layer 2 is complete), 2 K chunks for layer 3
+      mbar_wait(&bar_acc2, ph);
+      tc_fence_after();
+      epilogue_hidden<2>(tmem + ACC2_COL, bias2, ACT, bar_act2, g, q, lane);
+      // ---- layer-3 epilogue: TMEM[128 x 64] -> A3
+      mbar_wait(&bar_acc3, ph);
+      tc_fence_after();
+      epilogue_hidden<1>(tmem + ACC3_COL, bias3, A3, bar_act3, g, q, lane);
+    }
+    if (q == 0 && it > 0) {
+      mbar_wait(&bar_acch, (it - 1) & 1);
+      tc_fence_after();
+      epilogue_head(a, tmem + ACCH_COL, biash, tile0 + (int)(it - 1) * stride, g, lane);
+    }
   }
+  tc_fence_before();
+  __syncthreads();
   tc_fence_after();
-  if (warp == 0) tmem_dealloc(tmem, 256);
+  if (warp == E_WARPS) tmem_dealloc(tmem, TMEM_COLS);
 }
 
 // fp32 nn.Linear [out,in] -> bf16 canonical operand; rows >= out are zero
