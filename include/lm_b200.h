@@ -205,6 +205,10 @@ int lm_mlp_pack(LmMlp* mlp, const float* w1, const float* b1, const float* w2, c
 int lm_mlp_forward(LmMlp* mlp, const float* obs, const float* norm_mean, const float* norm_inv_std,
                    float norm_clip, float* mu, float* value, int32_t n, void* stream);
 
+/* Diagnostic: when stamps_dev != NULL (device buffer of >= 256 int64), CTA 0 of every following lm_mlp_forward records
+ * clock64() at its pipeline stages (see csrc/lm_mlp.cu `stamp`).  NULL switches it off (the default). */
+int lm_mlp_set_timeline(LmMlp* mlp, long long* stamps_dev);
+
 /* GNN limb-graph policy forward (scripts/graph_model_orebot_ov.py:11-241; wired at
  * scripts/skrl_ppo_locomanipulation.py:44-49 with hidden 32).  fp32.  Weights are the module's
  * own tensors in nn.Linear layout, concatenated by lm_gnn_pack in a fixed order. */

@@ -84,6 +84,7 @@ SYMBOLS = {
     "lm_mlp_destroy": (None, [_vp]),
     "lm_mlp_pack": (C.c_int, [_vp] * 11 + [_vp]),
     "lm_mlp_forward": (C.c_int, [_vp, _vp, _vp, _vp, _f, _vp, _vp, _i32, _vp]),
+    "lm_mlp_set_timeline": (C.c_int, [_vp, _vp]),
     "lm_gnn_create": (_vp, [C.c_int]),
     "lm_gnn_destroy": (None, [_vp]),
     "lm_gnn_pack": (C.c_int, [_vp, C.POINTER(_vp), _i32, _vp]),

@@ -47,14 +47,16 @@ constexpr int BIAS_OFF = WH_OFF + operand_bytes(DH, D3);          // fp32 biases
 constexpr int BLOB_BYTES = BIAS_OFF + (D1 + D2 + D3 + DH) * 4;
 static_assert(BLOB_BYTES % 16 == 0 && W2_OFF % 16 == 0 && W3_OFF % 16 == 0 && WH_OFF % 16 == 0 && BIAS_OFF % 16 == 0, "align");
 
-// activation regions (bf16 A operands).  A2 aliases A1: layer 2 has finished reading A1 when the layer-2 epilogue starts.
-constexpr int ACT_OFF = BLOB_BYTES;                               // A1 [128 x 256]; A2 [128 x 128] at +0
-constexpr int ACT_BYTES = operand_bytes(TM, D1);
-constexpr int A0_OFF = ACT_OFF + ACT_BYTES;                       // A0 [128 x 64]
-constexpr int A3_OFF = A0_OFF + operand_bytes(TM, D0);            // A3 [128 x 64]
-constexpr int SMEM_BYTES = A3_OFF + operand_bytes(TM, D3) + 64;
+// activation regions (bf16 A operands).  A1 [128 x 256] never exists as a whole: the layer-1 epilogue produces it in four
+// 64-column K chunks that layer 2 consumes at once, so a ring of two chunk slots is enough.
+constexpr int CHUNK_BYTES = operand_bytes(TM, 64);                // one 64-wide K chunk of an A operand (= A0, A3)
+constexpr int RING_OFF = BLOB_BYTES;                              // A1 chunk ring: 2 slots
+constexpr int A2_OFF = RING_OFF + 2 * CHUNK_BYTES;                // A2 [128 x 128]
+constexpr int A0_OFF = A2_OFF + operand_bytes(TM, D2);            // A0 [128 x 64]
+constexpr int A3_OFF = A0_OFF + CHUNK_BYTES;                      // A3 [128 x 64]
+constexpr int SMEM_BYTES = A3_OFF + CHUNK_BYTES + 64;
 static_assert(SMEM_BYTES <= 232448, "exceeds 227 KB");
-static_assert(ACT_OFF % 16 == 0 && A0_OFF % 16 == 0 && A3_OFF % 16 == 0, "align");
+static_assert(RING_OFF % 16 == 0 && CHUNK_BYTES % 16 == 0, "align");
 // TMEM accumulator columns
 constexpr uint32_t ACC1_COL = 0, ACC2_COL = 256, ACC3_COL = 384, ACCH_COL = 448, TMEM_COLS = 512;
 
@@ -126,19 +128,34 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-// the K/16 MMAs [ks0, ks0 + nks) of one layer (single thread)
+// four K/16 MMAs of one layer (single thread): k-steps [ks0, ks0 + 4) of the B operand; the A operand's K chunk starts at
+// `a_saddr` (k-step 0 there)
 template <int kN>
-__device__ __forceinline__ void issue_ksteps(uint32_t tmem_d, uint32_t a_saddr, uint32_t b_saddr, int ks0, int nks) {
+__device__ __forceinline__ void issue_ksteps(uint32_t tmem_d, uint32_t a_saddr, uint32_t b_saddr, int ks0) {
   constexpr uint32_t idesc = instr_desc(TM, kN);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    if (i < nks) {
-      const int ks = ks0 + i;
-      const uint64_t ad = smem_desc(a_saddr + ks * 2 * lbo_bytes(TM), lbo_bytes(TM));
-      const uint64_t bd = smem_desc(b_saddr + ks * 2 * lbo_bytes(kN), lbo_bytes(kN));
-      umma_bf16(tmem_d, ad, bd, idesc, ks > 0 ? 1u : 0u);
-    }
+    const uint64_t ad = smem_desc(a_saddr + i * 2 * lbo_bytes(TM), lbo_bytes(TM));
+    const uint64_t bd = smem_desc(b_saddr + (ks0 + i) * 2 * lbo_bytes(kN), lbo_bytes(kN));
+    umma_bf16(tmem_d, ad, bd, idesc, (ks0 + i) > 0 ? 1u : 0u);
   }
+}
+
+// packed fp32x2 arithmetic (sm_100: FADD2 / FMUL2 — one issue slot for two lanes' worth of work)
+__device__ __forceinline__ uint64_t pk2(float lo, float hi) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ uint64_t pk2u(uint32_t lo, uint32_t hi) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi)); return r; }
+__device__ __forceinline__ void upk2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) { uint64_t r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) { uint64_t r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+
+// two accumulator columns -> +bias, ELU -> packed bf16x2.  ELU(x) = max(x, min(exp(x) - 1, 0)).
+__device__ __forceinline__ uint32_t elu_pair(uint32_t acc_lo, uint32_t acc_hi, float b_lo, float b_hi) {
+  const uint64_t x2 = add2(pk2u(acc_lo, acc_hi), pk2(b_lo, b_hi));
+  float t0, t1, x0, x1, r0, r1;
+  upk2(mul2(x2, pk2(1.4426950408889634f, 1.4426950408889634f)), t0, t1);
+  upk2(add2(pk2(ex2_approx(t0), ex2_approx(t1)), pk2(-1.0f, -1.0f)), r0, r1);
+  upk2(x2, x0, x1);
+  return pack_bf16(fmaxf(x0, fminf(r0, 0.0f)), fmaxf(x1, fminf(r1, 0.0f)));
 }
 
 // 16 accumulator columns [c0, c0+16) of row `row` -> +bias, ELU, bf16 -> two 16-byte K chunks of the next A operand
@@ -147,19 +164,20 @@ __device__ __forceinline__ void emit16(const uint32_t* acc, const float* __restr
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const float4 b = *reinterpret_cast<const float4*>(bias + c0 + 4 * k);
-    w[2 * k] = pack_bf16(elu(__uint_as_float(acc[4 * k]) + b.x), elu(__uint_as_float(acc[4 * k + 1]) + b.y));
-    w[2 * k + 1] = pack_bf16(elu(__uint_as_float(acc[4 * k + 2]) + b.z), elu(__uint_as_float(acc[4 * k + 3]) + b.w));
+    w[2 * k] = elu_pair(acc[4 * k], acc[4 * k + 1], b.x, b.y);
+    w[2 * k + 1] = elu_pair(acc[4 * k + 2], acc[4 * k + 3], b.z, b.w);
   }
   *reinterpret_cast<uint4*>(dst + elem_offset(TM, row, c0)) = make_uint4(w[0], w[1], w[2], w[3]);
   *reinterpret_cast<uint4*>(dst + elem_offset(TM, row, c0 + 8)) = make_uint4(w[4], w[5], w[6], w[7]);
 }
 
 // Hidden-layer epilogue of one warp: kSub sub-steps; in sub-step s the 16 warps together cover accumulator columns
-// [64 s, 64 s + 64) (this warp: 16 of them), i.e. K chunk s of the next layer, and signal `bars[s]`.  The TMEM load
-// of sub-step s+1 is in flight while sub-step s is being processed.
-template <int kSub>
+// [64 s, 64 s + 64) (this warp: 16 of them), i.e. K chunk s of the next layer, written to dst + (s % kSlots) * CHUNK_BYTES,
+// and signal `bars[s]`.  The TMEM load of sub-step s+1 is in flight while sub-step s is being processed.  With a ring
+// (kSlots < kSub) sub-step s >= kSlots first waits until the MMAs of chunk s - kSlots have drained (`slot_free[s - kSlots]`).
+template <int kSub, int kSlots>
 __device__ __forceinline__ void epilogue_hidden(uint32_t tmem_acc, const float* __restrict__ bias, uint8_t* dst, uint64_t* bars,
-                                                int g, int q, int lane) {
+                                                uint64_t* slot_free, uint32_t slot_parity, int g, int q, int lane) {
   const int row = g * 32 + lane;
   const uint32_t taddr = tmem_acc + ((uint32_t)(g * 32) << 16) + (uint32_t)(q * 16);
   uint32_t a[16], b[16];
@@ -170,7 +188,8 @@ __device__ __forceinline__ void epilogue_hidden(uint32_t tmem_acc, const float* 
     uint32_t* cur = (s & 1) ? b : a;
     uint32_t* nxt = (s & 1) ? a : b;
     if (s + 1 < kSub) tmem_ld16(taddr + 64 * (s + 1), nxt);
-    emit16(cur, bias, dst, row, 64 * s + q * 16);
+    if (s >= kSlots) mbar_wait(&slot_free[s - kSlots], slot_parity);
+    emit16(cur, bias + 64 * s, dst + (s % kSlots) * CHUNK_BYTES, row, q * 16);
     fence_proxy_async();                       // generic-proxy A operand writes -> visible to the tensor core's async proxy
     if (s + 1 < kSub) tmem_wait();
     tc_fence_before();                         // orders this warp's tcgen05.ld before the MMA that reuses the accumulator
@@ -189,7 +208,13 @@ struct Args {
   float* value;
   int n;
   int num_tiles;
+  long long* timeline;         // diagnostic: clock64 stamps of CTA 0 (NULL in production launches)
 };
+
+// diagnostic timeline (lm_mlp_forward_timeline): slot k <- clock64(), first writer wins per launch
+__device__ __forceinline__ void stamp(const Args& a, int k) {
+  if (a.timeline != nullptr && blockIdx.x == 0) a.timeline[k] = clock64();
+}
 
 struct ObsRegs { float4 v[4]; };
 
@@ -243,13 +268,15 @@ __device__ __forceinline__ void epilogue_head(const Args& a, uint32_t tmem_acc, 
 
 __global__ void __launch_bounds__(THREADS, 1) k_mlp_forward(const Args a) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  // mbarriers.  count 1: bar_w (weight TMA), bar_acc* (tcgen05.commit).  count 16 (one arrive per epilogue warp):
-  // bar_a0 (A0 operand written), bar_act1[s] / bar_act2[s] / bar_act3 (K chunk s of the next layer's A operand written
-  // and, for the last sub-step, the accumulator fully read).  Every barrier completes exactly once per tile.
-  __shared__ uint64_t bar_w, bar_a0, bar_acc1, bar_acc2, bar_acc3, bar_acch, bar_act1[4], bar_act2[2], bar_act3[1];
+  // mbarriers.  count 1: bar_w (weight TMA), bar_acc* and bar_c2[s] (tcgen05.commit: accumulator complete / layer-2 K chunk s
+  // consumed).  count 16 (one arrive per epilogue warp): bar_a0 (A0 operand written), bar_act1[s] / bar_act2[s] / bar_act3
+  // (K chunk s of the next layer's A operand written; for the last sub-step also: accumulator fully read).  Every barrier
+  // completes exactly once per tile, so the parity of a wait is the parity of the CTA-local tile index.
+  __shared__ uint64_t bar_w, bar_a0, bar_acc1, bar_acc2, bar_acc3, bar_acch, bar_c2[2], bar_act1[4], bar_act2[2], bar_act3[1];
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  uint8_t* ACT = smem + ACT_OFF;
+  uint8_t* RING = smem + RING_OFF;
+  uint8_t* A2 = smem + A2_OFF;
   uint8_t* A0 = smem + A0_OFF;
   uint8_t* A3 = smem + A3_OFF;
   const float* bias1 = reinterpret_cast<const float*>(smem + BIAS_OFF);
@@ -260,6 +287,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_mlp_forward(const Args a) {
   if (tid == 0) {
     mbar_init(&bar_w, 1); mbar_init(&bar_a0, E_WARPS);
     mbar_init(&bar_acc1, 1); mbar_init(&bar_acc2, 1); mbar_init(&bar_acc3, 1); mbar_init(&bar_acch, 1);
+    mbar_init(&bar_c2[0], 1); mbar_init(&bar_c2[1], 1);
     for (int s = 0; s < 4; ++s) mbar_init(&bar_act1[s], E_WARPS);
     for (int s = 0; s < 2; ++s) mbar_init(&bar_act2[s], E_WARPS);
     mbar_init(&bar_act3[0], E_WARPS);
@@ -270,52 +298,67 @@ __global__ void __launch_bounds__(THREADS, 1) k_mlp_forward(const Args a) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
+  if (tid == 0) stamp(a, 0);
   const int tile0 = blockIdx.x, stride = gridDim.x;
+  const int n_loc = tile0 < a.num_tiles ? (a.num_tiles - tile0 + stride - 1) / stride : 0;   // tiles of this CTA
 
+  // Software pipeline over the CTA's tiles (iteration `it` = tile t).  Epilogue warps run, per iteration,
+  //   E1(t) -> obs(t+1) to A0 -> heads(t-2) -> E3(t-1) -> E2(t)
+  // so that every wait on a tensor-core result (acc2(t) after E1(t), acc3(t) after E2(t), heads(t) after E3(t)) has a
+  // full layer's worth of other work in front of it.  The control thread issues MMAs in the matching order.
   if (warp == E_WARPS) {
     // ================================================================== control warp: one thread issues TMA + every MMA
     if (lane == 0) {
       mbar_expect_tx(&bar_w, BLOB_BYTES);
       tma_load_1d(smem, a.blob, BLOB_BYTES, &bar_w);      // resident weights + biases: one bulk copy per CTA
       mbar_wait(&bar_w, 0);
+      stamp(a, 1);
       const uint32_t sW1 = smem_u32(smem + W1_OFF), sW2 = smem_u32(smem + W2_OFF), sW3 = smem_u32(smem + W3_OFF), sWH = smem_u32(smem + WH_OFF);
-      const uint32_t sACT = smem_u32(ACT), sA0 = smem_u32(A0), sA3 = smem_u32(A3);
-      if (tile0 < a.num_tiles) {
+      const uint32_t sRING = smem_u32(RING), sA2 = smem_u32(A2), sA0 = smem_u32(A0), sA3 = smem_u32(A3);
+      if (n_loc > 0) {
         mbar_wait(&bar_a0, 0);
         tc_fence_after();
-        issue_ksteps<D1>(tmem + ACC1_COL, sA0, sW1, 0, 4);
+        issue_ksteps<D1>(tmem + ACC1_COL, sA0, sW1, 0);
         umma_commit(&bar_acc1);
       }
-      uint32_t it = 0;
-      for (int tile = tile0; tile < a.num_tiles; tile += stride, ++it) {
+      for (int it = 0; it < n_loc; ++it) {
         const uint32_t ph = it & 1;
-        // layer 2: K chunk s as soon as the layer-1 epilogue has produced it
+        // layer 2 of tile t: K chunk s as soon as the layer-1 epilogue has produced it
 #pragma unroll
         for (int s = 0; s < 4; ++s) {
           mbar_wait(&bar_act1[s], ph);
           tc_fence_after();
-          issue_ksteps<D2>(tmem + ACC2_COL, sACT, sW2, 4 * s, 4);
+          issue_ksteps<D2>(tmem + ACC2_COL, sRING + (s & 1) * CHUNK_BYTES, sW2, 4 * s);
+          if (s < 2) umma_commit(&bar_c2[s]);             // ring slot s free again once these MMAs have drained
         }
         umma_commit(&bar_acc2);
-        // next tile's layer 1 (its accumulator columns were released by the last layer-1 sub-step above)
-        if (tile + stride < a.num_tiles) {
+        // layer 1 of tile t+1 (its accumulator columns were released by the last layer-1 sub-step above)
+        if (it + 1 < n_loc) {
           mbar_wait(&bar_a0, ph ^ 1);
           tc_fence_after();
-          issue_ksteps<D1>(tmem + ACC1_COL, sA0, sW1, 0, 4);
+          issue_ksteps<D1>(tmem + ACC1_COL, sA0, sW1, 0);
           umma_commit(&bar_acc1);
         }
-        // layer 3
+        // heads of tile t-1
+        if (it >= 1) {
+          mbar_wait(&bar_act3[0], ph ^ 1);
+          tc_fence_after();
+          issue_ksteps<DH>(tmem + ACCH_COL, sA3, sWH, 0);
+          umma_commit(&bar_acch);
+        }
+        // layer 3 of tile t
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
           mbar_wait(&bar_act2[s], ph);
           tc_fence_after();
-          issue_ksteps<D3>(tmem + ACC3_COL, sACT, sW3, 4 * s, 4);
+          issue_ksteps<D3>(tmem + ACC3_COL, sA2 + s * CHUNK_BYTES, sW3, 4 * s);
         }
         umma_commit(&bar_acc3);
-        // heads
-        mbar_wait(&bar_act3[0], ph);
+      }
+      if (n_loc > 0) {                                    // heads of the last tile
+        mbar_wait(&bar_act3[0], (n_loc - 1) & 1);
         tc_fence_after();
-        issue_ksteps<DH>(tmem + ACCH_COL, sA3, sWH, 0, 4);
+        issue_ksteps<DH>(tmem + ACCH_COL, sA3, sWH, 0);
         umma_commit(&bar_acch);
       }
     }
@@ -329,55 +372,76 @@ __global__ void __launch_bounds__(THREADS, 1) k_mlp_forward(const Args a) {
       inv_std = *reinterpret_cast<const float4*>(a.norm_inv_std + 4 * (tid & 15));
     }
     ObsRegs regs;
-    if (tile0 < a.num_tiles) {
+    if (n_loc > 0) {
       obs_fetch(a, tile0, tid, regs);
       obs_convert(a, tile0, tid, regs, mean, inv_std, has_norm, A0);
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_a0);
-      if (tile0 + stride < a.num_tiles) obs_fetch(a, tile0 + stride, tid, regs);
+      if (n_loc > 1) obs_fetch(a, tile0 + stride, tid, regs);
     }
+    const bool st = tid == 0;
+    if (st) stamp(a, 2);
     mbar_wait(&bar_w, 0);                                  // biases live in the weight blob
-    uint32_t it = 0;
-    for (int tile = tile0; tile < a.num_tiles; tile += stride, ++it) {
+    for (int it = 0; it < n_loc; ++it) {
       const uint32_t ph = it & 1;
-      const int next = tile + stride;
-      // ---- layer-1 epilogue: TMEM[128 x 256] -> A1 (4 K chunks for layer 2)
+      const int tile = tile0 + it * stride;
+      // ---- E1(t): TMEM[128 x 256] -> A1, four K chunks through the two-slot ring
+      if (st) stamp(a, 8 + 8 * it + 0);
       mbar_wait(&bar_acc1, ph);
       tc_fence_after();
-      epilogue_hidden<4>(tmem + ACC1_COL, bias1, ACT, bar_act1, g, q, lane);
-      // ---- next tile's observations -> A0 (layer 1 of this tile has consumed A0), then fetch the tile after it
-      if (next < a.num_tiles) {
-        obs_convert(a, next, tid, regs, mean, inv_std, has_norm, A0);
+      if (st) stamp(a, 8 + 8 * it + 1);
+      epilogue_hidden<4, 2>(tmem + ACC1_COL, bias1, RING, bar_act1, bar_c2, ph, g, q, lane);
+      if (st) stamp(a, 8 + 8 * it + 2);
+      // ---- observations of tile t+1 -> A0 (layer 1 of tile t has consumed A0), then fetch tile t+2
+      if (it + 1 < n_loc) {
+        obs_convert(a, tile + stride, tid, regs, mean, inv_std, has_norm, A0);
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar_a0);
-        if (next + stride < a.num_tiles) obs_fetch(a, next + stride, tid, regs);
+        if (it + 2 < n_loc) obs_fetch(a, tile + 2 * stride, tid, regs);
       }
-      // ---- previous tile's heads (its MMA finished long ago)
-      if (q == 0 && it > 0) {
-        mbar_wait(&bar_acch, ph ^ 1);
+      if (st) stamp(a, 8 + 8 * it + 3);
+      // ---- heads of tile t-2 (every warp waits: A3 must be drained before E3(t-1) overwrites it)
+      if (it >= 2) {
+        mbar_wait(&bar_acch, ph);
         tc_fence_after();
-        epilogue_head(a, tmem + ACCH_COL, biash, tile - stride, g, lane);
+        if (q == 0) epilogue_head(a, tmem + ACCH_COL, biash, tile - 2 * stride, g, lane);
       }
-      // ---- layer-2 epilogue: TMEM[128 x 128] -> A2 (aliases A1: layer 2 is complete), 2 K chunks for layer 3
+      // ---- E3(t-1): TMEM[128 x 64] -> A3
+      if (st) stamp(a, 8 + 8 * it + 4);
+      if (it >= 1) {
+        mbar_wait(&bar_acc3, ph ^ 1);
+        tc_fence_after();
+        epilogue_hidden<1, 1>(tmem + ACC3_COL, bias3, A3, bar_act3, nullptr, 0, g, q, lane);
+      }
+      // ---- E2(t): TMEM[128 x 128] -> A2 (layer 3 of tile t-1 has finished reading it: bar_acc3 above)
+      if (st) stamp(a, 8 + 8 * it + 5);
       mbar_wait(&bar_acc2, ph);
       tc_fence_after();
-      epilogue_hidden<2>(tmem + ACC2_COL, bias2, ACT, bar_act2, g, q, lane);
-      // ---- layer-3 epilogue: TMEM[128 x 64] -> A3
-      mbar_wait(&bar_acc3, ph);
-      tc_fence_after();
-      epilogue_hidden<1>(tmem + ACC3_COL, bias3, A3, bar_act3, g, q, lane);
+      if (st) stamp(a, 8 + 8 * it + 6);
+      epilogue_hidden<2, 2>(tmem + ACC2_COL, bias2, A2, bar_act2, nullptr, 0, g, q, lane);
+      if (st) stamp(a, 8 + 8 * it + 7);
     }
-    if (q == 0 && it > 0) {
-      mbar_wait(&bar_acch, (it - 1) & 1);
+    // ---- drain: heads(n-2), E3(n-1), heads(n-1)
+    if (n_loc >= 2) {
+      mbar_wait(&bar_acch, n_loc & 1);
       tc_fence_after();
-      epilogue_head(a, tmem + ACCH_COL, biash, tile0 + (int)(it - 1) * stride, g, lane);
+      if (q == 0) epilogue_head(a, tmem + ACCH_COL, biash, tile0 + (n_loc - 2) * stride, g, lane);
+    }
+    if (n_loc >= 1) {
+      mbar_wait(&bar_acc3, (n_loc - 1) & 1);
+      tc_fence_after();
+      epilogue_hidden<1, 1>(tmem + ACC3_COL, bias3, A3, bar_act3, nullptr, 0, g, q, lane);
+      mbar_wait(&bar_acch, (n_loc - 1) & 1);
+      tc_fence_after();
+      if (q == 0) epilogue_head(a, tmem + ACCH_COL, biash, tile0 + (n_loc - 1) * stride, g, lane);
     }
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (tid == 0) stamp(a, 3);
   if (warp == E_WARPS) tmem_dealloc(tmem, TMEM_COLS);
 }
 
@@ -411,6 +475,7 @@ struct LmMlp {
   int sm_count;
   uint8_t* blob;
   bool packed;
+  long long* timeline;   // diagnostic only (lm_mlp_set_timeline)
 };
 
 extern "C" {
@@ -422,7 +487,7 @@ LmMlp* lm_mlp_create(int device) {
   if (prop.major != 10) { lm_set_error("lm_mlp_create: tcgen05 kernel needs sm_100a, device is sm_%d%d", prop.major, prop.minor); return nullptr; }
   cudaSetDevice(device);
   LmMlp* m = new LmMlp();
-  m->device = device; m->sm_count = prop.multiProcessorCount; m->packed = false; m->blob = nullptr;
+  m->device = device; m->sm_count = prop.multiProcessorCount; m->packed = false; m->blob = nullptr; m->timeline = nullptr;
   if (cudaMalloc(&m->blob, BLOB_BYTES) != cudaSuccess) { lm_set_error("lm_mlp_create: cudaMalloc failed"); delete m; return nullptr; }
   cudaMemset(m->blob, 0, BLOB_BYTES);
   e = cudaFuncSetAttribute(k_mlp_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
@@ -434,6 +499,12 @@ void lm_mlp_destroy(LmMlp* m) {
   if (!m) return;
   cudaFree(m->blob);
   delete m;
+}
+
+int lm_mlp_set_timeline(LmMlp* m, long long* stamps_dev) {
+  if (!m) return lm_fail(LM_ERR_BAD_ARG, "lm_mlp_set_timeline: NULL");
+  m->timeline = stamps_dev;
+  return LM_OK;
 }
 
 int lm_mlp_pack(LmMlp* m, const float* w1, const float* b1, const float* w2, const float* b2, const float* w3, const float* b3,
@@ -461,7 +532,7 @@ int lm_mlp_forward(LmMlp* m, const float* obs, const float* norm_mean, const flo
   if ((norm_mean == nullptr) != (norm_inv_std == nullptr)) return lm_fail(LM_ERR_BAD_ARG, "lm_mlp_forward: give both norm vectors or neither");
   Args a;
   a.blob = m->blob; a.obs = obs; a.norm_mean = norm_mean; a.norm_inv_std = norm_inv_std; a.norm_clip = norm_clip;
-  a.mu = mu; a.value = value; a.n = n; a.num_tiles = (n + TM - 1) / TM;
+  a.mu = mu; a.value = value; a.n = n; a.num_tiles = (n + TM - 1) / TM; a.timeline = m->timeline;
   const int grid = a.num_tiles < m->sm_count ? a.num_tiles : m->sm_count;
   k_mlp_forward<<<grid, THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(a);
   return lm_check_launch("lm_mlp_forward");
