@@ -380,7 +380,7 @@ def cuda_arm(args):
             line_extra["roofline_large"] = large_roofline(device, graph_time, hbm)
 
     # ---- e2e: C-ABI host entry, pinned host buffers in, results out, every step
-    e2e = None if args.no_e2e else e2e_arm(pipe, args, world, device)
+    e2e = None if args.no_e2e else e2e_arm(pipe, args, world, device, rank)
 
     # ---- CPU baseline (rank 0, N=1 only)
     cpu = None
@@ -438,64 +438,42 @@ def large_roofline(device, graph_time, hbm, n=524288):
             "bytes_per_env": B_POST}
 
 
-def e2e_arm(pipe, args, world, device):
-    """Same step through lm_task_step_host: H2D of actions / uniforms / physics state from pinned memory, kernels,
-    D2H of obs / rew / reset, then the policy forward and D2H of its outputs.  Max over ranks."""
+def e2e_arm(pipe, args, world, device, rank=0):
+    """Same step through the host-buffer API (ShardedHostStepper -> lm_task_step_host_async per env shard): H2D of
+    actions / uniforms / physics state from pinned memory, kernels, D2H of obs / rew / reset, the policy forward and D2H
+    of its outputs, every step, with a host synchronisation at the end of every step.  Max over ranks."""
     import torch.distributed as tdist
-    from locomanipulationrl_b200 import _lib
-    task, n, lib = pipe.task, pipe.n, pipe.lib
-    sc = pipe.scenes[0]
-    task.set_up_scene(sc)
-    pin = lambda *shape, dtype=torch.float32: torch.zeros(*shape, dtype=dtype).pin_memory()
-    actions_h, uniforms_h = pin(n, 12), pin(n, 3)
-    obs_h, rew_h, reset_h = pin(n, 64), pin(n), pin(n, dtype=torch.long)
-    mu_h, value_h = pin(n, 12), pin(n, 1)
-    actions_d, uniforms_d = torch.zeros(n, 12, device=device), torch.zeros(n, 3, device=device)
-    uniforms_h.copy_(pipe.uniforms[0].cpu())
-    io = _lib.LmHostStep()
-    io.actions_host, io.uniforms_host = actions_h.data_ptr(), uniforms_h.data_ptr()
-    io.actions_dev, io.uniforms_dev = actions_d.data_ptr(), uniforms_d.data_ptr()
-    io.obs_host, io.rew_host, io.reset_host = obs_h.data_ptr(), rew_h.data_ptr(), reset_h.data_ptr()
-    h2d = actions_h.numel() * 4 + uniforms_h.numel() * 4
-    for grp in ("loco", "mani"):
-        if grp in pipe.host_states[0]:
-            h2d += pipe.host_states[0][grp].numel() * 4
-    d2h = (obs_h.numel() + rew_h.numel() + mu_h.numel() + value_h.numel()) * 4 + reset_h.numel() * 8
-    stream = torch.cuda.current_stream()
-
-    def one(t):
-        hs = pipe.host_states[t % STATE_SETS]
-        if "loco" in hs:
-            io.loco_state_host, io.loco_state_floats, io.loco_state_dev = hs["loco"].data_ptr(), hs["loco"].numel(), sc.arena["loco"].data_ptr()
-        if "mani" in hs:
-            io.mani_state_host, io.mani_state_floats, io.mani_state_dev = hs["mani"].data_ptr(), hs["mani"].numel(), sc.arena["mani"].data_ptr()
-        rc = lib.lm_task_step_host(task._handle, task._lp(), task._mp(), task._env_pos.data_ptr(), C.byref(task._buffers), C.byref(io),
-                                   stream.cuda_stream)
-        _lib.check(rc, "lm_task_step_host")
-        if pipe.w["policy"] == "mlp":
-            pipe.policy(task.obs_buf, norm_mean=pipe.norm_mean, norm_inv_std=pipe.norm_inv_std, out=(pipe.mu, pipe.value))
-        else:
-            pipe.policy(task.obs_buf, out=(pipe.mu, pipe.value))
-        mu_h.copy_(pipe.mu, non_blocking=True)
-        value_h.copy_(pipe.value, non_blocking=True)
-        stream.synchronize()
-        actions_h.copy_(mu_h)           # the host hands the policy output back as the next step's actions
-
-    steps = max(4, min(args.steps, 40))
+    from locomanipulationrl_b200.host_step import ShardedHostStepper
+    n = pipe.n
+    mlp = pipe.w["policy"] == "mlp"
+    stepper = ShardedHostStepper(pipe.cfg, n, pipe.policy, shards=args.e2e_shards, device=device, seed=1000 * rank + 42,
+                                 env_id_offset=rank * n, norm_mean=pipe.norm_mean if mlp else None,
+                                 norm_inv_std=pipe.norm_inv_std if mlp else None)
+    sets = []                                     # STATE_SETS x shards pinned host states (> L2, and never the same twice in a row)
+    for i in range(STATE_SETS):
+        sets.append([s.scene.pack_host(s.scene.generate(i)) for s in stepper.shards])
+    g = torch.Generator().manual_seed(11 + rank)
+    for s in stepper.shards:
+        s.uniforms_host.copy_(torch.rand(s.n, 3, generator=g))
+    h2d = stepper.h2d_bytes + sum(t.numel() * 4 for hs in sets[0] for t in hs.values())
+    d2h = stepper.d2h_bytes
+    steps = max(4, min(args.steps, 60))
     for t in range(3):
-        one(t)
+        stepper.step(sets[t % STATE_SETS])
     torch.cuda.synchronize()
     if world > 1:
         tdist.barrier()
     t0 = time.perf_counter()
     for t in range(steps):
-        one(t)
+        stepper.step(sets[t % STATE_SETS])
     torch.cuda.synchronize()
     dt = torch.tensor([time.perf_counter() - t0], device=device, dtype=torch.float64)
     if world > 1:
         tdist.all_reduce(dt, op=tdist.ReduceOp.MAX)
     return {"value": n * world * steps / float(dt.item()), "unit": "env-steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-            "steps": steps, "api": "lm_task_step_host (C ABI, pinned host buffers) + lm_mlp_forward"}
+            "steps": steps, "ms_per_step": float(dt.item()) / steps * 1e3,
+            "api": f"ShardedHostStepper.step: {args.e2e_shards} env shards x (lm_task_step_host_async + policy forward), pinned host buffers, "
+                   "host sync every step"}
 
 
 def main():
@@ -508,6 +486,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graphs", action="store_true", help="launch eagerly (for ncu captures)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-shards", type=int, default=2, help="env shards (streams) the host-buffer step is pipelined over")
     ap.add_argument("--no-large", action="store_true", help="skip the 524,288-env k_post roofline line")
     args = ap.parse_args()
     if args.impl == "reference":

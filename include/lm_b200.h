@@ -153,6 +153,10 @@ int lm_task_set_clamp_observations(LmTask* task, int on);
  * rl_task.py:222-225): the next pre_step then rescans reset_buf first. */
 int lm_task_invalidate_reset_scan(LmTask* task);
 
+/* Diagnostic: when stamps_dev != NULL (device buffer of num_tiles x 8 int64, num_tiles = ceil(envs per half / 128) per
+ * half), every CTA of the following lm_task_post_step launches records %globaltimer at its stages.  NULL = off (default). */
+int lm_task_set_timeline(LmTask* task, long long* stamps_dev);
+
 /* pre_physics_step (QPC:200-228 / QMP:213-236 / JLV:248-270) including reset_idx
  * (QPC:230-299 / JLV:272-377), rand_quaternions (utils/math.py:176-193) and take_action
  * (robot.py:444-461).  `actions` [N,12]; `uniforms` [N,3] = the torch.rand draw, row k is consumed
@@ -246,6 +250,13 @@ typedef struct LmHostStep {
 } LmHostStep;
 int lm_task_step_host(LmTask* task, const LmRobotViews* loco, const LmRobotViews* mani,
                       const float* env_pos, const LmTaskBuffers* buf, const LmHostStep* io, void* stream);
+/* Same, but returns as soon as the copies and kernels are enqueued on `stream` (no host synchronisation).  A batch
+ * split into env shards (one task + one stream per shard, the layout multi-GPU sharding uses) steps all shards
+ * back to back so that shard k's host->device copies overlap shard k-1's kernels and device->host copies (PCIe is
+ * full duplex); the caller then waits with lm_stream_synchronize on each shard's stream. */
+int lm_task_step_host_async(LmTask* task, const LmRobotViews* loco, const LmRobotViews* mani,
+                            const float* env_pos, const LmTaskBuffers* buf, const LmHostStep* io, void* stream);
+int lm_stream_synchronize(void* stream);
 
 #ifdef __cplusplus
 }

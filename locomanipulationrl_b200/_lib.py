@@ -74,6 +74,7 @@ SYMBOLS = {
     "lm_task_step_parity": (C.c_int, [_vp]),
     "lm_task_set_clamp_observations": (C.c_int, [_vp, C.c_int]),
     "lm_task_invalidate_reset_scan": (C.c_int, [_vp]),
+    "lm_task_set_timeline": (C.c_int, [_vp, _vp]),
     "lm_task_pre_step": (C.c_int, [_vp, C.POINTER(LmRobotViews), C.POINTER(LmRobotViews), _vp, C.POINTER(LmTaskBuffers), _vp, _vp, _vp]),
     "lm_task_reset_idx": (C.c_int, [_vp, C.POINTER(LmRobotViews), C.POINTER(LmRobotViews), _vp, C.POINTER(LmTaskBuffers), _vp, _i32, _vp, _vp]),
     "lm_task_post_step": (C.c_int, [_vp, C.POINTER(LmRobotViews), C.POINTER(LmRobotViews), _vp, C.POINTER(LmTaskBuffers), _vp]),
@@ -92,6 +93,8 @@ SYMBOLS = {
     "lm_gae": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _f, _f, _i32, _vp]),
     "lm_gae_env_major": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _f, _f, _i32, _vp]),
     "lm_task_step_host": (C.c_int, [_vp, C.POINTER(LmRobotViews), C.POINTER(LmRobotViews), _vp, C.POINTER(LmTaskBuffers), C.POINTER(LmHostStep), _vp]),
+    "lm_task_step_host_async": (C.c_int, [_vp, C.POINTER(LmRobotViews), C.POINTER(LmRobotViews), _vp, C.POINTER(LmTaskBuffers), C.POINTER(LmHostStep), _vp]),
+    "lm_stream_synchronize": (C.c_int, [_vp]),
 }
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "liblm_b200.so")

@@ -30,6 +30,7 @@ struct Derived {                  // host-computed constants (lm_task_create)
   int32_t tiles_per_half;
   int32_t num_tiles;
   int32_t dof_identity;           // dof_index == 0..11
+  int32_t scan_per;               // tiles per scan block: reset rank base of tile t = scan_base[t / scan_per] + tile_offsets[t]
 };
 
 struct KernelParams {
@@ -79,7 +80,8 @@ struct Stager {
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(T) k_reset_count(const KernelParams kp, const int64_t* __restrict__ reset_buf,
                                                    int32_t* __restrict__ tile_counts, int32_t* __restrict__ tile_offsets,
-                                                   int32_t* __restrict__ num_reset, unsigned int* __restrict__ ticket) {
+                                                   int32_t* __restrict__ scan_base, int32_t* __restrict__ num_reset,
+                                                   unsigned int* __restrict__ ticket) {
   __shared__ int warp_counts[T / 32];
   __shared__ int is_last;
   __shared__ int scan_s[T];
@@ -101,8 +103,9 @@ __global__ void __launch_bounds__(T) k_reset_count(const KernelParams kp, const 
   __syncthreads();
   if (!is_last) return;
   __threadfence();
-  // last CTA: exclusive scan over all tile counts, chunked per thread
+  // last CTA: exclusive scan over all tile counts, chunked per thread (absolute offsets: scan_base stays zero)
   const int nt = kp.d.num_tiles;
+  for (int i = r; i < (nt + kp.d.scan_per - 1) / kp.d.scan_per; i += T) scan_base[i] = 0;
   const int per = (nt + T - 1) / T;
   int lo = r * per, hi = min(nt, lo + per), s = 0;
   for (int i = lo; i < hi; ++i) s += __ldcg(tile_counts + i);
@@ -135,6 +138,7 @@ struct PreArgs {
   const float* actions;
   const float* uniforms;
   const int32_t* tile_offsets;
+  const int32_t* scan_base;
   int parity;                      // actions_ring slot that receives current_actions
 };
 
@@ -238,7 +242,7 @@ __global__ void __launch_bounds__(T) k_pre(const KernelParams kp, const PreArgs 
   __syncthreads();
   if (count > 0) {
     // two lanes per reset env: role 0 = goal + indicator pose (the double-precision chain), role 1 = defaults + history
-    const int tile_base = a.tile_offsets[blockIdx.x];
+    const int tile_base = a.scan_base[blockIdx.x / kp.d.scan_per] + a.tile_offsets[blockIdx.x];
     float* ring_last = a.buf.actions_ring + (size_t)(a.parity ^ 1) * N * LM_NUM_ACT;
     for (int idx = r; idx < 2 * count; idx += T) {
       const int lr = list[idx >> 1];
@@ -306,10 +310,22 @@ struct PostArgs {
   LmTaskBuffers buf;
   float* partials;                 // [num_tiles, STATS] fp32 per-CTA partial sums
   unsigned int* ticket;
-  int32_t* tile_offsets;           // by-product: exclusive scan of per-tile reset counts for the next pre_step
+  int32_t* tile_offsets;           // by-product: exclusive scan of per-tile reset counts for the next pre_step,
+  int32_t* scan_base;              //   as scan_base[t / scan_per] + tile_offsets[t]
+  int inline_finish;               // the last CTA runs the finish pass (else k_post_finish is launched behind the kernel)
   int parity;
   int clamp_observations;          // store clamp(obs, ±clip_observations) (fused _process_data)
+  long long* timeline;             // diagnostic: [num_tiles, 8] globaltimer stamps (NULL in production)
 };
+
+__device__ __forceinline__ long long globaltimer_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void stamp(const PostArgs& a, int k) {
+  if (a.timeline != nullptr && threadIdx.x == 0) a.timeline[(size_t)blockIdx.x * 8 + k] = globaltimer_ns();
+}
 
 struct EnvIn {
   float jp[12], jv[12], last_jv[12], cur[12], last[12];
@@ -491,19 +507,131 @@ __device__ __forceinline__ void store_flags(const LmTaskBuffers& b, int e, const
 }
 
 // per-CTA partial sums -> partials[tile]; the last CTA turns them into extras / counters / the next reset scan
-// (QPC:560,610,619-633 / JLV:758-802)
+// (QPC:560,610,619-633 / JLV:758-802).  The last CTA's pass is the serial tail of the launch, so it is kept short:
+// thread r owns a contiguous block of tiles (batched 128-bit L2 loads, per-thread sums in double), then one shuffle
+// tree / block scan.  Thread->tile mapping and tree shape are fixed, so `extras` are deterministic run to run.
+constexpr int FINISH_THREADS = 1024;   // stand-alone finish kernel (large grids)
+constexpr int INLINE_FINISH_MAX_TILES = 1024;
+
+struct FinishSmem {
+  float red_f[4][STATS];            // per-warp partial sums of this CTA
+  double red_d[32][13];             // finish pass: per-warp sums (11 totals + manipulation-half counts 9, 10)
+  int warp_scan[32];
+  int is_last;
+};
+
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+  return v;
+}
+
+// Finish pass over partials[num_tiles][STATS] by one CTA of kThreads threads.  Thread r owns the contiguous tiles
+// [r * scan_per, (r + 1) * scan_per): their partial sums are fetched with batched 128-bit L2 loads and summed in double;
+// one shuffle tree gives the totals and one block scan the reset ranks.  Per-tile offsets are written RELATIVE to the
+// owner's block and the block bases separately (scan_base), so no second pass over the tiles is needed.
 template <int kThreads>
-__device__ __forceinline__ void finish_stats(const KernelParams& kp, const PostArgs& a, const float stats[STATS],
-                                             float (*red_f)[STATS], int* is_last, double (*part)[kThreads / STATS][STATS],
-                                             double (*tot)[STATS], int* scan_s) {
+__device__ __forceinline__ void finish_tail(const KernelParams& kp, const PostArgs& a, FinishSmem& fs) {
   const LmTaskParams& P = kp.p;
-  const int r = threadIdx.x, N = P.num_envs;
+  const int r = threadIdx.x, N = P.num_envs, lane = r & 31, warp = r >> 5;
+  constexpr int kWarps = kThreads / 32;
+  const int nt = kp.d.num_tiles, tph = kp.d.tiles_per_half, per = kp.d.scan_per;
+  const int lo = min(nt, r * per), hi = min(nt, lo + per);
+  double acc[13];
+#pragma unroll
+  for (int i = 0; i < 13; ++i) acc[i] = 0.0;
+  int my_resets = 0, loco_rel = -1;
+  const float4* part4 = reinterpret_cast<const float4*>(a.partials);
+  for (int t0 = lo; t0 < hi; t0 += 4) {
+    float4 v[4][3];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {                      // 12 independent 128-bit loads in flight
+      const int t = min(t0 + u, hi - 1);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) v[u][k] = __ldcg(part4 + (size_t)t * (STATS / 4) + k);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int t = t0 + u;
+      if (t < hi) {
+        const float f[12] = {v[u][0].x, v[u][0].y, v[u][0].z, v[u][0].w, v[u][1].x, v[u][1].y, v[u][1].z, v[u][1].w,
+                             v[u][2].x, v[u][2].y, v[u][2].z, v[u][2].w};
+#pragma unroll
+        for (int i = 0; i < 11; ++i) acc[i] += (double)f[i];
+        if (P.kind == LM_KIND_COTRAIN && t >= tph) { acc[11] += (double)f[9]; acc[12] += (double)f[10]; }
+        if (P.kind == LM_KIND_COTRAIN && t == tph) loco_rel = my_resets;      // resets in the locomotion half
+        a.tile_offsets[t] = my_resets;
+        my_resets += (int)f[10];
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 13; ++i) {
+    const double v = warp_sum_d(acc[i]);
+    if (lane == 0) fs.red_d[warp][i] = v;
+  }
+  int incl = my_resets;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const int o = __shfl_up_sync(0xffffffffu, incl, off);
+    if (lane >= off) incl += o;
+  }
+  if (lane == 31) fs.warp_scan[warp] = incl;
+  __syncthreads();
+  int base = 0, total_resets = 0;
+  for (int w = 0; w < kWarps; ++w) {
+    const int c = fs.warp_scan[w];
+    if (w < warp) base += c;
+    total_resets += c;
+  }
+  base += incl - my_resets;
+  if (lo < hi) a.scan_base[r] = base;
+  if (loco_rel >= 0) a.buf.num_reset[1] = base + loco_rel;
+  if (r == 0) {
+    double tot[13];
+#pragma unroll
+    for (int i = 0; i < 13; ++i) {
+      tot[i] = 0.0;
+      for (int w = 0; w < kWarps; ++w) tot[i] += fs.red_d[w][i];
+    }
+    a.buf.num_reset[0] = total_resets;
+    if (P.kind == LM_KIND_LOCO) a.buf.num_reset[1] = total_resets;
+    if (P.kind == LM_KIND_MANI) a.buf.num_reset[1] = 0;
+    float* ex = a.buf.extras;
+    const double inv_n = 1.0 / (double)N;
+    for (int i = 0; i < 7; ++i) ex[i] = (float)(tot[i] * inv_n);
+    ex[LM_EXTRA_NAN_COUNT] = (float)tot[7];
+    ex[LM_EXTRA_BELOW_M50_COUNT] = (float)tot[8];
+    int64_t* c = a.buf.counters;
+    const int groups = (P.kind == LM_KIND_COTRAIN) ? 3 : 1;
+    // group 0 = all envs, 1 = locomotion half, 2 = manipulation half (QPC:619-633 / JLV:758-802)
+    const double goal[3] = {tot[9], tot[9] - tot[11], tot[11]};
+    const double rst[3] = {tot[10], tot[10] - tot[12], tot[12]};
+    for (int g = 0; g < groups; ++g) {
+      int64_t ns = c[2 * g], nr = c[2 * g + 1];
+      if (nr > (int64_t)P.max_reset_counts) {
+        ex[LM_EXTRA_SUCCESS_RATE + g] = (float)ns / (float)nr;
+        ns = 0; nr = 0;
+      }
+      c[2 * g] = ns + (int64_t)llrint(goal[g]);
+      c[2 * g + 1] = nr + (int64_t)llrint(rst[g]);
+    }
+    *a.ticket = 0;
+  }
+}
+
+// per-CTA partial sums -> partials[tile]; with inline_finish the last CTA to arrive runs the finish pass
+// (QPC:560,610,619-633 / JLV:758-802): thread->tile mapping and tree shape are fixed, so `extras` are deterministic.
+template <int kThreads>
+__device__ __forceinline__ void finish_stats(const KernelParams& kp, const PostArgs& a, const float stats[STATS], FinishSmem& fs) {
+  const int r = threadIdx.x, lane = r & 31, warp = r >> 5;
+  constexpr int kWarps = kThreads / 32;
 #pragma unroll
   for (int i = 0; i < 11; ++i) {
     float v = stats[i];
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-    if ((r & 31) == 0) red_f[r >> 5][i] = v;
+    if (lane == 0) fs.red_f[warp][i] = v;
   }
   __syncthreads();
   if (r == 0) {
@@ -516,76 +644,28 @@ __device__ __forceinline__ void finish_stats(const KernelParams& kp, const PostA
       v[i] = 0.0f;
       if (i < 11) {
 #pragma unroll
-        for (int w = 0; w < kThreads / 32; ++w) v[i] += red_f[w][i];
+        for (int w = 0; w < kWarps; ++w) v[i] += fs.red_f[w][i];
       }
     }
 #pragma unroll
     for (int k = 0; k < STATS / 4; ++k) __stcg(dst + k, make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]));
-    __threadfence();
-    *is_last = atomicAdd(a.ticket, 1u) == gridDim.x - 1;
+    if (a.inline_finish) {
+      __threadfence();
+      fs.is_last = atomicAdd(a.ticket, 1u) == gridDim.x - 1;
+    } else {
+      fs.is_last = 0;
+    }
   }
   __syncthreads();
-  if (!*is_last) return;
+  if (!fs.is_last) return;
   __threadfence();
-  {
-    const int i = r % STATS, g = r / STATS;
-    double s_l = 0.0, s_m = 0.0;
-    const int tph = kp.d.tiles_per_half;
-    for (int t = g; t < kp.d.num_tiles; t += kThreads / STATS) {
-      const double v = (double)__ldcg(a.partials + (size_t)t * STATS + i);
-      const bool second = (P.kind == LM_KIND_COTRAIN) && t >= tph;
-      if (second) s_m += v; else s_l += v;
-    }
-    part[0][g][i] = s_l; part[1][g][i] = s_m;
-  }
-  __syncthreads();
-  if (r < STATS) {
-    double s_l = 0.0, s_m = 0.0;
-    for (int g = 0; g < kThreads / STATS; ++g) { s_l += part[0][g][r]; s_m += part[1][g][r]; }
-    tot[0][r] = s_l + s_m; tot[1][r] = s_l; tot[2][r] = s_m;
-  }
-  // exclusive scan of per-tile reset counts (partials[t][10]) -> tile_offsets, num_reset: the next pre_step's reset ranks
-  const int nt = kp.d.num_tiles;
-  const int per = (nt + kThreads - 1) / kThreads;
-  const int lo = r * per, hi = min(nt, lo + per);
-  int s = 0;
-  for (int i = lo; i < hi; ++i) s += (int)__ldcg(a.partials + (size_t)i * STATS + 10);
-  scan_s[r] = s;
-  __syncthreads();
-  if (r == 0) {
-    int acc = 0;
-    for (int i = 0; i < kThreads; ++i) { const int v = scan_s[i]; scan_s[i] = acc; acc += v; }
-    a.buf.num_reset[0] = acc;
-    if (P.kind == LM_KIND_LOCO) a.buf.num_reset[1] = acc;
-    if (P.kind == LM_KIND_MANI) a.buf.num_reset[1] = 0;
-    float* ex = a.buf.extras;
-    const double inv_n = 1.0 / (double)N;
-    for (int i = 0; i < 7; ++i) ex[i] = (float)(tot[0][i] * inv_n);
-    ex[LM_EXTRA_NAN_COUNT] = (float)tot[0][7];
-    ex[LM_EXTRA_BELOW_M50_COUNT] = (float)tot[0][8];
-    int64_t* c = a.buf.counters;
-    const int groups = (P.kind == LM_KIND_COTRAIN) ? 3 : 1;
-    for (int g = 0; g < groups; ++g) {
-      int64_t& ns = c[2 * g];
-      int64_t& nr = c[2 * g + 1];
-      if (nr > (int64_t)P.max_reset_counts) {
-        ex[LM_EXTRA_SUCCESS_RATE + g] = (float)ns / (float)nr;
-        ns = 0; nr = 0;
-      }
-    }
-    for (int g = 0; g < groups; ++g) {
-      c[2 * g] += (int64_t)llrint(tot[g][9]);
-      c[2 * g + 1] += (int64_t)llrint(tot[g][10]);
-    }
-    *a.ticket = 0;
-  }
-  __syncthreads();
-  int acc = scan_s[r];
-  for (int i = lo; i < hi; ++i) {
-    if (P.kind == LM_KIND_COTRAIN && i == kp.d.tiles_per_half) a.buf.num_reset[1] = acc;
-    a.tile_offsets[i] = acc;
-    acc += (int)__ldcg(a.partials + (size_t)i * STATS + 10);
-  }
+  finish_tail<kThreads>(kp, a, fs);
+}
+
+// stand-alone finish pass for grids too large for a 128-thread tail
+__global__ void __launch_bounds__(FINISH_THREADS) k_post_finish(const KernelParams kp, const PostArgs a) {
+  __shared__ FinishSmem fs;
+  finish_tail<FINISH_THREADS>(kp, a, fs);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -619,11 +699,7 @@ __device__ __forceinline__ Vec3 ld3(const float* p) { return Vec3{p[0], p[1], p[
 __global__ void __launch_bounds__(T, 4) k_post_lean(const KernelParams kp, const PostArgs a) {
   extern __shared__ __align__(128) float sm[];
   __shared__ uint64_t bar;
-  __shared__ float red_f[T / 32][STATS];
-  __shared__ int is_last;
-  __shared__ double part[2][T / STATS][STATS];
-  __shared__ double tot[3][STATS];
-  __shared__ int scan_s[T];
+  __shared__ FinishSmem fs;
   const LmTaskParams& P = kp.p;
   const Tile tl = tile_of(kp, blockIdx.x);
   const int r = threadIdx.x;
@@ -633,6 +709,7 @@ __global__ void __launch_bounds__(T, 4) k_post_lean(const KernelParams kp, const
   const float* ring_last = a.buf.actions_ring + (size_t)(a.parity ^ 1) * N * LM_NUM_ACT;
   const int n = tl.n, h0 = tl.hr0, e0 = tl.e0;
 
+  stamp(a, 0);
   if (r == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
   __syncthreads();
   Stager st{&bar, 0u, (n % 4) == 0};
@@ -664,7 +741,9 @@ __global__ void __launch_bounds__(T, 4) k_post_lean(const KernelParams kp, const
     in.succ_prev = (int)a.buf.successes[e];
     in.consec = (int)a.buf.consecutive_successes[e];
   }
+  stamp(a, 1);
   if (st.use_tma) mbar_wait(&bar, 0); else __syncthreads();
+  stamp(a, 2);
   {
     const int rr = valid ? r : 0;
     if (kp.d.dof_identity) {
@@ -692,7 +771,12 @@ __global__ void __launch_bounds__(T, 4) k_post_lean(const KernelParams kp, const
       for (int i = 0; i < STATS; ++i) out.stats[i] = 0.0f;
     }
   }
-  finish_stats<T>(kp, a, out.stats, red_f, &is_last, part, tot, scan_s);
+  if (a.timeline != nullptr && r == 0) {
+    // first use of the register-loaded rows forces their arrival
+    a.timeline[(size_t)blockIdx.x * 8 + 3] = globaltimer_ns() + (long long)(out.rew != out.rew ? 1 : 0);
+  }
+  finish_stats<T>(kp, a, out.stats, fs);
+  stamp(a, 4);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -739,11 +823,7 @@ __device__ __forceinline__ float states_elem(const LmTaskParams& P, const float*
 __global__ void __launch_bounds__(T, 2) k_post(const KernelParams kp, const PostArgs a) {
   extern __shared__ __align__(128) float sm[];
   __shared__ uint64_t bar;
-  __shared__ float red_f[T / 32][STATS];
-  __shared__ int is_last;
-  __shared__ double part[2][T / STATS][STATS];
-  __shared__ double tot[3][STATS];
-  __shared__ int scan_s[T];
+  __shared__ FinishSmem fs;
   const LmTaskParams& P = kp.p;
   const Tile tl = tile_of(kp, blockIdx.x);
   const int r = threadIdx.x;
@@ -846,7 +926,7 @@ __global__ void __launch_bounds__(T, 2) k_post(const KernelParams kp, const Post
       }
     }
   }
-  finish_stats<T>(kp, a, out.stats, red_f, &is_last, part, tot, scan_s);
+  finish_stats<T>(kp, a, out.stats, fs);
   if (st.use_tma && r == 0) tma_store_wait_all();
 }
 
@@ -877,9 +957,12 @@ struct LmTask {
   int sm_count;
   int32_t* tile_counts;
   int32_t* tile_offsets;
+  int32_t* scan_base;
+  int inline_finish;
   float* partials;
   unsigned int* tickets;     // [2]: scan, post
   int clamp_observations;
+  long long* timeline;
   int scan_valid;            // tile_offsets / num_reset were produced by the last post_step and reset_buf is untouched since
 };
 
@@ -941,6 +1024,11 @@ LmTask* lm_task_create(const LmTaskParams* params, int device) {
   d.half = (p.kind == LM_KIND_COTRAIN) ? p.num_envs / 2 : p.num_envs;
   d.tiles_per_half = (d.half + T - 1) / T;
   d.num_tiles = d.tiles_per_half * ((p.kind == LM_KIND_COTRAIN) ? 2 : 1);
+  t->inline_finish = d.num_tiles <= INLINE_FINISH_MAX_TILES;
+  {
+    const int threads = t->inline_finish ? T : FINISH_THREADS;
+    d.scan_per = (d.num_tiles + threads - 1) / threads;
+  }
   d.dof_identity = 1;
   for (int j = 0; j < LM_NUM_ACT; ++j) {
     if (p.dof_index[j] < 0 || p.dof_index[j] >= LM_NUM_DOF) { lm_set_error("dof_index[%d] out of range", j); delete t; return nullptr; }
@@ -958,10 +1046,12 @@ LmTask* lm_task_create(const LmTaskParams* params, int device) {
     }
   bool ok = cudaMalloc(&t->tile_counts, sizeof(int32_t) * d.num_tiles) == cudaSuccess &&
             cudaMalloc(&t->tile_offsets, sizeof(int32_t) * d.num_tiles) == cudaSuccess &&
+            cudaMalloc(&t->scan_base, sizeof(int32_t) * FINISH_THREADS) == cudaSuccess &&
             cudaMalloc(&t->partials, sizeof(float) * STATS * d.num_tiles) == cudaSuccess &&
             cudaMalloc(&t->tickets, sizeof(unsigned int) * 2) == cudaSuccess;
   if (!ok) { lm_set_error("lm_task_create: cudaMalloc failed"); lm_task_destroy(t); return nullptr; }
   cudaMemset(t->tickets, 0, sizeof(unsigned int) * 2);
+  cudaMemset(t->scan_base, 0, sizeof(int32_t) * FINISH_THREADS);
   err = cudaFuncSetAttribute(k_post_lean, cudaFuncAttributeMaxDynamicSharedMemorySize, LeanSmem::kBytes);
   if (err == cudaSuccess) err = cudaFuncSetAttribute(k_post, cudaFuncAttributeMaxDynamicSharedMemorySize, PostSmem::kBytes);
   if (err != cudaSuccess) { lm_set_error("cudaFuncSetAttribute(k_post): %s", cudaGetErrorString(err)); lm_task_destroy(t); return nullptr; }
@@ -970,13 +1060,15 @@ LmTask* lm_task_create(const LmTaskParams* params, int device) {
 
 void lm_task_destroy(LmTask* t) {
   if (!t) return;
-  cudaFree(t->tile_counts); cudaFree(t->tile_offsets); cudaFree(t->partials); cudaFree(t->tickets);
+  cudaFree(t->tile_counts); cudaFree(t->tile_offsets); cudaFree(t->scan_base); cudaFree(t->partials); cudaFree(t->tickets);
   delete t;
 }
 
 int lm_task_step_parity(const LmTask* t) { return t ? t->parity : -1; }
 
 int lm_task_set_clamp_observations(LmTask* t, int on) { if (!t) return LM_ERR_BAD_ARG; t->clamp_observations = on; return LM_OK; }
+
+int lm_task_set_timeline(LmTask* t, long long* stamps_dev) { if (!t) return LM_ERR_BAD_ARG; t->timeline = stamps_dev; return LM_OK; }
 
 int lm_task_invalidate_reset_scan(LmTask* t) { if (!t) return LM_ERR_BAD_ARG; t->scan_valid = 0; return LM_OK; }
 
@@ -1019,14 +1111,14 @@ int lm_task_pre_step(LmTask* t, const LmRobotViews* loco, const LmRobotViews* ma
   const Derived& d = t->kp.d;
   t->parity ^= 1;
   if (!t->scan_valid)   // first step, or reset_buf was written from outside (task.reset(), lm_task_invalidate_reset_scan)
-    k_reset_count<<<d.num_tiles, T, 0, s>>>(t->kp, buf->reset_buf, t->tile_counts, t->tile_offsets, buf->num_reset, t->tickets + 0);
+    k_reset_count<<<d.num_tiles, T, 0, s>>>(t->kp, buf->reset_buf, t->tile_counts, t->tile_offsets, t->scan_base, buf->num_reset, t->tickets + 0);
   t->scan_valid = 0;
   PreArgs a;
   memset(&a, 0, sizeof(a));
   if (loco) a.loco = *loco;
   if (mani) a.mani = *mani;
   a.env_pos = env_pos; a.buf = *buf; a.actions = actions; a.uniforms = uniforms;
-  a.tile_offsets = t->tile_offsets; a.parity = t->parity;
+  a.tile_offsets = t->tile_offsets; a.scan_base = t->scan_base; a.parity = t->parity;
   k_pre<<<d.num_tiles, T, 0, s>>>(t->kp, a);
   return lm_check_launch("lm_task_pre_step");
 }
@@ -1057,11 +1149,13 @@ int lm_task_post_step(LmTask* t, const LmRobotViews* loco, const LmRobotViews* m
   if (loco) a.loco = *loco;
   if (mani) a.mani = *mani;
   a.env_pos = env_pos; a.buf = *buf; a.partials = t->partials; a.ticket = t->tickets + 1; a.tile_offsets = t->tile_offsets;
-  a.parity = t->parity; a.clamp_observations = t->clamp_observations;
+  a.parity = t->parity; a.clamp_observations = t->clamp_observations; a.timeline = t->timeline;
+  a.scan_base = t->scan_base; a.inline_finish = t->inline_finish;
   if (t->kp.p.num_states == LM_NUM_STATES_FULL)
     k_post<<<t->kp.d.num_tiles, T, PostSmem::kBytes, (cudaStream_t)stream>>>(t->kp, a);
   else
     k_post_lean<<<t->kp.d.num_tiles, T, LeanSmem::kBytes, (cudaStream_t)stream>>>(t->kp, a);
+  if (!t->inline_finish) k_post_finish<<<1, FINISH_THREADS, 0, (cudaStream_t)stream>>>(t->kp, a);
   t->scan_valid = 1;
   return lm_check_launch("lm_task_post_step");
 }
@@ -1077,8 +1171,8 @@ int lm_clamp_copy(const float* in, float* out, int64_t count, float clip, void* 
   return lm_check_launch("lm_clamp_copy");
 }
 
-int lm_task_step_host(LmTask* t, const LmRobotViews* loco, const LmRobotViews* mani, const float* env_pos,
-                      const LmTaskBuffers* buf, const LmHostStep* io, void* stream) {
+static int step_host_impl(LmTask* t, const LmRobotViews* loco, const LmRobotViews* mani, const float* env_pos,
+                          const LmTaskBuffers* buf, const LmHostStep* io, void* stream, bool sync) {
   if (!t || !io) return lm_fail(LM_ERR_BAD_ARG, "lm_task_step_host: NULL argument");
   cudaStream_t s = (cudaStream_t)stream;
   const int N = t->kp.p.num_envs;
@@ -1101,10 +1195,25 @@ int lm_task_step_host(LmTask* t, const LmRobotViews* loco, const LmRobotViews* m
   if (io->obs_host && (e = cudaMemcpyAsync(io->obs_host, buf->obs_buf, sizeof(float) * (size_t)N * LM_NUM_OBS, cudaMemcpyDeviceToHost, s)) != cudaSuccess) goto fail;
   if (io->rew_host && (e = cudaMemcpyAsync(io->rew_host, buf->rew_buf, sizeof(float) * N, cudaMemcpyDeviceToHost, s)) != cudaSuccess) goto fail;
   if (io->reset_host && (e = cudaMemcpyAsync(io->reset_host, buf->reset_buf, sizeof(int64_t) * N, cudaMemcpyDeviceToHost, s)) != cudaSuccess) goto fail;
-  if ((e = cudaStreamSynchronize(s)) != cudaSuccess) goto fail;
+  if (sync && (e = cudaStreamSynchronize(s)) != cudaSuccess) goto fail;
   return LM_OK;
 fail:
   return lm_fail((int)e, "lm_task_step_host: %s", cudaGetErrorString(e));
+}
+
+int lm_task_step_host(LmTask* t, const LmRobotViews* loco, const LmRobotViews* mani, const float* env_pos,
+                      const LmTaskBuffers* buf, const LmHostStep* io, void* stream) {
+  return step_host_impl(t, loco, mani, env_pos, buf, io, stream, true);
+}
+
+int lm_task_step_host_async(LmTask* t, const LmRobotViews* loco, const LmRobotViews* mani, const float* env_pos,
+                            const LmTaskBuffers* buf, const LmHostStep* io, void* stream) {
+  return step_host_impl(t, loco, mani, env_pos, buf, io, stream, false);
+}
+
+int lm_stream_synchronize(void* stream) {
+  cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
+  return e == cudaSuccess ? LM_OK : lm_fail((int)e, "lm_stream_synchronize: %s", cudaGetErrorString(e));
 }
 
 }  // extern "C"

@@ -1,0 +1,90 @@
+"""Host-buffer stepping of one GPU's env batch: the e2e entry a vec-env adapter with HOST tensors would call.
+
+The batch is split into ``shards`` env shards — the same block sharding the multi-GPU path uses (envs
+are independent; every shard keeps its own locomotion/manipulation halves) — each with its own task handle, CUDA
+stream and pinned host buffers.  One ``step`` enqueues, per shard and without any host synchronisation in between,
+
+    H2D actions + goal uniforms -> pre_physics_step -> H2D physics state -> post_physics_step -> D2H obs/rew/reset
+    -> policy forward -> D2H mu/value                         (lm_task_step_host_async + lm_mlp_forward)
+
+so shard k's host->device copies overlap shard k-1's kernels and device->host copies (PCIe is full duplex), then
+waits for every shard.  Inputs and outputs live in pinned host memory; nothing is cached across steps.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional
+
+import torch
+
+from . import _lib, synthetic
+from .configs import TaskConfig
+from .tasks.base import LocoManipulationTask
+
+
+class _Shard:
+    def __init__(self, cfg: TaskConfig, n: int, device, seed: int, env_id_offset: int):
+        pin = lambda *shape, dtype=torch.float32: torch.zeros(*shape, dtype=dtype).pin_memory()
+        self.n = n
+        self.scene = synthetic.SyntheticScene(cfg, n, device=device, seed=seed, env_id_offset=env_id_offset)
+        self.task = LocoManipulationTask(cfg, n, scene=self.scene, device=device, fuse_obs_clamp=True, seed=seed)
+        self.stream = torch.cuda.Stream(device=device)
+        self.actions_dev = torch.zeros(n, 12, device=device)
+        self.uniforms_dev = torch.zeros(n, 3, device=device)
+        self.mu_dev = torch.zeros(n, 12, device=device)
+        self.value_dev = torch.zeros(n, 1, device=device)
+        self.uniforms_host = pin(n, 3)
+        self.obs_host, self.rew_host, self.reset_host = pin(n, 64), pin(n), pin(n, dtype=torch.long)
+        self.mu_host = [pin(n, 12), pin(n, 12)]           # ping-pong: step t's mean is step t+1's action input
+        self.value_host = pin(n, 1)
+        self.io = _lib.LmHostStep()
+        self.io.actions_dev, self.io.uniforms_dev = self.actions_dev.data_ptr(), self.uniforms_dev.data_ptr()
+        self.io.uniforms_host = self.uniforms_host.data_ptr()
+        self.io.obs_host, self.io.rew_host, self.io.reset_host = self.obs_host.data_ptr(), self.rew_host.data_ptr(), self.reset_host.data_ptr()
+
+
+class ShardedHostStepper:
+    def __init__(self, cfg: TaskConfig, num_envs: int, policy, shards: int = 4, device="cuda:0", seed: int = 42,
+                 env_id_offset: int = 0, norm_mean: Optional[torch.Tensor] = None, norm_inv_std: Optional[torch.Tensor] = None):
+        if num_envs % shards or (num_envs // shards) % 2:
+            raise _lib.LmError("num_envs must split into an even number of envs per shard")
+        self.lib = _lib.load()
+        self.cfg, self.policy, self.device = cfg, policy, torch.device(device)
+        self.norm_mean, self.norm_inv_std = norm_mean, norm_inv_std
+        n = num_envs // shards
+        self.shards: List[_Shard] = [_Shard(cfg, n, self.device, seed + 17 * k, env_id_offset + k * n) for k in range(shards)]
+        self.parity = 0
+        self.h2d_bytes = sum(4 * (s.actions_dev.numel() + s.uniforms_dev.numel()) for s in self.shards)
+        self.d2h_bytes = sum(4 * (s.obs_host.numel() + s.rew_host.numel() + 12 * s.n + s.n) + 8 * s.reset_host.numel() for s in self.shards)
+
+    def step(self, host_states: List[Dict[str, torch.Tensor]]) -> None:
+        """One env step for the whole batch.  ``host_states[k]`` = shard k's PhysX state in pinned host memory, packed like
+        the shard's device arena (SyntheticScene.pack_host); goal uniforms are read from ``shards[k].uniforms_host``;
+        actions are the previous step's policy means (``shards[k].mu_host``), as a host-side RL loop would feed back."""
+        p = self.parity
+        for s, hs in zip(self.shards, host_states):
+            io, task = s.io, s.task
+            io.actions_host = s.mu_host[p].data_ptr()
+            for grp in ("loco", "mani"):
+                if grp in hs:
+                    setattr(io, grp + "_state_host", hs[grp].data_ptr())
+                    setattr(io, grp + "_state_floats", hs[grp].numel())
+                    setattr(io, grp + "_state_dev", s.scene.arena[grp].data_ptr())
+            with torch.cuda.stream(s.stream):
+                rc = self.lib.lm_task_step_host_async(task._handle, task._lp(), task._mp(), task._env_pos.data_ptr(),
+                                                      C.byref(task._buffers), C.byref(io), s.stream.cuda_stream)
+                _lib.check(rc, "lm_task_step_host_async")
+                task._posted_since_pre = True
+                if self.norm_mean is not None:
+                    self.policy(task.obs_buf, norm_mean=self.norm_mean, norm_inv_std=self.norm_inv_std, out=(s.mu_dev, s.value_dev))
+                else:
+                    self.policy(task.obs_buf, out=(s.mu_dev, s.value_dev))
+                s.mu_host[p ^ 1].copy_(s.mu_dev, non_blocking=True)
+                s.value_host.copy_(s.value_dev, non_blocking=True)
+        for s in self.shards:
+            _lib.check(self.lib.lm_stream_synchronize(s.stream.cuda_stream), "lm_stream_synchronize")
+        self.parity = p ^ 1
+
+    @property
+    def mu_host(self) -> List[torch.Tensor]:
+        return [s.mu_host[self.parity] for s in self.shards]
