@@ -326,6 +326,9 @@ __device__ __forceinline__ long long globaltimer_ns() {
 __device__ __forceinline__ void stamp(const PostArgs& a, int k) {
   if (a.timeline != nullptr && threadIdx.x == 0) a.timeline[(size_t)blockIdx.x * 8 + k] = globaltimer_ns();
 }
+__device__ __forceinline__ void stamp_at(const PostArgs& a, int k) {   // caller picks the thread
+  if (a.timeline != nullptr) a.timeline[(size_t)blockIdx.x * 8 + k] = globaltimer_ns();
+}
 
 struct EnvIn {
   float jp[12], jv[12], last_jv[12], cur[12], last[12];
@@ -343,8 +346,9 @@ struct EnvOut {
 
 // Emits one 16-byte chunk k (0..15) of the 64-float observation row.
 struct ObsToGlobal {
-  float4* row; float clip; int clamp;
+  float4* row; float clip; int clamp; bool on = true;
   __device__ __forceinline__ void operator()(int k, float a, float b, float c, float d) const {
+    if (!on) return;
     if (clamp) {
       a = fminf(fmaxf(a, -clip), clip); b = fminf(fmaxf(b, -clip), clip);
       c = fminf(fmaxf(c, -clip), clip); d = fminf(fmaxf(d, -clip), clip);
@@ -353,69 +357,76 @@ struct ObsToGlobal {
   }
 };
 
-// tips: 4x3 world positions in, base-frame positions out (in place); knees: 8x3 world positions
+// The per-env math is split into a POSE half (orientation / frame quantities, obs[0:16], orientation reward, success
+// state machine, termination) and a LIMB half (joint sums and limits, obs[16:64], tips / corners / knees).  The single-
+// kernels run both in one thread, in the order that suits their staging: k_post_lean needs the limb half to consume the
+// staged knees before observation chunks are emitted.  FrameShare (pose -> limb) and LimbOut (limb -> pose) are the
+// only values crossing between the halves.
+struct FrameShare {                // pose -> limb
+  float R[9];                      // rot_matrices_from_quat(q)   (math.py:7-19)
+  float pinv[3];                   // bmm(R^T, -pl)               (math.py:165-166)
+  float plz;                       // local z of the base
+};
+struct LimbOut {                   // limb -> pose
+  float jacc, arate;               // joint-acceleration / action-rate reward terms
+  int brk, rst, corner_low, knee_low;
+};
+
+// ---- limb half, part 1 (no frame needed): acceleration / action-rate sums (robot.py:290; QPC:443,446), joint-limit
+//      flags (QPC:466-504 / JLV:574-597) and obs[16:64] (QPC:367-370)
 template <typename Sink>
-__device__ __forceinline__ void env_math(const KernelParams& kp, const int is_mani, const EnvIn& in, float* tips,
-                                         const float* knees, const Sink& sink, EnvOut& out) {
+__device__ __forceinline__ void limb_joints(const KernelParams& kp, const float jp[12], const float jv[12], const float last_jv[12],
+                                            const float cur[12], const float last[12], const Sink& sink, LimbOut& lo) {
   const LmTaskParams& P = kp.p;
-#pragma unroll
-  for (int i = 0; i < STATS; ++i) out.stats[i] = 0.0f;
-  // ---- joint part first (its inputs die early): acceleration / action-rate sums (robot.py:290; QPC:443,446),
-  //      joint-limit flags (QPC:466-504 / JLV:574-597) and obs[16:64] (QPC:367-370)
   float acc_sum = 0.0f, rate_sum = 0.0f;
 #pragma unroll
   for (int j = 0; j < 12; ++j) {
-    const float acc = fdiv(sub(in.jv[j], in.last_jv[j]), P.time_interval);
+    const float acc = fdiv(sub(jv[j], last_jv[j]), P.time_interval);
     acc_sum = add(acc_sum, mul(fabsf(acc), P.joint_acc_scale));
-    rate_sum = add(rate_sum, fabsf(sub(in.last[j], in.cur[j])));
+    rate_sum = add(rate_sum, fabsf(sub(last[j], cur[j])));
   }
-  const float jacc = acc_sum, arate = mul(rate_sum, P.action_rate_scale);
+  lo.jacc = acc_sum;
+  lo.arate = mul(rate_sum, P.action_rate_scale);
   int brk = 0, rst = 0;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    const float d = fabsf(sub(in.jp[5 + 2 * k], in.jp[4 + 2 * k]));
+    const float d = fabsf(sub(jp[5 + 2 * k], jp[4 + 2 * k]));
     brk |= (d < P.min_joint_23_diff) | (d > P.max_joint_23_diff);
     rst |= (d < P.reset_min_joint_23_diff) | (d > P.reset_max_joint_23_diff);
     const bool mirrored = P.joint1_mirrored && (k == 1 || k == 2);
-    const float lo = mirrored ? -P.max_joint_1_pos : P.min_joint_1_pos, hi = mirrored ? -P.min_joint_1_pos : P.max_joint_1_pos;
+    const float lo1 = mirrored ? -P.max_joint_1_pos : P.min_joint_1_pos, hi1 = mirrored ? -P.min_joint_1_pos : P.max_joint_1_pos;
     const float rlo = mirrored ? -P.reset_max_joint_1_pos : P.reset_min_joint_1_pos;
     const float rhi = mirrored ? -P.reset_min_joint_1_pos : P.reset_max_joint_1_pos;
-    brk |= (in.jp[k] < lo) | (in.jp[k] > hi);
-    rst |= (in.jp[k] < rlo) | (in.jp[k] > rhi);
+    brk |= (jp[k] < lo1) | (jp[k] > hi1);
+    rst |= (jp[k] < rlo) | (jp[k] > rhi);
   }
+  lo.brk = brk; lo.rst = rst;
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
-    sink(4 + k, mul(P.joint_position_scale, in.jp[4 * k]), mul(P.joint_position_scale, in.jp[4 * k + 1]),
-         mul(P.joint_position_scale, in.jp[4 * k + 2]), mul(P.joint_position_scale, in.jp[4 * k + 3]));
-    sink(7 + k, mul(P.joint_velocity_scale, in.jv[4 * k]), mul(P.joint_velocity_scale, in.jv[4 * k + 1]),
-         mul(P.joint_velocity_scale, in.jv[4 * k + 2]), mul(P.joint_velocity_scale, in.jv[4 * k + 3]));
-    sink(10 + k, in.cur[4 * k], in.cur[4 * k + 1], in.cur[4 * k + 2], in.cur[4 * k + 3]);
-    sink(13 + k, in.last[4 * k], in.last[4 * k + 1], in.last[4 * k + 2], in.last[4 * k + 3]);
+    sink(4 + k, mul(P.joint_position_scale, jp[4 * k]), mul(P.joint_position_scale, jp[4 * k + 1]),
+         mul(P.joint_position_scale, jp[4 * k + 2]), mul(P.joint_position_scale, jp[4 * k + 3]));
+    sink(7 + k, mul(P.joint_velocity_scale, jv[4 * k]), mul(P.joint_velocity_scale, jv[4 * k + 1]),
+         mul(P.joint_velocity_scale, jv[4 * k + 2]), mul(P.joint_velocity_scale, jv[4 * k + 3]));
+    sink(10 + k, cur[4 * k], cur[4 * k + 1], cur[4 * k + 2], cur[4 * k + 3]);
+    sink(13 + k, last[4 * k], last[4 * k + 1], last[4 * k + 2], last[4 * k + 3]);
   }
+}
 
-  // ---- frame quantities per kind
-  const Vec3 O = in.O;
-  const Vec3 pl{sub(in.Pw.x, O.x), sub(in.Pw.y, O.y), sub(in.Pw.z, O.z)};      // local pose (robot.py:295 / rigid_object.py:54)
-  Vec3 pos, lin_o, ang_o;
-  Quat cur_q;
-  float body_height;
+// ---- limb half, part 2: tips into the robot frame (in place), corner / knee height tests
+//      tips: 4x3 world positions in, base-frame positions out; knees: 8x3 world positions
+__device__ __forceinline__ void limb_frame(const KernelParams& kp, const int is_mani, const Vec3& O, const FrameShare& f, float* tips,
+                                           const float* knees, LimbOut& lo) {
+  const LmTaskParams& P = kp.p;
   int corner_low = 0, knee_low = 0;
-  float R[9];
-  rot_from_quat_scipy(in.q, R);
   if (!is_mani) {
-    pos = quat_rotate_t<true>(in.q, Vec3{-pl.x, -pl.y, -pl.z});                          // QPC:319
-    cur_q = quat_conj(in.q);                                                            // QPC:322
-    lin_o = quat_rotate_t<true>(in.q, Vec3{-in.lin.x, -in.lin.y, -in.lin.z});           // QPC:326
-    ang_o = quat_rotate_t<true>(in.q, Vec3{-in.ang.x, -in.ang.y, -in.ang.z});           // QPC:329
-    const Vec3 pinv = tf_inverse_translation(R, pl);
+    const Vec3 pinv{f.pinv[0], f.pinv[1], f.pinv[2]};
 #pragma unroll
     for (int k = 0; k < 4; ++k) {                                                       // QPC:332-335
-      const Vec3 t = tf_inverse_apply(R, pinv, Vec3{sub(tips[3 * k], O.x), sub(tips[3 * k + 1], O.y), sub(tips[3 * k + 2], O.z)});
+      const Vec3 t = tf_inverse_apply(f.R, pinv, Vec3{sub(tips[3 * k], O.x), sub(tips[3 * k + 1], O.y), sub(tips[3 * k + 2], O.z)});
       tips[3 * k] = t.x; tips[3 * k + 1] = t.y; tips[3 * k + 2] = t.z;
-      const float cz = add(row_dot(R + 6, 1, Vec3{P.corners[k][0], P.corners[k][1], P.corners[k][2]}), pl.z);   // QPC:574-579
+      const float cz = add(row_dot(f.R + 6, 1, Vec3{P.corners[k][0], P.corners[k][1], P.corners[k][2]}), f.plz);   // QPC:574-579
       corner_low |= cz < P.baseline_corner_height;
     }
-    body_height = pl.z;                                                                 // QPC:569
 #pragma unroll
     for (int k = 0; k < 8; ++k) knee_low |= sub(sub(knees[3 * k + 2], O.z), P.baseline_knee_height) <= 0.0f;   // QPC:585-587
   } else {
@@ -423,27 +434,68 @@ __device__ __forceinline__ void env_math(const KernelParams& kp, const int is_ma
     float R0[9];
 #pragma unroll
     for (int i = 0; i < 9; ++i) R0[i] = kp.d.R0[i];
-    pos = tf_inverse_apply(R0, p0inv, pl);                                              // QMP:326-329
-    float M[9];
-    mat3_mul<true>(R0, R, M);                                                           // QMP:332 (math.py:70-74)
-    cur_q = quat_from_rot_scipy(M);
-    const Quat q0{P.mani_default_quaternion[0], P.mani_default_quaternion[1], P.mani_default_quaternion[2], P.mani_default_quaternion[3]};
-    lin_o = quat_rotate_t<true>(q0, in.lin);                                            // QMP:338
-    ang_o = quat_rotate_t<true>(q0, in.ang);
-    const Vec3 pinv = tf_inverse_translation(R, pl);                                    // plate frame (QMP:576-603)
-    body_height = tf_inverse_apply_z(R, pinv.z, Vec3{P.mani_default_position[0], P.mani_default_position[1], P.mani_default_position[2]});
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const Vec3 t = tf_inverse_apply(R0, p0inv, Vec3{sub(tips[3 * k], O.x), sub(tips[3 * k + 1], O.y), sub(tips[3 * k + 2], O.z)});   // QMP:343
       tips[3 * k] = t.x; tips[3 * k + 1] = t.y; tips[3 * k + 2] = t.z;
-      const float cz = tf_inverse_apply_z(R, pinv.z, Vec3{kp.d.corners_world[k][0], kp.d.corners_world[k][1], kp.d.corners_world[k][2]});
+      const float cz = tf_inverse_apply_z(f.R, f.pinv[2], Vec3{kp.d.corners_world[k][0], kp.d.corners_world[k][1], kp.d.corners_world[k][2]});
       corner_low |= cz < P.baseline_corner_height;
     }
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const float kz = tf_inverse_apply_z(R, pinv.z, Vec3{sub(knees[3 * k], O.x), sub(knees[3 * k + 1], O.y), sub(knees[3 * k + 2], O.z)});
+    for (int k = 0; k < 8; ++k) {                                                       // plate frame (QMP:576-603)
+      const float kz = tf_inverse_apply_z(f.R, f.pinv[2], Vec3{sub(knees[3 * k], O.x), sub(knees[3 * k + 1], O.y), sub(knees[3 * k + 2], O.z)});
       knee_low |= sub(kz, P.baseline_knee_height) <= 0.0f;
     }
+  }
+  lo.corner_low = corner_low; lo.knee_low = knee_low;
+}
+
+struct PoseIn {
+  Vec3 O, Pw, lin, ang;
+  Quat q, goal;
+  int progress, reset, succ_prev, consec;
+};
+struct PoseMid {                   // pose-half values that wait for the limb half
+  float posz, body_height, rot_rew, trans, bonus;
+  int goal_reset, success, consec;
+};
+
+// ---- pose half, part 1: local pose and the frame the limb half needs
+__device__ __forceinline__ Vec3 pose_frame(const PoseIn& in, FrameShare& f) {
+  const Vec3 pl{sub(in.Pw.x, in.O.x), sub(in.Pw.y, in.O.y), sub(in.Pw.z, in.O.z)};   // local pose (robot.py:295 / rigid_object.py:54)
+  rot_from_quat_scipy(in.q, f.R);
+  const Vec3 pinv = tf_inverse_translation(f.R, pl);
+  f.pinv[0] = pinv.x; f.pinv[1] = pinv.y; f.pinv[2] = pinv.z;
+  f.plz = pl.z;
+  return pl;
+}
+
+// ---- pose half, part 2: frame quantities per kind, orientation error, obs[0:16], reward terms, success state machine
+template <typename Sink>
+__device__ __forceinline__ void pose_main(const KernelParams& kp, const int is_mani, const PoseIn& in, const Vec3& pl, const FrameShare& f,
+                                          const Sink& sink, Quat& cur_q_out, PoseMid& m) {
+  const LmTaskParams& P = kp.p;
+  Vec3 pos, lin_o, ang_o;
+  Quat cur_q;
+  if (!is_mani) {
+    pos = quat_rotate_t<true>(in.q, Vec3{-pl.x, -pl.y, -pl.z});                          // QPC:319
+    cur_q = quat_conj(in.q);                                                            // QPC:322
+    lin_o = quat_rotate_t<true>(in.q, Vec3{-in.lin.x, -in.lin.y, -in.lin.z});           // QPC:326
+    ang_o = quat_rotate_t<true>(in.q, Vec3{-in.ang.x, -in.ang.y, -in.ang.z});           // QPC:329
+    m.body_height = pl.z;                                                               // QPC:569
+  } else {
+    const Vec3 p0inv{kp.d.p0inv[0], kp.d.p0inv[1], kp.d.p0inv[2]};
+    float R0[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) R0[i] = kp.d.R0[i];
+    pos = tf_inverse_apply(R0, p0inv, pl);                                              // QMP:326-329
+    float M[9];
+    mat3_mul<true>(R0, f.R, M);                                                         // QMP:332 (math.py:70-74)
+    cur_q = quat_from_rot_scipy(M);
+    const Quat q0{P.mani_default_quaternion[0], P.mani_default_quaternion[1], P.mani_default_quaternion[2], P.mani_default_quaternion[3]};
+    lin_o = quat_rotate_t<true>(q0, in.lin);                                            // QMP:338
+    ang_o = quat_rotate_t<true>(q0, in.ang);
+    m.body_height = tf_inverse_apply_z(f.R, f.pinv[2], Vec3{P.mani_default_position[0], P.mani_default_position[1], P.mani_default_position[2]});
   }
 
   // ---- orientation error (QPC:345-350,430-432)
@@ -459,42 +511,64 @@ __device__ __forceinline__ void env_math(const KernelParams& kp, const int is_ma
   sink(2, diff.y, diff.z, mul(P.linear_vel_scale, lin_o.x), mul(P.linear_vel_scale, lin_o.y));
   sink(3, mul(P.linear_vel_scale, lin_o.z), mul(P.angular_vel_scale, ang_o.x), mul(P.angular_vel_scale, ang_o.y),
        mul(P.angular_vel_scale, ang_o.z));
-  out.cur_q = cur_q;
+  cur_q_out = cur_q;
 
-  // ---- reward (QPC:432-457,506-515)
-  const float rot_rew = mul(fdiv(1.0f, add(fabsf(rot_dist), P.rot_eps)), P.quaternion_scale);
-  const float trans = mul(norm2_torch(pos.x, pos.y), P.translation_scale);
-  const int goal_reset = in.consec > P.max_consecutive_successes;                       // counter BEFORE update (QPC:449)
-  const float bonus = mul(P.consecutive_success_reward, (float)goal_reset);
-  const int success = fabsf(rot_dist) <= P.success_thresh;
-  const float limit_pen = mul(P.joint_limit_penalty, (float)brk);
-  float total = add(add(add(add(add(rot_rew, trans), jacc), arate), bonus), limit_pen);
+  // ---- reward terms that do not involve the limbs (QPC:432-457)
+  m.posz = pos.z;
+  m.rot_rew = mul(fdiv(1.0f, add(fabsf(rot_dist), P.rot_eps)), P.quaternion_scale);
+  m.trans = mul(norm2_torch(pos.x, pos.y), P.translation_scale);
+  m.goal_reset = in.consec > P.max_consecutive_successes;                                // counter BEFORE update (QPC:449)
+  m.bonus = mul(P.consecutive_success_reward, (float)m.goal_reset);
+  m.success = fabsf(rot_dist) <= P.success_thresh;
 
   // ---- consecutive-success state machine (QPC:534-545)
   int consec = in.consec;
-  const int both = success && (in.succ_prev != 0);
+  const int both = m.success && (in.succ_prev != 0);
   if (!both) consec = 0;
   if (both) consec += 1;
-  if (in.succ_prev == 0 && success) consec = 1;
+  if (in.succ_prev == 0 && m.success) consec = 1;
+  m.consec = consec;
+}
 
-  // ---- termination (QPC:562-616)
+// ---- pose half, part 3: total reward (QPC:506-515) and termination (QPC:562-616) once the limb half is known
+__device__ __forceinline__ void pose_finish(const KernelParams& kp, const PoseIn& in, const PoseMid& m, const LimbOut& lo, EnvOut& out) {
+  const LmTaskParams& P = kp.p;
+  const float limit_pen = mul(P.joint_limit_penalty, (float)lo.brk);
+  float total = add(add(add(add(add(m.rot_rew, m.trans), lo.jacc), lo.arate), m.bonus), limit_pen);
   int rs = in.reset != 0;
-  rs |= pos.z > 0.0f;
-  rs |= body_height <= P.baseline_height;
-  rs |= corner_low | knee_low | rst;
+  rs |= m.posz > 0.0f;
+  rs |= m.body_height <= P.baseline_height;
+  rs |= lo.corner_low | lo.knee_low | lo.rst;
   const float fall = mul(P.fall_penalty, (float)rs);
   total = add(total, fall);
-  rs |= goal_reset;
+  rs |= m.goal_reset;
   const int progress = in.progress + 1;                                                 // rl_task.py:251
   rs |= progress >= (P.max_episode_length - 1);
 
-  out.rew = total; out.progress = progress; out.consec = consec; out.reset = rs; out.success = success; out.goal_reset = goal_reset;
-  out.stats[0] = rot_rew; out.stats[1] = trans; out.stats[2] = jacc; out.stats[3] = arate; out.stats[4] = bonus;
+  out.rew = total; out.progress = progress; out.consec = m.consec; out.reset = rs; out.success = m.success; out.goal_reset = m.goal_reset;
+#pragma unroll
+  for (int i = 0; i < STATS; ++i) out.stats[i] = 0.0f;
+  out.stats[0] = m.rot_rew; out.stats[1] = m.trans; out.stats[2] = lo.jacc; out.stats[3] = lo.arate; out.stats[4] = m.bonus;
   out.stats[5] = limit_pen; out.stats[6] = fall;
   out.stats[7] = isnan(total) ? 1.0f : 0.0f;
   out.stats[8] = total < -50.0f ? 1.0f : 0.0f;
-  out.stats[9] = (float)goal_reset;
+  out.stats[9] = (float)m.goal_reset;
   out.stats[10] = (float)rs;
+}
+
+// Both halves in one thread (k_post: the 93-wide states variant)
+template <typename Sink>
+__device__ __forceinline__ void env_math(const KernelParams& kp, const int is_mani, const EnvIn& in, float* tips,
+                                         const float* knees, const Sink& sink, EnvOut& out) {
+  LimbOut lo;
+  limb_joints(kp, in.jp, in.jv, in.last_jv, in.cur, in.last, sink, lo);
+  PoseIn pin{in.O, in.Pw, in.lin, in.ang, in.q, in.goal, in.progress, in.reset, in.succ_prev, in.consec};
+  FrameShare f;
+  const Vec3 pl = pose_frame(pin, f);
+  limb_frame(kp, is_mani, in.O, f, tips, knees, lo);
+  PoseMid m;
+  pose_main(kp, is_mani, pin, pl, f, sink, out.cur_q, m);
+  pose_finish(kp, pin, m, lo, out);
 }
 
 __device__ __forceinline__ void store_flags(const LmTaskBuffers& b, int e, const EnvOut& out) {
@@ -514,7 +588,7 @@ constexpr int FINISH_THREADS = 1024;   // stand-alone finish kernel (large grids
 constexpr int INLINE_FINISH_MAX_TILES = 1024;
 
 struct FinishSmem {
-  float red_f[4][STATS];            // per-warp partial sums of this CTA
+  float red_f[8][STATS];            // per-warp partial sums of this CTA (up to 8 warps)
   double red_d[32][13];             // finish pass: per-warp sums (11 totals + manipulation-half counts 9, 10)
   int warp_scan[32];
   int is_last;
@@ -668,21 +742,6 @@ __global__ void __launch_bounds__(FINISH_THREADS) k_post_finish(const KernelPara
   finish_tail<FINISH_THREADS>(kp, a, fs);
 }
 
-// ------------------------------------------------------------------------------------------------
-// K_post, lean tiling (states alias obs: every co-train task).  Only the arrays whose row stride defeats
-// coalescing (20-wide DOF rows, 12-wide tip rows, 24-wide knee rows) are staged through shared memory by
-// TMA; 16-byte-friendly rows are loaded straight into registers while the bulk copies fly.  39 KB of
-// shared memory per CTA -> 4 resident CTAs (16 warps) per SM to hide the double-precision latency chains.
-// ------------------------------------------------------------------------------------------------
-struct LeanSmem {
-  static constexpr int kDofPos = 0;
-  static constexpr int kDofVel = kDofPos + T * 20;
-  static constexpr int kTips = kDofVel + T * 20;
-  static constexpr int kKnees = kTips + T * 12;
-  static constexpr int kEnd = kKnees + T * 24;
-  static constexpr int kBytes = kEnd * 4 + 64;
-};
-
 __device__ __forceinline__ void ld12(const float* p, float v[12]) {
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
@@ -696,13 +755,54 @@ __device__ __forceinline__ void st12(float* p, const float v[12]) {
 }
 __device__ __forceinline__ Vec3 ld3(const float* p) { return Vec3{p[0], p[1], p[2]}; }
 
+// ------------------------------------------------------------------------------------------------
+// K_post, lean tiling (states alias obs: every co-train task).  One env per thread, 128 envs per CTA.  Only the
+// arrays whose row stride defeats coalescing (20-wide DOF rows, 12-wide tip rows, 24-wide knee rows) are staged through
+// shared memory by TMA; 16-byte-friendly rows are loaded straight into registers while the bulk copies fly.
+// Observation rows leave through shared memory too: a thread storing its own 256-byte row would touch 32 different
+// sectors per 128-bit store instruction (measured: ~45 % of the kernel's compute phase).  Each warp therefore parks
+// its 32 rows, 16-byte chunks XOR-swizzled, in the staging space of its OWN 32 envs' inputs (dead once the limb half
+// has consumed them — no CTA-wide barrier needed) and copies them out two full rows per instruction.
+// 39 KB of shared memory per CTA -> 4 resident CTAs (16 warps) per SM; 65,536 envs are a single wave.
+// ------------------------------------------------------------------------------------------------
+struct LeanSmem {
+  static constexpr int kDofPos = 0;
+  static constexpr int kDofVel = kDofPos + T * 20;
+  static constexpr int kTips = kDofVel + T * 20;
+  static constexpr int kKnees = kTips + T * 12;
+  static constexpr int kEnd = kKnees + T * 24;
+  static constexpr int kBytes = kEnd * 4 + 64;
+};
+static_assert(LeanSmem::kDofVel % 32 == 0 && LeanSmem::kTips % 32 == 0 && LeanSmem::kKnees % 32 == 0, "staging rows must start on bank 0");
+
+// float offset (in the CTA's dynamic shared memory) of observation staging row i (0..31) of warp w: the warp's own
+// input rows hold 10 + 10 + 6 + 12 rows of 64 floats
+__device__ __forceinline__ int obs_stage_row(int w, int i) {
+  if (i < 10) return LeanSmem::kDofPos + w * 640 + i * 64;
+  if (i < 20) return LeanSmem::kDofVel + w * 640 + (i - 10) * 64;
+  if (i < 26) return LeanSmem::kTips + w * 384 + (i - 20) * 64;
+  return LeanSmem::kKnees + w * 768 + (i - 26) * 64;
+}
+
+// Emits chunk k of this lane's row into the swizzled staging row.
+struct ObsToStage {
+  float* row; int lane15; float clip; int clamp;
+  __device__ __forceinline__ void operator()(int k, float a, float b, float c, float d) const {
+    if (clamp) {
+      a = fminf(fmaxf(a, -clip), clip); b = fminf(fmaxf(b, -clip), clip);
+      c = fminf(fmaxf(c, -clip), clip); d = fminf(fmaxf(d, -clip), clip);
+    }
+    *reinterpret_cast<float4*>(row + ((k ^ lane15) << 2)) = make_float4(a, b, c, d);
+  }
+};
+
 __global__ void __launch_bounds__(T, 4) k_post_lean(const KernelParams kp, const PostArgs a) {
   extern __shared__ __align__(128) float sm[];
   __shared__ uint64_t bar;
   __shared__ FinishSmem fs;
   const LmTaskParams& P = kp.p;
   const Tile tl = tile_of(kp, blockIdx.x);
-  const int r = threadIdx.x;
+  const int r = threadIdx.x, lane = r & 31, warp = r >> 5;
   const int N = P.num_envs;
   const LmRobotViews& V = tl.is_mani ? a.mani : a.loco;
   const float* ring_cur = a.buf.actions_ring + (size_t)a.parity * N * LM_NUM_ACT;
@@ -719,62 +819,79 @@ __global__ void __launch_bounds__(T, 4) k_post_lean(const KernelParams kp, const
   st.load(sm + LeanSmem::kKnees, V.knee_pos + (size_t)h0 * 24, n * 24);
   if (st.use_tma && r == 0) mbar_expect_tx(&bar, st.bytes);
 
-  EnvIn in;
   EnvOut out;
   const bool valid = r < n;
-  const int e = e0 + (valid ? r : 0), hr = h0 + (valid ? r : 0);
+  const int rr = valid ? r : 0;                       // padding lanes of a ragged tile recompute env 0 (results discarded)
+  const int e = e0 + rr, hr = h0 + rr;
+  float jp[12], jv[12], last_jv[12], cur[12], last[12], tips[12];
+  PoseIn pin;
   {
     // register loads overlap the bulk copies
-    ld12(ring_cur + (size_t)e * 12, in.cur);
-    ld12(ring_last + (size_t)e * 12, in.last);
-    ld12(a.buf.last_joint_vel + (size_t)e * 12, in.last_jv);
+    ld12(ring_cur + (size_t)e * 12, cur);
+    ld12(ring_last + (size_t)e * 12, last);
+    ld12(a.buf.last_joint_vel + (size_t)e * 12, last_jv);
     const float4 g4 = *reinterpret_cast<const float4*>(a.buf.goal_quaternions + (size_t)e * 4);
     const float4 q4 = *reinterpret_cast<const float4*>((tl.is_mani ? V.plate_quat : V.root_quat) + (size_t)hr * 4);
-    in.goal = Quat{g4.x, g4.y, g4.z, g4.w};
-    in.q = Quat{q4.x, q4.y, q4.z, q4.w};
-    in.O = ld3(a.env_pos + (size_t)hr * 3);
-    in.Pw = ld3((tl.is_mani ? V.plate_pos : V.root_pos) + (size_t)hr * 3);
-    in.lin = ld3((tl.is_mani ? V.plate_lin_vel : V.root_lin_vel) + (size_t)hr * 3);
-    in.ang = ld3((tl.is_mani ? V.plate_ang_vel : V.root_ang_vel) + (size_t)hr * 3);
-    in.progress = (int)a.buf.progress_buf[e];
-    in.reset = (int)a.buf.reset_buf[e];
-    in.succ_prev = (int)a.buf.successes[e];
-    in.consec = (int)a.buf.consecutive_successes[e];
+    pin.goal = Quat{g4.x, g4.y, g4.z, g4.w};
+    pin.q = Quat{q4.x, q4.y, q4.z, q4.w};
+    pin.O = ld3(a.env_pos + (size_t)hr * 3);
+    pin.Pw = ld3((tl.is_mani ? V.plate_pos : V.root_pos) + (size_t)hr * 3);
+    pin.lin = ld3((tl.is_mani ? V.plate_lin_vel : V.root_lin_vel) + (size_t)hr * 3);
+    pin.ang = ld3((tl.is_mani ? V.plate_ang_vel : V.root_ang_vel) + (size_t)hr * 3);
+    pin.progress = (int)a.buf.progress_buf[e];
+    pin.reset = (int)a.buf.reset_buf[e];
+    pin.succ_prev = (int)a.buf.successes[e];
+    pin.consec = (int)a.buf.consecutive_successes[e];
   }
   stamp(a, 1);
   if (st.use_tma) mbar_wait(&bar, 0); else __syncthreads();
   stamp(a, 2);
+  if (kp.d.dof_identity) {
+    ld12(sm + LeanSmem::kDofPos + rr * 20, jp);
+    ld12(sm + LeanSmem::kDofVel + rr * 20, jv);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 12; ++j) {
+      jp[j] = sm[LeanSmem::kDofPos + rr * 20 + P.dof_index[j]];
+      jv[j] = sm[LeanSmem::kDofVel + rr * 20 + P.dof_index[j]];
+    }
+  }
+  ld12(sm + LeanSmem::kTips + rr * 12, tips);
+  if (valid) st12(a.buf.last_joint_vel + (size_t)e * 12, jv);                          // robot.py:291
+
+  // frame first, so the limb half consumes the knees (the last staged input) before the observation chunks start
+  // to overwrite this warp's staging space
+  LimbOut lo;
+  FrameShare f;
+  const Vec3 pl = pose_frame(pin, f);
+  limb_frame(kp, tl.is_mani, pin.O, f, tips, sm + LeanSmem::kKnees + rr * 24, lo);
+  if (valid) st12(a.buf.last_base_tip + (size_t)e * 12, tips);                         // QPC:426
+  __syncwarp();                                        // every lane of the warp is done with the staged inputs
+  const ObsToStage sink{sm + obs_stage_row(warp, lane), lane & 15, P.clip_observations, a.clamp_observations};
+  limb_joints(kp, jp, jv, last_jv, cur, last, sink, lo);
+  PoseMid m;
+  pose_main(kp, tl.is_mani, pin, pl, f, sink, out.cur_q, m);
+  pose_finish(kp, pin, m, lo, out);
+  if (valid) {
+    store_flags(a.buf, e, out);
+  } else {
+#pragma unroll
+    for (int i = 0; i < STATS; ++i) out.stats[i] = 0.0f;
+  }
+  __syncwarp();
   {
-    const int rr = valid ? r : 0;
-    if (kp.d.dof_identity) {
-      ld12(sm + LeanSmem::kDofPos + rr * 20, in.jp);
-      ld12(sm + LeanSmem::kDofVel + rr * 20, in.jv);
-    } else {
+    // copy-out: instruction j moves rows 2j and 2j+1 of the warp (2 x 256 contiguous bytes)
+    const int half = lane >> 4, c = lane & 15;
+    float4* obs_g = reinterpret_cast<float4*>(a.buf.obs_buf + (size_t)(e0 + (warp << 5)) * LM_NUM_OBS);
+    const int rows_here = min(32, n - (warp << 5));
 #pragma unroll
-      for (int j = 0; j < 12; ++j) {
-        in.jp[j] = sm[LeanSmem::kDofPos + rr * 20 + P.dof_index[j]];
-        in.jv[j] = sm[LeanSmem::kDofVel + rr * 20 + P.dof_index[j]];
-      }
-    }
-    float tips[12];
-    ld12(sm + LeanSmem::kTips + rr * 12, tips);
-    // padding lanes of a ragged tile write their (meaningless) obs row into a scratch row of shared memory
-    float4* orow = valid ? reinterpret_cast<float4*>(a.buf.obs_buf + (size_t)e * LM_NUM_OBS)
-                         : reinterpret_cast<float4*>(sm + LeanSmem::kDofPos + rr * 20);
-    if (valid) st12(a.buf.last_joint_vel + (size_t)e * 12, in.jv);                      // robot.py:291
-    env_math(kp, tl.is_mani, in, tips, sm + LeanSmem::kKnees + rr * 24, ObsToGlobal{orow, P.clip_observations, a.clamp_observations}, out);
-    if (valid) {
-      st12(a.buf.last_base_tip + (size_t)e * 12, tips);                                 // QPC:426
-      store_flags(a.buf, e, out);
-    } else {
-#pragma unroll
-      for (int i = 0; i < STATS; ++i) out.stats[i] = 0.0f;
+    for (int j = 0; j < 16; ++j) {
+      const int row = 2 * j + half;
+      const float4 v = *reinterpret_cast<const float4*>(sm + obs_stage_row(warp, row) + ((c ^ (row & 15)) << 2));
+      if (row < rows_here) obs_g[row * 16 + c] = v;
     }
   }
-  if (a.timeline != nullptr && r == 0) {
-    // first use of the register-loaded rows forces their arrival
-    a.timeline[(size_t)blockIdx.x * 8 + 3] = globaltimer_ns() + (long long)(out.rew != out.rew ? 1 : 0);
-  }
+  stamp(a, 3);
   finish_stats<T>(kp, a, out.stats, fs);
   stamp(a, 4);
 }

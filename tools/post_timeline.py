@@ -1,4 +1,4 @@
-"""Diagnostic: per-CTA stage timeline (%globaltimer) of k_post_lean (needs a B200).  python tools/post_timeline.py [n_envs]"""
+"""Diagnostic: per-CTA stage timeline (%globaltimer) of k_post_pair (needs a B200).  python tools/post_timeline.py [n_envs]"""
 import os
 import sys
 
