@@ -614,6 +614,11 @@ __device__ __forceinline__ void finish_tail(const KernelParams& kp, const PostAr
   double acc[13];
 #pragma unroll
   for (int i = 0; i < 13; ++i) acc[i] = 0.0;
+  int64_t cnt[6] = {0, 0, 0, 0, 0, 0};                // success / reset counters: fetched now, used by thread 0 at the very end
+  if (r == 0) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) cnt[i] = __ldcg(reinterpret_cast<const long long*>(a.buf.counters) + i);
+  }
   int my_resets = 0, loco_rel = -1;
   const float4* part4 = reinterpret_cast<const float4*>(a.partials);
   for (int t0 = lo; t0 < hi; t0 += 4) {
@@ -681,8 +686,10 @@ __device__ __forceinline__ void finish_tail(const KernelParams& kp, const PostAr
     // group 0 = all envs, 1 = locomotion half, 2 = manipulation half (QPC:619-633 / JLV:758-802)
     const double goal[3] = {tot[9], tot[9] - tot[11], tot[11]};
     const double rst[3] = {tot[10], tot[10] - tot[12], tot[12]};
-    for (int g = 0; g < groups; ++g) {
-      int64_t ns = c[2 * g], nr = c[2 * g + 1];
+#pragma unroll
+    for (int g = 0; g < 3; ++g) {
+      if (g >= groups) break;
+      int64_t ns = cnt[2 * g], nr = cnt[2 * g + 1];
       if (nr > (int64_t)P.max_reset_counts) {
         ex[LM_EXTRA_SUCCESS_RATE + g] = (float)ns / (float)nr;
         ns = 0; nr = 0;
@@ -694,10 +701,12 @@ __device__ __forceinline__ void finish_tail(const KernelParams& kp, const PostAr
   }
 }
 
-// per-CTA partial sums -> partials[tile]; with inline_finish the last CTA to arrive runs the finish pass
-// (QPC:560,610,619-633 / JLV:758-802): thread->tile mapping and tree shape are fixed, so `extras` are deterministic.
+// per-CTA partial sums -> partials[tile] (QPC:560,610,619-633 / JLV:758-802).  finish_publish reduces the CTA's stats and
+// lets ONE thread store them, fence and take the arrival ticket; the caller keeps the other threads busy (flag stores,
+// observation copy-out) while that round trip is in flight and then calls finish_join: with inline_finish the last
+// CTA to arrive runs the finish pass.  Thread->tile mapping and tree shape are fixed, so `extras` are deterministic.
 template <int kThreads>
-__device__ __forceinline__ void finish_stats(const KernelParams& kp, const PostArgs& a, const float stats[STATS], FinishSmem& fs) {
+__device__ __forceinline__ void finish_publish(const PostArgs& a, const float stats[STATS], FinishSmem& fs) {
   const int r = threadIdx.x, lane = r & 31, warp = r >> 5;
   constexpr int kWarps = kThreads / 32;
 #pragma unroll
@@ -709,8 +718,6 @@ __device__ __forceinline__ void finish_stats(const KernelParams& kp, const PostA
   }
   __syncthreads();
   if (r == 0) {
-    // one thread publishes the CTA's partial sums, fences them and takes the ticket: the other threads' pending stores
-    // (obs rows etc.) stay off the fence's critical path
     float4* dst = reinterpret_cast<float4*>(a.partials + (size_t)blockIdx.x * STATS);
     float v[STATS];
 #pragma unroll
@@ -730,10 +737,20 @@ __device__ __forceinline__ void finish_stats(const KernelParams& kp, const PostA
       fs.is_last = 0;
     }
   }
+}
+template <int kThreads>
+__device__ __forceinline__ void finish_join(const KernelParams& kp, const PostArgs& a, FinishSmem& fs) {
   __syncthreads();
   if (!fs.is_last) return;
-  __threadfence();
+  // No second fence: every other CTA fenced its partial sums (L2, st.cg) before its ticket increment, this CTA observed
+  // the final ticket value before the barrier above, and the finish pass reads them with L2 loads (ld.cg).  A full fence
+  // here would only wait for this CTA's own observation stores.
   finish_tail<kThreads>(kp, a, fs);
+}
+template <int kThreads>
+__device__ __forceinline__ void finish_stats(const KernelParams& kp, const PostArgs& a, const float stats[STATS], FinishSmem& fs) {
+  finish_publish<kThreads>(a, stats, fs);
+  finish_join<kThreads>(kp, a, fs);
 }
 
 // stand-alone finish pass for grids too large for a 128-thread tail
@@ -784,15 +801,17 @@ __device__ __forceinline__ int obs_stage_row(int w, int i) {
   return LeanSmem::kKnees + w * 768 + (i - 26) * 64;
 }
 
-// Emits chunk k of this lane's row into the swizzled staging row.
+// Emits 16-byte chunk k of this lane's observation row into its staging row at chunk slot (k ^ swz), swz = lane & 15:
+// eight consecutive lanes hit eight different bank groups (conflict-free 128-bit stores), and so does the copy-out
+// that reads the rows back two at a time.
 struct ObsToStage {
-  float* row; int lane15; float clip; int clamp;
+  float* row; int swz; float clip; int clamp;
   __device__ __forceinline__ void operator()(int k, float a, float b, float c, float d) const {
     if (clamp) {
       a = fminf(fmaxf(a, -clip), clip); b = fminf(fmaxf(b, -clip), clip);
       c = fminf(fmaxf(c, -clip), clip); d = fminf(fmaxf(d, -clip), clip);
     }
-    *reinterpret_cast<float4*>(row + ((k ^ lane15) << 2)) = make_float4(a, b, c, d);
+    *reinterpret_cast<float4*>(row + ((k ^ swz) << 2)) = make_float4(a, b, c, d);
   }
 };
 
@@ -826,10 +845,7 @@ __global__ void __launch_bounds__(T, 4) k_post_lean(const KernelParams kp, const
   float jp[12], jv[12], last_jv[12], cur[12], last[12], tips[12];
   PoseIn pin;
   {
-    // register loads overlap the bulk copies
-    ld12(ring_cur + (size_t)e * 12, cur);
-    ld12(ring_last + (size_t)e * 12, last);
-    ld12(a.buf.last_joint_vel + (size_t)e * 12, last_jv);
+    // register loads overlap the bulk copies; the small pose rows go first so the pose half can start early
     const float4 g4 = *reinterpret_cast<const float4*>(a.buf.goal_quaternions + (size_t)e * 4);
     const float4 q4 = *reinterpret_cast<const float4*>((tl.is_mani ? V.plate_quat : V.root_quat) + (size_t)hr * 4);
     pin.goal = Quat{g4.x, g4.y, g4.z, g4.w};
@@ -842,6 +858,9 @@ __global__ void __launch_bounds__(T, 4) k_post_lean(const KernelParams kp, const
     pin.reset = (int)a.buf.reset_buf[e];
     pin.succ_prev = (int)a.buf.successes[e];
     pin.consec = (int)a.buf.consecutive_successes[e];
+    ld12(ring_cur + (size_t)e * 12, cur);
+    ld12(ring_last + (size_t)e * 12, last);
+    ld12(a.buf.last_joint_vel + (size_t)e * 12, last_jv);
   }
   stamp(a, 1);
   if (st.use_tma) mbar_wait(&bar, 0); else __syncthreads();
@@ -858,26 +877,28 @@ __global__ void __launch_bounds__(T, 4) k_post_lean(const KernelParams kp, const
   }
   ld12(sm + LeanSmem::kTips + rr * 12, tips);
   if (valid) st12(a.buf.last_joint_vel + (size_t)e * 12, jv);                          // robot.py:291
-
-  // frame first, so the limb half consumes the knees (the last staged input) before the observation chunks start
-  // to overwrite this warp's staging space
   LimbOut lo;
   FrameShare f;
   const Vec3 pl = pose_frame(pin, f);
+  // the frame part of the limb half first: it consumes the knees, the last staged input, before the observation chunks
+  // start to overwrite this warp's staging space
   limb_frame(kp, tl.is_mani, pin.O, f, tips, sm + LeanSmem::kKnees + rr * 24, lo);
   if (valid) st12(a.buf.last_base_tip + (size_t)e * 12, tips);                         // QPC:426
   __syncwarp();                                        // every lane of the warp is done with the staged inputs
-  const ObsToStage sink{sm + obs_stage_row(warp, lane), lane & 15, P.clip_observations, a.clamp_observations};
-  limb_joints(kp, jp, jv, last_jv, cur, last, sink, lo);
   PoseMid m;
-  pose_main(kp, tl.is_mani, pin, pl, f, sink, out.cur_q, m);
+  {
+    const ObsToStage sink{sm + obs_stage_row(warp, lane), lane & 15, P.clip_observations, a.clamp_observations};
+    limb_joints(kp, jp, jv, last_jv, cur, last, sink, lo);
+    pose_main(kp, tl.is_mani, pin, pl, f, sink, out.cur_q, m);
+  }
   pose_finish(kp, pin, m, lo, out);
-  if (valid) {
-    store_flags(a.buf, e, out);
-  } else {
+  if (!valid) {
 #pragma unroll
     for (int i = 0; i < STATS; ++i) out.stats[i] = 0.0f;
   }
+  // ---- publish the CTA's partial sums (one thread: store, fence, ticket) while everybody else stores
+  finish_publish<T>(a, out.stats, fs);
+  if (valid) store_flags(a.buf, e, out);
   __syncwarp();
   {
     // copy-out: instruction j moves rows 2j and 2j+1 of the warp (2 x 256 contiguous bytes)
@@ -892,7 +913,7 @@ __global__ void __launch_bounds__(T, 4) k_post_lean(const KernelParams kp, const
     }
   }
   stamp(a, 3);
-  finish_stats<T>(kp, a, out.stats, fs);
+  finish_join<T>(kp, a, fs);
   stamp(a, 4);
 }
 
