@@ -127,13 +127,30 @@ enum {
   LM_NUM_EXTRAS = 16
 };
 
+/* State of the explicit position-PD variants (*_position_control.py: quadruped_pose_control_position_control.py:179-191,
+ * joint_locomanipulation_position_control.py:161-183), env-indexed like the RL buffers ([N,12]; co-train: locomotion rows
+ * first).  Registered once with lm_task_set_pd_state; then lm_task_pre_step resets these rows for reset envs
+ * (…position_control.py:377-386) and lm_task_post_step writes 0.3 * targets / 0.3 * last_targets into obs[40:64] instead
+ * of the current / last actions (…:438-452).  As in the reference, last_targets is only ever written on reset. */
+typedef struct LmPdState {
+  float* joint_pos;       /* [N,12] joint positions carried between PD sub-steps                 */
+  float* joint_vel;       /* [N,12]                                                              */
+  float* targets;         /* [N,12] current_joint_position_targets                               */
+  float* last_targets;    /* [N,12] last_joint_position_targets                                  */
+  float* targets_se;      /* [N,12] swing / extension form                                       */
+  float init_se[LM_NUM_ACT]; /* reset value of targets_se                                        */
+  int32_t carry_post_state; /* 1: post_step stores the observed joint state into joint_pos / joint_vel
+                             *    (single-task files, …position_control.py:392-393); 0: JL_PC            */
+  float target_obs_scale; /* the literal 0.3 of …position_control.py:438-439                     */
+} LmPdState;
+
 typedef struct LmTask LmTask; /* opaque */
 
 int lm_abi_version(void);
 const char* lm_last_error(void);
 /* number of SMs / name of the device the library will launch on (-1 / "" if none) */
 int lm_device_sm_count(int device);
-/* sizeof() of the ABI structs as compiled (0 LmTaskParams, 1 LmRobotViews, 2 LmTaskBuffers, 3 LmHostStep):
+/* sizeof() of the ABI structs as compiled (0 LmTaskParams, 1 LmRobotViews, 2 LmTaskBuffers, 3 LmHostStep, 4 LmPdState):
  * bindings assert their mirror structs agree. */
 int lm_struct_size(int which);
 
@@ -156,6 +173,9 @@ int lm_task_invalidate_reset_scan(LmTask* task);
 /* Diagnostic: when stamps_dev != NULL (device buffer of num_tiles x 8 int64, num_tiles = ceil(envs per half / 128) per
  * half), every CTA of the following lm_task_post_step launches records %globaltimer at its stages.  NULL = off (default). */
 int lm_task_set_timeline(LmTask* task, long long* stamps_dev);
+
+/* Registers (or, with NULL, clears) the PD state of a LM_CONTROL_PD task. */
+int lm_task_set_pd_state(LmTask* task, const LmPdState* pd);
 
 /* pre_physics_step (QPC:200-228 / QMP:213-236 / JLV:248-270) including reset_idx
  * (QPC:230-299 / JLV:272-377), rand_quaternions (utils/math.py:176-193) and take_action
@@ -187,6 +207,19 @@ int lm_clamp_copy(const float* in, float* out, int64_t count, float clip, void* 
 int lm_pd_substep(const float* dof_pos, const float* dof_vel, const float* targets, float* torque,
                   float* torque_sum, const int32_t* dof_index_host, int32_t n, float kp, float kd,
                   float max_effort, void* stream);
+/* The same torque law on the CARRIED joint state [n,12] (the first torque of a step uses the state read after the
+ * previous step's last sub-step, …position_control.py:295-297). */
+int lm_pd_torque(const float* joint_pos, const float* joint_vel, const float* targets, float* torque,
+                 float* torque_sum, int32_t n, float kp, float kd, float max_effort, void* stream);
+/* update_joint_states (robot.py:283-291) after a physics sub-step, fused with the next torque: gathers the actuated
+ * DOFs of the articulation rows into joint_pos / joint_vel, sets last_joint_vel = joint_vel, then applies the torque
+ * law.  accumulate = 0 leaves torque_sum alone (joint_locomanipulation_position_control.py:399-408 does not add the
+ * torque computed after the last sub-step).  With mean_torque != NULL (the last call of a step) it also stores
+ * torque_sum / torque_divisor, the `torque_sum / control_decimal` of …position_control.py:313. */
+int lm_pd_update_and_torque(const float* dof_pos, const float* dof_vel, const int32_t* dof_index_host,
+                            float* joint_pos, float* joint_vel, float* last_joint_vel, const float* targets,
+                            float* torque, float* torque_sum, int32_t accumulate, float* mean_torque,
+                            float torque_divisor, int32_t n, float kp, float kd, float max_effort, void* stream);
 /* Swing/extension target integration of the *_PC variants (…position_control.py:275-287). */
 int lm_pd_integrate_targets(const float* actions, float* targets_se, float* targets,
                             const float* se_lower_host, const float* se_upper_host, int32_t n,

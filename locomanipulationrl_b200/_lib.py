@@ -62,6 +62,11 @@ class LmHostStep(C.Structure):
                 ("obs_host", C.c_void_p), ("rew_host", C.c_void_p), ("reset_host", C.c_void_p)]
 
 
+class LmPdState(C.Structure):
+    _fields_ = [("joint_pos", C.c_void_p), ("joint_vel", C.c_void_p), ("targets", C.c_void_p), ("last_targets", C.c_void_p),
+                ("targets_se", C.c_void_p), ("init_se", C.c_float * NUM_ACT), ("carry_post_state", _i32), ("target_obs_scale", C.c_float)]
+
+
 # name -> (restype, argtypes); every symbol include/lm_b200.h declares
 _vp = C.c_void_p
 SYMBOLS = {
@@ -75,6 +80,9 @@ SYMBOLS = {
     "lm_task_set_clamp_observations": (C.c_int, [_vp, C.c_int]),
     "lm_task_invalidate_reset_scan": (C.c_int, [_vp]),
     "lm_task_set_timeline": (C.c_int, [_vp, _vp]),
+    "lm_task_set_pd_state": (C.c_int, [_vp, C.POINTER(LmPdState)]),
+    "lm_pd_torque": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _f, _f, _f, _vp]),
+    "lm_pd_update_and_torque": (C.c_int, [_vp, _vp, C.POINTER(_i32), _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _f, _i32, _f, _f, _f, _vp]),
     "lm_task_pre_step": (C.c_int, [_vp, C.POINTER(LmRobotViews), C.POINTER(LmRobotViews), _vp, C.POINTER(LmTaskBuffers), _vp, _vp, _vp]),
     "lm_task_reset_idx": (C.c_int, [_vp, C.POINTER(LmRobotViews), C.POINTER(LmRobotViews), _vp, C.POINTER(LmTaskBuffers), _vp, _i32, _vp, _vp]),
     "lm_task_post_step": (C.c_int, [_vp, C.POINTER(LmRobotViews), C.POINTER(LmRobotViews), _vp, C.POINTER(LmTaskBuffers), _vp]),
@@ -121,7 +129,7 @@ def load(path: Optional[str] = None) -> C.CDLL:
         fn.argtypes = args
     if lib.lm_abi_version() != 1:
         raise LmError("liblm_b200.so ABI version mismatch")
-    for which, struct in enumerate((LmTaskParams, LmRobotViews, LmTaskBuffers, LmHostStep)):
+    for which, struct in enumerate((LmTaskParams, LmRobotViews, LmTaskBuffers, LmHostStep, LmPdState)):
         if lib.lm_struct_size(which) != C.sizeof(struct):
             raise LmError(f"struct layout mismatch for {struct.__name__}: C {lib.lm_struct_size(which)} vs ctypes {C.sizeof(struct)}")
     _lib = lib

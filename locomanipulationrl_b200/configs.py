@@ -140,11 +140,17 @@ class TaskConfig:
     pd_max_se: List[float] = field(default_factory=lambda: list(_PC_MAX_SE))
     pd_init_se: List[float] = field(default_factory=lambda: list(_PC_INIT_SE))
 
+    pd_sum_final_torque: bool = True   # single-task files add the torque computed after the last sub-step to torque_sum (:311); JL_PC does not (:399-408)
+    pd_carry_post_state: bool = True   # single-task files re-point joint_positions_* at the post-step state in get_observations (:392-393); JL_PC keeps the last sub-step's
+    pd_target_obs_scale: float = 0.3  # literal ``* 0.3`` on the target rows of the observation (…position_control.py:438-439)
+
     @property
     def time_interval(self) -> float:
-        """Finite-difference Δt for joint acceleration (QPC:156; *_PC: dt*(control_decimal+1), :199)."""
+        """Finite-difference Δt of ``RobotOmni.update_joint_states`` (robot.py:290).  Velocity-target files hand the robot
+        ``dt * controlFrequencyInv`` (QPC:156,189); the *_PC files compute ``_time_inv = dt*(control_decimal+1)`` (:199)
+        but hand the robot the bare ``dt`` (:232), and refresh the joint state after every PD sub-step."""
         if self.control_mode == CONTROL_PD:
-            return self.dt * (self.pd_control_decimal + 1)
+            return self.dt
         return self.dt * self.control_frequency_inv
 
     def with_(self, **kw) -> "TaskConfig":
@@ -202,6 +208,42 @@ def joint_locomanipulation_vertical() -> TaskConfig:
                       **_vertical_limits())
 
 
+def _position_control(**kw) -> Dict[str, object]:
+    """Deltas shared by the three *_position_control.py files: effort mode + explicit PD loop, 64-wide states (alias of obs),
+    success threshold 0.1, the horizontal task pose."""
+    d = dict(vertical=False, control_mode=CONTROL_PD, num_states=64, success_thresh=0.1, control_frequency_inv=1,
+             loco_init_joint_pos=list(_HORIZONTAL_TASK_INIT), mani_init_joint_pos=list(_HORIZONTAL_TASK_INIT))
+    d.update(kw)
+    return d
+
+
+def quadruped_pose_control_position_control() -> TaskConfig:
+    """quadruped_pose_control_position_control.py:20-199; ``actions[:] = 0.0`` live at :261; cfg/task/QuadrupedPoseControlPositionControl.yaml."""
+    return TaskConfig(name="QuadrupedPoseControlPositionControl", kind=KIND_LOCO,
+                      **_position_control(min_roll=-0.5, max_roll=0.5, min_pitch=-0.5, max_pitch=0.5, min_yaw=-3.14, max_yaw=3.14,
+                                          zero_actions=True, dt=0.005, max_episode_length=500,
+                                          pd_control_decimal=4, pd_torque_divisor=4.0))
+
+
+def quadruped_manipulate_plate_position_control() -> TaskConfig:
+    """quadruped_manipulate_plate_position_control.py; ``actions[:] = 0.0`` live at :274; robot at z 0.3, plate at 0.44."""
+    return TaskConfig(name="QuadrupedManipulatePlatePositionControl", kind=KIND_MANI,
+                      **_position_control(min_roll=-0.5, max_roll=0.5, min_pitch=-0.5, max_pitch=0.5, min_yaw=-3.14, max_yaw=3.14,
+                                          zero_actions=True, dt=0.005, max_episode_length=450,
+                                          mani_default_position=[0.0, 0.0, 0.3], obj_default_position=[0.0, 0.0, 0.44],
+                                          indicator_mani_position=[0.0, 0.0, 0.5], pd_control_decimal=4, pd_torque_divisor=4.0))
+
+
+def joint_locomanipulation_position_control() -> TaskConfig:
+    """joint_locomanipulation_position_control.py:20-408: control_decimal 7, torque mean over decimal + 1 (:408), no action zeroing."""
+    return TaskConfig(name="JointLocomanipulationPositionControl", kind=KIND_COTRAIN,
+                      **_position_control(joint_acc_scale=-0.001, action_rate_scale=-0.03, dt=0.00417, max_episode_length=300,
+                                          loco_default_position=[0.0, 0.0, 0.14], mani_default_position=[0.0, 0.0, 0.5],
+                                          obj_default_position=[0.0, 0.0, 0.64], indicator_loco_position=[0.0, 0.0, 0.3],
+                                          indicator_mani_position=[0.0, 0.0, 0.8], pd_control_decimal=7, pd_torque_divisor=8.0,
+                                          pd_sum_final_torque=False, pd_carry_post_state=False))
+
+
 TASK_CONFIGS = {
     "QuadrupedPoseControl": quadruped_pose_control,
     "QuadrupedPoseControlVertical": quadruped_pose_control_vertical,
@@ -209,6 +251,9 @@ TASK_CONFIGS = {
     "QuadrupedManipulatePlateVertical": quadruped_manipulate_plate_vertical,
     "JointLocomanipulation": joint_locomanipulation,
     "JointLocomanipulationVertical": joint_locomanipulation_vertical,
+    "QuadrupedPoseControlPositionControl": quadruped_pose_control_position_control,
+    "QuadrupedManipulatePlatePositionControl": quadruped_manipulate_plate_position_control,
+    "JointLocomanipulationPositionControl": joint_locomanipulation_position_control,
 }
 
 

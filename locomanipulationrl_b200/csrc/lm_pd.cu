@@ -35,6 +35,47 @@ __global__ void __launch_bounds__(256) k_pd_substep(const float* __restrict__ do
   if (torque_sum) reinterpret_cast<float4*>(torque_sum)[i] = make_float4(acc[0], acc[1], acc[2], acc[3]);
 }
 
+// update_joint_states (robot.py:283-291) + torque law on the refreshed state.  One thread per (env, 4 joints).
+__global__ void __launch_bounds__(256) k_pd_update_torque(const float* __restrict__ dof_pos, const float* __restrict__ dof_vel, PdIndex ix,
+                                                          float* __restrict__ joint_pos, float* __restrict__ joint_vel,
+                                                          float* __restrict__ last_joint_vel, const float* __restrict__ targets,
+                                                          float* __restrict__ torque, float* __restrict__ torque_sum,
+                                                          float* __restrict__ mean_torque, float divisor, int n, float kp, float kd,
+                                                          float max_effort, int gather, int accumulate) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * 3) return;
+  const int env = i / 3, j0 = (i - env * 3) * 4;
+  float q[4], qd[4];
+  if (gather) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      q[k] = dof_pos[(size_t)env * LM_NUM_DOF + ix.idx[j0 + k]];
+      qd[k] = dof_vel[(size_t)env * LM_NUM_DOF + ix.idx[j0 + k]];
+    }
+    reinterpret_cast<float4*>(joint_pos)[i] = make_float4(q[0], q[1], q[2], q[3]);
+    reinterpret_cast<float4*>(joint_vel)[i] = make_float4(qd[0], qd[1], qd[2], qd[3]);
+    reinterpret_cast<float4*>(last_joint_vel)[i] = make_float4(qd[0], qd[1], qd[2], qd[3]);     // robot.py:291
+  } else {
+    const float4 a = reinterpret_cast<const float4*>(joint_pos)[i], b = reinterpret_cast<const float4*>(joint_vel)[i];
+    q[0] = a.x; q[1] = a.y; q[2] = a.z; q[3] = a.w; qd[0] = b.x; qd[1] = b.y; qd[2] = b.z; qd[3] = b.w;
+  }
+  const float4 tg = reinterpret_cast<const float4*>(targets)[i];
+  const float4 ts = reinterpret_cast<const float4*>(torque_sum)[i];
+  const float tgt[4] = {tg.x, tg.y, tg.z, tg.w};
+  float out[4], acc[4] = {ts.x, ts.y, ts.z, ts.w};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float tau = sub(mul(kp, sub(tgt[k], q[k])), mul(kd, qd[k]));
+    tau = fminf(fmaxf(tau, -max_effort), max_effort);
+    out[k] = tau;
+    if (accumulate) acc[k] = add(acc[k], tau);
+  }
+  reinterpret_cast<float4*>(torque)[i] = make_float4(out[0], out[1], out[2], out[3]);
+  if (accumulate) reinterpret_cast<float4*>(torque_sum)[i] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+  if (mean_torque)
+    reinterpret_cast<float4*>(mean_torque)[i] = make_float4(fdiv(acc[0], divisor), fdiv(acc[1], divisor), fdiv(acc[2], divisor), fdiv(acc[3], divisor));
+}
+
 // se += action_scale * a; clamp to swing/extension limits; dof1 = se[0:4], dof2 = swing + ext/2,
 // dof3 = swing - ext/2                                                              (…position_control.py:275-287)
 __global__ void __launch_bounds__(128) k_pd_integrate(const float* __restrict__ actions, float* __restrict__ targets_se,
@@ -86,6 +127,38 @@ int lm_pd_substep(const float* dof_pos, const float* dof_vel, const float* targe
   }
   k_pd_substep<<<(n * 3 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(dof_pos, dof_vel, targets, torque, torque_sum, ix, n, kp, kd, max_effort);
   return lm_check_launch("lm_pd_substep");
+}
+
+int lm_pd_torque(const float* joint_pos, const float* joint_vel, const float* targets, float* torque, float* torque_sum, int32_t n,
+                 float kp, float kd, float max_effort, void* stream) {
+  if (!joint_pos || !joint_vel || !targets || !torque || !torque_sum || n <= 0) return lm_fail(LM_ERR_BAD_ARG, "lm_pd_torque: bad argument");
+  if ((((uintptr_t)joint_pos) | ((uintptr_t)joint_vel) | ((uintptr_t)targets) | ((uintptr_t)torque) | ((uintptr_t)torque_sum)) & 15)
+    return lm_fail(LM_ERR_ALIGNMENT, "lm_pd_torque: unaligned");
+  PdIndex ix;
+  for (int j = 0; j < LM_NUM_ACT; ++j) ix.idx[j] = j;
+  k_pd_update_torque<<<(n * 3 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(nullptr, nullptr, ix, const_cast<float*>(joint_pos),
+                                                                          const_cast<float*>(joint_vel), nullptr, targets, torque, torque_sum,
+                                                                          nullptr, 1.0f, n, kp, kd, max_effort, 0, 1);
+  return lm_check_launch("lm_pd_torque");
+}
+
+int lm_pd_update_and_torque(const float* dof_pos, const float* dof_vel, const int32_t* dof_index_host, float* joint_pos, float* joint_vel,
+                            float* last_joint_vel, const float* targets, float* torque, float* torque_sum, int32_t accumulate,
+                            float* mean_torque, float torque_divisor, int32_t n, float kp, float kd, float max_effort, void* stream) {
+  if (!dof_pos || !dof_vel || !joint_pos || !joint_vel || !last_joint_vel || !targets || !torque || !torque_sum || n <= 0)
+    return lm_fail(LM_ERR_BAD_ARG, "lm_pd_update_and_torque: bad argument");
+  if ((((uintptr_t)joint_pos) | ((uintptr_t)joint_vel) | ((uintptr_t)last_joint_vel) | ((uintptr_t)targets) | ((uintptr_t)torque) |
+       ((uintptr_t)torque_sum) | ((uintptr_t)mean_torque)) & 15)
+    return lm_fail(LM_ERR_ALIGNMENT, "lm_pd_update_and_torque: unaligned");
+  if (mean_torque && torque_divisor == 0.0f) return lm_fail(LM_ERR_BAD_ARG, "lm_pd_update_and_torque: zero divisor");
+  PdIndex ix;
+  for (int j = 0; j < LM_NUM_ACT; ++j) {
+    ix.idx[j] = dof_index_host ? dof_index_host[j] : j;
+    if (ix.idx[j] < 0 || ix.idx[j] >= LM_NUM_DOF) return lm_fail(LM_ERR_BAD_ARG, "lm_pd_update_and_torque: dof index out of range");
+  }
+  k_pd_update_torque<<<(n * 3 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(dof_pos, dof_vel, ix, joint_pos, joint_vel, last_joint_vel, targets,
+                                                                          torque, torque_sum, mean_torque, torque_divisor, n, kp, kd, max_effort, 1, accumulate);
+  return lm_check_launch("lm_pd_update_and_torque");
 }
 
 int lm_pd_integrate_targets(const float* actions, float* targets_se, float* targets, const float* se_lower_host,

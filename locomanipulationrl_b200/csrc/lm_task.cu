@@ -140,6 +140,7 @@ struct PreArgs {
   const int32_t* tile_offsets;
   const int32_t* scan_base;
   int parity;                      // actions_ring slot that receives current_actions
+  LmPdState pd;                    // *_position_control variants (joint_pos == NULL otherwise)
 };
 
 __device__ __forceinline__ void store3(float* p, float a, float b, float c) { p[0] = a; p[1] = b; p[2] = c; }
@@ -210,6 +211,21 @@ __device__ __forceinline__ void reset_one_env(const KernelParams& kp, const PreA
     }
     a.buf.reset_buf[e] = 0; a.buf.progress_buf[e] = 0; a.buf.successes[e] = 0;
     a.buf.consecutive_successes[e] = 0; a.buf.goal_reset_buf[e] = 0;
+    if (a.pd.joint_pos != nullptr) {                                                    // …position_control.py:377-386
+      const float* init = is_mani ? P.mani_init_joint_pos : P.loco_init_joint_pos;
+      float4* jq = reinterpret_cast<float4*>(a.pd.joint_pos + (size_t)e * LM_NUM_ACT);
+      float4* jd = reinterpret_cast<float4*>(a.pd.joint_vel + (size_t)e * LM_NUM_ACT);
+      float4* tg = reinterpret_cast<float4*>(a.pd.targets + (size_t)e * LM_NUM_ACT);
+      float4* ltg = reinterpret_cast<float4*>(a.pd.last_targets + (size_t)e * LM_NUM_ACT);
+      float4* se = reinterpret_cast<float4*>(a.pd.targets_se + (size_t)e * LM_NUM_ACT);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const float4 d = make_float4(init[4 * k], init[4 * k + 1], init[4 * k + 2], init[4 * k + 3]);
+        jq[k] = d; tg[k] = d; ltg[k] = d;
+        jd[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        se[k] = make_float4(a.pd.init_se[4 * k], a.pd.init_se[4 * k + 1], a.pd.init_se[4 * k + 2], a.pd.init_se[4 * k + 3]);
+      }
+    }
   }
 }
 
@@ -313,6 +329,11 @@ struct PostArgs {
   int32_t* tile_offsets;           // by-product: exclusive scan of per-tile reset counts for the next pre_step,
   int32_t* scan_base;              //   as scan_base[t / scan_per] + tile_offsets[t]
   int inline_finish;               // the last CTA runs the finish pass (else k_post_finish is launched behind the kernel)
+  const float* pd_targets;         // *_position_control variants: obs[40:64] = scale * targets, scale * last_targets
+  const float* pd_last_targets;    //   (…position_control.py:438-452); NULL otherwise
+  float pd_target_obs_scale;
+  float* pd_joint_pos;             // single-task *_position_control: the observed joint state becomes the PD loop's carried
+  float* pd_joint_vel;             //   state (…position_control.py:392-393); NULL otherwise
   int parity;
   int clamp_observations;          // store clamp(obs, ±clip_observations) (fused _process_data)
   long long* timeline;             // diagnostic: [num_tiles, 8] globaltimer stamps (NULL in production)
@@ -374,9 +395,12 @@ struct LimbOut {                   // limb -> pose
 
 // ---- limb half, part 1 (no frame needed): acceleration / action-rate sums (robot.py:290; QPC:443,446), joint-limit
 //      flags (QPC:466-504 / JLV:574-597) and obs[16:64] (QPC:367-370)
+//      tail_cur / tail_last (global rows, NULL unless a *_position_control task): obs[40:64] = scale * targets,
+//      scale * last_targets instead of the actions (…position_control.py:438-452)
 template <typename Sink>
 __device__ __forceinline__ void limb_joints(const KernelParams& kp, const float jp[12], const float jv[12], const float last_jv[12],
-                                            const float cur[12], const float last[12], const Sink& sink, LimbOut& lo) {
+                                            float cur[12], float last[12], const Sink& sink, LimbOut& lo,
+                                            const float* tail_cur = nullptr, const float* tail_last = nullptr, float tail_scale = 1.0f) {
   const LmTaskParams& P = kp.p;
   float acc_sum = 0.0f, rate_sum = 0.0f;
 #pragma unroll
@@ -401,6 +425,14 @@ __device__ __forceinline__ void limb_joints(const KernelParams& kp, const float 
     rst |= (jp[k] < rlo) | (jp[k] > rhi);
   }
   lo.brk = brk; lo.rst = rst;
+  if (tail_cur != nullptr) {       // the action registers are dead: reuse them for the target rows
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const float4 c = reinterpret_cast<const float4*>(tail_cur)[k], l = reinterpret_cast<const float4*>(tail_last)[k];
+      cur[4 * k] = mul(c.x, tail_scale); cur[4 * k + 1] = mul(c.y, tail_scale); cur[4 * k + 2] = mul(c.z, tail_scale); cur[4 * k + 3] = mul(c.w, tail_scale);
+      last[4 * k] = mul(l.x, tail_scale); last[4 * k + 1] = mul(l.y, tail_scale); last[4 * k + 2] = mul(l.z, tail_scale); last[4 * k + 3] = mul(l.w, tail_scale);
+    }
+  }
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
     sink(4 + k, mul(P.joint_position_scale, jp[4 * k]), mul(P.joint_position_scale, jp[4 * k + 1]),
@@ -561,7 +593,10 @@ template <typename Sink>
 __device__ __forceinline__ void env_math(const KernelParams& kp, const int is_mani, const EnvIn& in, float* tips,
                                          const float* knees, const Sink& sink, EnvOut& out) {
   LimbOut lo;
-  limb_joints(kp, in.jp, in.jv, in.last_jv, in.cur, in.last, sink, lo);
+  float cur[12], last[12];
+#pragma unroll
+  for (int j = 0; j < 12; ++j) { cur[j] = in.cur[j]; last[j] = in.last[j]; }
+  limb_joints(kp, in.jp, in.jv, in.last_jv, cur, last, sink, lo);
   PoseIn pin{in.O, in.Pw, in.lin, in.ang, in.q, in.goal, in.progress, in.reset, in.succ_prev, in.consec};
   FrameShare f;
   const Vec3 pl = pose_frame(pin, f);
@@ -877,6 +912,10 @@ __global__ void __launch_bounds__(T, 4) k_post_lean(const KernelParams kp, const
   }
   ld12(sm + LeanSmem::kTips + rr * 12, tips);
   if (valid) st12(a.buf.last_joint_vel + (size_t)e * 12, jv);                          // robot.py:291
+  if (valid && a.pd_joint_pos != nullptr) {
+    st12(a.pd_joint_pos + (size_t)e * 12, jp);
+    st12(a.pd_joint_vel + (size_t)e * 12, jv);
+  }
   LimbOut lo;
   FrameShare f;
   const Vec3 pl = pose_frame(pin, f);
@@ -888,7 +927,8 @@ __global__ void __launch_bounds__(T, 4) k_post_lean(const KernelParams kp, const
   PoseMid m;
   {
     const ObsToStage sink{sm + obs_stage_row(warp, lane), lane & 15, P.clip_observations, a.clamp_observations};
-    limb_joints(kp, jp, jv, last_jv, cur, last, sink, lo);
+    limb_joints(kp, jp, jv, last_jv, cur, last, sink, lo, a.pd_targets ? a.pd_targets + (size_t)e * 12 : nullptr,
+                a.pd_last_targets ? a.pd_last_targets + (size_t)e * 12 : nullptr, a.pd_target_obs_scale);
     pose_main(kp, tl.is_mani, pin, pl, f, sink, out.cur_q, m);
   }
   pose_finish(kp, pin, m, lo, out);
@@ -1097,6 +1137,8 @@ struct LmTask {
   int32_t* tile_offsets;
   int32_t* scan_base;
   int inline_finish;
+  LmPdState pd;
+  int has_pd;
   float* partials;
   unsigned int* tickets;     // [2]: scan, post
   int clamp_observations;
@@ -1132,6 +1174,7 @@ int lm_struct_size(int which) {
     case 1: return (int)sizeof(LmRobotViews);
     case 2: return (int)sizeof(LmTaskBuffers);
     case 3: return (int)sizeof(LmHostStep);
+    case 4: return (int)sizeof(LmPdState);
     default: return -1;
   }
 }
@@ -1208,6 +1251,19 @@ int lm_task_set_clamp_observations(LmTask* t, int on) { if (!t) return LM_ERR_BA
 
 int lm_task_set_timeline(LmTask* t, long long* stamps_dev) { if (!t) return LM_ERR_BAD_ARG; t->timeline = stamps_dev; return LM_OK; }
 
+int lm_task_set_pd_state(LmTask* t, const LmPdState* pd) {
+  if (!t) return lm_fail(LM_ERR_BAD_ARG, "lm_task_set_pd_state: task is NULL");
+  if (!pd) { memset(&t->pd, 0, sizeof(t->pd)); t->has_pd = 0; return LM_OK; }
+  if (t->kp.p.num_states != LM_NUM_OBS) return lm_fail(LM_ERR_UNSUPPORTED, "PD state needs a task whose states alias obs (num_states 64)");
+  const void* ptrs[5] = {pd->joint_pos, pd->joint_vel, pd->targets, pd->last_targets, pd->targets_se};
+  for (int i = 0; i < 5; ++i) {
+    if (!ptrs[i]) return lm_fail(LM_ERR_BAD_ARG, "lm_task_set_pd_state: NULL tensor");
+    if (((uintptr_t)ptrs[i]) & 15) return lm_fail(LM_ERR_ALIGNMENT, "lm_task_set_pd_state: tensor not 16-byte aligned");
+  }
+  t->pd = *pd; t->has_pd = 1;
+  return LM_OK;
+}
+
 int lm_task_invalidate_reset_scan(LmTask* t) { if (!t) return LM_ERR_BAD_ARG; t->scan_valid = 0; return LM_OK; }
 
 static int check_views(const LmTask* t, const LmRobotViews* loco, const LmRobotViews* mani, const float* env_pos,
@@ -1257,6 +1313,7 @@ int lm_task_pre_step(LmTask* t, const LmRobotViews* loco, const LmRobotViews* ma
   if (mani) a.mani = *mani;
   a.env_pos = env_pos; a.buf = *buf; a.actions = actions; a.uniforms = uniforms;
   a.tile_offsets = t->tile_offsets; a.scan_base = t->scan_base; a.parity = t->parity;
+  if (t->has_pd) a.pd = t->pd;
   k_pre<<<d.num_tiles, T, 0, s>>>(t->kp, a);
   return lm_check_launch("lm_task_pre_step");
 }
@@ -1272,6 +1329,7 @@ int lm_task_reset_idx(LmTask* t, const LmRobotViews* loco, const LmRobotViews* m
   if (loco) a.loco = *loco;
   if (mani) a.mani = *mani;
   a.env_pos = env_pos; a.buf = *buf; a.uniforms = uniforms; a.parity = t->parity ^ 1;   // "last" slot = current one before the next pre_step
+  if (t->has_pd) a.pd = t->pd;
   k_reset_idx<<<(count + 127) / 128, 128, 0, (cudaStream_t)stream>>>(t->kp, a, env_ids, count);
   t->scan_valid = 0;   // reset_buf entries were cleared: the by-product scan of the last post_step is stale
   return lm_check_launch("lm_task_reset_idx");
@@ -1289,6 +1347,10 @@ int lm_task_post_step(LmTask* t, const LmRobotViews* loco, const LmRobotViews* m
   a.env_pos = env_pos; a.buf = *buf; a.partials = t->partials; a.ticket = t->tickets + 1; a.tile_offsets = t->tile_offsets;
   a.parity = t->parity; a.clamp_observations = t->clamp_observations; a.timeline = t->timeline;
   a.scan_base = t->scan_base; a.inline_finish = t->inline_finish;
+  if (t->has_pd) {
+    a.pd_targets = t->pd.targets; a.pd_last_targets = t->pd.last_targets; a.pd_target_obs_scale = t->pd.target_obs_scale;
+    if (t->pd.carry_post_state) { a.pd_joint_pos = t->pd.joint_pos; a.pd_joint_vel = t->pd.joint_vel; }
+  }
   if (t->kp.p.num_states == LM_NUM_STATES_FULL)
     k_post<<<t->kp.d.num_tiles, T, PostSmem::kBytes, (cudaStream_t)stream>>>(t->kp, a);
   else

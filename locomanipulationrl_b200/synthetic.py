@@ -302,5 +302,22 @@ class SyntheticScene:
             out[group] = host.pin_memory() if pin and torch.cuda.is_available() else host
         return out
 
+    def substep_joint_state(self, step: int, i: int) -> Dict[str, Dict[str, torch.Tensor]]:
+        """Joint rows after physics sub-step ``i`` of env step ``step`` (the explicit-PD variants re-read the joint state
+        after every ``SimulationContext.step``, …position_control.py:300-305).  CPU tensors; only dof_pos / dof_vel."""
+        gen = torch.Generator(device="cpu")
+        gen.manual_seed(self.seed + 7919 * (step + 1) + 31 * (i + 1))
+        out = {}
+        if self.loco:
+            jp, jv = _articulation_joints(gen, self.num_scenes, self.cfg.loco_init_joint_pos, self.knobs)
+            out["loco"] = {"dof_pos": jp, "dof_vel": jv}
+        if self.mani:
+            jp, jv = _articulation_joints(gen, self.num_scenes, self.cfg.mani_init_joint_pos, self.knobs)
+            out["mani"] = {"dof_pos": jp, "dof_vel": jv}
+        return out
+
+    def substep(self, step: int, i: int) -> None:
+        self.load(self.substep_joint_state(step, i))
+
     def step(self, step: int, goal_quaternions: Optional[torch.Tensor] = None) -> None:
         self.load(self.generate(step, goal_quaternions))

@@ -92,6 +92,9 @@ class LocoManipulationTask:
         self.targets_loco = torch.zeros((h, tw), device=dev, dtype=f32)
         self.targets_mani = torch.zeros((h, tw), device=dev, dtype=f32)
         ex = self._extras_buf
+        self._pd = None
+        if self.cfg.control_mode == CONTROL_PD:
+            self._setup_pd_state()
         self.extras: Dict[str, torch.Tensor] = {"env/rewards/" + k: ex[i] for i, k in enumerate(_lib.EXTRA_NAMES)}
         self.extras["env/success_rate"] = ex[_lib.EXTRA_SUCCESS_RATE]
         if self.cfg.kind == KIND_COTRAIN:
@@ -107,6 +110,78 @@ class LocoManipulationTask:
         b.goal_quaternions, b.reset_env_ids = self.goal_quaternions.data_ptr(), self.reset_env_ids_buf.data_ptr()
         b.num_reset, b.extras, b.counters = self.num_reset_buf.data_ptr(), self._extras_buf.data_ptr(), self._counters.data_ptr()
         self._buffers = b
+
+    # ------------------------------------------------------------------ *_position_control state
+    def _setup_pd_state(self) -> None:
+        """Buffers of the explicit-PD files (quadruped_pose_control_position_control.py:179-191;
+        joint_locomanipulation_position_control.py:161-183), env-indexed [N,12] with locomotion rows first."""
+        cfg, n, dev, f32 = self.cfg, self._num_envs, self._device, torch.float32
+        init = torch.zeros((n, 12), device=dev, dtype=f32)
+        h = self._single_task_num_envs
+        loco = torch.tensor(cfg.loco_init_joint_pos[:12], device=dev, dtype=f32)
+        mani = torch.tensor(cfg.mani_init_joint_pos[:12], device=dev, dtype=f32)
+        if cfg.kind == KIND_COTRAIN:
+            init[:h], init[h:] = loco, mani
+        else:
+            init[:] = loco if cfg.kind == KIND_LOCO else mani
+        self.joint_positions = init.clone()                       # joint_positions_loco / _mani / _combined
+        self.joint_velocities = torch.zeros((n, 12), device=dev, dtype=f32)
+        self.current_joint_position_targets = init.clone()
+        self.last_joint_position_targets = init.clone()
+        self.current_joint_position_targets_se = torch.tensor(cfg.pd_init_se, device=dev, dtype=f32).repeat(n, 1)
+        self.applied_torque = torch.zeros((n, 12), device=dev, dtype=f32)   # last set_joint_efforts value
+        self._torque_sum = torch.zeros((n, 12), device=dev, dtype=f32)
+        self.torque = torch.zeros((n, 12), device=dev, dtype=f32)           # …position_control.py:313
+        self._se_lower = (C.c_float * 12)(*cfg.pd_min_se)
+        self._se_upper = (C.c_float * 12)(*cfg.pd_max_se)
+        pd = _lib.LmPdState()
+        pd.joint_pos, pd.joint_vel = self.joint_positions.data_ptr(), self.joint_velocities.data_ptr()
+        pd.targets, pd.last_targets = self.current_joint_position_targets.data_ptr(), self.last_joint_position_targets.data_ptr()
+        pd.targets_se = self.current_joint_position_targets_se.data_ptr()
+        for j in range(12):
+            pd.init_se[j] = cfg.pd_init_se[j]
+        pd.target_obs_scale = cfg.pd_target_obs_scale
+        pd.carry_post_state = int(cfg.pd_carry_post_state)
+        _lib.check(self._lib.lm_task_set_pd_state(self._handle, C.byref(pd)), "lm_task_set_pd_state")
+        self._pd = pd
+
+    def _pd_groups(self):
+        """(articulation state dict, first env row, rows) per robot."""
+        h = self._single_task_num_envs
+        out = []
+        if self.cfg.kind != KIND_MANI:
+            out.append((self._scene.loco, 0, h))
+        if self.cfg.kind != KIND_LOCO:
+            out.append((self._scene.mani, h if self.cfg.kind == KIND_COTRAIN else 0, h))
+        return out
+
+    def _pd_loop(self, actions: torch.Tensor, physics_substep) -> None:
+        """…position_control.py:261-313: integrate the swing/extension targets, then control_decimal x (torque, physics
+        sub-step, joint-state refresh) and one final torque.  ``physics_substep(i)`` stands in for
+        ``SimulationContext.step`` (PhysX is out of scope): it must leave the articulation tensors holding the new state."""
+        cfg, lib, s = self.cfg, self._lib, self._stream()
+        n = self._num_envs
+        _lib.check(lib.lm_pd_integrate_targets(actions.data_ptr(), self.current_joint_position_targets_se.data_ptr(),
+                                               self.current_joint_position_targets.data_ptr(), self._se_lower, self._se_upper, n,
+                                               cfg.pd_action_scale, int(cfg.zero_actions), s), "lm_pd_integrate_targets")
+        self._torque_sum.zero_()
+        _lib.check(lib.lm_pd_torque(self.joint_positions.data_ptr(), self.joint_velocities.data_ptr(),
+                                    self.current_joint_position_targets.data_ptr(), self.applied_torque.data_ptr(),
+                                    self._torque_sum.data_ptr(), n, cfg.pd_kp, cfg.pd_kd, cfg.pd_max_effort, s), "lm_pd_torque")
+        for i in range(cfg.pd_control_decimal):
+            if physics_substep is not None:
+                physics_substep(i)
+            last = i == cfg.pd_control_decimal - 1
+            for st, row0, rows in self._pd_groups():
+                sl = slice(row0, row0 + rows)
+                rc = lib.lm_pd_update_and_torque(st["dof_pos"].data_ptr(), st["dof_vel"].data_ptr(), None,
+                                                 self.joint_positions[sl].data_ptr(), self.joint_velocities[sl].data_ptr(),
+                                                 self.last_joint_velocities[sl].data_ptr(), self.current_joint_position_targets[sl].data_ptr(),
+                                                 self.applied_torque[sl].data_ptr(), self._torque_sum[sl].data_ptr(),
+                                                 int(cfg.pd_sum_final_torque) if last else 1,
+                                                 self.torque[sl].data_ptr() if last else None, cfg.pd_torque_divisor, rows,
+                                                 cfg.pd_kp, cfg.pd_kd, cfg.pd_max_effort, s)
+                _lib.check(rc, "lm_pd_update_and_torque")
 
     # ------------------------------------------------------------------ scene / views
     def _views(self, state: Optional[Dict[str, torch.Tensor]], targets: torch.Tensor):
@@ -190,7 +265,7 @@ class LocoManipulationTask:
         front so no host sync on ``num_reset`` is needed; row k is consumed by the k-th reset env."""
         return torch.rand((self._num_envs, 3), device=self._device, generator=self._generator)
 
-    def pre_physics_step(self, actions: torch.Tensor, uniforms: Optional[torch.Tensor] = None) -> None:
+    def pre_physics_step(self, actions: torch.Tensor, uniforms: Optional[torch.Tensor] = None, physics_substep=None) -> None:
         if self._scene is None:
             raise _lib.LmError("set_up_scene(scene) must be called before stepping")
         actions = actions.to(self._device, dtype=torch.float32)
@@ -204,6 +279,8 @@ class LocoManipulationTask:
         rc = self._lib.lm_task_pre_step(self._handle, self._lp(), self._mp(), self._env_pos.data_ptr(), C.byref(self._buffers),
                                         actions.data_ptr(), uniforms.data_ptr(), self._stream())
         _lib.check(rc, "lm_task_pre_step")
+        if self._pd is not None:
+            self._pd_loop(self.current_actions, physics_substep)   # the stashed (adapter-clamped) actions
         self._posted_since_pre = False
         self._keep = (actions, uniforms)   # keep inputs alive until the stream has consumed them
 

@@ -36,18 +36,33 @@ def task_fixture(name):
     task = refshim.make_reference_task(cfg, scene)
     acts, unis = rollout_inputs(TASK_N, TASK_STEPS)
     out = {}
+    pd = cfg.control_mode == configs.CONTROL_PD
     for t in range(TASK_STEPS):
+        if pd:   # the PD loop steps the simulation itself: feed it the seeded sub-step joint states (generated before torch.rand is patched)
+            sub = [scene.substep_joint_state(t, i) for i in range(cfg.pd_control_decimal)]
+            cursor = {"i": 0}
+
+            def hook():
+                scene.load(sub[cursor["i"]])
+                cursor["i"] += 1
+            refshim._SimulationContext.hook = hook
         with refshim.supplied_uniforms(unis[t]), refshim.quiet():
             ids = task.reset_buf.nonzero(as_tuple=False).squeeze(-1).clone()
             task.pre_physics_step(acts[t].clone())
+        refshim._SimulationContext.hook = None
         full = t in FULL_STEPS
+        if pd:
+            out[f"s{t}_torque"] = task.torque.numpy().copy()
+            if full:
+                out[f"s{t}_pd_targets"] = task.current_joint_position_targets.numpy().copy()
+                out[f"s{t}_pd_targets_se"] = task.current_joint_position_targets_se.numpy().copy()
         out[f"s{t}_reset_ids"] = ids.numpy()
         out[f"s{t}_goal"] = task.goal_quaternions.numpy().copy()
         for grp in ("loco", "mani"):
             st = getattr(scene, grp)
             if st and full:
                 art = (task.robot_locomotion if grp == "loco" else task.robot_manipulation)._robot_articulation
-                out[f"s{t}_{grp}_targets"] = art.targets["velocity"][:, :12].numpy().copy()
+                out[f"s{t}_{grp}_targets"] = art.targets["effort" if pd else "velocity"][:, :12].numpy().copy()
                 for k in ("dof_pos", "dof_vel", "indicator_pos", "indicator_quat") + (("root_pos", "root_quat") if grp == "loco" else ("plate_pos", "plate_quat")):
                     out[f"s{t}_{grp}_{k}"] = st[k].numpy().copy()
         scene.step(t, task.goal_quaternions)

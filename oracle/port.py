@@ -6,6 +6,8 @@ One parameterised class restates what the reference spreads over six near-identi
   QMP  quadruped_manipulate_plate.py        pre :213-236  reset :238-309  obs :311-435  metrics :437-567  done :569-652
   JLV  joint_locomanipulation_vertical.py   pre :248-270  reset :272-377  obs :379-521  metrics :523-653  done :655-802
   (+ quadruped_pose_control_vertical.py, quadruped_manipulate_plate_vertical.py, joint_locomanipulation.py: constant deltas)
+  *_PC quadruped_pose_control_position_control.py:251-322,377-386,438-452 and its manipulation / co-train siblings
+       (joint_locomanipulation_position_control.py:341-408): explicit PD loop, target rows in the observation
   robot/base/robot.py:276-321 (state read-back), :444-461 (take_action); objects/base/rigid_object.py:36-58;
   utils/math.py:7-193 (SciPy float64 quaternion<->matrix round trips + float32 bmm);
   tasks/base/rl_task.py:104-113,240-260 (buffers, post_physics_step driver).
@@ -26,7 +28,7 @@ import numpy as np
 import torch
 from scipy.spatial.transform import Rotation
 
-from locomanipulationrl_b200.configs import (CONTROL_EFFORT, CONTROL_POSITION, CONTROL_VELOCITY, DEFAULT_BASE_TIP_POSITIONS,
+from locomanipulationrl_b200.configs import (CONTROL_EFFORT, CONTROL_PD, CONTROL_POSITION, CONTROL_VELOCITY, DEFAULT_BASE_TIP_POSITIONS,
                                              KIND_COTRAIN, KIND_LOCO, KIND_MANI, TaskConfig)
 
 from . import isaac_torch as it
@@ -152,11 +154,29 @@ class TaskPort:
         if self.has_mani:
             self.corners_world = transform_vectors(self.q0, self.p0, self.corners_robot)       # QMP:162-165
         self.time_interval = cfg.time_interval
+        self.pd = cfg.control_mode == CONTROL_PD
+        if self.pd:                                                                     # …position_control.py:179-191
+            init = torch.zeros(n, 12, dtype=f32)
+            li, mi = torch.tensor(cfg.loco_init_joint_pos[:12], dtype=f32), torch.tensor(cfg.mani_init_joint_pos[:12], dtype=f32)
+            if cfg.kind == KIND_COTRAIN:
+                init[:h], init[h:] = li, mi
+            else:
+                init[:] = li if cfg.kind == KIND_LOCO else mi
+            self.default_joint_positions = init
+            self.joint_positions = init.clone()
+            self.joint_velocities = torch.zeros(n, 12, dtype=f32)
+            self.current_joint_position_targets = init.clone()
+            self.last_joint_position_targets = init.clone()
+            self.current_joint_position_targets_se = torch.tensor(cfg.pd_init_se, dtype=f32).repeat(n, 1)
+            self.se_upper = torch.tensor(cfg.pd_max_se, dtype=f32)
+            self.se_lower = torch.tensor(cfg.pd_min_se, dtype=f32)
+            self.torque = torch.zeros(n, 12, dtype=f32)
+            self.applied_torque = torch.zeros(n, 12, dtype=f32)
         self.reset_env_ids = torch.zeros(0, dtype=i64)
         self.inter: Dict[str, torch.Tensor] = {}
 
     # ------------------------------------------------------------------ pre_physics_step  (QPC:200-228, JLV:248-270)
-    def pre_physics_step(self, actions: torch.Tensor, uniforms: torch.Tensor) -> None:
+    def pre_physics_step(self, actions: torch.Tensor, uniforms: torch.Tensor, physics_substep=None) -> None:
         cfg = self.cfg
         self.current_actions = actions.clone()
         ids = self.reset_buf.clone().nonzero(as_tuple=False).squeeze(-1)
@@ -164,11 +184,52 @@ class TaskPort:
         if len(ids) > 0:
             self.reset_idx(ids, uniforms)
         act = torch.zeros_like(actions) if cfg.zero_actions else actions
+        if self.pd:
+            self._pd_loop(act, physics_substep)
+            return
         h = self.half
         if self.has_loco:
             self.targets["loco"] = self._take_action(act[0:h])
         if self.has_mani:
             self.targets["mani"] = self._take_action(act[h:] if cfg.kind == KIND_COTRAIN else act)
+
+    def _pd_state_from_scene(self):
+        """update_joint_states of every robot (robot.py:283-291), concatenated locomotion-first."""
+        jps, jvs = [], []
+        for which in (("loco",) if self.has_loco else ()) + (("mani",) if self.has_mani else ()):
+            jp, jv, _ = self._joint_state(which)
+            jps.append(jp)
+            jvs.append(jv)
+        return torch.cat(jps, dim=0), torch.cat(jvs, dim=0)
+
+    def _pd_torque(self) -> torch.Tensor:
+        cfg = self.cfg
+        torque = cfg.pd_kp * (self.current_joint_position_targets - self.joint_positions) - cfg.pd_kd * self.joint_velocities
+        return torch.clamp(torque, min=-cfg.pd_max_effort, max=cfg.pd_max_effort)
+
+    def _pd_loop(self, act: torch.Tensor, physics_substep) -> None:
+        """quadruped_pose_control_position_control.py:275-313 / joint_locomanipulation_position_control.py:349-408."""
+        cfg = self.cfg
+        delta = act * cfg.pd_action_scale
+        se = self.current_joint_position_targets_se + delta
+        se = torch.clamp(se, min=self.se_lower, max=self.se_upper)
+        self.current_joint_position_targets_se = se
+        swing, ext = se[:, [4, 6, 8, 10]], se[:, [5, 7, 9, 11]]
+        self.current_joint_position_targets[:, 0:4] = se[:, 0:4]
+        self.current_joint_position_targets[:, [4, 6, 8, 10]] = swing + ext / 2.0
+        self.current_joint_position_targets[:, [5, 7, 9, 11]] = swing - ext / 2.0
+        torque_sum = 0.0
+        for i in range(cfg.pd_control_decimal):
+            torque = self._pd_torque()
+            torque_sum += torque
+            if physics_substep is not None:
+                physics_substep(i)                                                       # SimulationContext.step
+            self.joint_positions, self.joint_velocities = self._pd_state_from_scene()
+        torque = self._pd_torque()
+        if cfg.pd_sum_final_torque:                                                      # QPC_PC:311; absent in JL_PC:399-408
+            torque_sum += torque
+        self.applied_torque = torque
+        self.torque = torque_sum / cfg.pd_torque_divisor
 
     def _take_action(self, a: torch.Tensor) -> torch.Tensor:
         """robot.py:444-461."""
@@ -218,6 +279,12 @@ class TaskPort:
             self.goal_quaternions[ids_m_off] = goal_m
             s["indicator_quat"][ids_m] = rotate_orientations(self.q0[ids_m], goal_m)              # QMP:291 (SciPy)
             s["indicator_pos"][ids_m] = self.env_pos[ids_m] + torch.tensor(cfg.indicator_mani_position, dtype=f32).repeat(km, 1)
+        if self.pd:                                                                     # …position_control.py:377-386
+            self.joint_positions[env_ids] = self.default_joint_positions[env_ids]
+            self.joint_velocities[env_ids] = 0.0
+            self.current_joint_position_targets[env_ids] = self.default_joint_positions[env_ids]
+            self.last_joint_position_targets[env_ids] = self.current_joint_position_targets[env_ids].clone()
+            self.current_joint_position_targets_se[env_ids] = torch.tensor(cfg.pd_init_se, dtype=f32).repeat(k, 1)
         self.last_base_tip_positions[env_ids] = self.default_base_tip_positions[env_ids]
         self.last_actions[env_ids] = 0.0
         for buf in (self.reset_buf, self.progress_buf, self.successes, self.consecutive_successes, self.goal_reset_buf):
@@ -300,6 +367,9 @@ class TaskPort:
             s_jp = cfg.joint_position_scale * p["jp"]
             s_jv = cfg.joint_velocity_scale * p["jv"]
             cur_a, last_a = self.current_actions[rows], self.last_actions[rows]
+            if self.pd:                                                               # …position_control.py:438-452
+                cur_a = (self.current_joint_position_targets * cfg.pd_target_obs_scale)[rows]
+                last_a = (self.last_joint_position_targets * cfg.pd_target_obs_scale)[rows]
             obs_rows.append(torch.cat((s_pos, up, diff, s_lin, s_ang, s_jp, s_jv, cur_a, last_a), dim=-1))   # QPC:358-371
             if cfg.num_states == 93:                                                  # QPC:406-423
                 n = p["jp"].shape[0]
@@ -312,6 +382,9 @@ class TaskPort:
             self.states_buf[:] = torch.cat(state_rows, dim=0)
         else:
             self.states_buf = self.obs_buf                                            # JLV:515
+        if self.pd and cfg.pd_carry_post_state:                                       # QPC_PC:392-393
+            self.joint_positions = torch.cat([p["jp"] for p in parts], dim=0)
+            self.joint_velocities = torch.cat([p["jv"] for p in parts], dim=0)
         self.last_base_tip_positions = torch.cat([p["tip_base"] for p in parts], dim=0)   # QPC:426 / JLV:518-521
         cat = lambda k: torch.cat([p[k] for p in parts], dim=0)
         self.inter = {k: cat(k) for k in ("jp", "acc", "pos", "cur_q", "body_height", "corner_z", "knee_z")}

@@ -82,8 +82,21 @@ class CudaRollout:
     def step(self, t, actions, uniforms, check=True):
         p, task = self.port, self.task
         dev = task._device
-        p.pre_physics_step(actions.clone(), uniforms)
-        task.pre_physics_step(actions.to(dev), uniforms.to(dev))
+        pd = self.cfg.control_mode == configs.CONTROL_PD
+        if pd:   # the explicit-PD files step the simulation inside pre_physics_step: same seeded sub-step joint states on both sides
+            sub = [self.scene_cpu.substep_joint_state(t, i) for i in range(self.cfg.pd_control_decimal)]
+            p.pre_physics_step(actions.clone(), uniforms, lambda i: self.scene_cpu.load(sub[i]))
+            task.pre_physics_step(actions.to(dev), uniforms.to(dev), lambda i: self.scene_gpu.load(sub[i]))
+        else:
+            p.pre_physics_step(actions.clone(), uniforms)
+            task.pre_physics_step(actions.to(dev), uniforms.to(dev))
+        if check and pd:
+            self._track("torque", assert_close(f"step {t} mean torque", task.torque, p.torque))
+            self._track("torque", assert_close(f"step {t} applied torque", task.applied_torque, p.applied_torque))
+            self._track("pd_targets", assert_close(f"step {t} pd targets", task.current_joint_position_targets, p.current_joint_position_targets))
+            self._track("pd_targets", assert_close(f"step {t} pd targets_se", task.current_joint_position_targets_se, p.current_joint_position_targets_se))
+            self._track("pd_state", assert_close(f"step {t} pd joint_positions", task.joint_positions, p.joint_positions))
+            self._track("pd_state", assert_close(f"step {t} pd joint_velocities", task.joint_velocities, p.joint_velocities))
         if check:
             ids_ref = p.reset_env_ids
             ids = task.reset_env_ids().cpu()
@@ -99,8 +112,9 @@ class CudaRollout:
                 got_state = getattr(self.scene_gpu, grp)
                 for k, v in ref_state.items():
                     self._track("scene", assert_close(f"step {t} scene.{grp}.{k}", got_state[k], v))
-                tg = task.targets_loco if grp == "loco" else task.targets_mani
-                self._track("targets", assert_close(f"step {t} targets_{grp}", tg, p.targets[grp]))
+                if not pd:
+                    tg = task.targets_loco if grp == "loco" else task.targets_mani
+                    self._track("targets", assert_close(f"step {t} targets_{grp}", tg, p.targets[grp]))
             assert torch.equal(task.reset_buf.cpu(), p.reset_buf), f"step {t}: reset_buf after pre differs"
             assert torch.equal(task.progress_buf.cpu(), p.progress_buf)
         # identical "physics" on both sides, generated from the ORACLE's goals
@@ -141,6 +155,9 @@ class CudaRollout:
         self._track("last_jv", assert_close(f"step {t} last_joint_vel", task.last_joint_velocities,
                                             torch.cat([p.last_joint_velocities[g] for g in ("loco", "mani") if getattr(self.scene_cpu, g)], dim=0)))
         self._track("last_actions", assert_close(f"step {t} last_actions", task.last_actions, p.last_actions, atol=0, rtol=0))
+        if self.cfg.control_mode == configs.CONTROL_PD:
+            self._track("pd_state", assert_close(f"step {t} pd joint_positions (post)", task.joint_positions, p.joint_positions))
+            self._track("pd_state", assert_close(f"step {t} pd last_targets", task.last_joint_position_targets, p.last_joint_position_targets))
         if self.exempt_events == 0:
             for k, v in p.extras.items():
                 self._track("extras", assert_close(f"step {t} extras[{k}]", task.extras[k], v, rtol=2e-5, atol=1e-6))

@@ -24,15 +24,24 @@ def test_task_port_matches_reference_bit_exact(name):
     task = port.TaskPort(cfg, scene)
     acts, unis = rollout_inputs(GOLDEN_N, GOLDEN_STEPS)
     saw_reset_after_first, saw_goal_reset = False, False
+    pd = cfg.control_mode == configs.CONTROL_PD
     for t in range(GOLDEN_STEPS):
-        task.pre_physics_step(acts[t].clone(), unis[t])
+        task.pre_physics_step(acts[t].clone(), unis[t], (lambda i, t=t: scene.substep(t, i)) if pd else None)
         assert np.array_equal(task.reset_env_ids.numpy(), g[f"s{t}_reset_ids"]), f"step {t} reset ids"
         assert np.array_equal(task.goal_quaternions.numpy(), g[f"s{t}_goal"]), f"step {t} goals"
+        if pd:
+            assert np.array_equal(task.torque.numpy(), g[f"s{t}_torque"]), f"step {t} mean torque"
         if t in GOLDEN_FULL_STEPS:
+            if pd:
+                assert np.array_equal(task.current_joint_position_targets.numpy(), g[f"s{t}_pd_targets"])
+                assert np.array_equal(task.current_joint_position_targets_se.numpy(), g[f"s{t}_pd_targets_se"])
             for grp in ("loco", "mani"):
                 st = getattr(scene, grp)
                 if st:
-                    assert np.array_equal(task.targets[grp].numpy(), g[f"s{t}_{grp}_targets"])
+                    h = scene.num_scenes
+                    rows = slice(h, 2 * h) if (grp == "mani" and cfg.kind == configs.KIND_COTRAIN) else slice(0, h)
+                    tg = task.applied_torque[rows] if pd else task.targets[grp]
+                    assert np.array_equal(tg.numpy(), g[f"s{t}_{grp}_targets"])
                     for k in ("dof_pos", "dof_vel", "indicator_pos", "indicator_quat"):
                         assert np.array_equal(st[k].numpy(), g[f"s{t}_{grp}_{k}"]), f"step {t} {grp}.{k}"
         scene.step(t, task.goal_quaternions)

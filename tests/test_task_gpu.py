@@ -22,14 +22,23 @@ def test_cuda_matches_golden_reference_vectors(name):
     scene = synthetic.SyntheticScene(cfg, GOLDEN_N, device="cuda:0", seed=GOLDEN_SEED)
     task = LocoManipulationTask(cfg, GOLDEN_N, scene=scene)
     acts, unis = rollout_inputs(GOLDEN_N, GOLDEN_STEPS)
+    pd = cfg.control_mode == configs.CONTROL_PD
     for t in range(GOLDEN_STEPS):
-        task.pre_physics_step(acts[t].cuda(), unis[t].cuda())
+        task.pre_physics_step(acts[t].cuda(), unis[t].cuda(), (lambda i, t=t: scene.substep(t, i)) if pd else None)
         assert np.array_equal(task.reset_env_ids().cpu().numpy(), g[f"s{t}_reset_ids"]), f"step {t}: reset ids"
         assert_close(f"step {t} goal", task.goal_quaternions, g[f"s{t}_goal"])
+        if pd:
+            assert_close(f"step {t} mean torque", task.torque, g[f"s{t}_torque"])
         if t in GOLDEN_FULL_STEPS:
+            if pd:
+                assert_close(f"step {t} pd targets", task.current_joint_position_targets, g[f"s{t}_pd_targets"])
+                assert_close(f"step {t} pd targets_se", task.current_joint_position_targets_se, g[f"s{t}_pd_targets_se"])
+            h = scene.num_scenes
             for grp, tg in (("loco", task.targets_loco), ("mani", task.targets_mani)):
                 st = getattr(scene, grp)
                 if st:
+                    if pd:
+                        tg = task.applied_torque[h:2 * h] if (grp == "mani" and cfg.kind == configs.KIND_COTRAIN) else task.applied_torque[:h]
                     assert_close(f"step {t} {grp} targets", tg, g[f"s{t}_{grp}_targets"])
                     for k in ("dof_pos", "dof_vel", "indicator_pos", "indicator_quat"):
                         assert_close(f"step {t} {grp}.{k}", st[k], g[f"s{t}_{grp}_{k}"])
@@ -51,7 +60,9 @@ def test_cuda_matches_golden_reference_vectors(name):
 
 @pytest.mark.parametrize("name,n", [("QuadrupedPoseControl", 4096), ("QuadrupedManipulatePlate", 16384),
                                     ("JointLocomanipulationVertical", 8192), ("JointLocomanipulation", 4096),
-                                    ("QuadrupedPoseControlVertical", 1024), ("QuadrupedManipulatePlateVertical", 1024)])
+                                    ("QuadrupedPoseControlVertical", 1024), ("QuadrupedManipulatePlateVertical", 1024),
+                                    ("QuadrupedPoseControlPositionControl", 2048), ("QuadrupedManipulatePlatePositionControl", 2048),
+                                    ("JointLocomanipulationPositionControl", 4096)])
 def test_cuda_matches_oracle_port_rollout(name, n):
     """BASELINE.json configs 1-3 shapes (config 3 at 8192 to keep the CPU oracle quick): 24-step rollouts, TMA tile path."""
     ro = CudaRollout(name, n)
