@@ -7,9 +7,10 @@
 // W1 [h_i ; h_j] is split per endpoint: P_i = W1a h_i + b1, Q_j = W1b h_j, so each node is
 // transformed once instead of once per edge (50 instead of 72 32x32 mat-vecs per layer).
 //
-// Mapping: 4 threads per env, each owning 8 of the 32 hidden channels; 40 envs per CTA.  Node features h
-// and Q live in shared memory (adjacency is compile-time: the in-edge lists below are staged as constants),
-// all weights are staged in shared memory once per CTA in a bank-conflict-free [k/4][j][q] float4 order.
+// Mapping: TPE = 8 threads per env, each owning CH = 4 of the 32 hidden channels; 40 envs (10 warps) per CTA.  Node
+// features h and Q live in shared memory (adjacency is compile-time: the in-edge lists below are staged as
+// constants), all weights are staged in shared memory once per CTA in a bank-conflict-free [k/4][j][q] float4 order.
+// ELU is exp(x) - 1 on the negative side, as ATen's CPU kernel evaluates it.
 #include "lm_common.cuh"
 #include "lm_host.h"
 
@@ -19,12 +20,14 @@ namespace gnn {
 constexpr int H = 32;
 constexpr int NODES = 13;
 constexpr int ENVS = 40;                  // envs per CTA
-constexpr int THREADS = ENVS * 4;
+constexpr int TPE = 8;                    // threads per env
+constexpr int CH = H / TPE;               // hidden channels per thread
+constexpr int THREADS = ENVS * TPE;
 constexpr int HSTRIDE = NODES * H + 4;    // floats per env in the h / Q buffers (+4: rotate banks between envs)
 constexpr int ZSTRIDE = 4 * H + 4;        // up to 4 staged message inputs per env
 constexpr int OBS_STRIDE = 64 + 4;
 
-// packed weights (floats).  Matrices are stored as float4 [k/4][j][q] = W[8q+j][4(k/4) .. +3].
+// packed weights (floats).  Matrices are stored as float4 [k/4][j][q] = W[CH q + j][4(k/4) .. +3].
 constexpr int W_IN1 = 0;                          // [32 x 16]
 constexpr int W_IN2 = W_IN1 + H * 16;             // [32 x 4]
 constexpr int W_L = W_IN2 + H * 4;                // per layer: W1a [32x32], W1b [32x32], W2 [32x32]
@@ -41,22 +44,22 @@ constexpr int SMEM_BYTES = SMEM_FLOATS * 4;
 static_assert(SMEM_BYTES <= 232448, "exceeds 227 KB");
 static_assert(ENVS * OBS_STRIDE <= ENVS * HSTRIDE, "obs staging reuses the Q buffer");
 
-__device__ __forceinline__ float elu(float x) { return x > 0.0f ? x : expm1f(x); }
+__device__ __forceinline__ float elu(float x) { return x > 0.0f ? x : expf(x) - 1.0f; }
 
-// acc[v][j] += sum_k W[8q+j][k] * x_v[k]  for NV input vectors sharing one weight pass
+// acc[v][j] += sum_k W[CH q+j][k] * x_v[k]  for NV input vectors sharing one weight pass
 template <int NV, int K>
-__device__ __forceinline__ void matvec8(const float* __restrict__ wp, int q, const float* const x[NV], float acc[NV][8]) {
+__device__ __forceinline__ void matvec8(const float* __restrict__ wp, int q, const float* const x[NV], float acc[NV][CH]) {
   const float4* w4 = reinterpret_cast<const float4*>(wp);
 #pragma unroll
   for (int kq = 0; kq < K / 4; ++kq) {
-    float4 w[8];
+    float4 w[CH];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) w[j] = w4[(kq * 8 + j) * 4 + q];
+    for (int j = 0; j < CH; ++j) w[j] = w4[(kq * CH + j) * TPE + q];
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
       const float4 xv = *reinterpret_cast<const float4*>(x[v] + 4 * kq);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
+      for (int j = 0; j < CH; ++j) {
         acc[v][j] = fmaf(w[j].x, xv.x, acc[v][j]);
         acc[v][j] = fmaf(w[j].y, xv.y, acc[v][j]);
         acc[v][j] = fmaf(w[j].z, xv.z, acc[v][j]);
@@ -66,28 +69,28 @@ __device__ __forceinline__ void matvec8(const float* __restrict__ wp, int q, con
   }
 }
 
-__device__ __forceinline__ void store8(float* dst, const float v[8]) {
+static_assert(CH == 4, "store8 / load8 move one float4 per thread");
+__device__ __forceinline__ void store8(float* dst, const float v[CH]) {
   reinterpret_cast<float4*>(dst)[0] = make_float4(v[0], v[1], v[2], v[3]);
-  reinterpret_cast<float4*>(dst)[1] = make_float4(v[4], v[5], v[6], v[7]);
 }
-__device__ __forceinline__ void load8(const float* src, float v[8]) {
-  const float4 a = reinterpret_cast<const float4*>(src)[0], b = reinterpret_cast<const float4*>(src)[1];
-  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+__device__ __forceinline__ void load8(const float* src, float v[CH]) {
+  const float4 a = reinterpret_cast<const float4*>(src)[0];
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
 }
 
 // messages into up to two target nodes handled in one W2 pass: z_e = ELU(P_target + Q_source), NV = total in-edges (<= 4)
 template <int NV>
 __device__ __forceinline__ void message_pass(const float* __restrict__ w2, const float* __restrict__ b2, int q, float* zenv,
-                                             const float* Qenv, const float P[][8], const int tgt_of[NV], const int src[NV],
-                                             float out[NV][8]) {
+                                             const float* Qenv, const float P[][CH], const int tgt_of[NV], const int src[NV],
+                                             float out[NV][CH]) {
   // stage z (each thread its 8 channels), then every thread needs all 32 channels -> warp-level sync (4 lanes of an env share a warp)
 #pragma unroll
   for (int v = 0; v < NV; ++v) {
-    float qv[8], z[8];
-    load8(Qenv + src[v] * H + 8 * q, qv);
+    float qv[CH], z[CH];
+    load8(Qenv + src[v] * H + CH * q, qv);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) z[j] = elu(P[tgt_of[v]][j] + qv[j]);
-    store8(zenv + v * H + 8 * q, z);
+    for (int j = 0; j < CH; ++j) z[j] = elu(P[tgt_of[v]][j] + qv[j]);
+    store8(zenv + v * H + CH * q, z);
   }
   __syncwarp();
   const float* x[NV];
@@ -95,13 +98,13 @@ __device__ __forceinline__ void message_pass(const float* __restrict__ w2, const
   for (int v = 0; v < NV; ++v) {
     x[v] = zenv + v * H;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) out[v][j] = b2[8 * q + j];
+    for (int j = 0; j < CH; ++j) out[v][j] = b2[CH * q + j];
   }
   matvec8<NV, H>(w2, q, x, out);
 #pragma unroll
   for (int v = 0; v < NV; ++v)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) out[v][j] = elu(out[v][j]);
+    for (int j = 0; j < CH; ++j) out[v][j] = elu(out[v][j]);
   __syncwarp();   // z may be overwritten by the next pass
 }
 
@@ -120,7 +123,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gnn_forward(const Args a) {
   float* qbuf = hbuf + ENVS * HSTRIDE;
   float* zbuf = qbuf + ENVS * HSTRIDE;
   const int tid = threadIdx.x;
-  const int le = tid >> 2, q = tid & 3;          // local env, channel quarter
+  const int le = tid / TPE, q = tid % TPE;       // local env, channel slice
   const int env0 = blockIdx.x * ENVS;
   const int nenv = min(ENVS, a.n - env0);
 
@@ -143,30 +146,30 @@ __global__ void __launch_bounds__(THREADS, 1) k_gnn_forward(const Args a) {
     // ---- input layers (:97-104,112-126).  Lanes of padding envs (tail CTA) run the same code on their own
     // smem slots so that the warp-level syncs below stay convergent; only the global stores are guarded.
     {
-      float acc[1][8];
+      float acc[1][CH];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[0][j] = W[B_IN1 + 8 * q + j];
+      for (int j = 0; j < CH; ++j) acc[0][j] = W[B_IN1 + CH * q + j];
       const float* x[1] = {obs};
       matvec8<1, 16>(W + W_IN1, q, x, acc);
-      store8(henv + 8 * q, acc[0]);
+      store8(henv + CH * q, acc[0]);
     }
     // joint nodes: feature k of node 1+j is obs[16 + 12 k + pi(j)]
     const float4* w4 = reinterpret_cast<const float4*>(W + W_IN2);
-    float4 w[8];
+    float4 w[CH];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) w[j] = w4[j * 4 + q];
+    for (int j = 0; j < CH; ++j) w[j] = w4[j * TPE + q];
 #pragma unroll
     for (int jn = 0; jn < 12; ++jn) {
       const int pi = jn < 4 ? jn : (jn < 8 ? 4 + 2 * (jn - 4) : 5 + 2 * (jn - 8));
       const float f0 = obs[16 + pi], f1 = obs[28 + pi], f2 = obs[40 + pi], f3 = obs[52 + pi];
-      float y[8];
+      float y[CH];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float s = W[B_IN2 + 8 * q + j];
+      for (int j = 0; j < CH; ++j) {
+        float s = W[B_IN2 + CH * q + j];
         s = fmaf(w[j].x, f0, s); s = fmaf(w[j].y, f1, s); s = fmaf(w[j].z, f2, s); s = fmaf(w[j].w, f3, s);
         y[j] = s;
       }
-      store8(henv + (1 + jn) * H + 8 * q, y);
+      store8(henv + (1 + jn) * H + CH * q, y);
     }
   }
   __syncthreads();   // obs staging (Q buffer) fully consumed by every thread of the CTA before Q is written
@@ -183,62 +186,62 @@ __global__ void __launch_bounds__(THREADS, 1) k_gnn_forward(const Args a) {
       // ---- Q_n = W1b h_n for all 13 nodes (old h)
 #pragma unroll
       for (int g = 0; g < 3; ++g) {
-        float acc[4][8];
+        float acc[4][CH];
         const float* x[4];
 #pragma unroll
         for (int v = 0; v < 4; ++v) {
           x[v] = henv + (4 * g + v) * H;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[v][j] = 0.0f;
+          for (int j = 0; j < CH; ++j) acc[v][j] = 0.0f;
         }
         matvec8<4, H>(w1b, q, x, acc);
 #pragma unroll
-        for (int v = 0; v < 4; ++v) store8(Qenv + (4 * g + v) * H + 8 * q, acc[v]);
+        for (int v = 0; v < 4; ++v) store8(Qenv + (4 * g + v) * H + CH * q, acc[v]);
       }
       {
-        float acc[1][8];
+        float acc[1][CH];
         const float* x[1] = {henv + 12 * H};
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[0][j] = 0.0f;
+        for (int j = 0; j < CH; ++j) acc[0][j] = 0.0f;
         matvec8<1, H>(w1b, q, x, acc);
-        store8(Qenv + 12 * H + 8 * q, acc[0]);
+        store8(Qenv + 12 * H + CH * q, acc[0]);
       }
       // ---- P_i = W1a h_i + b1 for all targets, kept in registers level by level; h' written in place
-      float Pn[NODES][8];
+      float Pn[NODES][CH];
 #pragma unroll
       for (int g = 0; g < 3; ++g) {
         const float* x[4];
-        float acc[4][8];
+        float acc[4][CH];
 #pragma unroll
         for (int v = 0; v < 4; ++v) {
           x[v] = henv + (4 * g + v) * H;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[v][j] = b1[8 * q + j];
+          for (int j = 0; j < CH; ++j) acc[v][j] = b1[CH * q + j];
         }
         matvec8<4, H>(w1a, q, x, acc);
 #pragma unroll
         for (int v = 0; v < 4; ++v)
 #pragma unroll
-          for (int j = 0; j < 8; ++j) Pn[4 * g + v][j] = acc[v][j];
+          for (int j = 0; j < CH; ++j) Pn[4 * g + v][j] = acc[v][j];
       }
       {
         const float* x[1] = {henv + 12 * H};
-        float acc[1][8];
+        float acc[1][CH];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[0][j] = b1[8 * q + j];
+        for (int j = 0; j < CH; ++j) acc[0][j] = b1[CH * q + j];
         matvec8<1, H>(w1a, q, x, acc);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) Pn[12][j] = acc[0][j];
+        for (int j = 0; j < CH; ++j) Pn[12][j] = acc[0][j];
       }
       __syncwarp();   // every lane of the env has read old h and written its Q slice
       // node 0 <- {1,2,3,4}
       {
         const int tg[4] = {0, 0, 0, 0}, src[4] = {1, 2, 3, 4};
-        float out[4][8], m[8];
+        float out[4][CH], m[CH];
         message_pass<4>(w2, b2, q, zenv, Qenv, Pn, tg, src, out);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) m[j] = fmaxf(fmaxf(out[0][j], out[1][j]), fmaxf(out[2][j], out[3][j]));
-        store8(henv + 8 * q, m);
+        for (int j = 0; j < CH; ++j) m[j] = fmaxf(fmaxf(out[0][j], out[1][j]), fmaxf(out[2][j], out[3][j]));
+        store8(henv + CH * q, m);
       }
       // nodes 1..4 <- {0, k+4};  nodes 5..8 <- {k-4, k+4}: two targets (4 edges) per W2 pass
 #pragma unroll
@@ -246,45 +249,47 @@ __global__ void __launch_bounds__(THREADS, 1) k_gnn_forward(const Args a) {
         const int k0 = 1 + 2 * pair, k1 = k0 + 1;
         const int s00 = k0 <= 4 ? 0 : k0 - 4, s10 = k1 <= 4 ? 0 : k1 - 4;
         const int tg[4] = {k0, k0, k1, k1}, src[4] = {s00, k0 + 4, s10, k1 + 4};
-        float out[4][8], m0[8], m1[8];
+        float out[4][CH], m0[CH], m1[CH];
         message_pass<4>(w2, b2, q, zenv, Qenv, Pn, tg, src, out);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { m0[j] = fmaxf(out[0][j], out[1][j]); m1[j] = fmaxf(out[2][j], out[3][j]); }
-        store8(henv + k0 * H + 8 * q, m0);
-        store8(henv + k1 * H + 8 * q, m1);
+        for (int j = 0; j < CH; ++j) { m0[j] = fmaxf(out[0][j], out[1][j]); m1[j] = fmaxf(out[2][j], out[3][j]); }
+        store8(henv + k0 * H + CH * q, m0);
+        store8(henv + k1 * H + CH * q, m1);
       }
       // nodes 9..12 <- {k-4}
       {
         const int tg[4] = {9, 10, 11, 12}, src[4] = {5, 6, 7, 8};
-        float out[4][8];
+        float out[4][CH];
         message_pass<4>(w2, b2, q, zenv, Qenv, Pn, tg, src, out);
 #pragma unroll
-        for (int v = 0; v < 4; ++v) store8(henv + (9 + v) * H + 8 * q, out[v]);
+        for (int v = 0; v < 4; ++v) store8(henv + (9 + v) * H + CH * q, out[v]);
       }
     }
     __syncwarp();
     // ---- heads: action k = Wa . h[1+k] + ba (:215-226); value = Wv . max_n h[n] + bv (:228-241)
     const int env = env0 + le;
 #pragma unroll
-    for (int t = 0; t < 3; ++t) {
-      const int k = q + 4 * t;
-      const float* hv = henv + (1 + k) * H;
-      float s = W[B_HEAD];
+    for (int t = 0; t < (12 + TPE - 1) / TPE; ++t) {
+      const int k = q + TPE * t;
+      if (k < 12) {
+        const float* hv = henv + (1 + k) * H;
+        float s = W[B_HEAD];
 #pragma unroll
-      for (int c = 0; c < H; ++c) s = fmaf(W[W_ACT + c], hv[c], s);
-      if (active) a.mu[(size_t)env * 12 + k] = s;
+        for (int c = 0; c < H; ++c) s = fmaf(W[W_ACT + c], hv[c], s);
+        if (active) a.mu[(size_t)env * 12 + k] = s;
+      }
     }
     float part = 0.0f;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int c = 8 * q + j;
+    for (int j = 0; j < CH; ++j) {
+      const int c = CH * q + j;
       float m = henv[c];
 #pragma unroll
       for (int nidx = 1; nidx < NODES; ++nidx) m = fmaxf(m, henv[nidx * H + c]);
       part = fmaf(W[W_VAL + c], m, part);
     }
-    part += __shfl_xor_sync(0xffffffffu, part, 1);
-    part += __shfl_xor_sync(0xffffffffu, part, 2);
+#pragma unroll
+    for (int off = 1; off < TPE; off <<= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
     if (q == 0 && active) a.value[env] = part + W[B_HEAD + 1];
   }
 }
@@ -294,8 +299,8 @@ __global__ void k_pack_matrix(const float* __restrict__ w, float* __restrict__ d
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= H * K) return;
   const int c = i / K, k = i - c * K;
-  const int q = c >> 3, j = c & 7;
-  dst[(((k >> 2) * 8 + j) * 4 + q) * 4 + (k & 3)] = w[(size_t)c * ld + col0 + k];
+  const int q = c / CH, j = c % CH;
+  dst[(((k >> 2) * CH + j) * TPE + q) * 4 + (k & 3)] = w[(size_t)c * ld + col0 + k];
 }
 __global__ void k_copy(const float* __restrict__ src, float* __restrict__ dst, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
