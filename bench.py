@@ -35,7 +35,8 @@ STATE_SETS = 6            # distinct synthetic state sets rotated through: 6 x ~
 B_TASK = 1036             # algorithmic bytes / env-step, task path
 B_POST = 892              # of which the post_physics_step kernel moves (DESIGN.md "k_post bytes")
 MLP_FLOPS = 116352        # FLOP / env
-HORIZON = 16              # stats / gradient all-reduce cadence (rollout horizon of BASELINE configs[3])
+HORIZON = 16              # GAE rollout length of the gnn_gae workload (BASELINE configs[3]: "16-step rollout")
+HORIZON_MLP = 48          # rl_games horizon_length of the co-train yaml (cfg/train/JointLocomanipulationVerticalPPO.yaml:66)
 
 WORKLOADS = {
     "cotrain64k": dict(task="JointLocomanipulationVertical", envs=ENVS_PER_GPU, policy="mlp",
@@ -45,6 +46,18 @@ WORKLOADS = {
     "gnn_gae": dict(task="JointLocomanipulationVertical", envs=ENVS_PER_GPU, policy="gnn",
                     desc="JointLocomanipulationVertical co-train + GNN policy + GAE over 16-step rollouts, 65,536 envs per GPU"),
 }
+
+
+def measured_traffic(kernel):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed `ncu --set full` capture of this
+    kernel at the bench workload (profiles/traffic.json; a profiler measurement, never taken inside a timed run)."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        with open(path) as f:
+            d = json.load(f).get(kernel)
+        return None if d is None else float(d["dram_read_bytes"]) + float(d["dram_write_bytes"])
+    except (OSError, ValueError, KeyError):
+        return None
 
 
 def measured_peaks():
@@ -157,7 +170,7 @@ def reference_arm(args):
             "config": {"workload": w["desc"], "envs_per_step": envs},
             "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------------- CUDA arm
@@ -270,23 +283,56 @@ def cuda_arm(args):
     torch.cuda.set_device(device)
     pipe = Pipeline(args.workload, device, rank)
     n = pipe.n
-    stats = lmdist.StatReducer(n, device)
-    arena = lmdist.GradArena(pipe.policy.parameters())
+    reducer = lmdist.FusedHorizonReducer(pipe.policy.parameters(), n)
+    horizon = HORIZON_MLP if pipe.w["policy"] == "mlp" else HORIZON
     comm_stream = torch.cuda.Stream(device=device)
 
+    comm_graph = None
+
+    def comm_body():
+        reducer.reduce(pipe.task._extras_buf, pipe.task._counters)
+
     def comm():
-        """Episode-stat reduction + PPO gradient all-reduce, once per rollout horizon, on a side stream."""
-        if world == 1:
+        """Episode-stat reduction + PPO gradient all-reduce, once per rollout horizon, on a side stream (one CUDA-graph
+        replay: the host must not fall behind a 45 us step)."""
+        if world == 1 or os.environ.get("LM_BENCH_NO_COMM"):
+            return
+        if args.comm_stream == "main":
+            # at the rollout boundary, on the launching stream (where the PPO update that consumes the gradients would sit).
+            # On a side stream the collective's CTAs pin SMs while they wait for the peer rank, and the persistent MLP kernel
+            # (one 219 KB CTA per SM) then stalls on exactly those SMs: measured 216 us per event vs ~30 us in-line.
+            if comm_graph is not None:
+                comm_graph.replay()
+            else:
+                comm_body()
             return
         comm_stream.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(comm_stream):
-            stats.reduce(pipe.task._extras_buf, pipe.task._counters)
-            arena.allreduce_mean()
+            if comm_graph is not None:
+                comm_graph.replay()
+            else:
+                comm_body()
+
+    if world > 1:
+        comm(); comm()                       # eager first: NCCL connects lazily at the first collective of each size
+        torch.cuda.synchronize()
+        try:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=comm_stream if args.comm_stream == "side" else None):
+                comm_body()
+            comm_graph = g
+        except Exception as exc:             # capture of NCCL collectives unsupported in this build: stay eager
+            print(f"bench.py: comm graph capture failed ({exc}); using eager collectives", file=sys.stderr)
+            comm_graph = None
+        torch.cuda.synchronize()
 
     if not args.no_graphs:
         pipe.capture()
     for t in range(max(args.warmup, 3)):
         pipe.step(t)
+    for _ in range(2):      # NCCL connects lazily at the first collective of each size: keep that out of the timed region
+        comm()
+    torch.cuda.current_stream().wait_stream(comm_stream)
     torch.cuda.synchronize()
     if world > 1:
         tdist.barrier()
@@ -298,7 +344,7 @@ def cuda_arm(args):
     e0.record()
     for t in range(args.steps):
         pipe.step(t)
-        if (t + 1) % HORIZON == 0:
+        if (t + 1) % horizon == 0:
             comm()
     torch.cuda.current_stream().wait_stream(comm_stream)
     e1.record()
@@ -365,7 +411,9 @@ def cuda_arm(args):
         ach = n * B_POST / (ms_post * 1e-3) / 1e9
         ach_task = n * B_TASK / ((ms_post + ms_pre) * 1e-3) / 1e9
         line_extra["roofline"] = {"kernel": "k_post (post_physics_step)", "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s",
-                                  "frac": ach / hbm, "traffic": None, "peak_source": src, "bytes_per_env": B_POST, "ms": ms_post}
+                                  "frac": ach / hbm, "traffic": measured_traffic("k_post_lean") if pipe.w["task"].startswith("Joint") else None,
+                                  "traffic_unit": "bytes per launch (ncu dram read + write, 65,536 envs; stores mostly still in L2 at kernel end)",
+                                  "algorithmic_bytes": n * B_POST, "peak_source": src, "bytes_per_env": B_POST, "ms": ms_post}
         line_extra["roofline_task"] = {"kernels": "k_reset_count + k_pre + k_post", "bound": "hbm", "achieved": ach_task, "peak": hbm,
                                        "unit": "GB/s", "frac": ach_task / hbm, "bytes_per_env": B_TASK, "ms": ms_post + ms_pre}
         if pipe.w["policy"] == "mlp":
@@ -386,7 +434,7 @@ def cuda_arm(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         w = WORKLOADS[args.workload]
-        cpu_steps = 12 if w["policy"] == "mlp" else 6
+        cpu_steps = 96 if w["policy"] == "mlp" else 48     # ~12 s (MLP workload) / ~3 s of CPU work on a 16-core host
         cpu_envs = w["envs"] if w["policy"] == "mlp" else 8192
         v, per_step, cores = run_cpu_port(args.workload, cpu_steps, 2, cpu_envs)
         cpu = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
@@ -399,10 +447,10 @@ def cuda_arm(args):
                 "data": "synthetic",
                 "config": {"workload": pipe.w["desc"], "envs_per_gpu": n, "global_envs": n * world, "parallelism": f"env-shard x{world}",
                            "l2": f"{STATE_SETS} rotating synthetic state sets (> L2) - inputs larger than L2",
-                           "cuda_graphs": pipe.graphs is not None, "comm": f"stat + grad all-reduce every {HORIZON} steps" if world > 1 else "none"},
+                           "cuda_graphs": pipe.graphs is not None, "comm": f"one fused stat + gradient all-reduce (58,651 fp32) every {horizon} steps ({args.comm_stream} stream, CUDA graph)" if world > 1 else "none"},
                 "gpu_launches": pipe.launches_per_step * args.steps, "clocks": clocks, "e2e": e2e, "cpu_baseline": cpu}
         line.update(line_extra)
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         tdist.barrier()
         tdist.destroy_process_group()
@@ -476,7 +524,24 @@ def e2e_arm(pipe, args, world, device, rank=0):
                    "host sync every step"}
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    """The contract is ONE JSON line on stdout: libraries (NCCL's version banner) also write there, so everything but this
+    line is diverted to stderr (see main)."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)                              # fd 1 -> stderr for everything except emit()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=192)
@@ -486,6 +551,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graphs", action="store_true", help="launch eagerly (for ncu captures)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--comm-stream", default="main", choices=["main", "side"],
+                    help="where the per-horizon stat + gradient all-reduce runs (N > 1)")
     ap.add_argument("--e2e-shards", type=int, default=2, help="env shards (streams) the host-buffer step is pipelined over")
     ap.add_argument("--no-large", action="store_true", help="skip the 524,288-env k_post roofline line")
     args = ap.parse_args()

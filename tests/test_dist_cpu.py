@@ -6,7 +6,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from locomanipulationrl_b200.dist import EnvSharding, GradArena, StatReducer
+from locomanipulationrl_b200.dist import EnvSharding, FusedHorizonReducer, GradArena, StatReducer
 
 
 def test_sharding_permutation_covers_reference_order():
@@ -48,6 +48,16 @@ def _worker(rank, world, port, q):
     arena.allreduce_mean()
     ok &= torch.allclose(arena.flat, torch.full_like(arena.flat, 1.5))
     ok &= all(torch.allclose(p.grad, torch.full_like(p.grad, 1.5)) for p in net.parameters())
+    # fused rollout-boundary reduction: gradients + stats in one all-reduce
+    net2 = torch.nn.Linear(5, 2)
+    fr = FusedHorizonReducer(net2.parameters(), n_local)
+    for p in net2.parameters():
+        p.grad.fill_(float(2 * rank + 1))
+    fr.reduce(extras, counters)
+    out2 = fr.result()
+    ok &= torch.allclose(fr.arena.flat, torch.full_like(fr.arena.flat, 2.0))            # mean of 1 and 3
+    ok &= torch.allclose(out2["reward_means"], out["reward_means"], rtol=1e-6) and torch.equal(out2["counters"], out["counters"])
+    ok &= int(out2["num_envs"]) == int(out["num_envs"])
     dist.barrier()
     dist.destroy_process_group()
     q.put((rank, bool(ok)))
