@@ -452,8 +452,13 @@ def cuda_arm(args):
         line.update(line_extra)
         emit(line)
     if world > 1:
+        # The captured NCCL graph keeps communicator resources alive and destroy_process_group() then blocks (observed: the
+        # process sat in teardown until an outer timeout).  Everything is flushed and every rank has passed the barrier:
+        # leave without the teardown.
+        torch.cuda.synchronize()
         tdist.barrier()
-        tdist.destroy_process_group()
+        sys.stdout.flush(); sys.stderr.flush()
+        os._exit(0)
 
 
 def large_roofline(device, graph_time, hbm, n=524288):
