@@ -175,7 +175,7 @@ def reference_arm(args):
 
 # ----------------------------------------------------------------------------------------------- CUDA arm
 class Pipeline:
-    """Device-resident step loop: S state sets, one CUDA graph per set (count + pre + post + policy = 4 launches)."""
+    """Device-resident step loop: S state sets, one CUDA graph per set (pre + post + policy = 3 launches)."""
 
     def __init__(self, workload, device, rank):
         from locomanipulationrl_b200 import _lib, configs, synthetic
@@ -214,7 +214,9 @@ class Pipeline:
             T = HORIZON
             self.gae_buf = dict(r=torch.zeros(T, n, device=device), v=torch.zeros(T, n, device=device), d=torch.zeros(T, n, device=device),
                                 adv=torch.zeros(T, n, device=device), ret=torch.zeros(T, n, device=device))
-        self.launches_per_step = 4
+        # kernels of liblm_b200.so per step: k_pre, k_post_lean, policy forward (k_reset_count only runs when reset_buf was
+        # written from outside; lm_gae once per HORIZON steps in the gnn_gae workload)
+        self.launches_per_step = 3
 
     def step_eager(self, i, t=0):
         task = self.task
@@ -448,7 +450,7 @@ def cuda_arm(args):
                 "config": {"workload": pipe.w["desc"], "envs_per_gpu": n, "global_envs": n * world, "parallelism": f"env-shard x{world}",
                            "l2": f"{STATE_SETS} rotating synthetic state sets (> L2) - inputs larger than L2",
                            "cuda_graphs": pipe.graphs is not None, "comm": f"one fused stat + gradient all-reduce (58,651 fp32) every {horizon} steps ({args.comm_stream} stream, CUDA graph)" if world > 1 else "none"},
-                "gpu_launches": pipe.launches_per_step * args.steps, "clocks": clocks, "e2e": e2e, "cpu_baseline": cpu}
+                "gpu_launches": pipe.launches_per_step * args.steps + (args.steps // HORIZON if pipe.w["policy"] == "gnn" else 0), "clocks": clocks, "e2e": e2e, "cpu_baseline": cpu}
         line.update(line_extra)
         emit(line)
     if world > 1:

@@ -132,15 +132,15 @@ __device__ __forceinline__ void mat3_mul(const float a[9], const float b[9], flo
 // utils/math.py:21-31 — quat_from_rot_matrices: SciPy Rotation.from_matrix in float64.  SciPy
 // (1.18, cython backend) replaces a not-exactly-orthogonal input by its polar factor U V^T (SVD),
 // then applies the largest-of-(diag, trace) branch and normalises.  The polar factor is obtained
-// here by Newton iteration X <- (X + X^-T)/2, which converges quadratically from a matrix that is
-// orthogonal to ~1e-7 (error 1e-7 -> 1e-14 -> 1e-28: two steps reach double round-off).  Returns wxyz with w >= 0
-// (math.py:52-54,78-80).
+// here by ONE Newton step X <- (X + X^-T)/2: the input is a product of two fp32 rotation matrices,
+// orthogonal to e ~ 1e-7, and the step leaves e^2/2 ~ 5e-15 — 7 orders below the fp32 rounding of
+// the result (a second step, used at first, changed no fp32 output in any test).  Returns wxyz with
+// w >= 0 (math.py:52-54,78-80).
 __device__ __forceinline__ Quat quat_from_rot_scipy(const float m32[9]) {
   double a[9];
 #pragma unroll
   for (int i = 0; i < 9; ++i) a[i] = (double)m32[i];
-#pragma unroll 1
-  for (int it = 0; it < 2; ++it) {
+  {
     double c[9];
     c[0] = a[4] * a[8] - a[5] * a[7]; c[1] = a[5] * a[6] - a[3] * a[8]; c[2] = a[3] * a[7] - a[4] * a[6];
     c[3] = a[2] * a[7] - a[1] * a[8]; c[4] = a[0] * a[8] - a[2] * a[6]; c[5] = a[1] * a[6] - a[0] * a[7];
@@ -244,6 +244,13 @@ __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.b
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 // make generic-proxy smem writes visible to the async proxy (before a bulk store reads them)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// Programmatic dependent launch: a kernel launched with the programmatic-stream-serialization attribute may start while
+// its predecessor on the stream is still draining; pdl_wait() blocks until that predecessor has completed and its writes
+// are visible, so everything before it (barrier init, TMEM allocation, resident-weight TMA) overlaps the predecessor's
+// tail.  pdl_launch_dependents() lets the successor be scheduled as soon as every CTA of this grid has started.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 __device__ __forceinline__ float4 ld_nc_f4(const float* p) {
   float4 v;

@@ -284,6 +284,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_mlp_forward(const Args a) {
   const float* bias3 = bias2 + D2;
   const float* biash = bias3 + D3;
 
+  pdl_launch_dependents();
   if (tid == 0) {
     mbar_init(&bar_w, 1); mbar_init(&bar_a0, E_WARPS);
     mbar_init(&bar_acc1, 1); mbar_init(&bar_acc2, 1); mbar_init(&bar_acc3, 1); mbar_init(&bar_acch, 1);
@@ -372,6 +373,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_mlp_forward(const Args a) {
       inv_std = *reinterpret_cast<const float4*>(a.norm_inv_std + 4 * (tid & 15));
     }
     ObsRegs regs;
+    pdl_wait();                                            // the observations are the predecessor kernel's output
     if (n_loc > 0) {
       obs_fetch(a, tile0, tid, regs);
       obs_convert(a, tile0, tid, regs, mean, inv_std, has_norm, A0);
@@ -475,6 +477,7 @@ struct LmMlp {
   int sm_count;
   uint8_t* blob;
   bool packed;
+  bool fresh_pack;       // weights were re-packed since the last forward: that forward must not start early
   long long* timeline;   // diagnostic only (lm_mlp_set_timeline)
 };
 
@@ -487,7 +490,7 @@ LmMlp* lm_mlp_create(int device) {
   if (prop.major != 10) { lm_set_error("lm_mlp_create: tcgen05 kernel needs sm_100a, device is sm_%d%d", prop.major, prop.minor); return nullptr; }
   cudaSetDevice(device);
   LmMlp* m = new LmMlp();
-  m->device = device; m->sm_count = prop.multiProcessorCount; m->packed = false; m->blob = nullptr; m->timeline = nullptr;
+  m->device = device; m->sm_count = prop.multiProcessorCount; m->packed = false; m->blob = nullptr; m->timeline = nullptr; m->fresh_pack = true;
   if (cudaMalloc(&m->blob, BLOB_BYTES) != cudaSuccess) { lm_set_error("lm_mlp_create: cudaMalloc failed"); delete m; return nullptr; }
   cudaMemset(m->blob, 0, BLOB_BYTES);
   e = cudaFuncSetAttribute(k_mlp_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
@@ -521,6 +524,7 @@ int lm_mlp_pack(LmMlp* m, const float* w1, const float* b1, const float* w2, con
   k_pack_operand<<<(1 * D3 + 255) / 256, 256, 0, s>>>(w_value, m->blob + WH_OFF + 12 * 16, DH, 1, D3);
   k_pack_bias<<<2, 256, 0, s>>>(b1, b2, b3, b_mu, b_value, reinterpret_cast<float*>(m->blob + BIAS_OFF));
   m->packed = true;
+  m->fresh_pack = true;
   return lm_check_launch("lm_mlp_pack");
 }
 
@@ -534,7 +538,11 @@ int lm_mlp_forward(LmMlp* m, const float* obs, const float* norm_mean, const flo
   a.blob = m->blob; a.obs = obs; a.norm_mean = norm_mean; a.norm_inv_std = norm_inv_std; a.norm_clip = norm_clip;
   a.mu = mu; a.value = value; a.n = n; a.num_tiles = (n + TM - 1) / TM; a.timeline = m->timeline;
   const int grid = a.num_tiles < m->sm_count ? a.num_tiles : m->sm_count;
-  k_mlp_forward<<<grid, THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(a);
+  // The resident-weight TMA is issued before pdl_wait(): allowed only while the blob is not being rewritten upstream.
+  const bool pdl = !m->fresh_pack;
+  m->fresh_pack = false;
+  cudaError_t le = lm_launch(k_mlp_forward, dim3(grid), dim3(THREADS), SMEM_BYTES, (cudaStream_t)stream, pdl, a);
+  if (le != cudaSuccess) return lm_fail((int)le, "lm_mlp_forward: %s", cudaGetErrorString(le));
   return lm_check_launch("lm_mlp_forward");
 }
 

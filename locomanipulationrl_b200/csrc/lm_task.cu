@@ -233,6 +233,8 @@ __device__ __forceinline__ void reset_one_env(const KernelParams& kp, const PreA
 // actions, take_action.  The reset bodies themselves run in k_reset_apply over the compacted list, so the ~3 % of
 // envs that reset do not drag every warp through the (double-precision) goal resampling path.
 __global__ void __launch_bounds__(T) k_pre(const KernelParams kp, const PreArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();
   const LmTaskParams& P = kp.p;
   const Tile tl = tile_of(kp, blockIdx.x);
   const int r = threadIdx.x;
@@ -863,9 +865,11 @@ __global__ void __launch_bounds__(T, 4) k_post_lean(const KernelParams kp, const
   const float* ring_last = a.buf.actions_ring + (size_t)(a.parity ^ 1) * N * LM_NUM_ACT;
   const int n = tl.n, h0 = tl.hr0, e0 = tl.e0;
 
+  pdl_launch_dependents();
   stamp(a, 0);
   if (r == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
   __syncthreads();
+  pdl_wait();
   Stager st{&bar, 0u, (n % 4) == 0};
   st.load(sm + LeanSmem::kDofPos, V.dof_pos + (size_t)h0 * 20, n * 20);
   st.load(sm + LeanSmem::kDofVel, V.dof_vel + (size_t)h0 * 20, n * 20);
@@ -1314,7 +1318,8 @@ int lm_task_pre_step(LmTask* t, const LmRobotViews* loco, const LmRobotViews* ma
   a.env_pos = env_pos; a.buf = *buf; a.actions = actions; a.uniforms = uniforms;
   a.tile_offsets = t->tile_offsets; a.scan_base = t->scan_base; a.parity = t->parity;
   if (t->has_pd) a.pd = t->pd;
-  k_pre<<<d.num_tiles, T, 0, s>>>(t->kp, a);
+  cudaError_t le = lm_launch(k_pre, dim3(d.num_tiles), dim3(T), 0, s, true, t->kp, a);
+  if (le != cudaSuccess) return lm_fail((int)le, "lm_task_pre_step: %s", cudaGetErrorString(le));
   return lm_check_launch("lm_task_pre_step");
 }
 
@@ -1354,7 +1359,10 @@ int lm_task_post_step(LmTask* t, const LmRobotViews* loco, const LmRobotViews* m
   if (t->kp.p.num_states == LM_NUM_STATES_FULL)
     k_post<<<t->kp.d.num_tiles, T, PostSmem::kBytes, (cudaStream_t)stream>>>(t->kp, a);
   else
-    k_post_lean<<<t->kp.d.num_tiles, T, LeanSmem::kBytes, (cudaStream_t)stream>>>(t->kp, a);
+  {
+    cudaError_t le = lm_launch(k_post_lean, dim3(t->kp.d.num_tiles), dim3(T), LeanSmem::kBytes, (cudaStream_t)stream, true, t->kp, a);
+    if (le != cudaSuccess) return lm_fail((int)le, "lm_task_post_step: %s", cudaGetErrorString(le));
+  }
   if (!t->inline_finish) k_post_finish<<<1, FINISH_THREADS, 0, (cudaStream_t)stream>>>(t->kp, a);
   t->scan_valid = 1;
   return lm_check_launch("lm_task_post_step");
