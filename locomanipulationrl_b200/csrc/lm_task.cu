@@ -244,9 +244,64 @@ __global__ void __launch_bounds__(T) k_pre(const KernelParams kp, const PreArgs 
 
   __shared__ int warp_base[T / 32];
   __shared__ int list[T];
-  int flag = 0;
   const int e = tl.e0 + r, hr = tl.hr0 + r;
-  if (r < tl.n) flag = a.buf.reset_buf[e] != 0;
+  // ---- every independent load first: the reset flag, this tile's rank base and the thread's three action chunks are all
+  //      in flight before anything waits (the reset bodies below are a long dependent chain on a few lanes)
+  long long flag64 = 0;
+  if (r < tl.n) flag64 = a.buf.reset_buf[e];
+  const int tile_base = a.scan_base[blockIdx.x / kp.d.scan_per] + a.tile_offsets[blockIdx.x];
+  const int nflat4 = tl.n * (LM_NUM_ACT / 4);
+  const float* act_g = a.actions + (size_t)tl.e0 * LM_NUM_ACT;
+  float4 av[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const int i = r + k * T;
+    av[k] = i < nflat4 ? ld_nc_f4(act_g + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+
+  // ---- actions: clamp (vec_env_rlgames.py:60), stash as current_actions, take_action (robot.py:444-461)
+  {
+    float* cur_g = ring_cur + (size_t)tl.e0 * LM_NUM_ACT;
+    const float range = sub(P.action_limit, -P.action_limit);
+    const float offset = mul(add(-P.action_limit, P.action_limit), 0.5f);
+    const bool write_targets = (P.control_mode == LM_CONTROL_VELOCITY || P.control_mode == LM_CONTROL_POSITION) && V.targets;
+    float* tgt_g = write_targets ? V.targets + (size_t)tl.hr0 * LM_NUM_ACT : nullptr;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int i = r + k * T;
+      if (i >= nflat4) continue;
+      float4 v = av[k];
+      if (P.clamp_actions) {
+        v.x = fminf(fmaxf(v.x, -P.clip_actions), P.clip_actions); v.y = fminf(fmaxf(v.y, -P.clip_actions), P.clip_actions);
+        v.z = fminf(fmaxf(v.z, -P.clip_actions), P.clip_actions); v.w = fminf(fmaxf(v.w, -P.clip_actions), P.clip_actions);
+      }
+      reinterpret_cast<float4*>(cur_g)[i] = v;
+      if (write_targets) {
+        if (P.zero_actions) v = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 t;
+        t.x = add(mul(mul(v.x, range), 0.5f), offset); t.y = add(mul(mul(v.y, range), 0.5f), offset);
+        t.z = add(mul(mul(v.z, range), 0.5f), offset); t.w = add(mul(mul(v.w, range), 0.5f), offset);
+        reinterpret_cast<float4*>(tgt_g)[i] = t;
+      }
+    }
+    if (P.control_mode == LM_CONTROL_EFFORT && V.targets && r < tl.n) {                // robot.py:455-459
+      float* eff = V.targets + (size_t)hr * LM_NUM_DOF;
+      const float* avp = a.actions + (size_t)e * LM_NUM_ACT;
+#pragma unroll
+      for (int j = 0; j < LM_NUM_DOF; ++j) eff[j] = 0.0f;
+#pragma unroll
+      for (int j = 0; j < LM_NUM_ACT; ++j) {
+        float v = avp[j];
+        if (P.clamp_actions) v = fminf(fmaxf(v, -P.clip_actions), P.clip_actions);
+        if (P.zero_actions) v = 0.0f;
+        eff[P.dof_index[j]] = add(mul(mul(v, range), 0.5f), offset);
+      }
+    }
+  }
+
+  // ---- reset mask -> rank -> compacted ascending id list (the `nonzero()` of QPC:206); the reset bodies run on the first
+  //      lanes only, so the ~3 % of envs that reset do not drag every warp through the (double-precision) goal resampling
+  const int flag = flag64 != 0;
   unsigned b = __ballot_sync(0xffffffffu, flag);
   if ((r & 31) == 0) warp_base[r >> 5] = __popc(b);
   __syncthreads();
@@ -256,52 +311,17 @@ __global__ void __launch_bounds__(T) k_pre(const KernelParams kp, const PreArgs 
     if (w < (r >> 5)) local_rank += warp_base[w];
     count += warp_base[w];
   }
-  if (flag) list[local_rank] = r;          // tile-local compaction: the reset bodies run on the first lanes only
+  if (count == 0) return;
+  if (flag) list[local_rank] = r;
   __syncthreads();
-  if (count > 0) {
-    // two lanes per reset env: role 0 = goal + indicator pose (the double-precision chain), role 1 = defaults + history
-    const int tile_base = a.scan_base[blockIdx.x / kp.d.scan_per] + a.tile_offsets[blockIdx.x];
+  {
+    // two lanes per reset env: role 0 = goal + indicator pose (the double-precision chain), role 1 = defaults + history.
+    // Lanes are dealt round-robin over the four warps so that the chains of one tile run side by side.
     float* ring_last = a.buf.actions_ring + (size_t)(a.parity ^ 1) * N * LM_NUM_ACT;
-    for (int idx = r; idx < 2 * count; idx += T) {
+    const int slot = ((r & 31) << 2) | (r >> 5);      // lane-major order: slot 0..3 sit in four different warps
+    for (int idx = slot; idx < 2 * count; idx += T) {
       const int lr = list[idx >> 1];
       reset_one_env(kp, a, V, ring_last, tl.is_mani, tl.e0 + lr, tl.hr0 + lr, tile_base + (idx >> 1), idx & 1);
-    }
-  }
-
-  // ---- actions: clamp (vec_env_rlgames.py:60), stash as current_actions, take_action (robot.py:444-461)
-  const int nflat = tl.n * LM_NUM_ACT;
-  const float* act_g = a.actions + (size_t)tl.e0 * LM_NUM_ACT;
-  float* cur_g = ring_cur + (size_t)tl.e0 * LM_NUM_ACT;
-  const float range = sub(P.action_limit, -P.action_limit);
-  const float offset = mul(add(-P.action_limit, P.action_limit), 0.5f);
-  const bool write_targets = (P.control_mode == LM_CONTROL_VELOCITY || P.control_mode == LM_CONTROL_POSITION) && V.targets;
-  float* tgt_g = write_targets ? V.targets + (size_t)tl.hr0 * LM_NUM_ACT : nullptr;
-  for (int i = r; i < nflat / 4; i += T) {
-    float4 v = ld_nc_f4(act_g + 4 * i);
-    if (P.clamp_actions) {
-      v.x = fminf(fmaxf(v.x, -P.clip_actions), P.clip_actions); v.y = fminf(fmaxf(v.y, -P.clip_actions), P.clip_actions);
-      v.z = fminf(fmaxf(v.z, -P.clip_actions), P.clip_actions); v.w = fminf(fmaxf(v.w, -P.clip_actions), P.clip_actions);
-    }
-    reinterpret_cast<float4*>(cur_g)[i] = v;
-    if (write_targets) {
-      if (P.zero_actions) v = make_float4(0.f, 0.f, 0.f, 0.f);
-      float4 t;
-      t.x = add(mul(mul(v.x, range), 0.5f), offset); t.y = add(mul(mul(v.y, range), 0.5f), offset);
-      t.z = add(mul(mul(v.z, range), 0.5f), offset); t.w = add(mul(mul(v.w, range), 0.5f), offset);
-      reinterpret_cast<float4*>(tgt_g)[i] = t;
-    }
-  }
-  if (P.control_mode == LM_CONTROL_EFFORT && V.targets && r < tl.n) {                // robot.py:455-459
-    float* eff = V.targets + (size_t)hr * LM_NUM_DOF;
-    const float* av = a.actions + (size_t)e * LM_NUM_ACT;
-#pragma unroll
-    for (int j = 0; j < LM_NUM_DOF; ++j) eff[j] = 0.0f;
-#pragma unroll
-    for (int j = 0; j < LM_NUM_ACT; ++j) {
-      float v = av[j];
-      if (P.clamp_actions) v = fminf(fmaxf(v, -P.clip_actions), P.clip_actions);
-      if (P.zero_actions) v = 0.0f;
-      eff[P.dof_index[j]] = add(mul(mul(v, range), 0.5f), offset);
     }
   }
 }
