@@ -19,24 +19,17 @@
 
 #include "lm_common.cuh"
 #include "lm_host.h"
+#include "lm_tc.cuh"
 
 namespace lm {
 namespace mlp {
+using namespace tc;
 
 constexpr int TM = 128;                 // rows (envs) per tile == UMMA M
 constexpr int E_WARPS = 16;               // epilogue warps: 4 TMEM lane groups x 4 column quarters
 constexpr int E_THREADS = E_WARPS * 32;
 constexpr int THREADS = E_THREADS + 32;   // + the control warp (MMA issue, weight TMA)
 constexpr int D0 = 64, D1 = 256, D2 = 128, D3 = 64, DH = 16;   // head: 12 mean + 1 value + 3 pad
-
-// UMMA canonical K-major, no swizzle: core matrix = 8 rows x 16 B, rows 16 B apart; core matrices
-// 128 B apart along M/N (SBO); K chunks (8 bf16) `lbo` bytes apart.  lbo = rows*16 + 16: the extra
-// 16 B rotates banks so writing 8 chunks of one row is conflict free.
-__host__ __device__ constexpr int lbo_bytes(int rows) { return rows * 16 + 16; }
-__host__ __device__ constexpr int operand_bytes(int rows, int k) { return (k / 8) * lbo_bytes(rows); }
-__host__ __device__ constexpr int elem_offset(int rows, int row, int k) {   // byte offset of element (row, k)
-  return (k / 8) * lbo_bytes(rows) + row * 16 + (k % 8) * 2;
-}
 
 // packed parameter blob (global, produced by lm_mlp_pack; mirrored 1:1 in shared memory)
 constexpr int W1_OFF = 0;
@@ -59,74 +52,6 @@ static_assert(SMEM_BYTES <= 232448, "exceeds 227 KB");
 static_assert(RING_OFF % 16 == 0 && CHUNK_BYTES % 16 == 0, "align");
 // TMEM accumulator columns
 constexpr uint32_t ACC1_COL = 0, ACC2_COL = 256, ACC3_COL = 384, ACCH_COL = 448, TMEM_COLS = 512;
-
-// ---------------------------------------------------------------- tcgen05 wrappers
-__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, int lbo) {
-  // SmemDescriptor (cute/arch/mma_sm100_desc.hpp): start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout NONE
-  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)((128 >> 4) & 0x3FFF) << 32) |
-         (1ull << 46);
-}
-__host__ __device__ constexpr uint32_t instr_desc(int m, int n) {
-  // InstrDescriptor: c_format F32 (1) [4,6), a/b format BF16 (1) [7,10)/[10,13), K-major both, n>>3 [17,23), m>>4 [24,29)
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t cols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
-}
-// 32 lanes x 16 / 32 consecutive fp32 columns: thread i of the warp receives row (lane base + i).  The loads are
-// asynchronous; tmem_wait() must precede the first use of the registers.
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t r[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t r[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,"
-      "%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-__device__ __forceinline__ float ex2_approx(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-// nn.ELU(alpha=1) = max(x, min(exp(x) - 1, 0)): exp(x) - 1 >= x everywhere, and it is > 0 exactly when x > 0
-__device__ __forceinline__ float elu(float x) {
-  return fmaxf(x, fminf(ex2_approx(x * 1.4426950408889634f) - 1.0f, 0.0f));
-}
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
-  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&h);
-}
 
 // four K/16 MMAs of one layer (single thread): k-steps [ks0, ks0 + 4) of the B operand; the A operand's K chunk starts at
 // `a_saddr` (k-step 0 there)
