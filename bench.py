@@ -200,7 +200,7 @@ class Pipeline:
         if self.w["policy"] == "mlp":
             self.policy = MlpActorCritic(device=device)
         else:
-            self.policy = GnnActorCritic(device=device)
+            self.policy = GnnActorCritic(device=device, precision=os.environ.get("LM_GNN_PRECISION", "bf16"))
         self.policy.pack()
         g = torch.Generator(device=device).manual_seed(7 + rank)
         self.uniforms = [torch.rand(n, 3, device=device, generator=g) for _ in range(STATE_SETS)]
@@ -423,8 +423,15 @@ def cuda_arm(args):
             line_extra["roofline_policy"] = {"kernel": "k_mlp_forward (tcgen05)", "bound": "tensor", "achieved": tfl, "peak": tf, "unit": "TFLOP/s",
                                              "frac": tfl / tf, "ms": ms_pol, "hbm_gbs": n * 308 / (ms_pol * 1e-3) / 1e9}
         else:
-            line_extra["roofline_policy"] = {"kernel": "k_gnn_forward", "bound": "fp32", "achieved": n * 447296 / (ms_pol * 1e-3) / 1e12,
-                                             "unit": "TFLOP/s (naive FLOP count)", "ms": ms_pol}
+            tc = pipe.policy.precision == "bf16"
+            # issued tensor-core FLOP: 24 edges x (K = 64 then K = 32, N = 32) x 3 layers (the input layers and heads are fp32 CUDA-core work)
+            gnn_flops = 24 * 2 * (64 * 32 + 32 * 32) * 3 if tc else 447296
+            tfl = n * gnn_flops / (ms_pol * 1e-3) / 1e12
+            line_extra["roofline_policy"] = {"kernel": "k_gnn_forward_tc (tcgen05, bf16)" if tc else "k_gnn_forward (fp32 CUDA cores)",
+                                             "bound": "epilogue (TMEM->RF 64 B/clk/SM, MUFU ex2)" if tc else "fp32", "achieved": tfl,
+                                             "peak": tf if tc else None, "frac": tfl / tf if tc else None,
+                                             "unit": "TFLOP/s" if tc else "TFLOP/s (naive FLOP count)", "ms": ms_pol,
+                                             "hbm_gbs": n * 308 / (ms_pol * 1e-3) / 1e9}
         line_extra["kernel_ms"] = {"pre": ms_pre, "post": ms_post, "policy": ms_pol}
         if world == 1 and not args.no_large:
             line_extra["roofline_large"] = large_roofline(device, graph_time, hbm)

@@ -254,6 +254,11 @@ LmGnn* lm_gnn_create(int device);
 void lm_gnn_destroy(LmGnn* gnn);
 int lm_gnn_pack(LmGnn* gnn, const float* const* weights, int32_t num_tensors, void* stream);
 int lm_gnn_forward(LmGnn* gnn, const float* obs, float* mu, float* value, int32_t n, void* stream);
+/* The same forward on tcgen05 tensor cores: bf16 operands (weights and node features), fp32 accumulation, fp32 input
+ * layers and heads; logits within 1e-2 of lm_gnn_forward (north_star tolerance for bf16 policy logits). */
+int lm_gnn_forward_bf16(LmGnn* gnn, const float* obs, float* mu, float* value, int32_t n, void* stream);
+/* Diagnostic, as lm_mlp_set_timeline: clock64() stamps of CTA 0 of every following lm_gnn_forward_bf16 (>= 512 int64). */
+int lm_gnn_set_timeline(LmGnn* gnn, long long* stamps_dev);
 
 /* PPO generalised advantage estimation over a time-major [T,N] rollout.
  * LM_GAE_RLGAMES: rl_games 1.6.0 A2CBase.discount_values (next-step done mask; last step uses

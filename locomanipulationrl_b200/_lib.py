@@ -98,6 +98,8 @@ SYMBOLS = {
     "lm_gnn_destroy": (None, [_vp]),
     "lm_gnn_pack": (C.c_int, [_vp, C.POINTER(_vp), _i32, _vp]),
     "lm_gnn_forward": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _vp]),
+    "lm_gnn_forward_bf16": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _vp]),
+    "lm_gnn_set_timeline": (C.c_int, [_vp, _vp]),
     "lm_gae": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _f, _f, _i32, _vp]),
     "lm_gae_env_major": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _f, _f, _i32, _vp]),
     "lm_task_step_host": (C.c_int, [_vp, C.POINTER(LmRobotViews), C.POINTER(LmRobotViews), _vp, C.POINTER(LmTaskBuffers), C.POINTER(LmHostStep), _vp]),

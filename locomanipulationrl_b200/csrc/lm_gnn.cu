@@ -12,6 +12,7 @@
 // constants), all weights are staged in shared memory once per CTA in a bank-conflict-free [k/4][j][q] float4 order.
 // ELU is exp(x) - 1 on the negative side, as ATen's CPU kernel evaluates it.
 #include "lm_common.cuh"
+#include "lm_gnn.h"
 #include "lm_host.h"
 
 namespace lm {
@@ -313,12 +314,6 @@ __global__ void k_copy(const float* __restrict__ src, float* __restrict__ dst, i
 using namespace lm;
 using namespace lm::gnn;
 
-struct LmGnn {
-  int device;
-  float* packed;
-  bool ready;
-};
-
 extern "C" {
 
 LmGnn* lm_gnn_create(int device) {
@@ -328,17 +323,19 @@ LmGnn* lm_gnn_create(int device) {
   if (prop.major != 10) { lm_set_error("lm_gnn_create: library is sm_100a only (device sm_%d%d)", prop.major, prop.minor); return nullptr; }
   cudaSetDevice(device);
   LmGnn* g = new LmGnn();
-  g->device = device; g->ready = false; g->packed = nullptr;
+  g->device = device; g->sm_count = prop.multiProcessorCount; g->ready = false; g->packed = nullptr; g->tc_blob = nullptr; g->timeline = nullptr;
   if (cudaMalloc(&g->packed, PACKED_FLOATS * sizeof(float)) != cudaSuccess) { lm_set_error("lm_gnn_create: cudaMalloc failed"); delete g; return nullptr; }
   cudaMemset(g->packed, 0, PACKED_FLOATS * sizeof(float));
   e = cudaFuncSetAttribute(k_gnn_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   if (e != cudaSuccess) { lm_set_error("lm_gnn_create: smem attribute: %s", cudaGetErrorString(e)); cudaFree(g->packed); delete g; return nullptr; }
+  if (lm_gnn_tc_init(g) != LM_OK) { cudaFree(g->packed); delete g; return nullptr; }
   return g;
 }
 
 void lm_gnn_destroy(LmGnn* g) {
   if (!g) return;
   cudaFree(g->packed);
+  lm_gnn_tc_release(g);
   delete g;
 }
 
@@ -365,6 +362,8 @@ int lm_gnn_pack(LmGnn* g, const float* const* w, int32_t num_tensors, void* stre
   k_copy<<<1, 32, 0, s>>>(w[17], P + B_HEAD, 1);
   k_copy<<<1, 32, 0, s>>>(w[18], P + W_VAL, H);
   k_copy<<<1, 32, 0, s>>>(w[19], P + B_HEAD + 1, 1);
+  const int rc = lm_gnn_tc_pack(g, w, stream);          // the same tensors as bf16 tensor-core operands (lm_gnn_forward_bf16)
+  if (rc != LM_OK) return rc;
   g->ready = true;
   return lm_check_launch("lm_gnn_pack");
 }

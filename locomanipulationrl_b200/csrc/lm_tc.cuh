@@ -91,6 +91,22 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// packed fp32x2 arithmetic (sm_100: FADD2 / FMUL2 — one issue slot for two lanes' worth of work)
+__device__ __forceinline__ uint64_t pk2(float lo, float hi) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ uint64_t pk2u(uint32_t lo, uint32_t hi) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi)); return r; }
+__device__ __forceinline__ void upk2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) { uint64_t r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) { uint64_t r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+
+// two accumulator columns -> +bias, ELU -> packed bf16x2.  ELU(x) = max(x, min(exp(x) - 1, 0)).
+__device__ __forceinline__ uint32_t elu_pair(uint32_t acc_lo, uint32_t acc_hi, float b_lo, float b_hi) {
+  const uint64_t x2 = add2(pk2u(acc_lo, acc_hi), pk2(b_lo, b_hi));
+  float t0, t1, x0, x1, r0, r1;
+  upk2(mul2(x2, pk2(1.4426950408889634f, 1.4426950408889634f)), t0, t1);
+  upk2(add2(pk2(ex2_approx(t0), ex2_approx(t1)), pk2(-1.0f, -1.0f)), r0, r1);
+  upk2(x2, x0, x1);
+  return pack_bf16(fmaxf(x0, fminf(r0, 0.0f)), fmaxf(x1, fminf(r1, 0.0f)));
+}
 
 }  // namespace tc
 }  // namespace lm

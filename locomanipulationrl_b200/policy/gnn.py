@@ -1,4 +1,6 @@
-"""GNN limb-graph actor-critic with the forward pass on the fused fp32 kernel (csrc/lm_gnn.cu).
+"""GNN limb-graph actor-critic with the forward pass on the fused kernels: bf16 tcgen05 tensor cores
+(csrc/lm_gnn_tc.cu, ``precision="bf16"``, the default: logits within 1e-2 of fp32) or fp32 CUDA cores
+(csrc/lm_gnn.cu, ``precision="fp32"``: within 1e-5 of the reference).
 
 Module / parameter names follow the reference (scripts/graph_model_orebot_ov.py:82-241 and the ``Shared``
 wrapper at scripts/skrl_ppo_locomanipulation.py:44-49) so its checkpoints load unchanged.
@@ -40,8 +42,11 @@ class _Head(nn.Module):
 
 
 class GnnActorCritic(nn.Module):
-    def __init__(self, num_actions: int = 12, device="cuda:0"):
+    def __init__(self, num_actions: int = 12, device="cuda:0", precision: str = "bf16"):
         super().__init__()
+        if precision not in ("bf16", "fp32"):
+            raise ValueError(f"precision must be 'bf16' or 'fp32', got {precision!r}")
+        self.precision = precision
         self.net = _GraphNet()
         self.mean_layer = _Head(HIDDEN)
         self.log_std_parameter = nn.Parameter(torch.zeros(num_actions))
@@ -96,7 +101,8 @@ class GnnActorCritic(nn.Module):
         else:
             mu, value = out
         stream = torch.cuda.current_stream(self._device).cuda_stream
-        _lib.check(self._lib.lm_gnn_forward(self._handle, obs.data_ptr(), mu.data_ptr(), value.data_ptr(), n, stream), "lm_gnn_forward")
+        fn = self._lib.lm_gnn_forward_bf16 if self.precision == "bf16" else self._lib.lm_gnn_forward
+        _lib.check(fn(self._handle, obs.data_ptr(), mu.data_ptr(), value.data_ptr(), n, stream), "lm_gnn_forward")
         return mu, value, self.log_std_parameter
 
     def __del__(self):

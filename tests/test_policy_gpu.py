@@ -59,11 +59,11 @@ def test_mlp_normalisation_and_repack():
     assert_close("mu after update", mu2, mu_ref + 1.0, rtol=0, atol=1e-2)
 
 
-def _gnn_from_golden():
+def _gnn_from_golden(precision="fp32"):
     from locomanipulationrl_b200.policy.gnn import GnnActorCritic
     g = np.load(os.path.join(GOLDEN_DIR, "gnn_reference.npz"))
     sd = {k[2:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("p/")}
-    m = GnnActorCritic(device="cuda:0")
+    m = GnnActorCritic(device="cuda:0", precision=precision)
     missing = m.load_state_dict(sd, strict=False)
     assert not missing.unexpected_keys and set(missing.missing_keys) <= {"log_std_parameter"}
     return m, g, sd
@@ -84,6 +84,43 @@ def test_gnn_matches_port(n):
     mu_ref, value_ref = port_policy.gnn_forward(sd, obs)
     assert_close("gnn mu", mu, mu_ref, rtol=1e-5, atol=2e-6)
     assert_close("gnn value", value, value_ref, rtol=1e-5, atol=2e-6)
+
+
+def test_gnn_bf16_matches_reference_golden():
+    """tcgen05 path vs the reference GraphNet's own outputs: bf16 policy logits within 1e-2 (north_star)."""
+    m, g, _ = _gnn_from_golden("bf16")
+    mu, value, _ = m(torch.from_numpy(g["obs"]).cuda())
+    assert_close("gnn bf16 mu vs reference", mu, g["mu"], rtol=0, atol=1e-2)
+    assert_close("gnn bf16 value vs reference", value, g["value"], rtol=0, atol=1e-2)
+
+
+@pytest.mark.parametrize("n", [1, 127, 128, 129, 8192, 65536 + 37])
+def test_gnn_bf16_matches_port(n):
+    if n % 2:
+        m, _, sd = _gnn_from_golden("bf16")
+    else:                                                  # fresh nn.Linear initialisation, scaled up: larger activations
+        from locomanipulationrl_b200.policy.gnn import GnnActorCritic
+        torch.manual_seed(n)
+        m = GnnActorCritic(device="cuda:0", precision="bf16")
+        with torch.no_grad():
+            for prm in m.parameters():
+                prm.mul_(1.25)
+        sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    obs = torch.randn(n, 64, generator=torch.Generator().manual_seed(n)) * 1.5
+    mu, value, _ = m(obs.cuda())
+    mu_ref, value_ref = port_policy.gnn_forward(sd, obs)
+    e1 = assert_close("gnn bf16 mu", mu, mu_ref, rtol=0, atol=1e-2)
+    e2 = assert_close("gnn bf16 value", value, value_ref, rtol=0, atol=1e-2)
+    print(f"n={n} max |mu err| {e1:.2e}, |value err| {e2:.2e}")
+    # against an emulation that rounds weights and node features to bf16 exactly where the kernel does: tight agreement
+    mu_e, value_e = port_policy.gnn_forward(sd, obs, emulate_bf16=True)
+    assert_close("gnn mu vs bf16 emulation", mu, mu_e, rtol=0, atol=2e-3)
+    assert_close("gnn value vs bf16 emulation", value, value_e, rtol=0, atol=2e-3)
+    # fp32 and bf16 kernels share one handle / one pack
+    m.precision = "fp32"
+    mu32, value32, _ = m(obs.cuda())
+    assert_close("gnn fp32 (same handle) mu", mu32, mu_ref, rtol=1e-5, atol=2e-6)
+    assert_close("gnn fp32 (same handle) value", value32, value_ref, rtol=1e-5, atol=2e-6)
 
 
 @pytest.mark.parametrize("T,N", [(16, 65536), (48, 8192), (5, 333), (1, 7)])
