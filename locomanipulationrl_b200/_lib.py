@@ -107,7 +107,8 @@ SYMBOLS = {
     "lm_stream_synchronize": (C.c_int, [_vp]),
 }
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "liblm_b200.so")
+# LM_B200_LIB: load another build of the same library (kernel experiments); there is still no fallback
+LIB_PATH = os.environ.get("LM_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "liblm_b200.so")
 _lib: Optional[C.CDLL] = None
 
 

@@ -43,6 +43,16 @@ def source_files() -> List[str]:
     return srcs
 
 
+def build_variant(out_path: str, defines: List[str]) -> str:
+    """Experiment builds (-D switches of the kernels' diagnostics) next to the product library; never stamped."""
+    cmd = [_nvcc()] + NVCC_FLAGS + [f"-D{d}" for d in defines] + ["-o", out_path] + source_files()
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("nvcc failed building " + out_path)
+    return out_path
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     srcs = source_files()
     deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]

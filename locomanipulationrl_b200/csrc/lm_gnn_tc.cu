@@ -78,12 +78,26 @@ struct Args {
 __device__ __forceinline__ void stamp(const Args& a, int k) {
   if (a.timeline != nullptr && blockIdx.x == 0) a.timeline[k] = clock64();
 }
+#ifdef LM_EXP_NO_LDTM   // timing experiment only (wrong results): is the epilogue TMEM-read-bound?
+__device__ __forceinline__ void ld8(uint32_t taddr, uint32_t r[8]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r[i] = taddr * (i + 1);
+}
+#else
+__device__ __forceinline__ void ld8(uint32_t taddr, uint32_t r[8]) { tmem_ld8(taddr, r); }
+#endif
 __device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, %0;" ::"n"(E_THREADS) : "memory"); }
 
 // ---------------------------------------------------------------- control thread: MMA issue
 // one K = 32 product (two K/16 steps) accumulated into `acc`
+#ifndef LM_EXP_MMA_M   // timing experiments only (wrong results): what does one small-N MMA cost, and what does it scale with?
+#define LM_EXP_MMA_M TM
+#endif
+#ifndef LM_EXP_MMA_N
+#define LM_EXP_MMA_N H
+#endif
 __device__ __forceinline__ void mma_k32(uint32_t acc, uint32_t a_saddr, uint32_t b_saddr, uint32_t accumulate) {
-  constexpr uint32_t idesc = instr_desc(TM, H);
+  constexpr uint32_t idesc = instr_desc(LM_EXP_MMA_M, LM_EXP_MMA_N);
   umma_bf16(acc, smem_desc(a_saddr, lbo_bytes(TM)), smem_desc(b_saddr, lbo_bytes(H)), idesc, accumulate);
   umma_bf16(acc, smem_desc(a_saddr + 2 * lbo_bytes(TM), lbo_bytes(TM)), smem_desc(b_saddr + 2 * lbo_bytes(H), lbo_bytes(H)), idesc, 1u);
 }
@@ -96,6 +110,20 @@ __device__ __forceinline__ void issue_stage1(uint32_t tmem_set, uint32_t sH, uin
     mma_k32(tmem_set + e * H, sH + tgt[e] * OPB, sW1a, 0u);
     mma_k32(tmem_set + e * H, sH + src[e] * OPB, sW1b, 1u);
   }
+}
+// leg 1 of the NEXT layer, issued while the current layer is still in E2(leg 4): everything that does not read h[0]
+// (h'[1], h'[5], h'[9] were written by E2(leg 1)); e0 and e5 get their node-0 halves from issue_stage1_leg1_late.
+__device__ __forceinline__ void issue_stage1_leg1_early(uint32_t tmem_set, uint32_t sH, uint32_t sW1a, uint32_t sW1b) {
+  mma_k32(tmem_set + 0 * H, sH + 1 * OPB, sW1a, 0u);                                                  // e0 (1 <- 0): target half
+  mma_k32(tmem_set + 1 * H, sH + 1 * OPB, sW1a, 0u); mma_k32(tmem_set + 1 * H, sH + 5 * OPB, sW1b, 1u);   // e1 (1 <- 5)
+  mma_k32(tmem_set + 2 * H, sH + 5 * OPB, sW1a, 0u); mma_k32(tmem_set + 2 * H, sH + 1 * OPB, sW1b, 1u);   // e2 (5 <- 1)
+  mma_k32(tmem_set + 3 * H, sH + 5 * OPB, sW1a, 0u); mma_k32(tmem_set + 3 * H, sH + 9 * OPB, sW1b, 1u);   // e3 (5 <- 9)
+  mma_k32(tmem_set + 4 * H, sH + 9 * OPB, sW1a, 0u); mma_k32(tmem_set + 4 * H, sH + 5 * OPB, sW1b, 1u);   // e4 (9 <- 5)
+  mma_k32(tmem_set + 5 * H, sH + 1 * OPB, sW1b, 0u);                                                  // e5 (0 <- 1): source half
+}
+__device__ __forceinline__ void issue_stage1_leg1_late(uint32_t tmem_set, uint32_t sH, uint32_t sW1a, uint32_t sW1b) {
+  mma_k32(tmem_set + 0 * H, sH, sW1b, 1u);
+  mma_k32(tmem_set + 5 * H, sH, sW1a, 1u);
 }
 __device__ __forceinline__ void issue_stage2(uint32_t tmem_set, uint32_t sZset, uint32_t sW2) {
 #pragma unroll
@@ -129,10 +157,10 @@ __device__ __forceinline__ void elu8(const uint32_t r[8], const float b[8], floa
 __device__ __forceinline__ void epilogue_stage1(uint32_t taddr, const float b1[8], uint8_t* zdst /* + q*lbo + row*16 applied */) {
   uint32_t r[LEG][8];
 #pragma unroll
-  for (int e = 0; e < 3; ++e) tmem_ld8(taddr + e * H, r[e]);
+  for (int e = 0; e < 3; ++e) ld8(taddr + e * H, r[e]);
   tmem_wait();
 #pragma unroll
-  for (int e = 3; e < LEG; ++e) tmem_ld8(taddr + e * H, r[e]);
+  for (int e = 3; e < LEG; ++e) ld8(taddr + e * H, r[e]);
 #pragma unroll
   for (int e = 0; e < 3; ++e) *reinterpret_cast<uint4*>(zdst + e * OPB) = elu_chunk(r[e], b1);
   tmem_wait();
@@ -151,7 +179,7 @@ __device__ __forceinline__ void epilogue_stage2(uint32_t taddr, const float b2[8
                                                 uint32_t m0[8], const float* __restrict__ wact_sm, HeadAcc& head) {
   uint32_t r[LEG][8];
 #pragma unroll
-  for (int e = 0; e < LEG; ++e) tmem_ld8(taddr + e * H, r[e]);
+  for (int e = 0; e < LEG; ++e) ld8(taddr + e * H, r[e]);
   tmem_wait();
   max8(r[0], r[1]);          // node k    <- {0, k+4}
   max8(r[2], r[3]);          // node k+4  <- {k, k+8}
@@ -180,6 +208,18 @@ __device__ __forceinline__ void epilogue_stage2(uint32_t taddr, const float b2[8
       head.act[kLeg - 1 + 4 * t] = s;
     }
   }
+}
+
+// coalesced 128-bit loads: thread owns float4 j*512 + tid of the [128 x 64] fp32 tile (row j*32 + tid/16, columns 4 (tid%16) ..)
+__device__ __forceinline__ void obs_fetch(const Args& a, int row0, int rows, int tid, float4 v[4]) {
+  const float* base = a.obs + (size_t)row0 * 64;
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    v[j] = (j * 32 + (tid >> 4)) < rows ? ld_nc_f4(base + (size_t)(j * E_THREADS + tid) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+}
+__device__ __forceinline__ void obs_stage(float* stage, int tid, const float4 v[4]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) *reinterpret_cast<float4*>(stage + (j * 32 + (tid >> 4)) * OBS_STRIDE + 4 * (tid & 15)) = v[j];
 }
 
 // per-thread view of the epilogue side of the pipeline
@@ -263,13 +303,15 @@ __global__ void __launch_bounds__(THREADS, 1) k_gnn_forward_tc(const Args a) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
+  // (Dealing rows in 32-row groups so that the last round is a half tile was measured and dropped: a tile whose upper lane
+  // groups are idle takes as long as a full one - the epilogue is bound by each warp's own dependent chain, not by throughput.)
   const int tile0 = blockIdx.x, stride = gridDim.x;
   const int n_loc = tile0 < a.num_tiles ? (a.num_tiles - tile0 + stride - 1) / stride : 0;
   if (tid == 0) stamp(a, 0);
 
   if (warp == E_WARPS) {
     // ================================================================== control warp
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_expect_tx(&bar_w, BLOB_BYTES);
       tma_load_1d(smem, a.blob, BLOB_BYTES, &bar_w);          // resident weights: one bulk copy per CTA
       mbar_wait(&bar_w, 0);
@@ -282,7 +324,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_gnn_forward_tc(const Args a) {
           const uint32_t sW1a = sW + (3 * layer) * WB, sW1b = sW1a + WB, sW2 = sW1b + WB;
           mbar_wait(&bar_h, ph_h); ph_h ^= 1;
           tc_fence_after();
-          issue_stage1(set0, sH, sW1a, sW1b, 1); umma_commit(&bar_s1[0]);
+          long long* tl = (a.timeline != nullptr && blockIdx.x == 0 && it < 7 && layer == 0) ? a.timeline + 8 + 64 * it : nullptr;
+          if (tl) tl[6] = clock64();
+          if (layer == 0) issue_stage1(set0, sH, sW1a, sW1b, 1);
+          else issue_stage1_leg1_late(set0, sH, sW1a, sW1b);
+          if (tl) tl[7] = clock64();
+          umma_commit(&bar_s1[0]);
           issue_stage1(set1, sH, sW1a, sW1b, 2); umma_commit(&bar_s1[1]);
           mbar_wait(&bar_z[0], 0); tc_fence_after(); issue_stage2(set0, sZ, sW2); umma_commit(&bar_s2[0]);
           mbar_wait(&bar_z[1], 0); tc_fence_after(); issue_stage2(set1, sZ + LEG * OPB, sW2); umma_commit(&bar_s2[1]);
@@ -290,6 +337,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_gnn_forward_tc(const Args a) {
           mbar_wait(&bar_e2[1], 0); tc_fence_after(); issue_stage1(set1, sH, sW1a, sW1b, 4); umma_commit(&bar_s1[1]);
           mbar_wait(&bar_z[0], 1); tc_fence_after(); issue_stage2(set0, sZ, sW2); umma_commit(&bar_s2[0]);
           mbar_wait(&bar_z[1], 1); tc_fence_after(); issue_stage2(set1, sZ + LEG * OPB, sW2); umma_commit(&bar_s2[1]);
+          if (layer < 2) {                                   // E2(leg 3) done: set 0 is free, h'[1], h'[5], h'[9] exist
+            mbar_wait(&bar_e2[0], 1); tc_fence_after();
+            issue_stage1_leg1_early(set0, sH, sW1a + 3 * WB, sW1b + 3 * WB);
+          }
         }
       }
     }
@@ -311,23 +362,18 @@ __global__ void __launch_bounds__(THREADS, 1) k_gnn_forward_tc(const Args a) {
     pdl_wait();                                              // the observations are the predecessor kernel's output
     mbar_wait(&bar_w, 0);                                    // fp32 parameters live in the weight blob
     for (int it = 0; it < n_loc; ++it) {
-      const int tile = tile0 + it * stride;
-      const int row0 = tile * TM, rows = min(TM, a.n - row0);
+      const int row0 = (tile0 + it * stride) * TM, rows = min(TM, a.n - row0);
       c.tl = (st && a.timeline != nullptr && blockIdx.x == 0 && it < 7) ? a.timeline + 8 + 64 * it : nullptr;
       tstamp(c, 0);
-      // ---- observations -> padded fp32 staging (coalesced 128-bit loads: thread owns float4 j*512 + tid of the [128 x 64] tile)
-      {
-        const float* base = a.obs + (size_t)row0 * 64;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int r = j * 32 + (tid >> 4), c4 = tid & 15;
-          const float4 v = r < rows ? ld_nc_f4(base + (size_t)(j * E_THREADS + tid) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-          *reinterpret_cast<float4*>(stage + r * OBS_STRIDE + 4 * c4) = v;
-        }
-        if (it + 1 < n_loc && tid < 256) {                   // next tile's 32 KB -> L2
-          const char* nxt = reinterpret_cast<const char*>(a.obs + (size_t)(row0 + stride * TM) * 64) + tid * 128;
-          if (nxt < reinterpret_cast<const char*>(a.obs + (size_t)a.n * 64)) asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt));
-        }
+      // ---- observations -> padded fp32 staging (the first tile's here; later tiles' were fetched during the previous tile's heads)
+      if (it == 0) {
+        float4 v[4];
+        obs_fetch(a, row0, rows, tid, v);
+        obs_stage(stage, tid, v);
+      }
+      if (it + 1 < n_loc && tid < 256) {                     // the tile after this one -> L2
+        const char* nxt = reinterpret_cast<const char*>(a.obs + (size_t)(row0 + stride * TM) * 64) + tid * 128;
+        if (nxt < reinterpret_cast<const char*>(a.obs + (size_t)a.n * 64)) asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt));
       }
       epi_sync();
       // ---- input layers (:97-126): node 0 <- Linear(16,32)(obs[0:16]); node 1+j <- Linear(4,32)(jp, jv, a_cur, a_last of joint pi(j))
@@ -384,6 +430,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_gnn_forward_tc(const Args a) {
       tstamp(c, 4);
       // ---- heads (:215-241): action k = Wa . h[1+k] + ba; value = Wv . max_n h[n] + bv.  Partial sums of the four column
       // quarters meet in shared memory (z set 0: its last reader, stage 2 of leg 3, completed before E2(leg 3)).
+      float4 nobs[4];
+      const int nrow0 = row0 + stride * TM;
+      if (it + 1 < n_loc) obs_fetch(a, nrow0, min(TM, a.n - nrow0), tid, nobs);   // lands during the head reduction
       {
         float wv[8];
         load_bias8(F + F_WVAL + 8 * q, wv);
@@ -408,6 +457,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gnn_forward_tc(const Args a) {
           if (tid < rows) a.value[row0 + tid] = s + bv;
         }
       }
+      if (it + 1 < n_loc) obs_stage(stage, tid, nobs);        // z set 1 is idle: stage 2 of leg 4 completed before E2(leg 4)
       tstamp(c, 5);
       // the next tile's staging barrier (epi_sync) orders these reads of `red` before z set 0 is written again
     }

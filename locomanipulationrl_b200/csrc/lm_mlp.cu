@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_mlp_forward(const Args a) {
   // full layer's worth of other work in front of it.  The control thread issues MMAs in the matching order.
   if (warp == E_WARPS) {
     // ================================================================== control warp: one thread issues TMA + every MMA
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_expect_tx(&bar_w, BLOB_BYTES);
       tma_load_1d(smem, a.blob, BLOB_BYTES, &bar_w);      // resident weights + biases: one bulk copy per CTA
       mbar_wait(&bar_w, 0);

@@ -17,6 +17,22 @@ __host__ __device__ constexpr int elem_offset(int rows, int row, int k) {   // b
   return (k / 8) * lbo_bytes(rows) + row * 16 + (k % 8) * 2;
 }
 
+// One lane of a converged warp (elect.sync).  Code under `if (elect_one())` is known by ptxas to run on a single thread, so
+// tcgen05.mma operands stay in uniform registers; under `if (lane == 0)` it wraps every MMA in a per-lane ELECT/BRA loop
+// (measured: 62 cycles per issued MMA in the control thread, independent of the MMA shape).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n"
+      ".reg .b32 rx;\n"
+      ".reg .pred px;\n"
+      "elect.sync rx|px, 0xFFFFFFFF;\n"
+      "@px mov.s32 %0, 1;\n"
+      "}\n"
+      : "+r"(pred));
+  return pred != 0;
+}
+
 // ---------------------------------------------------------------- tcgen05 wrappers
 __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, int lbo) {
   // SmemDescriptor (cute/arch/mma_sm100_desc.hpp): start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout NONE
@@ -78,9 +94,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t r[32]) {
 __device__ __forceinline__ void tmem_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ float ex2_approx(float x) {
+#ifdef LM_EXP_NO_MUFU   // timing experiment only (wrong results): is the epilogue MUFU-bound?
+  return fmaf(x, 0.5f, 1.0f);
+#else
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+#endif
 }
 // nn.ELU(alpha=1) = max(x, min(exp(x) - 1, 0)): exp(x) - 1 >= x everywhere, and it is > 0 exactly when x > 0
 __device__ __forceinline__ float elu(float x) {

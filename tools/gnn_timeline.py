@@ -27,6 +27,7 @@ it = 0
 while it < 7 and s[8 + 64 * it] != 0:
     b = 8 + 64 * it
     print(f"tile {it}: start +{s[b] - t0}  input layer done +{s[b + 1] - t0}  layers done +{s[b + 2] - t0} +{s[b + 3] - t0} +{s[b + 4] - t0}  heads done +{s[b + 5] - t0}")
+    print(f"   control thread, layer 0: stage-1 issue of leg 1 (24 MMAs) started +{s[b + 6] - t0}, returned after {s[b + 7] - s[b + 6]} cycles")
     for layer in range(3):
         lb = b + 8 + 16 * layer
         prev = s[b + 1 + layer]
