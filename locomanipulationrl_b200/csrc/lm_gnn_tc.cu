@@ -59,9 +59,7 @@ constexpr int Z_OFF = H_OFF + NODES * OPB;           // 2 sets x 6 z operands
 constexpr int SMEM_BYTES = Z_OFF + 2 * LEG * OPB;
 constexpr int OBS_STRIDE = 68;                       // floats per staged observation row (+4: conflict-free row reads)
 constexpr int STAGE_OFF = Z_OFF + LEG * OPB;         // observation staging lives in z set 1 (idle between tiles)
-constexpr int RED_OFF = Z_OFF;                       // head partial sums [4 quarters][13][128] live in z set 0 (idle at tile end)
 static_assert(TM * OBS_STRIDE * 4 <= LEG * OPB, "obs staging fits one z set");
-static_assert(4 * 13 * TM * 4 <= LEG * OPB, "head partials fit one z set");
 static_assert(SMEM_BYTES + 256 <= 232448, "exceeds 227 KB");
 constexpr uint32_t TMEM_COLS = 512;                  // 12 slots x 32 columns used
 
@@ -78,26 +76,12 @@ struct Args {
 __device__ __forceinline__ void stamp(const Args& a, int k) {
   if (a.timeline != nullptr && blockIdx.x == 0) a.timeline[k] = clock64();
 }
-#ifdef LM_EXP_NO_LDTM   // timing experiment only (wrong results): is the epilogue TMEM-read-bound?
-__device__ __forceinline__ void ld8(uint32_t taddr, uint32_t r[8]) {
-#pragma unroll
-  for (int i = 0; i < 8; ++i) r[i] = taddr * (i + 1);
-}
-#else
-__device__ __forceinline__ void ld8(uint32_t taddr, uint32_t r[8]) { tmem_ld8(taddr, r); }
-#endif
 __device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, %0;" ::"n"(E_THREADS) : "memory"); }
 
 // ---------------------------------------------------------------- control thread: MMA issue
 // one K = 32 product (two K/16 steps) accumulated into `acc`
-#ifndef LM_EXP_MMA_M   // timing experiments only (wrong results): what does one small-N MMA cost, and what does it scale with?
-#define LM_EXP_MMA_M TM
-#endif
-#ifndef LM_EXP_MMA_N
-#define LM_EXP_MMA_N H
-#endif
 __device__ __forceinline__ void mma_k32(uint32_t acc, uint32_t a_saddr, uint32_t b_saddr, uint32_t accumulate) {
-  constexpr uint32_t idesc = instr_desc(LM_EXP_MMA_M, LM_EXP_MMA_N);
+  constexpr uint32_t idesc = instr_desc(TM, H);
   umma_bf16(acc, smem_desc(a_saddr, lbo_bytes(TM)), smem_desc(b_saddr, lbo_bytes(H)), idesc, accumulate);
   umma_bf16(acc, smem_desc(a_saddr + 2 * lbo_bytes(TM), lbo_bytes(TM)), smem_desc(b_saddr + 2 * lbo_bytes(H), lbo_bytes(H)), idesc, 1u);
 }
@@ -136,9 +120,13 @@ __device__ __forceinline__ void load_bias8(const float* p, float b[8]) {
   b[0] = lo.x; b[1] = lo.y; b[2] = lo.z; b[3] = lo.w; b[4] = hi.x; b[5] = hi.y; b[6] = hi.z; b[7] = hi.w;
 }
 // 8 accumulator columns + bias -> ELU -> 8 bf16 = one 16-byte K chunk
+#ifndef LM_GNN_FMA_PAIRS   // of the 4 ELU pairs of a chunk, how many take the FMA-pipe exp (tuned on B200)
+#define LM_GNN_FMA_PAIRS 1
+#endif
 __device__ __forceinline__ uint4 elu_chunk(const uint32_t r[8], const float b[8]) {
-  return make_uint4(elu_pair(r[0], r[1], b[0], b[1]), elu_pair(r[2], r[3], b[2], b[3]), elu_pair(r[4], r[5], b[4], b[5]),
-                    elu_pair(r[6], r[7], b[6], b[7]));
+  constexpr int F = LM_GNN_FMA_PAIRS;
+  return make_uint4(elu_pair_mix<F>(0, r[0], r[1], b[0], b[1]), elu_pair_mix<F>(1, r[2], r[3], b[2], b[3]),
+                    elu_pair_mix<F>(2, r[4], r[5], b[4], b[5]), elu_pair_mix<F>(3, r[6], r[7], b[6], b[7]));
 }
 __device__ __forceinline__ uint4 pack_chunk(const float v[8]) {
   return make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
@@ -154,58 +142,54 @@ __device__ __forceinline__ void elu8(const uint32_t r[8], const float b[8], floa
 }
 
 // E1 of one leg: stage-1 accumulators (6 slots) -> z operands.  taddr = this thread's lane group / column quarter in slot 0 of the set.
-__device__ __forceinline__ void epilogue_stage1(uint32_t taddr, const float b1[8], uint8_t* zdst /* + q*lbo + row*16 applied */) {
+__device__ __forceinline__ void epilogue_stage1(uint32_t taddr, const float b1[8], uint8_t* zdst /* + q*lbo + row*16 applied */,
+                                                long long* dg = nullptr) {
   uint32_t r[LEG][8];
 #pragma unroll
-  for (int e = 0; e < 3; ++e) ld8(taddr + e * H, r[e]);
+  for (int e = 0; e < 3; ++e) tmem_ld8(taddr + e * H, r[e]);
   tmem_wait();
+  if (dg) dg[0] = clock64();
 #pragma unroll
-  for (int e = 3; e < LEG; ++e) ld8(taddr + e * H, r[e]);
+  for (int e = 3; e < LEG; ++e) tmem_ld8(taddr + e * H, r[e]);
 #pragma unroll
   for (int e = 0; e < 3; ++e) *reinterpret_cast<uint4*>(zdst + e * OPB) = elu_chunk(r[e], b1);
+  if (dg) dg[1] = clock64();
   tmem_wait();
+  if (dg) dg[2] = clock64();
 #pragma unroll
   for (int e = 3; e < LEG; ++e) *reinterpret_cast<uint4*>(zdst + e * OPB) = elu_chunk(r[e], b1);
+  if (dg) dg[3] = clock64();
 }
 
-struct HeadAcc {
-  float act[12];   // this thread's 8-channel share of action_layer . h[1 + k]
-  float vmax[8];   // running max over nodes (value head input)
-};
-
-// E2 of leg kLeg: stage-2 accumulators -> max aggregation -> h' of nodes k, k+4, k+8 (in place) / head partials; node 0 keeps a running max
-template <int kLeg, bool kLast>
-__device__ __forceinline__ void epilogue_stage2(uint32_t taddr, const float b2[8], uint8_t* hdst /* + q*lbo + row*16 applied */,
-                                                uint32_t m0[8], const float* __restrict__ wact_sm, HeadAcc& head) {
+// E2 of leg `leg`: stage-2 accumulators -> max aggregation (pre-activation: ELU is monotone) -> nodes leg, leg+4, leg+8; node 0
+// keeps a running max.  hdst = this thread's 16-byte chunk in h[leg].  Graph layers 1-2 write h' (bf16 operand) in place.  The last
+// layer keeps fp32: the thread's 8-channel share of action_layer . h[n] goes into the same (now dead) 16-byte slot, where
+// the head reduction collects the four column quarters, and vmax follows the per-channel maximum over the nodes.
+__device__ __forceinline__ void epilogue_stage2(uint32_t taddr, const float b2[8], uint8_t* hdst, uint32_t m0[8], bool last,
+                                                const float* __restrict__ wact_sm, float vmax[8]) {
   uint32_t r[LEG][8];
 #pragma unroll
-  for (int e = 0; e < LEG; ++e) ld8(taddr + e * H, r[e]);
+  for (int e = 0; e < LEG; ++e) tmem_ld8(taddr + e * H, r[e]);
   tmem_wait();
   max8(r[0], r[1]);          // node k    <- {0, k+4}
   max8(r[2], r[3]);          // node k+4  <- {k, k+8}
-  if (kLeg == 1) {
+  max8(m0, r[5]);            // node 0    <- k
+  if (!last) {
 #pragma unroll
-    for (int c = 0; c < 8; ++c) m0[c] = r[5][c];
+    for (int t = 0; t < 3; ++t) *reinterpret_cast<uint4*>(hdst + 4 * t * OPB) = elu_chunk(r[2 * t], b2);
   } else {
-    max8(m0, r[5]);          // node 0    <- k
-  }
-  if (!kLast) {
-    *reinterpret_cast<uint4*>(hdst + kLeg * OPB) = elu_chunk(r[0], b2);
-    *reinterpret_cast<uint4*>(hdst + (kLeg + 4) * OPB) = elu_chunk(r[2], b2);
-    *reinterpret_cast<uint4*>(hdst + (kLeg + 8) * OPB) = elu_chunk(r[4], b2);
-  } else {
-    float v[8], wact[8];
+    float wact[8];
     load_bias8(wact_sm, wact);
 #pragma unroll
     for (int t = 0; t < 3; ++t) {
+      float v[8], s = 0.0f;
       elu8(r[2 * t], b2, v);
-      float s = 0.0f;
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
         s = fmaf(wact[c], v[c], s);
-        head.vmax[c] = (kLeg == 1 && t == 0) ? v[c] : fmaxf(head.vmax[c], v[c]);
+        vmax[c] = fmaxf(vmax[c], v[c]);
       }
-      head.act[kLeg - 1 + 4 * t] = s;
+      *reinterpret_cast<float*>(hdst + 4 * t * OPB) = s;
     }
   }
 }
@@ -236,47 +220,51 @@ __device__ __forceinline__ void tstamp(const EpiCtx& c, int k) {
 }
 
 // One graph layer on the epilogue side: E1(leg1) E1(leg2) E2(leg1) E2(leg2) E1(leg3) E1(leg4) E2(leg3) E2(leg4), then node 0.
-template <bool kLast>
-__device__ __forceinline__ void run_layer(const EpiCtx& c, int layer, HeadAcc& head) {
+// Rolled loops on purpose: one copy of each stage body keeps the kernel inside the instruction cache (the fully unrolled
+// version lost 14 % of its issue slots to instruction fetch, ncu stall_no_inst).
+__device__ __forceinline__ void run_layer(const EpiCtx& c, int layer, float vmax[8]) {
+  const bool last = layer == 2;
   float b1[8], b2[8];
   load_bias8(c.F + F_BL + layer * 2 * H + 8 * c.q, b1);
   load_bias8(c.F + F_BL + layer * 2 * H + H + 8 * c.q, b2);
   const float* wact_sm = c.F + F_WACT + 8 * c.q;
   uint32_t m0[8];
+#pragma unroll
+  for (int ch = 0; ch < 8; ++ch) m0[ch] = 0xff800000u;      // -inf
   const int tb = 8 + 16 * layer;
-#define LM_E1(SET, PAR, SLOT)                                                        \
-  mbar_wait(&c.bar_s1[SET], PAR); tc_fence_after(); tstamp(c, tb + 2 * SLOT);        \
-  epilogue_stage1(SET ? c.t_set1 : c.t_set0, b1, SET ? c.z1 : c.z0);                 \
-  fence_proxy_async(); tc_fence_before(); __syncwarp();                              \
-  if (c.lane == 0) mbar_arrive(&c.bar_z[SET]);                                       \
-  tstamp(c, tb + 2 * SLOT + 1);
-#define LM_E2(SET, PAR, LEGK, SLOT)                                                  \
-  mbar_wait(&c.bar_s2[SET], PAR); tc_fence_after(); tstamp(c, tb + 2 * SLOT);        \
-  epilogue_stage2<LEGK, kLast>(SET ? c.t_set1 : c.t_set0, b2, c.hmine, m0, wact_sm, head); \
-  fence_proxy_async(); tc_fence_before(); __syncwarp();                              \
-  if (c.lane == 0) mbar_arrive(&c.bar_e2[SET]);                                      \
-  tstamp(c, tb + 2 * SLOT + 1);
-  LM_E1(0, 0, 0)
-  LM_E1(1, 0, 1)
-  LM_E2(0, 0, 1, 2)
-  LM_E2(1, 0, 2, 3)
-  LM_E1(0, 1, 4)
-  LM_E1(1, 1, 5)
-  LM_E2(0, 1, 3, 6)
-  LM_E2(1, 1, 4, 7)
-#undef LM_E1
-#undef LM_E2
+#pragma unroll 1
+  for (int par = 0; par < 2; ++par) {
+#pragma unroll
+    for (int set = 0; set < 2; ++set) {
+      mbar_wait(&c.bar_s1[set], par); tc_fence_after(); tstamp(c, tb + 8 * par + 2 * set);
+      epilogue_stage1(c.t_set0 + set * LEG * H, b1, c.z0 + set * LEG * OPB, (c.tl && layer == 1 && par + set == 0) ? c.tl + 56 : nullptr);
+      fence_proxy_async(); tc_fence_before(); __syncwarp();
+      if (c.lane == 0) mbar_arrive(&c.bar_z[set]);
+      tstamp(c, tb + 8 * par + 2 * set + 1);
+    }
+#pragma unroll
+    for (int set = 0; set < 2; ++set) {
+      const int leg = 1 + 2 * par + set;
+      mbar_wait(&c.bar_s2[set], par); tc_fence_after(); tstamp(c, tb + 8 * par + 4 + 2 * set);
+      epilogue_stage2(c.t_set0 + set * LEG * H, b2, c.hmine + leg * OPB, m0, last, wact_sm, vmax);
+      fence_proxy_async(); tc_fence_before(); __syncwarp();
+      if (c.lane == 0) mbar_arrive(&c.bar_e2[set]);
+      tstamp(c, tb + 8 * par + 4 + 2 * set + 1);
+    }
+  }
   // node 0 <- {1, 2, 3, 4}: every stage-1 MMA of this layer has completed, h[0] may be overwritten
-  if (!kLast) {
+  if (!last) {
     *reinterpret_cast<uint4*>(c.hmine) = elu_chunk(m0, b2);
     fence_proxy_async();
     __syncwarp();
     if (c.lane == 0) mbar_arrive(c.bar_h);
   } else {
-    float v[8];
+    float v[8], wv[8], sv = 0.0f;
     elu8(m0, b2, v);
+    load_bias8(c.F + F_WVAL + 8 * c.q, wv);
 #pragma unroll
-    for (int ch = 0; ch < 8; ++ch) head.vmax[ch] = fmaxf(head.vmax[ch], v[ch]);
+    for (int ch = 0; ch < 8; ++ch) sv = fmaf(wv[ch], fmaxf(vmax[ch], v[ch]), sv);
+    *reinterpret_cast<float*>(c.hmine) = sv;                // value-head share, in the dead h[0] slot
   }
 }
 
@@ -354,7 +342,6 @@ __global__ void __launch_bounds__(THREADS, 1) k_gnn_forward_tc(const Args a) {
     uint8_t* z0 = smem + Z_OFF + my_off;
     uint8_t* z1 = z0 + LEG * OPB;
     float* stage = reinterpret_cast<float*>(smem + STAGE_OFF);
-    float* red = reinterpret_cast<float*>(smem + RED_OFF);
     const bool st = tid == 0;
     EpiCtx c;
     c.bar_h = &bar_h; c.bar_s1 = bar_s1; c.bar_s2 = bar_s2; c.bar_z = bar_z; c.bar_e2 = bar_e2;
@@ -421,45 +408,41 @@ __global__ void __launch_bounds__(THREADS, 1) k_gnn_forward_tc(const Args a) {
       if (lane == 0) mbar_arrive(&bar_h);
       tstamp(c, 1);
 
-      HeadAcc head;
-      run_layer<false>(c, 0, head);
-      tstamp(c, 2);
-      run_layer<false>(c, 1, head);
-      tstamp(c, 3);
-      run_layer<true>(c, 2, head);
-      tstamp(c, 4);
-      // ---- heads (:215-241): action k = Wa . h[1+k] + ba; value = Wv . max_n h[n] + bv.  Partial sums of the four column
-      // quarters meet in shared memory (z set 0: its last reader, stage 2 of leg 3, completed before E2(leg 3)).
+      float vmax[8];
+#pragma unroll
+      for (int ch = 0; ch < 8; ++ch) vmax[ch] = -INFINITY;
+#pragma unroll 1
+      for (int layer = 0; layer < 3; ++layer) {
+        run_layer(c, layer, vmax);
+        tstamp(c, 2 + layer);
+      }
+      // ---- heads (:215-241): action k = Wa . h[1+k] + ba; value = Wv . max_n h[n] + bv.  The four column quarters left
+      // their fp32 shares in their own 16-byte slots of the (dead) node operands; 512 threads sum them, coalesced stores.
       float4 nobs[4];
       const int nrow0 = row0 + stride * TM;
       if (it + 1 < n_loc) obs_fetch(a, nrow0, min(TM, a.n - nrow0), tid, nobs);   // lands during the head reduction
-      {
-        float wv[8];
-        load_bias8(F + F_WVAL + 8 * q, wv);
-        float sv = 0.0f;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) sv = fmaf(wv[c], head.vmax[c], sv);
-#pragma unroll
-        for (int k = 0; k < 12; ++k) red[(q * 13 + k) * TM + row] = head.act[k];
-        red[(q * 13 + 12) * TM + row] = sv;
-      }
       epi_sync();
       {
         const float ba = F[F_BHEAD], bv = F[F_BHEAD + 1];
+        const uint8_t* hb = smem + H_OFF;
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
           const int idx = j * E_THREADS + tid, r = idx / 12, k = idx - 12 * r;
-          const float s = ((red[(0 * 13 + k) * TM + r] + red[(1 * 13 + k) * TM + r]) + red[(2 * 13 + k) * TM + r]) + red[(3 * 13 + k) * TM + r];
+          const uint8_t* p0 = hb + (1 + k) * OPB + r * 16;
+          const float s = ((*reinterpret_cast<const float*>(p0) + *reinterpret_cast<const float*>(p0 + lbo_bytes(TM))) +
+                           *reinterpret_cast<const float*>(p0 + 2 * lbo_bytes(TM))) + *reinterpret_cast<const float*>(p0 + 3 * lbo_bytes(TM));
           if (r < rows) a.mu[(size_t)row0 * 12 + idx] = s + ba;
         }
         if (tid < TM) {
-          const float s = ((red[12 * TM + tid] + red[(13 + 12) * TM + tid]) + red[(26 + 12) * TM + tid]) + red[(39 + 12) * TM + tid];
+          const uint8_t* p0 = hb + tid * 16;
+          const float s = ((*reinterpret_cast<const float*>(p0) + *reinterpret_cast<const float*>(p0 + lbo_bytes(TM))) +
+                           *reinterpret_cast<const float*>(p0 + 2 * lbo_bytes(TM))) + *reinterpret_cast<const float*>(p0 + 3 * lbo_bytes(TM));
           if (tid < rows) a.value[row0 + tid] = s + bv;
         }
       }
       if (it + 1 < n_loc) obs_stage(stage, tid, nobs);        // z set 1 is idle: stage 2 of leg 4 completed before E2(leg 4)
       tstamp(c, 5);
-      // the next tile's staging barrier (epi_sync) orders these reads of `red` before z set 0 is written again
+      // the next tile's staging barrier (epi_sync) orders these reads before the input layer rewrites the node operands
     }
   }
   tc_fence_before();

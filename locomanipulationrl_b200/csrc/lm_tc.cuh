@@ -94,13 +94,9 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t r[32]) {
 __device__ __forceinline__ void tmem_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ float ex2_approx(float x) {
-#ifdef LM_EXP_NO_MUFU   // timing experiment only (wrong results): is the epilogue MUFU-bound?
-  return fmaf(x, 0.5f, 1.0f);
-#else
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
-#endif
 }
 // nn.ELU(alpha=1) = max(x, min(exp(x) - 1, 0)): exp(x) - 1 >= x everywhere, and it is > 0 exactly when x > 0
 __device__ __forceinline__ float elu(float x) {
@@ -126,6 +122,39 @@ __device__ __forceinline__ uint32_t elu_pair(uint32_t acc_lo, uint32_t acc_hi, f
   upk2(add2(pk2(ex2_approx(t0), ex2_approx(t1)), pk2(-1.0f, -1.0f)), r0, r1);
   upk2(x2, x0, x1);
   return pack_bf16(fmaxf(x0, fminf(r0, 0.0f)), fmaxf(x1, fminf(r1, 0.0f)));
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) { uint64_t r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+
+// The same ELU pair with exp on the FMA pipe instead of MUFU (the epilogues are MUFU-bound: 16 ex2/clk/SM, so a share of
+// the pairs is moved to the otherwise idle FMA pipe).  t = x log2(e) is clamped to [-64, 0] by ONE saturating FMA
+// (s = sat(t/64 + 1)); n = round(64 s) appears in the low mantissa bits of 64 s + (1.5 * 2^23 - 64); 2^f, f = 64 s - n in
+// [-0.5, 0.5], is a cubic with p(0) = 1 (max relative error 1.0e-4, 20x below the bf16 rounding of the result) and the
+// exponent is added as an integer.  exp <= 1 by construction, so ELU = max(x, exp - 1) needs no min().
+__device__ __forceinline__ uint32_t elu_pair_fma(uint32_t acc_lo, uint32_t acc_hi, float b_lo, float b_hi) {
+  constexpr float kMagic = 12582912.0f - 64.0f;
+  const uint64_t x2 = add2(pk2u(acc_lo, acc_hi), pk2(b_lo, b_hi));
+  float x0, x1;
+  upk2(x2, x0, x1);
+  const uint64_t s2 = pk2(__saturatef(fmaf(x0, 1.4426950408889634f / 64.0f, 1.0f)), __saturatef(fmaf(x1, 1.4426950408889634f / 64.0f, 1.0f)));
+  const uint64_t k64 = pk2(64.0f, 64.0f);
+  const uint64_t r2 = fma2(s2, k64, pk2(kMagic, kMagic));
+  const uint64_t f2 = fma2(s2, k64, fma2(r2, pk2(-1.0f, -1.0f), pk2(kMagic, kMagic)));     // 64 s - n
+  uint64_t p2 = fma2(f2, pk2(0.05500871f, 0.05500871f), pk2(0.24221068f, 0.24221068f));
+  p2 = fma2(p2, f2, pk2(0.69328292f, 0.69328292f));
+  p2 = fma2(p2, f2, pk2(1.0f, 1.0f));
+  float r0, r1, p0, p1;
+  upk2(r2, r0, r1);
+  upk2(p2, p0, p1);
+  const float e0 = __uint_as_float((__float_as_uint(r0) << 23) + __float_as_uint(p0));
+  const float e1 = __uint_as_float((__float_as_uint(r1) << 23) + __float_as_uint(p1));
+  float y0, y1;
+  upk2(add2(pk2(e0, e1), pk2(-1.0f, -1.0f)), y0, y1);
+  return pack_bf16(fmaxf(x0, y0), fmaxf(x1, y1));
+}
+// pair `i` of a group of four: the first kFma pairs go to the FMA pipe
+template <int kFma>
+__device__ __forceinline__ uint32_t elu_pair_mix(int i, uint32_t acc_lo, uint32_t acc_hi, float b_lo, float b_hi) {
+  return i < kFma ? elu_pair_fma(acc_lo, acc_hi, b_lo, b_hi) : elu_pair(acc_lo, acc_hi, b_lo, b_hi);
 }
 
 }  // namespace tc

@@ -28,6 +28,9 @@ while it < 7 and s[8 + 64 * it] != 0:
     b = 8 + 64 * it
     print(f"tile {it}: start +{s[b] - t0}  input layer done +{s[b + 1] - t0}  layers done +{s[b + 2] - t0} +{s[b + 3] - t0} +{s[b + 4] - t0}  heads done +{s[b + 5] - t0}")
     print(f"   control thread, layer 0: stage-1 issue of leg 1 (24 MMAs) started +{s[b + 6] - t0}, returned after {s[b + 7] - s[b + 6]} cycles")
+    e1 = s[b + 8 + 16]          # layer 1, E1a: barrier wait satisfied
+    print(f"   layer 1 E1a inside: first 3 TMEM loads landed +{s[b + 56] - e1}, 3 chunks stored +{s[b + 57] - e1}, next 3 loads landed +{s[b + 58] - e1}, "
+          f"3 chunks stored +{s[b + 59] - e1}, fence + arrive done +{s[b + 8 + 16 + 1] - e1}")
     for layer in range(3):
         lb = b + 8 + 16 * layer
         prev = s[b + 1 + layer]
