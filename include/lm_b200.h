@@ -275,6 +275,52 @@ int lm_gae_env_major(const float* rewards, const float* values, const float* don
                      float* returns, int32_t T, int32_t N, float gamma, float lambda, int32_t variant,
                      void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Rollout writer + running mean/std (the caller-side formats either side of the path).  Not in the
+ * reference repo: rl_games 1.6.0 ExperienceBuffer / RunningMeanStd / a2c_continuous.neglogp (cfg/train/*PPO.yaml:46-47,
+ * 66) and skrl RandomMemory / RunningStandardScaler / GaussianMixin (scripts/skrl_ppo_locomanipulation.py:100-122).
+ * Buffers are time-major [T,N,.] so that lm_gae and the PPO update read them coalesced. */
+enum { LM_RMS_RLGAMES = 0, LM_RMS_SKRL = 1 };
+typedef struct LmRunningStats {
+  double* mean;    /* [dim] float64, as both libraries keep them */
+  double* var;     /* [dim] */
+  double* count;   /* [1]   */
+  int32_t dim;     /* 1 or a multiple of 4, <= 64 */
+  int32_t variant; /* LM_RMS_RLGAMES: y = (x - mean) / sqrt(var + 1e-5); LM_RMS_SKRL: y = (x - mean) / (sqrt(var) + 1e-8) */
+} LmRunningStats;
+typedef struct LmRolloutStep {   /* one env step; device pointers */
+  const float* obs;       /* [N,64] what the policy saw               */
+  const float* mu;        /* [N,12] policy mean                       */
+  const float* value;     /* [N]                                      */
+  const float* log_std;   /* [12]   state-independent log sigma       */
+  const float* noise;     /* [N,12] standard-normal draws of the caller's generator; NULL: action = mu */
+  const float* rew;       /* [N]                                      */
+  const int64_t* dones;   /* [N]    reset_buf                         */
+} LmRolloutStep;
+typedef struct LmRolloutBuffers {
+  float* obses;    /* [T,N,64] */
+  float* actions;  /* [T,N,12] */
+  float* mus;      /* [T,N,12] */
+  float* values;   /* [T,N]    */
+  float* rewards;  /* [T,N]  rew * reward_scale (rl_games rewards_shaper scale_value) */
+  float* dones;    /* [T,N]  fp32 0/1 */
+  float* neglogp;  /* [T,N]  0.5 sum(((a - mu)/sigma)^2) + 0.5 log(2 pi) 12 + sum(log_std)  (= -log_prob of skrl) */
+  int32_t horizon; int32_t num_envs;
+  float reward_scale;
+} LmRolloutBuffers;
+typedef struct LmRollout LmRollout;
+LmRollout* lm_rollout_create(int device);
+void lm_rollout_destroy(LmRollout* r);
+/* Samples a = noise * sigma + mu (torch.normal's op order), writes slot t of every buffer, optionally copies the actions
+ * to `actions_out` [N,12] (the next pre_physics_step input) and, when obs_stats != NULL, folds this step's observation
+ * batch into the running mean / variance (batch mean, unbiased batch variance, parallel-variance combine).  One launch. */
+int lm_rollout_write(LmRollout* r, const LmRolloutStep* step, const LmRolloutBuffers* buf, int32_t t, float* actions_out,
+                     const LmRunningStats* obs_stats, void* stream);
+/* Folds a batch x [n,dim] into running statistics (value / return normalisation, or observations outside a rollout). */
+int lm_rms_update(LmRollout* r, const float* x, int64_t n, const LmRunningStats* stats, void* stream);
+/* fp32 vectors for lm_mlp_forward(norm_mean, norm_inv_std): mean and the variant's 1/std form. */
+int lm_rms_export(const LmRunningStats* stats, float* mean_f32, float* inv_std_f32, void* stream);
+
 /* End-to-end host-buffer entry used by bench.py's e2e leg: one env step with inputs in pinned
  * host memory (state of both robots packed as the LmRobotViews fields, actions, uniforms) and
  * outputs (obs, rew, reset) read back.  Copies run on `stream`; returns after synchronising it. */

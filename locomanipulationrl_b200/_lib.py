@@ -67,6 +67,19 @@ class LmPdState(C.Structure):
                 ("targets_se", C.c_void_p), ("init_se", C.c_float * NUM_ACT), ("carry_post_state", _i32), ("target_obs_scale", C.c_float)]
 
 
+class LmRunningStats(C.Structure):
+    _fields_ = [("mean", C.c_void_p), ("var", C.c_void_p), ("count", C.c_void_p), ("dim", _i32), ("variant", _i32)]
+
+
+class LmRolloutStep(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("obs", "mu", "value", "log_std", "noise", "rew", "dones")]
+
+
+class LmRolloutBuffers(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("obses", "actions", "mus", "values", "rewards", "dones", "neglogp")] + \
+               [("horizon", _i32), ("num_envs", _i32), ("reward_scale", _f)]
+
+
 # name -> (restype, argtypes); every symbol include/lm_b200.h declares
 _vp = C.c_void_p
 SYMBOLS = {
@@ -100,6 +113,11 @@ SYMBOLS = {
     "lm_gnn_forward": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _vp]),
     "lm_gnn_forward_bf16": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _vp]),
     "lm_gnn_set_timeline": (C.c_int, [_vp, _vp]),
+    "lm_rollout_create": (_vp, [C.c_int]),
+    "lm_rollout_destroy": (None, [_vp]),
+    "lm_rollout_write": (C.c_int, [_vp, C.POINTER(LmRolloutStep), C.POINTER(LmRolloutBuffers), _i32, _vp, C.POINTER(LmRunningStats), _vp]),
+    "lm_rms_update": (C.c_int, [_vp, _vp, _i64, C.POINTER(LmRunningStats), _vp]),
+    "lm_rms_export": (C.c_int, [C.POINTER(LmRunningStats), _vp, _vp, _vp]),
     "lm_gae": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _f, _f, _i32, _vp]),
     "lm_gae_env_major": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _f, _f, _i32, _vp]),
     "lm_task_step_host": (C.c_int, [_vp, C.POINTER(LmRobotViews), C.POINTER(LmRobotViews), _vp, C.POINTER(LmTaskBuffers), C.POINTER(LmHostStep), _vp]),
@@ -132,7 +150,7 @@ def load(path: Optional[str] = None) -> C.CDLL:
         fn.argtypes = args
     if lib.lm_abi_version() != 1:
         raise LmError("liblm_b200.so ABI version mismatch")
-    for which, struct in enumerate((LmTaskParams, LmRobotViews, LmTaskBuffers, LmHostStep, LmPdState)):
+    for which, struct in enumerate((LmTaskParams, LmRobotViews, LmTaskBuffers, LmHostStep, LmPdState, LmRunningStats, LmRolloutStep, LmRolloutBuffers)):
         if lib.lm_struct_size(which) != C.sizeof(struct):
             raise LmError(f"struct layout mismatch for {struct.__name__}: C {lib.lm_struct_size(which)} vs ctypes {C.sizeof(struct)}")
     _lib = lib

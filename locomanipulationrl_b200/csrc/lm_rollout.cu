@@ -1,0 +1,371 @@
+// Rollout writer + running mean/std: the caller-side formats around the task/policy path.
+//
+// Not in the reference repo.  rl_games 1.6.0 (pinned at RobotLearning/setup.py:20; cfg/train/*PPO.yaml:46-47 normalize_input /
+// normalize_value, :66 horizon) keeps an ExperienceBuffer of time-major tensors (obses, actions, mus, values, rewards, dones,
+// neglogpacs) and RunningMeanStd modules; skrl (scripts/skrl_ppo_locomanipulation.py:100-122) a RandomMemory and
+// RunningStandardScaler.  Both fold a batch into float64 running statistics with the parallel-variance rule
+//     delta = mean_b - mean; tot = count + n; mean += delta n / tot; var = (var count + var_b n + delta^2 count n / tot) / tot
+// where var_b is torch.var's unbiased batch variance.  Restated in oracle/port_policy.py.
+//
+// k_rollout_write: ONE launch per env step, one CTA per SM.  Phase A streams the observation tile [N,64] into obses[t]
+// with 128-bit accesses; thread tid always owns channel quad tid % 16, so the per-channel moments (shifted by the current
+// running mean against cancellation) accumulate in registers, meet per CTA in shared memory as doubles and per grid through
+// the last-CTA pattern, where 64 threads apply the fold.  Phase B is per env: sample the action, its negative log-prob,
+// and the scalar columns.  Algorithmic bytes: 368 read + 368 written per env-step (+48 for actions_out).
+#include "lm_common.cuh"
+#include "lm_host.h"
+
+namespace lm {
+namespace rollout {
+
+constexpr int THREADS = 512;
+constexpr int MAX_DIM = 64;
+constexpr int PART = 2 * MAX_DIM;     // per-CTA partials: sum[64], sumsq[64]
+
+struct Stats {
+  double* mean; double* var; double* count;
+  int dim; int variant;
+};
+
+struct WriteArgs {
+  const float* obs; const float* mu; const float* value; const float* log_std; const float* noise; const float* rew;
+  const long long* dones;
+  float* obses; float* actions; float* mus; float* values; float* rewards; float* dones_f; float* neglogp; float* actions_out;
+  int n; float reward_scale;
+  Stats st; int has_stats;
+  double* partials; unsigned int* ticket;
+};
+
+// fold of a whole batch (n samples, shifted sums S1 = sum(x - shift), S2 = sum((x - shift)^2)) into the running statistics
+__device__ __forceinline__ void fold(const Stats& st, int c, double shift, double S1, double S2, double n) {
+  const double mean_b = shift + S1 / n;
+  const double var_b = n > 1.0 ? (S2 - S1 * S1 / n) / (n - 1.0) : 0.0;      // torch.var: unbiased
+  const double mean = st.mean[c], var = st.var[c], count = st.count[0];
+  const double delta = mean_b - mean, tot = count + n;
+  st.mean[c] = mean + delta * n / tot;
+  st.var[c] = (var * count + var_b * n + delta * delta * count * n / tot) / tot;
+}
+
+// block-level meeting point of the per-thread moments: thread tid owns channels 4 (tid % 16) .. +3
+__device__ __forceinline__ void cta_moments(const float s1[4], const float s2[4], double* sm /* [16 warps][16 quads][8] */, double* out /* [PART] */) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double v[8];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { v[k] = (double)s1[k]; v[4 + k] = (double)s2[k]; }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) v[k] += __shfl_xor_sync(0xffffffffu, v[k], 16);      // lanes l and l+16 share a channel quad
+  if (lane < 16) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sm[(warp * 16 + lane) * 8 + k] = v[k];
+  }
+  __syncthreads();
+  if (tid < PART) {                    // tid = which * 64 + channel
+    const int which = tid >> 6, c = tid & 63, quad = c >> 2, k = (c & 3) + 4 * which;
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < THREADS / 32; ++w) s += sm[(w * 16 + quad) * 8 + k];
+    out[tid] = s;
+  }
+}
+
+// last-CTA pattern: returns true in exactly one CTA, after every CTA's partials are visible
+__device__ __forceinline__ bool last_cta(unsigned int* ticket) {
+  __shared__ unsigned int s_last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int t = atomicAdd(ticket, 1u);
+    s_last = (t == gridDim.x - 1) ? 1u : 0u;
+    if (s_last) { *ticket = 0u; __threadfence(); }
+  }
+  __syncthreads();
+  return s_last != 0u;
+}
+
+// grid-wide sum of partials[cta][PART] -> sm_tot[PART] (deterministic order), by the last CTA
+__device__ __forceinline__ void grid_moments(const double* partials, double* sm /* >= 4 * PART */, double* sm_tot) {
+  const int tid = threadIdx.x, sub = tid >> 7, j = tid & (PART - 1);       // 4 subsets of CTAs x 128 values
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  int cta = sub;
+  for (; cta + 12 < (int)gridDim.x; cta += 16) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) acc[u] += __ldcg(partials + (size_t)(cta + 4 * u) * PART + j);
+  }
+  for (; cta < (int)gridDim.x; cta += 4) acc[0] += __ldcg(partials + (size_t)cta * PART + j);
+  sm[sub * PART + j] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+  __syncthreads();
+  if (tid < PART) sm_tot[tid] = (sm[tid] + sm[PART + tid]) + (sm[2 * PART + tid] + sm[3 * PART + tid]);
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(THREADS, 1) k_rollout_write(const WriteArgs a) {
+  __shared__ double sm[16 * 16 * 8];
+  __shared__ double sm_tot[PART];
+  const int tid = threadIdx.x;
+  const size_t gtid = (size_t)blockIdx.x * THREADS + tid, gstride = (size_t)gridDim.x * THREADS;
+  pdl_launch_dependents();
+  pdl_wait();
+  // ---- phase A: observations -> obses[t]; per-channel shifted moments
+  {
+    const int c4 = tid & 15;
+    float shift[4] = {0.f, 0.f, 0.f, 0.f};
+    if (a.has_stats) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) shift[k] = (float)a.st.mean[4 * c4 + k];
+    }
+    float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+    const size_t total = (size_t)a.n * 16;
+    const float4* src = reinterpret_cast<const float4*>(a.obs);
+    float4* dst = reinterpret_cast<float4*>(a.obses);
+    size_t i = gtid;
+    for (; i + 3 * gstride < total; i += 4 * gstride) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = ld_nc_f4(reinterpret_cast<const float*>(src + i + u * gstride));
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        __stcs(dst + i + u * gstride, v[u]);
+        const float d[4] = {v[u].x - shift[0], v[u].y - shift[1], v[u].z - shift[2], v[u].w - shift[3]};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { s1[k] += d[k]; s2[k] = fmaf(d[k], d[k], s2[k]); }
+      }
+    }
+    for (; i < total; i += gstride) {
+      const float4 v = ld_nc_f4(reinterpret_cast<const float*>(src + i));
+      __stcs(dst + i, v);
+      const float d[4] = {v.x - shift[0], v.y - shift[1], v.z - shift[2], v.w - shift[3]};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { s1[k] += d[k]; s2[k] = fmaf(d[k], d[k], s2[k]); }
+    }
+    if (a.has_stats) cta_moments(s1, s2, sm, a.partials + (size_t)blockIdx.x * PART);
+  }
+  // ---- phase B: per env: action sample, negative log-prob, scalar columns
+  {
+    float sigma[12], logstd_sum = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 12; ++k) {
+      const float ls = a.log_std[k];
+      sigma[k] = (float)exp((double)ls);     // correctly rounded; torch's exp is within 1 ulp of it
+      logstd_sum += ls;
+    }
+    for (size_t e = gtid; e < (size_t)a.n; e += gstride) {
+      float m[12], z[12], act[12];
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        const float4 mv = ld_nc_f4(a.mu + e * 12 + 4 * q);
+        m[4 * q] = mv.x; m[4 * q + 1] = mv.y; m[4 * q + 2] = mv.z; m[4 * q + 3] = mv.w;
+        if (a.noise) {
+          const float4 nv = ld_nc_f4(a.noise + e * 12 + 4 * q);
+          z[4 * q] = nv.x; z[4 * q + 1] = nv.y; z[4 * q + 2] = nv.z; z[4 * q + 3] = nv.w;
+        } else {
+          z[4 * q] = z[4 * q + 1] = z[4 * q + 2] = z[4 * q + 3] = 0.0f;
+        }
+      }
+      float ss = 0.0f;
+#pragma unroll
+      for (int k = 0; k < 12; ++k) {
+        act[k] = add(mul(z[k], sigma[k]), m[k]);                  // torch.normal: randn * std + mean
+        const float u = fdiv(sub(act[k], m[k]), sigma[k]);
+        ss += u * u;
+      }
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        const float4 av = make_float4(act[4 * q], act[4 * q + 1], act[4 * q + 2], act[4 * q + 3]);
+        const float4 mv = make_float4(m[4 * q], m[4 * q + 1], m[4 * q + 2], m[4 * q + 3]);
+        __stcs(reinterpret_cast<float4*>(a.actions + e * 12) + q, av);
+        __stcs(reinterpret_cast<float4*>(a.mus + e * 12) + q, mv);
+        if (a.actions_out) reinterpret_cast<float4*>(a.actions_out + e * 12)[q] = av;
+      }
+      a.neglogp[e] = 0.5f * ss + 11.027262398456072f + logstd_sum;      // 0.5 log(2 pi) * 12
+      a.values[e] = a.value[e];
+      a.rewards[e] = mul(a.rew[e], a.reward_scale);
+      a.dones_f[e] = a.dones[e] != 0 ? 1.0f : 0.0f;
+    }
+  }
+  // ---- fold the batch into the running statistics (last CTA)
+  if (a.has_stats && last_cta(a.ticket)) {
+    grid_moments(a.partials, sm, sm_tot);
+    if (tid < a.st.dim) fold(a.st, tid, (double)(float)a.st.mean[tid], sm_tot[tid], sm_tot[MAX_DIM + tid], (double)a.n);
+    __syncthreads();
+    if (tid == 0) a.st.count[0] += (double)a.n;
+  }
+}
+
+// stand-alone fold of x [n, dim] (dim = 1 or a multiple of 4, <= 64)
+__global__ void __launch_bounds__(THREADS, 1) k_rms_update(const float* __restrict__ x, long long n, Stats st, double* partials, unsigned int* ticket) {
+  __shared__ double sm[16 * 16 * 8];
+  __shared__ double sm_tot[PART];
+  const int tid = threadIdx.x;
+  const size_t gtid = (size_t)blockIdx.x * THREADS + tid, gstride = (size_t)gridDim.x * THREADS;
+  float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+  if (st.dim == 1) {
+    // scalar column: every thread sums into "channel 0" of its quad; the quads are merged below
+    const float shift = (float)st.mean[0];
+    for (size_t i = gtid; i < (size_t)n; i += gstride) {
+      const float d = x[i] - shift;
+      s1[0] += d; s2[0] = fmaf(d, d, s2[0]);
+    }
+  } else {
+    // dim = 4 q: float4 index i covers channels 4 (i % q) ..; THREADS and the grid stride are multiples of 16 only, so the quad of a
+    // thread changes from iteration to iteration unless q divides the stride: walk rows instead (thread -> fixed quad, rows strided)
+    const int q = st.dim >> 2;
+    const int quad = (int)(gtid % q);
+    float shift[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) shift[k] = (float)st.mean[4 * quad + k];
+    const size_t rows_per_pass = gstride / q;       // threads [0, rows_per_pass * q) are active
+    if (gtid < rows_per_pass * q) {
+      for (size_t row = gtid / q; row < (size_t)n; row += rows_per_pass) {
+        const float4 v = ld_nc_f4(x + (row * q + quad) * 4);
+        const float d[4] = {v.x - shift[0], v.y - shift[1], v.z - shift[2], v.w - shift[3]};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { s1[k] += d[k]; s2[k] = fmaf(d[k], d[k], s2[k]); }
+      }
+    }
+    // move the sums to the slot of the thread's quad: cta_moments() keys on tid % 16, so publish through shared memory instead
+    __shared__ double qsum[16][8];
+    if (tid < 16 * 8) qsum[tid >> 3][tid & 7] = 0.0;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      atomicAdd(&qsum[quad][k], (double)s1[k]);       // shared-memory fp64 atomics: order-dependent only below 1e-16 relative
+      atomicAdd(&qsum[quad][4 + k], (double)s2[k]);
+    }
+    __syncthreads();
+    if (tid < PART) {
+      const int which = tid >> 6, c = tid & 63;
+      partials[(size_t)blockIdx.x * PART + tid] = (c >> 2) < q ? qsum[c >> 2][(c & 3) + 4 * which] : 0.0;
+    }
+  }
+  if (st.dim == 1) {
+    double v1 = (double)s1[0], v2 = (double)s2[0];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) { v1 += __shfl_xor_sync(0xffffffffu, v1, off); v2 += __shfl_xor_sync(0xffffffffu, v2, off); }
+    if ((tid & 31) == 0) { sm[(tid >> 5) * 2] = v1; sm[(tid >> 5) * 2 + 1] = v2; }
+    __syncthreads();
+    if (tid < PART) {
+      double s = 0.0;
+      if (tid == 0 || tid == MAX_DIM) {
+        for (int w = 0; w < THREADS / 32; ++w) s += sm[w * 2 + (tid == 0 ? 0 : 1)];
+      }
+      partials[(size_t)blockIdx.x * PART + tid] = s;
+    }
+  }
+  if (last_cta(ticket)) {
+    grid_moments(partials, sm, sm_tot);
+    if (tid < st.dim) fold(st, tid, (double)(float)st.mean[tid], sm_tot[tid], sm_tot[MAX_DIM + tid], (double)n);
+    __syncthreads();
+    if (tid == 0) st.count[0] += (double)n;
+  }
+}
+
+__global__ void k_rms_export(Stats st, float* __restrict__ mean_f32, float* __restrict__ inv_std_f32) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= st.dim) return;
+  mean_f32[c] = (float)st.mean[c];
+  const float var = (float)st.var[c];
+  // rl_games RunningMeanStd: / sqrt(var.float() + 1e-5);  skrl RunningStandardScaler: / (sqrt(var.float()) + 1e-8)
+  inv_std_f32[c] = st.variant == LM_RMS_RLGAMES ? fdiv(1.0f, __fsqrt_rn(add(var, 1e-5f))) : fdiv(1.0f, add(__fsqrt_rn(var), 1e-8f));
+}
+
+}  // namespace rollout
+}  // namespace lm
+
+using namespace lm;
+using namespace lm::rollout;
+
+struct LmRollout {
+  int device;
+  int sm_count;
+  double* partials;        // [sm_count][PART]
+  unsigned int* ticket;
+};
+
+static int check_stats(const LmRunningStats* s, const char* who) {
+  if (!s->mean || !s->var || !s->count) return lm_fail(LM_ERR_BAD_ARG, "%s: NULL running statistics", who);
+  if (!(s->dim == 1 || (s->dim % 4 == 0 && s->dim >= 4 && s->dim <= MAX_DIM))) return lm_fail(LM_ERR_BAD_ARG, "%s: dim must be 1 or a multiple of 4 <= 64", who);
+  if (s->variant != LM_RMS_RLGAMES && s->variant != LM_RMS_SKRL) return lm_fail(LM_ERR_BAD_ARG, "%s: unknown variant", who);
+  return LM_OK;
+}
+
+extern "C" {
+
+LmRollout* lm_rollout_create(int device) {
+  cudaDeviceProp prop;
+  cudaError_t e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) { lm_set_error("lm_rollout_create: %s", cudaGetErrorString(e)); return nullptr; }
+  if (prop.major != 10) { lm_set_error("lm_rollout_create: library is sm_100a only (device sm_%d%d)", prop.major, prop.minor); return nullptr; }
+  cudaSetDevice(device);
+  LmRollout* r = new LmRollout();
+  r->device = device; r->sm_count = prop.multiProcessorCount; r->partials = nullptr; r->ticket = nullptr;
+  if (cudaMalloc(&r->partials, (size_t)r->sm_count * PART * sizeof(double)) != cudaSuccess ||
+      cudaMalloc(&r->ticket, sizeof(unsigned int)) != cudaSuccess) {
+    lm_set_error("lm_rollout_create: cudaMalloc failed");
+    cudaFree(r->partials); delete r; return nullptr;
+  }
+  cudaMemset(r->ticket, 0, sizeof(unsigned int));
+  return r;
+}
+
+void lm_rollout_destroy(LmRollout* r) {
+  if (!r) return;
+  cudaFree(r->partials); cudaFree(r->ticket);
+  delete r;
+}
+
+int lm_rollout_write(LmRollout* r, const LmRolloutStep* step, const LmRolloutBuffers* buf, int32_t t, float* actions_out,
+                     const LmRunningStats* obs_stats, void* stream) {
+  if (!r || !step || !buf) return lm_fail(LM_ERR_BAD_ARG, "lm_rollout_write: NULL argument");
+  if (!step->obs || !step->mu || !step->value || !step->log_std || !step->rew || !step->dones) return lm_fail(LM_ERR_BAD_ARG, "lm_rollout_write: NULL step tensor");
+  if (!buf->obses || !buf->actions || !buf->mus || !buf->values || !buf->rewards || !buf->dones || !buf->neglogp) return lm_fail(LM_ERR_BAD_ARG, "lm_rollout_write: NULL rollout buffer");
+  if (buf->num_envs <= 0 || t < 0 || t >= buf->horizon) return lm_fail(LM_ERR_BAD_ARG, "lm_rollout_write: t = %d outside [0, %d)", t, buf->horizon);
+  if ((((uintptr_t)step->obs) | ((uintptr_t)step->mu) | ((uintptr_t)step->noise) | ((uintptr_t)buf->obses) | ((uintptr_t)buf->actions) | ((uintptr_t)buf->mus) |
+       ((uintptr_t)actions_out)) & 15)
+    return lm_fail(LM_ERR_ALIGNMENT, "lm_rollout_write: obs / mu / noise / obses / actions / mus must be 16-byte aligned");
+  if (obs_stats) {
+    const int rc = check_stats(obs_stats, "lm_rollout_write");
+    if (rc != LM_OK) return rc;
+    if (obs_stats->dim != 64) return lm_fail(LM_ERR_BAD_ARG, "lm_rollout_write: observation statistics must have dim 64");
+  }
+  const size_t n = (size_t)buf->num_envs;
+  WriteArgs a;
+  a.obs = step->obs; a.mu = step->mu; a.value = step->value; a.log_std = step->log_std; a.noise = step->noise; a.rew = step->rew;
+  a.dones = reinterpret_cast<const long long*>(step->dones);
+  a.obses = buf->obses + (size_t)t * n * 64; a.actions = buf->actions + (size_t)t * n * 12; a.mus = buf->mus + (size_t)t * n * 12;
+  a.values = buf->values + (size_t)t * n; a.rewards = buf->rewards + (size_t)t * n; a.dones_f = buf->dones + (size_t)t * n;
+  a.neglogp = buf->neglogp + (size_t)t * n; a.actions_out = actions_out;
+  a.n = buf->num_envs; a.reward_scale = buf->reward_scale;
+  a.has_stats = obs_stats ? 1 : 0;
+  if (obs_stats) a.st = Stats{obs_stats->mean, obs_stats->var, obs_stats->count, obs_stats->dim, obs_stats->variant};
+  else a.st = Stats{nullptr, nullptr, nullptr, 0, 0};
+  a.partials = r->partials; a.ticket = r->ticket;
+  const size_t work = (n * 16 + THREADS - 1) / THREADS;
+  const int grid = (int)(work < (size_t)r->sm_count ? work : (size_t)r->sm_count);
+  cudaError_t le = lm_launch(k_rollout_write, dim3(grid), dim3(THREADS), 0, (cudaStream_t)stream, true, a);
+  if (le != cudaSuccess) return lm_fail((int)le, "lm_rollout_write: %s", cudaGetErrorString(le));
+  return lm_check_launch("lm_rollout_write");
+}
+
+int lm_rms_update(LmRollout* r, const float* x, int64_t n, const LmRunningStats* stats, void* stream) {
+  if (!r || !x || !stats || n <= 0) return lm_fail(LM_ERR_BAD_ARG, "lm_rms_update: bad argument");
+  const int rc = check_stats(stats, "lm_rms_update");
+  if (rc != LM_OK) return rc;
+  if (stats->dim > 1 && (((uintptr_t)x) & 15)) return lm_fail(LM_ERR_ALIGNMENT, "lm_rms_update: x must be 16-byte aligned");
+  const size_t items = stats->dim == 1 ? (size_t)n : (size_t)n * (stats->dim / 4);
+  const size_t work = (items + THREADS - 1) / THREADS;
+  const int grid = (int)(work < (size_t)r->sm_count ? work : (size_t)r->sm_count);
+  Stats st{stats->mean, stats->var, stats->count, stats->dim, stats->variant};
+  k_rms_update<<<grid, THREADS, 0, (cudaStream_t)stream>>>(x, (long long)n, st, r->partials, r->ticket);
+  return lm_check_launch("lm_rms_update");
+}
+
+int lm_rms_export(const LmRunningStats* stats, float* mean_f32, float* inv_std_f32, void* stream) {
+  if (!stats || !mean_f32 || !inv_std_f32) return lm_fail(LM_ERR_BAD_ARG, "lm_rms_export: NULL argument");
+  const int rc = check_stats(stats, "lm_rms_export");
+  if (rc != LM_OK) return rc;
+  Stats st{stats->mean, stats->var, stats->count, stats->dim, stats->variant};
+  k_rms_export<<<1, 64, 0, (cudaStream_t)stream>>>(st, mean_f32, inv_std_f32);
+  return lm_check_launch("lm_rms_export");
+}
+
+}  // extern "C"

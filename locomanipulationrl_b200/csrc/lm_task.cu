@@ -1199,6 +1199,9 @@ int lm_struct_size(int which) {
     case 2: return (int)sizeof(LmTaskBuffers);
     case 3: return (int)sizeof(LmHostStep);
     case 4: return (int)sizeof(LmPdState);
+    case 5: return (int)sizeof(LmRunningStats);
+    case 6: return (int)sizeof(LmRolloutStep);
+    case 7: return (int)sizeof(LmRolloutBuffers);
     default: return -1;
   }
 }

@@ -1,0 +1,105 @@
+"""Rollout buffers and running mean/std on the GPU (csrc/lm_rollout.cu): the caller-side formats around the task/policy path.
+
+Names follow rl_games 1.6.0 (``ExperienceBuffer.tensor_dict`` keys, ``RunningMeanStd`` buffers ``running_mean`` /
+``running_var`` / ``count``) so that its PPO update can read the tensors unchanged; ``variant="skrl"`` switches the
+normaliser to skrl's ``RunningStandardScaler`` form.  Buffers are time-major ``[T, N, ...]``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import torch
+
+from . import _lib
+
+RLGAMES, SKRL = 0, 1
+
+
+def _handle(device: torch.device):
+    if device.type != "cuda" or not torch.cuda.is_available():
+        raise _lib.LmError("rollout kernels need a CUDA device (no CPU fallback)")
+    lib = _lib.load()
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    h = lib.lm_rollout_create(idx)
+    if not h:
+        raise _lib.LmError(f"lm_rollout_create failed: {lib.lm_last_error().decode()}")
+    return lib, h
+
+
+class RunningMeanStd:
+    """float64 running mean / variance / count, updated by ``lm_rms_update`` (or fused into ``RolloutBuffer.write``)."""
+
+    def __init__(self, dim: int, device="cuda:0", variant: int = RLGAMES):
+        self.device = torch.device(device)
+        self.dim, self.variant = int(dim), int(variant)
+        self.running_mean = torch.zeros(dim, dtype=torch.float64, device=self.device)
+        self.running_var = torch.ones(dim, dtype=torch.float64, device=self.device)
+        self.count = torch.ones((), dtype=torch.float64, device=self.device)
+        self._mean32 = torch.zeros(dim, dtype=torch.float32, device=self.device)
+        self._inv_std32 = torch.ones(dim, dtype=torch.float32, device=self.device)
+        self._lib, self._h = None, None
+
+    def c_struct(self) -> _lib.LmRunningStats:
+        return _lib.LmRunningStats(self.running_mean.data_ptr(), self.running_var.data_ptr(), self.count.data_ptr(), self.dim, self.variant)
+
+    def update(self, x: torch.Tensor) -> None:
+        if self._h is None:
+            self._lib, self._h = _handle(self.device)
+        x = x.to(self.device, dtype=torch.float32).contiguous()
+        n = x.numel() // self.dim
+        st = self.c_struct()
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(self._lib.lm_rms_update(self._h, x.data_ptr(), n, C.byref(st), stream), "lm_rms_update")
+
+    def export(self):
+        """(mean, inv_std) fp32 vectors in the form ``lm_mlp_forward`` takes."""
+        lib = _lib.load()
+        st = self.c_struct()
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(lib.lm_rms_export(C.byref(st), self._mean32.data_ptr(), self._inv_std32.data_ptr(), stream), "lm_rms_export")
+        return self._mean32, self._inv_std32
+
+    def __del__(self):
+        try:
+            if self._h:
+                self._lib.lm_rollout_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+
+class RolloutBuffer:
+    """Time-major rollout storage written by ONE kernel launch per env step."""
+
+    def __init__(self, horizon: int, num_envs: int, device="cuda:0", reward_scale: float = 1.0):
+        self.device = torch.device(device)
+        self.horizon, self.num_envs, self.reward_scale = int(horizon), int(num_envs), float(reward_scale)
+        T, N, d = self.horizon, self.num_envs, self.device
+        self.tensor_dict: Dict[str, torch.Tensor] = {
+            "obses": torch.zeros(T, N, 64, device=d), "actions": torch.zeros(T, N, 12, device=d), "mus": torch.zeros(T, N, 12, device=d),
+            "values": torch.zeros(T, N, device=d), "rewards": torch.zeros(T, N, device=d), "dones": torch.zeros(T, N, device=d),
+            "neglogpacs": torch.zeros(T, N, device=d)}
+        self._lib, self._h = _handle(self.device)
+        td = self.tensor_dict
+        self._buf = _lib.LmRolloutBuffers(td["obses"].data_ptr(), td["actions"].data_ptr(), td["mus"].data_ptr(), td["values"].data_ptr(),
+                                          td["rewards"].data_ptr(), td["dones"].data_ptr(), td["neglogpacs"].data_ptr(), T, N, self.reward_scale)
+
+    def write(self, t: int, obs, mu, value, log_std, rew, dones, noise: Optional[torch.Tensor] = None,
+              actions_out: Optional[torch.Tensor] = None, obs_stats: Optional[RunningMeanStd] = None) -> None:
+        """Slot ``t`` <- this step.  ``noise`` = standard-normal draws [N,12] of the caller's generator (None: act = mu);
+        ``actions_out`` receives the sampled actions for the next ``pre_physics_step``."""
+        step = _lib.LmRolloutStep(_lib.ptr(obs), _lib.ptr(mu), _lib.ptr(value), _lib.ptr(log_std), _lib.ptr(noise), _lib.ptr(rew), _lib.ptr(dones))
+        st = obs_stats.c_struct() if obs_stats is not None else None
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        rc = self._lib.lm_rollout_write(self._h, C.byref(step), C.byref(self._buf), int(t), _lib.ptr(actions_out),
+                                        C.byref(st) if st is not None else None, stream)
+        _lib.check(rc, "lm_rollout_write")
+
+    def __del__(self):
+        try:
+            if self._h:
+                self._lib.lm_rollout_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
