@@ -210,31 +210,44 @@ class Pipeline:
         self.norm_inv_std = torch.ones(64, device=device)
         self.graphs = None
         self.gae_buf = None
-        if self.w["policy"] == "gnn":
-            T = HORIZON
-            self.gae_buf = dict(r=torch.zeros(T, n, device=device), v=torch.zeros(T, n, device=device), d=torch.zeros(T, n, device=device),
-                                adv=torch.zeros(T, n, device=device), ret=torch.zeros(T, n, device=device))
+        self.actions = self.mu                          # MLP workload: the policy mean is the next action
         # kernels of liblm_b200.so per step: k_pre, k_post_lean, policy forward (k_reset_count only runs when reset_buf was
-        # written from outside; lm_gae once per HORIZON steps in the gnn_gae workload)
+        # written from outside); the gnn_gae workload adds k_rollout_write every step and lm_gae once per HORIZON steps
         self.launches_per_step = 3
+        if self.w["policy"] == "gnn":
+            from locomanipulationrl_b200.rollout import RolloutBuffer, RunningMeanStd
+            T = HORIZON
+            self.rollout = RolloutBuffer(T, n, device=device, reward_scale=0.01)
+            self.obs_stats = RunningMeanStd(64, device=device)
+            self.log_std = self.policy.log_std_parameter.detach()
+            self.actions = torch.zeros(n, 12, device=device)
+            self.gae_buf = dict(adv=torch.zeros(T, n, device=device), ret=torch.zeros(T, n, device=device))
+            self.launches_per_step = 4
 
     def step_eager(self, i, t=0):
         task = self.task
-        task.pre_physics_step(self.mu, self.uniforms[i])
+        task.pre_physics_step(self.actions, self.uniforms[i])
         task.set_up_scene(self.scenes[i])               # "physics": the next state set becomes the live views
         task.post_physics_step()
         if self.w["policy"] == "mlp":
             self.policy(task.obs_buf, norm_mean=self.norm_mean, norm_inv_std=self.norm_inv_std, out=(self.mu, self.value))
         else:
             self.policy(task.obs_buf, out=(self.mu, self.value))
-            b = self.gae_buf
             k = t % HORIZON
-            b["r"][k].copy_(task.rew_buf); b["v"][k].copy_(self.value.view(-1)); b["d"][k].copy_(task.reset_buf)
+            self.rollout_step(k)
             if k == HORIZON - 1:
+                b, td = self.gae_buf, self.rollout.tensor_dict
                 s = torch.cuda.current_stream().cuda_stream
-                self._lib_mod.check(self.lib.lm_gae(b["r"].data_ptr(), b["v"].data_ptr(), b["d"].data_ptr(), b["v"][-1].data_ptr(),
-                                                    b["d"][-1].data_ptr(), b["adv"].data_ptr(), b["ret"].data_ptr(), HORIZON, self.n,
+                self._lib_mod.check(self.lib.lm_gae(td["rewards"].data_ptr(), td["values"].data_ptr(), td["dones"].data_ptr(), td["values"][-1].data_ptr(),
+                                                    td["dones"][-1].data_ptr(), b["adv"].data_ptr(), b["ret"].data_ptr(), HORIZON, self.n,
                                                     0.99, 0.95, 0, s), "lm_gae")
+
+    def rollout_step(self, k):
+        """Slot k of the time-major rollout <- this step (obs, mean action, value, shaped reward, done, neglogp), observation
+        statistics folded in, actions handed to the next pre_physics_step: one launch (lm_rollout_write)."""
+        task = self.task
+        self.rollout.write(k, task.obs_buf, self.mu, self.value, self.log_std, task.rew_buf, task.reset_buf, noise=None,
+                           actions_out=self.actions, obs_stats=self.obs_stats)
 
     def capture(self):
         """One CUDA graph per state set (parity of the action ring alternates, STATE_SETS is even)."""
@@ -374,7 +387,7 @@ def cuda_arm(args):
             task.post_physics_step()
 
         def pre_only(i):
-            task.pre_physics_step(pipe.mu, pipe.uniforms[i % STATE_SETS])
+            task.pre_physics_step(pipe.actions, pipe.uniforms[i % STATE_SETS])
 
         def policy_only(i):
             if pipe.w["policy"] == "mlp":
@@ -433,6 +446,12 @@ def cuda_arm(args):
                                              "unit": "TFLOP/s" if tc else "TFLOP/s (naive FLOP count)", "ms": ms_pol,
                                              "hbm_gbs": n * 308 / (ms_pol * 1e-3) / 1e9}
         line_extra["kernel_ms"] = {"pre": ms_pre, "post": ms_post, "policy": ms_pol}
+        if pipe.w["policy"] == "gnn":
+            ms_ro = graph_time(lambda i: pipe.rollout_step(i % HORIZON))
+            B_RO = 368 + 368 + 48        # obs/mu/value/rew/done in, obses/actions/mus/values/rewards/dones/neglogp out, + actions_out
+            line_extra["roofline_rollout"] = {"kernel": "k_rollout_write", "bound": "hbm", "achieved": n * B_RO / (ms_ro * 1e-3) / 1e9, "peak": hbm,
+                                              "unit": "GB/s", "frac": n * B_RO / (ms_ro * 1e-3) / 1e9 / hbm, "bytes_per_env": B_RO, "ms": ms_ro}
+            line_extra["kernel_ms"]["rollout_write"] = ms_ro
         if world == 1 and not args.no_large:
             line_extra["roofline_large"] = large_roofline(device, graph_time, hbm)
 

@@ -7,7 +7,7 @@
 //     delta = mean_b - mean; tot = count + n; mean += delta n / tot; var = (var count + var_b n + delta^2 count n / tot) / tot
 // where var_b is torch.var's unbiased batch variance.  Restated in oracle/port_policy.py.
 //
-// k_rollout_write: ONE launch per env step, one CTA per SM.  Phase A streams the observation tile [N,64] into obses[t]
+// k_rollout_write: ONE launch per env step, one 1024-thread CTA per SM.  Phase A streams the observation tile [N,64] into obses[t]
 // with 128-bit accesses; thread tid always owns channel quad tid % 16, so the per-channel moments (shifted by the current
 // running mean against cancellation) accumulate in registers, meet per CTA in shared memory as doubles and per grid through
 // the last-CTA pattern, where 64 threads apply the fold.  Phase B is per env: sample the action, its negative log-prob,
@@ -18,7 +18,7 @@
 namespace lm {
 namespace rollout {
 
-constexpr int THREADS = 512;
+constexpr int THREADS = 1024;
 constexpr int MAX_DIM = 64;
 constexpr int PART = 2 * MAX_DIM;     // per-CTA partials: sum[64], sumsq[64]
 
@@ -47,7 +47,7 @@ __device__ __forceinline__ void fold(const Stats& st, int c, double shift, doubl
 }
 
 // block-level meeting point of the per-thread moments: thread tid owns channels 4 (tid % 16) .. +3
-__device__ __forceinline__ void cta_moments(const float s1[4], const float s2[4], double* sm /* [16 warps][16 quads][8] */, double* out /* [PART] */) {
+__device__ __forceinline__ void cta_moments(const float s1[4], const float s2[4], double* sm /* [THREADS/32 warps][16 quads][8] */, double* out /* [PART] */) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   double v[8];
 #pragma unroll
@@ -84,26 +84,82 @@ __device__ __forceinline__ bool last_cta(unsigned int* ticket) {
 
 // grid-wide sum of partials[cta][PART] -> sm_tot[PART] (deterministic order), by the last CTA
 __device__ __forceinline__ void grid_moments(const double* partials, double* sm /* >= 4 * PART */, double* sm_tot) {
-  const int tid = threadIdx.x, sub = tid >> 7, j = tid & (PART - 1);       // 4 subsets of CTAs x 128 values
+  constexpr int SUB = THREADS / PART;                                      // 8 subsets of CTAs x 128 values
+  constexpr int MAXC = 24;                                                 // loads per thread, all in flight: grids up to 192 CTAs
+  const int tid = threadIdx.x, sub = tid / PART, j = tid & (PART - 1);
   double acc[4] = {0.0, 0.0, 0.0, 0.0};
-  int cta = sub;
-  for (; cta + 12 < (int)gridDim.x; cta += 16) {
+  for (int c0 = sub; c0 < (int)gridDim.x; c0 += SUB * MAXC) {
+    double v[MAXC];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) acc[u] += __ldcg(partials + (size_t)(cta + 4 * u) * PART + j);
+    for (int u = 0; u < MAXC; ++u) {
+      const int cta = c0 + SUB * u;
+      v[u] = cta < (int)gridDim.x ? __ldcg(partials + (size_t)cta * PART + j) : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < MAXC; ++u) acc[u & 3] += v[u];
   }
-  for (; cta < (int)gridDim.x; cta += 4) acc[0] += __ldcg(partials + (size_t)cta * PART + j);
   sm[sub * PART + j] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
   __syncthreads();
-  if (tid < PART) sm_tot[tid] = (sm[tid] + sm[PART + tid]) + (sm[2 * PART + tid] + sm[3 * PART + tid]);
+  if (tid < PART) {
+    double s = 0.0;
+#pragma unroll
+    for (int u = 0; u < SUB; ++u) s += sm[u * PART + tid];
+    sm_tot[tid] = s;
+  }
   __syncthreads();
 }
 
+struct EnvIn { float4 mv[3], nv[3]; float val, rw; long long dn; };
+__device__ __forceinline__ EnvIn env_load(const WriteArgs& a, unsigned int e) {
+  EnvIn in;
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    in.mv[q] = __ldg(reinterpret_cast<const float4*>(a.mu + e * 12) + q);            // rows are 48 B: let L1 keep the shared sectors
+    in.nv[q] = a.noise ? __ldg(reinterpret_cast<const float4*>(a.noise + e * 12) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  in.val = a.value[e]; in.rw = a.rew[e]; in.dn = a.dones[e];
+  return in;
+}
+__device__ __forceinline__ void env_emit(const WriteArgs& a, unsigned int e, const EnvIn& in, const float* s_sigma, float lsum) {
+  float ss = 0.0f;
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    const float4 sg = *reinterpret_cast<const float4*>(&s_sigma[4 * q]);
+    const float m[4] = {in.mv[q].x, in.mv[q].y, in.mv[q].z, in.mv[q].w}, z[4] = {in.nv[q].x, in.nv[q].y, in.nv[q].z, in.nv[q].w};
+    const float sgm[4] = {sg.x, sg.y, sg.z, sg.w};
+    float act[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      act[k] = add(mul(z[k], sgm[k]), m[k]);                    // torch.normal: randn * std + mean
+      const float u = fdiv(sub(act[k], m[k]), sgm[k]);          // the libraries divide: ((x - mean) / std)^2
+      ss += u * u;
+    }
+    const float4 av = make_float4(act[0], act[1], act[2], act[3]);
+    __stcs(reinterpret_cast<float4*>(a.actions + e * 12) + q, av);
+    __stcs(reinterpret_cast<float4*>(a.mus + e * 12) + q, in.mv[q]);
+    if (a.actions_out) reinterpret_cast<float4*>(a.actions_out + e * 12)[q] = av;
+  }
+  a.neglogp[e] = 0.5f * ss + 11.027262398456072f + lsum;      // 0.5 log(2 pi) * 12
+  a.values[e] = in.val;
+  a.rewards[e] = mul(in.rw, a.reward_scale);
+  a.dones_f[e] = in.dn != 0 ? 1.0f : 0.0f;
+}
+
 __global__ void __launch_bounds__(THREADS, 1) k_rollout_write(const WriteArgs a) {
-  __shared__ double sm[16 * 16 * 8];
+  __shared__ double sm[(THREADS / 32) * 16 * 8];
   __shared__ double sm_tot[PART];
   const int tid = threadIdx.x;
-  const size_t gtid = (size_t)blockIdx.x * THREADS + tid, gstride = (size_t)gridDim.x * THREADS;
+  const unsigned int gtid = blockIdx.x * THREADS + tid, gstride = gridDim.x * THREADS;     // n <= 2^27 (host check): 32-bit indices
+  __shared__ __align__(16) float s_sigma[12];
+  __shared__ float s_lsum;
   pdl_launch_dependents();
+  if (tid < 12) s_sigma[tid] = (float)exp((double)a.log_std[tid]);     // correctly rounded; torch's exp is within 1 ulp of it
+  if (tid == 32) {
+    float ls = 0.0f;
+    for (int k = 0; k < 12; ++k) ls += a.log_std[k];
+    s_lsum = ls;
+  }
+  __syncthreads();
   pdl_wait();
   // ---- phase A: observations -> obses[t]; per-channel shifted moments
   {
@@ -114,73 +170,37 @@ __global__ void __launch_bounds__(THREADS, 1) k_rollout_write(const WriteArgs a)
       for (int k = 0; k < 4; ++k) shift[k] = (float)a.st.mean[4 * c4 + k];
     }
     float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
-    const size_t total = (size_t)a.n * 16;
+    const unsigned int total = (unsigned int)a.n * 16u;
     const float4* src = reinterpret_cast<const float4*>(a.obs);
     float4* dst = reinterpret_cast<float4*>(a.obses);
-    size_t i = gtid;
-    for (; i + 3 * gstride < total; i += 4 * gstride) {
-      float4 v[4];
+    constexpr int SLOTS = 8;                     // 65,536 envs on 148 x 1024 threads: 6.9 float4 per thread, all in flight at once
+    for (unsigned int base = gtid; base < total; base += SLOTS * gstride) {
+      float4 v[SLOTS];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) v[u] = ld_nc_f4(reinterpret_cast<const float*>(src + i + u * gstride));
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        __stcs(dst + i + u * gstride, v[u]);
-        const float d[4] = {v[u].x - shift[0], v[u].y - shift[1], v[u].z - shift[2], v[u].w - shift[3]};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) { s1[k] += d[k]; s2[k] = fmaf(d[k], d[k], s2[k]); }
+      for (int u = 0; u < SLOTS; ++u) {
+        const unsigned int i = base + u * gstride;
+        if (i < total) v[u] = ld_nc_f4(reinterpret_cast<const float*>(src + i));
       }
-    }
-    for (; i < total; i += gstride) {
-      const float4 v = ld_nc_f4(reinterpret_cast<const float*>(src + i));
-      __stcs(dst + i, v);
-      const float d[4] = {v.x - shift[0], v.y - shift[1], v.z - shift[2], v.w - shift[3]};
 #pragma unroll
-      for (int k = 0; k < 4; ++k) { s1[k] += d[k]; s2[k] = fmaf(d[k], d[k], s2[k]); }
-    }
-    if (a.has_stats) cta_moments(s1, s2, sm, a.partials + (size_t)blockIdx.x * PART);
-  }
-  // ---- phase B: per env: action sample, negative log-prob, scalar columns
-  {
-    float sigma[12], logstd_sum = 0.0f;
+      for (int u = 0; u < SLOTS; ++u) {
+        const unsigned int i = base + u * gstride;
+        if (i < total) {
+          __stcs(dst + i, v[u]);
+          const float d[4] = {v[u].x - shift[0], v[u].y - shift[1], v[u].z - shift[2], v[u].w - shift[3]};
 #pragma unroll
-    for (int k = 0; k < 12; ++k) {
-      const float ls = a.log_std[k];
-      sigma[k] = (float)exp((double)ls);     // correctly rounded; torch's exp is within 1 ulp of it
-      logstd_sum += ls;
-    }
-    for (size_t e = gtid; e < (size_t)a.n; e += gstride) {
-      float m[12], z[12], act[12];
-#pragma unroll
-      for (int q = 0; q < 3; ++q) {
-        const float4 mv = ld_nc_f4(a.mu + e * 12 + 4 * q);
-        m[4 * q] = mv.x; m[4 * q + 1] = mv.y; m[4 * q + 2] = mv.z; m[4 * q + 3] = mv.w;
-        if (a.noise) {
-          const float4 nv = ld_nc_f4(a.noise + e * 12 + 4 * q);
-          z[4 * q] = nv.x; z[4 * q + 1] = nv.y; z[4 * q + 2] = nv.z; z[4 * q + 3] = nv.w;
-        } else {
-          z[4 * q] = z[4 * q + 1] = z[4 * q + 2] = z[4 * q + 3] = 0.0f;
+          for (int k = 0; k < 4; ++k) { s1[k] += d[k]; s2[k] = fmaf(d[k], d[k], s2[k]); }
         }
       }
-      float ss = 0.0f;
-#pragma unroll
-      for (int k = 0; k < 12; ++k) {
-        act[k] = add(mul(z[k], sigma[k]), m[k]);                  // torch.normal: randn * std + mean
-        const float u = fdiv(sub(act[k], m[k]), sigma[k]);
-        ss += u * u;
-      }
-#pragma unroll
-      for (int q = 0; q < 3; ++q) {
-        const float4 av = make_float4(act[4 * q], act[4 * q + 1], act[4 * q + 2], act[4 * q + 3]);
-        const float4 mv = make_float4(m[4 * q], m[4 * q + 1], m[4 * q + 2], m[4 * q + 3]);
-        __stcs(reinterpret_cast<float4*>(a.actions + e * 12) + q, av);
-        __stcs(reinterpret_cast<float4*>(a.mus + e * 12) + q, mv);
-        if (a.actions_out) reinterpret_cast<float4*>(a.actions_out + e * 12)[q] = av;
-      }
-      a.neglogp[e] = 0.5f * ss + 11.027262398456072f + logstd_sum;      // 0.5 log(2 pi) * 12
-      a.values[e] = a.value[e];
-      a.rewards[e] = mul(a.rew[e], a.reward_scale);
-      a.dones_f[e] = a.dones[e] != 0 ? 1.0f : 0.0f;
     }
+    // phase B's loads for this thread's first env are issued before the CTA-level meeting point of the moments
+    EnvIn in0;
+    const bool have0 = gtid < (unsigned int)a.n;
+    if (have0) in0 = env_load(a, gtid);
+    if (a.has_stats) cta_moments(s1, s2, sm, a.partials + (size_t)blockIdx.x * PART);
+    // ---- phase B: per env: action sample, negative log-prob, scalar columns
+    const float lsum = s_lsum;
+    if (have0) env_emit(a, gtid, in0, s_sigma, lsum);
+    for (unsigned int e = gtid + gstride; e < (unsigned int)a.n; e += gstride) env_emit(a, e, env_load(a, e), s_sigma, lsum);
   }
   // ---- fold the batch into the running statistics (last CTA)
   if (a.has_stats && last_cta(a.ticket)) {
@@ -193,7 +213,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_rollout_write(const WriteArgs a)
 
 // stand-alone fold of x [n, dim] (dim = 1 or a multiple of 4, <= 64)
 __global__ void __launch_bounds__(THREADS, 1) k_rms_update(const float* __restrict__ x, long long n, Stats st, double* partials, unsigned int* ticket) {
-  __shared__ double sm[16 * 16 * 8];
+  __shared__ double sm[(THREADS / 32) * 16 * 8];
   __shared__ double sm_tot[PART];
   const int tid = threadIdx.x;
   const size_t gtid = (size_t)blockIdx.x * THREADS + tid, gstride = (size_t)gridDim.x * THREADS;
@@ -318,6 +338,7 @@ int lm_rollout_write(LmRollout* r, const LmRolloutStep* step, const LmRolloutBuf
   if (!r || !step || !buf) return lm_fail(LM_ERR_BAD_ARG, "lm_rollout_write: NULL argument");
   if (!step->obs || !step->mu || !step->value || !step->log_std || !step->rew || !step->dones) return lm_fail(LM_ERR_BAD_ARG, "lm_rollout_write: NULL step tensor");
   if (!buf->obses || !buf->actions || !buf->mus || !buf->values || !buf->rewards || !buf->dones || !buf->neglogp) return lm_fail(LM_ERR_BAD_ARG, "lm_rollout_write: NULL rollout buffer");
+  if (buf->num_envs > (1 << 27)) return lm_fail(LM_ERR_UNSUPPORTED, "lm_rollout_write: more than 2^27 envs per call");
   if (buf->num_envs <= 0 || t < 0 || t >= buf->horizon) return lm_fail(LM_ERR_BAD_ARG, "lm_rollout_write: t = %d outside [0, %d)", t, buf->horizon);
   if ((((uintptr_t)step->obs) | ((uintptr_t)step->mu) | ((uintptr_t)step->noise) | ((uintptr_t)buf->obses) | ((uintptr_t)buf->actions) | ((uintptr_t)buf->mus) |
        ((uintptr_t)actions_out)) & 15)
