@@ -321,6 +321,41 @@ int lm_rms_update(LmRollout* r, const float* x, int64_t n, const LmRunningStats*
 /* fp32 vectors for lm_mlp_forward(norm_mean, norm_inv_std): mean and the variant's 1/std form. */
 int lm_rms_export(const LmRunningStats* stats, float* mean_f32, float* inv_std_f32, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * PPO update pieces: the loss head and the optimiser step.  Not in the reference repo: rl_games 1.6.0
+ * a2c_continuous.calc_gradients / common_losses (cfg/train/JointLocomanipulationPPO.yaml:52-72: e_clip 0.2, clip_value,
+ * critic_coef 2, entropy_coef 0, bounds_loss_coef 1e-4, grad_norm 1, truncate_grads) and torch.optim.Adam.
+ *
+ * lm_ppo_loss: one pass over a minibatch of B samples.  From the fresh network outputs (mu, value, log_std) and the
+ * stored rollout columns it produces dLoss/dmu [B,12], dLoss/dvalue [B], dLoss/dlog_std [12] and the scalars rl_games
+ * logs, for   loss = mean(a_loss) + 0.5 critic_coef mean(c_loss) - entropy_coef mean(entropy) + bounds_loss_coef mean(b_loss)
+ * The caller back-propagates (grad_mu, grad_value) through its network.  stats[8] = {a_loss, c_loss, b_loss, entropy, kl,
+ * loss, clip fraction, 0}. */
+typedef struct LmPpoBatch {
+  const float* mu;          /* [B,12] fresh policy mean                      */
+  const float* value;       /* [B]    fresh value                            */
+  const float* log_std;     /* [12]   fresh log sigma                        */
+  const float* actions;     /* [B,12] rollout actions                        */
+  const float* old_neglogp; /* [B]                                           */
+  const float* advantages;  /* [B]    (normalised by the caller if it does)  */
+  const float* old_values;  /* [B]                                           */
+  const float* returns;     /* [B]                                           */
+  const float* old_mu;      /* [B,12] for the KL estimate; may be NULL       */
+  const float* old_log_std; /* [12]   for the KL estimate; may be NULL       */
+  int64_t batch;
+  float e_clip; float critic_coef; float entropy_coef; float bounds_loss_coef;
+  int32_t clip_value;       /* rl_games clip_value                           */
+  int32_t pad_;
+} LmPpoBatch;
+int lm_ppo_loss(LmRollout* workspace, const LmPpoBatch* batch, float* grad_mu, float* grad_value, float* grad_log_std,
+                float* stats, void* stream);
+/* torch.nn.utils.clip_grad_norm_(max_norm) (skipped when max_norm <= 0) followed by one torch.optim.Adam step over a flat
+ * fp32 parameter arena (the layout dist.FusedHorizonReducer keeps): grads are first multiplied by grad_scale
+ * (1 / world size after the all-reduce sum).  `step` counts from 1.  One launch; n <= 2^24 parameters. */
+int lm_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                 float beta2, float eps, float weight_decay, int32_t step, float max_grad_norm, float grad_scale,
+                 float* grad_norm_out, void* stream);
+
 /* End-to-end host-buffer entry used by bench.py's e2e leg: one env step with inputs in pinned
  * host memory (state of both robots packed as the LmRobotViews fields, actions, uniforms) and
  * outputs (obs, rew, reset) read back.  Copies run on `stream`; returns after synchronising it. */

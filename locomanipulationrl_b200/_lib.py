@@ -80,6 +80,13 @@ class LmRolloutBuffers(C.Structure):
                [("horizon", _i32), ("num_envs", _i32), ("reward_scale", _f)]
 
 
+class LmPpoBatch(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("mu", "value", "log_std", "actions", "old_neglogp", "advantages", "old_values", "returns",
+                                          "old_mu", "old_log_std")] + \
+               [("batch", _i64), ("e_clip", _f), ("critic_coef", _f), ("entropy_coef", _f), ("bounds_loss_coef", _f),
+                ("clip_value", _i32), ("pad_", _i32)]
+
+
 # name -> (restype, argtypes); every symbol include/lm_b200.h declares
 _vp = C.c_void_p
 SYMBOLS = {
@@ -118,6 +125,8 @@ SYMBOLS = {
     "lm_rollout_write": (C.c_int, [_vp, C.POINTER(LmRolloutStep), C.POINTER(LmRolloutBuffers), _i32, _vp, C.POINTER(LmRunningStats), _vp]),
     "lm_rms_update": (C.c_int, [_vp, _vp, _i64, C.POINTER(LmRunningStats), _vp]),
     "lm_rms_export": (C.c_int, [C.POINTER(LmRunningStats), _vp, _vp, _vp]),
+    "lm_ppo_loss": (C.c_int, [_vp, C.POINTER(LmPpoBatch), _vp, _vp, _vp, _vp, _vp]),
+    "lm_adam_step": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _f, _i32, _f, _f, _vp, _vp]),
     "lm_gae": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _f, _f, _i32, _vp]),
     "lm_gae_env_major": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _f, _f, _i32, _vp]),
     "lm_task_step_host": (C.c_int, [_vp, C.POINTER(LmRobotViews), C.POINTER(LmRobotViews), _vp, C.POINTER(LmTaskBuffers), C.POINTER(LmHostStep), _vp]),
@@ -150,7 +159,7 @@ def load(path: Optional[str] = None) -> C.CDLL:
         fn.argtypes = args
     if lib.lm_abi_version() != 1:
         raise LmError("liblm_b200.so ABI version mismatch")
-    for which, struct in enumerate((LmTaskParams, LmRobotViews, LmTaskBuffers, LmHostStep, LmPdState, LmRunningStats, LmRolloutStep, LmRolloutBuffers)):
+    for which, struct in enumerate((LmTaskParams, LmRobotViews, LmTaskBuffers, LmHostStep, LmPdState, LmRunningStats, LmRolloutStep, LmRolloutBuffers, LmPpoBatch)):
         if lib.lm_struct_size(which) != C.sizeof(struct):
             raise LmError(f"struct layout mismatch for {struct.__name__}: C {lib.lm_struct_size(which)} vs ctypes {C.sizeof(struct)}")
     _lib = lib

@@ -301,6 +301,11 @@ struct LmRollout {
   unsigned int* ticket;
 };
 
+// workspace shared with lm_ppo.cu (partials: sm_count * 128 doubles; ticket: zero between launches)
+void lm_rollout_workspace(LmRollout* r, double** partials, unsigned int** ticket, int* sm_count) {
+  *partials = r->partials; *ticket = r->ticket; *sm_count = r->sm_count;
+}
+
 static int check_stats(const LmRunningStats* s, const char* who) {
   if (!s->mean || !s->var || !s->count) return lm_fail(LM_ERR_BAD_ARG, "%s: NULL running statistics", who);
   if (!(s->dim == 1 || (s->dim % 4 == 0 && s->dim >= 4 && s->dim <= MAX_DIM))) return lm_fail(LM_ERR_BAD_ARG, "%s: dim must be 1 or a multiple of 4 <= 64", who);

@@ -1202,6 +1202,7 @@ int lm_struct_size(int which) {
     case 5: return (int)sizeof(LmRunningStats);
     case 6: return (int)sizeof(LmRolloutStep);
     case 7: return (int)sizeof(LmRolloutBuffers);
+    case 8: return (int)sizeof(LmPpoBatch);
     default: return -1;
   }
 }

@@ -1,0 +1,74 @@
+"""PPO update pieces on the GPU (csrc/lm_ppo.cu): the rl_games loss head in one launch and a fused clip + Adam step.
+
+``PpoLoss`` returns the gradients of the rl_games ``calc_gradients`` loss with respect to the network outputs; the caller
+back-propagates them through its own network (``torch.autograd.backward([mu, value], [grad_mu, grad_value])``).
+``FlatAdam`` steps a flat fp32 parameter arena (the layout ``dist.FusedHorizonReducer`` keeps for the gradient all-reduce).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import torch
+
+from . import _lib
+from .rollout import _handle
+
+
+class PpoLoss:
+    STAT_NAMES = ("a_loss", "c_loss", "b_loss", "entropy", "kl", "loss", "clip_frac")
+
+    def __init__(self, device="cuda:0", e_clip=0.2, critic_coef=2.0, entropy_coef=0.0, bounds_loss_coef=1e-4, clip_value=True):
+        self.device = torch.device(device)
+        self.cfg = dict(e_clip=float(e_clip), critic_coef=float(critic_coef), entropy_coef=float(entropy_coef),
+                        bounds_loss_coef=float(bounds_loss_coef), clip_value=int(bool(clip_value)))
+        self._lib, self._h = _handle(self.device)
+        self.stats = torch.zeros(8, device=self.device)
+        self.grad_log_std = torch.zeros(12, device=self.device)
+
+    def __call__(self, mu, value, log_std, actions, old_neglogp, advantages, old_values, returns, old_mu=None, old_log_std=None,
+                 out: Optional[Dict[str, torch.Tensor]] = None):
+        """All tensors fp32 contiguous on the device.  Returns (grad_mu [B,12], grad_value [B], grad_log_std [12], stats [8])."""
+        Bn = mu.shape[0]
+        grad_mu = out["grad_mu"] if out else torch.empty(Bn, 12, device=self.device)
+        grad_value = out["grad_value"] if out else torch.empty(Bn, device=self.device)
+        p = _lib.ptr
+        b = _lib.LmPpoBatch(p(mu), p(value), p(log_std), p(actions), p(old_neglogp), p(advantages), p(old_values), p(returns),
+                            p(old_mu), p(old_log_std), Bn, self.cfg["e_clip"], self.cfg["critic_coef"], self.cfg["entropy_coef"],
+                            self.cfg["bounds_loss_coef"], self.cfg["clip_value"], 0)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        rc = self._lib.lm_ppo_loss(self._h, C.byref(b), grad_mu.data_ptr(), grad_value.data_ptr(), self.grad_log_std.data_ptr(),
+                                   self.stats.data_ptr(), stream)
+        _lib.check(rc, "lm_ppo_loss")
+        return grad_mu, grad_value, self.grad_log_std, self.stats
+
+    def __del__(self):
+        try:
+            if self._h:
+                self._lib.lm_rollout_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+
+class FlatAdam:
+    """torch.optim.Adam (+ clip_grad_norm_) over one flat fp32 arena; ``params`` / ``grads`` are 1-D views of it."""
+
+    def __init__(self, params: torch.Tensor, lr=3e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, max_grad_norm=1.0):
+        if not params.is_cuda:
+            raise _lib.LmError("FlatAdam runs on CUDA tensors only (no CPU fallback)")
+        self.params = params
+        self.exp_avg = torch.zeros_like(params)
+        self.exp_avg_sq = torch.zeros_like(params)
+        self.lr, self.betas, self.eps, self.weight_decay, self.max_grad_norm = float(lr), betas, float(eps), float(weight_decay), float(max_grad_norm)
+        self.step_count = 0
+        self.grad_norm = torch.zeros(1, device=params.device)
+        self._lib = _lib.load()
+
+    def step(self, grads: torch.Tensor, grad_scale: float = 1.0) -> None:
+        self.step_count += 1
+        stream = torch.cuda.current_stream(self.params.device).cuda_stream
+        rc = self._lib.lm_adam_step(self.params.data_ptr(), grads.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
+                                    self.params.numel(), self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay,
+                                    self.step_count, self.max_grad_norm, float(grad_scale), self.grad_norm.data_ptr(), stream)
+        _lib.check(rc, "lm_adam_step")
