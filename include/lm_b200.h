@@ -356,6 +356,36 @@ int lm_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq,
                  float beta2, float eps, float weight_decay, int32_t step, float max_grad_norm, float grad_scale,
                  float* grad_norm_out, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Observation / action noise: utils/domain_randomization/randomize.py:212-305, applied inside
+ * VecEnvRLGames.step (envs/vec_env_rlgames.py:57-58,70-72).  Per env: a step counter, zeroed on reset; "on_reset" noise is
+ * redrawn for the reset envs, kept in `correlated` [N,dim] and applied to every env every step; "on_interval" noise is
+ * drawn afresh for the envs whose counter reached frequency_interval (which zeroes it).  noise = scale * draw + shift
+ * (exp() of it for loguniform): gaussian draw ~ N(0,1), scale = std, shift = mean; uniform draw ~ U[0,1), scale = hi - lo,
+ * shift = lo; loguniform scale = log hi - log lo, shift = log lo. */
+enum { LM_NOISE_ADDITIVE = 0, LM_NOISE_SCALING = 1 };
+enum { LM_DIST_GAUSSIAN = 0, LM_DIST_UNIFORM = 1, LM_DIST_LOGUNIFORM = 2 };
+typedef struct LmNoiseSpec {
+  int32_t enabled; int32_t operation; int32_t distribution; int32_t frequency_interval;   /* frequency_interval: on_interval only */
+  float scale; float shift;
+} LmNoiseSpec;
+typedef struct LmNoiseState {
+  int32_t* counter;      /* [N]      _observations_counter_buffer / _actions_counter_buffer (randomize.py:185,210) */
+  float* correlated;     /* [N,dim]  _observations_correlated_noise / _actions_correlated_noise (:186,211)          */
+  int32_t num_envs; int32_t dim;   /* dim: a multiple of 4 (64 observations, 12 actions) */
+  LmNoiseSpec on_reset; LmNoiseSpec on_interval;
+} LmNoiseState;
+typedef struct LmNoise LmNoise;
+LmNoise* lm_noise_create(int device);
+void lm_noise_destroy(LmNoise* h);
+/* In place on buffer [N,dim].  draws_reset / draws_interval: rows of N(0,1) (gaussian) or U[0,1) draws from the caller's
+ * generator, or NULL for the kernel's own counter-based generator (Philox4x32-10 keyed by seed, stream position `step`
+ * and the element index: no host synchronisation, no draw tensors in HBM).  compact_draws != 0: row j of a draw tensor
+ * belongs to the j-th affected env in ascending order, as the reference draws them (size (k, dim), randomize.py:265,291);
+ * otherwise row e belongs to env e. */
+int lm_noise_apply(LmNoise* h, const LmNoiseState* state, float* buffer, const int64_t* reset_buf, const float* draws_reset,
+                   const float* draws_interval, int32_t compact_draws, uint64_t seed, uint64_t step, void* stream);
+
 /* End-to-end host-buffer entry used by bench.py's e2e leg: one env step with inputs in pinned
  * host memory (state of both robots packed as the LmRobotViews fields, actions, uniforms) and
  * outputs (obs, rew, reset) read back.  Copies run on `stream`; returns after synchronising it. */

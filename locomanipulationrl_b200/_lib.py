@@ -80,6 +80,15 @@ class LmRolloutBuffers(C.Structure):
                [("horizon", _i32), ("num_envs", _i32), ("reward_scale", _f)]
 
 
+class LmNoiseSpec(C.Structure):
+    _fields_ = [("enabled", _i32), ("operation", _i32), ("distribution", _i32), ("frequency_interval", _i32), ("scale", _f), ("shift", _f)]
+
+
+class LmNoiseState(C.Structure):
+    _fields_ = [("counter", C.c_void_p), ("correlated", C.c_void_p), ("num_envs", _i32), ("dim", _i32),
+                ("on_reset", LmNoiseSpec), ("on_interval", LmNoiseSpec)]
+
+
 class LmPpoBatch(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("mu", "value", "log_std", "actions", "old_neglogp", "advantages", "old_values", "returns",
                                           "old_mu", "old_log_std")] + \
@@ -125,6 +134,9 @@ SYMBOLS = {
     "lm_rollout_write": (C.c_int, [_vp, C.POINTER(LmRolloutStep), C.POINTER(LmRolloutBuffers), _i32, _vp, C.POINTER(LmRunningStats), _vp]),
     "lm_rms_update": (C.c_int, [_vp, _vp, _i64, C.POINTER(LmRunningStats), _vp]),
     "lm_rms_export": (C.c_int, [C.POINTER(LmRunningStats), _vp, _vp, _vp]),
+    "lm_noise_create": (_vp, [C.c_int]),
+    "lm_noise_destroy": (None, [_vp]),
+    "lm_noise_apply": (C.c_int, [_vp, C.POINTER(LmNoiseState), _vp, _vp, _vp, _vp, _i32, C.c_uint64, C.c_uint64, _vp]),
     "lm_ppo_loss": (C.c_int, [_vp, C.POINTER(LmPpoBatch), _vp, _vp, _vp, _vp, _vp]),
     "lm_adam_step": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _f, _i32, _f, _f, _vp, _vp]),
     "lm_gae": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _f, _f, _i32, _vp]),
@@ -159,7 +171,7 @@ def load(path: Optional[str] = None) -> C.CDLL:
         fn.argtypes = args
     if lib.lm_abi_version() != 1:
         raise LmError("liblm_b200.so ABI version mismatch")
-    for which, struct in enumerate((LmTaskParams, LmRobotViews, LmTaskBuffers, LmHostStep, LmPdState, LmRunningStats, LmRolloutStep, LmRolloutBuffers, LmPpoBatch)):
+    for which, struct in enumerate((LmTaskParams, LmRobotViews, LmTaskBuffers, LmHostStep, LmPdState, LmRunningStats, LmRolloutStep, LmRolloutBuffers, LmPpoBatch, LmNoiseSpec, LmNoiseState)):
         if lib.lm_struct_size(which) != C.sizeof(struct):
             raise LmError(f"struct layout mismatch for {struct.__name__}: C {lib.lm_struct_size(which)} vs ctypes {C.sizeof(struct)}")
     _lib = lib

@@ -1203,6 +1203,8 @@ int lm_struct_size(int which) {
     case 6: return (int)sizeof(LmRolloutStep);
     case 7: return (int)sizeof(LmRolloutBuffers);
     case 8: return (int)sizeof(LmPpoBatch);
+    case 9: return (int)sizeof(LmNoiseSpec);
+    case 10: return (int)sizeof(LmNoiseState);
     default: return -1;
   }
 }

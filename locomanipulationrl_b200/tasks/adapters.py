@@ -32,6 +32,10 @@ def make_reference_task_class(task_name: str):
             device = sim_config.config.get("sim_device", "cuda:0")
             super().__init__(cfg, num_envs, scene=scene, device=device, rl_device=sim_config.config.get("rl_device", device))
             self.test = sim_config.config.get("test", False)
+            dr = sim_config.task_config.get("domain_randomization") or {}
+            params = dr.get("randomization_params") or {}
+            if dr.get("randomize", False) and (params.get("observations") or params.get("actions")):     # randomize.py:41-56,99-104
+                self.enable_noise_randomization(params, seed=int(sim_config.config.get("seed", 0)))
 
     _Task.__name__ = task_name
     _Task.__qualname__ = task_name

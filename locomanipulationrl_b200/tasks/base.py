@@ -256,6 +256,15 @@ class LocoManipulationTask:
     def get_extras(self):
         return self.extras
 
+    def enable_noise_randomization(self, randomization_params: dict, seed: int = 0) -> None:
+        """Observation / action noise of the vec-env step: ``randomization_params`` is the ``observations`` / ``actions`` part of
+        the task yaml's ``domain_randomization.randomization_params`` (cfg/task/JointLocomanipulation.yaml:171-191).  Sets the
+        attributes ``VecEnvRLGames.step`` reads (envs/vec_env_rlgames.py:57-58,70-72; randomize.py:156-211)."""
+        from ..noise import Randomizer
+        self._dr_randomizer = Randomizer(randomization_params, self._num_envs, self.num_observations, self.num_actions, device=self._device, seed=seed)
+        self.randomize_observations = self._dr_randomizer.randomize_observations
+        self.randomize_actions = self._dr_randomizer.randomize_actions
+
     def reset(self) -> None:
         """rl_task.py:222-225 (in place, so the pointer the kernels hold stays valid)."""
         self.reset_buf.fill_(1)

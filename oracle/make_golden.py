@@ -122,7 +122,93 @@ def math_fixture():
     print("wrote math")
 
 
+NOISE_CASES = {
+    # name: (buffer type, dim, randomization params in the reference yaml's format, cfg/task/JointLocomanipulation.yaml:171-191)
+    "obs_gauss_add": ("observations", 64, {"on_reset": {"operation": "additive", "distribution": "gaussian", "distribution_parameters": [0.0, 0.0001]},
+                                          "on_interval": {"frequency_interval": 1, "operation": "additive", "distribution": "gaussian",
+                                                          "distribution_parameters": [0.0, 0.002]}}),
+    "act_gauss_add": ("actions", 12, {"on_reset": {"operation": "additive", "distribution": "gaussian", "distribution_parameters": [0.0, 0.015]},
+                                      "on_interval": {"frequency_interval": 1, "operation": "additive", "distribution": "gaussian",
+                                                      "distribution_parameters": [0.0, 0.05]}}),
+    "obs_uniform_scale_every3": ("observations", 64, {"on_reset": {"operation": "scaling", "distribution": "uniform", "distribution_parameters": [0.9, 1.1]},
+                                                     "on_interval": {"frequency_interval": 3, "operation": "additive", "distribution": "uniform",
+                                                                     "distribution_parameters": [-0.05, 0.05]}}),
+    "act_loguniform_interval_only": ("actions", 12, {"on_interval": {"frequency_interval": 2, "operation": "scaling", "distribution": "loguniform",
+                                                                    "distribution_parameters": [0.8, 1.25]}}),
+}
+NOISE_N, NOISE_STEPS = 37, 8
+
+
+def noise_inputs(case, n=NOISE_N, steps=NOISE_STEPS, seed=SEED):
+    _, dim, _ = NOISE_CASES[case]
+    g = torch.Generator().manual_seed(seed + len(case))
+    bufs = [torch.randn(n, dim, generator=g) for _ in range(steps)]
+    resets = [(torch.rand(n, generator=g) < (1.0 if t == 0 else 0.15)).long() for t in range(steps)]     # step 0: reset storm (reset_buf starts as ones)
+    zs = [(torch.randn(n, dim, generator=g), torch.randn(n, dim, generator=g)) for _ in range(steps)]    # standard-normal rows (reset, interval)
+    us = [(torch.rand(n, dim, generator=g), torch.rand(n, dim, generator=g)) for _ in range(steps)]      # U[0,1) rows
+    return bufs, resets, zs, us
+
+
+def noise_fixture():
+    """utils/domain_randomization/randomize.py:212-305 run by the reference Randomizer, its draws supplied from outside."""
+    refshim.install()
+    import importlib
+    R = importlib.import_module("omniisaacgymenvs.utils.domain_randomization.randomize")
+
+    class _Cfg:
+        pass
+
+    class _Task:
+        num_observations, num_actions = 64, 12
+        randomize_observations = randomize_actions = False
+
+    out = {}
+    for case, (kind, dim, params) in NOISE_CASES.items():
+        sc = _Cfg()
+        sc.task_config = {"env": {"numEnvs": NOISE_N}, "domain_randomization": {"randomize": True, "randomization_params": {kind: params}}}
+        sc.config = {"rl_device": "cpu", "seed": 0}
+        rz = R.Randomizer(sc)
+        task = _Task()
+        (rz._set_up_observations_randomization if kind == "observations" else rz._set_up_actions_randomization)(task)
+        bufs, resets, zs, us = noise_inputs(case)
+        real_normal, real_rand = torch.normal, torch.rand
+        for t in range(NOISE_STEPS):
+            cursor = {"n": 0, "u": 0}       # first draw of a step = on_reset rows, second = on_interval rows (randomize.py order)
+
+            def fake_normal(mean, std, size, device=None, _t=t, _c=cursor):
+                z = zs[_t][_c["n"]][:size[0]]
+                _c["n"] += 1
+                return z * std + mean
+
+            def fake_rand(size, device=None, _t=t, _c=cursor):
+                u = us[_t][_c["u"]][:size[0]]
+                _c["u"] += 1
+                return u.clone()
+            has_reset = "on_reset" in params
+            torch.normal, torch.rand = fake_normal, fake_rand
+            try:
+                if not has_reset:
+                    cursor["n"] = cursor["u"] = 1                    # the interval draw is the first call then: keep it on the interval rows
+                buf = bufs[t].clone()
+                if has_reset and int(resets[t].sum()) == 0:
+                    cursor["n"] = cursor["u"] = 1                    # no reset draw this step (randomize.py:285 guards on len(reset_ids))
+                fn = rz.apply_observations_randomization if kind == "observations" else rz.apply_actions_randomization
+                res = fn(buf, resets[t])
+            finally:
+                torch.normal, torch.rand = real_normal, real_rand
+            out[f"{case}/s{t}_out"] = res.numpy().copy()
+            cnt = rz._observations_counter_buffer if kind == "observations" else rz._actions_counter_buffer
+            cor = rz._observations_correlated_noise if kind == "observations" else rz._actions_correlated_noise
+            out[f"{case}/s{t}_counter"] = cnt.numpy().astype(np.int16)
+            out[f"{case}/s{t}_correlated"] = cor.numpy().copy()
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "noise_reference.npz"), **out)
+    print("wrote noise", len(out), "arrays")
+
+
 def main():
+    if "--noise-only" in sys.argv:
+        noise_fixture()
+        return
     if not refshim.reference_available():
         sys.exit("reference tree not available; golden vectors can only be generated in the authoring container")
     os.makedirs(GOLDEN_DIR, exist_ok=True)
@@ -130,6 +216,7 @@ def main():
         task_fixture(name)
     gnn_fixture()
     math_fixture()
+    noise_fixture()
 
 
 if __name__ == "__main__":
