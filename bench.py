@@ -377,7 +377,7 @@ def cuda_arm(args):
 
     # ---- per-kernel timing (rank 0; eager launches bracketed by events, same state rotation)
     line_extra = {}
-    if rank == 0:
+    if rank == 0 and not args.no_kernel_times:
         task = pipe.task
         iters = max(12, min(args.steps, 60))
 
@@ -588,6 +588,8 @@ def main():
                     help="where the per-horizon stat + gradient all-reduce runs (N > 1)")
     ap.add_argument("--e2e-shards", type=int, default=2, help="env shards (streams) the host-buffer step is pipelined over")
     ap.add_argument("--no-large", action="store_true", help="skip the 524,288-env k_post roofline line")
+    ap.add_argument("--no-kernel-times", action="store_true",
+                    help="skip the per-kernel timing section (ncu launch lists: the capture then holds the warm-up and timed steps only)")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)

@@ -3,9 +3,9 @@
 // _apply_correlated_noise, _apply_uncorrelated_noise), called from envs/vec_env_rlgames.py:57-58,70-72.
 //
 // The reference compacts the affected envs with nonzero() (a host synchronisation per buffer per step) and draws (k, dim)
-// tensors.  Here one launch handles a buffer: a tile of 1024 envs computes its flags (and, when the caller supplies draws
+// tensors.  Here one launch handles a buffer: a tile of 256 envs computes its flags (and, when the caller supplies draws
 // in the reference's compact order, the ranks: per-tile counts from a first small launch + a block scan), then the tile's
-// [1024, dim] span is walked with 128-bit accesses.  Without supplied draws the noise comes from a counter-based
+// [256, dim] span is walked with 128-bit accesses.  Without supplied draws the noise comes from a counter-based
 // generator keyed by (seed, step, element), so the kernel needs neither draw tensors nor ranks.
 #include "lm_common.cuh"
 #include "lm_host.h"
@@ -13,7 +13,7 @@
 namespace lm {
 namespace noise {
 
-constexpr int TILE = 1024;
+constexpr int TILE = 256;       // envs (= threads) per CTA: 256 CTAs at 65,536 envs, several resident per SM
 
 struct Args {
   LmNoiseState s;
@@ -90,7 +90,7 @@ __device__ __forceinline__ float4 op4(int operation, const float4& x, const floa
                                         : make_float4(mul(x.x, n.x), mul(x.y, n.y), mul(x.z, n.z), mul(x.w, n.w));
 }
 
-__global__ void __launch_bounds__(TILE, 1) k_noise_apply(const Args a) {
+__global__ void __launch_bounds__(TILE) k_noise_apply(const Args a) {
   __shared__ int row_r[TILE], row_i[TILE];        // draw row of the env (-1: not affected)
   __shared__ int warp_tot[2][TILE / 32];
   __shared__ int base[2];
@@ -105,11 +105,13 @@ __global__ void __launch_bounds__(TILE, 1) k_noise_apply(const Args a) {
   int rr = e, ri = e;                             // dense rows: env e reads row e
   if (a.compact) {
     // ranks among the affected envs in ascending order: preceding tiles (k_noise_count) + block scan
-    if (tid < 2) {
-      int t = 0;
-      for (int b = 0; b < (int)blockIdx.x; ++b) t += a.counts[b * 2 + tid];
-      base[tid] = t;
-    }
+    int t0 = 0, t1 = 0;
+    for (int b = tid; b < (int)blockIdx.x; b += TILE) { t0 += a.counts[b * 2]; t1 += a.counts[b * 2 + 1]; }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) { t0 += __shfl_xor_sync(0xffffffffu, t0, off); t1 += __shfl_xor_sync(0xffffffffu, t1, off); }
+    if (tid < 2) base[tid] = 0;
+    __syncthreads();
+    if (lane == 0) { atomicAdd(&base[0], t0); atomicAdd(&base[1], t1); }       // integer sums: order-independent
     const unsigned br = __ballot_sync(0xffffffffu, fr), bi = __ballot_sync(0xffffffffu, fi);
     if (lane == 0) { warp_tot[0][warp] = __popc(br); warp_tot[1][warp] = __popc(bi); }
     __syncthreads();

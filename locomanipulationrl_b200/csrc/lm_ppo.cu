@@ -135,10 +135,27 @@ __global__ void __launch_bounds__(THREADS) k_ppo_loss(const Args a) {
   }
   __syncthreads();
   if (!s_last) return;
-  if (tid < NRED) {
-    double d = 0.0;
-    for (int c = 0; c < (int)gridDim.x; ++c) d += __ldcg(a.partials + (size_t)c * NRED + tid);
-    sm[0][tid] = d;
+  {
+    // 12 subsets of CTAs x 20 values: thread (sub, j) sums its strided share with 4 loads in flight, then the subsets meet
+    __shared__ double part[12][NRED];
+    const int sub = tid / NRED, j = tid - sub * NRED;
+    if (sub < 12) {
+      double acc[4] = {0.0, 0.0, 0.0, 0.0};
+      int c = sub;
+      for (; c + 36 < (int)gridDim.x; c += 48) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc[u] += __ldcg(a.partials + (size_t)(c + 12 * u) * NRED + j);
+      }
+      for (; c < (int)gridDim.x; c += 12) acc[0] += __ldcg(a.partials + (size_t)c * NRED + j);
+      part[sub][j] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+    }
+    __syncthreads();
+    if (tid < NRED) {
+      double d = 0.0;
+#pragma unroll
+      for (int u = 0; u < 12; ++u) d += part[u][tid];
+      sm[0][tid] = d;
+    }
   }
   __syncthreads();
   if (tid < 12) {
@@ -166,9 +183,12 @@ __global__ void __launch_bounds__(ADAM_THREADS) k_adam_step(float* __restrict__ 
   __shared__ float s_coef;
   const int tid = threadIdx.x;
   double ss = 0.0;
-  for (int i = tid; i < n; i += ADAM_THREADS) {
-    const float gi = g[i] * grad_scale;
-    ss += (double)gi * (double)gi;
+  for (int i0 = tid; i0 < n; i0 += 8 * ADAM_THREADS) {          // 8 independent loads in flight per thread
+    float gv[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { const int i = i0 + u * ADAM_THREADS; gv[u] = i < n ? g[i] * grad_scale : 0.0f; }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) ss += (double)gv[u] * (double)gv[u];
   }
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
@@ -185,16 +205,26 @@ __global__ void __launch_bounds__(ADAM_THREADS) k_adam_step(float* __restrict__ 
   __syncthreads();
   const float coef = s_coef * grad_scale;
   const float step_size = lr / bc1;
-  for (int i = tid; i < n; i += ADAM_THREADS) {
-    float gi = g[i] * coef;
-    const float pi = p[i];
-    g[i] = gi;                                                 // the clipped gradient, as clip_grad_norm_ leaves it
-    if (wd != 0.0f) gi = fmaf(wd, pi, gi);                   // torch.optim.Adam: grad = grad + weight_decay * param (not written back)
-    const float mi = m[i] + (gi - m[i]) * (1.0f - beta1);    // exp_avg.lerp_(grad, 1 - beta1)
-    const float vi = beta2 * v[i] + (1.0f - beta2) * gi * gi;
-    m[i] = mi; v[i] = vi;
-    const float denom = sqrtf(vi) / bc2_sqrt + eps;
-    p[i] = pi - step_size * (mi / denom);
+  for (int i0 = tid; i0 < n; i0 += 4 * ADAM_THREADS) {          // 16 independent loads in flight per thread
+    float gv[4], pv[4], mv[4], vv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * ADAM_THREADS;
+      if (i < n) { gv[u] = g[i]; pv[u] = p[i]; mv[u] = m[i]; vv[u] = v[i]; }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * ADAM_THREADS;
+      if (i >= n) continue;
+      float gi = gv[u] * coef;
+      g[i] = gi;                                                 // the clipped gradient, as clip_grad_norm_ leaves it
+      if (wd != 0.0f) gi = fmaf(wd, pv[u], gi);                // torch.optim.Adam: grad = grad + weight_decay * param (not written back)
+      const float mi = mv[u] + (gi - mv[u]) * (1.0f - beta1);  // exp_avg.lerp_(grad, 1 - beta1)
+      const float vi = beta2 * vv[u] + (1.0f - beta2) * gi * gi;
+      m[i] = mi; v[i] = vi;
+      const float denom = sqrtf(vi) / bc2_sqrt + eps;
+      p[i] = pv[u] - step_size * (mi / denom);
+    }
   }
 }
 

@@ -1,0 +1,83 @@
+"""Device times of the caller-side kernels (rollout writer, running statistics, noise, PPO loss head, Adam) at the bench sizes.
+python tools/update_bench.py  (needs a B200; CUDA events around graph replays, inputs rotated over > L2 worth of buffers)"""
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+from locomanipulationrl_b200.noise import NoiseRandomizer  # noqa: E402
+from locomanipulationrl_b200.ppo import FlatAdam, PpoLoss  # noqa: E402
+from locomanipulationrl_b200.rollout import RolloutBuffer, RunningMeanStd  # noqa: E402
+
+dev = "cuda:0"
+N, T, SETS = 65536, 16, 8
+HBM = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"] \
+    if os.path.exists(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")) else 6650.0
+
+
+def graph_time(fn, calls, reps=20):
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for i in range(calls):
+            fn(i)
+    g.replay()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        g.replay()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / (reps * calls)
+
+
+def report(name, ms, bytes_per_item, items):
+    gbs = items * bytes_per_item / (ms * 1e-3) / 1e9
+    print(json.dumps({"kernel": name, "us": round(ms * 1e3, 2), "items": items, "bytes_per_item": bytes_per_item, "GB/s": round(gbs, 1), "frac_of_measured_hbm": round(gbs / HBM, 3)}))
+
+
+g = torch.Generator(device=dev).manual_seed(0)
+obs = [torch.randn(N, 64, device=dev, generator=g) for _ in range(SETS)]          # 8 x 16.8 MB > L2
+mu = [torch.randn(N, 12, device=dev, generator=g) for _ in range(SETS)]
+noise = [torch.randn(N, 12, device=dev, generator=g) for _ in range(SETS)]
+value = torch.randn(N, 1, device=dev, generator=g)
+rew = torch.randn(N, device=dev, generator=g)
+dones = (torch.rand(N, device=dev, generator=g) < 0.03).long()
+log_std = torch.zeros(12, device=dev)
+actions = torch.zeros(N, 12, device=dev)
+buf, stats = RolloutBuffer(T, N, device=dev, reward_scale=0.01), RunningMeanStd(64, device=dev)
+for i in range(3):
+    buf.write(i, obs[i], mu[i], value, log_std, rew, dones, noise=noise[i], actions_out=actions, obs_stats=stats)
+torch.cuda.synchronize()
+ms = graph_time(lambda i: buf.write(i % T, obs[i % SETS], mu[i % SETS], value, log_std, rew, dones, noise=noise[i % SETS], actions_out=actions, obs_stats=stats), T)
+report("k_rollout_write (65,536 envs, sampled actions, fused obs statistics)", ms, 368 + 48 + 368 + 48, N)
+
+vals = torch.randn(T * N, device=dev, generator=g)
+vstats = RunningMeanStd(1, device=dev)
+vstats.update(vals)
+ms = graph_time(lambda i: vstats.update(vals), 4)
+report("k_rms_update (value statistics, 16 x 65,536 samples)", ms, 4, T * N)
+
+rz = NoiseRandomizer({"on_reset": {"operation": "additive", "distribution": "gaussian", "distribution_parameters": [0.0, 0.0001]},
+                      "on_interval": {"frequency_interval": 1, "operation": "additive", "distribution": "gaussian", "distribution_parameters": [0.0, 0.002]}},
+                     N, 64, device=dev, seed=1)
+rz.apply(obs[0], dones)
+ms = graph_time(lambda i: rz.apply(obs[i % SETS], dones), SETS)
+report("k_noise_apply (observations, in-kernel Philox draws)", ms, 256 * 3, N)
+
+B = T * N // 4                                                                     # rl_games minibatch: a quarter of the rollout
+pm, pa, pom = (torch.randn(B, 12, device=dev, generator=g) * 0.3 for _ in range(3))
+pv, pnl, padv, pov, pret = (torch.randn(B, device=dev, generator=g) for _ in range(5))
+head = PpoLoss(device=dev)
+out = {"grad_mu": torch.empty(B, 12, device=dev), "grad_value": torch.empty(B, device=dev)}
+head(pm, pv, log_std, pa, pnl, padv, pov, pret, pom, log_std, out=out)
+ms = graph_time(lambda i: head(pm, pv, log_std, pa, pnl, padv, pov, pret, pom, log_std, out=out), 4)
+report(f"k_ppo_loss (minibatch {B})", ms, 3 * 48 + 5 * 4 + 48 + 4, B)
+
+flat, grads = torch.randn(58637, device=dev, generator=g), torch.randn(58637, device=dev, generator=g)
+opt = FlatAdam(flat)
+opt.step(grads)
+ms = graph_time(lambda i: opt.step(grads), 8)
+report("k_adam_step (58,637 parameters, clip + Adam)", ms, 28, 58637)
