@@ -80,6 +80,15 @@ class LmRolloutBuffers(C.Structure):
                [("horizon", _i32), ("num_envs", _i32), ("reward_scale", _f)]
 
 
+class LmCustomController(C.Structure):
+    _fields_ = [("num_envs", _i32), ("clip_reward", _i32), ("clamp_observations", _i32), ("pad_", _i32),
+                ("clip_observations", _f), ("target_obs_scale", _f), ("action_rate_scale", _f), ("mechanical_power_penalty_scale", _f),
+                ("position_target_error_penalty_scale", _f), ("rot_dist_decreasing_reward_scale", _f),
+                ("no_rot_dist_decreasing_reward_thresh", _f), ("default_quaternion", _f * 4), ("dof_index", _i32 * NUM_ACT)] + \
+               [(n, C.c_void_p) for n in ("obs64", "root_quat", "dof_pos", "dof_vel", "goal", "torque", "targets", "last_targets", "joint_pos",
+                                          "joint_vel", "last_rot_dist", "obs", "states", "rew", "extras", "reset_env_ids", "num_reset")]
+
+
 class LmNoiseSpec(C.Structure):
     _fields_ = [("enabled", _i32), ("operation", _i32), ("distribution", _i32), ("frequency_interval", _i32), ("scale", _f), ("shift", _f)]
 
@@ -134,6 +143,8 @@ SYMBOLS = {
     "lm_rollout_write": (C.c_int, [_vp, C.POINTER(LmRolloutStep), C.POINTER(LmRolloutBuffers), _i32, _vp, C.POINTER(LmRunningStats), _vp]),
     "lm_rms_update": (C.c_int, [_vp, _vp, _i64, C.POINTER(LmRunningStats), _vp]),
     "lm_rms_export": (C.c_int, [C.POINTER(LmRunningStats), _vp, _vp, _vp]),
+    "lm_cc_pre": (C.c_int, [C.POINTER(LmCustomController), _vp]),
+    "lm_cc_post": (C.c_int, [_vp, C.POINTER(LmCustomController), _vp]),
     "lm_noise_create": (_vp, [C.c_int]),
     "lm_noise_destroy": (None, [_vp]),
     "lm_noise_apply": (C.c_int, [_vp, C.POINTER(LmNoiseState), _vp, _vp, _vp, _vp, _i32, C.c_uint64, C.c_uint64, _vp]),
@@ -171,7 +182,7 @@ def load(path: Optional[str] = None) -> C.CDLL:
         fn.argtypes = args
     if lib.lm_abi_version() != 1:
         raise LmError("liblm_b200.so ABI version mismatch")
-    for which, struct in enumerate((LmTaskParams, LmRobotViews, LmTaskBuffers, LmHostStep, LmPdState, LmRunningStats, LmRolloutStep, LmRolloutBuffers, LmPpoBatch, LmNoiseSpec, LmNoiseState)):
+    for which, struct in enumerate((LmTaskParams, LmRobotViews, LmTaskBuffers, LmHostStep, LmPdState, LmRunningStats, LmRolloutStep, LmRolloutBuffers, LmPpoBatch, LmNoiseSpec, LmNoiseState, LmCustomController)):
         if lib.lm_struct_size(which) != C.sizeof(struct):
             raise LmError(f"struct layout mismatch for {struct.__name__}: C {lib.lm_struct_size(which)} vs ctypes {C.sizeof(struct)}")
     _lib = lib

@@ -143,6 +143,14 @@ class TaskConfig:
     pd_sum_final_torque: bool = True   # single-task files add the torque computed after the last sub-step to torque_sum (:311); JL_PC does not (:399-408)
     pd_carry_post_state: bool = True   # single-task files re-point joint_positions_* at the post-step state in get_observations (:392-393); JL_PC keeps the last sub-step's
     pd_target_obs_scale: float = 0.3  # literal ``* 0.3`` on the target rows of the observation (…position_control.py:438-439)
+    # --- *_custom_controller.py (quadruped_pose_control_custom_controller.py:24-65): the PD loop of *_PC plus an 88-wide observation
+    # (actions AND target rows, :441-455), an unflipped quat_diff (:430), |a| as action-rate term (:531) and three more reward terms
+    custom_controller: bool = False
+    mechanical_power_penalty_scale: float = -0.02          # :48, :534-535
+    position_target_error_penalty_scale: float = -0.05     # :49, :538-539
+    rot_dist_decreasing_reward_scale: float = 0.0          # :50 (``# 50``), :542-545
+    no_rot_dist_decreasing_reward_thresh: float = 0.3      # :51
+    clip_reward: bool = False                              # :65, :619-620
 
     @property
     def time_interval(self) -> float:
@@ -244,6 +252,21 @@ def joint_locomanipulation_position_control() -> TaskConfig:
                                           pd_sum_final_torque=False, pd_carry_post_state=False))
 
 
+_CC_INIT_SE = [-1.2, 1.2, 1.2, -1.2, -1.57, 0.7, 1.57, 0.7, 1.57, 0.7, -1.57, 0.7]   # quadruped_pose_control_custom_controller.py:180-184
+
+
+def quadruped_pose_control_custom_controller() -> TaskConfig:
+    """quadruped_pose_control_custom_controller.py:20-190; cfg/task/QuadrupedPoseControlCustomController.yaml.  Robot-file defaults
+    (no pose override in __init__, :124-126), fixed goal yaw 1.57 (:38-43), 93-wide states (:161), actions are NOT zeroed (:258)."""
+    return TaskConfig(name="QuadrupedPoseControlCustomController", kind=KIND_LOCO, vertical=False, control_mode=CONTROL_PD,
+                      custom_controller=True, num_observations=88, num_states=93,
+                      min_roll=-0.0, max_roll=0.0, min_pitch=-0.0, max_pitch=0.0, min_yaw=1.57, max_yaw=1.57,
+                      joint_acc_scale=-0.00015, action_rate_scale=-0.01, success_thresh=0.15, max_consecutive_successes=20,
+                      loco_init_joint_pos=list(_HORIZONTAL_ROBOT_INIT), loco_default_position=[0.0, 0.0, 0.18],
+                      dt=0.005, control_frequency_inv=1, max_episode_length=500,
+                      pd_control_decimal=4, pd_torque_divisor=4.0, pd_init_se=list(_CC_INIT_SE))
+
+
 TASK_CONFIGS = {
     "QuadrupedPoseControl": quadruped_pose_control,
     "QuadrupedPoseControlVertical": quadruped_pose_control_vertical,
@@ -254,6 +277,7 @@ TASK_CONFIGS = {
     "QuadrupedPoseControlPositionControl": quadruped_pose_control_position_control,
     "QuadrupedManipulatePlatePositionControl": quadruped_manipulate_plate_position_control,
     "JointLocomanipulationPositionControl": joint_locomanipulation_position_control,
+    "QuadrupedPoseControlCustomController": quadruped_pose_control_custom_controller,
 }
 
 

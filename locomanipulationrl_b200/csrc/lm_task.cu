@@ -1205,6 +1205,7 @@ int lm_struct_size(int which) {
     case 8: return (int)sizeof(LmPpoBatch);
     case 9: return (int)sizeof(LmNoiseSpec);
     case 10: return (int)sizeof(LmNoiseState);
+    case 11: return (int)sizeof(LmCustomController);
     default: return -1;
   }
 }
@@ -1284,7 +1285,8 @@ int lm_task_set_timeline(LmTask* t, long long* stamps_dev) { if (!t) return LM_E
 int lm_task_set_pd_state(LmTask* t, const LmPdState* pd) {
   if (!t) return lm_fail(LM_ERR_BAD_ARG, "lm_task_set_pd_state: task is NULL");
   if (!pd) { memset(&t->pd, 0, sizeof(t->pd)); t->has_pd = 0; return LM_OK; }
-  if (t->kp.p.num_states != LM_NUM_OBS) return lm_fail(LM_ERR_UNSUPPORTED, "PD state needs a task whose states alias obs (num_states 64)");
+  // With the 93-wide states variant (the *_custom_controller files) k_post keeps the action rows in obs[40:64] and does not
+  // carry the post-step joint state: lm_cc_post adds the target rows and the carry.  k_pre resets the PD rows either way.
   const void* ptrs[5] = {pd->joint_pos, pd->joint_vel, pd->targets, pd->last_targets, pd->targets_se};
   for (int i = 0; i < 5; ++i) {
     if (!ptrs[i]) return lm_fail(LM_ERR_BAD_ARG, "lm_task_set_pd_state: NULL tensor");

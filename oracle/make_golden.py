@@ -20,6 +20,7 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file
 TASK_N = 50            # ragged: n % 4 != 0 (co-train halves of 25) -> exercises the non-TMA tail path of the kernels
 TASK_STEPS = 20        # long enough for the consecutive-success counter to pass 15 and trigger goal resets
 FULL_STEPS = (0, 1, 2, 17, 18, 19)   # steps whose float tensors are stored; the rest keep masks / ints / rewards only
+STEPS_OVERRIDE = {"QuadrupedPoseControlCustomController": 28}   # goal reset needs consecutive_successes > 20 (mirrored in tests/common.py)
 SEED = 7
 
 
@@ -34,10 +35,12 @@ def task_fixture(name):
     cfg = configs.get_task_config(name)
     scene = synthetic.SyntheticScene(cfg, TASK_N, seed=SEED)
     task = refshim.make_reference_task(cfg, scene)
-    acts, unis = rollout_inputs(TASK_N, TASK_STEPS)
+    steps = STEPS_OVERRIDE.get(name, TASK_STEPS)
+    full_steps = (0, 1, 2, steps - 3, steps - 2, steps - 1)
+    acts, unis = rollout_inputs(TASK_N, steps)
     out = {}
     pd = cfg.control_mode == configs.CONTROL_PD
-    for t in range(TASK_STEPS):
+    for t in range(steps):
         if pd:   # the PD loop steps the simulation itself: feed it the seeded sub-step joint states (generated before torch.rand is patched)
             sub = [scene.substep_joint_state(t, i) for i in range(cfg.pd_control_decimal)]
             cursor = {"i": 0}
@@ -50,7 +53,7 @@ def task_fixture(name):
             ids = task.reset_buf.nonzero(as_tuple=False).squeeze(-1).clone()
             task.pre_physics_step(acts[t].clone())
         refshim._SimulationContext.hook = None
-        full = t in FULL_STEPS
+        full = t in full_steps
         if pd:
             out[f"s{t}_torque"] = task.torque.numpy().copy()
             if full:
@@ -208,6 +211,11 @@ def noise_fixture():
 def main():
     if "--noise-only" in sys.argv:
         noise_fixture()
+        return
+    only = [a.split("=", 1)[1] for a in sys.argv if a.startswith("--task=")]
+    if only:                                            # regenerate selected task fixtures only
+        for name in only:
+            task_fixture(name)
         return
     if not refshim.reference_available():
         sys.exit("reference tree not available; golden vectors can only be generated in the authoring container")

@@ -172,6 +172,9 @@ class TaskPort:
             self.se_lower = torch.tensor(cfg.pd_min_se, dtype=f32)
             self.torque = torch.zeros(n, 12, dtype=f32)
             self.applied_torque = torch.zeros(n, 12, dtype=f32)
+        self.cc = bool(cfg.custom_controller)
+        if self.cc:
+            self.last_rot_dist = torch.zeros(n, dtype=f32)                              # …custom_controller.py:188
         self.reset_env_ids = torch.zeros(0, dtype=i64)
         self.inter: Dict[str, torch.Tensor] = {}
 
@@ -285,6 +288,10 @@ class TaskPort:
             self.current_joint_position_targets[env_ids] = self.default_joint_positions[env_ids]
             self.last_joint_position_targets[env_ids] = self.current_joint_position_targets[env_ids].clone()
             self.current_joint_position_targets_se[env_ids] = torch.tensor(cfg.pd_init_se, dtype=f32).repeat(k, 1)
+        if self.cc:                                                                     # …custom_controller.py:384-386
+            q_def = torch.tensor(cfg.loco_default_quaternion, dtype=f32).repeat(k, 1)
+            qd = it.quat_mul(it.quat_conjugate(q_def), it.quat_conjugate(self.goal_quaternions[env_ids]))
+            self.last_rot_dist[env_ids] = 2.0 * torch.asin(torch.clamp(torch.norm(qd[:, 1:4], p=2, dim=-1), max=1.0))
         self.last_base_tip_positions[env_ids] = self.default_base_tip_positions[env_ids]
         self.last_actions[env_ids] = 0.0
         for buf in (self.reset_buf, self.progress_buf, self.successes, self.consecutive_successes, self.goal_reset_buf):
@@ -359,7 +366,9 @@ class TaskPort:
         for p in parts:
             rows = p["rows"]
             goal = self.goal_quaternions[rows]
-            diff = _positive_w(it.quat_mul(p["cur_q"], it.quat_conjugate(goal)))      # QPC:345-349
+            diff = it.quat_mul(p["cur_q"], it.quat_conjugate(goal))
+            if not self.cc:                                                           # …custom_controller.py:430 keeps the raw product
+                diff = _positive_w(diff)                                              # QPC:345-349
             up = it.quat_axis(p["cur_q"], 2)
             s_pos = cfg.position_scale * p["pos"]
             s_lin = cfg.linear_vel_scale * p["lin"]
@@ -367,10 +376,14 @@ class TaskPort:
             s_jp = cfg.joint_position_scale * p["jp"]
             s_jv = cfg.joint_velocity_scale * p["jv"]
             cur_a, last_a = self.current_actions[rows], self.last_actions[rows]
-            if self.pd:                                                               # …position_control.py:438-452
+            if self.pd and not self.cc:                                               # …position_control.py:438-452
                 cur_a = (self.current_joint_position_targets * cfg.pd_target_obs_scale)[rows]
                 last_a = (self.last_joint_position_targets * cfg.pd_target_obs_scale)[rows]
-            obs_rows.append(torch.cat((s_pos, up, diff, s_lin, s_ang, s_jp, s_jv, cur_a, last_a), dim=-1))   # QPC:358-371
+            row = (s_pos, up, diff, s_lin, s_ang, s_jp, s_jv, cur_a, last_a)                                   # QPC:358-371
+            if self.cc:                                                               # …custom_controller.py:432-455: actions AND target rows
+                row = row + ((self.current_joint_position_targets * cfg.pd_target_obs_scale)[rows],
+                             (self.last_joint_position_targets * cfg.pd_target_obs_scale)[rows])
+            obs_rows.append(torch.cat(row, dim=-1))
             if cfg.num_states == 93:                                                  # QPC:406-423
                 n = p["jp"].shape[0]
                 tip_now = cfg.tip_position_scale * p["tip_base"].reshape(n, 12)
@@ -397,7 +410,10 @@ class TaskPort:
         rot_rew = 1.0 / (torch.abs(rot_dist) + cfg.rot_eps) * cfg.quaternion_scale
         translation_penalty = torch.norm(x["pos"][:, 0:2], dim=-1) * cfg.translation_scale
         joint_acc_penalty = torch.sum(torch.abs(x["acc"]) * cfg.joint_acc_scale, dim=1)
-        action_rate_penalty = torch.sum(torch.abs(self.last_actions - self.current_actions), dim=1) * cfg.action_rate_scale
+        if self.cc:                                                                   # …custom_controller.py:531
+            action_rate_penalty = torch.sum(torch.abs(self.current_actions), dim=1) * cfg.action_rate_scale
+        else:
+            action_rate_penalty = torch.sum(torch.abs(self.last_actions - self.current_actions), dim=1) * cfg.action_rate_scale
         goal_reset = torch.where(self.consecutive_successes > cfg.max_consecutive_successes,
                                  torch.ones_like(self.consecutive_successes), torch.zeros_like(self.consecutive_successes))
         bonus = cfg.consecutive_success_reward * goal_reset.to(torch.float32)
@@ -419,6 +435,20 @@ class TaskPort:
         brk = (brk1 + brk23).flatten()
         joint_limit_penalty = (cfg.joint_limit_penalty * torch.where(brk > 0, torch.ones_like(brk), torch.zeros_like(brk))).to(torch.float32)
         total = rot_rew + translation_penalty + joint_acc_penalty + action_rate_penalty + bonus + joint_limit_penalty
+        extra_terms = {}
+        if self.cc:                                                                   # …custom_controller.py:533-546,608-620
+            mechanical_power = torch.sum(torch.abs(self.torque * self.joint_velocities), dim=-1)
+            mechanical_power_penalty = cfg.mechanical_power_penalty_scale * mechanical_power
+            position_target_error = torch.sum(torch.abs(self.last_joint_position_targets - self.joint_positions), dim=-1)
+            position_target_error_penalty = cfg.position_target_error_penalty_scale * position_target_error
+            larger = rot_dist > cfg.no_rot_dist_decreasing_reward_thresh
+            rot_dist_decreasing_reward = larger.to(torch.float32) * (self.last_rot_dist - rot_dist) * cfg.rot_dist_decreasing_reward_scale
+            self.last_rot_dist = rot_dist
+            total = total + mechanical_power_penalty + position_target_error_penalty + rot_dist_decreasing_reward
+            if cfg.clip_reward:
+                total = torch.clip(total, 0.0, None)
+            extra_terms = {"mechanical_power_penalty": mechanical_power_penalty, "position_target_error_penalty": position_target_error_penalty,
+                           "rot_dist_decreasing_reward": rot_dist_decreasing_reward}
         self.rew_buf[:] = total
         self.goal_reset_buf = goal_reset
         both = torch.logical_and(successes, self.successes)                           # QPC:534-545
@@ -432,6 +462,7 @@ class TaskPort:
         terms = {"orientation_rew": rot_rew, "translation_penalty": translation_penalty, "joint_acc_penalty": joint_acc_penalty,
                  "action_rate_penalty": action_rate_penalty, "consecutive_successes_rew": bonus,
                  "joint_limit_panelty": joint_limit_penalty}
+        terms.update(extra_terms)
         self.extras.update({"env/rewards/" + k: v.mean() for k, v in terms.items()})
         self.inter["rot_dist"] = rot_dist
         self.inter["quat_diff_norm"] = torch.norm(quat_diff[:, 1:4], p=2, dim=-1)
@@ -453,6 +484,8 @@ class TaskPort:
         self.extras["env/rewards/fall_penalty"] = fall.mean()
         rb[:] = torch.where(self.goal_reset_buf == 1, one, rb)
         rb[:] = torch.where(self.progress_buf >= cfg.max_episode_length - 1, one, rb)
+        if self.cc:                                                                   # …custom_controller.py:724
+            self.last_joint_position_targets = self.current_joint_position_targets.clone()
         groups = [("", slice(0, self.num_envs))]
         if cfg.kind == KIND_COTRAIN:                                                   # JLV:769-798
             groups += [("_loco", slice(0, self.half)), ("_mani", slice(self.half, self.num_envs))]

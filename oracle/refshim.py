@@ -317,6 +317,7 @@ _TASK_CLASSES = {
     "QuadrupedPoseControlPositionControl": ("tasks.quadruped_pose_control_tasks.quadruped_pose_control_position_control", "QuadrupedPoseControlPositionControl"),
     "QuadrupedManipulatePlatePositionControl": ("tasks.quadruped_manipulate_plate.quadruped_manipulate_plate_position_control", "QuadrupedManipulatePlatePositionControl"),
     "JointLocomanipulationPositionControl": ("tasks.joint_train_locomanipulation.joint_locomanipulation_position_control", "JointLocomanipulationPositionControl"),
+    "QuadrupedPoseControlCustomController": ("tasks.quadruped_pose_control_tasks.quadruped_pose_control_custom_controller", "QuadrupedPoseControlCustomController"),
 }
 
 

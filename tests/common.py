@@ -11,6 +11,14 @@ from locomanipulationrl_b200 import configs, synthetic
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 GOLDEN_N, GOLDEN_STEPS, GOLDEN_SEED = 50, 20, 7
 GOLDEN_FULL_STEPS = (0, 1, 2, 17, 18, 19)
+# fixtures of tasks whose goal reset needs more than 20 steps (custom controller: max_consecutive_successes = 20)
+GOLDEN_STEPS_OVERRIDE = {"QuadrupedPoseControlCustomController": 28}
+
+
+def golden_steps(name):
+    """(number of steps, steps whose float tensors are stored) of the fixture of task ``name``."""
+    n = GOLDEN_STEPS_OVERRIDE.get(name, GOLDEN_STEPS)
+    return n, (0, 1, 2, n - 3, n - 2, n - 1)
 
 # fp32 tolerance of BASELINE.json's north_star ("within 1e-5 relative"), read norm-wise with an absolute floor
 # because several observation components cross zero (SURVEY.md §7 "hard parts").
@@ -158,6 +166,8 @@ class CudaRollout:
         if self.cfg.control_mode == configs.CONTROL_PD:
             self._track("pd_state", assert_close(f"step {t} pd joint_positions (post)", task.joint_positions, p.joint_positions))
             self._track("pd_state", assert_close(f"step {t} pd last_targets", task.last_joint_position_targets, p.last_joint_position_targets))
+        if self.cfg.custom_controller:
+            self._track("last_rot_dist", assert_close(f"step {t} last_rot_dist", task.last_rot_dist, p.last_rot_dist, rtol=1e-6, atol=1e-6))
         if self.exempt_events == 0:
             for k, v in p.extras.items():
                 self._track("extras", assert_close(f"step {t} extras[{k}]", task.extras[k], v, rtol=2e-5, atol=1e-6))

@@ -9,7 +9,7 @@ import torch
 from locomanipulationrl_b200 import configs, synthetic
 from oracle import isaac_torch as it
 from oracle import port, port_policy
-from tests.common import GOLDEN_DIR, GOLDEN_FULL_STEPS, GOLDEN_N, GOLDEN_SEED, GOLDEN_STEPS, rollout_inputs
+from tests.common import GOLDEN_DIR, GOLDEN_FULL_STEPS, GOLDEN_N, GOLDEN_SEED, GOLDEN_STEPS, golden_steps, rollout_inputs
 
 
 def _load(name):
@@ -22,16 +22,17 @@ def test_task_port_matches_reference_bit_exact(name):
     cfg = configs.get_task_config(name)
     scene = synthetic.SyntheticScene(cfg, GOLDEN_N, seed=GOLDEN_SEED)
     task = port.TaskPort(cfg, scene)
-    acts, unis = rollout_inputs(GOLDEN_N, GOLDEN_STEPS)
+    steps, full_steps = golden_steps(name)
+    acts, unis = rollout_inputs(GOLDEN_N, steps)
     saw_reset_after_first, saw_goal_reset = False, False
     pd = cfg.control_mode == configs.CONTROL_PD
-    for t in range(GOLDEN_STEPS):
+    for t in range(steps):
         task.pre_physics_step(acts[t].clone(), unis[t], (lambda i, t=t: scene.substep(t, i)) if pd else None)
         assert np.array_equal(task.reset_env_ids.numpy(), g[f"s{t}_reset_ids"]), f"step {t} reset ids"
         assert np.array_equal(task.goal_quaternions.numpy(), g[f"s{t}_goal"]), f"step {t} goals"
         if pd:
             assert np.array_equal(task.torque.numpy(), g[f"s{t}_torque"]), f"step {t} mean torque"
-        if t in GOLDEN_FULL_STEPS:
+        if t in full_steps:
             if pd:
                 assert np.array_equal(task.current_joint_position_targets.numpy(), g[f"s{t}_pd_targets"])
                 assert np.array_equal(task.current_joint_position_targets_se.numpy(), g[f"s{t}_pd_targets_se"])
@@ -46,7 +47,7 @@ def test_task_port_matches_reference_bit_exact(name):
                         assert np.array_equal(st[k].numpy(), g[f"s{t}_{grp}_{k}"]), f"step {t} {grp}.{k}"
         scene.step(t, task.goal_quaternions)
         obs, rew, reset, extras = task.post_physics_step()
-        if t in GOLDEN_FULL_STEPS:
+        if t in full_steps:
             assert np.array_equal(obs.numpy(), g[f"s{t}_obs"]), f"step {t} obs"
             if cfg.num_states == 93:
                 assert np.array_equal(task.states_buf.numpy(), g[f"s{t}_states"])

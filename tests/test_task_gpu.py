@@ -6,7 +6,7 @@ import pytest
 import torch
 
 from locomanipulationrl_b200 import configs, synthetic
-from tests.common import (ATOL, GOLDEN_DIR, GOLDEN_FULL_STEPS, GOLDEN_N, GOLDEN_SEED, GOLDEN_STEPS, RTOL, CudaRollout,
+from tests.common import (ATOL, GOLDEN_DIR, GOLDEN_FULL_STEPS, GOLDEN_N, GOLDEN_SEED, GOLDEN_STEPS, RTOL, CudaRollout, golden_steps,
                           assert_close, rollout_inputs)
 
 pytestmark = pytest.mark.gpu
@@ -21,15 +21,16 @@ def test_cuda_matches_golden_reference_vectors(name):
     cfg = configs.get_task_config(name)
     scene = synthetic.SyntheticScene(cfg, GOLDEN_N, device="cuda:0", seed=GOLDEN_SEED)
     task = LocoManipulationTask(cfg, GOLDEN_N, scene=scene)
-    acts, unis = rollout_inputs(GOLDEN_N, GOLDEN_STEPS)
+    steps, full_steps = golden_steps(name)
+    acts, unis = rollout_inputs(GOLDEN_N, steps)
     pd = cfg.control_mode == configs.CONTROL_PD
-    for t in range(GOLDEN_STEPS):
+    for t in range(steps):
         task.pre_physics_step(acts[t].cuda(), unis[t].cuda(), (lambda i, t=t: scene.substep(t, i)) if pd else None)
         assert np.array_equal(task.reset_env_ids().cpu().numpy(), g[f"s{t}_reset_ids"]), f"step {t}: reset ids"
         assert_close(f"step {t} goal", task.goal_quaternions, g[f"s{t}_goal"])
         if pd:
             assert_close(f"step {t} mean torque", task.torque, g[f"s{t}_torque"])
-        if t in GOLDEN_FULL_STEPS:
+        if t in full_steps:
             if pd:
                 assert_close(f"step {t} pd targets", task.current_joint_position_targets, g[f"s{t}_pd_targets"])
                 assert_close(f"step {t} pd targets_se", task.current_joint_position_targets_se, g[f"s{t}_pd_targets_se"])
@@ -44,7 +45,7 @@ def test_cuda_matches_golden_reference_vectors(name):
                         assert_close(f"step {t} {grp}.{k}", st[k], g[f"s{t}_{grp}_{k}"])
         scene.step(t, torch.from_numpy(g[f"s{t}_goal"]))
         obs, rew, reset, extras = task.post_physics_step()
-        if t in GOLDEN_FULL_STEPS:
+        if t in full_steps:
             assert_close(f"step {t} obs", obs, g[f"s{t}_obs"])
             if cfg.num_states == 93:
                 assert_close(f"step {t} states", task.get_states(), g[f"s{t}_states"])
@@ -62,7 +63,7 @@ def test_cuda_matches_golden_reference_vectors(name):
                                     ("JointLocomanipulationVertical", 8192), ("JointLocomanipulation", 4096),
                                     ("QuadrupedPoseControlVertical", 1024), ("QuadrupedManipulatePlateVertical", 1024),
                                     ("QuadrupedPoseControlPositionControl", 2048), ("QuadrupedManipulatePlatePositionControl", 2048),
-                                    ("JointLocomanipulationPositionControl", 4096)])
+                                    ("JointLocomanipulationPositionControl", 4096), ("QuadrupedPoseControlCustomController", 4096)])
 def test_cuda_matches_oracle_port_rollout(name, n):
     """BASELINE.json configs 1-3 shapes (config 3 at 8192 to keep the CPU oracle quick): 24-step rollouts, TMA tile path."""
     ro = CudaRollout(name, n)
@@ -71,6 +72,19 @@ def test_cuda_matches_oracle_port_rollout(name, n):
         ro.step(t, acts[t], unis[t])
     assert ro.exempt_events <= 2, f"{ro.exempt_events} near-threshold mask exemptions"
     print(name, n, "max abs err:", {k: f"{v:.2e}" for k, v in ro.max_err.items()}, "exempt:", ro.exempt_events)
+
+
+def test_custom_controller_optional_terms():
+    """quadruped_pose_control_custom_controller.py ships rot_dist_decreasing_reward_scale = 0 (``# 50``) and clip_reward = False:
+    switch both on (the port is pinned to the reference class with these values too) and track the port."""
+    cfg = configs.get_task_config("QuadrupedPoseControlCustomController").with_(rot_dist_decreasing_reward_scale=50.0, clip_reward=True)
+    ro = CudaRollout(cfg.name, 1000, cfg=cfg)
+    acts, unis = rollout_inputs(1000, 30, seed=5)
+    for t in range(30):
+        ro.step(t, acts[t], unis[t])
+    assert ro.exempt_events <= 2
+    assert float(ro.port.rew_buf.min()) >= 0.0 and float(ro.task.rew_buf.min()) >= 0.0
+    assert abs(float(ro.port.extras["env/rewards/rot_dist_decreasing_reward"])) > 1e-3        # the term was live
 
 
 @pytest.mark.parametrize("n", [2, 6, 130, 258])
