@@ -276,7 +276,8 @@ int lm_gae_env_major(const float* rewards, const float* values, const float* don
                      void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
- * *_custom_controller.py task variants (quadruped_pose_control_custom_controller.py): the explicit PD loop of
+ * *_custom_controller.py task variants (quadruped_pose_control_custom_controller.py and
+ * quadruped_manipulate_plate_custom_controller.py; line numbers below are the former's): the explicit PD loop of
  * the *_position_control files plus an 88-wide observation, an unflipped quat_diff, |a| as action-rate term, three more
  * reward terms and the last_rot_dist state.  The task kernels run unchanged (93-wide states variant, action-rate scale 0,
  * observations into a 64-wide scratch); these two calls add the variant's own rows:
@@ -285,15 +286,16 @@ int lm_gae_env_major(const float* rewards, const float* values, const float* don
  *     (:430-455), raw quat_diff into the states row (:466-479), reward += action-rate + mechanical-power + target-error +
  *     rot-dist-decrease terms (:531-546,608-620), their means into extras[3], [12..14], last_rot_dist <- rot_dist,
  *     last_targets <- targets (:724), carried joint state <- post-step joint state (:392-393). */
+enum { LM_CC_UPDATE_LAST_TARGETS = 1, LM_CC_ROT_DIST_TERM = 2 };
 enum { LM_EXTRA_MECHANICAL_POWER_PENALTY = 12, LM_EXTRA_TARGET_ERROR_PENALTY = 13, LM_EXTRA_ROT_DIST_DECREASING_REW = 14 };
 typedef struct LmCustomController {
-  int32_t num_envs; int32_t clip_reward; int32_t clamp_observations; int32_t pad_;
+  int32_t num_envs; int32_t clip_reward; int32_t clamp_observations;
+  int32_t flags;               /* LM_CC_UPDATE_LAST_TARGETS (:724; the manipulation file never does), LM_CC_ROT_DIST_TERM (locomotion file only) */
   float clip_observations; float target_obs_scale;
   float action_rate_scale; float mechanical_power_penalty_scale; float position_target_error_penalty_scale;
   float rot_dist_decreasing_reward_scale; float no_rot_dist_decreasing_reward_thresh; float default_quaternion[4];
   int32_t dof_index[12];
   const float* obs64;          /* [N,64] scratch written by lm_task_post_step          */
-  const float* root_quat;      /* [N,4]                                                */
   const float* dof_pos;        /* [N,20] post-step articulation state                  */
   const float* dof_vel;        /* [N,20]                                               */
   const float* goal;           /* [N,4]                                                */
@@ -302,9 +304,9 @@ typedef struct LmCustomController {
   float* last_targets;         /* [N,12]                                               */
   float* joint_pos;            /* [N,12] carried joint state of the PD loop            */
   float* joint_vel;            /* [N,12]                                               */
-  float* last_rot_dist;        /* [N]                                                  */
+  float* last_rot_dist;        /* [N]    NULL without LM_CC_ROT_DIST_TERM              */
   float* obs;                  /* [N,88] out                                           */
-  float* states;               /* [N,93] patched in place                              */
+  float* states;               /* [N,93] patched in place; columns 6..9 hold the frame quaternion k_post computed */
   float* rew;                  /* [N]    in / out                                      */
   float* extras;               /* [LM_NUM_EXTRAS]                                      */
   const int64_t* reset_env_ids; const int32_t* num_reset;   /* lm_cc_pre: what lm_task_pre_step left */

@@ -81,11 +81,11 @@ class LmRolloutBuffers(C.Structure):
 
 
 class LmCustomController(C.Structure):
-    _fields_ = [("num_envs", _i32), ("clip_reward", _i32), ("clamp_observations", _i32), ("pad_", _i32),
+    _fields_ = [("num_envs", _i32), ("clip_reward", _i32), ("clamp_observations", _i32), ("flags", _i32),
                 ("clip_observations", _f), ("target_obs_scale", _f), ("action_rate_scale", _f), ("mechanical_power_penalty_scale", _f),
                 ("position_target_error_penalty_scale", _f), ("rot_dist_decreasing_reward_scale", _f),
                 ("no_rot_dist_decreasing_reward_thresh", _f), ("default_quaternion", _f * 4), ("dof_index", _i32 * NUM_ACT)] + \
-               [(n, C.c_void_p) for n in ("obs64", "root_quat", "dof_pos", "dof_vel", "goal", "torque", "targets", "last_targets", "joint_pos",
+               [(n, C.c_void_p) for n in ("obs64", "dof_pos", "dof_vel", "goal", "torque", "targets", "last_targets", "joint_pos",
                                           "joint_vel", "last_rot_dist", "obs", "states", "rew", "extras", "reset_env_ids", "num_reset")]
 
 

@@ -151,6 +151,8 @@ class TaskConfig:
     rot_dist_decreasing_reward_scale: float = 0.0          # :50 (``# 50``), :542-545
     no_rot_dist_decreasing_reward_thresh: float = 0.3      # :51
     clip_reward: bool = False                              # :65, :619-620
+    cc_rot_dist_term: bool = True                          # the rot-dist-decrease term and last_rot_dist exist in the locomotion file only
+    cc_update_last_targets: bool = True                    # :724; the manipulation file never refreshes last_joint_position_targets after a reset
 
     @property
     def time_interval(self) -> float:
@@ -267,6 +269,18 @@ def quadruped_pose_control_custom_controller() -> TaskConfig:
                       pd_control_decimal=4, pd_torque_divisor=4.0, pd_init_se=list(_CC_INIT_SE))
 
 
+def quadruped_manipulate_plate_custom_controller() -> TaskConfig:
+    """quadruped_manipulate_plate_custom_controller.py; cfg/task/QuadrupedManipulatePlateCustomController.yaml.  Robot at the
+    origin with the robot-file default pose, plate at z 0.18, no rot-dist-decrease term, last targets frozen after a reset."""
+    return TaskConfig(name="QuadrupedManipulatePlateCustomController", kind=KIND_MANI, vertical=False, control_mode=CONTROL_PD,
+                      custom_controller=True, cc_rot_dist_term=False, cc_update_last_targets=False, num_observations=88, num_states=93,
+                      joint_acc_scale=-0.00015, action_rate_scale=-0.01, success_thresh=0.15, max_consecutive_successes=20,
+                      mani_init_joint_pos=list(_HORIZONTAL_ROBOT_INIT), mani_default_position=[0.0, 0.0, 0.0],
+                      obj_default_position=[0.0, 0.0, 0.18], indicator_mani_position=[0.0, 0.0, 0.3],
+                      dt=0.005, control_frequency_inv=1, max_episode_length=500,
+                      pd_control_decimal=4, pd_torque_divisor=4.0, pd_init_se=list(_CC_INIT_SE))
+
+
 TASK_CONFIGS = {
     "QuadrupedPoseControl": quadruped_pose_control,
     "QuadrupedPoseControlVertical": quadruped_pose_control_vertical,
@@ -278,6 +292,7 @@ TASK_CONFIGS = {
     "QuadrupedManipulatePlatePositionControl": quadruped_manipulate_plate_position_control,
     "JointLocomanipulationPositionControl": joint_locomanipulation_position_control,
     "QuadrupedPoseControlCustomController": quadruped_pose_control_custom_controller,
+    "QuadrupedManipulatePlateCustomController": quadruped_manipulate_plate_custom_controller,
 }
 
 

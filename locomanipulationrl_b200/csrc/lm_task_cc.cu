@@ -1,5 +1,7 @@
 // *_custom_controller.py task variants: the rows the variant adds on top of the shared task kernels.
-// Reference: tasks/quadruped_pose_control_tasks/quadruped_pose_control_custom_controller.py (cited per line below).
+// Reference: tasks/quadruped_pose_control_tasks/quadruped_pose_control_custom_controller.py (cited per line below) and its
+// manipulation sibling tasks/quadruped_manipulate_plate/quadruped_manipulate_plate_custom_controller.py (same rows, minus the
+// rot-dist-decrease term and the per-step refresh of last_joint_position_targets).
 // k_pre / k_post (lm_task.cu) run unchanged; k_cc_pre / k_cc_post are one thread per env, straight-line.
 #include "lm_common.cuh"
 #include "lm_host.h"
@@ -41,11 +43,13 @@ __global__ void __launch_bounds__(THREADS) k_cc_post(const PostArgs a) {
   const int e = blockIdx.x * THREADS + tid;
   float red[NRED] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (e < c.num_envs) {
-    // ---- raw orientation error (:430, :515-516): ground_quaternion = conj(base quaternion)
-    const float4 q4 = *reinterpret_cast<const float4*>(c.root_quat + (size_t)e * 4);
+    // ---- raw orientation error (:430, :515-516).  The frame quaternion (ground_quaternion = conj(base quaternion); plate quaternion
+    // in the robot frame for the manipulation file) is what k_post left in the states row, columns 6..9 (quaternion scale 1).
+    float* st = c.states + (size_t)e * 93;
     const float4 g4 = *reinterpret_cast<const float4*>(c.goal + (size_t)e * 4);
-    const Quat diff = quat_mul(quat_conj(Quat{q4.x, q4.y, q4.z, q4.w}), quat_conj(Quat{g4.x, g4.y, g4.z, g4.w}));
-    const float rot_dist = rot_distance(diff);
+    const Quat diff = quat_mul(Quat{st[6], st[7], st[8], st[9]}, quat_conj(Quat{g4.x, g4.y, g4.z, g4.w}));
+    const bool rot_term = (c.flags & LM_CC_ROT_DIST_TERM) != 0;
+    const float rot_dist = rot_term ? rot_distance(diff) : 0.0f;
     const float lim = c.clip_observations;
     float dq[4] = {diff.w, diff.x, diff.y, diff.z};
     if (c.clamp_observations) {
@@ -93,7 +97,6 @@ __global__ void __launch_bounds__(THREADS) k_cc_post(const PostArgs a) {
       o88[19 + q] = l;
     }
     // ---- states row: quat_diff columns 41..44 (:474)
-    float* st = c.states + (size_t)e * 93;
 #pragma unroll
     for (int k = 0; k < 4; ++k) st[41 + k] = dq[k];
     // ---- reward terms (:531-546)
@@ -107,10 +110,14 @@ __global__ void __launch_bounds__(THREADS) k_cc_post(const PostArgs a) {
     const float arate = mul(a_sum, c.action_rate_scale);
     const float mech_pen = mul(c.mechanical_power_penalty_scale, mech);
     const float terr_pen = mul(c.position_target_error_penalty_scale, terr);
-    const float larger = rot_dist > c.no_rot_dist_decreasing_reward_thresh ? 1.0f : 0.0f;
-    const float rdec = mul(mul(larger, sub(c.last_rot_dist[e], rot_dist)), c.rot_dist_decreasing_reward_scale);
-    c.last_rot_dist[e] = rot_dist;
-    float total = add(add(add(add(c.rew[e], arate), mech_pen), terr_pen), rdec);
+    float rdec = 0.0f;
+    float total = add(add(add(c.rew[e], arate), mech_pen), terr_pen);
+    if (rot_term) {
+      const float larger = rot_dist > c.no_rot_dist_decreasing_reward_thresh ? 1.0f : 0.0f;
+      rdec = mul(mul(larger, sub(c.last_rot_dist[e], rot_dist)), c.rot_dist_decreasing_reward_scale);
+      c.last_rot_dist[e] = rot_dist;
+      total = add(total, rdec);
+    }
     if (c.clip_reward) total = fmaxf(total, 0.0f);                                  // :619-620 (fall_penalty is 0 in the file)
     c.rew[e] = total;
     red[0] = arate; red[1] = mech_pen; red[2] = terr_pen; red[3] = rdec;
@@ -118,7 +125,8 @@ __global__ void __launch_bounds__(THREADS) k_cc_post(const PostArgs a) {
     // ---- bookkeeping: last_joint_position_targets (:724), carried joint state (:392-393)
 #pragma unroll
     for (int q = 0; q < 3; ++q) {
-      reinterpret_cast<float4*>(c.last_targets + (size_t)e * 12)[q] = make_float4(tg[4 * q], tg[4 * q + 1], tg[4 * q + 2], tg[4 * q + 3]);
+      if (c.flags & LM_CC_UPDATE_LAST_TARGETS)
+        reinterpret_cast<float4*>(c.last_targets + (size_t)e * 12)[q] = make_float4(tg[4 * q], tg[4 * q + 1], tg[4 * q + 2], tg[4 * q + 3]);
       reinterpret_cast<float4*>(c.joint_pos + (size_t)e * 12)[q] = make_float4(jp[4 * q], jp[4 * q + 1], jp[4 * q + 2], jp[4 * q + 3]);
       reinterpret_cast<float4*>(c.joint_vel + (size_t)e * 12)[q] = make_float4(jv[4 * q], jv[4 * q + 1], jv[4 * q + 2], jv[4 * q + 3]);
     }
@@ -164,7 +172,7 @@ __global__ void __launch_bounds__(THREADS) k_cc_post(const PostArgs a) {
       if (tid == 0) c.extras[LM_EXTRA_ACTION_RATE_PENALTY] = (float)(d / n);
       if (tid == 1) c.extras[LM_EXTRA_MECHANICAL_POWER_PENALTY] = (float)(d / n);
       if (tid == 2) c.extras[LM_EXTRA_TARGET_ERROR_PENALTY] = (float)(d / n);
-      if (tid == 3) c.extras[LM_EXTRA_ROT_DIST_DECREASING_REW] = (float)(d / n);
+      if (tid == 3 && (c.flags & LM_CC_ROT_DIST_TERM)) c.extras[LM_EXTRA_ROT_DIST_DECREASING_REW] = (float)(d / n);
       if (tid == 4) c.extras[LM_EXTRA_NAN_COUNT] = (float)d;
       if (tid == 5) c.extras[LM_EXTRA_BELOW_M50_COUNT] = (float)d;
     }
@@ -178,12 +186,14 @@ using namespace lm;
 
 static int cc_check(const LmCustomController* c, const char* who, bool post) {
   if (!c) return lm_fail(LM_ERR_BAD_ARG, "%s: NULL", who);
-  if (c->num_envs <= 0 || !c->goal || !c->last_rot_dist) return lm_fail(LM_ERR_BAD_ARG, "%s: bad num_envs / NULL tensor", who);
+  if (c->num_envs <= 0 || !c->goal) return lm_fail(LM_ERR_BAD_ARG, "%s: bad num_envs / NULL tensor", who);
+  if ((c->flags & LM_CC_ROT_DIST_TERM) && !c->last_rot_dist) return lm_fail(LM_ERR_BAD_ARG, "%s: last_rot_dist is NULL", who);
+  if (!post && !(c->flags & LM_CC_ROT_DIST_TERM)) return lm_fail(LM_ERR_BAD_ARG, "%s: nothing to do without the rot-dist term", who);
   if (!post) return (c->reset_env_ids && c->num_reset) ? LM_OK : lm_fail(LM_ERR_BAD_ARG, "%s: reset id list missing", who);
-  const void* ptrs[] = {c->obs64, c->root_quat, c->dof_pos, c->dof_vel, c->torque, c->targets, c->last_targets, c->joint_pos, c->joint_vel,
+  const void* ptrs[] = {c->obs64, c->dof_pos, c->dof_vel, c->torque, c->targets, c->last_targets, c->joint_pos, c->joint_vel,
                         c->obs, c->states, c->rew, c->extras};
   for (const void* p : ptrs) if (!p) return lm_fail(LM_ERR_BAD_ARG, "%s: NULL tensor", who);
-  const void* al[] = {c->obs64, c->root_quat, c->goal, c->torque, c->targets, c->last_targets, c->joint_pos, c->joint_vel, c->obs};
+  const void* al[] = {c->obs64, c->goal, c->torque, c->targets, c->last_targets, c->joint_pos, c->joint_vel, c->obs};
   for (const void* p : al) if (((uintptr_t)p) & 15) return lm_fail(LM_ERR_ALIGNMENT, "%s: tensor not 16-byte aligned", who);
   return LM_OK;
 }

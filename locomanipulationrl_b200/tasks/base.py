@@ -52,8 +52,8 @@ class LocoManipulationTask:
         idx = self._device.index if self._device.index is not None else torch.cuda.current_device()
         # *_custom_controller files: the shared kernels leave the action-rate term to lm_cc_post (|a| instead of |a_last - a|)
         kcfg = cfg.with_(action_rate_scale=0.0) if cfg.custom_controller else cfg
-        if cfg.custom_controller and (cfg.kind != KIND_LOCO or cfg.num_states != 93):
-            raise _lib.LmError("custom_controller is implemented for the locomotion file (quadruped_pose_control_custom_controller.py)")
+        if cfg.custom_controller and (cfg.kind == KIND_COTRAIN or cfg.num_states != 93 or cfg.quaternion_obs_scale != 1.0):
+            raise _lib.LmError("custom_controller: single-task files with the 93-wide states row and quaternion scale 1 only")
         if cfg.custom_controller and cfg.clip_reward and cfg.fall_penalty != 0.0:
             raise _lib.LmError("clip_reward with a non-zero fall_penalty is not supported (the reference clips before adding it)")
         self._fuse_obs_clamp = bool(fuse_obs_clamp)
@@ -106,10 +106,11 @@ class LocoManipulationTask:
         self._cc = None
         if self.cfg.custom_controller:                                   # …custom_controller.py:161,188,610-612
             self._obs64 = torch.zeros((n, 64), device=dev, dtype=f32)    # what the shared k_post writes; obs_buf is the 88-wide row
-            self.last_rot_dist = torch.zeros(n, device=dev, dtype=f32)
             self.extras["env/rewards/mechanical_power_penalty"] = ex[12]
             self.extras["env/rewards/position_target_error_penalty"] = ex[13]
-            self.extras["env/rewards/rot_dist_decreasing_reward"] = ex[14]
+            if self.cfg.cc_rot_dist_term:
+                self.last_rot_dist = torch.zeros(n, device=dev, dtype=f32)
+                self.extras["env/rewards/rot_dist_decreasing_reward"] = ex[14]
         self.extras["env/success_rate"] = ex[_lib.EXTRA_SUCCESS_RATE]
         if self.cfg.kind == KIND_COTRAIN:
             self.extras["env/success_rate_loco"] = ex[_lib.EXTRA_SUCCESS_RATE + 1]
@@ -161,24 +162,27 @@ class LocoManipulationTask:
 
     def _cc_struct(self):
         """LmCustomController over the current scene views (rebuilt when the scene changes)."""
-        cfg, st = self.cfg, self._scene.loco
+        cfg = self.cfg
+        st = self._scene.loco if cfg.kind == KIND_LOCO else self._scene.mani
         if self._cc is not None and self._cc_scene is self._scene:
             return self._cc
         c = _lib.LmCustomController()
         c.num_envs, c.clip_reward, c.clamp_observations = self._num_envs, int(cfg.clip_reward), int(self._fuse_obs_clamp)
+        c.flags = (1 if cfg.cc_update_last_targets else 0) | (2 if cfg.cc_rot_dist_term else 0)
         c.clip_observations, c.target_obs_scale = cfg.clip_observations, cfg.pd_target_obs_scale
         c.action_rate_scale, c.mechanical_power_penalty_scale = cfg.action_rate_scale, cfg.mechanical_power_penalty_scale
         c.position_target_error_penalty_scale = cfg.position_target_error_penalty_scale
         c.rot_dist_decreasing_reward_scale = cfg.rot_dist_decreasing_reward_scale
         c.no_rot_dist_decreasing_reward_thresh = cfg.no_rot_dist_decreasing_reward_thresh
         for i in range(4):
-            c.default_quaternion[i] = cfg.loco_default_quaternion[i]
+            c.default_quaternion[i] = cfg.loco_default_quaternion[i]          # lm_cc_pre (locomotion file only)
         for j in range(12):
             c.dof_index[j] = self._params.dof_index[j]
-        c.obs64, c.root_quat = self._obs64.data_ptr(), st["root_quat"].data_ptr()
+        c.obs64 = self._obs64.data_ptr()
         c.dof_pos, c.dof_vel, c.goal = st["dof_pos"].data_ptr(), st["dof_vel"].data_ptr(), self.goal_quaternions.data_ptr()
         c.torque, c.targets, c.last_targets = self.torque.data_ptr(), self.current_joint_position_targets.data_ptr(), self.last_joint_position_targets.data_ptr()
-        c.joint_pos, c.joint_vel, c.last_rot_dist = self.joint_positions.data_ptr(), self.joint_velocities.data_ptr(), self.last_rot_dist.data_ptr()
+        c.joint_pos, c.joint_vel = self.joint_positions.data_ptr(), self.joint_velocities.data_ptr()
+        c.last_rot_dist = self.last_rot_dist.data_ptr() if cfg.cc_rot_dist_term else None
         c.obs, c.states, c.rew, c.extras = self.obs_buf.data_ptr(), self.states_buf.data_ptr(), self.rew_buf.data_ptr(), self._extras_buf.data_ptr()
         c.reset_env_ids, c.num_reset = self.reset_env_ids_buf.data_ptr(), self.num_reset_buf.data_ptr()
         if getattr(self, "_cc_ws", None) is None:
@@ -330,7 +334,7 @@ class LocoManipulationTask:
         rc = self._lib.lm_task_pre_step(self._handle, self._lp(), self._mp(), self._env_pos.data_ptr(), C.byref(self._buffers),
                                         actions.data_ptr(), uniforms.data_ptr(), self._stream())
         _lib.check(rc, "lm_task_pre_step")
-        if self.cfg.custom_controller:                                   # last_rot_dist of the envs reset just now (…custom_controller.py:384-386)
+        if self.cfg.custom_controller and self.cfg.cc_rot_dist_term:     # last_rot_dist of the envs reset just now (…custom_controller.py:384-386)
             _lib.check(self._lib.lm_cc_pre(C.byref(self._cc_struct()), self._stream()), "lm_cc_pre")
         if self._pd is not None:
             self._pd_loop(self.current_actions, physics_substep)   # the stashed (adapter-clamped) actions

@@ -20,7 +20,7 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file
 TASK_N = 50            # ragged: n % 4 != 0 (co-train halves of 25) -> exercises the non-TMA tail path of the kernels
 TASK_STEPS = 20        # long enough for the consecutive-success counter to pass 15 and trigger goal resets
 FULL_STEPS = (0, 1, 2, 17, 18, 19)   # steps whose float tensors are stored; the rest keep masks / ints / rewards only
-STEPS_OVERRIDE = {"QuadrupedPoseControlCustomController": 28}   # goal reset needs consecutive_successes > 20 (mirrored in tests/common.py)
+STEPS_OVERRIDE = {"QuadrupedPoseControlCustomController": 28, "QuadrupedManipulatePlateCustomController": 28}   # goal reset needs consecutive_successes > 20 (mirrored in tests/common.py)
 SEED = 7
 
 

@@ -173,7 +173,7 @@ class TaskPort:
             self.torque = torch.zeros(n, 12, dtype=f32)
             self.applied_torque = torch.zeros(n, 12, dtype=f32)
         self.cc = bool(cfg.custom_controller)
-        if self.cc:
+        if self.cc and cfg.cc_rot_dist_term:
             self.last_rot_dist = torch.zeros(n, dtype=f32)                              # …custom_controller.py:188
         self.reset_env_ids = torch.zeros(0, dtype=i64)
         self.inter: Dict[str, torch.Tensor] = {}
@@ -288,7 +288,7 @@ class TaskPort:
             self.current_joint_position_targets[env_ids] = self.default_joint_positions[env_ids]
             self.last_joint_position_targets[env_ids] = self.current_joint_position_targets[env_ids].clone()
             self.current_joint_position_targets_se[env_ids] = torch.tensor(cfg.pd_init_se, dtype=f32).repeat(k, 1)
-        if self.cc:                                                                     # …custom_controller.py:384-386
+        if self.cc and cfg.cc_rot_dist_term:                                            # …custom_controller.py:384-386
             q_def = torch.tensor(cfg.loco_default_quaternion, dtype=f32).repeat(k, 1)
             qd = it.quat_mul(it.quat_conjugate(q_def), it.quat_conjugate(self.goal_quaternions[env_ids]))
             self.last_rot_dist[env_ids] = 2.0 * torch.asin(torch.clamp(torch.norm(qd[:, 1:4], p=2, dim=-1), max=1.0))
@@ -441,14 +441,16 @@ class TaskPort:
             mechanical_power_penalty = cfg.mechanical_power_penalty_scale * mechanical_power
             position_target_error = torch.sum(torch.abs(self.last_joint_position_targets - self.joint_positions), dim=-1)
             position_target_error_penalty = cfg.position_target_error_penalty_scale * position_target_error
-            larger = rot_dist > cfg.no_rot_dist_decreasing_reward_thresh
-            rot_dist_decreasing_reward = larger.to(torch.float32) * (self.last_rot_dist - rot_dist) * cfg.rot_dist_decreasing_reward_scale
-            self.last_rot_dist = rot_dist
-            total = total + mechanical_power_penalty + position_target_error_penalty + rot_dist_decreasing_reward
+            total = total + mechanical_power_penalty + position_target_error_penalty
+            extra_terms = {"mechanical_power_penalty": mechanical_power_penalty, "position_target_error_penalty": position_target_error_penalty}
+            if cfg.cc_rot_dist_term:                                                  # locomotion file only (:541-546)
+                larger = rot_dist > cfg.no_rot_dist_decreasing_reward_thresh
+                rot_dist_decreasing_reward = larger.to(torch.float32) * (self.last_rot_dist - rot_dist) * cfg.rot_dist_decreasing_reward_scale
+                self.last_rot_dist = rot_dist
+                total = total + rot_dist_decreasing_reward
+                extra_terms["rot_dist_decreasing_reward"] = rot_dist_decreasing_reward
             if cfg.clip_reward:
                 total = torch.clip(total, 0.0, None)
-            extra_terms = {"mechanical_power_penalty": mechanical_power_penalty, "position_target_error_penalty": position_target_error_penalty,
-                           "rot_dist_decreasing_reward": rot_dist_decreasing_reward}
         self.rew_buf[:] = total
         self.goal_reset_buf = goal_reset
         both = torch.logical_and(successes, self.successes)                           # QPC:534-545
@@ -484,7 +486,7 @@ class TaskPort:
         self.extras["env/rewards/fall_penalty"] = fall.mean()
         rb[:] = torch.where(self.goal_reset_buf == 1, one, rb)
         rb[:] = torch.where(self.progress_buf >= cfg.max_episode_length - 1, one, rb)
-        if self.cc:                                                                   # …custom_controller.py:724
+        if self.cc and cfg.cc_update_last_targets:                                    # …custom_controller.py:724
             self.last_joint_position_targets = self.current_joint_position_targets.clone()
         groups = [("", slice(0, self.num_envs))]
         if cfg.kind == KIND_COTRAIN:                                                   # JLV:769-798

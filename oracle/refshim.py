@@ -318,6 +318,7 @@ _TASK_CLASSES = {
     "QuadrupedManipulatePlatePositionControl": ("tasks.quadruped_manipulate_plate.quadruped_manipulate_plate_position_control", "QuadrupedManipulatePlatePositionControl"),
     "JointLocomanipulationPositionControl": ("tasks.joint_train_locomanipulation.joint_locomanipulation_position_control", "JointLocomanipulationPositionControl"),
     "QuadrupedPoseControlCustomController": ("tasks.quadruped_pose_control_tasks.quadruped_pose_control_custom_controller", "QuadrupedPoseControlCustomController"),
+    "QuadrupedManipulatePlateCustomController": ("tasks.quadruped_manipulate_plate.quadruped_manipulate_plate_custom_controller", "QuadrupedManipulatePlateCustomController"),
 }
 
 

@@ -12,7 +12,7 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 GOLDEN_N, GOLDEN_STEPS, GOLDEN_SEED = 50, 20, 7
 GOLDEN_FULL_STEPS = (0, 1, 2, 17, 18, 19)
 # fixtures of tasks whose goal reset needs more than 20 steps (custom controller: max_consecutive_successes = 20)
-GOLDEN_STEPS_OVERRIDE = {"QuadrupedPoseControlCustomController": 28}
+GOLDEN_STEPS_OVERRIDE = {"QuadrupedPoseControlCustomController": 28, "QuadrupedManipulatePlateCustomController": 28}
 
 
 def golden_steps(name):
@@ -166,7 +166,7 @@ class CudaRollout:
         if self.cfg.control_mode == configs.CONTROL_PD:
             self._track("pd_state", assert_close(f"step {t} pd joint_positions (post)", task.joint_positions, p.joint_positions))
             self._track("pd_state", assert_close(f"step {t} pd last_targets", task.last_joint_position_targets, p.last_joint_position_targets))
-        if self.cfg.custom_controller:
+        if self.cfg.custom_controller and self.cfg.cc_rot_dist_term:
             self._track("last_rot_dist", assert_close(f"step {t} last_rot_dist", task.last_rot_dist, p.last_rot_dist, rtol=1e-6, atol=1e-6))
         if self.exempt_events == 0:
             for k, v in p.extras.items():

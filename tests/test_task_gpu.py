@@ -63,7 +63,8 @@ def test_cuda_matches_golden_reference_vectors(name):
                                     ("JointLocomanipulationVertical", 8192), ("JointLocomanipulation", 4096),
                                     ("QuadrupedPoseControlVertical", 1024), ("QuadrupedManipulatePlateVertical", 1024),
                                     ("QuadrupedPoseControlPositionControl", 2048), ("QuadrupedManipulatePlatePositionControl", 2048),
-                                    ("JointLocomanipulationPositionControl", 4096), ("QuadrupedPoseControlCustomController", 4096)])
+                                    ("JointLocomanipulationPositionControl", 4096), ("QuadrupedPoseControlCustomController", 4096),
+                                    ("QuadrupedManipulatePlateCustomController", 2048)])
 def test_cuda_matches_oracle_port_rollout(name, n):
     """BASELINE.json configs 1-3 shapes (config 3 at 8192 to keep the CPU oracle quick): 24-step rollouts, TMA tile path."""
     ro = CudaRollout(name, n)

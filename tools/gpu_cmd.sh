@@ -1,1 +1,1 @@
-timeout 1200 python -m pytest tests/test_task_gpu.py -m gpu -q -x -k "CustomController or custom_controller" 2>&1 | tail -25 > gpurun_out/t.log
+timeout 1200 python -m pytest tests/test_task_gpu.py tests/test_cabi.py -m gpu -q -x -k "CustomController or custom_controller or cabi" 2>&1 | tail -25 > gpurun_out/t.log
