@@ -219,10 +219,30 @@ __global__ void __launch_bounds__(THREADS, 1) k_rms_update(const float* __restri
   const size_t gtid = (size_t)blockIdx.x * THREADS + tid, gstride = (size_t)gridDim.x * THREADS;
   float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
   if (st.dim == 1) {
-    // scalar column: every thread sums into "channel 0" of its quad; the quads are merged below
+    // scalar column: 128-bit loads, four of them in flight per thread; every thread sums into its own pair, merged below
     const float shift = (float)st.mean[0];
-    for (size_t i = gtid; i < (size_t)n; i += gstride) {
-      const float d = x[i] - shift;
+    const size_t n4 = (((uintptr_t)x) & 15) == 0 ? (size_t)n >> 2 : 0;
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    size_t i = gtid;
+    for (; i + 3 * gstride < n4; i += 4 * gstride) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = ld_nc_f4(reinterpret_cast<const float*>(x4 + i + u * gstride));
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float d[4] = {v[u].x - shift, v[u].y - shift, v[u].z - shift, v[u].w - shift};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { s1[0] += d[k]; s2[0] = fmaf(d[k], d[k], s2[0]); }
+      }
+    }
+    for (; i < n4; i += gstride) {
+      const float4 v = ld_nc_f4(reinterpret_cast<const float*>(x4 + i));
+      const float d[4] = {v.x - shift, v.y - shift, v.z - shift, v.w - shift};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { s1[0] += d[k]; s2[0] = fmaf(d[k], d[k], s2[0]); }
+    }
+    for (size_t j = (n4 << 2) + gtid; j < (size_t)n; j += gstride) {
+      const float d = x[j] - shift;
       s1[0] += d; s2[0] = fmaf(d, d, s2[0]);
     }
   } else {

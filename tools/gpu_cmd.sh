@@ -1,1 +1,2 @@
-timeout 1200 python -m pytest tests/test_task_gpu.py tests/test_cabi.py -m gpu -q -x -k "CustomController or custom_controller or cabi" 2>&1 | tail -25 > gpurun_out/t.log
+timeout 900 python -m pytest tests/test_rollout.py tests/test_ppo.py -m gpu -q -x 2>&1 | tail -5 > gpurun_out/t.log
+python tools/update_bench.py > gpurun_out/update_bench.log 2>&1
