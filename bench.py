@@ -457,6 +457,9 @@ def cuda_arm(args):
 
     # ---- e2e: C-ABI host entry, pinned host buffers in, results out, every step
     e2e = None if args.no_e2e else e2e_arm(pipe, args, world, device, rank)
+    if e2e is not None and world == 1:        # the same step with the observations copied back as well (a host-side policy's data flow)
+        full = e2e_arm(pipe, args, world, device, rank, readback_obs=True, shards=4)     # 21 MB back per step: pipelining over shards pays here
+        e2e["with_obs_readback"] = {k: full[k] for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step", "ms_per_step", "api")}
 
     # ---- CPU baseline (rank 0, N=1 only)
     cpu = None
@@ -519,17 +522,20 @@ def large_roofline(device, graph_time, hbm, n=524288):
             "bytes_per_env": B_POST}
 
 
-def e2e_arm(pipe, args, world, device, rank=0):
+def e2e_arm(pipe, args, world, device, rank=0, readback_obs=False, shards=None):
     """Same step through the host-buffer API (ShardedHostStepper -> lm_task_step_host_async per env shard): H2D of
-    actions / uniforms / physics state from pinned memory, kernels, D2H of obs / rew / reset, the policy forward and D2H
-    of its outputs, every step, with a host synchronisation at the end of every step.  Max over ranks."""
+    actions / uniforms / physics state from pinned memory, kernels, D2H of rew / reset, the policy forward and D2H of its
+    outputs (the next actions, value), every step, with a host synchronisation at the end of every step.  Max over ranks.
+    The policy is device-resident, so by default the observations stay on the device (the reference's adapter hands them to
+    rl_device = cuda too); ``readback_obs`` adds their D2H copy, the data flow of a host-side policy."""
     import torch.distributed as tdist
     from locomanipulationrl_b200.host_step import ShardedHostStepper
     n = pipe.n
     mlp = pipe.w["policy"] == "mlp"
-    stepper = ShardedHostStepper(pipe.cfg, n, pipe.policy, shards=args.e2e_shards, device=device, seed=1000 * rank + 42,
+    shards = shards or args.e2e_shards
+    stepper = ShardedHostStepper(pipe.cfg, n, pipe.policy, shards=shards, device=device, seed=1000 * rank + 42,
                                  env_id_offset=rank * n, norm_mean=pipe.norm_mean if mlp else None,
-                                 norm_inv_std=pipe.norm_inv_std if mlp else None)
+                                 norm_inv_std=pipe.norm_inv_std if mlp else None, readback_obs=readback_obs)
     sets = []                                     # STATE_SETS x shards pinned host states (> L2, and never the same twice in a row)
     for i in range(STATE_SETS):
         sets.append([s.scene.pack_host(s.scene.generate(i)) for s in stepper.shards])
@@ -553,8 +559,9 @@ def e2e_arm(pipe, args, world, device, rank=0):
         tdist.all_reduce(dt, op=tdist.ReduceOp.MAX)
     return {"value": n * world * steps / float(dt.item()), "unit": "env-steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
             "steps": steps, "ms_per_step": float(dt.item()) / steps * 1e3,
-            "api": f"ShardedHostStepper.step: {args.e2e_shards} env shards x (lm_task_step_host_async + policy forward), pinned host buffers, "
-                   "host sync every step"}
+            "api": f"ShardedHostStepper.step: {shards} env shard(s) x (lm_task_step_host_async + policy forward), pinned host buffers, "
+                   "host sync every step; H2D actions, goal uniforms, physics state; D2H next actions, value, reward, reset flags"
+                   + (", observations" if readback_obs else " (observations stay on the device for the device-resident policy)")}
 
 
 _REAL_STDOUT = None
@@ -586,7 +593,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--comm-stream", default="main", choices=["main", "side"],
                     help="where the per-horizon stat + gradient all-reduce runs (N > 1)")
-    ap.add_argument("--e2e-shards", type=int, default=2, help="env shards (streams) the host-buffer step is pipelined over")
+    ap.add_argument("--e2e-shards", type=int, default=1,
+                    help="env shards (streams) the host-buffer step is pipelined over (measured: 1 is fastest when only 4 MB return per step - "
+                         "fewer, larger PCIe copies; 4 when the observations return too)")
     ap.add_argument("--no-large", action="store_true", help="skip the 524,288-env k_post roofline line")
     ap.add_argument("--no-kernel-times", action="store_true",
                     help="skip the per-kernel timing section (ncu launch lists: the capture then holds the warm-up and timed steps only)")

@@ -4,8 +4,11 @@ The batch is split into ``shards`` env shards — the same block sharding the mu
 are independent; every shard keeps its own locomotion/manipulation halves) — each with its own task handle, CUDA
 stream and pinned host buffers.  One ``step`` enqueues, per shard and without any host synchronisation in between,
 
-    H2D actions + goal uniforms -> pre_physics_step -> H2D physics state -> post_physics_step -> D2H obs/rew/reset
+    H2D actions + goal uniforms -> pre_physics_step -> H2D physics state -> post_physics_step -> D2H [obs/]rew/reset
     -> policy forward -> D2H mu/value                         (lm_task_step_host_async + lm_mlp_forward)
+
+(``readback_obs=False`` keeps the observations on the device for the device-resident policy, as the reference's adapter
+does with ``rl_device = cuda``; the actions, value, reward and reset flags still return to the host every step)
 
 so shard k's host->device copies overlap shard k-1's kernels and device->host copies (PCIe is full duplex), then
 waits for every shard.  Inputs and outputs live in pinned host memory; nothing is cached across steps.
@@ -23,7 +26,7 @@ from .tasks.base import LocoManipulationTask
 
 
 class _Shard:
-    def __init__(self, cfg: TaskConfig, n: int, device, seed: int, env_id_offset: int):
+    def __init__(self, cfg: TaskConfig, n: int, device, seed: int, env_id_offset: int, readback_obs: bool = True):
         pin = lambda *shape, dtype=torch.float32: torch.zeros(*shape, dtype=dtype).pin_memory()
         self.n = n
         self.scene = synthetic.SyntheticScene(cfg, n, device=device, seed=seed, env_id_offset=env_id_offset)
@@ -40,22 +43,28 @@ class _Shard:
         self.io = _lib.LmHostStep()
         self.io.actions_dev, self.io.uniforms_dev = self.actions_dev.data_ptr(), self.uniforms_dev.data_ptr()
         self.io.uniforms_host = self.uniforms_host.data_ptr()
-        self.io.obs_host, self.io.rew_host, self.io.reset_host = self.obs_host.data_ptr(), self.rew_host.data_ptr(), self.reset_host.data_ptr()
+        # obs_host = NULL: the observations stay on the device for the device-resident policy (the reference's own data flow:
+        # VecEnvRLGames hands them to rl_device = cuda); actions, value, reward and reset flags still return every step
+        self.io.obs_host = self.obs_host.data_ptr() if readback_obs else None
+        self.io.rew_host, self.io.reset_host = self.rew_host.data_ptr(), self.reset_host.data_ptr()
 
 
 class ShardedHostStepper:
     def __init__(self, cfg: TaskConfig, num_envs: int, policy, shards: int = 4, device="cuda:0", seed: int = 42,
-                 env_id_offset: int = 0, norm_mean: Optional[torch.Tensor] = None, norm_inv_std: Optional[torch.Tensor] = None):
+                 env_id_offset: int = 0, norm_mean: Optional[torch.Tensor] = None, norm_inv_std: Optional[torch.Tensor] = None,
+                 readback_obs: bool = True):
         if num_envs % shards or (num_envs // shards) % 2:
             raise _lib.LmError("num_envs must split into an even number of envs per shard")
         self.lib = _lib.load()
         self.cfg, self.policy, self.device = cfg, policy, torch.device(device)
         self.norm_mean, self.norm_inv_std = norm_mean, norm_inv_std
         n = num_envs // shards
-        self.shards: List[_Shard] = [_Shard(cfg, n, self.device, seed + 17 * k, env_id_offset + k * n) for k in range(shards)]
+        self.readback_obs = bool(readback_obs)
+        self.shards: List[_Shard] = [_Shard(cfg, n, self.device, seed + 17 * k, env_id_offset + k * n, self.readback_obs) for k in range(shards)]
         self.parity = 0
         self.h2d_bytes = sum(4 * (s.actions_dev.numel() + s.uniforms_dev.numel()) for s in self.shards)
-        self.d2h_bytes = sum(4 * (s.obs_host.numel() + s.rew_host.numel() + 12 * s.n + s.n) + 8 * s.reset_host.numel() for s in self.shards)
+        self.d2h_bytes = sum(4 * ((s.obs_host.numel() if self.readback_obs else 0) + s.rew_host.numel() + 12 * s.n + s.n) + 8 * s.reset_host.numel()
+                             for s in self.shards)
 
     def step(self, host_states: List[Dict[str, torch.Tensor]]) -> None:
         """One env step for the whole batch.  ``host_states[k]`` = shard k's PhysX state in pinned host memory, packed like

@@ -1,2 +1,4 @@
-timeout 900 python -m pytest tests/test_rollout.py tests/test_ppo.py -m gpu -q -x 2>&1 | tail -5 > gpurun_out/t.log
-python tools/update_bench.py > gpurun_out/update_bench.log 2>&1
+for sh in 1 8; do
+python bench.py --steps 60 --warmup 3 --no-cpu-baseline --no-large --no-kernel-times --e2e-shards $sh > gpurun_out/e2e_$sh.json 2> gpurun_out/e2e_$sh.err
+done
+python tools/pcie_bw.py > gpurun_out/pcie.log 2>&1
