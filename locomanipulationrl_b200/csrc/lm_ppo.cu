@@ -9,6 +9,7 @@
 // HBM-bound, one launch instead of the ~40 element-wise launches of the torch graph (forward + backward).
 #include "lm_common.cuh"
 #include "lm_host.h"
+#include "lm_reduce.cuh"
 
 namespace lm {
 namespace ppo {
@@ -33,9 +34,8 @@ __device__ __forceinline__ void ld12(const float* p, float v[12]) {
 __global__ void __launch_bounds__(THREADS) k_ppo_loss(const Args a) {
   __shared__ double sm[THREADS / 32][NRED];
   __shared__ float s_sigma[12], s_inv_var[12], s_old_sigma[12];
-  __shared__ unsigned int s_last;
   const LmPpoBatch& B = a.b;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x;
   if (tid < 12) {
     const float sg = expf(B.log_std[tid]);
     s_sigma[tid] = sg;
@@ -112,50 +112,15 @@ __global__ void __launch_bounds__(THREADS) k_ppo_loss(const Args a) {
     }
   }
   // ---- CTA reduction (doubles), last CTA finishes
-#pragma unroll
-  for (int i = 0; i < NRED; ++i) {
-    double d = (double)red[i];
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) d += __shfl_xor_sync(0xffffffffu, d, off);
-    if (lane == 0) sm[warp][i] = d;
-  }
-  __syncthreads();
-  if (tid < NRED) {
-    double d = 0.0;
-#pragma unroll
-    for (int w = 0; w < THREADS / 32; ++w) d += sm[w][tid];
-    a.partials[(size_t)blockIdx.x * NRED + tid] = d;
-  }
-  __syncthreads();
-  if (tid == 0) {
-    __threadfence();
-    const unsigned int t = atomicAdd(a.ticket, 1u);
-    s_last = (t == gridDim.x - 1) ? 1u : 0u;
-    if (s_last) { *a.ticket = 0u; __threadfence(); }
-  }
-  __syncthreads();
-  if (!s_last) return;
   {
-    // 12 subsets of CTAs x 20 values: thread (sub, j) sums its strided share with 4 loads in flight, then the subsets meet
+    const double d = cta_sum<NRED, THREADS>(red, sm);
+    if (tid < NRED) a.partials[(size_t)blockIdx.x * NRED + tid] = d;
+  }
+  if (!last_cta(a.ticket)) return;
+  {
     __shared__ double part[12][NRED];
-    const int sub = tid / NRED, j = tid - sub * NRED;
-    if (sub < 12) {
-      double acc[4] = {0.0, 0.0, 0.0, 0.0};
-      int c = sub;
-      for (; c + 36 < (int)gridDim.x; c += 48) {
-#pragma unroll
-        for (int u = 0; u < 4; ++u) acc[u] += __ldcg(a.partials + (size_t)(c + 12 * u) * NRED + j);
-      }
-      for (; c < (int)gridDim.x; c += 12) acc[0] += __ldcg(a.partials + (size_t)c * NRED + j);
-      part[sub][j] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
-    }
-    __syncthreads();
-    if (tid < NRED) {
-      double d = 0.0;
-#pragma unroll
-      for (int u = 0; u < 12; ++u) d += part[u][tid];
-      sm[0][tid] = d;
-    }
+    const double d = grid_sum<NRED, 12>(a.partials, part);
+    if (tid < NRED) sm[0][tid] = d;
   }
   __syncthreads();
   if (tid < 12) {

@@ -14,6 +14,7 @@
 // and the scalar columns.  Algorithmic bytes: 368 read + 368 written per env-step (+48 for actions_out).
 #include "lm_common.cuh"
 #include "lm_host.h"
+#include "lm_reduce.cuh"
 
 namespace lm {
 namespace rollout {
@@ -66,20 +67,6 @@ __device__ __forceinline__ void cta_moments(const float s1[4], const float s2[4]
     for (int w = 0; w < THREADS / 32; ++w) s += sm[(w * 16 + quad) * 8 + k];
     out[tid] = s;
   }
-}
-
-// last-CTA pattern: returns true in exactly one CTA, after every CTA's partials are visible
-__device__ __forceinline__ bool last_cta(unsigned int* ticket) {
-  __shared__ unsigned int s_last;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    const unsigned int t = atomicAdd(ticket, 1u);
-    s_last = (t == gridDim.x - 1) ? 1u : 0u;
-    if (s_last) { *ticket = 0u; __threadfence(); }
-  }
-  __syncthreads();
-  return s_last != 0u;
 }
 
 // grid-wide sum of partials[cta][PART] -> sm_tot[PART] (deterministic order), by the last CTA

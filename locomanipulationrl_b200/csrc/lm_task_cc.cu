@@ -5,6 +5,7 @@
 // k_pre / k_post (lm_task.cu) run unchanged; k_cc_pre / k_cc_post are one thread per env, straight-line.
 #include "lm_common.cuh"
 #include "lm_host.h"
+#include "lm_reduce.cuh"
 
 void lm_rollout_workspace(LmRollout* r, double** partials, unsigned int** ticket, int* sm_count);   // lm_rollout.cu (library-internal)
 
@@ -37,9 +38,8 @@ struct PostArgs {
 
 __global__ void __launch_bounds__(THREADS) k_cc_post(const PostArgs a) {
   __shared__ double sm[THREADS / 32][NRED];
-  __shared__ unsigned int s_last;
   const LmCustomController& c = a.c;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x;
   const int e = blockIdx.x * THREADS + tid;
   float red[NRED] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (e < c.num_envs) {
@@ -132,42 +132,15 @@ __global__ void __launch_bounds__(THREADS) k_cc_post(const PostArgs a) {
     }
   }
   // ---- means of the new terms (extras), deterministic: per-CTA doubles -> last CTA
-#pragma unroll
-  for (int i = 0; i < NRED; ++i) {
-    double d = (double)red[i];
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) d += __shfl_xor_sync(0xffffffffu, d, off);
-    if (lane == 0) sm[warp][i] = d;
-  }
-  __syncthreads();
-  if (tid < NRED) {
-    double d = 0.0;
-#pragma unroll
-    for (int w = 0; w < THREADS / 32; ++w) d += sm[w][tid];
-    a.partials[(size_t)blockIdx.x * NRED + tid] = d;
-  }
-  __syncthreads();
-  if (tid == 0) {
-    __threadfence();
-    const unsigned int t = atomicAdd(a.ticket, 1u);
-    s_last = (t == gridDim.x - 1) ? 1u : 0u;
-    if (s_last) { *a.ticket = 0u; __threadfence(); }
-  }
-  __syncthreads();
-  if (!s_last) return;
   {
-    // thread (sub, j): strided share of the CTAs, 4 loads in flight; 32 subsets x 6 values
+    const double d = cta_sum<NRED, THREADS>(red, sm);
+    if (tid < NRED) a.partials[(size_t)blockIdx.x * NRED + tid] = d;
+  }
+  if (!last_cta(a.ticket)) return;
+  {
     __shared__ double part[32][NRED];
-    const int sub = tid / NRED, j = tid - sub * NRED;
-    if (sub < 32) {
-      double acc = 0.0;
-      for (int b = sub; b < (int)gridDim.x; b += 32) acc += __ldcg(a.partials + (size_t)b * NRED + j);
-      part[sub][j] = acc;
-    }
-    __syncthreads();
+    const double d = grid_sum<NRED, 32>(a.partials, part);
     if (tid < NRED) {
-      double d = 0.0;
-      for (int u = 0; u < 32; ++u) d += part[u][tid];
       const double n = (double)c.num_envs;
       if (tid == 0) c.extras[LM_EXTRA_ACTION_RATE_PENALTY] = (float)(d / n);
       if (tid == 1) c.extras[LM_EXTRA_MECHANICAL_POWER_PENALTY] = (float)(d / n);
