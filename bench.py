@@ -423,14 +423,17 @@ def cuda_arm(args):
         ms_pre = max(graph_time(pre_post) - ms_post, 1e-6)      # pre needs a preceding post (its reset scan is post's by-product)
         ms_pol = graph_time(policy_only)
         hbm, tf, src = measured_peaks()
-        ach = n * B_POST / (ms_post * 1e-3) / 1e9
-        ach_task = n * B_TASK / ((ms_post + ms_pre) * 1e-3) / 1e9
+        # single-task files with the 93-wide states_buf write 372 B/env more (1 036 -> 1 408 B/env-step)
+        b_states = 372 if pipe.cfg.num_states == 93 else 0
+        b_post, b_task = B_POST + b_states, B_TASK + b_states
+        ach = n * b_post / (ms_post * 1e-3) / 1e9
+        ach_task = n * b_task / ((ms_post + ms_pre) * 1e-3) / 1e9
         line_extra["roofline"] = {"kernel": "k_post (post_physics_step)", "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s",
                                   "frac": ach / hbm, "traffic": measured_traffic("k_post_lean") if pipe.w["task"].startswith("Joint") else None,
                                   "traffic_unit": "bytes per launch (ncu dram read + write, 65,536 envs; stores mostly still in L2 at kernel end)",
-                                  "algorithmic_bytes": n * B_POST, "peak_source": src, "bytes_per_env": B_POST, "ms": ms_post}
+                                  "algorithmic_bytes": n * b_post, "peak_source": src, "bytes_per_env": b_post, "ms": ms_post}
         line_extra["roofline_task"] = {"kernels": "k_reset_count + k_pre + k_post", "bound": "hbm", "achieved": ach_task, "peak": hbm,
-                                       "unit": "GB/s", "frac": ach_task / hbm, "bytes_per_env": B_TASK, "ms": ms_post + ms_pre}
+                                       "unit": "GB/s", "frac": ach_task / hbm, "bytes_per_env": b_task, "ms": ms_post + ms_pre}
         if pipe.w["policy"] == "mlp":
             tfl = n * MLP_FLOPS / (ms_pol * 1e-3) / 1e12
             line_extra["roofline_policy"] = {"kernel": "k_mlp_forward (tcgen05)", "bound": "tensor", "achieved": tfl, "peak": tf, "unit": "TFLOP/s",

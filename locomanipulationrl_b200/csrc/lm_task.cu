@@ -986,40 +986,59 @@ __global__ void __launch_bounds__(T, 4) k_post_lean(const KernelParams kp, const
 // shared memory so the 93-wide rows can be gathered and stored coalesced.
 // ------------------------------------------------------------------------------------------------
 struct PostSmem {
+  // front: inputs that are dead once the env math has run; the [T][93] states rows are assembled over them afterwards
   static constexpr int kDofPos = 0;
   static constexpr int kDofVel = kDofPos + T * 20;
   static constexpr int kPos = kDofVel + T * 20;      // root_pos | plate_pos
   static constexpr int kQuat = kPos + T * 3;
   static constexpr int kLin = kQuat + T * 4;
   static constexpr int kAng = kLin + T * 3;
-  static constexpr int kTips = kAng + T * 3;
-  static constexpr int kKnees = kTips + T * 12;
+  static constexpr int kKnees = kAng + T * 3;
   static constexpr int kEnvPos = kKnees + T * 24;
-  static constexpr int kGoal = kEnvPos + T * 3;
-  static constexpr int kCur = kGoal + T * 4;
+  static constexpr int kCur = kEnvPos + T * 3;
   static constexpr int kLast = kCur + T * 12;
-  static constexpr int kLastJv = kLast + T * 12;
+  static constexpr int kFrontEnd = kLast + T * 12;
+  static constexpr int kStates = 0;                  // [T][93] rows, contiguous like the global tile span
+  // back: what the write-back phase still reads
+  static constexpr int kTips = kFrontEnd;
+  static constexpr int kGoal = kTips + T * 12;
+  static constexpr int kLastJv = kGoal + T * 4;
   static constexpr int kLastTip = kLastJv + T * 12;
   static constexpr int kCurQ = kLastTip + T * 12;
   static constexpr int kObs = kCurQ + T * 4;
   static constexpr int kEnd = kObs + T * OBS_PAD;
   static constexpr int kBytes = kEnd * 4 + 64;
 };
+static_assert(PostSmem::kFrontEnd >= T * LM_NUM_STATES_FULL, "the states rows fit the dead input staging");
 static_assert(T % 4 == 0, "tile spans must stay 16-byte aligned");
 
-// column c of the 93-wide states row                                                         QPC:406-423
-__device__ __forceinline__ float states_elem(const LmTaskParams& P, const float* sm, int r, int c) {
+// the 93-wide states row of env r (QPC:406-423), assembled from what the env math left in shared memory: 93 conflict-free
+// scalar stores per thread (row stride 93 words is odd) instead of a per-element gather with a division by 93
+__device__ __forceinline__ void states_row(const LmTaskParams& P, float* sm, int r, bool clamp) {
   const float* obs = sm + PostSmem::kObs + r * OBS_PAD;
-  if (c < 3) return obs[c];                                   // scaled position
-  if (c < 6) return obs[10 + (c - 3)];                        // scaled linear velocity
-  if (c < 10) return mul(P.quaternion_obs_scale, sm[PostSmem::kCurQ + r * 4 + (c - 6)]);
-  if (c < 13) return obs[13 + (c - 10)];                      // scaled angular velocity
-  if (c < 37) return obs[16 + (c - 13)];                      // joint positions, velocities
-  if (c < 41) return mul(P.quaternion_obs_scale, sm[PostSmem::kGoal + r * 4 + (c - 37)]);
-  if (c < 45) return obs[6 + (c - 41)];                       // quat diff
-  if (c < 57) return mul(P.tip_position_scale, sm[PostSmem::kTips + r * 12 + (c - 45)]);      // tips now (base frame)
-  if (c < 69) return mul(P.tip_position_scale, sm[PostSmem::kLastTip + r * 12 + (c - 57)]);   // tips previous step
-  return obs[40 + (c - 69)];                                  // current, last actions
+  float* row = sm + PostSmem::kStates + r * LM_NUM_STATES_FULL;
+  const float lim = P.clip_observations;
+  auto put = [&](int c, float v) { row[c] = clamp ? fminf(fmaxf(v, -lim), lim) : v; };
+#pragma unroll
+  for (int k = 0; k < 3; ++k) put(k, obs[k]);                                                     // scaled position
+#pragma unroll
+  for (int k = 0; k < 3; ++k) put(3 + k, obs[10 + k]);                                            // scaled linear velocity
+#pragma unroll
+  for (int k = 0; k < 4; ++k) put(6 + k, mul(P.quaternion_obs_scale, sm[PostSmem::kCurQ + r * 4 + k]));
+#pragma unroll
+  for (int k = 0; k < 3; ++k) put(10 + k, obs[13 + k]);                                           // scaled angular velocity
+#pragma unroll
+  for (int k = 0; k < 24; ++k) put(13 + k, obs[16 + k]);                                          // joint positions, velocities
+#pragma unroll
+  for (int k = 0; k < 4; ++k) put(37 + k, mul(P.quaternion_obs_scale, sm[PostSmem::kGoal + r * 4 + k]));
+#pragma unroll
+  for (int k = 0; k < 4; ++k) put(41 + k, obs[6 + k]);                                            // quat diff
+#pragma unroll
+  for (int k = 0; k < 12; ++k) put(45 + k, mul(P.tip_position_scale, sm[PostSmem::kTips + r * 12 + k]));      // tips now (base frame)
+#pragma unroll
+  for (int k = 0; k < 12; ++k) put(57 + k, mul(P.tip_position_scale, sm[PostSmem::kLastTip + r * 12 + k]));   // tips previous step
+#pragma unroll
+  for (int k = 0; k < 24; ++k) put(69 + k, obs[40 + k]);                                          // current, last actions
 }
 
 __global__ void __launch_bounds__(T, 2) k_post(const KernelParams kp, const PostArgs a) {
@@ -1106,13 +1125,17 @@ __global__ void __launch_bounds__(T, 2) k_post(const KernelParams kp, const Post
       reinterpret_cast<float4*>(obs_g)[i] = *reinterpret_cast<const float4*>(sm + PostSmem::kObs + row * OBS_PAD + c4 * 4);
     }
     if (full_states) {
+      // rows assembled over the dead input staging (every thread passed the barrier above: nobody reads it any more), then the
+      // tile's contiguous [n][93] span leaves with 128-bit stores
+      if (r < n) states_row(P, sm, r, a.clamp_observations != 0);
+      __syncthreads();
       float* st_g = a.buf.states_buf + (size_t)e0 * LM_NUM_STATES_FULL;
       const int total_el = n * LM_NUM_STATES_FULL;
-      for (int i = r; i < total_el; i += T) {
-        const int row = i / LM_NUM_STATES_FULL, c = i - row * LM_NUM_STATES_FULL;
-        float v = states_elem(P, sm, row, c);
-        if (a.clamp_observations) v = fminf(fmaxf(v, -P.clip_observations), P.clip_observations);
-        st_g[i] = v;
+      const float* rows = sm + PostSmem::kStates;
+      if ((total_el & 3) == 0 && ((e0 * LM_NUM_STATES_FULL) & 3) == 0) {
+        for (int i = r; i < (total_el >> 2); i += T) reinterpret_cast<float4*>(st_g)[i] = reinterpret_cast<const float4*>(rows)[i];
+      } else {
+        for (int i = r; i < total_el; i += T) st_g[i] = rows[i];
       }
     }
     if (st.use_tma) {

@@ -1,1 +1,2 @@
-timeout 900 python -m pytest tests/test_rollout.py tests/test_ppo.py tests/test_task_gpu.py -m gpu -q -x -k "rollout or ppo or rms or adam or minibatch or Custom or custom" 2>&1 | tail -5 > gpurun_out/t.log
+timeout 1200 python -m pytest tests/test_task_gpu.py -m gpu -q -x 2>&1 | tail -6 > gpurun_out/t.log
+python bench.py --workload manip16k --steps 192 --warmup 12 --no-cpu-baseline --no-e2e --no-large > gpurun_out/final_manip.json 2> gpurun_out/final_manip.err
