@@ -389,6 +389,21 @@ typedef struct LmPpoBatch {
 } LmPpoBatch;
 int lm_ppo_loss(LmRollout* workspace, const LmPpoBatch* batch, float* grad_mu, float* grad_value, float* grad_log_std,
                 float* stats, void* stream);
+/* Weight gradients of the MLP actor-critic on tcgen05.  Activations and pre-activation gradients of a minibatch
+ * travel as bf16 "tile blobs": a [B, D] matrix stored per 128-sample tile in the UMMA canonical K-major operand layout
+ * (lm_mlp_blob_bytes / _pack / _unpack).  lm_mlp_wgrad accumulates, in TMEM over the whole minibatch,
+ *   dW1 = dZ1^T A0, dW2 = dZ2^T A1, dW3 = dZ3^T A2, dW_head = dH^T A3 and the bias gradients (column sums)
+ * by re-reading the same blobs as MN-major operands (no transpose pass), and writes them in nn.Linear layouts.
+ * dH [B,16]: columns 0..11 dLoss/dmu, 12 dLoss/dvalue, 13..15 zero.  workspace: workspace_ctas * lm_mlp_wgrad_workspace_floats()
+ * floats (one partial per CTA, summed in CTA order: deterministic). */
+int64_t lm_mlp_blob_bytes(int64_t rows, int32_t d);
+int lm_mlp_blob_pack(const float* x, void* blob, int64_t rows, int32_t d, void* stream);
+int lm_mlp_blob_unpack(const void* blob, float* x, int64_t rows, int32_t d, void* stream);
+int32_t lm_mlp_wgrad_workspace_floats(void);
+int lm_mlp_wgrad(const void* dz1, const void* dz2, const void* dz3, const void* dh, const void* a0, const void* a1, const void* a2,
+                 const void* a3, int64_t rows, float* workspace, int32_t workspace_ctas, float* g_w1, float* g_b1, float* g_w2,
+                 float* g_b2, float* g_w3, float* g_b3, float* g_w_mu, float* g_b_mu, float* g_w_value, float* g_b_value, void* stream);
+
 /* torch.nn.utils.clip_grad_norm_(max_norm) (skipped when max_norm <= 0) followed by one torch.optim.Adam step over a flat
  * fp32 parameter arena (the layout dist.FusedHorizonReducer keeps): grads are first multiplied by grad_scale
  * (1 / world size after the all-reduce sum).  `step` counts from 1.  One launch; n <= 2^24 parameters. */

@@ -149,6 +149,11 @@ SYMBOLS = {
     "lm_noise_destroy": (None, [_vp]),
     "lm_noise_apply": (C.c_int, [_vp, C.POINTER(LmNoiseState), _vp, _vp, _vp, _vp, _i32, C.c_uint64, C.c_uint64, _vp]),
     "lm_ppo_loss": (C.c_int, [_vp, C.POINTER(LmPpoBatch), _vp, _vp, _vp, _vp, _vp]),
+    "lm_mlp_blob_bytes": (_i64, [_i64, _i32]),
+    "lm_mlp_blob_pack": (C.c_int, [_vp, _vp, _i64, _i32, _vp]),
+    "lm_mlp_blob_unpack": (C.c_int, [_vp, _vp, _i64, _i32, _vp]),
+    "lm_mlp_wgrad_workspace_floats": (_i32, []),
+    "lm_mlp_wgrad": (C.c_int, [_vp] * 8 + [_i64, _vp, _i32] + [_vp] * 10 + [_vp]),
     "lm_adam_step": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _f, _i32, _f, _f, _vp, _vp]),
     "lm_gae": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _f, _f, _i32, _vp]),
     "lm_gae_env_major": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _f, _f, _i32, _vp]),

@@ -1,0 +1,54 @@
+"""tcgen05 pieces of the PPO update: tile blobs and the weight-gradient GEMMs, against torch on the same bf16 values."""
+import pytest
+import torch
+
+from tests.common import assert_close
+
+pytestmark = pytest.mark.gpu
+
+DIMS = dict(a0=64, a1=256, a2=128, a3=64, dz1=256, dz2=128, dz3=64, dh=16)
+
+
+def _blob(lib, x):
+    from locomanipulationrl_b200 import _lib
+    rows, d = x.shape
+    buf = torch.empty(lib.lm_mlp_blob_bytes(rows, d), dtype=torch.uint8, device="cuda")
+    s = torch.cuda.current_stream().cuda_stream
+    _lib.check(lib.lm_mlp_blob_pack(x.contiguous().data_ptr(), buf.data_ptr(), rows, d, s), "pack")
+    return buf
+
+
+@pytest.mark.parametrize("rows,d", [(1, 8), (128, 64), (300, 256), (1000, 16)])
+def test_blob_round_trip(rows, d):
+    from locomanipulationrl_b200 import _lib
+    lib = _lib.load()
+    x = torch.randn(rows, d, device="cuda")
+    out = torch.empty_like(x)
+    b = _blob(lib, x)
+    _lib.check(lib.lm_mlp_blob_unpack(b.data_ptr(), out.data_ptr(), rows, d, torch.cuda.current_stream().cuda_stream), "unpack")
+    assert torch.equal(out, x.bfloat16().float())
+
+
+@pytest.mark.parametrize("rows", [128, 130, 128 * 7, 128 * 300 + 5])
+def test_weight_gradients_match_torch(rows):
+    """dW = dZ^T A and db = dZ^T 1 from the MN-major re-read of the K-major blobs vs fp32 torch on the bf16-rounded values."""
+    from locomanipulationrl_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator(device="cuda").manual_seed(rows)
+    t = {k: torch.randn(rows, d, device="cuda", generator=g) * (0.5 if k.startswith("a") else 0.05) for k, d in DIMS.items()}
+    t["dh"][:, 13:] = 0.0
+    blobs = {k: _blob(lib, v) for k, v in t.items()}
+    r = {k: v.bfloat16().float() for k, v in t.items()}
+    shapes = dict(w1=(256, 64), b1=(256,), w2=(128, 256), b2=(128,), w3=(64, 128), b3=(64,), w_mu=(12, 64), b_mu=(12,), w_value=(1, 64), b_value=(1,))
+    out = {k: torch.full(s, float("nan"), device="cuda") for k, s in shapes.items()}
+    ctas = lib.lm_device_sm_count(0)
+    ws = torch.empty(ctas * lib.lm_mlp_wgrad_workspace_floats(), device="cuda")
+    rc = lib.lm_mlp_wgrad(*[blobs[k].data_ptr() for k in ("dz1", "dz2", "dz3", "dh", "a0", "a1", "a2", "a3")], rows, ws.data_ptr(), ctas,
+                          *[out[k].data_ptr() for k in ("w1", "b1", "w2", "b2", "w3", "b3", "w_mu", "b_mu", "w_value", "b_value")],
+                          torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, "lm_mlp_wgrad")
+    ref = dict(w1=r["dz1"].t() @ r["a0"], b1=r["dz1"].sum(0), w2=r["dz2"].t() @ r["a1"], b2=r["dz2"].sum(0), w3=r["dz3"].t() @ r["a2"], b3=r["dz3"].sum(0),
+               w_mu=r["dh"][:, :12].t() @ r["a3"], b_mu=r["dh"][:, :12].sum(0), w_value=r["dh"][:, 12:13].t() @ r["a3"], b_value=r["dh"][:, 12].sum().view(1))
+    for k in shapes:
+        scale = float(ref[k].abs().max()) + 1e-6
+        assert_close(k, out[k], ref[k], rtol=1e-4, atol=2e-5 * scale + 1e-6)

@@ -1,1 +1,1 @@
-python tools/kernel_zoo.py > gpurun_out/zoo.log 2>&1
+timeout 600 python -m pytest tests/test_mlp_train.py -m gpu -q -x 2>&1 | tail -25 > gpurun_out/t.log
