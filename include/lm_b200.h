@@ -396,6 +396,14 @@ int lm_ppo_loss(LmRollout* workspace, const LmPpoBatch* batch, float* grad_mu, f
  * by re-reading the same blobs as MN-major operands (no transpose pass), and writes them in nn.Linear layouts.
  * dH [B,16]: columns 0..11 dLoss/dmu, 12 dLoss/dvalue, 13..15 zero.  workspace: workspace_ctas * lm_mlp_wgrad_workspace_floats()
  * floats (one partial per CTA, summed in CTA order: deterministic). */
+/* Training forward: lm_mlp_forward that also leaves the bf16 operands of every layer (A0 = normalised observations [n,64],
+ * A1 [n,256], A2 [n,128], A3 [n,64]) as tile blobs.  lm_mlp_backward: from dLoss/dmu [n,12] and dLoss/dvalue [n] (lm_ppo_loss) and
+ * the saved activations to the pre-activation gradients dH [n,16], dZ3 [n,64], dZ2 [n,128], dZ1 [n,256] as tile blobs (three
+ * GEMMs against the transposed weights resident in shared memory, ELU' from the saved activation). */
+int lm_mlp_forward_train(LmMlp* mlp, const float* obs, const float* norm_mean, const float* norm_inv_std, float norm_clip, float* mu,
+                         float* value, void* a0, void* a1, void* a2, void* a3, int32_t n, void* stream);
+int lm_mlp_backward(LmMlp* mlp, const float* grad_mu, const float* grad_value, const void* a1, const void* a2, const void* a3, void* dh,
+                    void* dz3, void* dz2, void* dz1, int32_t n, void* stream);
 int64_t lm_mlp_blob_bytes(int64_t rows, int32_t d);
 int lm_mlp_blob_pack(const float* x, void* blob, int64_t rows, int32_t d, void* stream);
 int lm_mlp_blob_unpack(const void* blob, float* x, int64_t rows, int32_t d, void* stream);

@@ -149,6 +149,8 @@ SYMBOLS = {
     "lm_noise_destroy": (None, [_vp]),
     "lm_noise_apply": (C.c_int, [_vp, C.POINTER(LmNoiseState), _vp, _vp, _vp, _vp, _i32, C.c_uint64, C.c_uint64, _vp]),
     "lm_ppo_loss": (C.c_int, [_vp, C.POINTER(LmPpoBatch), _vp, _vp, _vp, _vp, _vp]),
+    "lm_mlp_forward_train": (C.c_int, [_vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
+    "lm_mlp_backward": (C.c_int, [_vp] * 10 + [_i32, _vp]),
     "lm_mlp_blob_bytes": (_i64, [_i64, _i32]),
     "lm_mlp_blob_pack": (C.c_int, [_vp, _vp, _i64, _i32, _vp]),
     "lm_mlp_blob_unpack": (C.c_int, [_vp, _vp, _i64, _i32, _vp]),

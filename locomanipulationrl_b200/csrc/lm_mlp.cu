@@ -19,6 +19,7 @@
 
 #include "lm_common.cuh"
 #include "lm_host.h"
+#include "lm_mlp.h"
 #include "lm_tc.cuh"
 
 namespace lm {
@@ -67,7 +68,8 @@ __device__ __forceinline__ void issue_ksteps(uint32_t tmem_d, uint32_t a_saddr, 
 }
 
 // 16 accumulator columns [c0, c0+16) of row `row` -> +bias, ELU, bf16 -> two 16-byte K chunks of the next A operand
-__device__ __forceinline__ void emit16(const uint32_t* acc, const float* __restrict__ bias, uint8_t* dst, int row, int c0) {
+// `gdst` (training forward only): the same two chunks into the tile's activation blob in global memory (same layout, same offsets)
+__device__ __forceinline__ void emit16(const uint32_t* acc, const float* __restrict__ bias, uint8_t* dst, int row, int c0, uint8_t* gdst = nullptr) {
   uint32_t w[8];
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
@@ -77,6 +79,10 @@ __device__ __forceinline__ void emit16(const uint32_t* acc, const float* __restr
   }
   *reinterpret_cast<uint4*>(dst + elem_offset(TM, row, c0)) = make_uint4(w[0], w[1], w[2], w[3]);
   *reinterpret_cast<uint4*>(dst + elem_offset(TM, row, c0 + 8)) = make_uint4(w[4], w[5], w[6], w[7]);
+  if (gdst != nullptr) {
+    __stcs(reinterpret_cast<uint4*>(gdst + elem_offset(TM, row, c0)), make_uint4(w[0], w[1], w[2], w[3]));
+    __stcs(reinterpret_cast<uint4*>(gdst + elem_offset(TM, row, c0 + 8)), make_uint4(w[4], w[5], w[6], w[7]));
+  }
 }
 
 // Hidden-layer epilogue of one warp: kSub sub-steps; in sub-step s the 16 warps together cover accumulator columns
@@ -85,7 +91,7 @@ __device__ __forceinline__ void emit16(const uint32_t* acc, const float* __restr
 // (kSlots < kSub) sub-step s >= kSlots first waits until the MMAs of chunk s - kSlots have drained (`slot_free[s - kSlots]`).
 template <int kSub, int kSlots>
 __device__ __forceinline__ void epilogue_hidden(uint32_t tmem_acc, const float* __restrict__ bias, uint8_t* dst, uint64_t* bars,
-                                                uint64_t* slot_free, uint32_t slot_parity, int g, int q, int lane) {
+                                                uint64_t* slot_free, uint32_t slot_parity, int g, int q, int lane, uint8_t* gsave = nullptr) {
   const int row = g * 32 + lane;
   const uint32_t taddr = tmem_acc + ((uint32_t)(g * 32) << 16) + (uint32_t)(q * 16);
   uint32_t a[16], b[16];
@@ -97,7 +103,7 @@ __device__ __forceinline__ void epilogue_hidden(uint32_t tmem_acc, const float* 
     uint32_t* nxt = (s & 1) ? a : b;
     if (s + 1 < kSub) tmem_ld16(taddr + 64 * (s + 1), nxt);
     if (s >= kSlots) mbar_wait(&slot_free[s - kSlots], slot_parity);
-    emit16(cur, bias + 64 * s, dst + (s % kSlots) * CHUNK_BYTES, row, q * 16);
+    emit16(cur, bias + 64 * s, dst + (s % kSlots) * CHUNK_BYTES, row, q * 16, gsave != nullptr ? gsave + s * CHUNK_BYTES : nullptr);
     fence_proxy_async();                       // generic-proxy A operand writes -> visible to the tensor core's async proxy
     if (s + 1 < kSub) tmem_wait();
     tc_fence_before();                         // orders this warp's tcgen05.ld before the MMA that reuses the accumulator
@@ -117,6 +123,8 @@ struct Args {
   int n;
   int num_tiles;
   long long* timeline;         // diagnostic: clock64 stamps of CTA 0 (NULL in production launches)
+  // training forward (k_mlp_forward<true>): the bf16 operands of every layer saved per tile for the backward kernels (lm_mlp_train.cu)
+  uint8_t *save_a0, *save_a1, *save_a2, *save_a3;
 };
 
 // diagnostic timeline (lm_mlp_forward_timeline): slot k <- clock64(), first writer wins per launch
@@ -137,7 +145,7 @@ __device__ __forceinline__ void obs_fetch(const Args& a, int tile, int tid, ObsR
   }
 }
 __device__ __forceinline__ void obs_convert(const Args& a, int tile, int tid, const ObsRegs& r, const float4& mean, const float4& inv_std,
-                                            bool has_norm, uint8_t* A0) {
+                                            bool has_norm, uint8_t* A0, uint8_t* gA0 = nullptr) {
   const int rows = min(TM, a.n - tile * TM);
   const int c4 = tid & 15;
 #pragma unroll
@@ -150,7 +158,9 @@ __device__ __forceinline__ void obs_convert(const Args& a, int tile, int tid, co
       x.z = fminf(fmaxf((x.z - mean.z) * inv_std.z, -a.norm_clip), a.norm_clip);
       x.w = fminf(fmaxf((x.w - mean.w) * inv_std.w, -a.norm_clip), a.norm_clip);
     }
-    *reinterpret_cast<uint2*>(A0 + elem_offset(TM, row, 4 * c4)) = make_uint2(pack_bf16(x.x, x.y), pack_bf16(x.z, x.w));
+    const uint2 w = make_uint2(pack_bf16(x.x, x.y), pack_bf16(x.z, x.w));
+    *reinterpret_cast<uint2*>(A0 + elem_offset(TM, row, 4 * c4)) = w;
+    if (gA0 != nullptr) *reinterpret_cast<uint2*>(gA0 + elem_offset(TM, row, 4 * c4)) = w;
   }
 }
 
@@ -174,6 +184,7 @@ __device__ __forceinline__ void epilogue_head(const Args& a, uint32_t tmem_acc, 
   }
 }
 
+template <bool kSave>
 __global__ void __launch_bounds__(THREADS, 1) k_mlp_forward(const Args a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   // mbarriers.  count 1: bar_w (weight TMA), bar_acc* and bar_c2[s] (tcgen05.commit: accumulator complete / layer-2 K chunk s
@@ -275,6 +286,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_mlp_forward(const Args a) {
     // ================================================================== epilogue warps
     const int g = warp & 3, q = warp >> 2;
     const bool has_norm = a.norm_mean != nullptr;
+    // training forward: tile t's saved operand of layer L lives at save_aL + t * operand_bytes(128, D_L)
+    auto g0 = [&](int t) -> uint8_t* { return kSave ? a.save_a0 + (size_t)t * operand_bytes(TM, D0) : nullptr; };
+    auto g1 = [&](int t) -> uint8_t* { return kSave ? a.save_a1 + (size_t)t * operand_bytes(TM, D1) : nullptr; };
+    auto g2 = [&](int t) -> uint8_t* { return kSave ? a.save_a2 + (size_t)t * operand_bytes(TM, D2) : nullptr; };
+    auto g3 = [&](int t) -> uint8_t* { return kSave ? a.save_a3 + (size_t)t * operand_bytes(TM, D3) : nullptr; };
     float4 mean = make_float4(0.f, 0.f, 0.f, 0.f), inv_std = make_float4(1.f, 1.f, 1.f, 1.f);
     if (has_norm) {
       mean = *reinterpret_cast<const float4*>(a.norm_mean + 4 * (tid & 15));
@@ -284,7 +300,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_mlp_forward(const Args a) {
     pdl_wait();                                            // the observations are the predecessor kernel's output
     if (n_loc > 0) {
       obs_fetch(a, tile0, tid, regs);
-      obs_convert(a, tile0, tid, regs, mean, inv_std, has_norm, A0);
+      obs_convert(a, tile0, tid, regs, mean, inv_std, has_norm, A0, g0(tile0));
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_a0);
@@ -301,11 +317,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_mlp_forward(const Args a) {
       mbar_wait(&bar_acc1, ph);
       tc_fence_after();
       if (st) stamp(a, 8 + 8 * it + 1);
-      epilogue_hidden<4, 2>(tmem + ACC1_COL, bias1, RING, bar_act1, bar_c2, ph, g, q, lane);
+      epilogue_hidden<4, 2>(tmem + ACC1_COL, bias1, RING, bar_act1, bar_c2, ph, g, q, lane, g1(tile));
       if (st) stamp(a, 8 + 8 * it + 2);
       // ---- observations of tile t+1 -> A0 (layer 1 of tile t has consumed A0), then fetch tile t+2
       if (it + 1 < n_loc) {
-        obs_convert(a, tile + stride, tid, regs, mean, inv_std, has_norm, A0);
+        obs_convert(a, tile + stride, tid, regs, mean, inv_std, has_norm, A0, g0(tile + stride));
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar_a0);
@@ -323,14 +339,14 @@ __global__ void __launch_bounds__(THREADS, 1) k_mlp_forward(const Args a) {
       if (it >= 1) {
         mbar_wait(&bar_acc3, ph ^ 1);
         tc_fence_after();
-        epilogue_hidden<1, 1>(tmem + ACC3_COL, bias3, A3, bar_act3, nullptr, 0, g, q, lane);
+        epilogue_hidden<1, 1>(tmem + ACC3_COL, bias3, A3, bar_act3, nullptr, 0, g, q, lane, g3(tile - stride));
       }
       // ---- E2(t): TMEM[128 x 128] -> A2 (layer 3 of tile t-1 has finished reading it: bar_acc3 above)
       if (st) stamp(a, 8 + 8 * it + 5);
       mbar_wait(&bar_acc2, ph);
       tc_fence_after();
       if (st) stamp(a, 8 + 8 * it + 6);
-      epilogue_hidden<2, 2>(tmem + ACC2_COL, bias2, A2, bar_act2, nullptr, 0, g, q, lane);
+      epilogue_hidden<2, 2>(tmem + ACC2_COL, bias2, A2, bar_act2, nullptr, 0, g, q, lane, g2(tile));
       if (st) stamp(a, 8 + 8 * it + 7);
     }
     // ---- drain: heads(n-2), E3(n-1), heads(n-1)
@@ -342,7 +358,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_mlp_forward(const Args a) {
     if (n_loc >= 1) {
       mbar_wait(&bar_acc3, (n_loc - 1) & 1);
       tc_fence_after();
-      epilogue_hidden<1, 1>(tmem + ACC3_COL, bias3, A3, bar_act3, nullptr, 0, g, q, lane);
+      epilogue_hidden<1, 1>(tmem + ACC3_COL, bias3, A3, bar_act3, nullptr, 0, g, q, lane, g3(tile0 + (n_loc - 1) * stride));
       mbar_wait(&bar_acch, (n_loc - 1) & 1);
       tc_fence_after();
       if (q == 0) epilogue_head(a, tmem + ACCH_COL, biash, tile0 + (n_loc - 1) * stride, g, lane);
@@ -380,15 +396,6 @@ __global__ void k_pack_bias(const float* __restrict__ b1, const float* __restric
 using namespace lm;
 using namespace lm::mlp;
 
-struct LmMlp {
-  int device;
-  int sm_count;
-  uint8_t* blob;
-  bool packed;
-  bool fresh_pack;       // weights were re-packed since the last forward: that forward must not start early
-  long long* timeline;   // diagnostic only (lm_mlp_set_timeline)
-};
-
 extern "C" {
 
 LmMlp* lm_mlp_create(int device) {
@@ -398,10 +405,11 @@ LmMlp* lm_mlp_create(int device) {
   if (prop.major != 10) { lm_set_error("lm_mlp_create: tcgen05 kernel needs sm_100a, device is sm_%d%d", prop.major, prop.minor); return nullptr; }
   cudaSetDevice(device);
   LmMlp* m = new LmMlp();
-  m->device = device; m->sm_count = prop.multiProcessorCount; m->packed = false; m->blob = nullptr; m->timeline = nullptr; m->fresh_pack = true;
+  m->device = device; m->sm_count = prop.multiProcessorCount; m->packed = false; m->blob = nullptr; m->blob_t = nullptr; m->timeline = nullptr; m->fresh_pack = true;
   if (cudaMalloc(&m->blob, BLOB_BYTES) != cudaSuccess) { lm_set_error("lm_mlp_create: cudaMalloc failed"); delete m; return nullptr; }
   cudaMemset(m->blob, 0, BLOB_BYTES);
-  e = cudaFuncSetAttribute(k_mlp_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  e = cudaFuncSetAttribute(k_mlp_forward<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_mlp_forward<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   if (e != cudaSuccess) { lm_set_error("lm_mlp_create: smem attribute: %s", cudaGetErrorString(e)); cudaFree(m->blob); delete m; return nullptr; }
   return m;
 }
@@ -409,6 +417,7 @@ LmMlp* lm_mlp_create(int device) {
 void lm_mlp_destroy(LmMlp* m) {
   if (!m) return;
   cudaFree(m->blob);
+  lm_mlp_train_release(m);
   delete m;
 }
 
@@ -431,6 +440,8 @@ int lm_mlp_pack(LmMlp* m, const float* w1, const float* b1, const float* w2, con
   k_pack_operand<<<(12 * D3 + 255) / 256, 256, 0, s>>>(w_mu, m->blob + WH_OFF, DH, 12, D3);
   k_pack_operand<<<(1 * D3 + 255) / 256, 256, 0, s>>>(w_value, m->blob + WH_OFF + 12 * 16, DH, 1, D3);
   k_pack_bias<<<2, 256, 0, s>>>(b1, b2, b3, b_mu, b_value, reinterpret_cast<float*>(m->blob + BIAS_OFF));
+  const int rc = lm_mlp_train_pack(m, w2, w3, w_mu, w_value, stream);      // transposed operands of the backward kernel
+  if (rc != LM_OK) return rc;
   m->packed = true;
   m->fresh_pack = true;
   return lm_check_launch("lm_mlp_pack");
@@ -445,13 +456,34 @@ int lm_mlp_forward(LmMlp* m, const float* obs, const float* norm_mean, const flo
   Args a;
   a.blob = m->blob; a.obs = obs; a.norm_mean = norm_mean; a.norm_inv_std = norm_inv_std; a.norm_clip = norm_clip;
   a.mu = mu; a.value = value; a.n = n; a.num_tiles = (n + TM - 1) / TM; a.timeline = m->timeline;
+  a.save_a0 = a.save_a1 = a.save_a2 = a.save_a3 = nullptr;
   const int grid = a.num_tiles < m->sm_count ? a.num_tiles : m->sm_count;
   // The resident-weight TMA is issued before pdl_wait(): allowed only while the blob is not being rewritten upstream.
   const bool pdl = !m->fresh_pack;
   m->fresh_pack = false;
-  cudaError_t le = lm_launch(k_mlp_forward, dim3(grid), dim3(THREADS), SMEM_BYTES, (cudaStream_t)stream, pdl, a);
+  cudaError_t le = lm_launch(k_mlp_forward<false>, dim3(grid), dim3(THREADS), SMEM_BYTES, (cudaStream_t)stream, pdl, a);
   if (le != cudaSuccess) return lm_fail((int)le, "lm_mlp_forward: %s", cudaGetErrorString(le));
   return lm_check_launch("lm_mlp_forward");
+}
+
+// The same forward for the PPO update: additionally leaves the bf16 operands of every layer (A0 = normalised observations,
+// A1, A2, A3) as tile blobs (lm_mlp_blob_bytes(n, D) bytes each) for lm_mlp_backward / lm_mlp_wgrad.
+int lm_mlp_forward_train(LmMlp* m, const float* obs, const float* norm_mean, const float* norm_inv_std, float norm_clip, float* mu,
+                         float* value, void* a0, void* a1, void* a2, void* a3, int32_t n, void* stream) {
+  if (!m || !obs || !mu || !value || !a0 || !a1 || !a2 || !a3 || n <= 0) return lm_fail(LM_ERR_BAD_ARG, "lm_mlp_forward_train: bad argument");
+  if (!m->packed) return lm_fail(LM_ERR_BAD_ARG, "lm_mlp_forward_train: weights not packed (call lm_mlp_pack)");
+  if ((((uintptr_t)obs) | ((uintptr_t)mu) | ((uintptr_t)a0) | ((uintptr_t)a1) | ((uintptr_t)a2) | ((uintptr_t)a3)) & 15)
+    return lm_fail(LM_ERR_ALIGNMENT, "lm_mlp_forward_train: obs / mu / activation blobs must be 16-byte aligned");
+  if ((norm_mean == nullptr) != (norm_inv_std == nullptr)) return lm_fail(LM_ERR_BAD_ARG, "lm_mlp_forward_train: give both norm vectors or neither");
+  Args a;
+  a.blob = m->blob; a.obs = obs; a.norm_mean = norm_mean; a.norm_inv_std = norm_inv_std; a.norm_clip = norm_clip;
+  a.mu = mu; a.value = value; a.n = n; a.num_tiles = (n + TM - 1) / TM; a.timeline = nullptr;
+  a.save_a0 = (uint8_t*)a0; a.save_a1 = (uint8_t*)a1; a.save_a2 = (uint8_t*)a2; a.save_a3 = (uint8_t*)a3;
+  const int grid = a.num_tiles < m->sm_count ? a.num_tiles : m->sm_count;
+  m->fresh_pack = false;
+  cudaError_t le = lm_launch(k_mlp_forward<true>, dim3(grid), dim3(THREADS), SMEM_BYTES, (cudaStream_t)stream, false, a);
+  if (le != cudaSuccess) return lm_fail((int)le, "lm_mlp_forward_train: %s", cudaGetErrorString(le));
+  return lm_check_launch("lm_mlp_forward_train");
 }
 
 }  // extern "C"

@@ -17,6 +17,7 @@
 
 #include "lm_common.cuh"
 #include "lm_host.h"
+#include "lm_mlp.h"
 #include "lm_tc.cuh"
 
 namespace lm {
@@ -43,6 +44,186 @@ __global__ void k_blob_unpack(const uint8_t* __restrict__ blob, float* __restric
   const long long row = i / d;
   const int k = (int)(i - row * d);
   x[i] = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(blob + (row / TM) * blob_bytes(d) + elem_offset(TM, (int)(row % TM), k)));
+}
+
+
+// ---------------------------------------------------------------- backward through the activations
+// k_mlp_backward: dH -> dZ3 -> dZ2 -> dZ1 per 128-sample tile, transposed weights resident in shared memory.
+//   dA3 = dH Wh      (K = 16),  dZ3 = dA3 * ELU'(A3)
+//   dA2 = dZ3 W3     (K = 64),  dZ2 = dA2 * ELU'(A2)
+//   dA1 = dZ2 W2     (K = 128), dZ1 = dA1 * ELU'(A1)          ELU'(z) = 1 for a > 0, a + 1 otherwise (a = ELU(z), the saved operand)
+// 16 epilogue warps (4 TMEM lane groups x 4 column quarters) + 1 control warp, as the forward kernel.  The saved activations are
+// read straight from their global blobs (each element is used once, by the thread that owns it); every dZ leaves as a tile
+// blob for lm_mlp_wgrad, dZ3 / dZ2 also stay in shared memory as the next GEMM's A operand.
+constexpr int B_WARPS = 16, B_THREADS = B_WARPS * 32 + 32;
+constexpr int WHT_OFF = 0;                                             // B operand of dA3: [N = 64 (in)][K = 16 (o)]
+constexpr int W3T_OFF = WHT_OFF + operand_bytes(D3, DH);               // B operand of dA2: [N = 128][K = 64]
+constexpr int W2T_OFF = W3T_OFF + operand_bytes(D2, D3);               // B operand of dA1: [N = 256][K = 128]
+constexpr int WT_BYTES = W2T_OFF + operand_bytes(D1, D2);
+constexpr int DH_OFF = WT_BYTES;
+constexpr int DZ3_OFF = DH_OFF + blob_bytes(DH);
+constexpr int DZ2_OFF = DZ3_OFF + blob_bytes(D3);
+constexpr int BWD_SMEM_BYTES = DZ2_OFF + blob_bytes(D2) + 64;
+static_assert(WT_BYTES % 16 == 0 && W3T_OFF % 16 == 0 && W2T_OFF % 16 == 0, "align");
+static_assert(BWD_SMEM_BYTES <= 232448 - 1024, "exceeds 227 KB");
+constexpr uint32_t BA3_COL = 0, BA2_COL = 64, BA1_COL = 192;           // 64 + 128 + 256 accumulator columns
+
+struct BwdArgs {
+  const uint8_t* wt;                        // transposed weight blob (lm_mlp_train_pack)
+  const float* grad_mu; const float* grad_value;       // [n,12], [n]
+  const uint8_t *a1, *a2, *a3;              // saved activations (lm_mlp_forward_train)
+  uint8_t *dh, *dz3, *dz2, *dz1;            // out: tile blobs
+  int n, num_tiles;
+};
+
+template <int kN, int kK>
+__device__ __forceinline__ void issue_gemm(uint32_t acc, uint32_t a_saddr, uint32_t b_saddr) {      // D[128 x kN] = A[128 x kK] B^T, K-major operands
+  constexpr uint32_t idesc = instr_desc(TM, kN);
+#pragma unroll
+  for (int ks = 0; ks < kK / 16; ++ks)
+    umma_bf16(acc, smem_desc(a_saddr + ks * 2 * lbo_bytes(TM), lbo_bytes(TM)), smem_desc(b_saddr + ks * 2 * lbo_bytes(kN), lbo_bytes(kN)), idesc,
+              (uint32_t)(ks > 0));
+}
+
+// 8 accumulator columns x the saved activation chunk -> dZ chunk (8 bf16)
+__device__ __forceinline__ uint4 dz_chunk(const uint32_t* acc, const uint4& act) {
+  const uint32_t aw[4] = {act.x, act.y, act.z, act.w};
+  uint32_t w[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const __nv_bfloat162 a2 = *reinterpret_cast<const __nv_bfloat162*>(&aw[k]);
+    const float a_lo = __low2float(a2), a_hi = __high2float(a2);
+    const float d_lo = a_lo > 0.0f ? 1.0f : a_lo + 1.0f, d_hi = a_hi > 0.0f ? 1.0f : a_hi + 1.0f;
+    w[k] = pack_bf16(__uint_as_float(acc[2 * k]) * d_lo, __uint_as_float(acc[2 * k + 1]) * d_hi);
+  }
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// one backward epilogue of a warp: kCols accumulator columns starting at column q * kCols of `tmem_acc` -> dZ chunks to `sdst`
+// (shared-memory operand, may be NULL) and `gdst` (global blob); `gact` = the saved activation blob of this tile
+template <int kCols>
+__device__ __forceinline__ void epilogue_bwd(uint32_t tmem_acc, const uint8_t* __restrict__ gact, uint8_t* sdst, uint8_t* gdst, int g, int q, int lane) {
+  const int row = g * 32 + lane;
+  const uint32_t taddr = tmem_acc + ((uint32_t)(g * 32) << 16) + (uint32_t)(q * kCols);
+#pragma unroll
+  for (int c = 0; c < kCols; c += 16) {
+    uint32_t acc[16];
+    tmem_ld16(taddr + c, acc);
+    const int col = q * kCols + c;
+    const uint4 a_lo = __ldcs(reinterpret_cast<const uint4*>(gact + elem_offset(TM, row, col)));
+    const uint4 a_hi = __ldcs(reinterpret_cast<const uint4*>(gact + elem_offset(TM, row, col + 8)));
+    tmem_wait();
+    const uint4 z_lo = dz_chunk(acc, a_lo), z_hi = dz_chunk(acc + 8, a_hi);
+    if (sdst != nullptr) {
+      *reinterpret_cast<uint4*>(sdst + elem_offset(TM, row, col)) = z_lo;
+      *reinterpret_cast<uint4*>(sdst + elem_offset(TM, row, col + 8)) = z_hi;
+    }
+    __stcs(reinterpret_cast<uint4*>(gdst + elem_offset(TM, row, col)), z_lo);
+    __stcs(reinterpret_cast<uint4*>(gdst + elem_offset(TM, row, col + 8)), z_hi);
+  }
+}
+
+__global__ void __launch_bounds__(B_THREADS, 1) k_mlp_backward(const BwdArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  // count 1: bar_w (weight TMA), bar_acc3 / bar_acc2 / bar_acc1 (tcgen05.commit).  count 16: bar_dh, bar_z3, bar_z2 (operand written by
+  // every epilogue warp).  Each completes once per tile: wait parity = CTA-local tile index & 1.
+  __shared__ uint64_t bar_w, bar_dh, bar_acc3, bar_z3, bar_acc2, bar_z2, bar_acc1;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    mbar_init(&bar_w, 1); mbar_init(&bar_dh, B_WARPS); mbar_init(&bar_acc3, 1); mbar_init(&bar_z3, B_WARPS); mbar_init(&bar_acc2, 1);
+    mbar_init(&bar_z2, B_WARPS); mbar_init(&bar_acc1, 1);
+    fence_mbar_init();
+  }
+  if (warp == B_WARPS) tmem_alloc(&tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const int tile0 = blockIdx.x, stride = gridDim.x;
+  const int n_loc = tile0 < a.num_tiles ? (a.num_tiles - tile0 + stride - 1) / stride : 0;
+  uint8_t* DHs = smem + DH_OFF;
+  uint8_t* DZ3s = smem + DZ3_OFF;
+  uint8_t* DZ2s = smem + DZ2_OFF;
+
+  if (warp == B_WARPS) {
+    if (elect_one()) {
+      mbar_expect_tx(&bar_w, WT_BYTES);
+      tma_load_1d(smem, a.wt, WT_BYTES, &bar_w);
+      mbar_wait(&bar_w, 0);
+      const uint32_t sWh = smem_u32(smem + WHT_OFF), sW3 = smem_u32(smem + W3T_OFF), sW2 = smem_u32(smem + W2T_OFF);
+      const uint32_t sDH = smem_u32(DHs), sZ3 = smem_u32(DZ3s), sZ2 = smem_u32(DZ2s);
+      for (int it = 0; it < n_loc; ++it) {
+        const uint32_t ph = it & 1;
+        mbar_wait(&bar_dh, ph); tc_fence_after();
+        issue_gemm<D3, DH>(tmem + BA3_COL, sDH, sWh); umma_commit(&bar_acc3);
+        mbar_wait(&bar_z3, ph); tc_fence_after();
+        issue_gemm<D2, D3>(tmem + BA2_COL, sZ3, sW3); umma_commit(&bar_acc2);
+        mbar_wait(&bar_z2, ph); tc_fence_after();
+        issue_gemm<D1, D2>(tmem + BA1_COL, sZ2, sW2); umma_commit(&bar_acc1);
+      }
+    }
+  } else {
+    const int g = warp & 3, q = warp >> 2;
+    const int row = g * 32 + lane;
+    for (int it = 0; it < n_loc; ++it) {
+      const uint32_t ph = it & 1;
+      const size_t tile = (size_t)(tile0 + it * stride);
+      const int row0 = (int)tile * TM, rows = min(TM, a.n - row0);
+      // ---- dH operand [128 x 16]: columns 0..11 dLoss/dmu, 12 dLoss/dvalue; rows past the batch are zero.  The previous tile's
+      // GEMM on it completed before that tile's E3 (bar_acc3), so it may be overwritten.
+      if (q == 0) {
+        float v[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) v[k] = 0.0f;
+        if (row < rows) {
+          const float4* gm = reinterpret_cast<const float4*>(a.grad_mu + (size_t)(row0 + row) * 12);
+          const float4 m0 = __ldg(gm), m1 = __ldg(gm + 1), m2 = __ldg(gm + 2);
+          v[0] = m0.x; v[1] = m0.y; v[2] = m0.z; v[3] = m0.w; v[4] = m1.x; v[5] = m1.y; v[6] = m1.z; v[7] = m1.w;
+          v[8] = m2.x; v[9] = m2.y; v[10] = m2.z; v[11] = m2.w; v[12] = __ldg(a.grad_value + row0 + row);
+        }
+        const uint4 lo = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+        const uint4 hi = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
+        *reinterpret_cast<uint4*>(DHs + elem_offset(TM, row, 0)) = lo;
+        *reinterpret_cast<uint4*>(DHs + elem_offset(TM, row, 8)) = hi;
+        uint8_t* gdh = a.dh + tile * blob_bytes(DH);
+        __stcs(reinterpret_cast<uint4*>(gdh + elem_offset(TM, row, 0)), lo);
+        __stcs(reinterpret_cast<uint4*>(gdh + elem_offset(TM, row, 8)), hi);
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_dh);
+      // ---- E3: dZ3 = dA3 * ELU'(A3)
+      mbar_wait(&bar_acc3, ph); tc_fence_after();
+      epilogue_bwd<D3 / 4>(tmem + BA3_COL, a.a3 + tile * blob_bytes(D3), DZ3s, a.dz3 + tile * blob_bytes(D3), g, q, lane);
+      fence_proxy_async(); tc_fence_before(); __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_z3);
+      // ---- E2
+      mbar_wait(&bar_acc2, ph); tc_fence_after();
+      epilogue_bwd<D2 / 4>(tmem + BA2_COL, a.a2 + tile * blob_bytes(D2), DZ2s, a.dz2 + tile * blob_bytes(D2), g, q, lane);
+      fence_proxy_async(); tc_fence_before(); __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_z2);
+      // ---- E1: dZ1 leaves for the weight-gradient kernel only
+      mbar_wait(&bar_acc1, ph); tc_fence_after();
+      epilogue_bwd<D1 / 4>(tmem + BA1_COL, a.a1 + tile * blob_bytes(D1), nullptr, a.dz1 + tile * blob_bytes(D1), g, q, lane);
+      tc_fence_before();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == B_WARPS) tmem_dealloc(tmem, 512);
+}
+
+// nn.Linear W [O][I] -> K-major B operand of dA = dZ W: element (n = i, k = o); rows of `w` at o >= o_valid are zero
+__global__ void k_pack_operand_t(const float* __restrict__ w, uint8_t* __restrict__ dst, int O, int o_valid, int I, int o_offset, int o_count) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= o_count * I) return;
+  const int o_src = idx / I, i = idx - o_src * I;
+  const int o = o_offset + o_src;
+  const float v = o_src < o_valid ? w[(size_t)o_src * I + i] : 0.0f;
+  *reinterpret_cast<__nv_bfloat16*>(dst + elem_offset(I, i, o)) = __float2bfloat16_rn(v);
+  (void)O;
 }
 
 // ---------------------------------------------------------------- weight gradients
@@ -252,6 +433,26 @@ __global__ void k_wgrad_reduce(const ReduceArgs a) {
 using namespace lm;
 using namespace lm::mlp_train;
 
+
+int lm_mlp_train_pack(LmMlp* m, const float* w2, const float* w3, const float* w_mu, const float* w_value, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!m->blob_t) {
+    if (cudaMalloc(&m->blob_t, WT_BYTES) != cudaSuccess) { m->blob_t = nullptr; return lm_fail((int)cudaErrorMemoryAllocation, "lm_mlp_pack: cudaMalloc failed"); }
+  }
+  cudaMemsetAsync(m->blob_t, 0, WT_BYTES, s);
+  // head: B[n = i (64)][k = o (16)]: o 0..11 = mean rows, 12 = value row, 13..15 zero
+  k_pack_operand_t<<<(12 * D3 + 255) / 256, 256, 0, s>>>(w_mu, m->blob_t + WHT_OFF, 12, 12, D3, 0, 12);
+  k_pack_operand_t<<<(1 * D3 + 255) / 256, 256, 0, s>>>(w_value, m->blob_t + WHT_OFF, 1, 1, D3, 12, 1);
+  k_pack_operand_t<<<(D3 * D2 + 255) / 256, 256, 0, s>>>(w3, m->blob_t + W3T_OFF, D3, D3, D2, 0, D3);
+  k_pack_operand_t<<<(D2 * D1 + 255) / 256, 256, 0, s>>>(w2, m->blob_t + W2T_OFF, D2, D2, D1, 0, D2);
+  return lm_check_launch("lm_mlp_pack (transposed operands)");
+}
+
+void lm_mlp_train_release(LmMlp* m) {
+  if (m->blob_t) cudaFree(m->blob_t);
+  m->blob_t = nullptr;
+}
+
 extern "C" {
 
 int64_t lm_mlp_blob_bytes(int64_t rows, int32_t d) { return ((rows + TM - 1) / TM) * (int64_t)blob_bytes(d); }
@@ -294,5 +495,28 @@ int lm_mlp_wgrad(const void* dz1, const void* dz2, const void* dz3, const void* 
 }
 
 int32_t lm_mlp_wgrad_workspace_floats(void) { return P_COUNT; }
+
+int lm_mlp_backward(LmMlp* m, const float* grad_mu, const float* grad_value, const void* a1, const void* a2, const void* a3, void* dh, void* dz3,
+                    void* dz2, void* dz1, int32_t n, void* stream) {
+  if (!m || !grad_mu || !grad_value || !a1 || !a2 || !a3 || !dh || !dz3 || !dz2 || !dz1 || n <= 0) return lm_fail(LM_ERR_BAD_ARG, "lm_mlp_backward: bad argument");
+  if (!m->packed || !m->blob_t) return lm_fail(LM_ERR_BAD_ARG, "lm_mlp_backward: weights not packed (call lm_mlp_pack)");
+  if ((((uintptr_t)grad_mu) | ((uintptr_t)a1) | ((uintptr_t)a2) | ((uintptr_t)a3) | ((uintptr_t)dh) | ((uintptr_t)dz3) | ((uintptr_t)dz2) | ((uintptr_t)dz1)) & 15)
+    return lm_fail(LM_ERR_ALIGNMENT, "lm_mlp_backward: grad_mu / blobs must be 16-byte aligned");
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_mlp_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM_BYTES);
+    if (e != cudaSuccess) return lm_fail((int)e, "lm_mlp_backward: smem attribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  BwdArgs a;
+  a.wt = m->blob_t; a.grad_mu = grad_mu; a.grad_value = grad_value;
+  a.a1 = (const uint8_t*)a1; a.a2 = (const uint8_t*)a2; a.a3 = (const uint8_t*)a3;
+  a.dh = (uint8_t*)dh; a.dz3 = (uint8_t*)dz3; a.dz2 = (uint8_t*)dz2; a.dz1 = (uint8_t*)dz1;
+  a.n = n; a.num_tiles = (n + TM - 1) / TM;
+  const int grid = a.num_tiles < m->sm_count ? a.num_tiles : m->sm_count;
+  k_mlp_backward<<<grid, B_THREADS, BWD_SMEM_BYTES, (cudaStream_t)stream>>>(a);
+  return lm_check_launch("lm_mlp_backward");
+}
+
 
 }  // extern "C"

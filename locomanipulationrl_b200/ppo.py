@@ -72,3 +72,61 @@ class FlatAdam:
                                     self.params.numel(), self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay,
                                     self.step_count, self.max_grad_norm, float(grad_scale), self.grad_norm.data_ptr(), stream)
         _lib.check(rc, "lm_adam_step")
+
+
+class MlpPpoGradients:
+    """Gradients of the rl_games PPO loss for ``MlpActorCritic`` on tcgen05 end to end (csrc/lm_mlp.cu, lm_ppo.cu, lm_mlp_train.cu):
+
+        training forward (activations saved as bf16 tile blobs) -> lm_ppo_loss -> backward through the activations ->
+        weight / bias gradients accumulated in TMEM over the minibatch
+
+    bf16 operands with fp32 accumulation throughout (what torch autocast would run); the result lands in the parameters' ``.grad``
+    tensors, ready for the fused all-reduce and ``FlatAdam``.
+    """
+
+    def __init__(self, model, max_batch: int, **loss_cfg):
+        self.model, self.device = model, model._device
+        self.max_batch = int(max_batch)
+        self.loss = PpoLoss(device=self.device, **loss_cfg)
+        self._lib = _lib.load()
+        model._ensure()
+        nb = lambda d: torch.empty(self._lib.lm_mlp_blob_bytes(self.max_batch, d), dtype=torch.uint8, device=self.device)
+        self.a0, self.a1, self.a2, self.a3 = nb(64), nb(256), nb(128), nb(64)
+        self.dz1, self.dz2, self.dz3, self.dh = nb(256), nb(128), nb(64), nb(16)
+        self.mu = torch.empty(self.max_batch, 12, device=self.device)
+        self.value = torch.empty(self.max_batch, device=self.device)
+        self.grad_mu = torch.empty(self.max_batch, 12, device=self.device)
+        self.grad_value = torch.empty(self.max_batch, device=self.device)
+        idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self._ctas = self._lib.lm_device_sm_count(idx)
+        self._ws = torch.empty(self._ctas * self._lib.lm_mlp_wgrad_workspace_floats(), device=self.device)
+
+    @torch.no_grad()
+    def __call__(self, obs, actions, old_neglogp, advantages, old_values, returns, old_mu=None, old_log_std=None,
+                 norm_mean=None, norm_inv_std=None, norm_clip: float = 5.0):
+        """One minibatch (all tensors fp32, contiguous, on the device).  Fills ``.grad`` of every parameter; returns the loss head's stats [8]."""
+        m, lib = self.model, self._lib
+        n = obs.shape[0]
+        if n > self.max_batch:
+            raise _lib.LmError(f"minibatch of {n} exceeds max_batch {self.max_batch}")
+        if m._packed_version != m._param_version():
+            m.pack()
+        s = torch.cuda.current_stream(self.device).cuda_stream
+        p = _lib.ptr
+        mu, value = self.mu[:n], self.value[:n]
+        _lib.check(lib.lm_mlp_forward_train(m._handle, p(obs), p(norm_mean), p(norm_inv_std), float(norm_clip), p(mu), p(value),
+                                            p(self.a0), p(self.a1), p(self.a2), p(self.a3), n, s), "lm_mlp_forward_train")
+        log_std = m.log_std_parameter.detach()
+        out = {"grad_mu": self.grad_mu[:n], "grad_value": self.grad_value[:n]}
+        _, _, g_ls, stats = self.loss(mu, value, log_std, actions, old_neglogp, advantages, old_values, returns, old_mu, old_log_std, out=out)
+        _lib.check(lib.lm_mlp_backward(m._handle, p(out["grad_mu"]), p(out["grad_value"]), p(self.a1), p(self.a2), p(self.a3),
+                                       p(self.dh), p(self.dz3), p(self.dz2), p(self.dz1), n, s), "lm_mlp_backward")
+        l1, l2, l3 = m.net[0], m.net[2], m.net[4]
+        params = [l1.weight, l1.bias, l2.weight, l2.bias, l3.weight, l3.bias, m.mean_layer.weight, m.mean_layer.bias, m.value_layer.weight, m.value_layer.bias]
+        for q in params + [m.log_std_parameter]:
+            if q.grad is None:
+                q.grad = torch.zeros_like(q)
+        _lib.check(lib.lm_mlp_wgrad(p(self.dz1), p(self.dz2), p(self.dz3), p(self.dh), p(self.a0), p(self.a1), p(self.a2), p(self.a3), n,
+                                    p(self._ws), self._ctas, *[q.grad.data_ptr() for q in params], s), "lm_mlp_wgrad")
+        m.log_std_parameter.grad.copy_(g_ls)
+        return stats

@@ -52,3 +52,35 @@ def test_weight_gradients_match_torch(rows):
     for k in shapes:
         scale = float(ref[k].abs().max()) + 1e-6
         assert_close(k, out[k], ref[k], rtol=1e-4, atol=2e-5 * scale + 1e-6)
+
+
+@pytest.mark.parametrize("B", [128, 1000, 32768 + 17])
+def test_ppo_gradients_match_autograd(B):
+    """Training forward + loss head + backward + weight gradients on tcgen05 vs torch autograd of the fp32 model on the restated loss.
+    bf16 operands (activations, pre-activation gradients, weights): tolerance 3 % of each tensor's largest gradient."""
+    from locomanipulationrl_b200.policy.mlp import MlpActorCritic
+    from locomanipulationrl_b200.ppo import MlpPpoGradients
+    from oracle import port_policy as pp
+    from tests.test_ppo import _batch
+    torch.manual_seed(B)
+    model = MlpActorCritic(device="cuda:0")
+    with torch.no_grad():
+        model.log_std_parameter.copy_(torch.randn(12) * 0.1)
+    obs = torch.randn(B, 64, device="cuda").clamp(-5, 5)
+    _, _, _, actions, old_nlp, adv, old_v, ret, old_mu, old_ls = (t.cuda() for t in _batch(B, B + 1, wide=True))
+    cfg = dict(e_clip=0.2, critic_coef=2.0, entropy_coef=0.0, bounds_loss_coef=1e-4, clip_value=True)
+    # reference: fp32 autograd
+    mu, value, log_std = model.reference_forward(obs)
+    loss, _ = pp.ppo_loss(mu, value.view(-1), log_std, actions, old_nlp, adv, old_v, ret, old_mu, old_ls, **cfg)
+    loss.backward()
+    ref = {k: p.grad.clone() for k, p in model.named_parameters()}
+    for p in model.parameters():
+        p.grad = None
+    stats = MlpPpoGradients(model, max_batch=B, **cfg)(obs, actions, old_nlp, adv, old_v, ret, old_mu, old_ls)
+    assert abs(float(stats[5]) - float(loss.detach())) <= 2e-2 * abs(float(loss.detach())) + 1e-3
+    for k, p in model.named_parameters():
+        scale = float(ref[k].abs().max()) + 1e-12
+        err = float((p.grad - ref[k]).abs().max())
+        assert err <= 3e-2 * scale, f"{k}: max err {err:.3e} vs scale {scale:.3e}"
+        cos = torch.nn.functional.cosine_similarity(p.grad.flatten(), ref[k].flatten(), dim=0)
+        assert float(cos) > 0.999, f"{k}: cosine {float(cos):.5f}"
