@@ -1,1 +1,1 @@
-timeout 600 python -m pytest tests/test_mlp_train.py -m gpu -q -x 2>&1 | tail -25 > gpurun_out/t.log
+python tools/update_bench.py > gpurun_out/update_bench.log 2>&1

@@ -81,3 +81,61 @@ opt = FlatAdam(flat)
 opt.step(grads)
 ms = graph_time(lambda i: opt.step(grads), 8)
 report("k_adam_step (58,637 parameters, clip + Adam)", ms, 28, 58637)
+
+# ---------------------------------------------------------------- the MLP update on tcgen05 vs torch autograd on the same GPU
+from locomanipulationrl_b200 import _lib  # noqa: E402
+from locomanipulationrl_b200.policy.mlp import MlpActorCritic  # noqa: E402
+from locomanipulationrl_b200.ppo import MlpPpoGradients  # noqa: E402
+from oracle import port_policy as pp  # noqa: E402  (bench-side checker / baseline only)
+
+torch.manual_seed(0)
+model = MlpActorCritic(device=dev)
+model.pack()
+pobs = torch.randn(B, 64, device=dev, generator=g).clamp(-5, 5)
+grads = MlpPpoGradients(model, max_batch=B)
+lib = _lib.load()
+cs = lambda: torch.cuda.current_stream().cuda_stream      # graph capture runs on its own stream
+p = _lib.ptr
+
+
+def run_all(i=0):
+    grads(pobs, pa, pnl, padv, pov, pret, pom, log_std)
+
+
+run_all()
+torch.cuda.synchronize()
+ms_all = graph_time(run_all, 2, reps=10)
+ms_fwd = graph_time(lambda i: lib.lm_mlp_forward_train(model._handle, p(pobs), None, None, 5.0, p(grads.mu), p(grads.value), p(grads.a0), p(grads.a1),
+                                                       p(grads.a2), p(grads.a3), B, cs()), 2, reps=10)
+ms_bwd = graph_time(lambda i: lib.lm_mlp_backward(model._handle, p(grads.grad_mu), p(grads.grad_value), p(grads.a1), p(grads.a2), p(grads.a3), p(grads.dh),
+                                                  p(grads.dz3), p(grads.dz2), p(grads.dz1), B, cs()), 2, reps=10)
+prm = [model.net[0].weight, model.net[0].bias, model.net[2].weight, model.net[2].bias, model.net[4].weight, model.net[4].bias,
+       model.mean_layer.weight, model.mean_layer.bias, model.value_layer.weight, model.value_layer.bias]
+ms_wg = graph_time(lambda i: lib.lm_mlp_wgrad(p(grads.dz1), p(grads.dz2), p(grads.dz3), p(grads.dh), p(grads.a0), p(grads.a1), p(grads.a2), p(grads.a3), B,
+                                              p(grads._ws), grads._ctas, *[q.grad.data_ptr() for q in prm], cs()), 2, reps=10)
+FLOP = 3 * 116352 * B
+print(json.dumps({"update": f"MLP PPO gradients on tcgen05, minibatch {B}", "us_total": round(ms_all * 1e3, 1), "us_forward_train": round(ms_fwd * 1e3, 1),
+                  "us_backward_act": round(ms_bwd * 1e3, 1), "us_wgrad": round(ms_wg * 1e3, 1), "TFLOP/s (3x forward FLOP)": round(FLOP / (ms_all * 1e-3) / 1e12, 1),
+                  "hbm_bytes_per_sample": 64 * 4 + 2 * (64 + 256 + 128 + 64) + 2 * 2 * (256 + 128 + 64) + 2 * 2 * (256 + 128 + 64 + 16) + 2 * (64 + 256 + 128 + 64)}))
+
+
+def torch_step(autocast):
+    for q in model.parameters():
+        q.grad = None
+    with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+        mu, value, ls = model.reference_forward(pobs)
+    loss, _ = pp.ppo_loss(mu.float(), value.float().view(-1), ls, pa, pnl, padv, pov, pret, pom, log_std)
+    loss.backward()
+
+
+for ac in (False, True):
+    for _ in range(3):
+        torch_step(ac)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        torch_step(ac)
+    e1.record()
+    torch.cuda.synchronize()
+    print(json.dumps({"baseline": f"torch autograd, same GPU, {'bf16 autocast' if ac else 'fp32 (TF32 off)'}, minibatch {B}", "us_total": round(e0.elapsed_time(e1) / 10 * 1e3, 1)}))
