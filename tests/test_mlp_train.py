@@ -84,3 +84,50 @@ def test_ppo_gradients_match_autograd(B):
         assert err <= 3e-2 * scale, f"{k}: max err {err:.3e} vs scale {scale:.3e}"
         cos = torch.nn.functional.cosine_similarity(p.grad.flatten(), ref[k].flatten(), dim=0)
         assert float(cos) > 0.999, f"{k}: cosine {float(cos):.5f}"
+
+
+def test_whole_update_step_with_normalisation_and_adam():
+    """Observation normalisation in the training forward, gradients on tcgen05, fused clip + Adam on the flat arena: the parameter
+    step points the same way as the all-torch fp32 update (Adam divides by |g|, so compare the step direction, not its entries)."""
+    from locomanipulationrl_b200.policy.mlp import MlpActorCritic
+    from locomanipulationrl_b200.ppo import FlatAdam, MlpPpoGradients
+    from oracle import port_policy as pp
+    from tests.test_ppo import _batch
+    B = 16384
+    torch.manual_seed(5)
+    model, ref_model = MlpActorCritic(device="cuda:0"), MlpActorCritic(device="cuda:0")
+    ref_model.load_state_dict(model.state_dict())
+    obs = torch.randn(B, 64, device="cuda") * 3 + 0.5
+    mean, inv_std = torch.randn(64, device="cuda") * 0.3, 1.0 / torch.sqrt(torch.rand(64, device="cuda") + 0.5)
+    _, _, _, actions, old_nlp, adv, old_v, ret, old_mu, old_ls = (t.cuda() for t in _batch(B, 77, wide=True))
+    cfg = dict(e_clip=0.2, critic_coef=2.0, entropy_coef=0.0, bounds_loss_coef=1e-4, clip_value=True)
+    # all-torch reference
+    ref_params = list(ref_model.parameters())
+    before = torch.cat([p.detach().reshape(-1) for p in ref_params]).clone()
+    opt = torch.optim.Adam(ref_params, lr=3e-4, eps=1e-8)
+    mu, value, log_std = ref_model.reference_forward(torch.clamp((obs - mean) * inv_std, -5.0, 5.0))
+    loss, _ = pp.ppo_loss(mu, value.view(-1), log_std, actions, old_nlp, adv, old_v, ret, old_mu, old_ls, **cfg)
+    loss.backward()
+    torch.nn.utils.clip_grad_norm_(ref_params, 1.0)
+    opt.step()
+    step_ref = torch.cat([p.detach().reshape(-1) for p in ref_params]) - before
+    # ours: parameters and gradients as views of two flat arenas
+    params = list(model.parameters())
+    flat = torch.cat([p.detach().reshape(-1) for p in params])
+    flat_grad = torch.zeros_like(flat)
+    off = 0
+    for p in params:
+        k = p.numel()
+        p.data = flat[off:off + k].view_as(p)
+        p.grad = flat_grad[off:off + k].view_as(p)
+        off += k
+    MlpPpoGradients(model, max_batch=B, **cfg)(obs, actions, old_nlp, adv, old_v, ret, old_mu, old_ls, norm_mean=mean, norm_inv_std=inv_std)
+    g_ref = torch.cat([p.grad.reshape(-1) for p in ref_params])          # clipped reference gradient
+    opt_ours = FlatAdam(flat, lr=3e-4, eps=1e-8, max_grad_norm=1.0)
+    opt_ours.step(flat_grad)
+    cos_g = torch.nn.functional.cosine_similarity(flat_grad, g_ref, dim=0)
+    assert float(cos_g) > 0.999, float(cos_g)
+    step = flat - before
+    big = g_ref.abs() > 0.05 * g_ref.abs().max()                         # entries whose sign is not decided by bf16 noise
+    assert torch.equal(torch.sign(step[big]), torch.sign(step_ref[big]))
+    assert float((step - step_ref).abs().max()) <= 2.05 * 3e-4
