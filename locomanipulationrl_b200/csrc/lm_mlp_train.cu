@@ -99,10 +99,20 @@ __device__ __forceinline__ uint4 dz_chunk(const uint32_t* acc, const uint4& act)
   return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
-// one backward epilogue of a warp: kCols accumulator columns starting at column q * kCols of `tmem_acc` -> dZ chunks to `sdst`
-// (shared-memory operand, may be NULL) and `gdst` (global blob); `gact` = the saved activation blob of this tile
-template <int kCols>
-__device__ __forceinline__ void epilogue_bwd(uint32_t tmem_acc, const uint8_t* __restrict__ gact, uint8_t* sdst, uint8_t* gdst, int g, int q, int lane) {
+// One backward epilogue of a warp: kCols accumulator columns starting at column q * kCols of `tmem_acc` -> dZ chunks to `sdst`
+// (shared-memory operand, may be NULL) and `gdst` (global blob).  The saved activation chunks of the first kPre columns are fetched by
+// act_prefetch BEFORE the wait on the accumulator, so their global latency hides behind the GEMM; the rest is fetched in the loop.
+template <int kPre>
+struct ActRegs { uint4 v[kPre / 8]; };
+template <int kCols, int kPre>
+__device__ __forceinline__ void act_prefetch(const uint8_t* __restrict__ gact, int g, int q, int lane, ActRegs<kPre>& r) {
+  const int row = g * 32 + lane;
+#pragma unroll
+  for (int c = 0; c < kPre; c += 8) r.v[c / 8] = __ldcs(reinterpret_cast<const uint4*>(gact + elem_offset(TM, row, q * kCols + c)));
+}
+template <int kCols, int kPre>
+__device__ __forceinline__ void epilogue_bwd(uint32_t tmem_acc, const uint8_t* __restrict__ gact, uint8_t* sdst, uint8_t* gdst, int g, int q, int lane,
+                                             const ActRegs<kPre>& pre) {
   const int row = g * 32 + lane;
   const uint32_t taddr = tmem_acc + ((uint32_t)(g * 32) << 16) + (uint32_t)(q * kCols);
 #pragma unroll
@@ -110,8 +120,12 @@ __device__ __forceinline__ void epilogue_bwd(uint32_t tmem_acc, const uint8_t* _
     uint32_t acc[16];
     tmem_ld16(taddr + c, acc);
     const int col = q * kCols + c;
-    const uint4 a_lo = __ldcs(reinterpret_cast<const uint4*>(gact + elem_offset(TM, row, col)));
-    const uint4 a_hi = __ldcs(reinterpret_cast<const uint4*>(gact + elem_offset(TM, row, col + 8)));
+    uint4 a_lo, a_hi;
+    if (c < kPre) { a_lo = pre.v[c / 8]; a_hi = pre.v[c / 8 + 1]; }
+    else {
+      a_lo = __ldcs(reinterpret_cast<const uint4*>(gact + elem_offset(TM, row, col)));
+      a_hi = __ldcs(reinterpret_cast<const uint4*>(gact + elem_offset(TM, row, col + 8)));
+    }
     tmem_wait();
     const uint4 z_lo = dz_chunk(acc, a_lo), z_hi = dz_chunk(acc + 8, a_hi);
     if (sdst != nullptr) {
@@ -194,18 +208,24 @@ __global__ void __launch_bounds__(B_THREADS, 1) k_mlp_backward(const BwdArgs a) 
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_dh);
       // ---- E3: dZ3 = dA3 * ELU'(A3)
+      ActRegs<16> p3;
+      act_prefetch<D3 / 4, 16>(a.a3 + tile * blob_bytes(D3), g, q, lane, p3);
       mbar_wait(&bar_acc3, ph); tc_fence_after();
-      epilogue_bwd<D3 / 4>(tmem + BA3_COL, a.a3 + tile * blob_bytes(D3), DZ3s, a.dz3 + tile * blob_bytes(D3), g, q, lane);
+      epilogue_bwd<D3 / 4, 16>(tmem + BA3_COL, a.a3 + tile * blob_bytes(D3), DZ3s, a.dz3 + tile * blob_bytes(D3), g, q, lane, p3);
       fence_proxy_async(); tc_fence_before(); __syncwarp();
       if (lane == 0) mbar_arrive(&bar_z3);
       // ---- E2
+      ActRegs<32> p2;
+      act_prefetch<D2 / 4, 32>(a.a2 + tile * blob_bytes(D2), g, q, lane, p2);
       mbar_wait(&bar_acc2, ph); tc_fence_after();
-      epilogue_bwd<D2 / 4>(tmem + BA2_COL, a.a2 + tile * blob_bytes(D2), DZ2s, a.dz2 + tile * blob_bytes(D2), g, q, lane);
+      epilogue_bwd<D2 / 4, 32>(tmem + BA2_COL, a.a2 + tile * blob_bytes(D2), DZ2s, a.dz2 + tile * blob_bytes(D2), g, q, lane, p2);
       fence_proxy_async(); tc_fence_before(); __syncwarp();
       if (lane == 0) mbar_arrive(&bar_z2);
       // ---- E1: dZ1 leaves for the weight-gradient kernel only
+      ActRegs<64> p1;
+      act_prefetch<D1 / 4, 64>(a.a1 + tile * blob_bytes(D1), g, q, lane, p1);
       mbar_wait(&bar_acc1, ph); tc_fence_after();
-      epilogue_bwd<D1 / 4>(tmem + BA1_COL, a.a1 + tile * blob_bytes(D1), nullptr, a.dz1 + tile * blob_bytes(D1), g, q, lane);
+      epilogue_bwd<D1 / 4, 64>(tmem + BA1_COL, a.a1 + tile * blob_bytes(D1), nullptr, a.dz1 + tile * blob_bytes(D1), g, q, lane, p1);
       tc_fence_before();
     }
   }
