@@ -105,6 +105,31 @@ class GnnActorCritic(nn.Module):
         _lib.check(fn(self._handle, obs.data_ptr(), mu.data_ptr(), value.data_ptr(), n, stream), "lm_gnn_forward")
         return mu, value, self.log_std_parameter
 
+    def reference_forward(self, obs: torch.Tensor):
+        """The same network in stock torch ops, differentiable: the training path (autograd) and the tests' fp32 reference.
+        Per-endpoint form of graph_model_orebot_ov.py:46-59,142-159 — P = W1[:, :32] h, Q = W1[:, 32:] h per node, then per edge
+        ELU(W2 ELU(P_target + Q_source + b1) + b2) and a max over the in-edges of each target."""
+        F = torch.nn.functional
+        n = obs.shape[0]
+        net = self.net
+        order = (0, 1, 2, 3, 4, 6, 8, 10, 5, 7, 9, 11)                          # :117-126
+        cols = torch.tensor([[16 + j, 28 + j, 40 + j, 52 + j] for j in order], device=obs.device)
+        h = torch.cat([net.input_layer1(obs[:, 0:16]).view(n, 1, -1), net.input_layer2(obs[:, cols])], dim=1)        # [n,13,32]
+        src = [0] * 4 + list(range(1, 5)) + list(range(5, 9))
+        dst = list(range(1, 5)) + list(range(5, 9)) + list(range(9, 13))
+        s_idx = torch.tensor(src + dst, device=obs.device)                       # both directions (:142-159)
+        t_idx = torch.tensor(dst + src, device=obs.device)
+        for layer in (net.graph_layer1, net.graph_layer2, net.graph_layer3):
+            w1, hd = layer.linear1.weight, h.shape[-1]
+            pq = F.linear(h, torch.cat([w1[:, :hd], w1[:, hd:]], dim=0))         # [n,13,64]: P | Q
+            m = F.elu(pq[:, t_idx, :hd] + pq[:, s_idx, hd:] + layer.linear1.bias)
+            m = F.elu(layer.linear2(m))                                          # [n,24,32]
+            out = torch.full((n, 13, m.shape[-1]), -float("inf"), device=obs.device, dtype=m.dtype)
+            h = out.scatter_reduce(1, t_idx.view(1, -1, 1).expand_as(m), m, reduce="amax", include_self=True)
+        mu = self.mean_layer.action_layer(h[:, 1:13]).squeeze(-1)
+        value = self.value_layer.action_layer(torch.max(h, dim=1).values)
+        return mu, value, self.log_std_parameter
+
     def __del__(self):
         try:
             if self._handle:

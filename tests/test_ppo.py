@@ -119,3 +119,44 @@ def test_minibatch_update_through_the_mlp():
     FlatAdam(flat, lr=3e-4, eps=1e-8, max_grad_norm=1.0).step(flat_grad)
     for (name, p), q in zip(model.named_parameters(), ref_model.parameters()):
         assert_close(f"updated {name}", p, q, rtol=1e-4, atol=2e-6)
+
+
+@pytest.mark.gpu
+def test_minibatch_update_through_the_gnn():
+    """The GNN policy trains through its torch forward (autograd) + lm_ppo_loss + lm_adam_step; the same update all in torch."""
+    from locomanipulationrl_b200.policy.gnn import GnnActorCritic
+    from locomanipulationrl_b200.ppo import FlatAdam, PpoLoss
+    B = 4096
+    torch.manual_seed(4)
+    model, ref_model = GnnActorCritic(device="cuda:0"), GnnActorCritic(device="cuda:0")
+    ref_model.load_state_dict(model.state_dict())
+    obs = torch.randn(B, 64, device="cuda")
+    _, _, _, actions, old_nlp, adv, old_v, ret, old_mu, old_ls = (t.cuda() for t in _batch(B, 21, wide=True))
+    cfg = dict(e_clip=0.2, critic_coef=2.0, entropy_coef=0.0, bounds_loss_coef=1e-4, clip_value=True)
+    ref_params = list(ref_model.parameters())
+    opt = torch.optim.Adam(ref_params, lr=3e-4, eps=1e-8)
+    mu, value, log_std = ref_model.reference_forward(obs)
+    loss, _ = pp.ppo_loss(mu, value.view(-1), log_std, actions, old_nlp, adv, old_v, ret, old_mu, old_ls, **cfg)
+    loss.backward()
+    torch.nn.utils.clip_grad_norm_(ref_params, 1.0)
+    opt.step()
+    params = list(model.parameters())
+    flat = torch.cat([p.detach().reshape(-1) for p in params])
+    flat_grad = torch.zeros_like(flat)
+    off = 0
+    for p in params:
+        k = p.numel()
+        p.data = flat[off:off + k].view_as(p)
+        p.grad = flat_grad[off:off + k].view_as(p)
+        off += k
+    mu, value, log_std = model.reference_forward(obs)
+    g_mu, g_v, g_ls, _ = PpoLoss(**cfg)(mu.detach().contiguous(), value.detach().view(-1).contiguous(), log_std.detach().contiguous(), actions,
+                                        old_nlp, adv, old_v, ret, old_mu, old_ls)
+    torch.autograd.backward([mu, value.view(-1), log_std], [g_mu, g_v, g_ls])
+    FlatAdam(flat, lr=3e-4, eps=1e-8, max_grad_norm=1.0).step(flat_grad)
+    for (name, p), q in zip(model.named_parameters(), ref_model.parameters()):
+        assert_close(f"updated {name}", p, q, rtol=1e-4, atol=2e-6)
+    # and the kernels' inference forward tracks the updated parameters
+    mu_k, value_k, _ = GnnActorCritic.forward(model, obs)
+    mu_t, value_t, _ = model.reference_forward(obs)
+    assert_close("bf16 kernel after the update", mu_k, mu_t.detach(), rtol=0, atol=1e-2)
