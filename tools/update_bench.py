@@ -86,7 +86,21 @@ report("k_adam_step (58,637 parameters, clip + Adam)", ms, 28, 58637)
 from locomanipulationrl_b200 import _lib  # noqa: E402
 from locomanipulationrl_b200.policy.mlp import MlpActorCritic  # noqa: E402
 from locomanipulationrl_b200.ppo import MlpPpoGradients  # noqa: E402
-from oracle import port_policy as pp  # noqa: E402  (bench-side checker / baseline only)
+
+
+def torch_ppo_loss(mu, value, log_std, actions, old_neglogp, advantages, old_values, returns, e_clip=0.2, critic_coef=2.0, bounds_loss_coef=1e-4):
+    """The rl_games loss in stock torch ops, written out here for the torch-autograd timing baseline only (the checked
+    restatement lives with the tests; this tool must not reach into oracle/)."""
+    import math
+    sigma = torch.exp(log_std)
+    nlp = 0.5 * (((actions - mu) / sigma) ** 2).sum(-1) + 0.5 * math.log(2.0 * math.pi) * actions.shape[-1] + log_std.sum(-1)
+    ratio = torch.exp(old_neglogp - nlp)
+    a_loss = torch.max(-advantages * ratio, -advantages * torch.clamp(ratio, 1.0 - e_clip, 1.0 + e_clip))
+    vpc = old_values + (value - old_values).clamp(-e_clip, e_clip)
+    c_loss = torch.max((value - returns) ** 2, (vpc - returns) ** 2)
+    b_loss = (torch.clamp_max(mu + 1.1, 0.0) ** 2 + torch.clamp_min(mu - 1.1, 0.0) ** 2).sum(-1)
+    return a_loss.mean() + 0.5 * c_loss.mean() * critic_coef + b_loss.mean() * bounds_loss_coef
+
 
 torch.manual_seed(0)
 model = MlpActorCritic(device=dev)
@@ -124,7 +138,7 @@ def torch_step(autocast):
         q.grad = None
     with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
         mu, value, ls = model.reference_forward(pobs)
-    loss, _ = pp.ppo_loss(mu.float(), value.float().view(-1), ls, pa, pnl, padv, pov, pret, pom, log_std)
+    loss = torch_ppo_loss(mu.float(), value.float().view(-1), ls, pa, pnl, padv, pov, pret)
     loss.backward()
 
 
