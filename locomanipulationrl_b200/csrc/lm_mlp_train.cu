@@ -497,11 +497,9 @@ int lm_mlp_wgrad(const void* dz1, const void* dz2, const void* dz3, const void* 
     return lm_fail(LM_ERR_BAD_ARG, "lm_mlp_wgrad: bad argument");
   if (!g_w1 || !g_b1 || !g_w2 || !g_b2 || !g_w3 || !g_b3 || !g_w_mu || !g_b_mu || !g_w_value || !g_b_value)
     return lm_fail(LM_ERR_BAD_ARG, "lm_mlp_wgrad: NULL gradient tensor");
-  static bool attr_set = false;
-  if (!attr_set) {
+  {   // per call and per current device: the entry takes no handle, and the attribute is a cheap host-side setting
     cudaError_t e = cudaFuncSetAttribute(k_mlp_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_BYTES);
     if (e != cudaSuccess) return lm_fail((int)e, "lm_mlp_wgrad: smem attribute: %s", cudaGetErrorString(e));
-    attr_set = true;
   }
   WgArgs a;
   a.dz1 = (const uint8_t*)dz1; a.dz2 = (const uint8_t*)dz2; a.dz3 = (const uint8_t*)dz3; a.dh = (const uint8_t*)dh;
@@ -522,11 +520,9 @@ int lm_mlp_backward(LmMlp* m, const float* grad_mu, const float* grad_value, con
   if (!m->packed || !m->blob_t) return lm_fail(LM_ERR_BAD_ARG, "lm_mlp_backward: weights not packed (call lm_mlp_pack)");
   if ((((uintptr_t)grad_mu) | ((uintptr_t)a1) | ((uintptr_t)a2) | ((uintptr_t)a3) | ((uintptr_t)dh) | ((uintptr_t)dz3) | ((uintptr_t)dz2) | ((uintptr_t)dz1)) & 15)
     return lm_fail(LM_ERR_ALIGNMENT, "lm_mlp_backward: grad_mu / blobs must be 16-byte aligned");
-  static bool attr_set = false;
-  if (!attr_set) {
+  {
     cudaError_t e = cudaFuncSetAttribute(k_mlp_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM_BYTES);
     if (e != cudaSuccess) return lm_fail((int)e, "lm_mlp_backward: smem attribute: %s", cudaGetErrorString(e));
-    attr_set = true;
   }
   BwdArgs a;
   a.wt = m->blob_t; a.grad_mu = grad_mu; a.grad_value = grad_value;
