@@ -455,6 +455,34 @@ def cuda_arm(args):
             line_extra["roofline_rollout"] = {"kernel": "k_rollout_write", "bound": "hbm", "achieved": n * B_RO / (ms_ro * 1e-3) / 1e9, "peak": hbm,
                                               "unit": "GB/s", "frac": n * B_RO / (ms_ro * 1e-3) / 1e9 / hbm, "bytes_per_env": B_RO, "ms": ms_ro}
             line_extra["kernel_ms"]["rollout_write"] = ms_ro
+
+            # 8 rotating rollouts (8 x 21 MB > the 126 MB L2), so the figure is HBM traffic, not L2 hits
+            gsets = [tuple(torch.randn(HORIZON, n, device=device) for _ in range(3)) + (torch.empty(HORIZON, n, device=device), torch.empty(HORIZON, n, device=device))
+                     for _ in range(8)]
+
+            def gae_only(i):
+                r_, v_, d_, adv_, ret_ = gsets[i % 8]
+                pipe._lib_mod.check(pipe.lib.lm_gae(r_.data_ptr(), v_.data_ptr(), d_.data_ptr(), v_[-1].data_ptr(), d_[-1].data_ptr(), adv_.data_ptr(),
+                                                    ret_.data_ptr(), HORIZON, n, 0.99, 0.95, 0, torch.cuda.current_stream().cuda_stream), "lm_gae")
+            for i in range(8):
+                gae_only(i)
+            torch.cuda.synchronize()
+            g8 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g8):
+                for i in range(8):
+                    gae_only(i)
+            g8.replay(); torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(20):
+                g8.replay()
+            e1.record(); torch.cuda.synchronize()
+            ms_gae = e0.elapsed_time(e1) / (20 * 8)
+            b_gae = 20 * HORIZON + 8             # r, V, d in, advantages, returns out per (env, t) + last value / done per env
+            line_extra["roofline_gae"] = {"kernel": "k_gae_time_major (once per 16-step rollout)", "bound": "hbm", "achieved": n * b_gae / (ms_gae * 1e-3) / 1e9,
+                                          "peak": hbm, "unit": "GB/s", "frac": n * b_gae / (ms_gae * 1e-3) / 1e9 / hbm, "bytes_per_env": b_gae, "ms": ms_gae,
+                                          "l2": "8 rotating rollouts (172 MB > L2)"}
+            line_extra["kernel_ms"]["gae_per_rollout"] = ms_gae
         if world == 1 and not args.no_large:
             line_extra["roofline_large"] = large_roofline(device, graph_time, hbm)
 
