@@ -73,8 +73,17 @@ pv, pnl, padv, pov, pret = (torch.randn(B, device=dev, generator=g) for _ in ran
 head = PpoLoss(device=dev)
 out = {"grad_mu": torch.empty(B, 12, device=dev), "grad_value": torch.empty(B, device=dev)}
 head(pm, pv, log_std, pa, pnl, padv, pov, pret, pom, log_std, out=out)
-ms = graph_time(lambda i: head(pm, pv, log_std, pa, pnl, padv, pov, pret, pom, log_std, out=out), 4)
-report(f"k_ppo_loss (minibatch {B})", ms, 3 * 48 + 5 * 4 + 48 + 4, B)
+# three rotating input sets (3 x 57 MB > L2): replaying one set alone would time L2 hits, not HBM
+psets = [(pm, pv, pa, pnl, padv, pov, pret, pom)] + [tuple(t.clone() for t in (pm, pv, pa, pnl, padv, pov, pret, pom)) for _ in range(2)]
+
+
+def loss_call(i):
+    m_, v_, a_, nl_, ad_, ov_, rt_, om_ = psets[i % 3]
+    head(m_, v_, log_std, a_, nl_, ad_, ov_, rt_, om_, log_std, out=out)
+
+
+ms = graph_time(loss_call, 6)
+report(f"k_ppo_loss (minibatch {B}, inputs rotated past L2)", ms, 3 * 48 + 5 * 4 + 48 + 4, B)
 
 flat, grads = torch.randn(58637, device=dev, generator=g), torch.randn(58637, device=dev, generator=g)
 opt = FlatAdam(flat)
