@@ -130,3 +130,82 @@ class MlpPpoGradients:
                                     p(self._ws), self._ctas, *[q.grad.data_ptr() for q in params], s), "lm_mlp_wgrad")
         m.log_std_parameter.grad.copy_(g_ls)
         return stats
+
+
+class PpoUpdater:
+    """rl_games' ``train_epoch`` for the MLP actor-critic on the library's kernels: GAE over the time-major rollout, advantage
+    normalisation, ``mini_epochs`` passes over contiguous minibatches (rl_games' PPODataset slices the flattened batch without
+    shuffling, so every minibatch is a zero-copy view of the rollout buffers), tcgen05 gradients, one all-reduce of the flat gradient arena when a
+    process group exists, clip + Adam, and the KL-adaptive learning rate (cfg/train/JointLocomanipulationPPO.yaml:52-72).
+
+    Tested single-process (tests/test_mlp_train.py); the ``world > 1`` all-reduce branch has not been run yet.
+    """
+
+    def __init__(self, model, rollout, minibatch_size: int, mini_epochs: int = 5, lr: float = 3e-4, gamma: float = 0.99, tau: float = 0.95,
+                 e_clip: float = 0.2, critic_coef: float = 2.0, entropy_coef: float = 0.0, bounds_loss_coef: float = 1e-4, clip_value: bool = True,
+                 max_grad_norm: float = 1.0, normalize_advantage: bool = True, kl_threshold: Optional[float] = 0.008, lr_bounds=(1e-6, 1e-2)):
+        self.model, self.rollout = model, rollout
+        T, N = rollout.horizon, rollout.num_envs
+        if (T * N) % minibatch_size:
+            raise ValueError("batch size must be divisible by the minibatch size (rl_games asserts the same)")
+        self.minibatch_size, self.mini_epochs = int(minibatch_size), int(mini_epochs)
+        self.gamma, self.tau, self.normalize_advantage = float(gamma), float(tau), bool(normalize_advantage)
+        self.kl_threshold, self.lr_bounds = kl_threshold, lr_bounds
+        dev = rollout.device
+        # parameters and gradients as views of two flat arenas (the layout FlatAdam and the fused all-reduce work on)
+        params = list(model.parameters())
+        self.flat = torch.cat([p.detach().reshape(-1) for p in params])
+        self.flat_grad = torch.zeros_like(self.flat)
+        off = 0
+        for p in params:
+            k = p.numel()
+            p.data = self.flat[off:off + k].view_as(p)
+            p.grad = self.flat_grad[off:off + k].view_as(p)
+            off += k
+        self.opt = FlatAdam(self.flat, lr=lr, max_grad_norm=max_grad_norm)
+        self.grads = MlpPpoGradients(model, max_batch=self.minibatch_size, e_clip=e_clip, critic_coef=critic_coef, entropy_coef=entropy_coef,
+                                     bounds_loss_coef=bounds_loss_coef, clip_value=clip_value)
+        self.advantages = torch.empty(T, N, device=dev)
+        self.returns = torch.empty(T, N, device=dev)
+        self.old_log_std = torch.empty(12, device=dev)
+        self._kl = torch.zeros(1, device=dev)
+
+    @torch.no_grad()
+    def update(self, last_values: torch.Tensor, last_dones: torch.Tensor, norm_mean=None, norm_inv_std=None):
+        """One PPO update over the rollout currently in the buffer.  Returns the last minibatch's loss-head stats (device tensor [8])."""
+        from . import gae as _gae
+        td = self.rollout.tensor_dict
+        T, N = self.rollout.horizon, self.rollout.num_envs
+        adv, ret = _gae.compute_gae(td["rewards"], td["values"], td["dones"], last_values, last_dones, gamma=self.gamma, lam=self.tau,
+                                    variant=_gae.RLGAMES)
+        self.returns.copy_(ret)
+        if self.normalize_advantage:                      # rl_games: (adv - mean) / (std + 1e-8) over the whole batch
+            adv = (adv - adv.mean()) / (adv.std() + 1e-8)
+        self.advantages.copy_(adv)
+        self.old_log_std.copy_(self.model.log_std_parameter.detach())
+        flat = lambda t: t.view(T * N, *t.shape[2:])
+        obs, actions, mus = flat(td["obses"]), flat(td["actions"]), flat(td["mus"])
+        values, neglogp = flat(td["values"]), flat(td["neglogpacs"])
+        advs, rets = flat(self.advantages), flat(self.returns)
+        import torch.distributed as tdist
+        world = tdist.get_world_size() if (tdist.is_available() and tdist.is_initialized()) else 1
+        stats = None
+        for _ in range(self.mini_epochs):
+            self._kl.zero_()
+            nmb = (T * N) // self.minibatch_size
+            for i in range(nmb):
+                sl = slice(i * self.minibatch_size, (i + 1) * self.minibatch_size)
+                stats = self.grads(obs[sl], actions[sl], neglogp[sl], advs[sl], values[sl], rets[sl], mus[sl], self.old_log_std,
+                                   norm_mean=norm_mean, norm_inv_std=norm_inv_std)
+                if world > 1:                             # one collective per minibatch over the flat gradient arena (sum; scaled in the Adam step)
+                    tdist.all_reduce(self.flat_grad)
+                self.opt.step(self.flat_grad, grad_scale=1.0 / world)
+                self._kl += stats[4]
+            if self.kl_threshold is not None:             # rl_games adaptive schedule, once per mini-epoch (one host sync)
+                kl = float(self._kl) / nmb
+                lo, hi = self.lr_bounds
+                if kl > 2.0 * self.kl_threshold:
+                    self.opt.lr = max(self.opt.lr / 1.5, lo)
+                elif kl < 0.5 * self.kl_threshold:
+                    self.opt.lr = min(self.opt.lr * 1.5, hi)
+        return stats

@@ -131,3 +131,55 @@ def test_whole_update_step_with_normalisation_and_adam():
     big = g_ref.abs() > 0.05 * g_ref.abs().max()                         # entries whose sign is not decided by bf16 noise
     assert torch.equal(torch.sign(step[big]), torch.sign(step_ref[big]))
     assert float((step - step_ref).abs().max()) <= 2.05 * 3e-4
+
+
+def test_ppo_updater_epoch_tracks_the_all_torch_loop():
+    """PpoUpdater (GAE, advantage normalisation, contiguous minibatches, tcgen05 gradients, clip + Adam) against the same loop in
+    stock torch on a copy of the model: after one mini-epoch the parameter steps point the same way and the value loss went down."""
+    from locomanipulationrl_b200.policy.mlp import MlpActorCritic
+    from locomanipulationrl_b200.ppo import PpoUpdater
+    from locomanipulationrl_b200.rollout import RolloutBuffer
+    from oracle import port_policy as pp
+    T, N, MB = 8, 2048, 4096
+    torch.manual_seed(11)
+    model, ref_model = MlpActorCritic(device="cuda:0"), MlpActorCritic(device="cuda:0")
+    ref_model.load_state_dict(model.state_dict())
+    buf = RolloutBuffer(T, N, reward_scale=1.0)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    log_std = model.log_std_parameter.detach().clone()
+    with torch.no_grad():
+        for t in range(T):                                   # a synthetic rollout under the current policy
+            obs = torch.randn(N, 64, device="cuda", generator=g).clamp(-5, 5)
+            mu, value, _ = model.reference_forward(obs)
+            buf.write(t, obs, mu.contiguous(), value.contiguous(), log_std, torch.randn(N, device="cuda", generator=g),
+                      (torch.rand(N, device="cuda", generator=g) < 0.02).long(), noise=torch.randn(N, 12, device="cuda", generator=g))
+    last_v = torch.randn(N, device="cuda", generator=g)
+    last_d = torch.zeros(N, device="cuda")
+    td = {k: v.clone() for k, v in buf.tensor_dict.items()}
+    before = torch.cat([p.detach().reshape(-1) for p in ref_model.parameters()]).clone()
+    # ---- all-torch loop
+    adv, ret = pp.gae_rlgames(td["rewards"].cpu(), td["values"].cpu(), td["dones"].cpu(), last_v.cpu(), last_d.cpu())
+    adv, ret = adv.cuda(), ret.cuda()
+    adv = (adv - adv.mean()) / (adv.std() + 1e-8)
+    fl = lambda x: x.reshape(T * N, *x.shape[2:])
+    ref_params = list(ref_model.parameters())
+    opt = torch.optim.Adam(ref_params, lr=3e-4, eps=1e-8)
+    c_first = c_last = None
+    for i in range(T * N // MB):
+        sl = slice(i * MB, (i + 1) * MB)
+        mu, value, ls = ref_model.reference_forward(fl(td["obses"])[sl])
+        loss, info = pp.ppo_loss(mu, value.view(-1), ls, fl(td["actions"])[sl], fl(td["neglogpacs"])[sl], fl(adv)[sl], fl(td["values"])[sl], fl(ret)[sl],
+                                 fl(td["mus"])[sl], log_std)
+        opt.zero_grad()
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(ref_params, 1.0)
+        opt.step()
+    step_ref = torch.cat([p.detach().reshape(-1) for p in ref_params]) - before
+    # ---- ours
+    up = PpoUpdater(model, buf, minibatch_size=MB, mini_epochs=1, lr=3e-4, kl_threshold=None)
+    stats = up.update(last_v, last_d)
+    step = up.flat - before
+    cos = torch.nn.functional.cosine_similarity(step, step_ref, dim=0)
+    assert float(cos) > 0.97, float(cos)
+    assert torch.isfinite(stats).all()
+    assert_close("GAE returns inside the updater", up.returns, ret, rtol=1e-5, atol=1e-5)
