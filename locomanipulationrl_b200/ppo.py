@@ -138,7 +138,8 @@ class PpoUpdater:
     shuffling, so every minibatch is a zero-copy view of the rollout buffers), tcgen05 gradients, one all-reduce of the flat gradient arena when a
     process group exists, clip + Adam, and the KL-adaptive learning rate (cfg/train/JointLocomanipulationPPO.yaml:52-72).
 
-    Tested single-process (tests/test_mlp_train.py); the ``world > 1`` all-reduce branch has not been run yet.
+    Tested single-process against the all-torch loop (tests/test_mlp_train.py); the ``world > 1`` all-reduce branch is checked by
+    tools/ppo_updater_2rank.py under torchrun on 2 GPUs (identical parameters on both ranks, different from a rank on its own).
     """
 
     def __init__(self, model, rollout, minibatch_size: int, mini_epochs: int = 5, lr: float = 3e-4, gamma: float = 0.99, tau: float = 0.95,
