@@ -138,6 +138,10 @@ class PpoUpdater:
     shuffling, so every minibatch is a zero-copy view of the rollout buffers), tcgen05 gradients, one all-reduce of the flat gradient arena when a
     process group exists, clip + Adam, and the KL-adaptive learning rate (cfg/train/JointLocomanipulationPPO.yaml:52-72).
 
+    Not covered: rl_games' ``normalize_value`` (values / returns standardised by a running mean/std, cfg/train/*PPO.yaml:47) — the
+    statistics kernel exists (``rollout.RunningMeanStd`` with dim 1) but is not wired into this loop; observation normalisation is
+    passed in as ``norm_mean`` / ``norm_inv_std``.
+
     Tested single-process against the all-torch loop (tests/test_mlp_train.py); the ``world > 1`` all-reduce branch is checked by
     tools/ppo_updater_2rank.py under torchrun on 2 GPUs (identical parameters on both ranks, different from a rank on its own).
     """
