@@ -333,9 +333,12 @@ typedef struct LmRolloutStep {   /* one env step; device pointers */
   const float* mu;        /* [N,12] policy mean                       */
   const float* value;     /* [N]                                      */
   const float* log_std;   /* [12]   state-independent log sigma       */
-  const float* noise;     /* [N,12] standard-normal draws of the caller's generator; NULL: action = mu */
+  const float* noise;     /* [N,12] standard-normal draws of the caller's generator; NULL: see sample_in_kernel */
   const float* rew;       /* [N]                                      */
   const int64_t* dones;   /* [N]    reset_buf                         */
+  /* noise == NULL: sample_in_kernel != 0 draws N(0,1) in the kernel (Philox4x32-10 keyed by noise_seed, stream position noise_step,
+   * element index: no draw tensor in HBM, reproducible for a given seed / step); 0: action = mu (evaluation) */
+  uint64_t noise_seed; uint64_t noise_step; int32_t sample_in_kernel; int32_t pad_;
 } LmRolloutStep;
 typedef struct LmRolloutBuffers {
   float* obses;    /* [T,N,64] */

@@ -72,7 +72,8 @@ class LmRunningStats(C.Structure):
 
 
 class LmRolloutStep(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in ("obs", "mu", "value", "log_std", "noise", "rew", "dones")]
+    _fields_ = [(n, C.c_void_p) for n in ("obs", "mu", "value", "log_std", "noise", "rew", "dones")] + \
+               [("noise_seed", C.c_uint64), ("noise_step", C.c_uint64), ("sample_in_kernel", _i32), ("pad_", _i32)]
 
 
 class LmRolloutBuffers(C.Structure):

@@ -9,6 +9,7 @@
 // generator keyed by (seed, step, element), so the kernel needs neither draw tensors nor ranks.
 #include "lm_common.cuh"
 #include "lm_host.h"
+#include "lm_rng.cuh"
 
 namespace lm {
 namespace noise {
@@ -51,33 +52,10 @@ __global__ void __launch_bounds__(TILE) k_noise_count(const Args a) {
   }
 }
 
-// ---- Philox4x32-10 (Salmon et al., SC'11): counter = (element, stream), key = seed
-__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    const unsigned int hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
-    const unsigned int hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
-    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
-    key.x += 0x9E3779B9u; key.y += 0xBB67AE85u;
-  }
-  return ctr;
-}
 __device__ __forceinline__ float4 draw4(const Args& a, int distribution, unsigned long long element, unsigned int which) {
-  const unsigned long long stream = a.step * 2ull + which;
-  const uint4 r = philox4x32_10(make_uint4((unsigned int)element, (unsigned int)(element >> 32), (unsigned int)stream, (unsigned int)(stream >> 32)),
-                                make_uint2((unsigned int)a.seed, (unsigned int)(a.seed >> 32)));
-  if (distribution == LM_DIST_GAUSSIAN) {      // Box-Muller on two pairs
-    const float u0 = ((float)(r.x >> 8) + 1.0f) * 5.9604644775390625e-08f, u1 = ((float)(r.z >> 8) + 1.0f) * 5.9604644775390625e-08f;   // (0, 1]
-    const float r0 = sqrtf(-2.0f * logf(u0)), r1 = sqrtf(-2.0f * logf(u1));
-    float s0, c0, s1, c1;
-    sincospif((float)r.y * 4.656612873077393e-10f, &s0, &c0);       // 2 pi * (y / 2^32)
-    sincospif((float)r.w * 4.656612873077393e-10f, &s1, &c1);
-    return make_float4(r0 * c0, r0 * s0, r1 * c1, r1 * s1);
-  }
-  return make_float4((float)(r.x >> 8) * 5.9604644775390625e-08f, (float)(r.y >> 8) * 5.9604644775390625e-08f,       // [0, 1)
-                     (float)(r.z >> 8) * 5.9604644775390625e-08f, (float)(r.w >> 8) * 5.9604644775390625e-08f);
+  const uint4 r = philox_at(a.seed, a.step * 2ull + which, element);
+  return distribution == LM_DIST_GAUSSIAN ? normal4(r) : uniform4(r);
 }
-
 __device__ __forceinline__ float shape1(const LmNoiseSpec& sp, float d) {
   const float v = add(mul(sp.scale, d), sp.shift);          // randn * std + mean | (hi - lo) * rand + lo | (log hi - log lo) * rand + log lo
   return sp.distribution == LM_DIST_LOGUNIFORM ? expf(v) : v;

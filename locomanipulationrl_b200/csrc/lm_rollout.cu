@@ -15,6 +15,7 @@
 #include "lm_common.cuh"
 #include "lm_host.h"
 #include "lm_reduce.cuh"
+#include "lm_rng.cuh"
 
 namespace lm {
 namespace rollout {
@@ -33,6 +34,7 @@ struct WriteArgs {
   const long long* dones;
   float* obses; float* actions; float* mus; float* values; float* rewards; float* dones_f; float* neglogp; float* actions_out;
   int n; float reward_scale;
+  unsigned long long noise_seed, noise_step; int sample_in_kernel;
   Stats st; int has_stats;
   double* partials; unsigned int* ticket;
 };
@@ -102,7 +104,8 @@ __device__ __forceinline__ EnvIn env_load(const WriteArgs& a, unsigned int e) {
 #pragma unroll
   for (int q = 0; q < 3; ++q) {
     in.mv[q] = __ldg(reinterpret_cast<const float4*>(a.mu + e * 12) + q);            // rows are 48 B: let L1 keep the shared sectors
-    in.nv[q] = a.noise ? __ldg(reinterpret_cast<const float4*>(a.noise + e * 12) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+    in.nv[q] = a.noise ? __ldg(reinterpret_cast<const float4*>(a.noise + e * 12) + q)
+                       : (a.sample_in_kernel ? normal4(philox_at(a.noise_seed, a.noise_step, (unsigned long long)e * 3ull + q)) : make_float4(0.f, 0.f, 0.f, 0.f));
   }
   in.val = a.value[e]; in.rw = a.rew[e]; in.dn = a.dones[e];
   return in;
@@ -368,6 +371,7 @@ int lm_rollout_write(LmRollout* r, const LmRolloutStep* step, const LmRolloutBuf
   a.values = buf->values + (size_t)t * n; a.rewards = buf->rewards + (size_t)t * n; a.dones_f = buf->dones + (size_t)t * n;
   a.neglogp = buf->neglogp + (size_t)t * n; a.actions_out = actions_out;
   a.n = buf->num_envs; a.reward_scale = buf->reward_scale;
+  a.noise_seed = step->noise_seed; a.noise_step = step->noise_step; a.sample_in_kernel = step->sample_in_kernel;
   a.has_stats = obs_stats ? 1 : 0;
   if (obs_stats) a.st = Stats{obs_stats->mean, obs_stats->var, obs_stats->count, obs_stats->dim, obs_stats->variant};
   else a.st = Stats{nullptr, nullptr, nullptr, 0, 0};

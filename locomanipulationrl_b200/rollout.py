@@ -81,15 +81,21 @@ class RolloutBuffer:
             "values": torch.zeros(T, N, device=d), "rewards": torch.zeros(T, N, device=d), "dones": torch.zeros(T, N, device=d),
             "neglogpacs": torch.zeros(T, N, device=d)}
         self._lib, self._h = _handle(self.device)
+        self._sample_calls = 0                    # stream position of the kernel's own generator
         td = self.tensor_dict
         self._buf = _lib.LmRolloutBuffers(td["obses"].data_ptr(), td["actions"].data_ptr(), td["mus"].data_ptr(), td["values"].data_ptr(),
                                           td["rewards"].data_ptr(), td["dones"].data_ptr(), td["neglogpacs"].data_ptr(), T, N, self.reward_scale)
 
     def write(self, t: int, obs, mu, value, log_std, rew, dones, noise: Optional[torch.Tensor] = None,
-              actions_out: Optional[torch.Tensor] = None, obs_stats: Optional[RunningMeanStd] = None) -> None:
-        """Slot ``t`` <- this step.  ``noise`` = standard-normal draws [N,12] of the caller's generator (None: act = mu);
-        ``actions_out`` receives the sampled actions for the next ``pre_physics_step``."""
-        step = _lib.LmRolloutStep(_lib.ptr(obs), _lib.ptr(mu), _lib.ptr(value), _lib.ptr(log_std), _lib.ptr(noise), _lib.ptr(rew), _lib.ptr(dones))
+              actions_out: Optional[torch.Tensor] = None, obs_stats: Optional[RunningMeanStd] = None, sample_seed: Optional[int] = None) -> None:
+        """Slot ``t`` <- this step.  ``noise`` = standard-normal draws [N,12] of the caller's generator; without it, ``sample_seed``
+        makes the kernel draw its own N(0,1) noise (counter-based: reproducible for a given seed and call count, no draw tensor),
+        and neither means act = mu (evaluation).  ``actions_out`` receives the sampled actions for the next ``pre_physics_step``."""
+        in_kernel = noise is None and sample_seed is not None
+        step = _lib.LmRolloutStep(_lib.ptr(obs), _lib.ptr(mu), _lib.ptr(value), _lib.ptr(log_std), _lib.ptr(noise), _lib.ptr(rew), _lib.ptr(dones),
+                                  int(sample_seed or 0), self._sample_calls, int(in_kernel), 0)
+        if in_kernel:
+            self._sample_calls += 1
         st = obs_stats.c_struct() if obs_stats is not None else None
         stream = torch.cuda.current_stream(self.device).cuda_stream
         rc = self._lib.lm_rollout_write(self._h, C.byref(step), C.byref(self._buf), int(t), _lib.ptr(actions_out),

@@ -99,3 +99,30 @@ def test_rms_update_matches_port(dim, n):
     assert float(stats.count) == float(ref["count"])
     mean32, inv_std32 = stats.export()
     assert_close("skrl 1/std", inv_std32, 1.0 / (torch.sqrt(ref["var"].float()) + 1e-8), rtol=2e-6, atol=0)
+
+
+@pytest.mark.gpu
+def test_rollout_write_in_kernel_sampling():
+    """sample_seed: the kernel draws its own N(0,1) noise.  Check the moments of (a - mu) / sigma, that neglogp is consistent with the
+    stored action, reproducibility for a seed, and fresh draws from call to call."""
+    from locomanipulationrl_b200.rollout import RolloutBuffer
+    n, T = 65536, 2
+    obs, mu, value, _, rew, dones = (t.cuda() for t in _step_inputs(n, 1))
+    log_std = torch.linspace(-0.5, 0.3, 12).cuda()
+    a = torch.zeros(n, 12, device="cuda")
+
+    def run(seed):
+        buf = RolloutBuffer(T, n)
+        for t in range(T):
+            buf.write(t, obs, mu, value, log_std, rew, dones, actions_out=a, sample_seed=seed)
+        return buf.tensor_dict
+
+    td = run(7)
+    z = (td["actions"] - td["mus"]) / log_std.exp()
+    assert abs(float(z.mean())) < 5e-3 and abs(float(z.std()) - 1.0) < 5e-3 and float(z.abs().max()) < 7.0
+    assert float(torch.corrcoef(z[0, :, :6].t()).fill_diagonal_(0).abs().max()) < 0.02          # columns independent
+    c01 = float((z[0] * z[1]).mean())
+    assert abs(c01) < 5e-3, c01                                                                  # fresh draws every call
+    ref = pp.neglogp(td["actions"][1].cpu(), td["mus"][1].cpu(), log_std.cpu())
+    assert_close("neglogp of the in-kernel sample", td["neglogpacs"][1], ref, rtol=1e-5, atol=1e-5)
+    assert torch.equal(run(7)["actions"], td["actions"]) and not torch.equal(run(8)["actions"], td["actions"])
