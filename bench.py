@@ -12,6 +12,13 @@ Other workloads: --workload manip16k (configs[1]), gnn_gae (configs[3]).
 
 Prints ONE JSON line (rank 0).  `value` = device-resident throughput; `e2e` = the same step driven through the
 C-ABI host entry (lm_task_step_host) with pinned-host inputs/outputs copied every step.
+
+Timed region: whole rollout horizons.  --steps K is rounded UP to a multiple of the horizon (48 for the MLP co-train workload,
+the reference yaml; 16 for gnn_gae) and repeated until the region lasts >= 0.2 s; the line's `steps` is the number of steps
+actually timed (`steps_requested` = K).  Every horizon ends with the rollout-boundary collective (episode statistics + the
+gradient arena, one message), so a multi-rank line always has `collectives_in_timed_region` >= 1.  The `train` block is
+the same loop with real work at the boundary: rollout writer every step, then GAE and the PPO update (5 mini-epochs x 8
+minibatches, tcgen05 gradients, the gradient all-reduce fused into the weight-gradient reduction, clip + Adam).
 """
 from __future__ import annotations
 
@@ -37,6 +44,7 @@ B_POST = 892              # of which the post_physics_step kernel moves (DESIGN.
 MLP_FLOPS = 116352        # FLOP / env
 HORIZON = 16              # GAE rollout length of the gnn_gae workload (BASELINE configs[3]: "16-step rollout")
 HORIZON_MLP = 48          # rl_games horizon_length of the co-train yaml (cfg/train/JointLocomanipulationVerticalPPO.yaml:66)
+MIN_TIMED_S = 0.2         # the timed region is at least this long whatever --steps says
 
 WORKLOADS = {
     "cotrain64k": dict(task="JointLocomanipulationVertical", envs=ENVS_PER_GPU, policy="mlp",
@@ -167,13 +175,44 @@ def reference_arm(args):
     line = {"impl": "reference", "metric": "env-steps/s (obs+reward+PD+reset+policy)", "value": value, "unit": "env-steps/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": w["desc"], "envs_per_step": envs},
+            "config": {"workload": w["desc"], "envs_per_gpu": w["envs"], "global_envs": w["envs"] * args.gpus,
+                       "parallelism": f"env-shard x{args.gpus}", "reference_sample_envs": envs},
             "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
 
 # ----------------------------------------------------------------------------------------------- CUDA arm
+def bind_host_cores(local_rank, world):
+    """One disjoint slice of the host cores per rank (launch thread + pinned-buffer first touch stay put); NUMA-local to the rank's
+    GPU when the platform exposes more than one node.  No-op for a single rank."""
+    if world <= 1 or not hasattr(os, "sched_setaffinity"):
+        return
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+        node_cores = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(local_rank)).busId
+            bus = bus.decode() if isinstance(bus, bytes) else bus
+            path = f"/sys/bus/pci/devices/{bus.lower()[-12:]}/local_cpulist"
+            if os.path.exists(path):
+                node_cores = []
+                for part in open(path).read().strip().split(","):
+                    lo, _, hi = part.partition("-")
+                    node_cores += list(range(int(lo), int(hi or lo) + 1))
+                node_cores = [c for c in node_cores if c in cores]
+        except Exception:
+            node_cores = None
+        pool = node_cores if node_cores and len(node_cores) >= world else cores
+        per = max(1, len(pool) // world)
+        mine = pool[local_rank * per:(local_rank + 1) * per] or pool
+        os.sched_setaffinity(0, mine)
+    except Exception as exc:                      # affinity is an optimisation, never a failure
+        print(f"bench.py: core binding skipped ({exc})", file=sys.stderr)
+
+
 class Pipeline:
     """Device-resident step loop: S state sets, one CUDA graph per set (pre + post + policy = 3 launches)."""
 
@@ -249,8 +288,9 @@ class Pipeline:
         self.rollout.write(k, task.obs_buf, self.mu, self.value, self.log_std, task.rew_buf, task.reset_buf, noise=None,
                            actions_out=self.actions, obs_stats=self.obs_stats)
 
-    def capture(self):
-        """One CUDA graph per state set (parity of the action ring alternates, STATE_SETS is even)."""
+    def capture(self, after_step=None):
+        """One CUDA graph per state set (parity of the action ring alternates, STATE_SETS is even).  ``after_step(i)``: called after
+        each eager warm-up step (tests/test_bench_shapes_gpu.py tracks the oracle through them)."""
         assert STATE_SETS % 2 == 0
         if self.w["policy"] != "mlp":
             return                                      # the GAE cadence needs a host-side counter: stay eager
@@ -259,6 +299,8 @@ class Pipeline:
         with torch.cuda.stream(side):
             for i in range(STATE_SETS):
                 self.step_eager(i)                      # warm everything on the capture stream
+                if after_step is not None:
+                    after_step(i)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.graphs = []
@@ -296,9 +338,24 @@ def cuda_arm(args):
         raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback (use --impl reference for the CPU baseline)")
     device = torch.device(f"cuda:{local_rank}")
     torch.cuda.set_device(device)
+    bind_host_cores(local_rank, world)
     pipe = Pipeline(args.workload, device, rank)
     n = pipe.n
-    reducer = lmdist.FusedHorizonReducer(pipe.policy.parameters(), n)
+    # rollout-boundary collective: episode statistics + the gradient arena in ONE message.  Default: our one-shot NVLink
+    # all-reduce (lm_comm: peer stores + flag + local sum); --collective nccl: the same message through torch.distributed.
+    peer = None
+    if world > 1 and args.collective == "peer":
+        try:
+            peer = lmdist.PeerComm(max_floats=65536, device=device)
+        except Exception as exc:
+            print(f"bench.py: peer-memory communicator unavailable ({exc}); using NCCL for the collective", file=sys.stderr)
+            peer = None
+    flags = torch.tensor([1.0 if (peer is not None or world == 1) else 0.0], device=device)
+    if world > 1:
+        tdist.all_reduce(flags, op=tdist.ReduceOp.MIN)             # all ranks or none
+        if float(flags.item()) == 0.0:
+            peer = None
+    reducer = lmdist.FusedHorizonReducer(pipe.policy.parameters(), n, comm=peer)
     horizon = HORIZON_MLP if pipe.w["policy"] == "mlp" else HORIZON
     comm_stream = torch.cuda.Stream(device=device)
 
@@ -308,25 +365,26 @@ def cuda_arm(args):
         reducer.reduce(pipe.task._extras_buf, pipe.task._counters)
 
     def comm():
-        """Episode-stat reduction + PPO gradient all-reduce, once per rollout horizon, on a side stream (one CUDA-graph
-        replay: the host must not fall behind a 45 us step)."""
+        """Episode-stat reduction + gradient arena, once per rollout horizon (one CUDA-graph replay: the host must not fall behind a
+        45 us step)."""
         if world == 1 or os.environ.get("LM_BENCH_NO_COMM"):
-            return
+            return 0
         if args.comm_stream == "main":
-            # at the rollout boundary, on the launching stream (where the PPO update that consumes the gradients would sit).
+            # at the rollout boundary, on the launching stream (where the PPO update that consumes the gradients sits).
             # On a side stream the collective's CTAs pin SMs while they wait for the peer rank, and the persistent MLP kernel
             # (one 219 KB CTA per SM) then stalls on exactly those SMs: measured 216 us per event vs ~30 us in-line.
             if comm_graph is not None:
                 comm_graph.replay()
             else:
                 comm_body()
-            return
+            return 1
         comm_stream.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(comm_stream):
             if comm_graph is not None:
                 comm_graph.replay()
             else:
                 comm_body()
+        return 1
 
     if world > 1:
         comm(); comm()                       # eager first: NCCL connects lazily at the first collective of each size
@@ -336,7 +394,7 @@ def cuda_arm(args):
             with torch.cuda.graph(g, stream=comm_stream if args.comm_stream == "side" else None):
                 comm_body()
             comm_graph = g
-        except Exception as exc:             # capture of NCCL collectives unsupported in this build: stay eager
+        except Exception as exc:             # capture of the collective unsupported in this build: stay eager
             print(f"bench.py: comm graph capture failed ({exc}); using eager collectives", file=sys.stderr)
             comm_graph = None
         torch.cuda.synchronize()
@@ -349,6 +407,24 @@ def cuda_arm(args):
         comm()
     torch.cuda.current_stream().wait_stream(comm_stream)
     torch.cuda.synchronize()
+
+    def run_horizons(reps):
+        c = 0
+        for r in range(reps):
+            for k in range(horizon):
+                pipe.step(r * horizon + k)
+            c += comm()
+        return c
+
+    # calibrate: whole horizons, >= the requested step count, >= MIN_TIMED_S of device time (every rank takes the same count)
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record(); run_horizons(1); c1.record()
+    torch.cuda.synchronize()
+    per_h = torch.tensor([c0.elapsed_time(c1) * 1e-3], device=device, dtype=torch.float64)
+    if world > 1:
+        tdist.all_reduce(per_h, op=tdist.ReduceOp.MIN)
+    reps = max((args.steps + horizon - 1) // horizon, int(MIN_TIMED_S / max(float(per_h.item()), 1e-6)) + 1)
+    steps_timed = reps * horizon
     if world > 1:
         tdist.barrier()
     sampler = ClockSampler(local_rank)
@@ -357,10 +433,7 @@ def cuda_arm(args):
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for t in range(args.steps):
-        pipe.step(t)
-        if (t + 1) % horizon == 0:
-            comm()
+    collectives = run_horizons(reps)
     torch.cuda.current_stream().wait_stream(comm_stream)
     e1.record()
     torch.cuda.synchronize()
@@ -373,7 +446,24 @@ def cuda_arm(args):
     if world > 1:
         tdist.all_reduce(t_ms, op=tdist.ReduceOp.MAX)
     ms_total = float(t_ms.item())
-    value = n * world * args.steps / (ms_total * 1e-3)
+    value = n * world * steps_timed / (ms_total * 1e-3)
+    if world > 1 and collectives == 0 and not os.environ.get("LM_BENCH_NO_COMM"):
+        raise SystemExit("bench.py: a multi-rank line needs at least one collective inside the timed region")
+    comm_us = None
+    if world > 1 and collectives > 0:
+        # the collective alone (same graph, back to back on the launching stream), max over ranks: what a horizon boundary costs
+        torch.cuda.synchronize(); tdist.barrier()
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record()
+        for _ in range(50):
+            comm()
+        torch.cuda.current_stream().wait_stream(comm_stream)
+        k1.record(); torch.cuda.synchronize()
+        t_c = torch.tensor([k0.elapsed_time(k1) / 50.0 * 1e3], device=device, dtype=torch.float64)
+        tdist.all_reduce(t_c, op=tdist.ReduceOp.MAX)
+        comm_us = float(t_c.item())
+    if peer is not None and peer.status() != 0:
+        raise SystemExit(f"bench.py: peer communicator reported a time-out (status {peer.status()})")
 
     # ---- per-kernel timing (rank 0; eager launches bracketed by events, same state rotation)
     line_extra = {}
@@ -428,7 +518,7 @@ def cuda_arm(args):
         b_post, b_task = B_POST + b_states, B_TASK + b_states
         ach = n * b_post / (ms_post * 1e-3) / 1e9
         ach_task = n * b_task / ((ms_post + ms_pre) * 1e-3) / 1e9
-        line_extra["roofline"] = {"kernel": "k_post (post_physics_step)", "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s",
+        line_extra["roofline_post"] = {"kernel": "k_post (post_physics_step)", "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s",
                                   "frac": ach / hbm, "traffic": measured_traffic("k_post_lean") if pipe.w["task"].startswith("Joint") else None,
                                   "traffic_unit": "bytes per launch (ncu dram read + write, 65,536 envs; stores mostly still in L2 at kernel end)",
                                   "algorithmic_bytes": n * b_post, "peak_source": src, "bytes_per_env": b_post, "ms": ms_post}
@@ -449,6 +539,14 @@ def cuda_arm(args):
                                              "unit": "TFLOP/s" if tc else "TFLOP/s (naive FLOP count)", "ms": ms_pol,
                                              "hbm_gbs": n * 308 / (ms_pol * 1e-3) / 1e9}
         line_extra["kernel_ms"] = {"pre": ms_pre, "post": ms_post, "policy": ms_pol}
+        # `roofline` = the dominant kernel of the step (largest share of the device time), the others keep their own blocks
+        if ms_pol >= ms_post and line_extra["roofline_policy"].get("frac") is not None:
+            line_extra["roofline"] = dict(line_extra["roofline_policy"], traffic=measured_traffic("k_mlp_forward") if pipe.w["policy"] == "mlp" else measured_traffic("k_gnn_forward_tc"),
+                                          algorithmic_flops=n * (MLP_FLOPS if pipe.w["policy"] == "mlp" else 24 * 2 * (64 * 32 + 32 * 32) * 3),
+                                          algorithmic_bytes=n * 308, peak_source=src,
+                                          share_of_step=ms_pol / (ms_pre + ms_post + ms_pol))
+        else:
+            line_extra["roofline"] = dict(line_extra["roofline_post"], share_of_step=ms_post / (ms_pre + ms_post + ms_pol))
         if pipe.w["policy"] == "gnn":
             ms_ro = graph_time(lambda i: pipe.rollout_step(i % HORIZON))
             B_RO = 368 + 368 + 48        # obs/mu/value/rew/done in, obses/actions/mus/values/rewards/dones/neglogp out, + actions_out
@@ -492,6 +590,11 @@ def cuda_arm(args):
         full = e2e_arm(pipe, args, world, device, rank, readback_obs=True, shards=4)     # 21 MB back per step: pipelining over shards pays here
         e2e["with_obs_readback"] = {k: full[k] for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step", "ms_per_step", "api")}
 
+    # ---- train block: the same loop with the rollout writer, GAE and the PPO update (real gradients in the all-reduce)
+    train = None
+    if pipe.w["policy"] == "mlp" and args.workload == "cotrain64k" and not args.no_train:
+        train = train_arm(pipe, args, world, device, rank, peer)
+
     # ---- CPU baseline (rank 0, N=1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -504,13 +607,19 @@ def cuda_arm(args):
     if rank == 0:
         clocks = sampler.summary()
         line = {"metric": "env-steps/s (obs+reward+PD+reset+policy)", "value": value, "unit": "env-steps/s", "n_gpus": world,
-                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+                "steps": steps_timed, "steps_requested": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / steps_timed,
+                "timed_region_s": ms_total * 1e-3, "collectives_in_timed_region": collectives, "collective_us": comm_us,
+                "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32 task math, bf16 x bf16 -> f32 policy GEMMs",
                 "data": "synthetic",
                 "config": {"workload": pipe.w["desc"], "envs_per_gpu": n, "global_envs": n * world, "parallelism": f"env-shard x{world}",
                            "l2": f"{STATE_SETS} rotating synthetic state sets (> L2) - inputs larger than L2",
-                           "cuda_graphs": pipe.graphs is not None, "comm": f"one fused stat + gradient all-reduce (58,651 fp32) every {horizon} steps ({args.comm_stream} stream, CUDA graph)" if world > 1 else "none"},
-                "gpu_launches": pipe.launches_per_step * args.steps + (args.steps // HORIZON if pipe.w["policy"] == "gnn" else 0), "clocks": clocks, "e2e": e2e, "cpu_baseline": cpu}
+                           "cuda_graphs": pipe.graphs is not None, "comm": (f"one stat + gradient-arena all-reduce (58,651 fp32) every {horizon} steps, "
+                                    + ("one-shot NVLink peer-memory kernel (lm_comm_allreduce)" if peer is not None else "NCCL all_reduce")
+                                    + f", {args.comm_stream} stream, CUDA graph") if world > 1 else "none",
+                           "timed": f"{reps} rollout horizons of {horizon} steps"},
+                "gpu_launches": pipe.launches_per_step * steps_timed + (steps_timed // HORIZON if pipe.w["policy"] == "gnn" else 0)
+                                + (collectives if peer is not None else 0), "clocks": clocks, "e2e": e2e, "cpu_baseline": cpu, "train": train}
         line.update(line_extra)
         emit(line)
     if world > 1:
@@ -521,6 +630,78 @@ def cuda_arm(args):
         tdist.barrier()
         sys.stdout.flush(); sys.stderr.flush()
         os._exit(0)
+
+
+def train_arm(pipe, args, world, device, rank, peer):
+    """The same env loop with real work at the rollout boundary (cfg/train/JointLocomanipulationVerticalPPO.yaml: horizon 48, 5
+    mini-epochs, minibatch = batch / 8, normalize_input / normalize_value, adaptive schedule at kl_threshold 0.008):
+    per step pre_physics_step -> state swap -> post_physics_step -> MLP forward on the normalised observations -> rollout write
+    (in-kernel action sampling); per rollout finish -> GAE -> PpoUpdater.update, whose per-minibatch gradient all-reduce is fused
+    into the weight-gradient reduction over NVLink peer memory (N > 1).  Device time, max over ranks."""
+    import torch.distributed as tdist
+    from locomanipulationrl_b200.ppo import PpoUpdater
+    from locomanipulationrl_b200.rollout import RolloutBuffer, RunningMeanStd
+    T, n, task, policy = HORIZON_MLP, pipe.n, pipe.task, pipe.policy
+    buf = RolloutBuffer(T, n, device=device, reward_scale=1.0)
+    obs_rms = RunningMeanStd(64, device=device)
+    nmb = 8
+    up = PpoUpdater(policy, buf, minibatch_size=T * n // nmb, mini_epochs=5, normalize_value=True, obs_rms=obs_rms, comm=peer)
+    log_std = policy.log_std_parameter.detach()
+    actions = torch.zeros(n, 12, device=device)
+    mu, value = torch.zeros(n, 12, device=device), torch.zeros(n, 1, device=device)
+    state = {"i": 0}
+
+    def forward():
+        mean, inv = obs_rms.export()
+        policy(task.obs_buf, norm_mean=mean, norm_inv_std=inv, out=(mu, value))
+
+    def iteration(seed):
+        for t in range(T):
+            forward()
+            buf.write(t, task.obs_buf, mu, value, log_std, task.rew_buf, task.reset_buf, actions_out=actions, sample_seed=seed,
+                      value_denorm=up.value_denorm)
+            i = state["i"] = (state["i"] + 1) % STATE_SETS
+            task.pre_physics_step(actions, pipe.uniforms[i])
+            task.set_up_scene(pipe.scenes[i])
+            task.post_physics_step()
+        forward()                                         # value of the observation after the last stored action: GAE's bootstrap
+        lv, ld = buf.finish(task.rew_buf, value, task.reset_buf, value_denorm=up.value_denorm)
+        return up.update(lv, ld)
+
+    iteration(1)
+    torch.cuda.synchronize()
+    if world > 1:
+        tdist.barrier()
+    iters = 2
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    ev[0].record()
+    for k in range(iters):
+        stats = iteration(2 + k)
+    ev[1].record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([ev[0].elapsed_time(ev[1]) / iters], device=device, dtype=torch.float64)
+    # the update alone (same rollout again): what the boundary costs
+    u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if world > 1:
+        tdist.barrier()
+    u0.record()
+    up.update(buf.last_values, buf.last_dones)
+    u1.record(); torch.cuda.synchronize()
+    ms_up = torch.tensor([u0.elapsed_time(u1)], device=device, dtype=torch.float64)
+    if world > 1:
+        tdist.all_reduce(ms, op=tdist.ReduceOp.MAX)
+        tdist.all_reduce(ms_up, op=tdist.ReduceOp.MAX)
+    st = stats.detach().float().cpu() / world
+    if peer is not None and peer.status() != 0:
+        raise SystemExit(f"bench.py: peer communicator reported a time-out (status {peer.status()})")
+    return {"metric": "env-steps/s incl. rollout write, GAE and the PPO update", "value": n * world * T / (float(ms.item()) * 1e-3), "unit": "env-steps/s",
+            "ms_per_iteration": float(ms.item()), "ms_update": float(ms_up.item()), "ms_rollout": float(ms.item()) - float(ms_up.item()),
+            "horizon": T, "mini_epochs": 5, "minibatches": nmb, "minibatch_size": T * n // nmb, "samples_per_update": T * n * 5,
+            "collectives_per_iteration": (5 * nmb if world > 1 else 0),
+            "allreduce": ("fused into k_wgrad_reduce_allreduce: 58,645 fp32 per minibatch pushed over NVLink peer memory" if peer is not None
+                          else ("torch.distributed all_reduce of the flat arena per minibatch" if world > 1 else "none")),
+            "loss_stats_last_minibatch": {k: float(st[i]) for i, k in enumerate(("a_loss", "c_loss", "b_loss", "entropy", "kl", "loss", "clip_frac"))},
+            "lr_after": up.opt.lr}
 
 
 def large_roofline(device, graph_time, hbm, n=524288):
@@ -624,6 +805,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--comm-stream", default="main", choices=["main", "side"],
                     help="where the per-horizon stat + gradient all-reduce runs (N > 1)")
+    ap.add_argument("--collective", default="peer", choices=["peer", "nccl"],
+                    help="rollout-boundary all-reduce: our one-shot NVLink peer-memory kernel (default) or torch.distributed/NCCL")
+    ap.add_argument("--no-train", action="store_true", help="skip the train block (rollout + GAE + PPO update)")
     ap.add_argument("--e2e-shards", type=int, default=1,
                     help="env shards (streams) the host-buffer step is pipelined over (measured: 1 is fastest when only 4 MB return per step - "
                          "fewer, larger PCIe copies; 4 when the observations return too)")

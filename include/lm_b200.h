@@ -334,11 +334,17 @@ typedef struct LmRolloutStep {   /* one env step; device pointers */
   const float* value;     /* [N]                                      */
   const float* log_std;   /* [12]   state-independent log sigma       */
   const float* noise;     /* [N,12] standard-normal draws of the caller's generator; NULL: see sample_in_kernel */
-  const float* rew;       /* [N]                                      */
+  const float* rew;       /* [N]    the reward that arrived WITH this observation = the reward of the action in slot t-1 */
   const int64_t* dones;   /* [N]    reset_buf                         */
   /* noise == NULL: sample_in_kernel != 0 draws N(0,1) in the kernel (Philox4x32-10 keyed by noise_seed, stream position noise_step,
    * element index: no draw tensor in HBM, reproducible for a given seed / step); 0: action = mu (evaluation) */
   uint64_t noise_seed; uint64_t noise_step; int32_t sample_in_kernel; int32_t pad_;
+  /* rl_games value_bootstrap (cfg/train/*PPO.yaml:48): rewards[t-1] += gamma * values[t-1] * time_outs; NULL: off (the reference tasks
+   * put no 'time_outs' into their extras, so the switch is inert there) */
+  const int64_t* time_outs; float gamma; int32_t pad2_;
+  /* normalize_value (cfg/train/*PPO.yaml:47): {mean, std} from lm_rms_export_denorm; values are stored as std * clamp(v, +-5) + mean.
+   * NULL: stored as they come */
+  const float* value_denorm;
 } LmRolloutStep;
 typedef struct LmRolloutBuffers {
   float* obses;    /* [T,N,64] */
@@ -354,20 +360,35 @@ typedef struct LmRolloutBuffers {
 typedef struct LmRollout LmRollout;
 LmRollout* lm_rollout_create(int device);
 void lm_rollout_destroy(LmRollout* r);
-/* Samples a = noise * sigma + mu (torch.normal's op order), writes slot t of every buffer, optionally copies the actions
- * to `actions_out` [N,12] (the next pre_physics_step input) and, when obs_stats != NULL, folds this step's observation
- * batch into the running mean / variance (batch mean, unbiased batch variance, parallel-variance combine).  One launch. */
+/* Samples a = noise * sigma + mu (torch.normal's op order), writes slot t of obses / actions / mus / values / dones / neglogp and
+ * the shaped reward into slot t-1 (rl_games play_steps stores rewards[n] AFTER env_step(actions[n]): the reward that comes with
+ * observation t belongs to the action of slot t-1; nothing at t = 0), optionally copies the actions to `actions_out` [N,12] (the
+ * next pre_physics_step input) and, when obs_stats != NULL, folds this step's observation batch into the running mean /
+ * variance (batch mean, unbiased batch variance, parallel-variance combine).  One launch.
+ * lm_rollout_finish closes the rollout with the step that follows slot T-1: reward into slot T-1, last_values / last_dones [N]
+ * (the bootstrap inputs of lm_gae). */
 int lm_rollout_write(LmRollout* r, const LmRolloutStep* step, const LmRolloutBuffers* buf, int32_t t, float* actions_out,
                      const LmRunningStats* obs_stats, void* stream);
+int lm_rollout_finish(LmRollout* r, const LmRolloutStep* step, const LmRolloutBuffers* buf, float* last_values, float* last_dones,
+                      void* stream);
 /* Folds a batch x [n,dim] into running statistics (value / return normalisation, or observations outside a rollout). */
 int lm_rms_update(LmRollout* r, const float* x, int64_t n, const LmRunningStats* stats, void* stream);
 /* fp32 vectors for lm_mlp_forward(norm_mean, norm_inv_std): mean and the variant's 1/std form. */
 int lm_rms_export(const LmRunningStats* stats, float* mean_f32, float* inv_std_f32, void* stream);
+/* {mean, std} of a scalar normaliser for LmRolloutStep.value_denorm. */
+int lm_rms_export_denorm(const LmRunningStats* stats, float* mean_std_f32, void* stream);
+/* y = clamp((x - mean[0]) * inv_std[0], +-clip) over n floats (rl_games prepare_dataset: values / returns through value_mean_std;
+ * clip <= 0: no clamp).  In place allowed. */
+int lm_normalize_clamp(const float* x, float* y, int64_t n, const float* mean, const float* inv_std, float clip, void* stream);
+/* Advantage normalisation (a - a.mean()) / (a.std() + eps) in two steps so that a sharded job can sum the moments over ranks in
+ * between: moments[3] = {sum, sum of squares, count} as doubles. */
+int lm_moments(LmRollout* r, const float* x, int64_t n, double* moments, void* stream);
+int lm_moment_normalize(const float* x, float* y, int64_t n, const double* moments, float eps, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * PPO update pieces: the loss head and the optimiser step.  Not in the reference repo: rl_games 1.6.0
  * a2c_continuous.calc_gradients / common_losses (cfg/train/JointLocomanipulationPPO.yaml:52-72: e_clip 0.2, clip_value,
- * critic_coef 2, entropy_coef 0, bounds_loss_coef 1e-4, grad_norm 1, truncate_grads) and torch.optim.Adam.
+ * critic_coef 2, entropy_coef 0, bounds_loss_coef 1e-3, grad_norm 1, truncate_grads) and torch.optim.Adam.
  *
  * lm_ppo_loss: one pass over a minibatch of B samples.  From the fresh network outputs (mu, value, log_std) and the
  * stored rollout columns it produces dLoss/dmu [B,12], dLoss/dvalue [B], dLoss/dlog_std [12] and the scalars rl_games
@@ -388,7 +409,7 @@ typedef struct LmPpoBatch {
   int64_t batch;
   float e_clip; float critic_coef; float entropy_coef; float bounds_loss_coef;
   int32_t clip_value;       /* rl_games clip_value                           */
-  int32_t pad_;
+  int32_t update_old;       /* != 0: after use, old_mu <- mu and old_log_std <- log_std in place (rl_games dataset.update_mu_sigma) */
 } LmPpoBatch;
 int lm_ppo_loss(LmRollout* workspace, const LmPpoBatch* batch, float* grad_mu, float* grad_value, float* grad_log_std,
                 float* stats, void* stream);
@@ -415,12 +436,52 @@ int lm_mlp_wgrad(const void* dz1, const void* dz2, const void* dz3, const void* 
                  const void* a3, int64_t rows, float* workspace, int32_t workspace_ctas, float* g_w1, float* g_b1, float* g_w2,
                  float* g_b2, float* g_w3, float* g_b3, float* g_w_mu, float* g_b_mu, float* g_w_value, float* g_b_value, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * One-shot all-reduce over NVLink peer memory (the PPO gradient all-reduce and the episode-stat reduction — the
+ * only collectives of the path; the reference only forwards rl_games' multi_gpu flag, cfg/config.yaml:29,
+ * scripts/rlgames_train.py:93-96).  One process per GPU.  lm_comm_create allocates this rank's receive memory;
+ * lm_comm_get_handle exports it as a cudaIpc handle (lm_comm_handle_bytes() bytes) which the caller exchanges between the
+ * ranks through its own channel (e.g. torch.distributed.all_gather); lm_comm_open maps the peers.  lm_comm_allreduce sums
+ * n <= max_floats floats in place over the ranks: every rank pushes its values into every peer's slot, raises a flag and
+ * sums the slots in rank order — the result is bit-identical on every rank.  Every rank must call the collectives of one
+ * communicator in the same order.  CUDA-graph capturable (the epoch counter lives on the device).
+ * lm_mlp_wgrad_allreduce = lm_mlp_wgrad whose final reduction pushes each gradient element to the peers as its partial sum is
+ * formed (compute and collective in ONE kernel).  `arena` [arena_floats] is the flat buffer every gradient tensor is a view
+ * of; two extra ranges of it (log_std gradient, loss-head statistics) ride in the same message; on return the whole arena
+ * holds the sum over ranks.  lm_comm_status: 0, or 1 + r after a time-out waiting for rank r (synchronises the device). */
+typedef struct LmComm LmComm;
+int lm_comm_handle_bytes(void);
+LmComm* lm_comm_create(int device, int rank, int world, int64_t max_floats);
+int lm_comm_get_handle(LmComm* c, void* handle_out);
+int lm_comm_open(LmComm* c, const void* handles);
+void lm_comm_destroy(LmComm* c);
+int lm_comm_allreduce(LmComm* c, float* data, int64_t n, void* stream);
+int lm_comm_status(LmComm* c);
+int lm_mlp_wgrad_allreduce(LmComm* c, const void* dz1, const void* dz2, const void* dz3, const void* dh, const void* a0, const void* a1,
+                           const void* a2, const void* a3, int64_t rows, float* workspace, int32_t workspace_ctas, float* g_w1,
+                           float* g_b1, float* g_w2, float* g_b2, float* g_w3, float* g_b3, float* g_w_mu, float* g_b_mu,
+                           float* g_w_value, float* g_b_value, float* arena, int64_t arena_floats, int64_t extra_off0,
+                           int64_t extra_n0, int64_t extra_off1, int64_t extra_n1, void* stream);
+
 /* torch.nn.utils.clip_grad_norm_(max_norm) (skipped when max_norm <= 0) followed by one torch.optim.Adam step over a flat
  * fp32 parameter arena (the layout dist.FusedHorizonReducer keeps): grads are first multiplied by grad_scale
  * (1 / world size after the all-reduce sum).  `step` counts from 1.  One launch; n <= 2^24 parameters. */
 int lm_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
                  float beta2, float eps, float weight_decay, int32_t step, float max_grad_norm, float grad_scale,
                  float* grad_norm_out, void* stream);
+/* The same step with the learning rate kept on the device and rl_games' adaptive schedule (lr_schedule: adaptive, legacy = per
+ * minibatch; cfg/train/JointLocomanipulationPPO.yaml:57-58) applied inside the launch: the step runs with *lr, then
+ *   kl = *kl * kl_scale;  kl > 2 thr: lr = max(lr / 1.5, lr_min);  kl < thr / 2: lr = min(lr * 1.5, lr_max)
+ * for the next one.  `kl` usually points into the all-reduced gradient arena's tail (sum of the ranks' minibatch KL, kl_scale =
+ * 1 / world size: every rank takes the same decision).  kl == NULL: *lr is used and left alone.  sched == NULL: `lr` argument. */
+typedef struct LmAdamSchedule {
+  float* lr;            /* [1] device */
+  const float* kl;      /* [1] device, may be NULL */
+  float kl_scale; float kl_threshold; float lr_min; float lr_max;
+} LmAdamSchedule;
+int lm_adam_step_scheduled(float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, const LmAdamSchedule* sched,
+                           float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step, float max_grad_norm,
+                           float grad_scale, float* grad_norm_out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Observation / action noise: utils/domain_randomization/randomize.py:212-305, applied inside

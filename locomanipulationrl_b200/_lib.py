@@ -73,7 +73,8 @@ class LmRunningStats(C.Structure):
 
 class LmRolloutStep(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("obs", "mu", "value", "log_std", "noise", "rew", "dones")] + \
-               [("noise_seed", C.c_uint64), ("noise_step", C.c_uint64), ("sample_in_kernel", _i32), ("pad_", _i32)]
+               [("noise_seed", C.c_uint64), ("noise_step", C.c_uint64), ("sample_in_kernel", _i32), ("pad_", _i32),
+                ("time_outs", C.c_void_p), ("gamma", _f), ("pad2_", _i32), ("value_denorm", C.c_void_p)]
 
 
 class LmRolloutBuffers(C.Structure):
@@ -103,7 +104,11 @@ class LmPpoBatch(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("mu", "value", "log_std", "actions", "old_neglogp", "advantages", "old_values", "returns",
                                           "old_mu", "old_log_std")] + \
                [("batch", _i64), ("e_clip", _f), ("critic_coef", _f), ("entropy_coef", _f), ("bounds_loss_coef", _f),
-                ("clip_value", _i32), ("pad_", _i32)]
+                ("clip_value", _i32), ("update_old", _i32)]
+
+
+class LmAdamSchedule(C.Structure):
+    _fields_ = [("lr", C.c_void_p), ("kl", C.c_void_p), ("kl_scale", _f), ("kl_threshold", _f), ("lr_min", _f), ("lr_max", _f)]
 
 
 # name -> (restype, argtypes); every symbol include/lm_b200.h declares
@@ -142,7 +147,12 @@ SYMBOLS = {
     "lm_rollout_create": (_vp, [C.c_int]),
     "lm_rollout_destroy": (None, [_vp]),
     "lm_rollout_write": (C.c_int, [_vp, C.POINTER(LmRolloutStep), C.POINTER(LmRolloutBuffers), _i32, _vp, C.POINTER(LmRunningStats), _vp]),
+    "lm_rollout_finish": (C.c_int, [_vp, C.POINTER(LmRolloutStep), C.POINTER(LmRolloutBuffers), _vp, _vp, _vp]),
     "lm_rms_update": (C.c_int, [_vp, _vp, _i64, C.POINTER(LmRunningStats), _vp]),
+    "lm_rms_export_denorm": (C.c_int, [C.POINTER(LmRunningStats), _vp, _vp]),
+    "lm_normalize_clamp": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _f, _vp]),
+    "lm_moments": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
+    "lm_moment_normalize": (C.c_int, [_vp, _vp, _i64, _vp, _f, _vp]),
     "lm_rms_export": (C.c_int, [C.POINTER(LmRunningStats), _vp, _vp, _vp]),
     "lm_cc_pre": (C.c_int, [C.POINTER(LmCustomController), _vp]),
     "lm_cc_post": (C.c_int, [_vp, C.POINTER(LmCustomController), _vp]),
@@ -158,6 +168,15 @@ SYMBOLS = {
     "lm_mlp_wgrad_workspace_floats": (_i32, []),
     "lm_mlp_wgrad": (C.c_int, [_vp] * 8 + [_i64, _vp, _i32] + [_vp] * 10 + [_vp]),
     "lm_adam_step": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _f, _i32, _f, _f, _vp, _vp]),
+    "lm_adam_step_scheduled": (C.c_int, [_vp, _vp, _vp, _vp, _i64, C.POINTER(LmAdamSchedule), _f, _f, _f, _f, _f, _i32, _f, _f, _vp, _vp]),
+    "lm_comm_handle_bytes": (C.c_int, []),
+    "lm_comm_create": (_vp, [C.c_int, C.c_int, C.c_int, _i64]),
+    "lm_comm_get_handle": (C.c_int, [_vp, _vp]),
+    "lm_comm_open": (C.c_int, [_vp, _vp]),
+    "lm_comm_destroy": (None, [_vp]),
+    "lm_comm_allreduce": (C.c_int, [_vp, _vp, _i64, _vp]),
+    "lm_comm_status": (C.c_int, [_vp]),
+    "lm_mlp_wgrad_allreduce": (C.c_int, [_vp] + [_vp] * 8 + [_i64, _vp, _i32] + [_vp] * 10 + [_vp, _i64, _i64, _i64, _i64, _i64, _vp]),
     "lm_gae": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _f, _f, _i32, _vp]),
     "lm_gae_env_major": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _f, _f, _i32, _vp]),
     "lm_task_step_host": (C.c_int, [_vp, C.POINTER(LmRobotViews), C.POINTER(LmRobotViews), _vp, C.POINTER(LmTaskBuffers), C.POINTER(LmHostStep), _vp]),
@@ -190,7 +209,7 @@ def load(path: Optional[str] = None) -> C.CDLL:
         fn.argtypes = args
     if lib.lm_abi_version() != 1:
         raise LmError("liblm_b200.so ABI version mismatch")
-    for which, struct in enumerate((LmTaskParams, LmRobotViews, LmTaskBuffers, LmHostStep, LmPdState, LmRunningStats, LmRolloutStep, LmRolloutBuffers, LmPpoBatch, LmNoiseSpec, LmNoiseState, LmCustomController)):
+    for which, struct in enumerate((LmTaskParams, LmRobotViews, LmTaskBuffers, LmHostStep, LmPdState, LmRunningStats, LmRolloutStep, LmRolloutBuffers, LmPpoBatch, LmNoiseSpec, LmNoiseState, LmCustomController, LmAdamSchedule)):
         if lib.lm_struct_size(which) != C.sizeof(struct):
             raise LmError(f"struct layout mismatch for {struct.__name__}: C {lib.lm_struct_size(which)} vs ctypes {C.sizeof(struct)}")
     _lib = lib

@@ -26,6 +26,9 @@ namespace lm {
 namespace mlp {
 using namespace tc;
 
+#ifndef LM_MLP_FMA_PAIRS
+#define LM_MLP_FMA_PAIRS 0
+#endif
 constexpr int TM = 128;                 // rows (envs) per tile == UMMA M
 constexpr int E_WARPS = 16;               // epilogue warps: 4 TMEM lane groups x 4 column quarters
 constexpr int E_THREADS = E_WARPS * 32;
@@ -74,8 +77,9 @@ __device__ __forceinline__ void emit16(const uint32_t* acc, const float* __restr
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const float4 b = *reinterpret_cast<const float4*>(bias + c0 + 4 * k);
-    w[2 * k] = elu_pair(acc[4 * k], acc[4 * k + 1], b.x, b.y);
-    w[2 * k + 1] = elu_pair(acc[4 * k + 2], acc[4 * k + 3], b.z, b.w);
+    // LM_MLP_FMA_PAIRS of every 4 ELU pairs take their exponential on the FMA pipe instead of MUFU (lm_tc.cuh)
+    w[2 * k] = elu_pair_mix<LM_MLP_FMA_PAIRS>((2 * k) & 3, acc[4 * k], acc[4 * k + 1], b.x, b.y);
+    w[2 * k + 1] = elu_pair_mix<LM_MLP_FMA_PAIRS>((2 * k + 1) & 3, acc[4 * k + 2], acc[4 * k + 3], b.z, b.w);
   }
   *reinterpret_cast<uint4*>(dst + elem_offset(TM, row, c0)) = make_uint4(w[0], w[1], w[2], w[3]);
   *reinterpret_cast<uint4*>(dst + elem_offset(TM, row, c0 + 8)) = make_uint4(w[4], w[5], w[6], w[7]);
@@ -371,23 +375,35 @@ __global__ void __launch_bounds__(THREADS, 1) k_mlp_forward(const Args a) {
   if (warp == E_WARPS) tmem_dealloc(tmem, TMEM_COLS);
 }
 
-// fp32 nn.Linear [out,in] -> bf16 canonical operand; rows >= out are zero
-__global__ void k_pack_operand(const float* __restrict__ w, uint8_t* __restrict__ dst, int rows_total, int rows_valid, int k) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= rows_total * k) return;
+// fp32 nn.Linear parameters -> the resident blob (bf16 canonical operands + fp32 biases) in ONE launch: the PPO update re-packs
+// after every optimiser step (the fp32 masters are written by lm_adam_step, the kernels read this blob).
+struct PackArgs {
+  const float *w1, *b1, *w2, *b2, *w3, *b3, *w_mu, *b_mu, *w_value, *b_value;
+  uint8_t* blob;
+};
+constexpr int PK_W1 = D1 * D0, PK_W2 = PK_W1 + D2 * D1, PK_W3 = PK_W2 + D3 * D2, PK_WH = PK_W3 + DH * D3, PK_ALL = PK_WH + D1 + D2 + D3 + DH;
+__device__ __forceinline__ void pack_elem(const float* __restrict__ w, uint8_t* dst, int rows_total, int k, int i) {
   const int row = i / k, col = i - row * k;
-  const float v = row < rows_valid ? w[(size_t)row * k + col] : 0.0f;
-  *reinterpret_cast<__nv_bfloat16*>(dst + elem_offset(rows_total, row, col)) = __float2bfloat16_rn(v);
+  *reinterpret_cast<__nv_bfloat16*>(dst + elem_offset(rows_total, row, col)) = __float2bfloat16_rn(w[i]);
 }
-__global__ void k_pack_bias(const float* __restrict__ b1, const float* __restrict__ b2, const float* __restrict__ b3,
-                            const float* __restrict__ b_mu, const float* __restrict__ b_value, float* __restrict__ dst) {
+__global__ void k_pack_all(const PackArgs a) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < D1) dst[i] = b1[i];
-  else if (i < D1 + D2) dst[i] = b2[i - D1];
-  else if (i < D1 + D2 + D3) dst[i] = b3[i - D1 - D2];
-  else if (i < D1 + D2 + D3 + 12) dst[i] = b_mu[i - D1 - D2 - D3];
-  else if (i == D1 + D2 + D3 + 12) dst[i] = b_value[0];
-  else if (i < D1 + D2 + D3 + DH) dst[i] = 0.0f;
+  if (i < PK_W1) pack_elem(a.w1, a.blob + W1_OFF, D1, D0, i);
+  else if (i < PK_W2) pack_elem(a.w2, a.blob + W2_OFF, D2, D1, i - PK_W1);
+  else if (i < PK_W3) pack_elem(a.w3, a.blob + W3_OFF, D3, D2, i - PK_W2);
+  else if (i < PK_WH) {                       // head rows 0..11 = mean weights, row 12 = value weights, 13..15 zero
+    const int j = i - PK_W3, row = j / D3, col = j - row * D3;
+    const float v = row < 12 ? a.w_mu[j] : (row == 12 ? a.w_value[col] : 0.0f);
+    *reinterpret_cast<__nv_bfloat16*>(a.blob + WH_OFF + elem_offset(DH, row, col)) = __float2bfloat16_rn(v);
+  } else if (i < PK_ALL) {
+    const int j = i - PK_WH;
+    float* dst = reinterpret_cast<float*>(a.blob + BIAS_OFF);
+    if (j < D1) dst[j] = a.b1[j];
+    else if (j < D1 + D2) dst[j] = a.b2[j - D1];
+    else if (j < D1 + D2 + D3) dst[j] = a.b3[j - D1 - D2];
+    else if (j < D1 + D2 + D3 + 12) dst[j] = a.b_mu[j - D1 - D2 - D3];
+    else dst[j] = j == D1 + D2 + D3 + 12 ? a.b_value[0] : 0.0f;
+  }
 }
 
 }  // namespace mlp
@@ -432,14 +448,9 @@ int lm_mlp_pack(LmMlp* m, const float* w1, const float* b1, const float* w2, con
   if (!m || !w1 || !b1 || !w2 || !b2 || !w3 || !b3 || !w_mu || !b_mu || !w_value || !b_value)
     return lm_fail(LM_ERR_BAD_ARG, "lm_mlp_pack: NULL argument");
   cudaStream_t s = (cudaStream_t)stream;
-  cudaMemsetAsync(m->blob, 0, BLOB_BYTES, s);
-  k_pack_operand<<<(D1 * D0 + 255) / 256, 256, 0, s>>>(w1, m->blob + W1_OFF, D1, D1, D0);
-  k_pack_operand<<<(D2 * D1 + 255) / 256, 256, 0, s>>>(w2, m->blob + W2_OFF, D2, D2, D1);
-  k_pack_operand<<<(D3 * D2 + 255) / 256, 256, 0, s>>>(w3, m->blob + W3_OFF, D3, D3, D2);
-  // head rows 0..11 = mean weights, row 12 = value weights (two passes into the same operand)
-  k_pack_operand<<<(12 * D3 + 255) / 256, 256, 0, s>>>(w_mu, m->blob + WH_OFF, DH, 12, D3);
-  k_pack_operand<<<(1 * D3 + 255) / 256, 256, 0, s>>>(w_value, m->blob + WH_OFF + 12 * 16, DH, 1, D3);
-  k_pack_bias<<<2, 256, 0, s>>>(b1, b2, b3, b_mu, b_value, reinterpret_cast<float*>(m->blob + BIAS_OFF));
+  // the blob's padding bytes (zeroed at creation) are never read and every element is rewritten: no memset between packs
+  const PackArgs pa{w1, b1, w2, b2, w3, b3, w_mu, b_mu, w_value, b_value, m->blob};
+  k_pack_all<<<(PK_ALL + 255) / 256, 256, 0, s>>>(pa);
   const int rc = lm_mlp_train_pack(m, w2, w3, w_mu, w_value, stream);      // transposed operands of the backward kernel
   if (rc != LM_OK) return rc;
   m->packed = true;

@@ -15,6 +15,7 @@
 //   dWh^T [64 x 16] = A3^T dH    (rows 64.. ignored)       dbh = dH^T 1
 #include <cuda_bf16.h>
 
+#include "lm_comm.cuh"
 #include "lm_common.cuh"
 #include "lm_host.h"
 #include "lm_mlp.h"
@@ -235,15 +236,24 @@ __global__ void __launch_bounds__(B_THREADS, 1) k_mlp_backward(const BwdArgs a) 
   if (warp == B_WARPS) tmem_dealloc(tmem, 512);
 }
 
-// nn.Linear W [O][I] -> K-major B operand of dA = dZ W: element (n = i, k = o); rows of `w` at o >= o_valid are zero
-__global__ void k_pack_operand_t(const float* __restrict__ w, uint8_t* __restrict__ dst, int O, int o_valid, int I, int o_offset, int o_count) {
+// nn.Linear W [O][I] -> K-major B operand of dA = dZ W: element (n = i, k = o).  All three transposed operands in one launch
+// (the PPO update re-packs after every optimiser step).  Head: B[n = i (64)][k = o (16)]: o 0..11 = mean rows, 12 = value row,
+// 13..15 zero.
+constexpr int PT_WH = D3 * DH, PT_W3 = PT_WH + D3 * D2, PT_ALL = PT_W3 + D2 * D1;
+__global__ void k_pack_t_all(const float* __restrict__ w2, const float* __restrict__ w3, const float* __restrict__ w_mu,
+                             const float* __restrict__ w_value, uint8_t* __restrict__ blob_t) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= o_count * I) return;
-  const int o_src = idx / I, i = idx - o_src * I;
-  const int o = o_offset + o_src;
-  const float v = o_src < o_valid ? w[(size_t)o_src * I + i] : 0.0f;
-  *reinterpret_cast<__nv_bfloat16*>(dst + elem_offset(I, i, o)) = __float2bfloat16_rn(v);
-  (void)O;
+  if (idx < PT_WH) {
+    const int o = idx / D3, i = idx - o * D3;
+    const float v = o < 12 ? w_mu[idx] : (o == 12 ? w_value[i] : 0.0f);
+    *reinterpret_cast<__nv_bfloat16*>(blob_t + WHT_OFF + elem_offset(D3, i, o)) = __float2bfloat16_rn(v);
+  } else if (idx < PT_W3) {
+    const int j = idx - PT_WH, o = j / D2, i = j - o * D2;
+    *reinterpret_cast<__nv_bfloat16*>(blob_t + W3T_OFF + elem_offset(D2, i, o)) = __float2bfloat16_rn(w3[j]);
+  } else if (idx < PT_ALL) {
+    const int j = idx - PT_W3, o = j / D1, i = j - o * D1;
+    *reinterpret_cast<__nv_bfloat16*>(blob_t + W2T_OFF + elem_offset(D1, i, o)) = __float2bfloat16_rn(w2[j]);
+  }
 }
 
 // ---------------------------------------------------------------- weight gradients
@@ -427,24 +437,66 @@ struct ReduceArgs {
   const float* partials; int num_ctas;
   float *w1, *b1, *w2, *b2, *w3, *b3, *w_mu, *b_mu, *w_value, *b_value;
 };
+// flat partial index j -> where that gradient element lives (NULL: padding rows of the head operand)
+__device__ __forceinline__ float* wgrad_dst(const ReduceArgs& a, int j) {
+  if (j < P_B1) return a.w1 + (j - P_W1);
+  if (j < P_W2) return a.b1 + (j - P_B1);
+  if (j < P_B2) return a.w2 + (j - P_W2);
+  if (j < P_W3) return a.b2 + (j - P_B2);
+  if (j < P_B3) return a.w3 + (j - P_W3);
+  if (j < P_WH) return a.b3 + (j - P_B3);
+  if (j < P_BH) {
+    const int k = j - P_WH, o = k / D3;
+    return o < 12 ? a.w_mu + k : (o == 12 ? a.w_value + (k - 12 * D3) : nullptr);
+  }
+  const int o = j - P_BH;
+  return o < 12 ? a.b_mu + o : (o == 12 ? a.b_value : nullptr);
+}
+__device__ __forceinline__ float partial_sum(const ReduceArgs& a, int j) {
+  float s = 0.0f;
+  int c = 0;
+  for (; c + 8 <= a.num_ctas; c += 8) {                       // eight independent loads in flight; summed in CTA order
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = __ldcg(a.partials + (size_t)(c + u) * P_COUNT + j);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) s += v[u];
+  }
+  for (; c < a.num_ctas; ++c) s += __ldcg(a.partials + (size_t)c * P_COUNT + j);
+  return s;
+}
 __global__ void k_wgrad_reduce(const ReduceArgs a) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= P_COUNT) return;
-  float s = 0.0f;
-  for (int c = 0; c < a.num_ctas; ++c) s += a.partials[(size_t)c * P_COUNT + j];
-  if (j < P_B1) a.w1[j - P_W1] = s;
-  else if (j < P_W2) a.b1[j - P_B1] = s;
-  else if (j < P_B2) a.w2[j - P_W2] = s;
-  else if (j < P_W3) a.b2[j - P_B2] = s;
-  else if (j < P_B3) a.w3[j - P_W3] = s;
-  else if (j < P_WH) a.b3[j - P_B3] = s;
-  else if (j < P_BH) {
-    const int k = j - P_WH, o = k / D3;
-    if (o < 12) a.w_mu[k] = s; else if (o == 12) a.w_value[k - 12 * D3] = s;
-  } else {
-    const int o = j - P_BH;
-    if (o < 12) a.b_mu[o] = s; else if (o == 12) a.b_value[0] = s;
+  float* dst = wgrad_dst(a, j);
+  if (dst != nullptr) *dst = partial_sum(a, j);
+}
+
+// The same reduction fused with the data-parallel gradient all-reduce (SURVEY 8f-1 "fused with the grad allreduce"): every
+// gradient element is pushed into the peers' receive slots the moment its partial sum exists (NVLink stores, lm_comm.cuh), the
+// ranks exchange one flag, and each rank sums the slots in rank order straight into its gradient arena.  `arena` is the flat
+// fp32 buffer all gradient tensors are views of; the elements wgrad does not produce (log_std gradient, the loss head's
+// statistics in the tail: two ranges) travel in the same message.
+struct ReduceCommArgs {
+  ReduceArgs r;
+  comm::Ctx c;
+  float* arena; long long arena_n;
+  long long extra_off[2], extra_n[2];
+};
+__global__ void __launch_bounds__(1024, 1) k_wgrad_reduce_allreduce(const ReduceCommArgs a) {
+  const unsigned int epoch = comm::epoch_of(a.c);
+  const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gstride = gridDim.x * blockDim.x;
+  for (int j = gtid; j < P_COUNT; j += gstride) {
+    float* dst = wgrad_dst(a.r, j);
+    if (dst != nullptr) comm::push(a.c, epoch, (long long)(dst - a.arena), partial_sum(a.r, j));
   }
+#pragma unroll
+  for (int x = 0; x < 2; ++x)
+    for (long long i = gtid; i < a.extra_n[x]; i += gstride) comm::push(a.c, epoch, a.extra_off[x] + i, a.arena[a.extra_off[x] + i]);
+  if (comm::signal_and_wait(a.c, epoch)) {
+    for (long long f = gtid; f < a.arena_n; f += gstride) a.arena[f] = comm::sum(a.c, epoch, f);
+  }
+  comm::leave(a.c);
 }
 
 }  // namespace mlp_train
@@ -458,13 +510,9 @@ int lm_mlp_train_pack(LmMlp* m, const float* w2, const float* w3, const float* w
   cudaStream_t s = (cudaStream_t)stream;
   if (!m->blob_t) {
     if (cudaMalloc(&m->blob_t, WT_BYTES) != cudaSuccess) { m->blob_t = nullptr; return lm_fail((int)cudaErrorMemoryAllocation, "lm_mlp_pack: cudaMalloc failed"); }
+    cudaMemsetAsync(m->blob_t, 0, WT_BYTES, s);           // padding bytes once; every element is rewritten by each pack
   }
-  cudaMemsetAsync(m->blob_t, 0, WT_BYTES, s);
-  // head: B[n = i (64)][k = o (16)]: o 0..11 = mean rows, 12 = value row, 13..15 zero
-  k_pack_operand_t<<<(12 * D3 + 255) / 256, 256, 0, s>>>(w_mu, m->blob_t + WHT_OFF, 12, 12, D3, 0, 12);
-  k_pack_operand_t<<<(1 * D3 + 255) / 256, 256, 0, s>>>(w_value, m->blob_t + WHT_OFF, 1, 1, D3, 12, 1);
-  k_pack_operand_t<<<(D3 * D2 + 255) / 256, 256, 0, s>>>(w3, m->blob_t + W3T_OFF, D3, D3, D2, 0, D3);
-  k_pack_operand_t<<<(D2 * D1 + 255) / 256, 256, 0, s>>>(w2, m->blob_t + W2T_OFF, D2, D2, D1, 0, D2);
+  k_pack_t_all<<<(PT_ALL + 255) / 256, 256, 0, s>>>(w2, w3, w_mu, w_value, m->blob_t);
   return lm_check_launch("lm_mlp_pack (transposed operands)");
 }
 
@@ -510,6 +558,44 @@ int lm_mlp_wgrad(const void* dz1, const void* dz2, const void* dz3, const void* 
   ReduceArgs r{workspace, grid, g_w1, g_b1, g_w2, g_b2, g_w3, g_b3, g_w_mu, g_b_mu, g_w_value, g_b_value};
   k_wgrad_reduce<<<(P_COUNT + 255) / 256, 256, 0, (cudaStream_t)stream>>>(r);
   return lm_check_launch("lm_mlp_wgrad");
+}
+
+int lm_mlp_wgrad_allreduce(LmComm* comm_h, const void* dz1, const void* dz2, const void* dz3, const void* dh, const void* a0, const void* a1,
+                           const void* a2, const void* a3, int64_t rows, float* workspace, int32_t workspace_ctas, float* g_w1, float* g_b1,
+                           float* g_w2, float* g_b2, float* g_w3, float* g_b3, float* g_w_mu, float* g_b_mu, float* g_w_value, float* g_b_value,
+                           float* arena, int64_t arena_floats, int64_t extra_off0, int64_t extra_n0, int64_t extra_off1, int64_t extra_n1,
+                           void* stream) {
+  if (!comm_h || !arena || arena_floats <= 0) return lm_fail(LM_ERR_BAD_ARG, "lm_mlp_wgrad_allreduce: bad argument");
+  if (!dz1 || !dz2 || !dz3 || !dh || !a0 || !a1 || !a2 || !a3 || !workspace || rows <= 0 || workspace_ctas <= 0)
+    return lm_fail(LM_ERR_BAD_ARG, "lm_mlp_wgrad_allreduce: bad argument");
+  float* g[10] = {g_w1, g_b1, g_w2, g_b2, g_w3, g_b3, g_w_mu, g_b_mu, g_w_value, g_b_value};
+  const long long gn[10] = {D1 * D0, D1, D2 * D1, D2, D3 * D2, D3, 12 * D3, 12, D3, 1};
+  long long covered = (extra_n0 > 0 ? extra_n0 : 0) + (extra_n1 > 0 ? extra_n1 : 0);
+  for (int i = 0; i < 10; ++i) {
+    if (!g[i] || g[i] < arena || g[i] + gn[i] > arena + arena_floats)
+      return lm_fail(LM_ERR_BAD_ARG, "lm_mlp_wgrad_allreduce: gradient tensor %d is not a view of the arena", i);
+    covered += gn[i];
+  }
+  if (covered != arena_floats) return lm_fail(LM_ERR_BAD_ARG, "lm_mlp_wgrad_allreduce: arena of %lld floats, %lld accounted for", (long long)arena_floats, covered);
+  if (arena_floats > lm_comm_slot_floats(comm_h)) return lm_fail(LM_ERR_BAD_ARG, "lm_mlp_wgrad_allreduce: arena exceeds the communicator's slot size");
+  {
+    cudaError_t e = cudaFuncSetAttribute(k_mlp_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_BYTES);
+    if (e != cudaSuccess) return lm_fail((int)e, "lm_mlp_wgrad_allreduce: smem attribute: %s", cudaGetErrorString(e));
+  }
+  WgArgs a;
+  a.dz1 = (const uint8_t*)dz1; a.dz2 = (const uint8_t*)dz2; a.dz3 = (const uint8_t*)dz3; a.dh = (const uint8_t*)dh;
+  a.a0 = (const uint8_t*)a0; a.a1 = (const uint8_t*)a1; a.a2 = (const uint8_t*)a2; a.a3 = (const uint8_t*)a3;
+  a.partials = workspace; a.num_tiles = (int)((rows + TM - 1) / TM);
+  const int grid = a.num_tiles < workspace_ctas ? a.num_tiles : workspace_ctas;
+  k_mlp_wgrad<<<grid, WG_THREADS, WG_SMEM_BYTES, (cudaStream_t)stream>>>(a);
+  ReduceCommArgs rc;
+  rc.r = ReduceArgs{workspace, grid, g_w1, g_b1, g_w2, g_b2, g_w3, g_b3, g_w_mu, g_b_mu, g_w_value, g_b_value};
+  rc.c = *lm_comm_ctx(comm_h);
+  rc.arena = arena; rc.arena_n = arena_floats;
+  rc.extra_off[0] = extra_off0; rc.extra_n[0] = extra_n0 > 0 ? extra_n0 : 0; rc.extra_off[1] = extra_off1; rc.extra_n[1] = extra_n1 > 0 ? extra_n1 : 0;
+  const int want = (P_COUNT + 1023) / 1024, cap = lm_comm_max_ctas(comm_h);
+  k_wgrad_reduce_allreduce<<<want < cap ? want : cap, 1024, 0, (cudaStream_t)stream>>>(rc);
+  return lm_check_launch("lm_mlp_wgrad_allreduce");
 }
 
 int32_t lm_mlp_wgrad_workspace_floats(void) { return P_COUNT; }

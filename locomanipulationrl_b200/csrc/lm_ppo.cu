@@ -109,6 +109,11 @@ __global__ void __launch_bounds__(THREADS) k_ppo_loss(const Args a) {
         kl += logf(p1s / p0s + 1e-5f) + (p0s * p0s + dm * dm) / (2.0f * (p1s * p1s + 1e-5f)) - 0.5f;
       }
       red[3] += kl;
+      if (B.update_old) {   // rl_games dataset.update_mu_sigma: the next mini-epoch measures its KL against this pass's policy
+        float4* om = reinterpret_cast<float4*>(const_cast<float*>(B.old_mu) + i * 12);
+#pragma unroll
+        for (int q = 0; q < 3; ++q) om[q] = make_float4(mu[4 * q], mu[4 * q + 1], mu[4 * q + 2], mu[4 * q + 3]);
+      }
     }
   }
   // ---- CTA reduction (doubles), last CTA finishes
@@ -126,6 +131,8 @@ __global__ void __launch_bounds__(THREADS) k_ppo_loss(const Args a) {
   if (tid < 12) {
     // loss terms that reach log_std: actor (through neglogp) and -entropy_coef * entropy (d entropy / d logstd = 1)
     a.grad_log_std[tid] = (float)(sm[0][5 + tid] / (double)B.batch) - B.entropy_coef;
+    // every CTA read old_log_std before it took its ticket: safe to overwrite in the last one
+    if (B.update_old && B.old_log_std) const_cast<float*>(B.old_log_std)[tid] = B.log_std[tid];
   }
   if (tid == 0) {
     const double nb = (double)B.batch;
@@ -143,9 +150,9 @@ __global__ void __launch_bounds__(THREADS) k_ppo_loss(const Args a) {
 constexpr int ADAM_THREADS = 1024;
 __global__ void __launch_bounds__(ADAM_THREADS) k_adam_step(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                                                             int n, float lr, float beta1, float beta2, float eps, float wd, float bc1, float bc2_sqrt,
-                                                            float max_norm, float grad_scale, float* __restrict__ norm_out) {
+                                                            float max_norm, float grad_scale, float* __restrict__ norm_out, const LmAdamSchedule sched) {
   __shared__ double red[ADAM_THREADS / 32];
-  __shared__ float s_coef;
+  __shared__ float s_coef, s_lr;
   const int tid = threadIdx.x;
   double ss = 0.0;
   for (int i0 = tid; i0 < n; i0 += 8 * ADAM_THREADS) {          // 8 independent loads in flight per thread
@@ -166,10 +173,24 @@ __global__ void __launch_bounds__(ADAM_THREADS) k_adam_step(float* __restrict__ 
     if (norm_out) *norm_out = total_norm;
     // torch.nn.utils.clip_grad_norm_: clip_coef = max_norm / (total_norm + 1e-6), clamped to <= 1
     s_coef = max_norm > 0.0f ? fminf(max_norm / (total_norm + 1e-6f), 1.0f) : 1.0f;
+    // learning rate on the device (no host round trip per minibatch): this step runs with the stored rate, then rl_games'
+    // AdaptiveScheduler.update moves it for the next one from the (rank-averaged) KL of this minibatch
+    float cur = lr;
+    if (sched.lr) {
+      cur = *sched.lr;
+      if (sched.kl) {
+        const float kl = *sched.kl * sched.kl_scale;
+        float nxt = cur;
+        if (kl > 2.0f * sched.kl_threshold) nxt = fmaxf(cur / 1.5f, sched.lr_min);
+        if (kl < 0.5f * sched.kl_threshold) nxt = fminf(cur * 1.5f, sched.lr_max);
+        *sched.lr = nxt;
+      }
+    }
+    s_lr = cur;
   }
   __syncthreads();
   const float coef = s_coef * grad_scale;
-  const float step_size = lr / bc1;
+  const float step_size = s_lr / bc1;
   for (int i0 = tid; i0 < n; i0 += 4 * ADAM_THREADS) {          // 16 independent loads in flight per thread
     float gv[4], pv[4], mv[4], vv[4];
 #pragma unroll
@@ -222,15 +243,25 @@ int lm_ppo_loss(LmRollout* workspace, const LmPpoBatch* batch, float* grad_mu, f
   return lm_check_launch("lm_ppo_loss");
 }
 
-int lm_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1, float beta2, float eps,
-                 float weight_decay, int32_t step, float max_grad_norm, float grad_scale, float* grad_norm_out, void* stream) {
+int lm_adam_step_scheduled(float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, const LmAdamSchedule* sched, float lr,
+                           float beta1, float beta2, float eps, float weight_decay, int32_t step, float max_grad_norm, float grad_scale,
+                           float* grad_norm_out, void* stream) {
   if (!params || !grads || !exp_avg || !exp_avg_sq || n <= 0 || step < 1) return lm_fail(LM_ERR_BAD_ARG, "lm_adam_step: bad argument");
   if (n > (1 << 24)) return lm_fail(LM_ERR_UNSUPPORTED, "lm_adam_step: single-CTA kernel, n <= 2^24");
+  LmAdamSchedule sc;
+  if (sched) sc = *sched; else { sc.lr = nullptr; sc.kl = nullptr; sc.kl_scale = 1.0f; sc.kl_threshold = 0.0f; sc.lr_min = 0.0f; sc.lr_max = 0.0f; }
+  if (sc.kl && !sc.lr) return lm_fail(LM_ERR_BAD_ARG, "lm_adam_step_scheduled: a KL input needs the device learning rate");
   const float bc1 = 1.0f - powf(beta1, (float)step);
   const float bc2_sqrt = sqrtf(1.0f - powf(beta2, (float)step));
   ppo::k_adam_step<<<1, ppo::ADAM_THREADS, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, (int)n, lr, beta1, beta2, eps, weight_decay,
-                                                                      bc1, bc2_sqrt, max_grad_norm, grad_scale, grad_norm_out);
+                                                                      bc1, bc2_sqrt, max_grad_norm, grad_scale, grad_norm_out, sc);
   return lm_check_launch("lm_adam_step");
+}
+
+int lm_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1, float beta2, float eps,
+                 float weight_decay, int32_t step, float max_grad_norm, float grad_scale, float* grad_norm_out, void* stream) {
+  return lm_adam_step_scheduled(params, grads, exp_avg, exp_avg_sq, n, nullptr, lr, beta1, beta2, eps, weight_decay, step, max_grad_norm, grad_scale,
+                                grad_norm_out, stream);
 }
 
 }  // extern "C"

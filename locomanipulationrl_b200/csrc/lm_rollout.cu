@@ -32,7 +32,11 @@ struct Stats {
 struct WriteArgs {
   const float* obs; const float* mu; const float* value; const float* log_std; const float* noise; const float* rew;
   const long long* dones;
-  float* obses; float* actions; float* mus; float* values; float* rewards; float* dones_f; float* neglogp; float* actions_out;
+  float* obses; float* actions; float* mus; float* values; float* dones_f; float* neglogp; float* actions_out;
+  // The reward that arrives with observation t is the reward of the action stored in slot t - 1 (rl_games play_steps: rewards[n] is
+  // written after env_step(actions[n])): `rewards` / `prev_values` point at slot t - 1, NULL at t = 0.
+  float* rewards; const float* prev_values; const long long* time_outs; float gamma;
+  const float* value_denorm;            // [2] {mean, sqrt(var + eps)} of the value normaliser, NULL: values stored as they come
   int n; float reward_scale;
   unsigned long long noise_seed, noise_step; int sample_in_kernel;
   Stats st; int has_stats;
@@ -98,6 +102,18 @@ __device__ __forceinline__ void grid_moments(const double* partials, double* sm 
   __syncthreads();
 }
 
+// rl_games RunningMeanStd(denorm=True): sqrt(var + eps) * clamp(v, -5, 5) + mean (the network's value head is trained in
+// normalised units when normalize_value is on; the rollout stores de-normalised values)
+__device__ __forceinline__ float denorm_value(const float* dn, float v) {
+  return dn ? add(mul(dn[1], fminf(fmaxf(v, -5.0f), 5.0f)), dn[0]) : v;
+}
+// rewards_shaper scale, then value_bootstrap: + gamma * value * time_out (a2c_common.play_steps)
+template <typename A>
+__device__ __forceinline__ float shaped_reward(const A& a, unsigned int e, float rw) {
+  float r = mul(rw, a.reward_scale);
+  if (a.time_outs && a.time_outs[e] != 0) r = add(r, mul(a.gamma, a.prev_values[e]));
+  return r;
+}
 struct EnvIn { float4 mv[3], nv[3]; float val, rw; long long dn; };
 __device__ __forceinline__ EnvIn env_load(const WriteArgs& a, unsigned int e) {
   EnvIn in;
@@ -107,7 +123,7 @@ __device__ __forceinline__ EnvIn env_load(const WriteArgs& a, unsigned int e) {
     in.nv[q] = a.noise ? __ldg(reinterpret_cast<const float4*>(a.noise + e * 12) + q)
                        : (a.sample_in_kernel ? normal4(philox_at(a.noise_seed, a.noise_step, (unsigned long long)e * 3ull + q)) : make_float4(0.f, 0.f, 0.f, 0.f));
   }
-  in.val = a.value[e]; in.rw = a.rew[e]; in.dn = a.dones[e];
+  in.val = a.value[e]; in.rw = a.rewards ? a.rew[e] : 0.0f; in.dn = a.dones[e];
   return in;
 }
 __device__ __forceinline__ void env_emit(const WriteArgs& a, unsigned int e, const EnvIn& in, const float* s_sigma, float lsum) {
@@ -130,8 +146,8 @@ __device__ __forceinline__ void env_emit(const WriteArgs& a, unsigned int e, con
     if (a.actions_out) reinterpret_cast<float4*>(a.actions_out + e * 12)[q] = av;
   }
   a.neglogp[e] = 0.5f * ss + 11.027262398456072f + lsum;      // 0.5 log(2 pi) * 12
-  a.values[e] = in.val;
-  a.rewards[e] = mul(in.rw, a.reward_scale);
+  a.values[e] = denorm_value(a.value_denorm, in.val);
+  if (a.rewards) a.rewards[e] = shaped_reward(a, e, in.rw);
   a.dones_f[e] = in.dn != 0 ? 1.0f : 0.0f;
 }
 
@@ -143,6 +159,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_rollout_write(const WriteArgs a)
   __shared__ __align__(16) float s_sigma[12];
   __shared__ float s_lsum;
   pdl_launch_dependents();
+  pdl_wait();                                                          // log_std may be the predecessor's output (optimiser step)
   if (tid < 12) s_sigma[tid] = (float)exp((double)a.log_std[tid]);     // correctly rounded; torch's exp is within 1 ulp of it
   if (tid == 32) {
     float ls = 0.0f;
@@ -150,7 +167,6 @@ __global__ void __launch_bounds__(THREADS, 1) k_rollout_write(const WriteArgs a)
     s_lsum = ls;
   }
   __syncthreads();
-  pdl_wait();
   // ---- phase A: observations -> obses[t]; per-channel shifted moments
   {
     const int c4 = tid & 15;
@@ -199,6 +215,67 @@ __global__ void __launch_bounds__(THREADS, 1) k_rollout_write(const WriteArgs a)
     __syncthreads();
     if (tid == 0) a.st.count[0] += (double)a.n;
   }
+}
+
+// closes a rollout: the reward of the last stored action (slot T - 1) and the bootstrap inputs of GAE (last value, last done)
+struct FinishArgs {
+  const float* rew; const float* value; const long long* dones; const long long* time_outs;
+  float* rewards; const float* prev_values; float* last_values; float* last_dones;
+  const float* value_denorm; float gamma; float reward_scale; int n;
+};
+__global__ void k_rollout_finish(const FinishArgs a) {
+  const unsigned int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (unsigned int)a.n) return;
+  a.rewards[e] = shaped_reward(a, e, a.rew[e]);
+  a.last_values[e] = denorm_value(a.value_denorm, a.value[e]);
+  a.last_dones[e] = a.dones[e] != 0 ? 1.0f : 0.0f;
+}
+
+// y = clamp((x - mean) * inv_std, -clip, clip)   (RunningMeanStd.forward in eval mode; clip <= 0: no clamp)
+__global__ void k_normalize_clamp(const float* __restrict__ x, float* __restrict__ y, long long n, const float* __restrict__ mean,
+                                  const float* __restrict__ inv_std, float clip) {
+  const float m = mean[0], is = inv_std[0];
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float v = mul(sub(x[i], m), is);
+    if (clip > 0.0f) v = fminf(fmaxf(v, -clip), clip);
+    y[i] = v;
+  }
+}
+
+// moments[0..2] = {sum(x), sum(x^2), n} as doubles (advantage normalisation; summed over ranks by the caller when sharded)
+__global__ void __launch_bounds__(THREADS, 1) k_moments(const float* __restrict__ x, long long n, double* __restrict__ moments, double* partials,
+                                                        unsigned int* ticket) {
+  __shared__ double sm[THREADS / 32][2];
+  const int tid = threadIdx.x;
+  const long long stride = (long long)gridDim.x * THREADS;
+  double s1 = 0.0, s2 = 0.0;
+  for (long long i = (long long)blockIdx.x * THREADS + tid; i < n; i += stride) { const double v = (double)x[i]; s1 += v; s2 += v * v; }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, off); s2 += __shfl_xor_sync(0xffffffffu, s2, off); }
+  if ((tid & 31) == 0) { sm[tid >> 5][0] = s1; sm[tid >> 5][1] = s2; }
+  __syncthreads();
+  if (tid < 2) {
+    double s = 0.0;
+    for (int w = 0; w < THREADS / 32; ++w) s += sm[w][tid];
+    partials[(size_t)blockIdx.x * 2 + tid] = s;
+  }
+  if (last_cta(ticket)) {
+    if (tid < 2) {
+      double s = 0.0;
+      for (int c = 0; c < (int)gridDim.x; ++c) s += __ldcg(partials + (size_t)c * 2 + tid);
+      moments[tid] = s;
+    }
+    if (tid == 2) moments[2] = (double)n;
+  }
+}
+// y = (x - mean) / (std + eps), mean / unbiased std from the (possibly all-reduced) moments: torch `(a - a.mean()) / (a.std() + 1e-8)`
+__global__ void k_moment_normalize(const float* __restrict__ x, float* __restrict__ y, long long n, const double* __restrict__ moments, float eps) {
+  const double cnt = moments[2], mean_d = moments[0] / cnt;
+  const double var = cnt > 1.0 ? fmax((moments[1] - moments[0] * mean_d) / (cnt - 1.0), 0.0) : 0.0;
+  const float mean = (float)mean_d, denom = add((float)sqrt(var), eps);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) y[i] = fdiv(sub(x[i], mean), denom);
 }
 
 // stand-alone fold of x [n, dim] (dim = 1 or a multiple of 4, <= 64)
@@ -298,6 +375,14 @@ __global__ void k_rms_export(Stats st, float* __restrict__ mean_f32, float* __re
   inv_std_f32[c] = st.variant == LM_RMS_RLGAMES ? fdiv(1.0f, __fsqrt_rn(add(var, 1e-5f))) : fdiv(1.0f, add(__fsqrt_rn(var), 1e-8f));
 }
 
+// {mean, std} of a scalar normaliser in the form RunningMeanStd(denorm=True) applies: y = std * clamp(x, -5, 5) + mean
+__global__ void k_rms_export_denorm(Stats st, float* __restrict__ out) {
+  if (threadIdx.x != 0) return;
+  out[0] = (float)st.mean[0];
+  const float var = (float)st.var[0];
+  out[1] = st.variant == LM_RMS_RLGAMES ? __fsqrt_rn(add(var, 1e-5f)) : add(__fsqrt_rn(var), 1e-8f);
+}
+
 }  // namespace rollout
 }  // namespace lm
 
@@ -351,7 +436,8 @@ void lm_rollout_destroy(LmRollout* r) {
 int lm_rollout_write(LmRollout* r, const LmRolloutStep* step, const LmRolloutBuffers* buf, int32_t t, float* actions_out,
                      const LmRunningStats* obs_stats, void* stream) {
   if (!r || !step || !buf) return lm_fail(LM_ERR_BAD_ARG, "lm_rollout_write: NULL argument");
-  if (!step->obs || !step->mu || !step->value || !step->log_std || !step->rew || !step->dones) return lm_fail(LM_ERR_BAD_ARG, "lm_rollout_write: NULL step tensor");
+  if (!step->obs || !step->mu || !step->value || !step->log_std || !step->dones) return lm_fail(LM_ERR_BAD_ARG, "lm_rollout_write: NULL step tensor");
+  if (t > 0 && !step->rew) return lm_fail(LM_ERR_BAD_ARG, "lm_rollout_write: rew is required for t > 0 (it completes slot t - 1)");
   if (!buf->obses || !buf->actions || !buf->mus || !buf->values || !buf->rewards || !buf->dones || !buf->neglogp) return lm_fail(LM_ERR_BAD_ARG, "lm_rollout_write: NULL rollout buffer");
   if (buf->num_envs > (1 << 27)) return lm_fail(LM_ERR_UNSUPPORTED, "lm_rollout_write: more than 2^27 envs per call");
   if (buf->num_envs <= 0 || t < 0 || t >= buf->horizon) return lm_fail(LM_ERR_BAD_ARG, "lm_rollout_write: t = %d outside [0, %d)", t, buf->horizon);
@@ -368,7 +454,11 @@ int lm_rollout_write(LmRollout* r, const LmRolloutStep* step, const LmRolloutBuf
   a.obs = step->obs; a.mu = step->mu; a.value = step->value; a.log_std = step->log_std; a.noise = step->noise; a.rew = step->rew;
   a.dones = reinterpret_cast<const long long*>(step->dones);
   a.obses = buf->obses + (size_t)t * n * 64; a.actions = buf->actions + (size_t)t * n * 12; a.mus = buf->mus + (size_t)t * n * 12;
-  a.values = buf->values + (size_t)t * n; a.rewards = buf->rewards + (size_t)t * n; a.dones_f = buf->dones + (size_t)t * n;
+  a.values = buf->values + (size_t)t * n; a.dones_f = buf->dones + (size_t)t * n;
+  a.rewards = t > 0 ? buf->rewards + (size_t)(t - 1) * n : nullptr;
+  a.prev_values = t > 0 ? buf->values + (size_t)(t - 1) * n : nullptr;
+  a.time_outs = t > 0 ? reinterpret_cast<const long long*>(step->time_outs) : nullptr; a.gamma = step->gamma;
+  a.value_denorm = step->value_denorm;
   a.neglogp = buf->neglogp + (size_t)t * n; a.actions_out = actions_out;
   a.n = buf->num_envs; a.reward_scale = buf->reward_scale;
   a.noise_seed = step->noise_seed; a.noise_step = step->noise_step; a.sample_in_kernel = step->sample_in_kernel;
@@ -383,6 +473,42 @@ int lm_rollout_write(LmRollout* r, const LmRolloutStep* step, const LmRolloutBuf
   return lm_check_launch("lm_rollout_write");
 }
 
+int lm_rollout_finish(LmRollout* r, const LmRolloutStep* step, const LmRolloutBuffers* buf, float* last_values, float* last_dones, void* stream) {
+  if (!r || !step || !buf || !last_values || !last_dones) return lm_fail(LM_ERR_BAD_ARG, "lm_rollout_finish: NULL argument");
+  if (!step->rew || !step->value || !step->dones || !buf->rewards || !buf->values || buf->num_envs <= 0 || buf->horizon <= 0)
+    return lm_fail(LM_ERR_BAD_ARG, "lm_rollout_finish: NULL tensor");
+  const size_t n = (size_t)buf->num_envs, last = (size_t)(buf->horizon - 1) * n;
+  FinishArgs a;
+  a.rew = step->rew; a.value = step->value; a.dones = reinterpret_cast<const long long*>(step->dones);
+  a.time_outs = reinterpret_cast<const long long*>(step->time_outs);
+  a.rewards = buf->rewards + last; a.prev_values = buf->values + last; a.last_values = last_values; a.last_dones = last_dones;
+  a.value_denorm = step->value_denorm; a.gamma = step->gamma; a.reward_scale = buf->reward_scale; a.n = buf->num_envs;
+  k_rollout_finish<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a);
+  return lm_check_launch("lm_rollout_finish");
+}
+
+int lm_normalize_clamp(const float* x, float* y, int64_t n, const float* mean, const float* inv_std, float clip, void* stream) {
+  if (!x || !y || !mean || !inv_std || n <= 0) return lm_fail(LM_ERR_BAD_ARG, "lm_normalize_clamp: bad argument");
+  const long long want = (n + 255) / 256;
+  k_normalize_clamp<<<(unsigned)(want < 4096 ? want : 4096), 256, 0, (cudaStream_t)stream>>>(x, y, (long long)n, mean, inv_std, clip);
+  return lm_check_launch("lm_normalize_clamp");
+}
+
+int lm_moments(LmRollout* r, const float* x, int64_t n, double* moments, void* stream) {
+  if (!r || !x || !moments || n <= 0) return lm_fail(LM_ERR_BAD_ARG, "lm_moments: bad argument");
+  const size_t work = ((size_t)n + THREADS - 1) / THREADS;
+  const int grid = (int)(work < (size_t)r->sm_count ? work : (size_t)r->sm_count);
+  k_moments<<<grid, THREADS, 0, (cudaStream_t)stream>>>(x, (long long)n, moments, r->partials, r->ticket);
+  return lm_check_launch("lm_moments");
+}
+
+int lm_moment_normalize(const float* x, float* y, int64_t n, const double* moments, float eps, void* stream) {
+  if (!x || !y || !moments || n <= 0) return lm_fail(LM_ERR_BAD_ARG, "lm_moment_normalize: bad argument");
+  const long long want = (n + 255) / 256;
+  k_moment_normalize<<<(unsigned)(want < 4096 ? want : 4096), 256, 0, (cudaStream_t)stream>>>(x, y, (long long)n, moments, eps);
+  return lm_check_launch("lm_moment_normalize");
+}
+
 int lm_rms_update(LmRollout* r, const float* x, int64_t n, const LmRunningStats* stats, void* stream) {
   if (!r || !x || !stats || n <= 0) return lm_fail(LM_ERR_BAD_ARG, "lm_rms_update: bad argument");
   const int rc = check_stats(stats, "lm_rms_update");
@@ -394,6 +520,16 @@ int lm_rms_update(LmRollout* r, const float* x, int64_t n, const LmRunningStats*
   Stats st{stats->mean, stats->var, stats->count, stats->dim, stats->variant};
   k_rms_update<<<grid, THREADS, 0, (cudaStream_t)stream>>>(x, (long long)n, st, r->partials, r->ticket);
   return lm_check_launch("lm_rms_update");
+}
+
+int lm_rms_export_denorm(const LmRunningStats* stats, float* mean_std_f32, void* stream) {
+  if (!stats || !mean_std_f32) return lm_fail(LM_ERR_BAD_ARG, "lm_rms_export_denorm: NULL argument");
+  const int rc = check_stats(stats, "lm_rms_export_denorm");
+  if (rc != LM_OK) return rc;
+  if (stats->dim != 1) return lm_fail(LM_ERR_BAD_ARG, "lm_rms_export_denorm: scalar statistics only (the value normaliser)");
+  Stats st{stats->mean, stats->var, stats->count, stats->dim, stats->variant};
+  k_rms_export_denorm<<<1, 32, 0, (cudaStream_t)stream>>>(st, mean_std_f32);
+  return lm_check_launch("lm_rms_export_denorm");
 }
 
 int lm_rms_export(const LmRunningStats* stats, float* mean_f32, float* inv_std_f32, void* stream) {

@@ -1229,6 +1229,7 @@ int lm_struct_size(int which) {
     case 9: return (int)sizeof(LmNoiseSpec);
     case 10: return (int)sizeof(LmNoiseState);
     case 11: return (int)sizeof(LmCustomController);
+    case 12: return (int)sizeof(LmAdamSchedule);
     default: return -1;
   }
 }

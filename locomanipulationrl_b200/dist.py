@@ -31,6 +31,61 @@ def init_from_env(backend: Optional[str] = None) -> "tuple[int, int, int]":
     return rank, world, local_rank
 
 
+class PeerComm:
+    """One-shot all-reduce over NVLink peer memory (csrc/lm_comm.cuh): every rank pushes its values into every peer's receive
+    slot, raises a flag, and sums the slots in rank order.  Receive memory is allocated by the library; its cudaIpc handle is
+    exchanged here through the process group that already exists (torch.distributed is the plumbing, the data path is ours).
+    ``all_reduce`` is CUDA-graph capturable; the gradient path uses the same communicator from inside the weight-gradient
+    kernel (``ppo.MlpPpoGradients(comm=...)``)."""
+
+    def __init__(self, max_floats: int, device=None, group=None):
+        import ctypes as C
+        from . import _lib
+        self._lib_mod, self._lib = _lib, _lib.load()
+        if dist.is_initialized():
+            self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        else:
+            self.rank, self.world = 0, 1
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.handle = self._lib.lm_comm_create(idx, self.rank, self.world, int(max_floats))
+        if not self.handle:
+            raise _lib.LmError(f"lm_comm_create failed: {self._lib.lm_last_error().decode()}")
+        self.max_floats = int(max_floats)
+        if self.world > 1:
+            nb = self._lib.lm_comm_handle_bytes()
+            mine = (C.c_uint8 * nb)()
+            _lib.check(self._lib.lm_comm_get_handle(self.handle, mine), "lm_comm_get_handle")
+            backend = dist.get_backend(group)
+            t = torch.tensor(list(bytes(mine)), dtype=torch.uint8, device=self.device if backend == "nccl" else "cpu")
+            gathered = [torch.empty_like(t) for _ in range(self.world)]
+            dist.all_gather(gathered, t, group=group)
+            blob = b"".join(bytes(g.cpu().tolist()) for g in gathered)
+            buf = (C.c_uint8 * len(blob)).from_buffer_copy(blob)
+            _lib.check(self._lib.lm_comm_open(self.handle, buf), "lm_comm_open")
+            dist.barrier(group=group)
+
+    def all_reduce(self, t: torch.Tensor) -> torch.Tensor:
+        """In-place sum over the ranks of a contiguous fp32 CUDA tensor (<= max_floats elements)."""
+        if t.dtype != torch.float32 or not t.is_cuda or not t.is_contiguous():
+            raise self._lib_mod.LmError("PeerComm.all_reduce: contiguous fp32 CUDA tensor required")
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        self._lib_mod.check(self._lib.lm_comm_allreduce(self.handle, t.data_ptr(), t.numel(), stream), "lm_comm_allreduce")
+        return t
+
+    def status(self) -> int:
+        """0, or 1 + r after a time-out waiting for rank r (host synchronisation)."""
+        return int(self._lib.lm_comm_status(self.handle))
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                self._lib.lm_comm_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
 @dataclass
 class EnvSharding:
     """Block sharding of ``global_envs`` environments over ``world`` ranks."""
@@ -86,7 +141,8 @@ class GradArena:
     ``tail`` extra fp32 slots ride along in the same call (``FusedHorizonReducer`` puts the episode stats there: at these
     sizes a collective is pure latency, so one call instead of two halves the cost of the rollout boundary)."""
 
-    def __init__(self, params: Iterable[torch.nn.Parameter], group=None, tail: int = 0):
+    def __init__(self, params: Iterable[torch.nn.Parameter], group=None, tail: int = 0, comm: Optional[PeerComm] = None):
+        self.comm = comm
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
         n = sum(p.numel() for p in self.params)
         dev = self.params[0].device
@@ -109,6 +165,10 @@ class GradArena:
     def allreduce_mean(self, async_op: bool = False):
         if not (dist.is_initialized() and dist.get_world_size(self.group) > 1):
             return None
+        if self.comm is not None:                     # one-shot NVLink all-reduce (our kernel) instead of the NCCL call
+            self.comm.all_reduce(self.storage)
+            self.flat.div_(self.comm.world)
+            return None
         work = dist.all_reduce(self.storage, op=dist.ReduceOp.SUM, group=self.group, async_op=async_op)
         if async_op:
             return work
@@ -122,8 +182,8 @@ class FusedHorizonReducer:
     (< 2^24) and costs the means one rounding (6e-8 relative)."""
     TAIL = 14
 
-    def __init__(self, params: Iterable[torch.nn.Parameter], num_local_envs: int, group=None):
-        self.arena = GradArena(params, group=group, tail=self.TAIL)
+    def __init__(self, params: Iterable[torch.nn.Parameter], num_local_envs: int, group=None, comm: Optional[PeerComm] = None):
+        self.arena = GradArena(params, group=group, tail=self.TAIL, comm=comm)
         self.n = float(num_local_envs)
 
     def reduce(self, extras_buf: torch.Tensor, counters: torch.Tensor) -> None:

@@ -13,6 +13,15 @@ from .gnn import GnnActorCritic
 from .mlp import MlpActorCritic
 
 
+def _core_forward(core, obs):
+    """Inference: the fused kernels.  With autograd on (rl_games ``calc_gradients`` / skrl ``_update``): the MLP's differentiable
+    tcgen05 path (``_MlpTrainFunction``); the GNN's differentiable torch restatement (``reference_forward``) — its update kernels
+    are ``ppo.GnnPpoGradients``, which works outside autograd."""
+    if torch.is_grad_enabled() and isinstance(core, GnnActorCritic) and any(p.requires_grad for p in core.parameters()):
+        return core.reference_forward(obs)
+    return core(obs)
+
+
 class _RlGamesNet(nn.Module):
     """rl_games 1.6.0 network contract: ``forward(obs_dict) -> (mu, sigma, value, states)``; ``is_rnn() -> False``."""
 
@@ -29,7 +38,7 @@ class _RlGamesNet(nn.Module):
 
     def forward(self, obs_dict):
         obs = obs_dict["obs"]
-        mu, value, log_std = self.core(obs)
+        mu, value, log_std = _core_forward(self.core, obs)
         sigma = log_std.expand_as(mu) if self.fixed_sigma else log_std     # rl_games applies exp() in the model wrapper
         return mu, sigma, value, obs_dict.get("rnn_states", None)
 
@@ -82,12 +91,26 @@ class SkrlShared(nn.Module):
         super().__init__()
         self.core = GnnActorCritic(device=device) if use_graph else MlpActorCritic(device=device)
         self._cache = None
+        self._register_load_state_dict_pre_hook(self._remap_reference_keys)
+
+    @staticmethod
+    def _remap_reference_keys(state_dict, prefix, *args):
+        """A checkpoint of the reference's ``Shared`` has its parameters at the top level (``net.0.weight``, ``mean_layer.weight``,
+        ``log_std_parameter`` ...); here they live under ``core.``: accept both."""
+        for k in list(state_dict.keys()):
+            if k.startswith(prefix) and not k.startswith(prefix + "core."):
+                state_dict[prefix + "core." + k[len(prefix):]] = state_dict.pop(k)
 
     def compute(self, inputs, role):
         states = inputs["states"]
-        # the reference evaluates the shared trunk once per role; here both heads come out of one kernel launch
-        if self._cache is None or self._cache[0] is not states:
-            self._cache = (states, self.core(states))
+        # The reference evaluates the shared trunk once per role; here both heads come out of one kernel launch, reused by the second
+        # role of the SAME step.  The task hands out the same obs_buf object every step and the kernels rewrite it in place, so the
+        # key is (storage, torch version counter, role already served) — never object identity alone — and differentiable calls
+        # are never cached (each role's loss needs its own graph).
+        key = (states.data_ptr(), states._version, tuple(states.shape))
+        if torch.is_grad_enabled() or self._cache is None or self._cache[0] != key or role in self._cache[2]:
+            self._cache = (key, _core_forward(self.core, states), set())
+        self._cache[2].add(role)
         mu, value, log_std = self._cache[1]
         if role == "policy":
             return mu, log_std, {}

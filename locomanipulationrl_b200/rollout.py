@@ -60,6 +60,25 @@ class RunningMeanStd:
         _lib.check(lib.lm_rms_export(C.byref(st), self._mean32.data_ptr(), self._inv_std32.data_ptr(), stream), "lm_rms_export")
         return self._mean32, self._inv_std32
 
+    def export_denorm(self) -> torch.Tensor:
+        """[2] = (mean, std) fp32 of a scalar normaliser, the form ``RolloutBuffer.write(value_denorm=...)`` takes."""
+        if getattr(self, "_denorm32", None) is None:
+            self._denorm32 = torch.zeros(2, dtype=torch.float32, device=self.device)
+        st = self.c_struct()
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(_lib.load().lm_rms_export_denorm(C.byref(st), self._denorm32.data_ptr(), stream), "lm_rms_export_denorm")
+        return self._denorm32
+
+    def normalize(self, x: torch.Tensor, out: Optional[torch.Tensor] = None, clip: float = 5.0) -> torch.Tensor:
+        """Scalar normaliser only: clamp((x - mean) / std, +-clip) with the CURRENT statistics (eval-mode forward)."""
+        assert self.dim == 1
+        mean32, inv_std32 = self.export()
+        out = torch.empty_like(x) if out is None else out
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(_lib.load().lm_normalize_clamp(x.data_ptr(), out.data_ptr(), x.numel(), mean32.data_ptr(), inv_std32.data_ptr(), float(clip), stream),
+                   "lm_normalize_clamp")
+        return out
+
     def __del__(self):
         try:
             if self._h:
@@ -86,14 +105,24 @@ class RolloutBuffer:
         self._buf = _lib.LmRolloutBuffers(td["obses"].data_ptr(), td["actions"].data_ptr(), td["mus"].data_ptr(), td["values"].data_ptr(),
                                           td["rewards"].data_ptr(), td["dones"].data_ptr(), td["neglogpacs"].data_ptr(), T, N, self.reward_scale)
 
-    def write(self, t: int, obs, mu, value, log_std, rew, dones, noise: Optional[torch.Tensor] = None,
-              actions_out: Optional[torch.Tensor] = None, obs_stats: Optional[RunningMeanStd] = None, sample_seed: Optional[int] = None) -> None:
-        """Slot ``t`` <- this step.  ``noise`` = standard-normal draws [N,12] of the caller's generator; without it, ``sample_seed``
-        makes the kernel draw its own N(0,1) noise (counter-based: reproducible for a given seed and call count, no draw tensor),
-        and neither means act = mu (evaluation).  ``actions_out`` receives the sampled actions for the next ``pre_physics_step``."""
+    def _step(self, obs, mu, value, log_std, rew, dones, noise, sample_seed, time_outs, gamma, value_denorm):
         in_kernel = noise is None and sample_seed is not None
         step = _lib.LmRolloutStep(_lib.ptr(obs), _lib.ptr(mu), _lib.ptr(value), _lib.ptr(log_std), _lib.ptr(noise), _lib.ptr(rew), _lib.ptr(dones),
-                                  int(sample_seed or 0), self._sample_calls, int(in_kernel), 0)
+                                  int(sample_seed or 0), self._sample_calls, int(in_kernel), 0, _lib.ptr(time_outs), float(gamma), 0,
+                                  _lib.ptr(value_denorm))
+        return step, in_kernel
+
+    def write(self, t: int, obs, mu, value, log_std, rew, dones, noise: Optional[torch.Tensor] = None,
+              actions_out: Optional[torch.Tensor] = None, obs_stats: Optional[RunningMeanStd] = None, sample_seed: Optional[int] = None,
+              time_outs: Optional[torch.Tensor] = None, gamma: float = 0.99, value_denorm: Optional[torch.Tensor] = None) -> None:
+        """Slot ``t`` <- this step, in rl_games' ``play_steps`` order: ``obs`` / ``dones`` / ``rew`` are what the env returned last, so
+        ``rew`` (the reward of the action stored in slot t-1) goes to slot t-1 — nothing at t = 0 — and :meth:`finish` closes the
+        rollout.  ``noise`` = standard-normal draws [N,12] of the caller's generator; without it, ``sample_seed`` makes the kernel
+        draw its own N(0,1) noise (counter-based: reproducible for a given seed and call count, no draw tensor), and neither means
+        act = mu (evaluation).  ``actions_out`` receives the sampled actions for the next ``pre_physics_step``.  ``time_outs``
+        (int64 [N]) switches on value_bootstrap; ``value_denorm`` ([2] = mean, std from ``RunningMeanStd.export_denorm``) stores
+        de-normalised values (normalize_value)."""
+        step, in_kernel = self._step(obs, mu, value, log_std, rew, dones, noise, sample_seed, time_outs, gamma, value_denorm)
         if in_kernel:
             self._sample_calls += 1
         st = obs_stats.c_struct() if obs_stats is not None else None
@@ -101,6 +130,18 @@ class RolloutBuffer:
         rc = self._lib.lm_rollout_write(self._h, C.byref(step), C.byref(self._buf), int(t), _lib.ptr(actions_out),
                                         C.byref(st) if st is not None else None, stream)
         _lib.check(rc, "lm_rollout_write")
+
+    def finish(self, rew, value, dones, time_outs: Optional[torch.Tensor] = None, gamma: float = 0.99,
+               value_denorm: Optional[torch.Tensor] = None):
+        """The env step after slot T-1: its reward completes slot T-1; returns (last_values, last_dones) [N], GAE's bootstrap."""
+        if not hasattr(self, "last_values"):
+            self.last_values = torch.empty(self.num_envs, device=self.device)
+            self.last_dones = torch.empty(self.num_envs, device=self.device)
+        step, _ = self._step(None, None, value, None, rew, dones, None, None, time_outs, gamma, value_denorm)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        rc = self._lib.lm_rollout_finish(self._h, C.byref(step), C.byref(self._buf), self.last_values.data_ptr(), self.last_dones.data_ptr(), stream)
+        _lib.check(rc, "lm_rollout_finish")
+        return self.last_values, self.last_dones
 
     def __del__(self):
         try:

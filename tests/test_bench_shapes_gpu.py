@@ -1,0 +1,206 @@
+"""Parity at the shapes and through the entry points bench.py times: the 65,536-env co-train Pipeline under
+CUDA-graph replay with the fused observation clamp, the > 1,024-tile finish path (k_post_finish), the host-buffer stepper behind
+the e2e figure, shard invariance of the env sharding, and the position / effort branches of take_action."""
+import pytest
+import torch
+
+from locomanipulationrl_b200 import configs, synthetic
+from tests.common import CudaRollout, assert_close, rollout_inputs
+
+pytestmark = pytest.mark.gpu
+
+
+def _tracker(task, port, scene_cpu, cfg, n):
+    """A CudaRollout shell around an existing (task, port) pair: reuses compare_post()."""
+    ro = CudaRollout.__new__(CudaRollout)
+    ro.cfg, ro.n, ro.task, ro.port, ro.scene_cpu, ro.scene_gpu = cfg, n, task, port, scene_cpu, None
+    ro.exempt_events, ro.max_err = 0, {}
+    return ro
+
+
+def test_bench_pipeline_65536_graph_replay_matches_port():
+    """BASELINE configs[2] exactly as bench.py runs it: JointLocomanipulationVertical, 65,536 envs, fuse_obs_clamp, six rotating
+    state sets, the policy's mean fed back as the next action, one CUDA graph per state set — tracked by the oracle port for the
+    six eager warm-up steps and eight replayed ones."""
+    import bench
+    from oracle import port
+    dev = torch.device("cuda:0")
+    pipe = bench.Pipeline("cotrain64k", dev, rank=0)
+    cfg, n = pipe.cfg, pipe.n
+    assert n == 65536 and pipe.task._fuse_obs_clamp
+    scenes_cpu = []
+    for i in range(bench.STATE_SETS):
+        sc = synthetic.SyntheticScene(cfg, n, seed=42)
+        sc.load(sc.generate(i))
+        scenes_cpu.append(sc)
+    p = port.TaskPort(cfg, scenes_cpu[0])
+    ro = _tracker(pipe.task, p, scenes_cpu[0], cfg, n)
+    unis = [u.cpu() for u in pipe.uniforms]
+    actions = {"a": pipe.actions.detach().cpu().clone()}
+
+    def track(i, t):
+        torch.cuda.synchronize()
+        p.pre_physics_step(torch.clamp(actions["a"], -1.0, 1.0), unis[i])      # the adapter's clamp (vec_env_rlgames.py:60)
+        p.scene = scenes_cpu[i]
+        ro.scene_cpu = scenes_cpu[i]
+        p.post_physics_step()
+        p.obs_buf = torch.clamp(p.obs_buf, -cfg.clip_observations, cfg.clip_observations)      # _process_data, fused into the kernel
+        ro.compare_post(t)
+        for grp in ("loco", "mani"):                                            # reset scatter landed in the same (rotating) views
+            prev = scenes_cpu[(i - 1) % bench.STATE_SETS] if t > 0 else scenes_cpu[0]
+            got = getattr(pipe.scenes[(i - 1) % bench.STATE_SETS] if t > 0 else pipe.scenes[0], grp)
+            for k in ("dof_pos", "root_pos" if grp == "loco" else "plate_pos", "indicator_quat"):
+                assert_close(f"step {t} scene.{grp}.{k}", got[k], getattr(prev, grp)[k])
+        mu_ref, v_ref, _ = pipe.policy.reference_forward((pipe.task.obs_buf - pipe.norm_mean) * pipe.norm_inv_std)
+        assert_close(f"step {t} mu", pipe.mu, mu_ref.detach(), rtol=0, atol=1e-2)
+        assert_close(f"step {t} value", pipe.value, v_ref.detach(), rtol=0, atol=1e-2)
+        actions["a"] = pipe.mu.detach().cpu().clone()
+
+    pipe.capture(after_step=lambda i: track(i, i))
+    assert pipe.graphs is not None and len(pipe.graphs) == bench.STATE_SETS
+    for t in range(bench.STATE_SETS, bench.STATE_SETS + 8):
+        pipe.step(t)
+        track(t % bench.STATE_SETS, t)
+    assert ro.exempt_events == 0, f"{ro.exempt_events} near-threshold mask exemptions"
+    print("65,536-env graph replay max abs err:", {k: f"{v:.2e}" for k, v in ro.max_err.items()})
+
+
+def test_large_grid_finish_kernel_262144_envs():
+    """2,048 tiles: beyond the 1,024-tile in-kernel tail, the finish pass runs as k_post_finish (the path behind bench.py's
+    `roofline_large`).  Reset id lists (the scan the finish pass leaves), counters and extras are compared inside step()."""
+    n = 262144
+    ro = CudaRollout("JointLocomanipulationVertical", n)
+    acts, unis = rollout_inputs(n, 3, seed=21)
+    for t in range(3):
+        ro.step(t, acts[t], unis[t])
+    assert ro.exempt_events <= 2
+    print("262,144 envs max abs err:", {k: f"{v:.2e}" for k, v in ro.max_err.items()}, "exempt:", ro.exempt_events)
+
+
+@pytest.mark.parametrize("shards", [1, 4])
+def test_host_stepper_matches_port(shards):
+    """ShardedHostStepper / lm_task_step_host_async — the entry behind bench.py's e2e figure — against the port + the fp32 torch MLP:
+    rewards, reset flags, observations, policy mean and value as they arrive in the pinned host buffers, actions fed back."""
+    from locomanipulationrl_b200.host_step import ShardedHostStepper
+    from locomanipulationrl_b200.policy.mlp import MlpActorCritic
+    from oracle import port
+    cfg = configs.get_task_config("JointLocomanipulationVertical")
+    n = 8192
+    torch.manual_seed(0)
+    policy = MlpActorCritic(device="cuda:0")
+    norm_mean, norm_inv = torch.randn(64, device="cuda") * 0.1, torch.rand(64, device="cuda") + 0.5
+    st = ShardedHostStepper(cfg, n, policy, shards=shards, device="cuda:0", seed=5, env_id_offset=0, norm_mean=norm_mean, norm_inv_std=norm_inv,
+                            readback_obs=True)
+    g = torch.Generator().manual_seed(9)
+    ports, scenes = [], []
+    for k, s in enumerate(st.shards):
+        sc = synthetic.SyntheticScene(cfg, s.n, seed=5 + 17 * k, env_id_offset=k * s.n)
+        scenes.append(sc)
+        ports.append(port.TaskPort(cfg, sc))
+    exempt = 0
+    for t in range(5):
+        for s in st.shards:
+            s.uniforms_host.copy_(torch.rand(s.n, 3, generator=g))
+        actions_in = [a.clone() for a in st.mu_host]
+        states = [sc.generate(t) for sc in scenes]
+        st.step([s.scene.pack_host(x) for s, x in zip(st.shards, states)])
+        for k, (s, p, sc) in enumerate(zip(st.shards, ports, scenes)):
+            p.pre_physics_step(torch.clamp(actions_in[k], -1.0, 1.0), s.uniforms_host.clone())
+            sc.load(states[k])
+            p.post_physics_step()
+            ro = _tracker(s.task, p, sc, cfg, s.n)
+            p.obs_buf = torch.clamp(p.obs_buf, -5.0, 5.0)
+            ro.compare_post(t)
+            exempt += ro.exempt_events
+            assert_close(f"step {t} shard {k} obs_host", s.obs_host, p.obs_buf)
+            assert torch.equal(s.reset_host, s.task.reset_buf.cpu()) and torch.equal(s.rew_host, s.task.rew_buf.cpu())
+            with torch.no_grad():
+                mu_ref, v_ref, _ = policy.reference_forward(torch.clamp((s.task.obs_buf - norm_mean) * norm_inv, -5.0, 5.0))
+            assert_close(f"step {t} shard {k} mu_host", st.mu_host[k], mu_ref.cpu(), rtol=0, atol=1e-2)
+            assert_close(f"step {t} shard {k} value_host", s.value_host, v_ref.cpu(), rtol=0, atol=1e-2)
+    assert exempt <= 2
+
+
+def test_shard_invariance_two_shards_equal_one_task():
+    """N envs on one rank == N/k envs on each of k ranks after the fixed permutation EnvSharding.global_ids.  Two
+    half-size tasks fed the slices of the global state / actions (and the uniform rows their reset ranks map to) reproduce the
+    global task bit for bit; counters add up."""
+    from locomanipulationrl_b200.dist import EnvSharding
+    from locomanipulationrl_b200.tasks.base import LocoManipulationTask
+    cfg = configs.get_task_config("JointLocomanipulationVertical")
+    N, K = 4096, 2
+    H = N // 2
+    glob_scene = synthetic.SyntheticScene(cfg, N, device="cuda:0", seed=31)
+    glob = LocoManipulationTask(cfg, N, scene=glob_scene)
+    shards = []
+    for r in range(K):
+        sh = EnvSharding(N, K, r)
+        sc = synthetic.SyntheticScene(cfg, sh.local_envs, device="cuda:0", seed=31)
+        hl = sh.local_envs // 2
+        sc.env_pos.copy_(glob_scene.env_pos[r * hl:(r + 1) * hl])
+        shards.append((sh, sc, LocoManipulationTask(cfg, sh.local_envs, scene=sc), sh.global_ids().cuda()))
+    acts, unis = rollout_inputs(N, 10, seed=13)
+    reset_prev = torch.ones(N, dtype=torch.long)
+    for t in range(10):
+        ids_g = reset_prev.nonzero().squeeze(-1)                     # the global reset list: uniform row = position in it
+        rank_of = torch.full((N,), -1, dtype=torch.long)
+        rank_of[ids_g] = torch.arange(ids_g.numel())
+        glob.pre_physics_step(acts[t].cuda(), unis[t].cuda())
+        for sh, sc, task, gids in shards:
+            local_reset = reset_prev[gids.cpu()].nonzero().squeeze(-1)
+            u = torch.zeros(sh.local_envs, 3)
+            u[:local_reset.numel()] = unis[t][rank_of[gids.cpu()[local_reset]]]
+            task.pre_physics_step(acts[t][gids.cpu()].cuda(), u.cuda())
+        st = glob_scene.generate(t, glob.goal_quaternions)
+        glob_scene.load(st)
+        for r, (sh, sc, task, gids) in enumerate(shards):
+            hl = sh.local_envs // 2
+            part = {}
+            for grp in ("loco", "mani"):
+                part[grp] = {}
+                for k, v in st[grp].items():
+                    per = v.shape[0] // H                              # rows per env (tips 4, knees 8)
+                    part[grp][k] = v[r * hl * per:(r + 1) * hl * per]
+            sc.load(part)
+        glob.post_physics_step()
+        for sh, sc, task, gids in shards:
+            task.post_physics_step()
+            for name in ("obs_buf", "rew_buf", "reset_buf", "progress_buf", "successes", "consecutive_successes", "goal_reset_buf",
+                         "goal_quaternions", "last_joint_velocities"):
+                assert torch.equal(getattr(task, name), getattr(glob, name)[gids]), f"step {t}: {name}"
+        assert torch.equal(sum(task._counters for _, _, task, _ in shards), glob._counters), f"step {t}: counters"
+        ex = sum(task._extras_buf[:7].double() * sh.local_envs for sh, _, task, _ in shards) / N
+        assert_close(f"step {t} reward-term means", ex, glob._extras_buf[:7], rtol=1e-5, atol=1e-7)
+        reset_prev = glob.reset_buf.cpu().clone()
+
+
+@pytest.mark.parametrize("mode", [configs.CONTROL_POSITION, configs.CONTROL_EFFORT])
+def test_take_action_position_and_effort_modes(mode):
+    """robot.py:444-461: position targets (+-pi) and effort targets (+-1.5 N m scattered into the 20-wide DOF row).  Every shipped
+    robot config uses velocity mode; these branches exist in the reference and in k_pre."""
+    from locomanipulationrl_b200.tasks.base import LocoManipulationTask
+    from oracle import port
+    cfg = configs.get_task_config("QuadrupedPoseControl").with_(control_mode=mode)
+    n = 1000
+    scene_gpu, scene_cpu = synthetic.SyntheticScene(cfg, n, device="cuda:0", seed=3), synthetic.SyntheticScene(cfg, n, seed=3)
+    task, p = LocoManipulationTask(cfg, n, scene=scene_gpu), port.TaskPort(cfg, scene_cpu)
+    acts, unis = rollout_inputs(n, 3, seed=8)
+    for t in range(3):
+        a = acts[t] * 1.7                                             # beyond +-1: the adapter clamp is part of the entry
+        p.pre_physics_step(torch.clamp(a, -1.0, 1.0), unis[t])
+        task.pre_physics_step(a.cuda(), unis[t].cuda())
+        ref = p.targets["loco"]
+        if mode == configs.CONTROL_EFFORT:
+            assert task.targets_loco.shape == (n, 20)
+            full = torch.zeros(n, 20)
+            full[:, :12] = ref                                        # dof_index is the identity for the synthetic articulation
+            assert_close(f"step {t} effort targets", task.targets_loco, full)
+            assert float(ref.abs().max()) <= 1.5 + 1e-6
+        else:
+            assert_close(f"step {t} position targets", task.targets_loco, ref)
+            assert 3.0 < float(ref.abs().max()) <= 3.1415928
+        st = scene_cpu.generate(t, p.goal_quaternions)
+        scene_cpu.load(st); scene_gpu.load(st)
+        p.post_physics_step(); task.post_physics_step()
+        assert_close(f"step {t} obs", task.obs_buf, p.obs_buf)
+        assert torch.equal(task.reset_buf.cpu(), p.reset_buf)

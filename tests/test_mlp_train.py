@@ -133,53 +133,165 @@ def test_whole_update_step_with_normalisation_and_adam():
     assert float((step - step_ref).abs().max()) <= 2.05 * 3e-4
 
 
-def test_ppo_updater_epoch_tracks_the_all_torch_loop():
-    """PpoUpdater (GAE, advantage normalisation, contiguous minibatches, tcgen05 gradients, clip + Adam) against the same loop in
-    stock torch on a copy of the model: after one mini-epoch the parameter steps point the same way and the value loss went down."""
+def _synthetic_rollout(model, buf, seed, dev="cuda:0", value_denorm=None):
+    """Fills ``buf`` with a rollout under the current policy in rl_games' play_steps order (T writes + finish)."""
+    T, N = buf.horizon, buf.num_envs
+    g = torch.Generator(device=dev).manual_seed(seed)
+    log_std = model.log_std_parameter.detach().clone()
+    with torch.no_grad():
+        for t in range(T + 1):
+            obs = torch.randn(N, 64, device=dev, generator=g).clamp(-5, 5)
+            mu, value, _ = model.reference_forward(obs)
+            rew = torch.randn(N, device=dev, generator=g)
+            dones = (torch.rand(N, device=dev, generator=g) < 0.02).long()
+            if t == T:
+                last_v, last_d = buf.finish(rew, value.contiguous(), dones, value_denorm=value_denorm)
+            else:
+                buf.write(t, obs, mu.contiguous(), value.contiguous(), log_std, rew, dones, noise=torch.randn(N, 12, device=dev, generator=g),
+                          value_denorm=value_denorm)
+    return last_v.clone(), last_d.clone()
+
+
+def _torch_train_epoch(ref_model, td, last_v, last_d, T, N, MB, mini_epochs, lr, kl_threshold, normalize_value, value_rms=None):
+    """rl_games train_epoch in stock torch + the oracle restatements (fp32): prepare_dataset, mini-epochs, legacy adaptive schedule."""
+    from oracle import port_policy as pp
+    adv, ret = pp.gae_rlgames(td["rewards"].cpu(), td["values"].cpu(), td["dones"].cpu(), last_v.cpu(), last_d.cpu())
+    values = td["values"].cpu()
+    if normalize_value:
+        value_rms = pp.rms_update(value_rms, values.reshape(-1, 1))
+        values = pp.rms_normalise(value_rms, values)
+        value_rms = pp.rms_update(value_rms, ret.reshape(-1, 1))
+        ret_n = pp.rms_normalise(value_rms, ret)
+    else:
+        ret_n = ret
+    adv = pp.normalize_advantages(adv)
+    fl = lambda x: x.reshape(T * N, *x.shape[2:]).cuda()
+    obs, actions, nlp = fl(td["obses"]), fl(td["actions"]), fl(td["neglogpacs"])
+    mus = fl(td["mus"]).clone()
+    advs, vals, rets = fl(adv), fl(values), fl(ret_n)
+    nmb = T * N // MB
+    old_ls = ref_model.log_std_parameter.detach().clone().expand(nmb, 12).clone()
+    ref_params = list(ref_model.parameters())
+    opt = torch.optim.Adam(ref_params, lr=lr, eps=1e-8)
+    kls, lrs = [], []
+    for _ in range(mini_epochs):
+        for i in range(nmb):
+            sl = slice(i * MB, (i + 1) * MB)
+            mu, value, ls = ref_model.reference_forward(obs[sl])
+            loss, info = pp.ppo_loss(mu, value.view(-1), ls, actions[sl], nlp[sl], advs[sl], vals[sl], rets[sl], mus[sl], old_ls[i])
+            opt.zero_grad()
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(ref_params, 1.0)
+            opt.step()
+            mus[sl] = mu.detach()                                  # dataset.update_mu_sigma
+            old_ls[i] = ls.detach()
+            kls.append(float(info["kl"]))
+            if kl_threshold is not None:
+                lr = pp.adaptive_lr(lr, kls[-1], kl_threshold)
+                for gr in opt.param_groups:
+                    gr["lr"] = lr
+            lrs.append(lr)
+    return ret, adv, value_rms, kls, lrs
+
+
+@pytest.mark.parametrize("normalize_value", [False, True])
+def test_ppo_updater_tracks_the_all_torch_train_epoch(normalize_value):
+    """PpoUpdater with the reference yaml's settings (5 mini-epochs, adaptive legacy schedule at kl_threshold 0.008, update_mu_sigma,
+    normalize_value) against rl_games' train_epoch in stock torch on a copy of the model: same learning-rate trajectory, parameter
+    steps pointing the same way, and — the stale-weights check — the kernels' forward after the update agrees with the UPDATED
+    fp32 masters."""
     from locomanipulationrl_b200.policy.mlp import MlpActorCritic
     from locomanipulationrl_b200.ppo import PpoUpdater
-    from locomanipulationrl_b200.rollout import RolloutBuffer
     from oracle import port_policy as pp
-    T, N, MB = 8, 2048, 4096
+    T, N, MB, EPOCHS, LR = 8, 2048, 4096, 5, 3e-3                  # a rate high enough that the schedule has to act
     torch.manual_seed(11)
     model, ref_model = MlpActorCritic(device="cuda:0"), MlpActorCritic(device="cuda:0")
     ref_model.load_state_dict(model.state_dict())
+    from locomanipulationrl_b200.rollout import RolloutBuffer
     buf = RolloutBuffer(T, N, reward_scale=1.0)
-    g = torch.Generator(device="cuda").manual_seed(3)
-    log_std = model.log_std_parameter.detach().clone()
-    with torch.no_grad():
-        for t in range(T):                                   # a synthetic rollout under the current policy
-            obs = torch.randn(N, 64, device="cuda", generator=g).clamp(-5, 5)
-            mu, value, _ = model.reference_forward(obs)
-            buf.write(t, obs, mu.contiguous(), value.contiguous(), log_std, torch.randn(N, device="cuda", generator=g),
-                      (torch.rand(N, device="cuda", generator=g) < 0.02).long(), noise=torch.randn(N, 12, device="cuda", generator=g))
-    last_v = torch.randn(N, device="cuda", generator=g)
-    last_d = torch.zeros(N, device="cuda")
+    up = PpoUpdater(model, buf, minibatch_size=MB, mini_epochs=EPOCHS, lr=LR, normalize_value=normalize_value)
+    last_v, last_d = _synthetic_rollout(model, buf, 3, value_denorm=up.value_denorm)
     td = {k: v.clone() for k, v in buf.tensor_dict.items()}
     before = torch.cat([p.detach().reshape(-1) for p in ref_model.parameters()]).clone()
-    # ---- all-torch loop
-    adv, ret = pp.gae_rlgames(td["rewards"].cpu(), td["values"].cpu(), td["dones"].cpu(), last_v.cpu(), last_d.cpu())
-    adv, ret = adv.cuda(), ret.cuda()
-    adv = (adv - adv.mean()) / (adv.std() + 1e-8)
-    fl = lambda x: x.reshape(T * N, *x.shape[2:])
-    ref_params = list(ref_model.parameters())
-    opt = torch.optim.Adam(ref_params, lr=3e-4, eps=1e-8)
-    c_first = c_last = None
-    for i in range(T * N // MB):
-        sl = slice(i * MB, (i + 1) * MB)
-        mu, value, ls = ref_model.reference_forward(fl(td["obses"])[sl])
-        loss, info = pp.ppo_loss(mu, value.view(-1), ls, fl(td["actions"])[sl], fl(td["neglogpacs"])[sl], fl(adv)[sl], fl(td["values"])[sl], fl(ret)[sl],
-                                 fl(td["mus"])[sl], log_std)
-        opt.zero_grad()
-        loss.backward()
-        torch.nn.utils.clip_grad_norm_(ref_params, 1.0)
-        opt.step()
-    step_ref = torch.cat([p.detach().reshape(-1) for p in ref_params]) - before
-    # ---- ours
-    up = PpoUpdater(model, buf, minibatch_size=MB, mini_epochs=1, lr=3e-4, kl_threshold=None)
+    probe = torch.randn(4096, 64, device="cuda").clamp(-5, 5)
+    mu_before = model(probe)[0].clone()
+    ret, adv, vrms, kls, lrs = _torch_train_epoch(ref_model, td, last_v, last_d, T, N, MB, EPOCHS, LR, 0.008, normalize_value,
+                                                  pp.rms_new(1) if normalize_value else None)
     stats = up.update(last_v, last_d)
+    assert torch.isfinite(stats).all()
+    # prepare_dataset
+    if normalize_value:
+        assert_close("normalised returns", up.returns, pp.rms_normalise(vrms, ret), rtol=1e-5, atol=1e-5)
+        assert_close("value normaliser mean", up.value_rms.running_mean, vrms["mean"], rtol=1e-6, atol=1e-6)
+        assert_close("value normaliser var", up.value_rms.running_var, vrms["var"], rtol=1e-5, atol=1e-6)
+        assert_close("value_denorm", up.value_denorm, torch.stack([vrms["mean"].float()[0], torch.sqrt(vrms["var"].float() + 1e-5)[0]]), rtol=1e-5, atol=1e-6)
+    else:
+        assert_close("GAE returns inside the updater", up.returns, ret, rtol=1e-5, atol=1e-5)
+    assert_close("normalised advantages", up.advantages, adv, rtol=1e-4, atol=1e-5)
+    # schedule: the decisions are only comparable while no reference KL sits at a threshold
+    margin = min(min(abs(k - 0.016) / 0.016, abs(k - 0.004) / 0.004) for k in kls)
+    assert len(set(lrs)) > 1, "the test rollout must make the schedule act"
+    if margin > 0.15:
+        assert abs(up.opt.lr / lrs[-1] - 1.0) < 1e-5, (up.opt.lr, lrs[-1], kls)
+    else:
+        assert 0.4 < up.opt.lr / lrs[-1] < 2.5, (up.opt.lr, lrs[-1])
+    # parameters
+    step_ref = torch.cat([p.detach().reshape(-1) for p in ref_model.parameters()]) - before
     step = up.flat - before
     cos = torch.nn.functional.cosine_similarity(step, step_ref, dim=0)
-    assert float(cos) > 0.97, float(cos)
-    assert torch.isfinite(stats).all()
-    assert_close("GAE returns inside the updater", up.returns, ret, rtol=1e-5, atol=1e-5)
+    assert float(cos) > 0.9, float(cos)
+    # the acting policy is the updated one: kernel forward (bf16 blobs) vs the fp32 masters the optimiser wrote
+    mu_k, v_k, _ = model(probe)
+    with torch.no_grad():
+        mu_m, v_m, _ = model.reference_forward(probe)
+    assert_close("mu after the update", mu_k, mu_m, rtol=0, atol=1e-2)
+    assert_close("value after the update", v_k, v_m, rtol=0, atol=1.5e-2)
+    moved = float((mu_m - mu_before).abs().max())
+    assert moved > 0.05, f"the update must move the policy for this check to mean anything ({moved})"
+
+
+def test_mlp_forward_is_differentiable_through_the_kernels():
+    """rl_games calc_gradients / skrl _update run their own torch loss on the module's outputs: under enable_grad the forward is an
+    autograd.Function whose backward is lm_mlp_backward + lm_mlp_wgrad.  Compared with autograd through the fp32 restatement."""
+    from locomanipulationrl_b200.policy.adapters import SkrlShared
+    torch.manual_seed(5)
+    shared = SkrlShared(device="cuda:0")
+    model = shared.core
+    obs = torch.randn(3000, 64, device="cuda").clamp(-5, 5)
+    target_mu, target_v = torch.randn(3000, 12, device="cuda"), torch.randn(3000, 1, device="cuda")
+
+    def loss_of(mu, value, ls):
+        return ((mu - target_mu) ** 2).mean() + 0.5 * ((value - target_v) ** 2).mean() + 0.01 * ls.sum()
+
+    mu, ls, _ = shared.compute({"states": obs}, "policy")
+    value, _ = shared.compute({"states": obs}, "value")
+    assert mu.requires_grad and value.requires_grad
+    # two differentiable calls share one saved-activation workspace: take each backward right after its forward
+    (mu_g,) = torch.autograd.grad(((mu - target_mu) ** 2).mean(), [model.mean_layer.weight], retain_graph=False, allow_unused=True)
+    model.zero_grad()
+    mu, value, ls = model(obs)
+    loss_of(mu, value, ls).backward()
+    got = {k: p.grad.clone() for k, p in model.named_parameters()}
+    model.zero_grad()
+    mu_r, value_r, ls_r = model.reference_forward(obs)
+    loss_of(mu_r, value_r, ls_r).backward()
+    for k, p in model.named_parameters():
+        ref = p.grad
+        scale = float(ref.abs().max()) + 1e-12
+        assert float((got[k] - ref).abs().max()) <= 0.04 * scale + 1e-6, (k, float((got[k] - ref).abs().max()), scale)
+    g_all = torch.cat([got[k].reshape(-1) for k, _ in model.named_parameters()])
+    r_all = torch.cat([p.grad.reshape(-1) for _, p in model.named_parameters()])
+    assert float(torch.nn.functional.cosine_similarity(g_all, r_all, dim=0)) > 0.999
+    # inference path: stale-cache check — the task rewrites obs_buf in place, the second step must not return the first step's heads
+    with torch.no_grad():
+        m1, _, _ = shared.compute({"states": obs}, "policy")
+        v1, _ = shared.compute({"states": obs}, "value")
+        obs.copy_(torch.randn_like(obs).clamp(-5, 5).contiguous())            # torch op: version bump
+        m2, _, _ = shared.compute({"states": obs}, "policy")
+        assert float((m1 - m2).abs().max()) > 1e-3
+        import ctypes
+        torch.cuda.synchronize()
+        lib = model._lib                                                        # a kernel writes through data_ptr: NO version bump
+        lib.lm_clamp_copy(obs.data_ptr(), obs.data_ptr(), obs.numel(), 0.01, torch.cuda.current_stream().cuda_stream)
+        m3, _, _ = shared.compute({"states": obs}, "policy")
+        assert float((m3 - m2).abs().max()) > 1e-3
