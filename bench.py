@@ -253,6 +253,12 @@ class Pipeline:
         # kernels of liblm_b200.so per step: k_pre, k_post_lean, policy forward (k_reset_count only runs when reset_buf was
         # written from outside); the gnn_gae workload adds k_rollout_write every step and lm_gae once per HORIZON steps
         self.launches_per_step = 3
+        self.use_sink = not os.environ.get("LM_BENCH_NO_SINK")
+        self.overlap_pre = self.use_sink and self.w["policy"] == "mlp" and not os.environ.get("LM_BENCH_NO_OVERLAP")
+        self.side = torch.cuda.Stream(device=device)
+        self.graph_parity = None
+        if self.overlap_pre:                             # prime: the first step's pre_physics_step (later ones ride next to the policy forward)
+            self.task.pre_physics_step(self.actions, self.uniforms[0])
         if self.w["policy"] == "gnn":
             from locomanipulationrl_b200.rollout import RolloutBuffer, RunningMeanStd
             T = HORIZON
@@ -265,11 +271,28 @@ class Pipeline:
 
     def step_eager(self, i, t=0):
         task = self.task
-        task.pre_physics_step(self.actions, self.uniforms[i])
+        if self.overlap_pre:
+            # MLP workload with the action sink: the head epilogue delivers action = mean into the task, so the only thing left of the
+            # NEXT pre_physics_step is its reset half, which depends on this post step alone: it runs on a second stream next to the
+            # policy forward (the persistent MLP CTAs leave room for its 128-thread CTAs on every SM) and joins before the next step.
+            task.set_up_scene(self.scenes[i])           # "physics": the next state set becomes the live views
+            task.post_physics_step()
+            cur = torch.cuda.current_stream()
+            sink = task.action_sink()
+            self.side.wait_stream(cur)
+            with torch.cuda.stream(self.side):
+                task.pre_physics_step(None, self.uniforms[(i + 1) % STATE_SETS])
+            self.policy(task.obs_buf, norm_mean=self.norm_mean, norm_inv_std=self.norm_inv_std, out=(self.mu, self.value), sink=sink)
+            cur.wait_stream(self.side)
+            return
+        # action sink (default): the kernel that produced the actions (MLP head epilogue / rollout writer) already delivered them into
+        # the task's buffers (clamp, current_actions, joint targets), so pre_physics_step runs its reset half only
+        task.pre_physics_step(None if self.use_sink else self.actions, self.uniforms[i])
         task.set_up_scene(self.scenes[i])               # "physics": the next state set becomes the live views
         task.post_physics_step()
         if self.w["policy"] == "mlp":
-            self.policy(task.obs_buf, norm_mean=self.norm_mean, norm_inv_std=self.norm_inv_std, out=(self.mu, self.value))
+            self.policy(task.obs_buf, norm_mean=self.norm_mean, norm_inv_std=self.norm_inv_std, out=(self.mu, self.value),
+                        sink=task.action_sink() if self.use_sink else None)
         else:
             self.policy(task.obs_buf, out=(self.mu, self.value))
             k = t % HORIZON
@@ -286,7 +309,7 @@ class Pipeline:
         statistics folded in, actions handed to the next pre_physics_step: one launch (lm_rollout_write)."""
         task = self.task
         self.rollout.write(k, task.obs_buf, self.mu, self.value, self.log_std, task.rew_buf, task.reset_buf, noise=None,
-                           actions_out=self.actions, obs_stats=self.obs_stats)
+                           actions_out=self.actions, obs_stats=self.obs_stats, sink=task.action_sink() if self.use_sink else None)
 
     def capture(self, after_step=None):
         """One CUDA graph per state set (parity of the action ring alternates, STATE_SETS is even).  ``after_step(i)``: called after
@@ -303,17 +326,20 @@ class Pipeline:
                     after_step(i)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        self.graphs = []
+        self.graphs, self.graph_parity = [], []
         for i in range(STATE_SETS):
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 self.step_eager(i)
             self.graphs.append(g)
+            self.graph_parity.append(self.lib.lm_task_step_parity(self.task._handle))
         torch.cuda.synchronize()
 
     def step(self, t):
         if self.graphs is not None:
             self.graphs[t % STATE_SETS].replay()
+            # replays skip the host side of pre_physics_step: keep the handle's ring parity in step for host-side readers
+            self.lib.lm_task_set_step_parity(self.task._handle, self.graph_parity[t % STATE_SETS])
         else:
             self.step_eager(t % STATE_SETS, t)
 
@@ -477,11 +503,12 @@ def cuda_arm(args):
             task.post_physics_step()
 
         def pre_only(i):
-            task.pre_physics_step(pipe.actions, pipe.uniforms[i % STATE_SETS])
+            task.pre_physics_step(None if pipe.use_sink else pipe.actions, pipe.uniforms[i % STATE_SETS])
 
         def policy_only(i):
             if pipe.w["policy"] == "mlp":
-                pipe.policy(task.obs_buf, norm_mean=pipe.norm_mean, norm_inv_std=pipe.norm_inv_std, out=(pipe.mu, pipe.value))
+                pipe.policy(task.obs_buf, norm_mean=pipe.norm_mean, norm_inv_std=pipe.norm_inv_std, out=(pipe.mu, pipe.value),
+                            sink=task.action_sink() if pipe.use_sink else None)
             else:
                 pipe.policy(task.obs_buf, out=(pipe.mu, pipe.value))
 
@@ -614,7 +641,8 @@ def cuda_arm(args):
                 "data": "synthetic",
                 "config": {"workload": pipe.w["desc"], "envs_per_gpu": n, "global_envs": n * world, "parallelism": f"env-shard x{world}",
                            "l2": f"{STATE_SETS} rotating synthetic state sets (> L2) - inputs larger than L2",
-                           "cuda_graphs": pipe.graphs is not None, "comm": (f"one stat + gradient-arena all-reduce (58,651 fp32) every {horizon} steps, "
+                           "cuda_graphs": pipe.graphs is not None, "action_sink": pipe.use_sink,
+                           "pre_reset_overlaps_policy": pipe.overlap_pre, "comm": (f"one stat + gradient-arena all-reduce (58,651 fp32) every {horizon} steps, "
                                     + ("one-shot NVLink peer-memory kernel (lm_comm_allreduce)" if peer is not None else "NCCL all_reduce")
                                     + f", {args.comm_stream} stream, CUDA graph") if world > 1 else "none",
                            "timed": f"{reps} rollout horizons of {horizon} steps"},
@@ -658,10 +686,10 @@ def train_arm(pipe, args, world, device, rank, peer):
     def iteration(seed):
         for t in range(T):
             forward()
-            buf.write(t, task.obs_buf, mu, value, log_std, task.rew_buf, task.reset_buf, actions_out=actions, sample_seed=seed,
-                      value_denorm=up.value_denorm)
+            buf.write(t, task.obs_buf, mu, value, log_std, task.rew_buf, task.reset_buf, sample_seed=seed, value_denorm=up.value_denorm,
+                      sink=task.action_sink() if pipe.use_sink else None, actions_out=None if pipe.use_sink else actions)
             i = state["i"] = (state["i"] + 1) % STATE_SETS
-            task.pre_physics_step(actions, pipe.uniforms[i])
+            task.pre_physics_step(None if pipe.use_sink else actions, pipe.uniforms[i])
             task.set_up_scene(pipe.scenes[i])
             task.post_physics_step()
         forward()                                         # value of the observation after the last stored action: GAE's bootstrap

@@ -198,6 +198,23 @@ int lm_task_reset_idx(LmTask* task, const LmRobotViews* loco, const LmRobotViews
 int lm_task_post_step(LmTask* task, const LmRobotViews* loco, const LmRobotViews* mani,
                       const float* env_pos, const LmTaskBuffers* buf, void* stream);
 
+/* Action sink: the action half of pre_physics_step (adapter clamp, current_actions stash, take_action) handed to the kernel that
+ * produces the actions.  lm_task_action_sink fills the struct for the NEXT pre_physics_step (call it after lm_task_post_step);
+ * lm_mlp_forward_sink (evaluation: action = policy mean) and lm_rollout_write (LmRolloutStep.sink: action = the sample) then
+ * deliver the actions into the task's buffers themselves, and the next lm_task_pre_step is called with actions == NULL: it runs
+ * only the reset half (reset scan, reset_idx scatter, goal resample).  Velocity / position control modes (the effort mode's
+ * 20-wide scatter and the explicit-PD files keep the plain path). */
+typedef struct LmActionSink {
+  float* ring_next;      /* [N,12] the slot of actions_ring the next pre_physics_step treats as current_actions */
+  float* targets_loco;   /* [H,12] or NULL */
+  float* targets_mani;   /* [H,12] or NULL */
+  int32_t loco_envs;     /* envs [0, loco_envs) drive the locomotion robot's targets, the rest the manipulation robot's */
+  int32_t clamp_actions; int32_t zero_actions; int32_t pad_;
+  float clip_actions; float action_limit;
+} LmActionSink;
+int lm_task_set_step_parity(LmTask* task, int parity);   /* after replaying a captured step: the ring slot (lm_task_step_parity at capture) it used */
+int lm_task_action_sink(LmTask* task, const LmRobotViews* loco, const LmRobotViews* mani, const LmTaskBuffers* buf, LmActionSink* out);
+
 /* _process_data of the vec-env adapter (envs/vec_env_rlgames.py:41-46): out = clamp(in, ±clip). */
 int lm_clamp_copy(const float* in, float* out, int64_t count, float clip, void* stream);
 
@@ -241,6 +258,9 @@ int lm_mlp_pack(LmMlp* mlp, const float* w1, const float* b1, const float* w2, c
  * 1/(sqrt(var) + 1e-8), clamp 5).  Outputs mu [N,12], value [N] fp32. */
 int lm_mlp_forward(LmMlp* mlp, const float* obs, const float* norm_mean, const float* norm_inv_std,
                    float norm_clip, float* mu, float* value, int32_t n, void* stream);
+/* lm_mlp_forward whose head epilogue also delivers action = mean into the task (LmActionSink above). */
+int lm_mlp_forward_sink(LmMlp* mlp, const float* obs, const float* norm_mean, const float* norm_inv_std, float norm_clip, float* mu,
+                        float* value, int32_t n, const LmActionSink* sink, void* stream);
 
 /* Diagnostic: when stamps_dev != NULL (device buffer of >= 256 int64), CTA 0 of every following lm_mlp_forward records
  * clock64() at its pipeline stages (see csrc/lm_mlp.cu `stamp`).  NULL switches it off (the default). */
@@ -257,6 +277,13 @@ int lm_gnn_forward(LmGnn* gnn, const float* obs, float* mu, float* value, int32_
 /* The same forward on tcgen05 tensor cores: bf16 operands (weights and node features), fp32 accumulation, fp32 input
  * layers and heads; logits within 1e-2 of lm_gnn_forward (north_star tolerance for bf16 policy logits). */
 int lm_gnn_forward_bf16(LmGnn* gnn, const float* obs, float* mu, float* value, int32_t n, void* stream);
+/* PPO update of the GNN policy: gradients of a loss w.r.t. all 20 parameter tensors (the order of lm_gnn_pack) from
+ * dLoss/dmu [n,12] and dLoss/dvalue [n] (lm_ppo_loss).  One kernel recomputes the fp32 forward per env and walks the limb graph
+ * backwards (max-aggregation routes to the first arg-max in-edge); weight gradients accumulate per CTA in shared memory and are
+ * summed in CTA order.  workspace: workspace_ctas * lm_gnn_grad_workspace_floats() floats.  Gradients are WRITTEN (not accumulated). */
+int32_t lm_gnn_grad_workspace_floats(void);
+int lm_gnn_backward(LmGnn* gnn, const float* obs, const float* grad_mu, const float* grad_value, int32_t n, float* workspace,
+                    int32_t workspace_ctas, float* const* grads, int32_t num_grads, void* stream);
 /* Diagnostic, as lm_mlp_set_timeline: clock64() stamps of CTA 0 of every following lm_gnn_forward_bf16 (>= 512 int64). */
 int lm_gnn_set_timeline(LmGnn* gnn, long long* stamps_dev);
 
@@ -345,6 +372,7 @@ typedef struct LmRolloutStep {   /* one env step; device pointers */
   /* normalize_value (cfg/train/*PPO.yaml:47): {mean, std} from lm_rms_export_denorm; values are stored as std * clamp(v, +-5) + mean.
    * NULL: stored as they come */
   const float* value_denorm;
+  const LmActionSink* sink;   /* NULL, or: the sampled actions also go straight into the task (see LmActionSink) */
 } LmRolloutStep;
 typedef struct LmRolloutBuffers {
   float* obses;    /* [T,N,64] */

@@ -74,7 +74,7 @@ class LmRunningStats(C.Structure):
 class LmRolloutStep(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("obs", "mu", "value", "log_std", "noise", "rew", "dones")] + \
                [("noise_seed", C.c_uint64), ("noise_step", C.c_uint64), ("sample_in_kernel", _i32), ("pad_", _i32),
-                ("time_outs", C.c_void_p), ("gamma", _f), ("pad2_", _i32), ("value_denorm", C.c_void_p)]
+                ("time_outs", C.c_void_p), ("gamma", _f), ("pad2_", _i32), ("value_denorm", C.c_void_p), ("sink", C.c_void_p)]
 
 
 class LmRolloutBuffers(C.Structure):
@@ -107,6 +107,11 @@ class LmPpoBatch(C.Structure):
                 ("clip_value", _i32), ("update_old", _i32)]
 
 
+class LmActionSink(C.Structure):
+    _fields_ = [("ring_next", C.c_void_p), ("targets_loco", C.c_void_p), ("targets_mani", C.c_void_p), ("loco_envs", _i32),
+                ("clamp_actions", _i32), ("zero_actions", _i32), ("pad_", _i32), ("clip_actions", _f), ("action_limit", _f)]
+
+
 class LmAdamSchedule(C.Structure):
     _fields_ = [("lr", C.c_void_p), ("kl", C.c_void_p), ("kl_scale", _f), ("kl_threshold", _f), ("lr_min", _f), ("lr_max", _f)]
 
@@ -121,6 +126,7 @@ SYMBOLS = {
     "lm_task_create": (_vp, [C.POINTER(LmTaskParams), C.c_int]),
     "lm_task_destroy": (None, [_vp]),
     "lm_task_step_parity": (C.c_int, [_vp]),
+    "lm_task_set_step_parity": (C.c_int, [_vp, C.c_int]),
     "lm_task_set_clamp_observations": (C.c_int, [_vp, C.c_int]),
     "lm_task_invalidate_reset_scan": (C.c_int, [_vp]),
     "lm_task_set_timeline": (C.c_int, [_vp, _vp]),
@@ -137,6 +143,8 @@ SYMBOLS = {
     "lm_mlp_destroy": (None, [_vp]),
     "lm_mlp_pack": (C.c_int, [_vp] * 11 + [_vp]),
     "lm_mlp_forward": (C.c_int, [_vp, _vp, _vp, _vp, _f, _vp, _vp, _i32, _vp]),
+    "lm_mlp_forward_sink": (C.c_int, [_vp, _vp, _vp, _vp, _f, _vp, _vp, _i32, C.POINTER(LmActionSink), _vp]),
+    "lm_task_action_sink": (C.c_int, [_vp, C.POINTER(LmRobotViews), C.POINTER(LmRobotViews), C.POINTER(LmTaskBuffers), C.POINTER(LmActionSink)]),
     "lm_mlp_set_timeline": (C.c_int, [_vp, _vp]),
     "lm_gnn_create": (_vp, [C.c_int]),
     "lm_gnn_destroy": (None, [_vp]),
@@ -144,6 +152,8 @@ SYMBOLS = {
     "lm_gnn_forward": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _vp]),
     "lm_gnn_forward_bf16": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _vp]),
     "lm_gnn_set_timeline": (C.c_int, [_vp, _vp]),
+    "lm_gnn_grad_workspace_floats": (_i32, []),
+    "lm_gnn_backward": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _vp, _i32, C.POINTER(_vp), _i32, _vp]),
     "lm_rollout_create": (_vp, [C.c_int]),
     "lm_rollout_destroy": (None, [_vp]),
     "lm_rollout_write": (C.c_int, [_vp, C.POINTER(LmRolloutStep), C.POINTER(LmRolloutBuffers), _i32, _vp, C.POINTER(LmRunningStats), _vp]),
@@ -209,7 +219,7 @@ def load(path: Optional[str] = None) -> C.CDLL:
         fn.argtypes = args
     if lib.lm_abi_version() != 1:
         raise LmError("liblm_b200.so ABI version mismatch")
-    for which, struct in enumerate((LmTaskParams, LmRobotViews, LmTaskBuffers, LmHostStep, LmPdState, LmRunningStats, LmRolloutStep, LmRolloutBuffers, LmPpoBatch, LmNoiseSpec, LmNoiseState, LmCustomController, LmAdamSchedule)):
+    for which, struct in enumerate((LmTaskParams, LmRobotViews, LmTaskBuffers, LmHostStep, LmPdState, LmRunningStats, LmRolloutStep, LmRolloutBuffers, LmPpoBatch, LmNoiseSpec, LmNoiseState, LmCustomController, LmAdamSchedule, LmActionSink)):
         if lib.lm_struct_size(which) != C.sizeof(struct):
             raise LmError(f"struct layout mismatch for {struct.__name__}: C {lib.lm_struct_size(which)} vs ctypes {C.sizeof(struct)}")
     _lib = lib

@@ -16,7 +16,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "liblm_b200.so")
 STAMP = os.path.join(PKG_DIR, "liblm_b200.stamp")
-SOURCES = ["lm_task.cu", "lm_pd.cu", "lm_gae.cu", "lm_mlp.cu", "lm_gnn.cu", "lm_gnn_tc.cu", "lm_rollout.cu", "lm_ppo.cu", "lm_noise.cu", "lm_task_cc.cu", "lm_mlp_train.cu", "lm_comm.cu"]
+SOURCES = ["lm_task.cu", "lm_pd.cu", "lm_gae.cu", "lm_mlp.cu", "lm_gnn.cu", "lm_gnn_tc.cu", "lm_rollout.cu", "lm_ppo.cu", "lm_noise.cu", "lm_task_cc.cu", "lm_mlp_train.cu", "lm_comm.cu", "lm_gnn_train.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--shared",
               "-Xcompiler", "-fPIC,-O2", "-cudart", "static", "--expt-relaxed-constexpr"]
 

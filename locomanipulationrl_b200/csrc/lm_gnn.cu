@@ -323,7 +323,7 @@ LmGnn* lm_gnn_create(int device) {
   if (prop.major != 10) { lm_set_error("lm_gnn_create: library is sm_100a only (device sm_%d%d)", prop.major, prop.minor); return nullptr; }
   cudaSetDevice(device);
   LmGnn* g = new LmGnn();
-  g->device = device; g->sm_count = prop.multiProcessorCount; g->ready = false; g->packed = nullptr; g->tc_blob = nullptr; g->timeline = nullptr;
+  g->device = device; g->sm_count = prop.multiProcessorCount; g->ready = false; g->packed = nullptr; g->tc_blob = nullptr; g->train_blob = nullptr; g->timeline = nullptr;
   if (cudaMalloc(&g->packed, PACKED_FLOATS * sizeof(float)) != cudaSuccess) { lm_set_error("lm_gnn_create: cudaMalloc failed"); delete g; return nullptr; }
   cudaMemset(g->packed, 0, PACKED_FLOATS * sizeof(float));
   e = cudaFuncSetAttribute(k_gnn_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
@@ -336,6 +336,7 @@ void lm_gnn_destroy(LmGnn* g) {
   if (!g) return;
   cudaFree(g->packed);
   lm_gnn_tc_release(g);
+  lm_gnn_train_release(g);
   delete g;
 }
 
@@ -364,6 +365,8 @@ int lm_gnn_pack(LmGnn* g, const float* const* w, int32_t num_tensors, void* stre
   k_copy<<<1, 32, 0, s>>>(w[19], P + B_HEAD + 1, 1);
   const int rc = lm_gnn_tc_pack(g, w, stream);          // the same tensors as bf16 tensor-core operands (lm_gnn_forward_bf16)
   if (rc != LM_OK) return rc;
+  const int rc2 = lm_gnn_train_pack(g, w, stream);      // and as the fp32 image of the update kernel (lm_gnn_backward)
+  if (rc2 != LM_OK) return rc2;
   g->ready = true;
   return lm_check_launch("lm_gnn_pack");
 }

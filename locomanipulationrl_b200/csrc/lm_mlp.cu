@@ -16,10 +16,12 @@
 //     normalised/clamped and written as the bf16 A0 operand in the bubble between the layer-1 and layer-2 epilogues.
 // Activations never touch HBM; per env the kernel reads 256 B and writes 52 B.
 #include <cuda_bf16.h>
+#include <string.h>
 
 #include "lm_common.cuh"
 #include "lm_host.h"
 #include "lm_mlp.h"
+#include "lm_sink.cuh"
 #include "lm_tc.cuh"
 
 namespace lm {
@@ -129,6 +131,8 @@ struct Args {
   long long* timeline;         // diagnostic: clock64 stamps of CTA 0 (NULL in production launches)
   // training forward (k_mlp_forward<true>): the bf16 operands of every layer saved per tile for the backward kernels (lm_mlp_train.cu)
   uint8_t *save_a0, *save_a1, *save_a2, *save_a3;
+  // evaluation with an action sink: the head epilogue also delivers action = mean into the task's buffers (lm_sink.cuh)
+  LmActionSink sink; int has_sink;
 };
 
 // diagnostic timeline (lm_mlp_forward_timeline): slot k <- clock64(), first writer wins per launch
@@ -168,8 +172,10 @@ __device__ __forceinline__ void obs_convert(const Args& a, int tile, int tid, co
   }
 }
 
-// head epilogue of one lane-group warp: 16 accumulator columns -> +bias -> mu[12], value
-__device__ __forceinline__ void epilogue_head(const Args& a, uint32_t tmem_acc, const float* __restrict__ biash, int tile, int g, int lane) {
+// head epilogue of one lane-group warp: 16 accumulator columns -> +bias -> mu[12], value.  With an action sink the three
+// destinations of a row (mu / value, current_actions, joint targets) are written by three different column-quarter warps
+// (q = 0, 1, 2 all read the same 16 accumulator columns), so the stores of a tile leave in parallel instead of in a row.
+__device__ __forceinline__ void epilogue_head(const Args& a, uint32_t tmem_acc, const float* __restrict__ biash, int tile, int g, int lane, int q) {
   uint32_t acc[16];
   tmem_ld16(tmem_acc + ((uint32_t)(g * 32) << 16), acc);
   tmem_wait();
@@ -180,11 +186,17 @@ __device__ __forceinline__ void epilogue_head(const Args& a, uint32_t tmem_acc, 
     float o[13];
 #pragma unroll
     for (int j = 0; j < 13; ++j) o[j] = __uint_as_float(acc[j]) + biash[j];
-    float4* m = reinterpret_cast<float4*>(a.mu + (size_t)(row0 + row) * 12);
-    m[0] = make_float4(o[0], o[1], o[2], o[3]);
-    m[1] = make_float4(o[4], o[5], o[6], o[7]);
-    m[2] = make_float4(o[8], o[9], o[10], o[11]);
-    a.value[row0 + row] = o[12];
+    if (q == 0) {
+      float4* m = reinterpret_cast<float4*>(a.mu + (size_t)(row0 + row) * 12);
+      m[0] = make_float4(o[0], o[1], o[2], o[3]);
+      m[1] = make_float4(o[4], o[5], o[6], o[7]);
+      m[2] = make_float4(o[8], o[9], o[10], o[11]);
+      a.value[row0 + row] = o[12];
+    } else {
+#pragma unroll
+      for (int qq = 0; qq < 3; ++qq)
+        sink_store(a.sink, row0 + row, qq, make_float4(o[4 * qq], o[4 * qq + 1], o[4 * qq + 2], o[4 * qq + 3]), q == 1, q == 2);
+    }
   }
 }
 
@@ -336,7 +348,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_mlp_forward(const Args a) {
       if (it >= 2) {
         mbar_wait(&bar_acch, ph);
         tc_fence_after();
-        if (q == 0) epilogue_head(a, tmem + ACCH_COL, biash, tile - 2 * stride, g, lane);
+        if (q == 0 || (a.has_sink && q < 3)) epilogue_head(a, tmem + ACCH_COL, biash, tile - 2 * stride, g, lane, q);
       }
       // ---- E3(t-1): TMEM[128 x 64] -> A3
       if (st) stamp(a, 8 + 8 * it + 4);
@@ -357,7 +369,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_mlp_forward(const Args a) {
     if (n_loc >= 2) {
       mbar_wait(&bar_acch, n_loc & 1);
       tc_fence_after();
-      if (q == 0) epilogue_head(a, tmem + ACCH_COL, biash, tile0 + (n_loc - 2) * stride, g, lane);
+      if (q == 0 || (a.has_sink && q < 3)) epilogue_head(a, tmem + ACCH_COL, biash, tile0 + (n_loc - 2) * stride, g, lane, q);
     }
     if (n_loc >= 1) {
       mbar_wait(&bar_acc3, (n_loc - 1) & 1);
@@ -365,7 +377,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_mlp_forward(const Args a) {
       epilogue_hidden<1, 1>(tmem + ACC3_COL, bias3, A3, bar_act3, nullptr, 0, g, q, lane, g3(tile0 + (n_loc - 1) * stride));
       mbar_wait(&bar_acch, (n_loc - 1) & 1);
       tc_fence_after();
-      if (q == 0) epilogue_head(a, tmem + ACCH_COL, biash, tile0 + (n_loc - 1) * stride, g, lane);
+      if (q == 0 || (a.has_sink && q < 3)) epilogue_head(a, tmem + ACCH_COL, biash, tile0 + (n_loc - 1) * stride, g, lane, q);
     }
   }
   tc_fence_before();
@@ -460,7 +472,14 @@ int lm_mlp_pack(LmMlp* m, const float* w1, const float* b1, const float* w2, con
 
 int lm_mlp_forward(LmMlp* m, const float* obs, const float* norm_mean, const float* norm_inv_std, float norm_clip, float* mu,
                    float* value, int32_t n, void* stream) {
+  return lm_mlp_forward_sink(m, obs, norm_mean, norm_inv_std, norm_clip, mu, value, n, nullptr, stream);
+}
+
+int lm_mlp_forward_sink(LmMlp* m, const float* obs, const float* norm_mean, const float* norm_inv_std, float norm_clip, float* mu,
+                        float* value, int32_t n, const LmActionSink* sink, void* stream) {
   if (!m || !obs || !mu || !value || n <= 0) return lm_fail(LM_ERR_BAD_ARG, "lm_mlp_forward: bad argument");
+  if (sink && (!sink->ring_next || (((uintptr_t)sink->ring_next | (uintptr_t)sink->targets_loco | (uintptr_t)sink->targets_mani) & 15)))
+    return lm_fail(LM_ERR_BAD_ARG, "lm_mlp_forward_sink: sink buffers must be non-NULL / 16-byte aligned");
   if (!m->packed) return lm_fail(LM_ERR_BAD_ARG, "lm_mlp_forward: weights not packed (call lm_mlp_pack)");
   if ((((uintptr_t)obs) | ((uintptr_t)mu)) & 15) return lm_fail(LM_ERR_ALIGNMENT, "lm_mlp_forward: obs/mu must be 16-byte aligned");
   if ((norm_mean == nullptr) != (norm_inv_std == nullptr)) return lm_fail(LM_ERR_BAD_ARG, "lm_mlp_forward: give both norm vectors or neither");
@@ -468,6 +487,8 @@ int lm_mlp_forward(LmMlp* m, const float* obs, const float* norm_mean, const flo
   a.blob = m->blob; a.obs = obs; a.norm_mean = norm_mean; a.norm_inv_std = norm_inv_std; a.norm_clip = norm_clip;
   a.mu = mu; a.value = value; a.n = n; a.num_tiles = (n + TM - 1) / TM; a.timeline = m->timeline;
   a.save_a0 = a.save_a1 = a.save_a2 = a.save_a3 = nullptr;
+  a.has_sink = sink != nullptr;
+  if (sink) a.sink = *sink; else memset(&a.sink, 0, sizeof(a.sink));
   const int grid = a.num_tiles < m->sm_count ? a.num_tiles : m->sm_count;
   // The resident-weight TMA is issued before pdl_wait(): allowed only while the blob is not being rewritten upstream.
   const bool pdl = !m->fresh_pack;
@@ -490,6 +511,7 @@ int lm_mlp_forward_train(LmMlp* m, const float* obs, const float* norm_mean, con
   a.blob = m->blob; a.obs = obs; a.norm_mean = norm_mean; a.norm_inv_std = norm_inv_std; a.norm_clip = norm_clip;
   a.mu = mu; a.value = value; a.n = n; a.num_tiles = (n + TM - 1) / TM; a.timeline = nullptr;
   a.save_a0 = (uint8_t*)a0; a.save_a1 = (uint8_t*)a1; a.save_a2 = (uint8_t*)a2; a.save_a3 = (uint8_t*)a3;
+  a.has_sink = 0; memset(&a.sink, 0, sizeof(a.sink));
   const int grid = a.num_tiles < m->sm_count ? a.num_tiles : m->sm_count;
   m->fresh_pack = false;
   cudaError_t le = lm_launch(k_mlp_forward<true>, dim3(grid), dim3(THREADS), SMEM_BYTES, (cudaStream_t)stream, false, a);

@@ -12,10 +12,13 @@
 // running mean against cancellation) accumulate in registers, meet per CTA in shared memory as doubles and per grid through
 // the last-CTA pattern, where 64 threads apply the fold.  Phase B is per env: sample the action, its negative log-prob,
 // and the scalar columns.  Algorithmic bytes: 368 read + 368 written per env-step (+48 for actions_out).
+#include <string.h>
+
 #include "lm_common.cuh"
 #include "lm_host.h"
 #include "lm_reduce.cuh"
 #include "lm_rng.cuh"
+#include "lm_sink.cuh"
 
 namespace lm {
 namespace rollout {
@@ -37,6 +40,7 @@ struct WriteArgs {
   // written after env_step(actions[n])): `rewards` / `prev_values` point at slot t - 1, NULL at t = 0.
   float* rewards; const float* prev_values; const long long* time_outs; float gamma;
   const float* value_denorm;            // [2] {mean, sqrt(var + eps)} of the value normaliser, NULL: values stored as they come
+  LmActionSink sink; int has_sink;      // the sampled actions also go straight into the task's buffers (lm_sink.cuh)
   int n; float reward_scale;
   unsigned long long noise_seed, noise_step; int sample_in_kernel;
   Stats st; int has_stats;
@@ -144,6 +148,7 @@ __device__ __forceinline__ void env_emit(const WriteArgs& a, unsigned int e, con
     __stcs(reinterpret_cast<float4*>(a.actions + e * 12) + q, av);
     __stcs(reinterpret_cast<float4*>(a.mus + e * 12) + q, in.mv[q]);
     if (a.actions_out) reinterpret_cast<float4*>(a.actions_out + e * 12)[q] = av;
+    if (a.has_sink) sink_store(a.sink, (int)e, q, av);
   }
   a.neglogp[e] = 0.5f * ss + 11.027262398456072f + lsum;      // 0.5 log(2 pi) * 12
   a.values[e] = denorm_value(a.value_denorm, in.val);
@@ -459,6 +464,8 @@ int lm_rollout_write(LmRollout* r, const LmRolloutStep* step, const LmRolloutBuf
   a.prev_values = t > 0 ? buf->values + (size_t)(t - 1) * n : nullptr;
   a.time_outs = t > 0 ? reinterpret_cast<const long long*>(step->time_outs) : nullptr; a.gamma = step->gamma;
   a.value_denorm = step->value_denorm;
+  a.has_sink = step->sink != nullptr;
+  if (step->sink) a.sink = *step->sink; else memset(&a.sink, 0, sizeof(a.sink));
   a.neglogp = buf->neglogp + (size_t)t * n; a.actions_out = actions_out;
   a.n = buf->num_envs; a.reward_scale = buf->reward_scale;
   a.noise_seed = step->noise_seed; a.noise_step = step->noise_step; a.sample_in_kernel = step->sample_in_kernel;

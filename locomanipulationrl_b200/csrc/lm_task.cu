@@ -252,15 +252,16 @@ __global__ void __launch_bounds__(T) k_pre(const KernelParams kp, const PreArgs 
   const int tile_base = a.scan_base[blockIdx.x / kp.d.scan_per] + a.tile_offsets[blockIdx.x];
   const int nflat4 = tl.n * (LM_NUM_ACT / 4);
   const float* act_g = a.actions + (size_t)tl.e0 * LM_NUM_ACT;
+  const bool have_actions = a.actions != nullptr;       // NULL: delivered by the producing kernel through an LmActionSink
   float4 av[3];
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
     const int i = r + k * T;
-    av[k] = i < nflat4 ? ld_nc_f4(act_g + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    av[k] = (have_actions && i < nflat4) ? ld_nc_f4(act_g + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
 
   // ---- actions: clamp (vec_env_rlgames.py:60), stash as current_actions, take_action (robot.py:444-461)
-  {
+  if (have_actions) {
     float* cur_g = ring_cur + (size_t)tl.e0 * LM_NUM_ACT;
     const float range = sub(P.action_limit, -P.action_limit);
     const float offset = mul(add(-P.action_limit, P.action_limit), 0.5f);
@@ -1230,6 +1231,7 @@ int lm_struct_size(int which) {
     case 10: return (int)sizeof(LmNoiseState);
     case 11: return (int)sizeof(LmCustomController);
     case 12: return (int)sizeof(LmAdamSchedule);
+    case 13: return (int)sizeof(LmActionSink);
     default: return -1;
   }
 }
@@ -1351,9 +1353,36 @@ static int check_views(const LmTask* t, const LmRobotViews* loco, const LmRobotV
   return LM_OK;
 }
 
+// CUDA-graph replays do not run the host side of lm_task_pre_step: a caller replaying captured steps tells the handle which ring
+// slot the replayed step used, so that host-side readers (current_actions / last_actions, lm_task_action_sink) stay in step
+int lm_task_set_step_parity(LmTask* t, int parity) {
+  if (!t || (parity != 0 && parity != 1)) return lm_fail(LM_ERR_BAD_ARG, "lm_task_set_step_parity: bad argument");
+  t->parity = parity;
+  return LM_OK;
+}
+
+int lm_task_action_sink(LmTask* t, const LmRobotViews* loco, const LmRobotViews* mani, const LmTaskBuffers* buf, LmActionSink* out) {
+  if (!t || !buf || !out) return lm_fail(LM_ERR_BAD_ARG, "lm_task_action_sink: NULL argument");
+  const LmTaskParams& P = t->kp.p;
+  if (!(P.control_mode == LM_CONTROL_VELOCITY || P.control_mode == LM_CONTROL_POSITION))
+    return lm_fail(LM_ERR_UNSUPPORTED, "lm_task_action_sink: velocity / position control only");
+  if (!buf->actions_ring) return lm_fail(LM_ERR_BAD_ARG, "lm_task_action_sink: NULL actions_ring");
+  memset(out, 0, sizeof(*out));
+  out->ring_next = buf->actions_ring + (size_t)(t->parity ^ 1) * P.num_envs * LM_NUM_ACT;    // the next pre_step flips the parity
+  out->targets_loco = (loco && P.kind != LM_KIND_MANI) ? loco->targets : nullptr;
+  out->targets_mani = (mani && P.kind != LM_KIND_LOCO) ? mani->targets : nullptr;
+  out->loco_envs = P.kind == LM_KIND_MANI ? 0 : (P.kind == LM_KIND_COTRAIN ? t->kp.d.half : P.num_envs);
+  out->clamp_actions = P.clamp_actions; out->zero_actions = P.zero_actions;
+  out->clip_actions = P.clip_actions; out->action_limit = P.action_limit;
+  return LM_OK;
+}
+
 int lm_task_pre_step(LmTask* t, const LmRobotViews* loco, const LmRobotViews* mani, const float* env_pos,
                      const LmTaskBuffers* buf, const float* actions, const float* uniforms, void* stream) {
-  if (!t || !actions || !uniforms) return lm_fail(LM_ERR_BAD_ARG, "lm_task_pre_step: NULL argument");
+  if (!t || !uniforms) return lm_fail(LM_ERR_BAD_ARG, "lm_task_pre_step: NULL argument");
+  // actions == NULL: the producing kernel delivered them through an LmActionSink (lm_task_action_sink): reset half only
+  if (!actions && (t->has_pd || t->kp.p.control_mode == LM_CONTROL_EFFORT))
+    return lm_fail(LM_ERR_BAD_ARG, "lm_task_pre_step: actions == NULL needs a velocity / position control task (action sink)");
   if (((uintptr_t)actions) & 15) return lm_fail(LM_ERR_ALIGNMENT, "actions is not 16-byte aligned");
   int rc = check_views(t, loco, mani, env_pos, buf);
   if (rc) return rc;

@@ -79,6 +79,10 @@ class GnnActorCritic(nn.Module):
     def _param_version(self):
         return tuple(p._version for p in self.parameters()) + tuple(p.data_ptr() for p in self.parameters())
 
+    def mark_updated(self) -> None:
+        """Call after writing the parameters behind torch's back (optimiser kernels): the next forward re-packs."""
+        self._packed_version = None
+
     def pack(self) -> None:
         self._ensure()
         ts = [p.detach().float().contiguous() for p in self.ordered_parameters()]

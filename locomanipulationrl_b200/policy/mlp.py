@@ -113,7 +113,7 @@ class MlpActorCritic(nn.Module):
         return ws
 
     def forward(self, obs: torch.Tensor, norm_mean: Optional[torch.Tensor] = None, norm_inv_std: Optional[torch.Tensor] = None,
-                norm_clip: float = 5.0, out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None):
+                norm_clip: float = 5.0, out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, sink=None):
         """obs [N,64] fp32 -> (mu [N,12], value [N,1], log_std [12]).  Under ``torch.enable_grad()`` with trainable parameters the
         outputs carry an autograd graph whose backward runs on the tcgen05 kernels (one saved-activation workspace per module: take
         the backward of a forward before calling the next differentiable forward); under ``no_grad`` it is the inference kernel."""
@@ -124,10 +124,11 @@ class MlpActorCritic(nn.Module):
         if torch.is_grad_enabled() and out is None and any(q.requires_grad for q in self._kernel_params()):
             mu, value = _MlpTrainFunction.apply(self, obs.detach(), norm_mean, norm_inv_std, norm_clip, *self._kernel_params())
             return mu, value, self.log_std_parameter
-        return self._forward_inference(obs, norm_mean, norm_inv_std, norm_clip, out)
+        return self._forward_inference(obs, norm_mean, norm_inv_std, norm_clip, out, sink)
 
     @torch.no_grad()
-    def _forward_inference(self, obs, norm_mean, norm_inv_std, norm_clip, out):
+    def _forward_inference(self, obs, norm_mean, norm_inv_std, norm_clip, out, sink=None):
+        """``sink`` (``LocoManipulationTask.action_sink()``): evaluation mode — the head epilogue also hands action = mean to the task."""
         n = obs.shape[0]
         if out is None:
             mu = torch.empty((n, 12), device=self._device, dtype=torch.float32)
@@ -135,8 +136,9 @@ class MlpActorCritic(nn.Module):
         else:
             mu, value = out
         stream = torch.cuda.current_stream(self._device).cuda_stream
-        rc = self._lib.lm_mlp_forward(self._handle, obs.data_ptr(), _lib.ptr(norm_mean), _lib.ptr(norm_inv_std), float(norm_clip),
-                                      mu.data_ptr(), value.data_ptr(), n, stream)
+        import ctypes as C
+        rc = self._lib.lm_mlp_forward_sink(self._handle, obs.data_ptr(), _lib.ptr(norm_mean), _lib.ptr(norm_inv_std), float(norm_clip),
+                                           mu.data_ptr(), value.data_ptr(), n, C.byref(sink) if sink is not None else None, stream)
         _lib.check(rc, "lm_mlp_forward")
         return mu, value, self.log_std_parameter
 

@@ -182,6 +182,63 @@ class MlpPpoGradients:
         return stats
 
 
+class GnnPpoGradients:
+    """The same for ``GnnActorCritic``: forward on the fused kernels (the module's ``precision``) -> ``lm_ppo_loss`` ->
+    ``lm_gnn_backward`` (csrc/lm_gnn_train.cu: one kernel recomputes the fp32 forward per env, walks the limb graph backwards and
+    accumulates all 20 weight / bias gradients per CTA in shared memory).  With ``comm`` the flat arena (gradients + the loss
+    head's statistics) is summed over the ranks by the one-shot NVLink all-reduce right behind it."""
+
+    def __init__(self, model, max_batch: int, arena: Optional[torch.Tensor] = None, comm=None, **loss_cfg):
+        self.model, self.device = model, model._device
+        self.max_batch, self.arena, self.comm = int(max_batch), arena, comm
+        self._lib = _lib.load()
+        model._ensure()
+        params = model.ordered_parameters()
+        for q in params + [model.log_std_parameter]:
+            if q.grad is None:
+                q.grad = torch.zeros_like(q)
+        stats_out = None
+        if arena is not None:
+            n_par = sum(q.numel() for q in params) + 12
+            if arena.numel() != n_par + 8:
+                raise _lib.LmError("arena must hold every gradient plus an 8-float tail")
+            stats_out = arena[n_par:]
+        self.loss = PpoLoss(device=self.device, stats_out=stats_out,
+                            grad_log_std_out=model.log_std_parameter.grad if arena is not None else None, **loss_cfg)
+        self.mu = torch.empty(self.max_batch, 12, device=self.device)
+        self.value = torch.empty(self.max_batch, 1, device=self.device)
+        self.grad_mu = torch.empty(self.max_batch, 12, device=self.device)
+        self.grad_value = torch.empty(self.max_batch, device=self.device)
+        idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self._ctas = self._lib.lm_device_sm_count(idx)
+        self._ws = torch.empty(self._ctas * self._lib.lm_gnn_grad_workspace_floats(), device=self.device)
+
+    @torch.no_grad()
+    def __call__(self, obs, actions, old_neglogp, advantages, old_values, returns, old_mu=None, old_log_std=None,
+                 norm_mean=None, norm_inv_std=None, norm_clip: float = 5.0, update_old: bool = False):
+        if norm_mean is not None:
+            raise _lib.LmError("the GNN kernels take pre-processed observations (skrl applies its state scaler outside the model)")
+        m, lib = self.model, self._lib
+        n = obs.shape[0]
+        if n > self.max_batch:
+            raise _lib.LmError(f"minibatch of {n} exceeds max_batch {self.max_batch}")
+        mu, value = self.mu[:n], self.value[:n]
+        m(obs, out=(mu, value))
+        s = torch.cuda.current_stream(self.device).cuda_stream
+        out = {"grad_mu": self.grad_mu[:n], "grad_value": self.grad_value[:n]}
+        _, _, g_ls, stats = self.loss(mu, value.view(-1), m.log_std_parameter.detach(), actions, old_neglogp, advantages, old_values, returns,
+                                      old_mu, old_log_std, out=out, update_old=update_old)
+        grads = m.ordered_parameters()
+        arr = (C.c_void_p * 20)(*[q.grad.data_ptr() for q in grads])
+        _lib.check(lib.lm_gnn_backward(m._handle, obs.data_ptr(), out["grad_mu"].data_ptr(), out["grad_value"].data_ptr(), n, self._ws.data_ptr(),
+                                       self._ctas, arr, 20, s), "lm_gnn_backward")
+        if g_ls.data_ptr() != m.log_std_parameter.grad.data_ptr():
+            m.log_std_parameter.grad.copy_(g_ls)
+        if self.comm is not None and self.comm.world > 1 and self.arena is not None:
+            self.comm.all_reduce(self.arena)
+        return stats
+
+
 class PpoUpdater:
     """rl_games' ``train_epoch`` for the MLP actor-critic on the library's kernels (cfg/train/JointLocomanipulationPPO.yaml:44-72):
 
@@ -234,8 +291,10 @@ class PpoUpdater:
             off += k
         model.mark_updated()
         self.opt = FlatAdam(self.flat, lr=lr, max_grad_norm=max_grad_norm, kl_threshold=kl_threshold, lr_bounds=lr_bounds)
-        self.grads = MlpPpoGradients(model, max_batch=self.minibatch_size, arena=self.grad_storage, comm=comm, e_clip=e_clip, critic_coef=critic_coef,
-                                     entropy_coef=entropy_coef, bounds_loss_coef=bounds_loss_coef, clip_value=clip_value)
+        from .policy.gnn import GnnActorCritic
+        engine = GnnPpoGradients if isinstance(model, GnnActorCritic) else MlpPpoGradients     # the GNN policy trains on its own kernels
+        self.grads = engine(model, max_batch=self.minibatch_size, arena=self.grad_storage, comm=comm, e_clip=e_clip, critic_coef=critic_coef,
+                            entropy_coef=entropy_coef, bounds_loss_coef=bounds_loss_coef, clip_value=clip_value)
         self.advantages = torch.empty(T, N, device=dev)
         self.returns = torch.empty(T, N, device=dev)
         self.old_values = torch.empty(T, N, device=dev)

@@ -105,24 +105,27 @@ class RolloutBuffer:
         self._buf = _lib.LmRolloutBuffers(td["obses"].data_ptr(), td["actions"].data_ptr(), td["mus"].data_ptr(), td["values"].data_ptr(),
                                           td["rewards"].data_ptr(), td["dones"].data_ptr(), td["neglogpacs"].data_ptr(), T, N, self.reward_scale)
 
-    def _step(self, obs, mu, value, log_std, rew, dones, noise, sample_seed, time_outs, gamma, value_denorm):
+    def _step(self, obs, mu, value, log_std, rew, dones, noise, sample_seed, time_outs, gamma, value_denorm, sink=None):
         in_kernel = noise is None and sample_seed is not None
         step = _lib.LmRolloutStep(_lib.ptr(obs), _lib.ptr(mu), _lib.ptr(value), _lib.ptr(log_std), _lib.ptr(noise), _lib.ptr(rew), _lib.ptr(dones),
                                   int(sample_seed or 0), self._sample_calls, int(in_kernel), 0, _lib.ptr(time_outs), float(gamma), 0,
-                                  _lib.ptr(value_denorm))
+                                  _lib.ptr(value_denorm), C.addressof(sink) if sink is not None else None)
+        self._keep_sink = sink
         return step, in_kernel
 
     def write(self, t: int, obs, mu, value, log_std, rew, dones, noise: Optional[torch.Tensor] = None,
               actions_out: Optional[torch.Tensor] = None, obs_stats: Optional[RunningMeanStd] = None, sample_seed: Optional[int] = None,
-              time_outs: Optional[torch.Tensor] = None, gamma: float = 0.99, value_denorm: Optional[torch.Tensor] = None) -> None:
-        """Slot ``t`` <- this step, in rl_games' ``play_steps`` order: ``obs`` / ``dones`` / ``rew`` are what the env returned last, so
+              time_outs: Optional[torch.Tensor] = None, gamma: float = 0.99, value_denorm: Optional[torch.Tensor] = None, sink=None) -> None:
+        """``sink`` (``LocoManipulationTask.action_sink()``): the sampled actions also go straight into the task's buffers (clamp,
+        stash, take_action), and the next ``pre_physics_step`` is called with ``actions=None``.
+        Slot ``t`` <- this step, in rl_games' ``play_steps`` order: ``obs`` / ``dones`` / ``rew`` are what the env returned last, so
         ``rew`` (the reward of the action stored in slot t-1) goes to slot t-1 — nothing at t = 0 — and :meth:`finish` closes the
         rollout.  ``noise`` = standard-normal draws [N,12] of the caller's generator; without it, ``sample_seed`` makes the kernel
         draw its own N(0,1) noise (counter-based: reproducible for a given seed and call count, no draw tensor), and neither means
         act = mu (evaluation).  ``actions_out`` receives the sampled actions for the next ``pre_physics_step``.  ``time_outs``
         (int64 [N]) switches on value_bootstrap; ``value_denorm`` ([2] = mean, std from ``RunningMeanStd.export_denorm``) stores
         de-normalised values (normalize_value)."""
-        step, in_kernel = self._step(obs, mu, value, log_std, rew, dones, noise, sample_seed, time_outs, gamma, value_denorm)
+        step, in_kernel = self._step(obs, mu, value, log_std, rew, dones, noise, sample_seed, time_outs, gamma, value_denorm, sink)
         if in_kernel:
             self._sample_calls += 1
         st = obs_stats.c_struct() if obs_stats is not None else None

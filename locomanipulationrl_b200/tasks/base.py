@@ -320,19 +320,30 @@ class LocoManipulationTask:
         front so no host sync on ``num_reset`` is needed; row k is consumed by the k-th reset env."""
         return torch.rand((self._num_envs, 3), device=self._device, generator=self._generator)
 
-    def pre_physics_step(self, actions: torch.Tensor, uniforms: Optional[torch.Tensor] = None, physics_substep=None) -> None:
+    def action_sink(self) -> "_lib.LmActionSink":
+        """The action half of the NEXT ``pre_physics_step`` as a struct the producing kernel takes (``MlpActorCritic.forward(sink=)``,
+        ``RolloutBuffer.write(sink=)``): clamp, ``current_actions`` stash and ``take_action`` then happen inside that kernel, and the
+        next ``pre_physics_step(None, uniforms)`` runs only its reset half.  Call after ``post_physics_step`` (it depends on the
+        ring parity and on the scene bound at that moment)."""
+        sink = _lib.LmActionSink()
+        _lib.check(self._lib.lm_task_action_sink(self._handle, self._lp(), self._mp(), C.byref(self._buffers), C.byref(sink)), "lm_task_action_sink")
+        return sink
+
+    def pre_physics_step(self, actions: Optional[torch.Tensor], uniforms: Optional[torch.Tensor] = None, physics_substep=None) -> None:
+        """``actions is None``: they were delivered through :meth:`action_sink` by the kernel that produced them."""
         if self._scene is None:
             raise _lib.LmError("set_up_scene(scene) must be called before stepping")
-        actions = actions.to(self._device, dtype=torch.float32)
-        if not actions.is_contiguous():
-            actions = actions.contiguous()
+        if actions is not None:
+            actions = actions.to(self._device, dtype=torch.float32)
+            if not actions.is_contiguous():
+                actions = actions.contiguous()
         if uniforms is None:
             uniforms = self.draw_goal_uniforms()
         if self.reset_buf._version != self._reset_version:
             # reset_buf was written through torch since the last post step (task.reset(), user code): rescan it
             self._lib.lm_task_invalidate_reset_scan(self._handle)
         rc = self._lib.lm_task_pre_step(self._handle, self._lp(), self._mp(), self._env_pos.data_ptr(), C.byref(self._buffers),
-                                        actions.data_ptr(), uniforms.data_ptr(), self._stream())
+                                        _lib.ptr(actions), uniforms.data_ptr(), self._stream())
         _lib.check(rc, "lm_task_pre_step")
         if self.cfg.custom_controller and self.cfg.cc_rot_dist_term:     # last_rot_dist of the envs reset just now (…custom_controller.py:384-386)
             _lib.check(self._lib.lm_cc_pre(C.byref(self._cc_struct()), self._stream()), "lm_cc_pre")

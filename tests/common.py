@@ -35,13 +35,13 @@ def rollout_inputs(n, steps, seed=GOLDEN_SEED):
     return acts, unis
 
 
-def rot_reward_conditioning(p):
+def rot_reward_conditioning(p, ulps=4.0):
     """Forward-error allowance for the orientation reward 0.5 / (2 asin(min(x, 1)) + 0.1) of the reference (QPC:431-432):
     d asin / dx = 1 / sqrt(1 - x^2) is unbounded as x -> 1 (180-degree orientation error), so a 2-ulp perturbation of
-    x = |quat_diff.xyz| (goal quaternions differ by <= 1 ulp between libm implementations) moves rot_dist by
-    2 * 2.4e-7 / sqrt(1 - x^2).  Away from x ~ 1 this term is < 1e-7 and irrelevant."""
+    x = |quat_diff.xyz| (goal quaternions differ by <= 1 ulp between libm implementations; ``ulps`` = 4 by default, i.e. 2.4e-7)
+    moves rot_dist by 2 * 2.4e-7 / sqrt(1 - x^2).  Away from x ~ 1 this term is < 1e-7 and irrelevant."""
     x = torch.clamp(p.inter["quat_diff_norm"].double(), max=1.0)
-    d_rd = 2.0 * 2.4e-7 / torch.sqrt(torch.clamp(1.0 - x * x, min=1.2e-7))
+    d_rd = 2.0 * (ulps * 5.96e-8) / torch.sqrt(torch.clamp(1.0 - x * x, min=1.2e-7))      # ulp(x) = 2^-24 just below 1
     d_rew = 0.5 / (p.inter["rot_dist"].double().abs() + p.cfg.rot_eps) ** 2
     return d_rew * d_rd
 
@@ -158,7 +158,7 @@ class CudaRollout:
         if self.cfg.num_states == 93:
             self._track("states", assert_close(f"step {t} states_buf", task.states_buf, p.states_buf))
         self._track("rew", assert_close(f"step {t} rew_buf", task.rew_buf, p.rew_buf, rows=ok, scale=p.inter["rew_scale"],
-                                        extra_atol=rot_reward_conditioning(p)))
+                                        extra_atol=rot_reward_conditioning(p, getattr(self, "cond_ulps", 4.0))))
         self._track("last_tip", assert_close(f"step {t} last_base_tip", task.last_base_tip_positions, p.last_base_tip_positions))
         self._track("last_jv", assert_close(f"step {t} last_joint_vel", task.last_joint_velocities,
                                             torch.cat([p.last_joint_velocities[g] for g in ("loco", "mani") if getattr(self.scene_cpu, g)], dim=0)))

@@ -295,3 +295,81 @@ def test_mlp_forward_is_differentiable_through_the_kernels():
         lib.lm_clamp_copy(obs.data_ptr(), obs.data_ptr(), obs.numel(), 0.01, torch.cuda.current_stream().cuda_stream)
         m3, _, _ = shared.compute({"states": obs}, "policy")
         assert float((m3 - m2).abs().max()) > 1e-3
+
+
+# ----------------------------------------------------------------------------------------------- GNN policy
+@pytest.mark.parametrize("n", [5, 64, 3000])
+def test_gnn_backward_matches_autograd(n):
+    """lm_gnn_backward (forward recomputed in fp32, limb graph walked backwards, shared-memory weight-gradient accumulation) against
+    torch autograd through GnnActorCritic.reference_forward for an arbitrary upstream gradient."""
+    import ctypes as C
+    from locomanipulationrl_b200 import _lib
+    from locomanipulationrl_b200.policy.gnn import GnnActorCritic
+    torch.manual_seed(7)
+    model = GnnActorCritic(device="cuda:0", precision="fp32")
+    with torch.no_grad():
+        for q in model.parameters():
+            q.mul_(1.6)                                            # livelier activations than the default initialisation
+    obs = (torch.randn(n, 64, device="cuda") * 1.5).clamp(-5, 5)
+    g_mu, g_v = torch.randn(n, 12, device="cuda") / n, torch.randn(n, device="cuda") / n
+    mu, value, _ = model.reference_forward(obs)
+    (mu * g_mu).sum().add((value.view(-1) * g_v).sum()).backward()
+    ref = [q.grad.clone() for q in model.ordered_parameters()]
+    model.zero_grad()
+    model.pack()
+    lib = _lib.load()
+    ctas = lib.lm_device_sm_count(0)
+    ws = torch.empty(ctas * lib.lm_gnn_grad_workspace_floats(), device="cuda")
+    got = [torch.full_like(q, 7.0) for q in model.ordered_parameters()]      # the kernel WRITES the gradients
+    arr = (C.c_void_p * 20)(*[t.data_ptr() for t in got])
+    _lib.check(lib.lm_gnn_backward(model._handle, obs.data_ptr(), g_mu.data_ptr(), g_v.data_ptr(), n, ws.data_ptr(), ctas, arr, 20,
+                                   torch.cuda.current_stream().cuda_stream), "lm_gnn_backward")
+    names = [k for k, _ in model.named_parameters() if k != "log_std_parameter"]
+    for k, g, r in zip(names, got, ref):
+        scale = float(r.abs().max()) + 1e-9
+        err = float((g - r).abs().max())
+        assert err <= 2e-4 * scale + 1e-7, (k, err, scale)
+
+
+def test_ppo_updater_gnn_tracks_autograd():
+    """PpoUpdater on the GNN policy (kernel forward, loss head, lm_gnn_backward, clip + Adam, re-pack) against the same minibatch loop
+    through torch autograd on a copy of the model."""
+    from locomanipulationrl_b200.policy.gnn import GnnActorCritic
+    from locomanipulationrl_b200.ppo import PpoUpdater
+    from locomanipulationrl_b200.rollout import RolloutBuffer
+    from oracle import port_policy as pp
+    T, N, MB = 4, 1024, 2048
+    torch.manual_seed(2)
+    model, ref_model = GnnActorCritic(device="cuda:0", precision="fp32"), GnnActorCritic(device="cuda:0", precision="fp32")
+    ref_model.load_state_dict(model.state_dict())
+    buf = RolloutBuffer(T, N)
+    up = PpoUpdater(model, buf, minibatch_size=MB, mini_epochs=2, lr=1e-3, kl_threshold=None)
+    last_v, last_d = _synthetic_rollout(model, buf, 5)
+    td = {k: v.clone() for k, v in buf.tensor_dict.items()}
+    before = torch.cat([p.detach().reshape(-1) for p in ref_model.parameters()]).clone()
+    adv, ret = pp.gae_rlgames(td["rewards"].cpu(), td["values"].cpu(), td["dones"].cpu(), last_v.cpu(), last_d.cpu())
+    adv = pp.normalize_advantages(adv)
+    fl = lambda x: x.reshape(T * N, *x.shape[2:]).cuda()
+    mus = fl(td["mus"]).clone()
+    ref_params = list(ref_model.parameters())
+    opt = torch.optim.Adam(ref_params, lr=1e-3, eps=1e-8)
+    old_ls = ref_model.log_std_parameter.detach().clone().expand(T * N // MB, 12).clone()
+    for _ in range(2):
+        for i in range(T * N // MB):
+            sl = slice(i * MB, (i + 1) * MB)
+            mu, value, ls = ref_model.reference_forward(fl(td["obses"])[sl])
+            loss, _ = pp.ppo_loss(mu, value.view(-1), ls, fl(td["actions"])[sl], fl(td["neglogpacs"])[sl], fl(adv)[sl], fl(td["values"])[sl], fl(ret)[sl],
+                                  mus[sl], old_ls[i])
+            opt.zero_grad(); loss.backward()
+            torch.nn.utils.clip_grad_norm_(ref_params, 1.0)
+            opt.step()
+            mus[sl] = mu.detach(); old_ls[i] = ls.detach()
+    up.update(last_v, last_d)
+    step_ref = torch.cat([p.detach().reshape(-1) for p in ref_params]) - before
+    step = up.flat - before
+    cos = float(torch.nn.functional.cosine_similarity(step, step_ref, dim=0))
+    assert cos > 0.995, cos
+    probe = torch.randn(256, 64, device="cuda").clamp(-5, 5)
+    with torch.no_grad():
+        mu_k, mu_m = model(probe)[0], model.reference_forward(probe)[0]
+    assert_close("GNN acts with the updated weights", mu_k, mu_m, rtol=1e-4, atol=1e-5)
