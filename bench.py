@@ -253,12 +253,22 @@ class Pipeline:
         # kernels of liblm_b200.so per step: k_pre, k_post_lean, policy forward (k_reset_count only runs when reset_buf was
         # written from outside); the gnn_gae workload adds k_rollout_write every step and lm_gae once per HORIZON steps
         self.launches_per_step = 3
-        self.use_sink = not os.environ.get("LM_BENCH_NO_SINK")
-        self.overlap_pre = self.use_sink and self.w["policy"] == "mlp" and not os.environ.get("LM_BENCH_NO_OVERLAP")
+        # Pipeline variants, all measured on B200 at 65,536 envs (gpurun_out/r2d_*.json) and all OFF by default because
+        # none beat the plain chain pre -> post -> policy (45.6 us / step):
+        #   LM_BENCH_SINK=1          action half of pre_physics_step folded into the MLP head epilogue (LmActionSink)       45.9 us
+        #   + LM_BENCH_OVERLAP=1     reset half of the next pre_physics_step on a second stream next to the policy forward   45.9 us
+        #   + LM_BENCH_DEFER_FINISH=1  post kernel without its finish tail (14.1 instead of 17.5 us), k_post_finish separate     50.1 us
+        #   + LM_BENCH_EARLY_RESET=1   reset half ahead of the policy forward on the same stream                              47.2 us
+        self.use_sink = bool(os.environ.get("LM_BENCH_SINK")) and self.w["policy"] == "mlp"
+        self.early_reset = bool(os.environ.get("LM_BENCH_EARLY_RESET"))
+        self.overlap_pre = self.use_sink and (bool(os.environ.get("LM_BENCH_OVERLAP")) or self.early_reset)
         self.side = torch.cuda.Stream(device=device)
         self.graph_parity = None
+        self.defer_finish = self.overlap_pre and bool(os.environ.get("LM_BENCH_DEFER_FINISH"))
         if self.overlap_pre:                             # prime: the first step's pre_physics_step (later ones ride next to the policy forward)
             self.task.pre_physics_step(self.actions, self.uniforms[0])
+            if self.defer_finish:
+                self.task.set_defer_finish(True)
         if self.w["policy"] == "gnn":
             from locomanipulationrl_b200.rollout import RolloutBuffer, RunningMeanStd
             T = HORIZON
@@ -279,8 +289,18 @@ class Pipeline:
             task.post_physics_step()
             cur = torch.cuda.current_stream()
             sink = task.action_sink()
+            if self.early_reset:
+                # same stream, reset half first: the policy kernel's prologue (117 KB of weights per CTA, TMEM allocation) then
+                # overlaps it through programmatic dependent launch
+                if self.defer_finish:
+                    task.post_finish()
+                task.pre_physics_step(None, self.uniforms[(i + 1) % STATE_SETS])
+                self.policy(task.obs_buf, norm_mean=self.norm_mean, norm_inv_std=self.norm_inv_std, out=(self.mu, self.value), sink=sink)
+                return
             self.side.wait_stream(cur)
             with torch.cuda.stream(self.side):
+                if self.defer_finish:
+                    task.post_finish()                  # extras / counters / reset scan: off the post kernel's critical path
                 task.pre_physics_step(None, self.uniforms[(i + 1) % STATE_SETS])
             self.policy(task.obs_buf, norm_mean=self.norm_mean, norm_inv_std=self.norm_inv_std, out=(self.mu, self.value), sink=sink)
             cur.wait_stream(self.side)
@@ -502,6 +522,11 @@ def cuda_arm(args):
             task._posted_since_pre = False     # time the kernel alone (no double-post fix-up copy)
             task.post_physics_step()
 
+        def post_and_finish(i):
+            post_only(i)
+            if pipe.defer_finish:
+                task.post_finish()
+
         def pre_only(i):
             task.pre_physics_step(None if pipe.use_sink else pipe.actions, pipe.uniforms[i % STATE_SETS])
 
@@ -534,10 +559,11 @@ def cuda_arm(args):
             return a0.elapsed_time(a1) / (reps * STATE_SETS)
 
         def pre_post(i):
-            pre_only(i); post_only(i)
+            pre_only(i); post_and_finish(i)
 
         ms_post = graph_time(post_only)
-        ms_pre = max(graph_time(pre_post) - ms_post, 1e-6)      # pre needs a preceding post (its reset scan is post's by-product)
+        ms_post_fin = graph_time(post_and_finish) if pipe.defer_finish else ms_post
+        ms_pre = max(graph_time(pre_post) - ms_post_fin, 1e-6)      # pre needs a preceding post + finish (its reset scan is their by-product)
         ms_pol = graph_time(policy_only)
         hbm, tf, src = measured_peaks()
         # single-task files with the 93-wide states_buf write 372 B/env more (1 036 -> 1 408 B/env-step)
@@ -565,7 +591,7 @@ def cuda_arm(args):
                                              "peak": tf if tc else None, "frac": tfl / tf if tc else None,
                                              "unit": "TFLOP/s" if tc else "TFLOP/s (naive FLOP count)", "ms": ms_pol,
                                              "hbm_gbs": n * 308 / (ms_pol * 1e-3) / 1e9}
-        line_extra["kernel_ms"] = {"pre": ms_pre, "post": ms_post, "policy": ms_pol}
+        line_extra["kernel_ms"] = {"pre": ms_pre, "post": ms_post, "policy": ms_pol, "post_finish": ms_post_fin - ms_post}
         # `roofline` = the dominant kernel of the step (largest share of the device time), the others keep their own blocks
         if ms_pol >= ms_post and line_extra["roofline_policy"].get("frac") is not None:
             line_extra["roofline"] = dict(line_extra["roofline_policy"], traffic=measured_traffic("k_mlp_forward") if pipe.w["policy"] == "mlp" else measured_traffic("k_gnn_forward_tc"),
@@ -642,7 +668,8 @@ def cuda_arm(args):
                 "config": {"workload": pipe.w["desc"], "envs_per_gpu": n, "global_envs": n * world, "parallelism": f"env-shard x{world}",
                            "l2": f"{STATE_SETS} rotating synthetic state sets (> L2) - inputs larger than L2",
                            "cuda_graphs": pipe.graphs is not None, "action_sink": pipe.use_sink,
-                           "pre_reset_overlaps_policy": pipe.overlap_pre, "comm": (f"one stat + gradient-arena all-reduce (58,651 fp32) every {horizon} steps, "
+                           "pre_reset_overlaps_policy": pipe.overlap_pre and not pipe.early_reset, "post_finish_deferred": pipe.defer_finish,
+                           "early_reset": pipe.early_reset, "comm": (f"one stat + gradient-arena all-reduce (58,651 fp32) every {horizon} steps, "
                                     + ("one-shot NVLink peer-memory kernel (lm_comm_allreduce)" if peer is not None else "NCCL all_reduce")
                                     + f", {args.comm_stream} stream, CUDA graph") if world > 1 else "none",
                            "timed": f"{reps} rollout horizons of {horizon} steps"},
@@ -670,6 +697,10 @@ def train_arm(pipe, args, world, device, rank, peer):
     from locomanipulationrl_b200.ppo import PpoUpdater
     from locomanipulationrl_b200.rollout import RolloutBuffer, RunningMeanStd
     T, n, task, policy = HORIZON_MLP, pipe.n, pipe.task, pipe.policy
+    if pipe.defer_finish:
+        task.set_defer_finish(False)
+    task.set_up_scene(pipe.scenes[0])                  # whatever pipeline variant ran before: start from a plain post step
+    task.post_physics_step()
     buf = RolloutBuffer(T, n, device=device, reward_scale=1.0)
     obs_rms = RunningMeanStd(64, device=device)
     nmb = 8
@@ -687,9 +718,9 @@ def train_arm(pipe, args, world, device, rank, peer):
         for t in range(T):
             forward()
             buf.write(t, task.obs_buf, mu, value, log_std, task.rew_buf, task.reset_buf, sample_seed=seed, value_denorm=up.value_denorm,
-                      sink=task.action_sink() if pipe.use_sink else None, actions_out=None if pipe.use_sink else actions)
+                      actions_out=actions)
             i = state["i"] = (state["i"] + 1) % STATE_SETS
-            task.pre_physics_step(None if pipe.use_sink else actions, pipe.uniforms[i])
+            task.pre_physics_step(actions, pipe.uniforms[i])
             task.set_up_scene(pipe.scenes[i])
             task.post_physics_step()
         forward()                                         # value of the observation after the last stored action: GAE's bootstrap

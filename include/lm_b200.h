@@ -212,6 +212,11 @@ typedef struct LmActionSink {
   int32_t clamp_actions; int32_t zero_actions; int32_t pad_;
   float clip_actions; float action_limit;
 } LmActionSink;
+/* Deferred finish pass (see lm_task.cu): with defer on, lm_task_post_step leaves extras / counters / the reset scan to
+ * lm_task_post_finish, which the caller may launch on another stream (it must complete before the next lm_task_pre_step and
+ * before extras / counters are read). */
+int lm_task_set_defer_finish(LmTask* task, int on);
+int lm_task_post_finish(LmTask* task, const LmTaskBuffers* buf, void* stream);
 int lm_task_set_step_parity(LmTask* task, int parity);   /* after replaying a captured step: the ring slot (lm_task_step_parity at capture) it used */
 int lm_task_action_sink(LmTask* task, const LmRobotViews* loco, const LmRobotViews* mani, const LmTaskBuffers* buf, LmActionSink* out);
 

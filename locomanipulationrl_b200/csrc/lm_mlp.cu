@@ -72,10 +72,8 @@ __device__ __forceinline__ void issue_ksteps(uint32_t tmem_d, uint32_t a_saddr, 
   }
 }
 
-// 16 accumulator columns [c0, c0+16) of row `row` -> +bias, ELU, bf16 -> two 16-byte K chunks of the next A operand
-// `gdst` (training forward only): the same two chunks into the tile's activation blob in global memory (same layout, same offsets)
-__device__ __forceinline__ void emit16(const uint32_t* acc, const float* __restrict__ bias, uint8_t* dst, int row, int c0, uint8_t* gdst = nullptr) {
-  uint32_t w[8];
+// 16 accumulator columns [c0, c0+16) -> +bias, ELU, bf16 -> eight packed words (two 16-byte K chunks of the next A operand)
+__device__ __forceinline__ void elu16(const uint32_t* acc, const float* __restrict__ bias, int c0, uint32_t (&w)[8]) {
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const float4 b = *reinterpret_cast<const float4*>(bias + c0 + 4 * k);
@@ -83,6 +81,9 @@ __device__ __forceinline__ void emit16(const uint32_t* acc, const float* __restr
     w[2 * k] = elu_pair_mix<LM_MLP_FMA_PAIRS>((2 * k) & 3, acc[4 * k], acc[4 * k + 1], b.x, b.y);
     w[2 * k + 1] = elu_pair_mix<LM_MLP_FMA_PAIRS>((2 * k + 1) & 3, acc[4 * k + 2], acc[4 * k + 3], b.z, b.w);
   }
+}
+// `gdst` (training forward only): the same two chunks into the tile's activation blob in global memory (same layout, same offsets)
+__device__ __forceinline__ void store16(const uint32_t (&w)[8], uint8_t* dst, int row, int c0, uint8_t* gdst = nullptr) {
   *reinterpret_cast<uint4*>(dst + elem_offset(TM, row, c0)) = make_uint4(w[0], w[1], w[2], w[3]);
   *reinterpret_cast<uint4*>(dst + elem_offset(TM, row, c0 + 8)) = make_uint4(w[4], w[5], w[6], w[7]);
   if (gdst != nullptr) {
@@ -93,25 +94,32 @@ __device__ __forceinline__ void emit16(const uint32_t* acc, const float* __restr
 
 // Hidden-layer epilogue of one warp: kSub sub-steps; in sub-step s the 16 warps together cover accumulator columns
 // [64 s, 64 s + 64) (this warp: 16 of them), i.e. K chunk s of the next layer, written to dst + (s % kSlots) * CHUNK_BYTES,
-// and signal `bars[s]`.  The TMEM load of sub-step s+1 is in flight while sub-step s is being processed.  With a ring
-// (kSlots < kSub) sub-step s >= kSlots first waits until the MMAs of chunk s - kSlots have drained (`slot_free[s - kSlots]`).
+// and signal `bars[s]`.  With a ring (kSlots < kSub) sub-step s >= kSlots first waits until the MMAs of chunk s - kSlots have
+// drained (`slot_free[s - kSlots]`).
+// The ELU arithmetic of sub-step s+1 is written ahead of the fence / arrival of sub-step s, with the TMEM load of s+2 in flight: the
+// scheduler is free to fill the stores' completion latency with the next sub-step's MUFU work.
 template <int kSub, int kSlots>
 __device__ __forceinline__ void epilogue_hidden(uint32_t tmem_acc, const float* __restrict__ bias, uint8_t* dst, uint64_t* bars,
                                                 uint64_t* slot_free, uint32_t slot_parity, int g, int q, int lane, uint8_t* gsave = nullptr) {
   const int row = g * 32 + lane;
   const uint32_t taddr = tmem_acc + ((uint32_t)(g * 32) << 16) + (uint32_t)(q * 16);
-  uint32_t a[16], b[16];
+  uint32_t a[16], b[16], w[8];
   tmem_ld16(taddr, a);
   tmem_wait();
+  if (kSub > 1) tmem_ld16(taddr + 64, b);
+  elu16(a, bias, q * 16, w);
 #pragma unroll
   for (int s = 0; s < kSub; ++s) {
-    uint32_t* cur = (s & 1) ? b : a;
-    uint32_t* nxt = (s & 1) ? a : b;
-    if (s + 1 < kSub) tmem_ld16(taddr + 64 * (s + 1), nxt);
+    uint32_t* nxt = (s & 1) ? a : b;          // holds sub-step s + 1 (in flight or landed)
+    uint32_t* free_buf = (s & 1) ? b : a;     // sub-step s: already consumed into w
     if (s >= kSlots) mbar_wait(&slot_free[s - kSlots], slot_parity);
-    emit16(cur, bias + 64 * s, dst + (s % kSlots) * CHUNK_BYTES, row, q * 16, gsave != nullptr ? gsave + s * CHUNK_BYTES : nullptr);
+    store16(w, dst + (s % kSlots) * CHUNK_BYTES, row, q * 16, gsave != nullptr ? gsave + s * CHUNK_BYTES : nullptr);
+    if (s + 1 < kSub) {
+      tmem_wait();
+      if (s + 2 < kSub) tmem_ld16(taddr + 64 * (s + 2), free_buf);
+      elu16(nxt, bias + 64 * (s + 1), q * 16, w);
+    }
     fence_proxy_async();                       // generic-proxy A operand writes -> visible to the tensor core's async proxy
-    if (s + 1 < kSub) tmem_wait();
     tc_fence_before();                         // orders this warp's tcgen05.ld before the MMA that reuses the accumulator
     __syncwarp();
     if (lane == 0) mbar_arrive(&bars[s]);

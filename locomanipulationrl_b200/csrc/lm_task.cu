@@ -1185,6 +1185,7 @@ struct LmTask {
   int32_t* tile_offsets;
   int32_t* scan_base;
   int inline_finish;
+  int defer_finish;                // the caller launches the finish pass itself (lm_task_post_finish), e.g. on a second stream
   LmPdState pd;
   int has_pd;
   float* partials;
@@ -1262,6 +1263,7 @@ LmTask* lm_task_create(const LmTaskParams* params, int device) {
   d.half = (p.kind == LM_KIND_COTRAIN) ? p.num_envs / 2 : p.num_envs;
   d.tiles_per_half = (d.half + T - 1) / T;
   d.num_tiles = d.tiles_per_half * ((p.kind == LM_KIND_COTRAIN) ? 2 : 1);
+  t->defer_finish = 0;
   t->inline_finish = d.num_tiles <= INLINE_FINISH_MAX_TILES;
   {
     const int threads = t->inline_finish ? T : FINISH_THREADS;
@@ -1444,9 +1446,32 @@ int lm_task_post_step(LmTask* t, const LmRobotViews* loco, const LmRobotViews* m
     cudaError_t le = lm_launch(k_post_lean, dim3(t->kp.d.num_tiles), dim3(T), LeanSmem::kBytes, (cudaStream_t)stream, true, t->kp, a);
     if (le != cudaSuccess) return lm_fail((int)le, "lm_task_post_step: %s", cudaGetErrorString(le));
   }
-  if (!t->inline_finish) k_post_finish<<<1, FINISH_THREADS, 0, (cudaStream_t)stream>>>(t->kp, a);
+  if (!t->inline_finish && !t->defer_finish) k_post_finish<<<1, FINISH_THREADS, 0, (cudaStream_t)stream>>>(t->kp, a);
   t->scan_valid = 1;
   return lm_check_launch("lm_task_post_step");
+}
+
+// Deferred finish pass: lm_task_post_step then only publishes the per-tile partial sums, and the pass that turns them into extras /
+// counters / the next step's reset scan is launched by the caller — e.g. on a second stream next to the policy forward, ahead of
+// the next lm_task_pre_step (which needs the scan).  The post kernel sheds its serial tail (one CTA reading every tile's partials).
+int lm_task_set_defer_finish(LmTask* t, int on) {
+  if (!t) return lm_fail(LM_ERR_BAD_ARG, "lm_task_set_defer_finish: task is NULL");
+  t->defer_finish = on != 0;
+  t->inline_finish = (t->kp.d.num_tiles <= INLINE_FINISH_MAX_TILES) && !t->defer_finish;
+  const int threads = t->inline_finish ? T : FINISH_THREADS;
+  t->kp.d.scan_per = (t->kp.d.num_tiles + threads - 1) / threads;
+  t->scan_valid = 0;                  // the layout of tile_offsets / scan_base depends on scan_per
+  return LM_OK;
+}
+
+int lm_task_post_finish(LmTask* t, const LmTaskBuffers* buf, void* stream) {
+  if (!t || !buf) return lm_fail(LM_ERR_BAD_ARG, "lm_task_post_finish: NULL argument");
+  if (!t->defer_finish) return lm_fail(LM_ERR_BAD_ARG, "lm_task_post_finish: the task runs its finish pass itself (lm_task_set_defer_finish)");
+  PostArgs a;
+  memset(&a, 0, sizeof(a));
+  a.buf = *buf; a.partials = t->partials; a.ticket = t->tickets + 1; a.tile_offsets = t->tile_offsets; a.scan_base = t->scan_base;
+  k_post_finish<<<1, FINISH_THREADS, 0, (cudaStream_t)stream>>>(t->kp, a);
+  return lm_check_launch("lm_task_post_finish");
 }
 
 int lm_clamp_copy(const float* in, float* out, int64_t count, float clip, void* stream) {

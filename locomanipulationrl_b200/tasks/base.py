@@ -364,6 +364,16 @@ class LocoManipulationTask:
         _lib.check(rc, "lm_task_reset_idx")
         self._keep = (env_ids, uniforms)
 
+    def set_defer_finish(self, on: bool = True) -> None:
+        """``on``: ``post_physics_step`` leaves the finish pass (extras, success counters, the reset scan the next ``pre_physics_step``
+        consumes) to :meth:`post_finish`, which may be launched on another stream — next to the policy forward — instead of as the
+        serial tail of the post kernel."""
+        _lib.check(self._lib.lm_task_set_defer_finish(self._handle, int(bool(on))), "lm_task_set_defer_finish")
+        self._defer_finish = bool(on)
+
+    def post_finish(self) -> None:
+        _lib.check(self._lib.lm_task_post_finish(self._handle, C.byref(self._buffers), self._stream()), "lm_task_post_finish")
+
     def post_physics_step(self):
         """rl_task.py:240-260: progress += 1, observations, metrics, termination — one fused launch."""
         if self._posted_since_pre:

@@ -18,13 +18,16 @@ def _tracker(task, port, scene_cpu, cfg, n):
     return ro
 
 
-def test_bench_pipeline_65536_graph_replay_matches_port():
-    """BASELINE configs[2] exactly as bench.py runs it: JointLocomanipulationVertical, 65,536 envs, fuse_obs_clamp, six rotating
+def test_bench_pipeline_65536_graph_replay_matches_port(monkeypatch):
+    """BASELINE configs[2] in bench.py's sink / second-stream variant (LM_BENCH_SINK=1 LM_BENCH_OVERLAP=1; the default pipeline is
+    the next test): JointLocomanipulationVertical, 65,536 envs, fuse_obs_clamp, six rotating
     state sets, action = policy mean delivered through the action sink, the reset half of the next pre_physics_step running next to
     the policy forward on a second stream, one CUDA graph per state set — tracked by the oracle port for the six eager warm-up
     steps and eight replayed ones.  One pipeline step = post(t) -> {policy(t) || pre(t+1)}; the port runs the same calls in order."""
     import bench
     from oracle import port
+    monkeypatch.setenv("LM_BENCH_SINK", "1")
+    monkeypatch.setenv("LM_BENCH_OVERLAP", "1")
     dev = torch.device("cuda:0")
     pipe = bench.Pipeline("cotrain64k", dev, rank=0)
     cfg, n, task = pipe.cfg, pipe.n, pipe.task
@@ -88,6 +91,55 @@ def test_bench_pipeline_65536_graph_replay_matches_port():
         pipe.step(t)
         track(t % S, t)
     print("65,536-env graph replay max abs err:", {k.split(" ", 2)[-1]: f"{v:.2e}" for k, v in sorted(stats["err"].items())[-12:]})
+
+
+def test_bench_default_pipeline_65536_graph_replay_matches_port():
+    """BASELINE configs[2] exactly as bench.py times it by default: JointLocomanipulationVertical, 65,536 envs, fuse_obs_clamp, six
+    rotating state sets, the policy mean fed back as the next action, pre -> post -> policy captured as one CUDA graph per state
+    set — tracked by the oracle port through the six eager warm-up steps and eight replayed ones."""
+    import bench
+    from oracle import port
+    dev = torch.device("cuda:0")
+    pipe = bench.Pipeline("cotrain64k", dev, rank=0)
+    cfg, n = pipe.cfg, pipe.n
+    S = bench.STATE_SETS
+    assert n == 65536 and pipe.task._fuse_obs_clamp and not pipe.use_sink and not pipe.overlap_pre
+    scenes_cpu = []
+    for i in range(S):
+        sc = synthetic.SyntheticScene(cfg, n, seed=42)
+        sc.load(sc.generate(i))
+        scenes_cpu.append(sc)
+    p = port.TaskPort(cfg, scenes_cpu[0])
+    ro = _tracker(pipe.task, p, scenes_cpu[0], cfg, n)
+    unis = [u.cpu() for u in pipe.uniforms]
+    actions = {"a": pipe.actions.detach().cpu().clone()}
+
+    def track(i, t):
+        torch.cuda.synchronize()
+        p.pre_physics_step(torch.clamp(actions["a"], -1.0, 1.0), unis[i])      # the adapter's clamp (vec_env_rlgames.py:60)
+        prev = scenes_cpu[(i - 1) % S] if t > 0 else scenes_cpu[0]             # the views that were live during pre_physics_step
+        got_prev = pipe.scenes[(i - 1) % S] if t > 0 else pipe.scenes[0]
+        for grp in ("loco", "mani"):
+            for k in ("dof_pos", "root_pos" if grp == "loco" else "plate_pos", "indicator_quat"):
+                assert_close(f"step {t} scene.{grp}.{k}", getattr(got_prev, grp)[k], getattr(prev, grp)[k])
+        p.scene = scenes_cpu[i]
+        ro.scene_cpu = scenes_cpu[i]
+        p.post_physics_step()
+        p.obs_buf = torch.clamp(p.obs_buf, -cfg.clip_observations, cfg.clip_observations)      # _process_data, fused into the kernel
+        ro.compare_post(t)
+        with torch.no_grad():
+            mu_ref, v_ref, _ = pipe.policy.reference_forward((pipe.task.obs_buf - pipe.norm_mean) * pipe.norm_inv_std)
+        assert_close(f"step {t} mu", pipe.mu, mu_ref, rtol=0, atol=1e-2)
+        assert_close(f"step {t} value", pipe.value, v_ref, rtol=0, atol=1e-2)
+        actions["a"] = pipe.mu.detach().cpu().clone()
+
+    pipe.capture(after_step=lambda i: track(i, i))
+    assert pipe.graphs is not None and len(pipe.graphs) == S
+    for t in range(S, S + 8):
+        pipe.step(t)
+        track(t % S, t)
+    assert ro.exempt_events == 0, f"{ro.exempt_events} near-threshold mask exemptions"
+    print("65,536-env default pipeline, graph replay, max abs err:", {k: f"{v:.2e}" for k, v in ro.max_err.items()})
 
 
 @pytest.mark.parametrize("name,n", [("JointLocomanipulationVertical", 4096), ("QuadrupedManipulatePlate", 1000), ("QuadrupedPoseControl", 130)])
