@@ -228,6 +228,27 @@ def load(path: Optional[str] = None) -> C.CDLL:
     return lib
 
 
+class _NoRange:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NO_RANGE = _NoRange()
+NVTX = bool(os.environ.get("LM_NVTX"))
+
+
+def nvtx(name: str):
+    """NVTX range around a host-side section (LM_NVTX=1; SURVEY §5 tracing): shows up on the nsys / ncu timeline as
+    ``lm/<name>``.  A no-op object otherwise — the step loop pays nothing."""
+    if not NVTX:
+        return _NO_RANGE
+    import torch
+    return torch.cuda.nvtx.range("lm/" + name)
+
+
 def check(rc: int, what: str = "") -> None:
     if rc != 0:
         msg = load().lm_last_error()

@@ -106,7 +106,9 @@ class GnnActorCritic(nn.Module):
             mu, value = out
         stream = torch.cuda.current_stream(self._device).cuda_stream
         fn = self._lib.lm_gnn_forward_bf16 if self.precision == "bf16" else self._lib.lm_gnn_forward
-        _lib.check(fn(self._handle, obs.data_ptr(), mu.data_ptr(), value.data_ptr(), n, stream), "lm_gnn_forward")
+        with _lib.nvtx("gnn_forward"):
+            rc = fn(self._handle, obs.data_ptr(), mu.data_ptr(), value.data_ptr(), n, stream)
+        _lib.check(rc, "lm_gnn_forward")
         return mu, value, self.log_std_parameter
 
     def reference_forward(self, obs: torch.Tensor):

@@ -137,8 +137,9 @@ class MlpActorCritic(nn.Module):
             mu, value = out
         stream = torch.cuda.current_stream(self._device).cuda_stream
         import ctypes as C
-        rc = self._lib.lm_mlp_forward_sink(self._handle, obs.data_ptr(), _lib.ptr(norm_mean), _lib.ptr(norm_inv_std), float(norm_clip),
-                                           mu.data_ptr(), value.data_ptr(), n, C.byref(sink) if sink is not None else None, stream)
+        with _lib.nvtx("mlp_forward"):
+            rc = self._lib.lm_mlp_forward_sink(self._handle, obs.data_ptr(), _lib.ptr(norm_mean), _lib.ptr(norm_inv_std), float(norm_clip),
+                                               mu.data_ptr(), value.data_ptr(), n, C.byref(sink) if sink is not None else None, stream)
         _lib.check(rc, "lm_mlp_forward")
         return mu, value, self.log_std_parameter
 

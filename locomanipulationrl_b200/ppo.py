@@ -318,6 +318,10 @@ class PpoUpdater:
     def update(self, last_values: torch.Tensor, last_dones: torch.Tensor, norm_mean=None, norm_inv_std=None):
         """One PPO update over the rollout currently in the buffer.  Returns the last minibatch's loss-head stats (device tensor [8];
         summed over ranks when sharded — divide by the world size)."""
+        with _lib.nvtx("ppo_update"):
+            return self._update(last_values, last_dones, norm_mean, norm_inv_std)
+
+    def _update(self, last_values, last_dones, norm_mean, norm_inv_std):
         import torch.distributed as tdist
         from . import gae as _gae
         lib, s = self._lib, torch.cuda.current_stream(self.rollout.device).cuda_stream

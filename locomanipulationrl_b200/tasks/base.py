@@ -342,8 +342,9 @@ class LocoManipulationTask:
         if self.reset_buf._version != self._reset_version:
             # reset_buf was written through torch since the last post step (task.reset(), user code): rescan it
             self._lib.lm_task_invalidate_reset_scan(self._handle)
-        rc = self._lib.lm_task_pre_step(self._handle, self._lp(), self._mp(), self._env_pos.data_ptr(), C.byref(self._buffers),
-                                        _lib.ptr(actions), uniforms.data_ptr(), self._stream())
+        with _lib.nvtx("pre_physics_step"):
+            rc = self._lib.lm_task_pre_step(self._handle, self._lp(), self._mp(), self._env_pos.data_ptr(), C.byref(self._buffers),
+                                            _lib.ptr(actions), uniforms.data_ptr(), self._stream())
         _lib.check(rc, "lm_task_pre_step")
         if self.cfg.custom_controller and self.cfg.cc_rot_dist_term:     # last_rot_dist of the envs reset just now (…custom_controller.py:384-386)
             _lib.check(self._lib.lm_cc_pre(C.byref(self._cc_struct()), self._stream()), "lm_cc_pre")
@@ -380,8 +381,9 @@ class LocoManipulationTask:
             # second post without a pre: the reference would see last_actions == current_actions (QPC:548)
             p = self._lib.lm_task_step_parity(self._handle)
             self._actions_ring[p ^ 1].copy_(self._actions_ring[p])
-        rc = self._lib.lm_task_post_step(self._handle, self._lp(), self._mp(), self._env_pos.data_ptr(), C.byref(self._buffers),
-                                         self._stream())
+        with _lib.nvtx("post_physics_step"):
+            rc = self._lib.lm_task_post_step(self._handle, self._lp(), self._mp(), self._env_pos.data_ptr(), C.byref(self._buffers),
+                                             self._stream())
         _lib.check(rc, "lm_task_post_step")
         if self.cfg.custom_controller:
             c = self._cc_struct()

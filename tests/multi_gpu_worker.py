@@ -98,7 +98,8 @@ for name, c in (("nccl", None), ("peer", comm)):
     probe = torch.randn(512, 64, device=dev, generator=torch.Generator(device=dev).manual_seed(5)).clamp(-5, 5)
     with torch.no_grad():
         mu_k, mu_m = model(probe)[0], model.reference_forward(probe)[0]
-    check(float((mu_k - mu_m).abs().max()) < 1e-2, f"{name}: the kernels act with the updated weights")
+    err, mag = float((mu_k - mu_m).abs().max()), float(mu_m.abs().max())
+    check(err < 1e-2 * max(1.0, mag), f"{name}: the kernels act with the updated weights (|mu| up to {mag:.2f}, max err {err:.2e})")
     results[name] = (up.flat.clone(), up.opt.lr)
 d = float((results["nccl"][0] - results["peer"][0]).abs().max())
 check(d <= (0.0 if world == 2 else 1e-4), f"fused NVLink all-reduce == NCCL all-reduce (max |delta| {d:.2e})")

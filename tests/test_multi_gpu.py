@@ -16,7 +16,11 @@ def test_two_rank_collectives_and_ppo_update():
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
            "--master-port", "29611", os.path.join(ROOT, "tests", "multi_gpu_worker.py")]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
-    sys.stdout.write(res.stdout[-6000:])
+    sys.stdout.write(res.stdout[-12000:])
     sys.stderr.write(res.stderr[-3000:])
+    out_dir = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(out_dir):                          # the full transcript, for the record
+        with open(os.path.join(out_dir, "multi_gpu_worker.log"), "w") as f:
+            f.write(res.stdout + "\n---- stderr ----\n" + res.stderr[-6000:])
     assert res.returncode == 0, "a rank reported failures (see the captured output)"
     assert "FAIL" not in res.stdout
