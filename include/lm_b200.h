@@ -489,6 +489,11 @@ int lm_comm_get_handle(LmComm* c, void* handle_out);
 int lm_comm_open(LmComm* c, const void* handles);
 void lm_comm_destroy(LmComm* c);
 int lm_comm_allreduce(LmComm* c, float* data, int64_t n, void* stream);
+/* The same, with elements [gather_off, gather_off + n_f32 + n_i64 + 1) of the message taken from elsewhere instead of `data`: n_f32
+ * fp32 values times f32_scale, then n_i64 int64 counters converted to fp32, then the constant one_more (this rank's env count):
+ * the episode statistics join the gradient arena's tail in the same launch. */
+int lm_comm_allreduce_gather(LmComm* c, float* data, int64_t n, int64_t gather_off, const float* f32_src, int32_t n_f32,
+                             float f32_scale, const int64_t* i64_src, int32_t n_i64, float one_more, void* stream);
 int lm_comm_status(LmComm* c);
 int lm_mlp_wgrad_allreduce(LmComm* c, const void* dz1, const void* dz2, const void* dz3, const void* dh, const void* a0, const void* a1,
                            const void* a2, const void* a3, int64_t rows, float* workspace, int32_t workspace_ctas, float* g_w1,

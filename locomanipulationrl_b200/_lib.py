@@ -187,6 +187,7 @@ SYMBOLS = {
     "lm_comm_open": (C.c_int, [_vp, _vp]),
     "lm_comm_destroy": (None, [_vp]),
     "lm_comm_allreduce": (C.c_int, [_vp, _vp, _i64, _vp]),
+    "lm_comm_allreduce_gather": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _i32, _f, _vp, _i32, _f, _vp]),
     "lm_comm_status": (C.c_int, [_vp]),
     "lm_mlp_wgrad_allreduce": (C.c_int, [_vp] + [_vp] * 8 + [_i64, _vp, _i32] + [_vp] * 10 + [_vp, _i64, _i64, _i64, _i64, _i64, _vp]),
     "lm_gae": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _f, _f, _i32, _vp]),

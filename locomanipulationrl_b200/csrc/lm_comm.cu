@@ -41,10 +41,22 @@ namespace lm {
 namespace comm {
 
 // stand-alone all-reduce (sum) of n floats, in place.  grid <= SM count (every CTA must be resident: they wait for each other's ranks)
-__global__ void __launch_bounds__(1024, 1) k_allreduce(const Ctx c, float* __restrict__ data, long long n) {
+// Optional gather: elements [g.off, g.off + g.n_f32 + g.n_i64) of the message are taken from two other places (fp32 values, then
+// int64 counters converted to fp32) instead of `data` — the episode statistics ride in the gradient arena's tail without a
+// separate packing launch.
+struct Gather { long long off; const float* f32; int n_f32; const long long* i64; int n_i64; float f32_scale; float one_more; int has_one_more; };
+__global__ void __launch_bounds__(1024, 1) k_allreduce(const Ctx c, float* __restrict__ data, long long n, const Gather g) {
   const unsigned int epoch = epoch_of(c);
   const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x; f < n; f += stride) push(c, epoch, f, data[f]);
+  for (long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x; f < n; f += stride) {
+    const long long r = f - g.off;
+    float v;
+    if (r >= 0 && r < g.n_f32) v = g.f32[r] * g.f32_scale;
+    else if (r >= g.n_f32 && r < g.n_f32 + g.n_i64) v = (float)g.i64[r - g.n_f32];
+    else if (g.has_one_more && r == g.n_f32 + g.n_i64) v = g.one_more;
+    else v = data[f];
+    push(c, epoch, f, v);
+  }
   if (signal_and_wait(c, epoch)) {
     for (long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x; f < n; f += stride) data[f] = sum(c, epoch, f);
   }
@@ -122,14 +134,27 @@ void lm_comm_destroy(LmComm* c) {
   delete c;
 }
 
-int lm_comm_allreduce(LmComm* c, float* data, int64_t n, void* stream) {
+static int allreduce_impl(LmComm* c, float* data, int64_t n, const comm::Gather& g, void* stream) {
   if (!c || !data || n <= 0) return lm_fail(LM_ERR_BAD_ARG, "lm_comm_allreduce: bad argument");
   if (!c->opened) return lm_fail(LM_ERR_BAD_ARG, "lm_comm_allreduce: peers not opened (lm_comm_open)");
   if (n > c->slot_floats) return lm_fail(LM_ERR_BAD_ARG, "lm_comm_allreduce: %lld floats exceed the slot size %lld", (long long)n, c->slot_floats);
   const long long want = (n + 1023) / 1024;
   const int grid = (int)(want < c->sm_count ? want : c->sm_count);
-  comm::k_allreduce<<<grid, 1024, 0, (cudaStream_t)stream>>>(c->ctx, data, (long long)n);
+  comm::k_allreduce<<<grid, 1024, 0, (cudaStream_t)stream>>>(c->ctx, data, (long long)n, g);
   return lm_check_launch("lm_comm_allreduce");
+}
+
+int lm_comm_allreduce(LmComm* c, float* data, int64_t n, void* stream) {
+  const comm::Gather g{0, nullptr, 0, nullptr, 0, 1.0f, 0.0f, 0};
+  return allreduce_impl(c, data, n, g, stream);
+}
+
+int lm_comm_allreduce_gather(LmComm* c, float* data, int64_t n, int64_t gather_off, const float* f32_src, int32_t n_f32, float f32_scale,
+                             const int64_t* i64_src, int32_t n_i64, float one_more, void* stream) {
+  if (gather_off < 0 || n_f32 < 0 || n_i64 < 0 || gather_off + n_f32 + n_i64 + 1 > n || (n_f32 > 0 && !f32_src) || (n_i64 > 0 && !i64_src))
+    return lm_fail(LM_ERR_BAD_ARG, "lm_comm_allreduce_gather: bad gather range");
+  const comm::Gather g{(long long)gather_off, f32_src, n_f32, reinterpret_cast<const long long*>(i64_src), n_i64, f32_scale, one_more, 1};
+  return allreduce_impl(c, data, n, g, stream);
 }
 
 // error word of the handle: 0 = fine, 1 + r = timed out waiting for rank r (host synchronisation on the device)

@@ -73,6 +73,16 @@ class PeerComm:
         self._lib_mod.check(self._lib.lm_comm_allreduce(self.handle, t.data_ptr(), t.numel(), stream), "lm_comm_allreduce")
         return t
 
+    def all_reduce_gather(self, t: torch.Tensor, off: int, f32_src: torch.Tensor, f32_scale: float, i64_src: torch.Tensor,
+                          one_more: float) -> torch.Tensor:
+        """``all_reduce`` whose elements [off, off + len(f32_src) + len(i64_src) + 1) are f32_src * f32_scale, i64_src (-> fp32) and
+        the constant ``one_more`` instead of ``t``'s own: one launch packs and reduces."""
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        self._lib_mod.check(self._lib.lm_comm_allreduce_gather(self.handle, t.data_ptr(), t.numel(), int(off), f32_src.data_ptr(), f32_src.numel(),
+                                                               float(f32_scale), i64_src.data_ptr(), i64_src.numel(), float(one_more), stream),
+                            "lm_comm_allreduce_gather")
+        return t
+
     def status(self) -> int:
         """0, or 1 + r after a time-out waiting for rank r (host synchronisation)."""
         return int(self._lib.lm_comm_status(self.handle))
@@ -179,19 +189,32 @@ class GradArena:
 class FusedHorizonReducer:
     """Everything that crosses GPUs at a rollout boundary in ONE all-reduce: the gradient arena plus, in its 14-slot tail,
     [7 reward-term sums (mean x local envs), 6 success / reset counters, env count].  fp32 is exact for the counters
-    (< 2^24) and costs the means one rounding (6e-8 relative)."""
+    (< 2^24) and costs the means one rounding (6e-8 relative).  With a ``PeerComm`` the whole boundary is ONE launch (the all-reduce
+    kernel gathers the statistics into the message itself); through NCCL it is three small torch ops and the collective.  The
+    gradient part holds the MEAN over ranks afterwards (NCCL path) or the SUM (``PeerComm`` path: ``FlatAdam.step(grad_scale=
+    1 / world)`` averages inside its own launch) — ``grad_scale`` says which."""
     TAIL = 14
 
     def __init__(self, params: Iterable[torch.nn.Parameter], num_local_envs: int, group=None, comm: Optional[PeerComm] = None):
-        self.arena = GradArena(params, group=group, tail=self.TAIL, comm=comm)
+        self.arena = GradArena(params, group=group, tail=self.TAIL, comm=None)
         self.n = float(num_local_envs)
+        self.comm, self.group = comm, group
+
+    @property
+    def grad_scale(self) -> float:
+        """What ``FlatAdam.step(grad_scale=...)`` must apply to the arena after :meth:`reduce`."""
+        return 1.0 / self.comm.world if (self.comm is not None and self.comm.world > 1) else 1.0
 
     def reduce(self, extras_buf: torch.Tensor, counters: torch.Tensor) -> None:
-        t = self.arena.tail
+        a = self.arena
+        if self.comm is not None and self.comm.world > 1:
+            self.comm.all_reduce_gather(a.storage, a.numel, extras_buf[0:7], self.n, counters, self.n)
+            return
+        t = a.tail
         torch.mul(extras_buf[0:7], self.n, out=t[0:7])
         t[7:13].copy_(counters)
         t[13].fill_(self.n)
-        self.arena.allreduce_mean()
+        a.allreduce_mean()
 
     def result(self) -> Dict[str, torch.Tensor]:
         t = self.arena.tail

@@ -59,6 +59,27 @@ gr.replay(); torch.cuda.synchronize()                        # second replay red
 check(float((y - ref2).abs().max()) <= 1e-5 * float(ref2.abs().max()), "graph-captured all-reduce, second replay")
 check(comm.status() == 0, "no time-out recorded")
 
+# ---- 1b. the rollout-boundary reducer: statistics gathered into the message by the all-reduce kernel == the NCCL path
+from locomanipulationrl_b200.dist import FusedHorizonReducer  # noqa: E402
+extras = torch.arange(16, device=dev, dtype=torch.float32) * (rank + 1) * 0.37
+counters = torch.arange(1, 7, device=dev) * (3 * rank + 1)
+outs = []
+for c in (None, comm):
+    net = torch.nn.Linear(7, 3).to(dev)
+    fr = FusedHorizonReducer(net.parameters(), 100 * (rank + 1), comm=c)
+    for p_ in net.parameters():
+        p_.grad.fill_(float(2 * rank + 1))
+    for rep in range(2):
+        fr.reduce(extras, counters)
+        if rep == 0:
+            for p_ in net.parameters():
+                p_.grad.fill_(float(2 * rank + 1))
+    torch.cuda.synchronize()
+    r = fr.result()
+    outs.append((fr.arena.flat.clone() * fr.grad_scale, r["reward_means"].clone(), r["counters"].clone(), int(r["num_envs"])))
+check(torch.allclose(outs[0][0], outs[1][0]) and torch.allclose(outs[0][1], outs[1][1], rtol=1e-6) and torch.equal(outs[0][2], outs[1][2])
+      and outs[0][3] == outs[1][3] == 100 * world * (world + 1) // 2, "FusedHorizonReducer: peer gather path == NCCL path")
+
 
 # ---- 2. the update
 def make(seed_model, seed_data, comm_=None, **kw):
