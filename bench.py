@@ -830,7 +830,8 @@ def e2e_arm(pipe, args, world, device, rank=0, readback_obs=False, shards=None):
         tdist.all_reduce(dt, op=tdist.ReduceOp.MAX)
     return {"value": n * world * steps / float(dt.item()), "unit": "env-steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
             "steps": steps, "ms_per_step": float(dt.item()) / steps * 1e3,
-            "api": f"ShardedHostStepper.step: {shards} env shard(s) x (lm_task_step_host_async + policy forward), pinned host buffers, "
+            "api": f"ShardedHostStepper.step: {shards} env shard(s) x lm_task_step_host_policy_async (env step + policy forward + read-back in one "
+                   "C-ABI call per shard; the shards' physics-state copies queue on one copy stream), pinned host buffers, "
                    "host sync every step; H2D actions, goal uniforms, physics state; D2H next actions, value, reward, reset flags"
                    + (", observations" if readback_obs else " (observations stay on the device for the device-resident policy)")}
 
@@ -867,9 +868,9 @@ def main():
     ap.add_argument("--collective", default="peer", choices=["peer", "nccl"],
                     help="rollout-boundary all-reduce: our one-shot NVLink peer-memory kernel (default) or torch.distributed/NCCL")
     ap.add_argument("--no-train", action="store_true", help="skip the train block (rollout + GAE + PPO update)")
-    ap.add_argument("--e2e-shards", type=int, default=1,
-                    help="env shards (streams) the host-buffer step is pipelined over (measured: 1 is fastest when only 4 MB return per step - "
-                         "fewer, larger PCIe copies; 4 when the observations return too)")
+    ap.add_argument("--e2e-shards", type=int, default=4,
+                    help="env shards the host-buffer step is pipelined over: the shards' state copies queue on one copy stream, shard k's "
+                         "kernels and read-back run under shard k+1's copy")
     ap.add_argument("--no-large", action="store_true", help="skip the 524,288-env k_post roofline line")
     ap.add_argument("--no-kernel-times", action="store_true",
                     help="skip the per-kernel timing section (ncu launch lists: the capture then holds the warm-up and timed steps only)")

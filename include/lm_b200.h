@@ -561,7 +561,23 @@ typedef struct LmHostStep {
   const float* mani_state_host; int64_t mani_state_floats; float* mani_state_dev;
   float* actions_dev; float* uniforms_dev;
   float* obs_host; float* rew_host; int64_t* reset_host;
+  /* Optional dedicated host->device copy stream (NULL: the copies run on `stream`).  When several env shards hand the SAME
+   * copy stream to their calls, their input copies queue back to back at full PCIe bandwidth (instead of sharing it between
+   * concurrently running copies), and each shard's kernels start on the shard's own stream as soon as that shard's inputs have
+   * landed: shard k's kernels and device->host copies run under shard k+1's input copy.  The library orders the two streams
+   * with events it owns (inputs landed -> kernels; kernels done with the state arena -> next step's copy). */
+  void* h2d_stream;
 } LmHostStep;
+/* The policy forward that follows the env step in the same call (lm_task_step_host_policy_async): kind 0 none, 1 MLP actor-critic
+ * (handle = LmMlp*), 2 GNN on tcgen05 (LmGnn*, lm_gnn_forward_bf16), 3 GNN fp32 (lm_gnn_forward).  mu_host / value_host
+ * (pinned, may be NULL) receive the outputs by device->host copies on `stream`. */
+typedef struct LmHostPolicy {
+  int32_t kind; int32_t pad_;
+  void* handle;
+  const float* norm_mean; const float* norm_inv_std; float norm_clip; int32_t pad2_;   /* MLP only; both NULL: no standardisation */
+  float* mu_dev; float* value_dev;       /* [N,12], [N] */
+  float* mu_host; float* value_host;
+} LmHostPolicy;
 int lm_task_step_host(LmTask* task, const LmRobotViews* loco, const LmRobotViews* mani,
                       const float* env_pos, const LmTaskBuffers* buf, const LmHostStep* io, void* stream);
 /* Same, but returns as soon as the copies and kernels are enqueued on `stream` (no host synchronisation).  A batch
@@ -570,6 +586,10 @@ int lm_task_step_host(LmTask* task, const LmRobotViews* loco, const LmRobotViews
  * full duplex); the caller then waits with lm_stream_synchronize on each shard's stream. */
 int lm_task_step_host_async(LmTask* task, const LmRobotViews* loco, const LmRobotViews* mani,
                             const float* env_pos, const LmTaskBuffers* buf, const LmHostStep* io, void* stream);
+/* lm_task_step_host_async followed by the policy forward on the step's observations and the device->host copies of its outputs,
+ * all enqueued by ONE call (one shard of a host-driven step costs one library call instead of five). */
+int lm_task_step_host_policy_async(LmTask* task, const LmRobotViews* loco, const LmRobotViews* mani, const float* env_pos,
+                                   const LmTaskBuffers* buf, const LmHostStep* io, const LmHostPolicy* policy, void* stream);
 int lm_stream_synchronize(void* stream);
 
 #ifdef __cplusplus

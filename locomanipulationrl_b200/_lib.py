@@ -59,7 +59,13 @@ class LmHostStep(C.Structure):
                 ("loco_state_host", C.c_void_p), ("loco_state_floats", _i64), ("loco_state_dev", C.c_void_p),
                 ("mani_state_host", C.c_void_p), ("mani_state_floats", _i64), ("mani_state_dev", C.c_void_p),
                 ("actions_dev", C.c_void_p), ("uniforms_dev", C.c_void_p),
-                ("obs_host", C.c_void_p), ("rew_host", C.c_void_p), ("reset_host", C.c_void_p)]
+                ("obs_host", C.c_void_p), ("rew_host", C.c_void_p), ("reset_host", C.c_void_p), ("h2d_stream", C.c_void_p)]
+
+
+class LmHostPolicy(C.Structure):
+    _fields_ = [("kind", _i32), ("pad_", _i32), ("handle", C.c_void_p), ("norm_mean", C.c_void_p), ("norm_inv_std", C.c_void_p),
+                ("norm_clip", C.c_float), ("pad2_", _i32), ("mu_dev", C.c_void_p), ("value_dev", C.c_void_p),
+                ("mu_host", C.c_void_p), ("value_host", C.c_void_p)]
 
 
 class LmPdState(C.Structure):
@@ -194,6 +200,8 @@ SYMBOLS = {
     "lm_gae_env_major": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _f, _f, _i32, _vp]),
     "lm_task_step_host": (C.c_int, [_vp, C.POINTER(LmRobotViews), C.POINTER(LmRobotViews), _vp, C.POINTER(LmTaskBuffers), C.POINTER(LmHostStep), _vp]),
     "lm_task_step_host_async": (C.c_int, [_vp, C.POINTER(LmRobotViews), C.POINTER(LmRobotViews), _vp, C.POINTER(LmTaskBuffers), C.POINTER(LmHostStep), _vp]),
+    "lm_task_step_host_policy_async": (C.c_int, [_vp, C.POINTER(LmRobotViews), C.POINTER(LmRobotViews), _vp, C.POINTER(LmTaskBuffers), C.POINTER(LmHostStep),
+                                                 C.POINTER(LmHostPolicy), _vp]),
     "lm_stream_synchronize": (C.c_int, [_vp]),
 }
 
@@ -222,7 +230,7 @@ def load(path: Optional[str] = None) -> C.CDLL:
         fn.argtypes = args
     if lib.lm_abi_version() != 1:
         raise LmError("liblm_b200.so ABI version mismatch")
-    for which, struct in enumerate((LmTaskParams, LmRobotViews, LmTaskBuffers, LmHostStep, LmPdState, LmRunningStats, LmRolloutStep, LmRolloutBuffers, LmPpoBatch, LmNoiseSpec, LmNoiseState, LmCustomController, LmAdamSchedule, LmActionSink)):
+    for which, struct in enumerate((LmTaskParams, LmRobotViews, LmTaskBuffers, LmHostStep, LmPdState, LmRunningStats, LmRolloutStep, LmRolloutBuffers, LmPpoBatch, LmNoiseSpec, LmNoiseState, LmCustomController, LmAdamSchedule, LmActionSink, LmHostPolicy)):
         if lib.lm_struct_size(which) != C.sizeof(struct):
             raise LmError(f"struct layout mismatch for {struct.__name__}: C {lib.lm_struct_size(which)} vs ctypes {C.sizeof(struct)}")
     _lib = lib

@@ -12,8 +12,8 @@
 //     pipe runs underneath the epilogue instead of after it;
 //   * every layer has its own TMEM accumulator columns (256 + 128 + 64 + 16 of the 512), so the next tile's layer-1
 //     MMA is issued while the current tile is still in layers 2-4;
-//   * the next tile's observations are fetched into registers one tile ahead (coalesced 128-bit loads),
-//     normalised/clamped and written as the bf16 A0 operand in the bubble between the layer-1 and layer-2 epilogues.
+//   * the next tile's observations are fetched into registers one tile ahead (coalesced 128-bit loads), normalised/clamped
+//     and written as the bf16 A0 operand inside the layer-1 epilogue's sub-steps (one float4 per sub-step).
 // Activations never touch HBM; per env the kernel reads 256 B and writes 52 B.
 #include <cuda_bf16.h>
 #include <string.h>
@@ -31,6 +31,10 @@ using namespace tc;
 #ifndef LM_MLP_FMA_PAIRS
 #define LM_MLP_FMA_PAIRS 0
 #endif
+#ifndef LM_MLP_PIECES
+#define LM_MLP_PIECES 2
+#endif
+constexpr int kPc = LM_MLP_PIECES;        // 16-column pieces per warp between two proxy fences (layers 1 and 2)
 constexpr int TM = 128;                 // rows (envs) per tile == UMMA M
 constexpr int E_WARPS = 16;               // epilogue warps: 4 TMEM lane groups x 4 column quarters
 constexpr int E_THREADS = E_WARPS * 32;
@@ -46,16 +50,19 @@ constexpr int BIAS_OFF = WH_OFF + operand_bytes(DH, D3);          // fp32 biases
 constexpr int BLOB_BYTES = BIAS_OFF + (D1 + D2 + D3 + DH) * 4;
 static_assert(BLOB_BYTES % 16 == 0 && W2_OFF % 16 == 0 && W3_OFF % 16 == 0 && WH_OFF % 16 == 0 && BIAS_OFF % 16 == 0, "align");
 
-// activation regions (bf16 A operands).  A1 [128 x 256] never exists as a whole: the layer-1 epilogue produces it in four
-// 64-column K chunks that layer 2 consumes at once, so a ring of two chunk slots is enough.
+// activation regions (bf16 A operands).  A1 [128 x 256] = four 64-column K chunks (slots) that the layer-1 epilogue produces one by
+// one and layer 2 consumes at once.  Slots 2-3 are ALIASED onto A2: A2 is only live from E2(t) until layer 3 of tile t has read
+// it, A1's chunks 2-3 from E1's sub-steps 2-3 until layer 2 has read them (= before E2 starts), so the two never overlap; the only
+// condition — layer 3 of tile t-1 complete before sub-step 2 of E1(t) stores — holds long before that store is reached.  (A two-slot
+// ring in the same memory made sub-step s wait for the layer-2 MMAs of chunk s-2: 20.3 -> 18.4 us per launch at 65,536 envs.)
 constexpr int CHUNK_BYTES = operand_bytes(TM, 64);                // one 64-wide K chunk of an A operand (= A0, A3)
-constexpr int RING_OFF = BLOB_BYTES;                              // A1 chunk ring: 2 slots
-constexpr int A2_OFF = RING_OFF + 2 * CHUNK_BYTES;                // A2 [128 x 128]
+constexpr int A1_OFF = BLOB_BYTES;                                // A1 slots 0..3
+constexpr int A2_OFF = A1_OFF + 2 * CHUNK_BYTES;                  // A2 [128 x 128] = slots 2-3 of A1
 constexpr int A0_OFF = A2_OFF + operand_bytes(TM, D2);            // A0 [128 x 64]
 constexpr int A3_OFF = A0_OFF + CHUNK_BYTES;                      // A3 [128 x 64]
 constexpr int SMEM_BYTES = A3_OFF + CHUNK_BYTES + 64;
 static_assert(SMEM_BYTES <= 232448, "exceeds 227 KB");
-static_assert(RING_OFF % 16 == 0 && CHUNK_BYTES % 16 == 0, "align");
+static_assert(A1_OFF % 16 == 0 && CHUNK_BYTES % 16 == 0, "align");
 // TMEM accumulator columns
 constexpr uint32_t ACC1_COL = 0, ACC2_COL = 256, ACC3_COL = 384, ACCH_COL = 448, TMEM_COLS = 512;
 
@@ -92,37 +99,51 @@ __device__ __forceinline__ void store16(const uint32_t (&w)[8], uint8_t* dst, in
   }
 }
 
-// Hidden-layer epilogue of one warp: kSub sub-steps; in sub-step s the 16 warps together cover accumulator columns
-// [64 s, 64 s + 64) (this warp: 16 of them), i.e. K chunk s of the next layer, written to dst + (s % kSlots) * CHUNK_BYTES,
-// and signal `bars[s]`.  With a ring (kSlots < kSub) sub-step s >= kSlots first waits until the MMAs of chunk s - kSlots have
-// drained (`slot_free[s - kSlots]`).
-// The ELU arithmetic of sub-step s+1 is written ahead of the fence / arrival of sub-step s, with the TMEM load of s+2 in flight: the
-// scheduler is free to fill the stores' completion latency with the next sub-step's MUFU work.
-template <int kSub, int kSlots>
-__device__ __forceinline__ void epilogue_hidden(uint32_t tmem_acc, const float* __restrict__ bias, uint8_t* dst, uint64_t* bars,
-                                                uint64_t* slot_free, uint32_t slot_parity, int g, int q, int lane, uint8_t* gsave = nullptr) {
+// Hidden-layer epilogue of one warp.  The layer's accumulator is handed to the next layer in kMacro steps; in step m the 16 warps
+// together cover accumulator columns [W m, W (m + 1)), W = 64 kPieces (this warp: 16 kPieces of them, as kPieces TMEM loads of 16
+// columns), i.e. kPieces 64-wide K chunks of the next layer's A operand, then publish them with ONE proxy fence and ONE arrival on
+// `bars[m]` (LM_MLP_PIECES = 1: a fence per 16 columns, 7 per tile; 2: 4 per tile).  The ELU arithmetic of the next piece is
+// written ahead of the fence, with the TMEM load after it issued as soon as its registers are free.
+// `hook(k)` runs once per piece k before the following fence (shared-memory stores made there are published by the same fence).
+// `alias_bar`: waited before the first store into A1 slot 2 (= A2's memory, see above).
+struct NoHook { __device__ __forceinline__ void operator()(int) const {} };
+template <int kMacro, int kPieces, typename Hook = NoHook>
+__device__ __forceinline__ void epilogue_hidden(uint32_t tmem_acc, const float* __restrict__ bias, uint8_t* dst, uint64_t* bars, int g, int q,
+                                                int lane, uint8_t* gsave = nullptr, uint64_t* alias_bar = nullptr, uint32_t alias_parity = 0,
+                                                Hook hook = Hook()) {
+  constexpr int kN = kMacro * kPieces;
   const int row = g * 32 + lane;
-  const uint32_t taddr = tmem_acc + ((uint32_t)(g * 32) << 16) + (uint32_t)(q * 16);
+  // piece k = (m, p): columns c0(k) = 64 kPieces m + 16 kPieces q + 16 p
+  auto c0 = [&](int k) { return 64 * kPieces * (k / kPieces) + 16 * kPieces * q + 16 * (k % kPieces); };
+  const uint32_t tbase = tmem_acc + ((uint32_t)(g * 32) << 16);
   uint32_t a[16], b[16], w[8];
-  tmem_ld16(taddr, a);
+  tmem_ld16(tbase + c0(0), a);
   tmem_wait();
-  if (kSub > 1) tmem_ld16(taddr + 64, b);
-  elu16(a, bias, q * 16, w);
+  if (kN > 1) tmem_ld16(tbase + c0(1), b);
+  elu16(a, bias, c0(0), w);
 #pragma unroll
-  for (int s = 0; s < kSub; ++s) {
-    uint32_t* nxt = (s & 1) ? a : b;          // holds sub-step s + 1 (in flight or landed)
-    uint32_t* free_buf = (s & 1) ? b : a;     // sub-step s: already consumed into w
-    if (s >= kSlots) mbar_wait(&slot_free[s - kSlots], slot_parity);
-    store16(w, dst + (s % kSlots) * CHUNK_BYTES, row, q * 16, gsave != nullptr ? gsave + s * CHUNK_BYTES : nullptr);
-    if (s + 1 < kSub) {
+  for (int k = 0; k < kN; ++k) {
+    uint32_t* nxt = (k & 1) ? a : b;          // holds piece k + 1 (in flight or landed)
+    uint32_t* free_buf = (k & 1) ? b : a;     // piece k: already consumed into w
+    const int c = c0(k);
+    if (alias_bar != nullptr && c / 64 >= 2 && (k == 0 || c0(k - 1) / 64 < 2)) mbar_wait(alias_bar, alias_parity);
+    store16(w, dst + (c / 64) * CHUNK_BYTES, row, c % 64, gsave != nullptr ? gsave + (c / 64) * CHUNK_BYTES : nullptr);
+    if (k + 1 < kN) {
       tmem_wait();
-      if (s + 2 < kSub) tmem_ld16(taddr + 64 * (s + 2), free_buf);
-      elu16(nxt, bias + 64 * (s + 1), q * 16, w);
+#ifdef LM_DIAG_HALF_LDTM      // diagnostic (wrong results): every other TMEM load skipped -> is the kernel TMEM-read bound?
+      if (k + 2 < kN && ((k + 2) & 1) == 0) tmem_ld16(tbase + c0(k + 2), free_buf);
+#else
+      if (k + 2 < kN) tmem_ld16(tbase + c0(k + 2), free_buf);
+#endif
+      elu16(nxt, bias, c0(k + 1), w);
     }
-    fence_proxy_async();                       // generic-proxy A operand writes -> visible to the tensor core's async proxy
-    tc_fence_before();                         // orders this warp's tcgen05.ld before the MMA that reuses the accumulator
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&bars[s]);
+    hook(k);
+    if (k % kPieces == kPieces - 1) {
+      fence_proxy_async();                     // generic-proxy A operand writes -> visible to the tensor core's async proxy
+      tc_fence_before();                       // orders this warp's tcgen05.ld before the MMA that reuses the accumulator
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[k / kPieces]);
+    }
   }
 }
 
@@ -143,9 +164,11 @@ struct Args {
   LmActionSink sink; int has_sink;
 };
 
-// diagnostic timeline (lm_mlp_forward_timeline): slot k <- clock64(), first writer wins per launch
+// diagnostic timeline (lm_mlp_set_timeline): slot k <- clock64() of CTA 0.  Compiled into the kStamp instantiation only, which is
+// launched while a timeline buffer is registered: the production kernel carries none of these instructions.
+template <bool kStamp>
 __device__ __forceinline__ void stamp(const Args& a, int k) {
-  if (a.timeline != nullptr && blockIdx.x == 0) a.timeline[k] = clock64();
+  if (kStamp && a.timeline != nullptr && blockIdx.x == 0) a.timeline[k] = clock64();
 }
 
 struct ObsRegs { float4 v[4]; };
@@ -160,65 +183,57 @@ __device__ __forceinline__ void obs_fetch(const Args& a, int tile, int tid, ObsR
     r.v[j] = row < rows ? ld_nc_f4(base + (size_t)(j * E_THREADS + tid) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
 }
-__device__ __forceinline__ void obs_convert(const Args& a, int tile, int tid, const ObsRegs& r, const float4& mean, const float4& inv_std,
-                                            bool has_norm, uint8_t* A0, uint8_t* gA0 = nullptr) {
-  const int rows = min(TM, a.n - tile * TM);
+// float4 j of the thread: normalise / clamp, bf16, into the A0 operand (and the training forward's saved copy)
+// (`rows`: valid rows of the tile, computed once per tile by the caller; rows beyond the batch stay zero)
+__device__ __forceinline__ void obs_convert_one(const Args& a, int rows, int tid, int j, const ObsRegs& r, const float4& mean, const float4& inv_std,
+                                                bool has_norm, uint8_t* A0, uint8_t* gA0) {
   const int c4 = tid & 15;
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int row = j * 32 + (tid >> 4);
-    float4 x = r.v[j];
-    if (has_norm && row < rows) {
-      x.x = fminf(fmaxf((x.x - mean.x) * inv_std.x, -a.norm_clip), a.norm_clip);
-      x.y = fminf(fmaxf((x.y - mean.y) * inv_std.y, -a.norm_clip), a.norm_clip);
-      x.z = fminf(fmaxf((x.z - mean.z) * inv_std.z, -a.norm_clip), a.norm_clip);
-      x.w = fminf(fmaxf((x.w - mean.w) * inv_std.w, -a.norm_clip), a.norm_clip);
-    }
-    const uint2 w = make_uint2(pack_bf16(x.x, x.y), pack_bf16(x.z, x.w));
-    *reinterpret_cast<uint2*>(A0 + elem_offset(TM, row, 4 * c4)) = w;
-    if (gA0 != nullptr) *reinterpret_cast<uint2*>(gA0 + elem_offset(TM, row, 4 * c4)) = w;
+  const int row = j * 32 + (tid >> 4);
+  float4 x = r.v[j];
+  if (has_norm && row < rows) {
+    x.x = fminf(fmaxf((x.x - mean.x) * inv_std.x, -a.norm_clip), a.norm_clip);
+    x.y = fminf(fmaxf((x.y - mean.y) * inv_std.y, -a.norm_clip), a.norm_clip);
+    x.z = fminf(fmaxf((x.z - mean.z) * inv_std.z, -a.norm_clip), a.norm_clip);
+    x.w = fminf(fmaxf((x.w - mean.w) * inv_std.w, -a.norm_clip), a.norm_clip);
   }
+  const uint2 w = make_uint2(pack_bf16(x.x, x.y), pack_bf16(x.z, x.w));
+  *reinterpret_cast<uint2*>(A0 + elem_offset(TM, row, 4 * c4)) = w;
+  if (gA0 != nullptr) *reinterpret_cast<uint2*>(gA0 + elem_offset(TM, row, 4 * c4)) = w;
 }
 
-// head epilogue of one lane-group warp: 16 accumulator columns -> +bias -> mu[12], value.  With an action sink the three
-// destinations of a row (mu / value, current_actions, joint targets) are written by three different column-quarter warps
-// (q = 0, 1, 2 all read the same 16 accumulator columns), so the stores of a tile leave in parallel instead of in a row.
+// Head epilogue, spread over the four column-quarter warps of a lane group: quarter q reads accumulator columns [4q, 4q + 4) —
+// q = 0..2: four policy means -> mu (and, with an action sink, the same chunk into the task's action ring / joint targets),
+// q = 3: column 12 -> value.  Every warp does a quarter of the work instead of one warp per scheduler doing all of it.
 __device__ __forceinline__ void epilogue_head(const Args& a, uint32_t tmem_acc, const float* __restrict__ biash, int tile, int g, int lane, int q) {
-  uint32_t acc[16];
-  tmem_ld16(tmem_acc + ((uint32_t)(g * 32) << 16), acc);
+  uint32_t acc[4];
+  tmem_ld4(tmem_acc + ((uint32_t)(g * 32) << 16) + (uint32_t)(4 * q), acc);
   tmem_wait();
   tc_fence_before();
   const int row0 = tile * TM, rows = min(TM, a.n - row0);
   const int row = g * 32 + lane;
   if (row < rows) {
-    float o[13];
-#pragma unroll
-    for (int j = 0; j < 13; ++j) o[j] = __uint_as_float(acc[j]) + biash[j];
-    if (q == 0) {
-      float4* m = reinterpret_cast<float4*>(a.mu + (size_t)(row0 + row) * 12);
-      m[0] = make_float4(o[0], o[1], o[2], o[3]);
-      m[1] = make_float4(o[4], o[5], o[6], o[7]);
-      m[2] = make_float4(o[8], o[9], o[10], o[11]);
-      a.value[row0 + row] = o[12];
+    const float4 b = *reinterpret_cast<const float4*>(biash + 4 * q);
+    const float4 o = make_float4(__uint_as_float(acc[0]) + b.x, __uint_as_float(acc[1]) + b.y, __uint_as_float(acc[2]) + b.z, __uint_as_float(acc[3]) + b.w);
+    if (q < 3) {
+      reinterpret_cast<float4*>(a.mu + (size_t)(row0 + row) * 12)[q] = o;
+      if (a.has_sink) sink_store(a.sink, row0 + row, q, o);
     } else {
-#pragma unroll
-      for (int qq = 0; qq < 3; ++qq)
-        sink_store(a.sink, row0 + row, qq, make_float4(o[4 * qq], o[4 * qq + 1], o[4 * qq + 2], o[4 * qq + 3]), q == 1, q == 2);
+      a.value[row0 + row] = o.x;
     }
   }
 }
 
-template <bool kSave>
+template <bool kSave, bool kStamp = false>
 __global__ void __launch_bounds__(THREADS, 1) k_mlp_forward(const Args a) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  // mbarriers.  count 1: bar_w (weight TMA), bar_acc* and bar_c2[s] (tcgen05.commit: accumulator complete / layer-2 K chunk s
-  // consumed).  count 16 (one arrive per epilogue warp): bar_a0 (A0 operand written), bar_act1[s] / bar_act2[s] / bar_act3
-  // (K chunk s of the next layer's A operand written; for the last sub-step also: accumulator fully read).  Every barrier
-  // completes exactly once per tile, so the parity of a wait is the parity of the CTA-local tile index.
-  __shared__ uint64_t bar_w, bar_a0, bar_acc1, bar_acc2, bar_acc3, bar_acch, bar_c2[2], bar_act1[4], bar_act2[2], bar_act3[1];
+  // mbarriers.  count 1: bar_w (weight TMA), bar_acc* (tcgen05.commit: accumulator complete).  count 16 (one arrive per epilogue
+  // warp): bar_a0 (A0 operand written), bar_act1[s] / bar_act2[s] / bar_act3 (K chunk s of the next layer's A operand written; for
+  // the last sub-step also: accumulator fully read).  Every barrier completes exactly once per tile, so the parity of a wait is the
+  // parity of the CTA-local tile index.
+  __shared__ uint64_t bar_w, bar_a0, bar_acc1, bar_acc2, bar_acc3, bar_acch, bar_act1[4 / kPc], bar_act2[2 / kPc], bar_act3[1];
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  uint8_t* RING = smem + RING_OFF;
+  uint8_t* A1 = smem + A1_OFF;
   uint8_t* A2 = smem + A2_OFF;
   uint8_t* A0 = smem + A0_OFF;
   uint8_t* A3 = smem + A3_OFF;
@@ -231,9 +246,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_mlp_forward(const Args a) {
   if (tid == 0) {
     mbar_init(&bar_w, 1); mbar_init(&bar_a0, E_WARPS);
     mbar_init(&bar_acc1, 1); mbar_init(&bar_acc2, 1); mbar_init(&bar_acc3, 1); mbar_init(&bar_acch, 1);
-    mbar_init(&bar_c2[0], 1); mbar_init(&bar_c2[1], 1);
-    for (int s = 0; s < 4; ++s) mbar_init(&bar_act1[s], E_WARPS);
-    for (int s = 0; s < 2; ++s) mbar_init(&bar_act2[s], E_WARPS);
+    for (int s = 0; s < 4 / kPc; ++s) mbar_init(&bar_act1[s], E_WARPS);
+    for (int s = 0; s < 2 / kPc; ++s) mbar_init(&bar_act2[s], E_WARPS);
     mbar_init(&bar_act3[0], E_WARPS);
     fence_mbar_init();
   }
@@ -242,12 +256,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_mlp_forward(const Args a) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
-  if (tid == 0) stamp(a, 0);
+  if (tid == 0) stamp<kStamp>(a, 0);
   const int tile0 = blockIdx.x, stride = gridDim.x;
   const int n_loc = tile0 < a.num_tiles ? (a.num_tiles - tile0 + stride - 1) / stride : 0;   // tiles of this CTA
 
   // Software pipeline over the CTA's tiles (iteration `it` = tile t).  Epilogue warps run, per iteration,
-  //   E1(t) -> obs(t+1) to A0 -> heads(t-2) -> E3(t-1) -> E2(t)
+  //   E1(t) [+ obs(t+1) -> A0, one float4 per sub-step] -> heads(t-2) -> E3(t-1) -> E2(t)
   // so that every wait on a tensor-core result (acc2(t) after E1(t), acc3(t) after E2(t), heads(t) after E3(t)) has a
   // full layer's worth of other work in front of it.  The control thread issues MMAs in the matching order.
   if (warp == E_WARPS) {
@@ -256,9 +270,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_mlp_forward(const Args a) {
       mbar_expect_tx(&bar_w, BLOB_BYTES);
       tma_load_1d(smem, a.blob, BLOB_BYTES, &bar_w);      // resident weights + biases: one bulk copy per CTA
       mbar_wait(&bar_w, 0);
-      stamp(a, 1);
+      stamp<kStamp>(a, 1);
       const uint32_t sW1 = smem_u32(smem + W1_OFF), sW2 = smem_u32(smem + W2_OFF), sW3 = smem_u32(smem + W3_OFF), sWH = smem_u32(smem + WH_OFF);
-      const uint32_t sRING = smem_u32(RING), sA2 = smem_u32(A2), sA0 = smem_u32(A0), sA3 = smem_u32(A3);
+      const uint32_t sA1 = smem_u32(A1), sA2 = smem_u32(A2), sA0 = smem_u32(A0), sA3 = smem_u32(A3);
       if (n_loc > 0) {
         mbar_wait(&bar_a0, 0);
         tc_fence_after();
@@ -270,10 +284,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_mlp_forward(const Args a) {
         // layer 2 of tile t: K chunk s as soon as the layer-1 epilogue has produced it
 #pragma unroll
         for (int s = 0; s < 4; ++s) {
-          mbar_wait(&bar_act1[s], ph);
-          tc_fence_after();
-          issue_ksteps<D2>(tmem + ACC2_COL, sRING + (s & 1) * CHUNK_BYTES, sW2, 4 * s);
-          if (s < 2) umma_commit(&bar_c2[s]);             // ring slot s free again once these MMAs have drained
+          if (s % kPc == 0) {
+            mbar_wait(&bar_act1[s / kPc], ph);
+            tc_fence_after();
+          }
+          issue_ksteps<D2>(tmem + ACC2_COL, sA1 + s * CHUNK_BYTES, sW2, 4 * s);
         }
         umma_commit(&bar_acc2);
         // layer 1 of tile t+1 (its accumulator columns were released by the last layer-1 sub-step above)
@@ -293,8 +308,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_mlp_forward(const Args a) {
         // layer 3 of tile t
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
-          mbar_wait(&bar_act2[s], ph);
-          tc_fence_after();
+          if (s % kPc == 0) {
+            mbar_wait(&bar_act2[s / kPc], ph);
+            tc_fence_after();
+          }
           issue_ksteps<D3>(tmem + ACC3_COL, sA2 + s * CHUNK_BYTES, sW3, 4 * s);
         }
         umma_commit(&bar_acc3);
@@ -324,74 +341,77 @@ __global__ void __launch_bounds__(THREADS, 1) k_mlp_forward(const Args a) {
     pdl_wait();                                            // the observations are the predecessor kernel's output
     if (n_loc > 0) {
       obs_fetch(a, tile0, tid, regs);
-      obs_convert(a, tile0, tid, regs, mean, inv_std, has_norm, A0, g0(tile0));
+#pragma unroll
+      for (int j = 0; j < 4; ++j) obs_convert_one(a, min(TM, a.n - tile0 * TM), tid, j, regs, mean, inv_std, has_norm, A0, g0(tile0));
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_a0);
       if (n_loc > 1) obs_fetch(a, tile0 + stride, tid, regs);
     }
     const bool st = tid == 0;
-    if (st) stamp(a, 2);
+    if (st) stamp<kStamp>(a, 2);
     mbar_wait(&bar_w, 0);                                  // biases live in the weight blob
     for (int it = 0; it < n_loc; ++it) {
       const uint32_t ph = it & 1;
       const int tile = tile0 + it * stride;
-      // ---- E1(t): TMEM[128 x 256] -> A1, four K chunks through the two-slot ring
-      if (st) stamp(a, 8 + 8 * it + 0);
+      const bool more = it + 1 < n_loc;
+      // ---- E1(t): TMEM[128 x 256] -> A1, four K chunks.  Layer 1 of tile t has consumed A0 (bar_acc1), so sub-step s also converts
+      // float4 s of this thread's share of tile t+1's observations into A0: the conversion rides in the MUFU-bound sub-steps' spare
+      // issue slots and its stores are published by the epilogue's own fences.
+      if (st) stamp<kStamp>(a, 8 + 8 * it + 0);
       mbar_wait(&bar_acc1, ph);
       tc_fence_after();
-      if (st) stamp(a, 8 + 8 * it + 1);
-      epilogue_hidden<4, 2>(tmem + ACC1_COL, bias1, RING, bar_act1, bar_c2, ph, g, q, lane, g1(tile));
-      if (st) stamp(a, 8 + 8 * it + 2);
-      // ---- observations of tile t+1 -> A0 (layer 1 of tile t has consumed A0), then fetch tile t+2
-      if (it + 1 < n_loc) {
-        obs_convert(a, tile + stride, tid, regs, mean, inv_std, has_norm, A0, g0(tile + stride));
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bar_a0);
+      if (st) stamp<kStamp>(a, 8 + 8 * it + 1);
+      uint8_t* gA0n = more ? g0(tile + stride) : nullptr;
+      const int rows_n = min(TM, a.n - (tile + stride) * TM);
+      auto obs_hook = [&](int s) { if (more) obs_convert_one(a, rows_n, tid, s, regs, mean, inv_std, has_norm, A0, gA0n); };
+      epilogue_hidden<4 / kPc, kPc>(tmem + ACC1_COL, bias1, A1, bar_act1, g, q, lane, g1(tile), it >= 1 ? &bar_acc3 : nullptr, ph ^ 1, obs_hook);
+      if (st) stamp<kStamp>(a, 8 + 8 * it + 2);
+      if (more) {
+        if (lane == 0) mbar_arrive(&bar_a0);               // behind the last fence of E1
         if (it + 2 < n_loc) obs_fetch(a, tile + 2 * stride, tid, regs);
       }
-      if (st) stamp(a, 8 + 8 * it + 3);
+      if (st) stamp<kStamp>(a, 8 + 8 * it + 3);
       // ---- heads of tile t-2 (every warp waits: A3 must be drained before E3(t-1) overwrites it)
       if (it >= 2) {
         mbar_wait(&bar_acch, ph);
         tc_fence_after();
-        if (q == 0 || (a.has_sink && q < 3)) epilogue_head(a, tmem + ACCH_COL, biash, tile - 2 * stride, g, lane, q);
+        epilogue_head(a, tmem + ACCH_COL, biash, tile - 2 * stride, g, lane, q);
       }
       // ---- E3(t-1): TMEM[128 x 64] -> A3
-      if (st) stamp(a, 8 + 8 * it + 4);
+      if (st) stamp<kStamp>(a, 8 + 8 * it + 4);
       if (it >= 1) {
         mbar_wait(&bar_acc3, ph ^ 1);
         tc_fence_after();
-        epilogue_hidden<1, 1>(tmem + ACC3_COL, bias3, A3, bar_act3, nullptr, 0, g, q, lane, g3(tile - stride));
+        epilogue_hidden<1, 1>(tmem + ACC3_COL, bias3, A3, bar_act3, g, q, lane, g3(tile - stride));
       }
       // ---- E2(t): TMEM[128 x 128] -> A2 (layer 3 of tile t-1 has finished reading it: bar_acc3 above)
-      if (st) stamp(a, 8 + 8 * it + 5);
+      if (st) stamp<kStamp>(a, 8 + 8 * it + 5);
       mbar_wait(&bar_acc2, ph);
       tc_fence_after();
-      if (st) stamp(a, 8 + 8 * it + 6);
-      epilogue_hidden<2, 2>(tmem + ACC2_COL, bias2, A2, bar_act2, nullptr, 0, g, q, lane, g2(tile));
-      if (st) stamp(a, 8 + 8 * it + 7);
+      if (st) stamp<kStamp>(a, 8 + 8 * it + 6);
+      epilogue_hidden<2 / kPc, kPc>(tmem + ACC2_COL, bias2, A2, bar_act2, g, q, lane, g2(tile));
+      if (st) stamp<kStamp>(a, 8 + 8 * it + 7);
     }
     // ---- drain: heads(n-2), E3(n-1), heads(n-1)
     if (n_loc >= 2) {
       mbar_wait(&bar_acch, n_loc & 1);
       tc_fence_after();
-      if (q == 0 || (a.has_sink && q < 3)) epilogue_head(a, tmem + ACCH_COL, biash, tile0 + (n_loc - 2) * stride, g, lane, q);
+      epilogue_head(a, tmem + ACCH_COL, biash, tile0 + (n_loc - 2) * stride, g, lane, q);
     }
     if (n_loc >= 1) {
       mbar_wait(&bar_acc3, (n_loc - 1) & 1);
       tc_fence_after();
-      epilogue_hidden<1, 1>(tmem + ACC3_COL, bias3, A3, bar_act3, nullptr, 0, g, q, lane, g3(tile0 + (n_loc - 1) * stride));
+      epilogue_hidden<1, 1>(tmem + ACC3_COL, bias3, A3, bar_act3, g, q, lane, g3(tile0 + (n_loc - 1) * stride));
       mbar_wait(&bar_acch, (n_loc - 1) & 1);
       tc_fence_after();
-      if (q == 0 || (a.has_sink && q < 3)) epilogue_head(a, tmem + ACCH_COL, biash, tile0 + (n_loc - 1) * stride, g, lane, q);
+      epilogue_head(a, tmem + ACCH_COL, biash, tile0 + (n_loc - 1) * stride, g, lane, q);
     }
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (tid == 0) stamp(a, 3);
+  if (tid == 0) stamp<kStamp>(a, 3);
   if (warp == E_WARPS) tmem_dealloc(tmem, TMEM_COLS);
 }
 
@@ -446,6 +466,7 @@ LmMlp* lm_mlp_create(int device) {
   cudaMemset(m->blob, 0, BLOB_BYTES);
   e = cudaFuncSetAttribute(k_mlp_forward<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_mlp_forward<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_mlp_forward<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   if (e != cudaSuccess) { lm_set_error("lm_mlp_create: smem attribute: %s", cudaGetErrorString(e)); cudaFree(m->blob); delete m; return nullptr; }
   return m;
 }
@@ -501,7 +522,9 @@ int lm_mlp_forward_sink(LmMlp* m, const float* obs, const float* norm_mean, cons
   // The resident-weight TMA is issued before pdl_wait(): allowed only while the blob is not being rewritten upstream.
   const bool pdl = !m->fresh_pack;
   m->fresh_pack = false;
-  cudaError_t le = lm_launch(k_mlp_forward<false>, dim3(grid), dim3(THREADS), SMEM_BYTES, (cudaStream_t)stream, pdl, a);
+  cudaError_t le = a.timeline != nullptr
+                       ? lm_launch(k_mlp_forward<false, true>, dim3(grid), dim3(THREADS), SMEM_BYTES, (cudaStream_t)stream, pdl, a)
+                       : lm_launch(k_mlp_forward<false>, dim3(grid), dim3(THREADS), SMEM_BYTES, (cudaStream_t)stream, pdl, a);
   if (le != cudaSuccess) return lm_fail((int)le, "lm_mlp_forward: %s", cudaGetErrorString(le));
   return lm_check_launch("lm_mlp_forward");
 }

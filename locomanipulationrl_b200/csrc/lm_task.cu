@@ -1193,6 +1193,9 @@ struct LmTask {
   int clamp_observations;
   long long* timeline;
   int scan_valid;            // tile_offsets / num_reset were produced by the last post_step and reset_buf is untouched since
+  // host-buffer step with a dedicated copy stream (LmHostStep.h2d_stream): state landed / state arena free for the next copy
+  cudaEvent_t ev_state, ev_consumed;
+  int have_events;
 };
 
 static void host_rot_from_quat(const float q[4], float m[9]) {   // same formulas as lm::rot_from_quat_scipy
@@ -1233,6 +1236,7 @@ int lm_struct_size(int which) {
     case 11: return (int)sizeof(LmCustomController);
     case 12: return (int)sizeof(LmAdamSchedule);
     case 13: return (int)sizeof(LmActionSink);
+    case 14: return (int)sizeof(LmHostPolicy);
     default: return -1;
   }
 }
@@ -1301,6 +1305,7 @@ LmTask* lm_task_create(const LmTaskParams* params, int device) {
 void lm_task_destroy(LmTask* t) {
   if (!t) return;
   cudaFree(t->tile_counts); cudaFree(t->tile_offsets); cudaFree(t->scan_base); cudaFree(t->partials); cudaFree(t->tickets);
+  if (t->have_events) { cudaEventDestroy(t->ev_state); cudaEventDestroy(t->ev_consumed); }
   delete t;
 }
 
@@ -1489,8 +1494,18 @@ static int step_host_impl(LmTask* t, const LmRobotViews* loco, const LmRobotView
                           const LmTaskBuffers* buf, const LmHostStep* io, void* stream, bool sync) {
   if (!t || !io) return lm_fail(LM_ERR_BAD_ARG, "lm_task_step_host: NULL argument");
   cudaStream_t s = (cudaStream_t)stream;
+  // hs: where the physics-state copies run.  With a dedicated copy stream the shards' state copies queue back to back at full PCIe
+  // bandwidth and post_physics_step on `s` waits for exactly the copy it reads; the small action / uniform copies stay on `s`
+  // (they run under another shard's state copy).  Without one everything is in order on `s`.
+  cudaStream_t hs = io->h2d_stream ? (cudaStream_t)io->h2d_stream : s;
+  const bool split = hs != s;
   const int N = t->kp.p.num_envs;
   cudaError_t e;
+  if (split && !t->have_events) {
+    if ((e = cudaEventCreateWithFlags(&t->ev_state, cudaEventDisableTiming)) != cudaSuccess) goto fail;
+    if ((e = cudaEventCreateWithFlags(&t->ev_consumed, cudaEventDisableTiming)) != cudaSuccess) goto fail;
+    t->have_events = 1;
+  }
   // pre_physics_step on the previous state, then the "physics" arrives from the host, then post_physics_step
   if ((e = cudaMemcpyAsync(io->actions_dev, io->actions_host, sizeof(float) * N * LM_NUM_ACT, cudaMemcpyHostToDevice, s)) != cudaSuccess) goto fail;
   if ((e = cudaMemcpyAsync(io->uniforms_dev, io->uniforms_host, sizeof(float) * N * 3, cudaMemcpyHostToDevice, s)) != cudaSuccess) goto fail;
@@ -1498,10 +1513,20 @@ static int step_host_impl(LmTask* t, const LmRobotViews* loco, const LmRobotView
     int rc = lm_task_pre_step(t, loco, mani, env_pos, buf, io->actions_dev, io->uniforms_dev, stream);
     if (rc) return rc;
   }
+  if (split) {
+    // the state copy replaces the arena that (a) the previous post_physics_step read and (b) this pre_physics_step's reset scatter
+    // wrote: both are behind this point of `s`
+    if ((e = cudaEventRecord(t->ev_consumed, s)) != cudaSuccess) goto fail;
+    if ((e = cudaStreamWaitEvent(hs, t->ev_consumed, 0)) != cudaSuccess) goto fail;
+  }
   if (io->loco_state_host && io->loco_state_floats > 0)
-    if ((e = cudaMemcpyAsync(io->loco_state_dev, io->loco_state_host, sizeof(float) * io->loco_state_floats, cudaMemcpyHostToDevice, s)) != cudaSuccess) goto fail;
+    if ((e = cudaMemcpyAsync(io->loco_state_dev, io->loco_state_host, sizeof(float) * io->loco_state_floats, cudaMemcpyHostToDevice, hs)) != cudaSuccess) goto fail;
   if (io->mani_state_host && io->mani_state_floats > 0)
-    if ((e = cudaMemcpyAsync(io->mani_state_dev, io->mani_state_host, sizeof(float) * io->mani_state_floats, cudaMemcpyHostToDevice, s)) != cudaSuccess) goto fail;
+    if ((e = cudaMemcpyAsync(io->mani_state_dev, io->mani_state_host, sizeof(float) * io->mani_state_floats, cudaMemcpyHostToDevice, hs)) != cudaSuccess) goto fail;
+  if (split) {
+    if ((e = cudaEventRecord(t->ev_state, hs)) != cudaSuccess) goto fail;
+    if ((e = cudaStreamWaitEvent(s, t->ev_state, 0)) != cudaSuccess) goto fail;
+  }
   {
     int rc = lm_task_post_step(t, loco, mani, env_pos, buf, stream);
     if (rc) return rc;
@@ -1523,6 +1548,28 @@ int lm_task_step_host(LmTask* t, const LmRobotViews* loco, const LmRobotViews* m
 int lm_task_step_host_async(LmTask* t, const LmRobotViews* loco, const LmRobotViews* mani, const float* env_pos,
                             const LmTaskBuffers* buf, const LmHostStep* io, void* stream) {
   return step_host_impl(t, loco, mani, env_pos, buf, io, stream, false);
+}
+
+int lm_task_step_host_policy_async(LmTask* t, const LmRobotViews* loco, const LmRobotViews* mani, const float* env_pos,
+                                   const LmTaskBuffers* buf, const LmHostStep* io, const LmHostPolicy* pol, void* stream) {
+  if (!pol) return lm_fail(LM_ERR_BAD_ARG, "lm_task_step_host_policy_async: policy is NULL");
+  int rc = step_host_impl(t, loco, mani, env_pos, buf, io, stream, false);
+  if (rc) return rc;
+  if (pol->kind == 0) return LM_OK;
+  if (!pol->handle || !pol->mu_dev || !pol->value_dev) return lm_fail(LM_ERR_BAD_ARG, "lm_task_step_host_policy_async: policy handle / outputs missing");
+  const int N = t->kp.p.num_envs;
+  switch (pol->kind) {
+    case 1: rc = lm_mlp_forward((LmMlp*)pol->handle, buf->obs_buf, pol->norm_mean, pol->norm_inv_std, pol->norm_clip, pol->mu_dev, pol->value_dev, N, stream); break;
+    case 2: rc = lm_gnn_forward_bf16((LmGnn*)pol->handle, buf->obs_buf, pol->mu_dev, pol->value_dev, N, stream); break;
+    case 3: rc = lm_gnn_forward((LmGnn*)pol->handle, buf->obs_buf, pol->mu_dev, pol->value_dev, N, stream); break;
+    default: return lm_fail(LM_ERR_BAD_ARG, "lm_task_step_host_policy_async: unknown policy kind %d", pol->kind);
+  }
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaError_t e = cudaSuccess;
+  if (pol->mu_host) e = cudaMemcpyAsync(pol->mu_host, pol->mu_dev, sizeof(float) * (size_t)N * LM_NUM_ACT, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess && pol->value_host) e = cudaMemcpyAsync(pol->value_host, pol->value_dev, sizeof(float) * (size_t)N, cudaMemcpyDeviceToHost, s);
+  return e == cudaSuccess ? LM_OK : lm_fail((int)e, "lm_task_step_host_policy_async: %s", cudaGetErrorString(e));
 }
 
 int lm_stream_synchronize(void* stream) {

@@ -66,6 +66,12 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
 }
 // 32 lanes x 16 / 32 consecutive fp32 columns: thread i of the warp receives row (lane base + i).  The loads are
 // asynchronous; tmem_wait() must precede the first use of the registers.
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t r[4]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(taddr)
+               : "memory");
+}
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t r[8]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
@@ -123,6 +129,22 @@ __device__ __forceinline__ uint32_t elu_pair(uint32_t acc_lo, uint32_t acc_hi, f
   upk2(x2, x0, x1);
   return pack_bf16(fmaxf(x0, fminf(r0, 0.0f)), fmaxf(x1, fminf(r1, 0.0f)));
 }
+// The same pair in 8 instructions instead of 10: ELU(x) = min(e^x - 1, relu(x)) — for x > 0, e^x - 1 >= x; for x <= 0, e^x - 1 <= 0 —
+// with relu folded into the conversion (cvt.rn.relu.bf16x2) and the min taken on the packed bf16 pair (rounding is monotone, so
+// min(bf16(a), bf16(b)) = bf16(min(a, b))).  No FMNMX on the half-rate ALU pipe, one packed add for both "- 1".  Differs from elu_pair
+// only where ex2.approx returns a value below 1 for a tiny positive argument (|difference| <= 2^-22).
+__device__ __forceinline__ uint32_t elu_pair_relu(uint32_t acc_lo, uint32_t acc_hi, float b_lo, float b_hi) {
+  const uint64_t x2 = add2(pk2u(acc_lo, acc_hi), pk2(b_lo, b_hi));
+  float t0, t1, x0, x1, r0, r1;
+  upk2(mul2(x2, pk2(1.4426950408889634f, 1.4426950408889634f)), t0, t1);
+  upk2(x2, x0, x1);
+  upk2(add2(pk2(ex2_approx(t0), ex2_approx(t1)), pk2(-1.0f, -1.0f)), r0, r1);
+  uint32_t pos, neg, out;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(pos) : "f"(x1), "f"(x0));
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(neg) : "f"(r1), "f"(r0));
+  asm("min.bf16x2 %0, %1, %2;" : "=r"(out) : "r"(pos), "r"(neg));
+  return out;
+}
 __device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) { uint64_t r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
 
 // The same ELU pair with exp on the FMA pipe instead of MUFU (the epilogues are MUFU-bound: 16 ex2/clk/SM, so a share of
@@ -154,7 +176,14 @@ __device__ __forceinline__ uint32_t elu_pair_fma(uint32_t acc_lo, uint32_t acc_h
 // pair `i` of a group of four: the first kFma pairs go to the FMA pipe
 template <int kFma>
 __device__ __forceinline__ uint32_t elu_pair_mix(int i, uint32_t acc_lo, uint32_t acc_hi, float b_lo, float b_hi) {
+#ifdef LM_DIAG_NO_EX2             // diagnostic (wrong results): no exponential at all -> is the kernel MUFU / issue bound?
+  return pack_bf16(__uint_as_float(acc_lo) + b_lo, __uint_as_float(acc_hi) + b_hi);
+#endif
+#ifdef LM_ELU_MINMAX            // the FMNMX form (measured 4 % slower in k_mlp_forward: 4 half-rate ALU instructions per pair)
   return i < kFma ? elu_pair_fma(acc_lo, acc_hi, b_lo, b_hi) : elu_pair(acc_lo, acc_hi, b_lo, b_hi);
+#else
+  return i < kFma ? elu_pair_fma(acc_lo, acc_hi, b_lo, b_hi) : elu_pair_relu(acc_lo, acc_hi, b_lo, b_hi);
+#endif
 }
 
 }  // namespace tc

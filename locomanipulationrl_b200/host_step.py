@@ -5,13 +5,16 @@ are independent; every shard keeps its own locomotion/manipulation halves) — e
 stream and pinned host buffers.  One ``step`` enqueues, per shard and without any host synchronisation in between,
 
     H2D actions + goal uniforms -> pre_physics_step -> H2D physics state -> post_physics_step -> D2H [obs/]rew/reset
-    -> policy forward -> D2H mu/value                         (lm_task_step_host_async + lm_mlp_forward)
+    -> policy forward -> D2H mu/value                         (ONE library call: lm_task_step_host_policy_async)
 
 (``readback_obs=False`` keeps the observations on the device for the device-resident policy, as the reference's adapter
 does with ``rl_device = cuda``; the actions, value, reward and reset flags still return to the host every step)
 
-so shard k's host->device copies overlap shard k-1's kernels and device->host copies (PCIe is full duplex), then
-waits for every shard.  Inputs and outputs live in pinned host memory; nothing is cached across steps.
+then waits for every shard.  The physics-state copies of all shards go through ONE dedicated copy stream
+(``LmHostStep.h2d_stream``): they queue back to back at full PCIe bandwidth — copies issued on different streams would run
+concurrently and share the link, so every shard's state would land late — and shard k's kernels and device->host copies
+run under shard k+1's state copy (PCIe is full duplex).  The step is then one pass of the state over PCIe plus the last
+shard's kernels and read-back.  Inputs and outputs live in pinned host memory; nothing is cached across steps.
 """
 from __future__ import annotations
 
@@ -47,12 +50,15 @@ class _Shard:
         # VecEnvRLGames hands them to rl_device = cuda); actions, value, reward and reset flags still return every step
         self.io.obs_host = self.obs_host.data_ptr() if readback_obs else None
         self.io.rew_host, self.io.reset_host = self.rew_host.data_ptr(), self.reset_host.data_ptr()
+        self.pol = _lib.LmHostPolicy()
+        self.pol.mu_dev, self.pol.value_dev = self.mu_dev.data_ptr(), self.value_dev.data_ptr()
+        self.pol.value_host = self.value_host.data_ptr()
 
 
 class ShardedHostStepper:
     def __init__(self, cfg: TaskConfig, num_envs: int, policy, shards: int = 4, device="cuda:0", seed: int = 42,
                  env_id_offset: int = 0, norm_mean: Optional[torch.Tensor] = None, norm_inv_std: Optional[torch.Tensor] = None,
-                 readback_obs: bool = True):
+                 readback_obs: bool = True, copy_stream: bool = True):
         if num_envs % shards or (num_envs // shards) % 2:
             raise _lib.LmError("num_envs must split into an even number of envs per shard")
         self.lib = _lib.load()
@@ -62,6 +68,17 @@ class ShardedHostStepper:
         self.readback_obs = bool(readback_obs)
         self.shards: List[_Shard] = [_Shard(cfg, n, self.device, seed + 17 * k, env_id_offset + k * n, self.readback_obs) for k in range(shards)]
         self.parity = 0
+        # one copy stream for every shard's physics state (see the module docstring); a single shard needs none
+        self.h2d_stream = torch.cuda.Stream(device=self.device) if (copy_stream and shards > 1) else None
+        from .policy.mlp import MlpActorCritic
+        policy._ensure()
+        if getattr(policy, "_packed_version", None) != policy._param_version():
+            policy.pack()
+        kind = 1 if isinstance(policy, MlpActorCritic) else (2 if getattr(policy, "precision", "bf16") == "bf16" else 3)
+        for s in self.shards:
+            s.io.h2d_stream = self.h2d_stream.cuda_stream if self.h2d_stream is not None else None
+            s.pol.kind, s.pol.handle = kind, policy._handle
+            s.pol.norm_mean, s.pol.norm_inv_std, s.pol.norm_clip = _lib.ptr(norm_mean), _lib.ptr(norm_inv_std), 5.0
         self.h2d_bytes = sum(4 * (s.actions_dev.numel() + s.uniforms_dev.numel()) for s in self.shards)
         self.d2h_bytes = sum(4 * ((s.obs_host.numel() if self.readback_obs else 0) + s.rew_host.numel() + 12 * s.n + s.n) + 8 * s.reset_host.numel()
                              for s in self.shards)
@@ -79,17 +96,11 @@ class ShardedHostStepper:
                     setattr(io, grp + "_state_host", hs[grp].data_ptr())
                     setattr(io, grp + "_state_floats", hs[grp].numel())
                     setattr(io, grp + "_state_dev", s.scene.arena[grp].data_ptr())
-            with torch.cuda.stream(s.stream):
-                rc = self.lib.lm_task_step_host_async(task._handle, task._lp(), task._mp(), task._env_pos.data_ptr(),
-                                                      C.byref(task._buffers), C.byref(io), s.stream.cuda_stream)
-                _lib.check(rc, "lm_task_step_host_async")
-                task._posted_since_pre = True
-                if self.norm_mean is not None:
-                    self.policy(task.obs_buf, norm_mean=self.norm_mean, norm_inv_std=self.norm_inv_std, out=(s.mu_dev, s.value_dev))
-                else:
-                    self.policy(task.obs_buf, out=(s.mu_dev, s.value_dev))
-                s.mu_host[p ^ 1].copy_(s.mu_dev, non_blocking=True)
-                s.value_host.copy_(s.value_dev, non_blocking=True)
+            s.pol.mu_host = s.mu_host[p ^ 1].data_ptr()
+            rc = self.lib.lm_task_step_host_policy_async(task._handle, task._lp(), task._mp(), task._env_pos.data_ptr(),
+                                                         C.byref(task._buffers), C.byref(io), C.byref(s.pol), s.stream.cuda_stream)
+            _lib.check(rc, "lm_task_step_host_policy_async")
+            task._posted_since_pre = True
         for s in self.shards:
             _lib.check(self.lib.lm_stream_synchronize(s.stream.cuda_stream), "lm_stream_synchronize")
         self.parity = p ^ 1

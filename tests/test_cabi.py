@@ -30,7 +30,7 @@ def test_loads_and_struct_layouts(built_library):
     lib = _lib.load()
     assert lib.lm_abi_version() == 1
     for which, struct in enumerate((_lib.LmTaskParams, _lib.LmRobotViews, _lib.LmTaskBuffers, _lib.LmHostStep, _lib.LmPdState,
-                                    _lib.LmRunningStats, _lib.LmRolloutStep, _lib.LmRolloutBuffers, _lib.LmPpoBatch, _lib.LmNoiseSpec, _lib.LmNoiseState, _lib.LmCustomController, _lib.LmAdamSchedule, _lib.LmActionSink)):
+                                    _lib.LmRunningStats, _lib.LmRolloutStep, _lib.LmRolloutBuffers, _lib.LmPpoBatch, _lib.LmNoiseSpec, _lib.LmNoiseState, _lib.LmCustomController, _lib.LmAdamSchedule, _lib.LmActionSink, _lib.LmHostPolicy)):
         assert lib.lm_struct_size(which) == ctypes.sizeof(struct)
 
 

@@ -11,6 +11,7 @@ from locomanipulationrl_b200.policy.mlp import MlpActorCritic  # noqa: E402
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
 m = MlpActorCritic(device="cuda:0")
 obs = torch.randn(n, 64, device="cuda")
+torch.set_grad_enabled(False)          # the inference kernel (the differentiable forward carries no stamps)
 for _ in range(3):
     m(obs)
 stamps = torch.zeros(256, dtype=torch.int64, device="cuda")
