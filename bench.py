@@ -261,22 +261,22 @@ class Pipeline:
         # kernels of liblm_b200.so per step: k_pre, k_post_lean, policy forward (k_reset_count only runs when reset_buf was
         # written from outside); the gnn_gae workload adds k_rollout_write every step and lm_gae once per HORIZON steps
         self.launches_per_step = 3
-        # Pipeline variants, all measured on B200 at 65,536 envs (gpurun_out/r2d_*.json) and all OFF by default because
-        # none beat the plain chain pre -> post -> policy (45.6 us / step):
-        #   LM_BENCH_SINK=1          action half of pre_physics_step folded into the MLP head epilogue (LmActionSink)       45.9 us
-        #   + LM_BENCH_OVERLAP=1     reset half of the next pre_physics_step on a second stream next to the policy forward   45.9 us
-        #   + LM_BENCH_DEFER_FINISH=1  post kernel without its finish tail (14.1 instead of 17.5 us), k_post_finish separate     50.1 us
-        #   + LM_BENCH_EARLY_RESET=1   reset half ahead of the policy forward on the same stream                              47.2 us
+        # Default chain: pre -> post -> policy with the post kernel's finish pass (extras, counters) deferred into one extra CTA of the
+        # next pre launch (LM_BENCH_INLINE_FINISH=1: the last-CTA tail inside the post kernel, the library's default mode).
+        # Other variants, measured on B200 at 65,536 envs and OFF by default because none beat the plain chain:
+        #   LM_BENCH_SINK=1          action half of pre_physics_step folded into the MLP head epilogue (LmActionSink)
+        #   + LM_BENCH_OVERLAP=1     reset half of the next pre_physics_step on a second stream next to the policy forward
+        #   + LM_BENCH_EARLY_RESET=1 reset half ahead of the policy forward on the same stream
         self.use_sink = bool(os.environ.get("LM_BENCH_SINK")) and self.w["policy"] == "mlp"
         self.early_reset = bool(os.environ.get("LM_BENCH_EARLY_RESET"))
         self.overlap_pre = self.use_sink and (bool(os.environ.get("LM_BENCH_OVERLAP")) or self.early_reset)
         self.side = torch.cuda.Stream(device=device)
         self.graph_parity = None
-        self.defer_finish = self.overlap_pre and bool(os.environ.get("LM_BENCH_DEFER_FINISH"))
+        self.defer_finish = not bool(os.environ.get("LM_BENCH_INLINE_FINISH"))
+        if self.defer_finish:
+            self.task.set_defer_finish(True)
         if self.overlap_pre:                             # prime: the first step's pre_physics_step (later ones ride next to the policy forward)
             self.task.pre_physics_step(self.actions, self.uniforms[0])
-            if self.defer_finish:
-                self.task.set_defer_finish(True)
         if self.w["policy"] == "gnn":
             from locomanipulationrl_b200.rollout import RolloutBuffer, RunningMeanStd
             T = HORIZON
@@ -300,15 +300,11 @@ class Pipeline:
             if self.early_reset:
                 # same stream, reset half first: the policy kernel's prologue (117 KB of weights per CTA, TMEM allocation) then
                 # overlaps it through programmatic dependent launch
-                if self.defer_finish:
-                    task.post_finish()
                 task.pre_physics_step(None, self.uniforms[(i + 1) % STATE_SETS])
                 self.policy(task.obs_buf, norm_mean=self.norm_mean, norm_inv_std=self.norm_inv_std, out=(self.mu, self.value), sink=sink)
                 return
             self.side.wait_stream(cur)
             with torch.cuda.stream(self.side):
-                if self.defer_finish:
-                    task.post_finish()                  # extras / counters / reset scan: off the post kernel's critical path
                 task.pre_physics_step(None, self.uniforms[(i + 1) % STATE_SETS])
             self.policy(task.obs_buf, norm_mean=self.norm_mean, norm_inv_std=self.norm_inv_std, out=(self.mu, self.value), sink=sink)
             cur.wait_stream(self.side)
@@ -467,6 +463,8 @@ def cuda_arm(args):
         for r in range(reps):
             for k in range(horizon):
                 pipe.step(r * horizon + k)
+            if pipe.defer_finish:
+                pipe.task.post_finish()       # extras / counters of the horizon's last step, ahead of the statistics reduction
             c += comm()
         return c
 
@@ -532,8 +530,6 @@ def cuda_arm(args):
 
         def post_and_finish(i):
             post_only(i)
-            if pipe.defer_finish:
-                task.post_finish()
 
         def pre_only(i):
             task.pre_physics_step(None if pipe.use_sink else pipe.actions, pipe.uniforms[i % STATE_SETS])
@@ -570,7 +566,7 @@ def cuda_arm(args):
             pre_only(i); post_and_finish(i)
 
         ms_post = graph_time(post_only)
-        ms_post_fin = graph_time(post_and_finish) if pipe.defer_finish else ms_post
+        ms_post_fin = ms_post      # deferred finish: its CTA rides inside the pre launch and is timed with it
         ms_pre = max(graph_time(pre_post) - ms_post_fin, 1e-6)      # pre needs a preceding post + finish (its reset scan is their by-product)
         ms_pol = graph_time(policy_only)
         hbm, tf, src = measured_peaks()
@@ -705,6 +701,7 @@ def train_arm(pipe, args, world, device, rank, peer):
     from locomanipulationrl_b200.rollout import RolloutBuffer, RunningMeanStd
     T, n, task, policy = HORIZON_MLP, pipe.n, pipe.task, pipe.policy
     if pipe.defer_finish:
+        task.post_finish()
         task.set_defer_finish(False)
     task.set_up_scene(pipe.scenes[0])                  # whatever pipeline variant ran before: start from a plain post step
     task.post_physics_step()

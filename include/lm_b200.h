@@ -212,9 +212,11 @@ typedef struct LmActionSink {
   int32_t clamp_actions; int32_t zero_actions; int32_t pad_;
   float clip_actions; float action_limit;
 } LmActionSink;
-/* Deferred finish pass (see lm_task.cu): with defer on, lm_task_post_step leaves extras / counters / the reset scan to
- * lm_task_post_finish, which the caller may launch on another stream (it must complete before the next lm_task_pre_step and
- * before extras / counters are read). */
+/* Deferred finish pass (opt-in pipelining, see lm_task.cu): with defer on, lm_task_post_step only publishes per-tile partial sums and
+ * reset counts (the post kernel sheds its serial last-CTA tail); extras / counters / num_reset are then produced by ONE extra CTA
+ * inside the next lm_task_pre_step's launch, beside the reset bodies, or by lm_task_post_finish when they are wanted earlier (e.g. at
+ * a rollout boundary).  Until one of the two has run they describe the step before.  The pass acts at most once per post step, so
+ * calling lm_task_post_finish in front of a captured step graph that carries the extra CTA is safe. */
 int lm_task_set_defer_finish(LmTask* task, int on);
 int lm_task_post_finish(LmTask* task, const LmTaskBuffers* buf, void* stream);
 int lm_task_set_step_parity(LmTask* task, int parity);   /* after replaying a captured step: the ring slot (lm_task_step_parity at capture) it used */

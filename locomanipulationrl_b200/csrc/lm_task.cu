@@ -137,10 +137,17 @@ struct PreArgs {
   LmTaskBuffers buf;
   const float* actions;
   const float* uniforms;
-  const int32_t* tile_offsets;
-  const int32_t* scan_base;
+  int32_t* tile_offsets;
+  int32_t* scan_base;
   int parity;                      // actions_ring slot that receives current_actions
   LmPdState pd;                    // *_position_control variants (joint_pos == NULL otherwise)
+  // deferred finish (lm_task_set_defer_finish): the post kernel only published per-tile partial sums and reset counts.  Every CTA
+  // then derives its reset-rank base from the dense per-tile counts itself (`tile_counts`, one 128-bit load per thread up to 512
+  // tiles), and ONE extra CTA (blockIdx.x == num_tiles) runs the finish pass of the previous post step — extras, counters — next to
+  // the reset bodies instead of as the serial tail of the post kernel.
+  const int32_t* tile_counts;      // non-NULL: rank base = sum of tile_counts[0 .. blockIdx.x)
+  float* partials;                 // non-NULL: the extra CTA runs the finish pass over these
+  unsigned int* ticket;
 };
 
 __device__ __forceinline__ void store3(float* p, float a, float b, float c) { p[0] = a; p[1] = b; p[2] = c; }
@@ -229,104 +236,6 @@ __device__ __forceinline__ void reset_one_env(const KernelParams& kp, const PreA
   }
 }
 
-// K_pre: (1) reset mask -> rank -> compacted ascending id list (the `nonzero()` of QPC:206); (2) clamp + stash
-// actions, take_action.  The reset bodies themselves run in k_reset_apply over the compacted list, so the ~3 % of
-// envs that reset do not drag every warp through the (double-precision) goal resampling path.
-__global__ void __launch_bounds__(T) k_pre(const KernelParams kp, const PreArgs a) {
-  pdl_launch_dependents();
-  pdl_wait();
-  const LmTaskParams& P = kp.p;
-  const Tile tl = tile_of(kp, blockIdx.x);
-  const int r = threadIdx.x;
-  const int N = P.num_envs;
-  float* ring_cur = a.buf.actions_ring + (size_t)a.parity * N * LM_NUM_ACT;
-  const LmRobotViews& V = tl.is_mani ? a.mani : a.loco;
-
-  __shared__ int warp_base[T / 32];
-  __shared__ int list[T];
-  const int e = tl.e0 + r, hr = tl.hr0 + r;
-  // ---- every independent load first: the reset flag, this tile's rank base and the thread's three action chunks are all
-  //      in flight before anything waits (the reset bodies below are a long dependent chain on a few lanes)
-  long long flag64 = 0;
-  if (r < tl.n) flag64 = a.buf.reset_buf[e];
-  const int tile_base = a.scan_base[blockIdx.x / kp.d.scan_per] + a.tile_offsets[blockIdx.x];
-  const int nflat4 = tl.n * (LM_NUM_ACT / 4);
-  const float* act_g = a.actions + (size_t)tl.e0 * LM_NUM_ACT;
-  const bool have_actions = a.actions != nullptr;       // NULL: delivered by the producing kernel through an LmActionSink
-  float4 av[3];
-#pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    const int i = r + k * T;
-    av[k] = (have_actions && i < nflat4) ? ld_nc_f4(act_g + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-
-  // ---- actions: clamp (vec_env_rlgames.py:60), stash as current_actions, take_action (robot.py:444-461)
-  if (have_actions) {
-    float* cur_g = ring_cur + (size_t)tl.e0 * LM_NUM_ACT;
-    const float range = sub(P.action_limit, -P.action_limit);
-    const float offset = mul(add(-P.action_limit, P.action_limit), 0.5f);
-    const bool write_targets = (P.control_mode == LM_CONTROL_VELOCITY || P.control_mode == LM_CONTROL_POSITION) && V.targets;
-    float* tgt_g = write_targets ? V.targets + (size_t)tl.hr0 * LM_NUM_ACT : nullptr;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      const int i = r + k * T;
-      if (i >= nflat4) continue;
-      float4 v = av[k];
-      if (P.clamp_actions) {
-        v.x = fminf(fmaxf(v.x, -P.clip_actions), P.clip_actions); v.y = fminf(fmaxf(v.y, -P.clip_actions), P.clip_actions);
-        v.z = fminf(fmaxf(v.z, -P.clip_actions), P.clip_actions); v.w = fminf(fmaxf(v.w, -P.clip_actions), P.clip_actions);
-      }
-      reinterpret_cast<float4*>(cur_g)[i] = v;
-      if (write_targets) {
-        if (P.zero_actions) v = make_float4(0.f, 0.f, 0.f, 0.f);
-        float4 t;
-        t.x = add(mul(mul(v.x, range), 0.5f), offset); t.y = add(mul(mul(v.y, range), 0.5f), offset);
-        t.z = add(mul(mul(v.z, range), 0.5f), offset); t.w = add(mul(mul(v.w, range), 0.5f), offset);
-        reinterpret_cast<float4*>(tgt_g)[i] = t;
-      }
-    }
-    if (P.control_mode == LM_CONTROL_EFFORT && V.targets && r < tl.n) {                // robot.py:455-459
-      float* eff = V.targets + (size_t)hr * LM_NUM_DOF;
-      const float* avp = a.actions + (size_t)e * LM_NUM_ACT;
-#pragma unroll
-      for (int j = 0; j < LM_NUM_DOF; ++j) eff[j] = 0.0f;
-#pragma unroll
-      for (int j = 0; j < LM_NUM_ACT; ++j) {
-        float v = avp[j];
-        if (P.clamp_actions) v = fminf(fmaxf(v, -P.clip_actions), P.clip_actions);
-        if (P.zero_actions) v = 0.0f;
-        eff[P.dof_index[j]] = add(mul(mul(v, range), 0.5f), offset);
-      }
-    }
-  }
-
-  // ---- reset mask -> rank -> compacted ascending id list (the `nonzero()` of QPC:206); the reset bodies run on the first
-  //      lanes only, so the ~3 % of envs that reset do not drag every warp through the (double-precision) goal resampling
-  const int flag = flag64 != 0;
-  unsigned b = __ballot_sync(0xffffffffu, flag);
-  if ((r & 31) == 0) warp_base[r >> 5] = __popc(b);
-  __syncthreads();
-  int local_rank = __popc(b & ((1u << (r & 31)) - 1u)), count = 0;
-#pragma unroll
-  for (int w = 0; w < T / 32; ++w) {
-    if (w < (r >> 5)) local_rank += warp_base[w];
-    count += warp_base[w];
-  }
-  if (count == 0) return;
-  if (flag) list[local_rank] = r;
-  __syncthreads();
-  {
-    // two lanes per reset env: role 0 = goal + indicator pose (the double-precision chain), role 1 = defaults + history.
-    // Lanes are dealt round-robin over the four warps so that the chains of one tile run side by side.
-    float* ring_last = a.buf.actions_ring + (size_t)(a.parity ^ 1) * N * LM_NUM_ACT;
-    const int slot = ((r & 31) << 2) | (r >> 5);      // lane-major order: slot 0..3 sit in four different warps
-    for (int idx = slot; idx < 2 * count; idx += T) {
-      const int lr = list[idx >> 1];
-      reset_one_env(kp, a, V, ring_last, tl.is_mani, tl.e0 + lr, tl.hr0 + lr, tile_base + (idx >> 1), idx & 1);
-    }
-  }
-}
-
 // direct reset_idx(env_ids) call (random_policy.py-style drivers): env k of the list consumes uniform row k
 __global__ void k_reset_idx(const KernelParams kp, const PreArgs a, const int64_t* __restrict__ env_ids, int count) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -351,6 +260,7 @@ struct PostArgs {
   unsigned int* ticket;
   int32_t* tile_offsets;           // by-product: exclusive scan of per-tile reset counts for the next pre_step,
   int32_t* scan_base;              //   as scan_base[t / scan_per] + tile_offsets[t]
+  int32_t* tile_counts;            // dense per-tile reset counts, always written (k_pre's own scan after a deferred finish)
   int inline_finish;               // the last CTA runs the finish pass (else k_post_finish is launched behind the kernel)
   const float* pd_targets;         // *_position_control variants: obs[40:64] = scale * targets, scale * last_targets
   const float* pd_last_targets;    //   (…position_control.py:438-452); NULL otherwise
@@ -662,13 +572,21 @@ __device__ __forceinline__ double warp_sum_d(double v) {
 // [r * scan_per, (r + 1) * scan_per): their partial sums are fetched with batched 128-bit L2 loads and summed in double;
 // one shuffle tree gives the totals and one block scan the reset ranks.  Per-tile offsets are written RELATIVE to the
 // owner's block and the block bases separately (scan_base), so no second pass over the tiles is needed.
-template <int kThreads>
-__device__ __forceinline__ void finish_tail(const KernelParams& kp, const PostArgs& a, FinishSmem& fs) {
+template <int kThreads, bool kSeparate, typename FinArgs>
+__device__ __forceinline__ void finish_tail(const KernelParams& kp, const FinArgs& a, FinishSmem& fs) {
   const LmTaskParams& P = kp.p;
   const int r = threadIdx.x, N = P.num_envs, lane = r & 31, warp = r >> 5;
   constexpr int kWarps = kThreads / 32;
   const int nt = kp.d.num_tiles, tph = kp.d.tiles_per_half, per = kp.d.scan_per;
   const int lo = min(nt, r * per), hi = min(nt, lo + per);
+  if (kSeparate) {
+    // A separately launched pass (deferred finish: an extra CTA of k_pre, or k_post_finish) may be issued twice for one post step —
+    // a captured step graph carries the extra CTA, the caller ran lm_task_post_finish at a rollout boundary — and the counters
+    // accumulate: only the first one after a post step acts.
+    if (r == 0) fs.is_last = (int)__ldcg(a.ticket + 1);
+    __syncthreads();
+    if (fs.is_last == 0) return;
+  }
   double acc[13];
 #pragma unroll
   for (int i = 0; i < 13; ++i) acc[i] = 0.0;
@@ -756,6 +674,7 @@ __device__ __forceinline__ void finish_tail(const KernelParams& kp, const PostAr
       c[2 * g + 1] = nr + (int64_t)llrint(rst[g]);
     }
     *a.ticket = 0;
+    if (kSeparate) a.ticket[1] = 0u;
   }
 }
 
@@ -793,7 +712,9 @@ __device__ __forceinline__ void finish_publish(const PostArgs& a, const float st
       fs.is_last = atomicAdd(a.ticket, 1u) == gridDim.x - 1;
     } else {
       fs.is_last = 0;
+      if (blockIdx.x == 0) a.ticket[1] = 1u;              // partials are fresh: a separately launched finish pass consumes them ONCE
     }
+    a.tile_counts[blockIdx.x] = (int)v[10];               // dense per-tile reset counts (read by k_pre after a deferred finish)
   }
 }
 template <int kThreads>
@@ -803,7 +724,7 @@ __device__ __forceinline__ void finish_join(const KernelParams& kp, const PostAr
   // No second fence: every other CTA fenced its partial sums (L2, st.cg) before its ticket increment, this CTA observed
   // the final ticket value before the barrier above, and the finish pass reads them with L2 loads (ld.cg).  A full fence
   // here would only wait for this CTA's own observation stores.
-  finish_tail<kThreads>(kp, a, fs);
+  finish_tail<kThreads, false>(kp, a, fs);
 }
 template <int kThreads>
 __device__ __forceinline__ void finish_stats(const KernelParams& kp, const PostArgs& a, const float stats[STATS], FinishSmem& fs) {
@@ -814,8 +735,142 @@ __device__ __forceinline__ void finish_stats(const KernelParams& kp, const PostA
 // stand-alone finish pass for grids too large for a 128-thread tail
 __global__ void __launch_bounds__(FINISH_THREADS) k_post_finish(const KernelParams kp, const PostArgs a) {
   __shared__ FinishSmem fs;
-  finish_tail<FINISH_THREADS>(kp, a, fs);
+  finish_tail<FINISH_THREADS, true>(kp, a, fs);
 }
+
+// K_pre: (1) reset mask -> rank -> compacted ascending id list (the `nonzero()` of QPC:206); (2) clamp + stash
+// actions, take_action.  The reset bodies themselves run in k_reset_apply over the compacted list, so the ~3 % of
+// envs that reset do not drag every warp through the (double-precision) goal resampling path.
+__global__ void __launch_bounds__(T) k_pre(const KernelParams kp, const PreArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const LmTaskParams& P = kp.p;
+  if (blockIdx.x == (unsigned)kp.d.num_tiles) {         // the extra CTA of a deferred finish: extras / counters of the previous post step
+    __shared__ FinishSmem fs;
+    finish_tail<T, true>(kp, a, fs);
+    return;
+  }
+  const Tile tl = tile_of(kp, blockIdx.x);
+  const int r = threadIdx.x;
+  const int N = P.num_envs;
+  float* ring_cur = a.buf.actions_ring + (size_t)a.parity * N * LM_NUM_ACT;
+  const LmRobotViews& V = tl.is_mani ? a.mani : a.loco;
+
+  __shared__ int warp_base[T / 32];
+  __shared__ int base_part[T / 32];
+  __shared__ int list[T];
+  const int e = tl.e0 + r, hr = tl.hr0 + r;
+  // ---- every independent load first: the reset flag, this tile's rank base and the thread's three action chunks are all
+  //      in flight before anything waits (the reset bodies below are a long dependent chain on a few lanes)
+  long long flag64 = 0;
+  if (r < tl.n) flag64 = a.buf.reset_buf[e];
+  int tile_base = 0;
+  if (a.tile_counts == nullptr) {
+    tile_base = a.scan_base[blockIdx.x / kp.d.scan_per] + a.tile_offsets[blockIdx.x];
+  } else {
+    // rank base from the dense per-tile reset counts of the last post step: tiles [0, blockIdx.x), four per 128-bit load
+    const int4* c4 = reinterpret_cast<const int4*>(a.tile_counts);
+    for (int i = r; 4 * i < (int)blockIdx.x; i += T) {
+      const int4 c = __ldcg(c4 + i);
+      const int t0 = 4 * i, lim = (int)blockIdx.x;
+      tile_base += c.x + (t0 + 1 < lim ? c.y : 0) + (t0 + 2 < lim ? c.z : 0) + (t0 + 3 < lim ? c.w : 0);
+    }
+  }
+  const int nflat4 = tl.n * (LM_NUM_ACT / 4);
+  const float* act_g = a.actions + (size_t)tl.e0 * LM_NUM_ACT;
+  const bool have_actions = a.actions != nullptr;       // NULL: delivered by the producing kernel through an LmActionSink
+  float4 av[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const int i = r + k * T;
+    av[k] = (have_actions && i < nflat4) ? ld_nc_f4(act_g + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+
+  // ---- actions: clamp (vec_env_rlgames.py:60), stash as current_actions, take_action (robot.py:444-461)
+  if (have_actions) {
+    float* cur_g = ring_cur + (size_t)tl.e0 * LM_NUM_ACT;
+    const float range = sub(P.action_limit, -P.action_limit);
+    const float offset = mul(add(-P.action_limit, P.action_limit), 0.5f);
+    const bool write_targets = (P.control_mode == LM_CONTROL_VELOCITY || P.control_mode == LM_CONTROL_POSITION) && V.targets;
+    float* tgt_g = write_targets ? V.targets + (size_t)tl.hr0 * LM_NUM_ACT : nullptr;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int i = r + k * T;
+      if (i >= nflat4) continue;
+      float4 v = av[k];
+      if (P.clamp_actions) {
+        v.x = fminf(fmaxf(v.x, -P.clip_actions), P.clip_actions); v.y = fminf(fmaxf(v.y, -P.clip_actions), P.clip_actions);
+        v.z = fminf(fmaxf(v.z, -P.clip_actions), P.clip_actions); v.w = fminf(fmaxf(v.w, -P.clip_actions), P.clip_actions);
+      }
+      reinterpret_cast<float4*>(cur_g)[i] = v;
+      if (write_targets) {
+        if (P.zero_actions) v = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 t;
+        t.x = add(mul(mul(v.x, range), 0.5f), offset); t.y = add(mul(mul(v.y, range), 0.5f), offset);
+        t.z = add(mul(mul(v.z, range), 0.5f), offset); t.w = add(mul(mul(v.w, range), 0.5f), offset);
+        reinterpret_cast<float4*>(tgt_g)[i] = t;
+      }
+    }
+    if (P.control_mode == LM_CONTROL_EFFORT && V.targets && r < tl.n) {                // robot.py:455-459
+      float* eff = V.targets + (size_t)hr * LM_NUM_DOF;
+      const float* avp = a.actions + (size_t)e * LM_NUM_ACT;
+#pragma unroll
+      for (int j = 0; j < LM_NUM_DOF; ++j) eff[j] = 0.0f;
+#pragma unroll
+      for (int j = 0; j < LM_NUM_ACT; ++j) {
+        float v = avp[j];
+        if (P.clamp_actions) v = fminf(fmaxf(v, -P.clip_actions), P.clip_actions);
+        if (P.zero_actions) v = 0.0f;
+        eff[P.dof_index[j]] = add(mul(mul(v, range), 0.5f), offset);
+      }
+    }
+  }
+
+  // ---- reset mask -> rank -> compacted ascending id list (the `nonzero()` of QPC:206); the reset bodies run on the first
+  //      lanes only, so the ~3 % of envs that reset do not drag every warp through the (double-precision) goal resampling
+  const int flag = flag64 != 0;
+  unsigned b = __ballot_sync(0xffffffffu, flag);
+  if (a.tile_counts != nullptr) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) tile_base += __shfl_xor_sync(0xffffffffu, tile_base, off);
+    if ((r & 31) == 0) base_part[r >> 5] = tile_base;
+  }
+  if ((r & 31) == 0) warp_base[r >> 5] = __popc(b);
+  __syncthreads();
+  if (a.tile_counts != nullptr) {
+    tile_base = 0;
+#pragma unroll
+    for (int w = 0; w < T / 32; ++w) tile_base += base_part[w];
+  }
+  int local_rank = __popc(b & ((1u << (r & 31)) - 1u)), count = 0;
+#pragma unroll
+  for (int w = 0; w < T / 32; ++w) {
+    if (w < (r >> 5)) local_rank += warp_base[w];
+    count += warp_base[w];
+  }
+  if (a.tile_counts != nullptr && r == 0) {             // num_reset, which the inline finish pass writes otherwise
+    if ((int)blockIdx.x == kp.d.num_tiles - 1) {
+      a.buf.num_reset[0] = tile_base + count;
+      if (P.kind == LM_KIND_LOCO) a.buf.num_reset[1] = tile_base + count;
+      if (P.kind == LM_KIND_MANI) a.buf.num_reset[1] = 0;
+    }
+    if (P.kind == LM_KIND_COTRAIN && (int)blockIdx.x == kp.d.tiles_per_half) a.buf.num_reset[1] = tile_base;   // resets in the locomotion half
+  }
+  if (count == 0) return;
+  if (flag) list[local_rank] = r;
+  __syncthreads();
+  {
+    // two lanes per reset env: role 0 = goal + indicator pose (the double-precision chain), role 1 = defaults + history.
+    // Lanes are dealt round-robin over the four warps so that the chains of one tile run side by side.
+    float* ring_last = a.buf.actions_ring + (size_t)(a.parity ^ 1) * N * LM_NUM_ACT;
+    const int slot = ((r & 31) << 2) | (r >> 5);      // lane-major order: slot 0..3 sit in four different warps
+    for (int idx = slot; idx < 2 * count; idx += T) {
+      const int lr = list[idx >> 1];
+      reset_one_env(kp, a, V, ring_last, tl.is_mani, tl.e0 + lr, tl.hr0 + lr, tile_base + (idx >> 1), idx & 1);
+    }
+  }
+}
+
 
 __device__ __forceinline__ void ld12(const float* p, float v[12]) {
 #pragma unroll
@@ -1186,10 +1241,11 @@ struct LmTask {
   int32_t* scan_base;
   int inline_finish;
   int defer_finish;                // the caller launches the finish pass itself (lm_task_post_finish), e.g. on a second stream
+  int finish_pending;              // a deferred finish pass has not run yet
   LmPdState pd;
   int has_pd;
   float* partials;
-  unsigned int* tickets;     // [2]: scan, post
+  unsigned int* tickets;     // [4]: scan ticket, post ticket, 'partials are fresh' flag (deferred finish), spare
   int clamp_observations;
   long long* timeline;
   int scan_valid;            // tile_offsets / num_reset were produced by the last post_step and reset_buf is untouched since
@@ -1292,9 +1348,9 @@ LmTask* lm_task_create(const LmTaskParams* params, int device) {
             cudaMalloc(&t->tile_offsets, sizeof(int32_t) * d.num_tiles) == cudaSuccess &&
             cudaMalloc(&t->scan_base, sizeof(int32_t) * FINISH_THREADS) == cudaSuccess &&
             cudaMalloc(&t->partials, sizeof(float) * STATS * d.num_tiles) == cudaSuccess &&
-            cudaMalloc(&t->tickets, sizeof(unsigned int) * 2) == cudaSuccess;
+            cudaMalloc(&t->tickets, sizeof(unsigned int) * 4) == cudaSuccess;
   if (!ok) { lm_set_error("lm_task_create: cudaMalloc failed"); lm_task_destroy(t); return nullptr; }
-  cudaMemset(t->tickets, 0, sizeof(unsigned int) * 2);
+  cudaMemset(t->tickets, 0, sizeof(unsigned int) * 4);
   cudaMemset(t->scan_base, 0, sizeof(int32_t) * FINISH_THREADS);
   err = cudaFuncSetAttribute(k_post_lean, cudaFuncAttributeMaxDynamicSharedMemorySize, LeanSmem::kBytes);
   if (err == cudaSuccess) err = cudaFuncSetAttribute(k_post, cudaFuncAttributeMaxDynamicSharedMemorySize, PostSmem::kBytes);
@@ -1396,7 +1452,8 @@ int lm_task_pre_step(LmTask* t, const LmRobotViews* loco, const LmRobotViews* ma
   cudaStream_t s = (cudaStream_t)stream;
   const Derived& d = t->kp.d;
   t->parity ^= 1;
-  if (!t->scan_valid)   // first step, or reset_buf was written from outside (task.reset(), lm_task_invalidate_reset_scan)
+  const bool scan_was_valid = t->scan_valid != 0;
+  if (!scan_was_valid)  // first step, or reset_buf was written from outside (task.reset(), lm_task_invalidate_reset_scan)
     k_reset_count<<<d.num_tiles, T, 0, s>>>(t->kp, buf->reset_buf, t->tile_counts, t->tile_offsets, t->scan_base, buf->num_reset, t->tickets + 0);
   t->scan_valid = 0;
   PreArgs a;
@@ -1406,8 +1463,35 @@ int lm_task_pre_step(LmTask* t, const LmRobotViews* loco, const LmRobotViews* ma
   a.env_pos = env_pos; a.buf = *buf; a.actions = actions; a.uniforms = uniforms;
   a.tile_offsets = t->tile_offsets; a.scan_base = t->scan_base; a.parity = t->parity;
   if (t->has_pd) a.pd = t->pd;
-  cudaError_t le = lm_launch(k_pre, dim3(d.num_tiles), dim3(T), 0, s, true, t->kp, a);
+  int grid = d.num_tiles;
+  bool finish_behind = false;
+  if (t->defer_finish) {
+    // the reset scan: k_reset_count's (absolute tile_offsets, scan_per of the 128-thread layout) when it just ran, else from the
+    // per-tile counts the last post step left.  The pending finish pass: an extra CTA of this launch (<= 1024 tiles: a 128-thread
+    // pass is short), else the stand-alone 1024-thread kernel behind it.
+    if (scan_was_valid) a.tile_counts = t->tile_counts;
+    if (t->finish_pending) {
+      // (with k_reset_count's scan in use the pass must not run beside the reset bodies: it rewrites tile_offsets / scan_base)
+      if (d.num_tiles <= INLINE_FINISH_MAX_TILES && scan_was_valid) {
+        a.partials = t->partials; a.ticket = t->tickets + 1;
+        grid = d.num_tiles + 1;
+      } else {
+        finish_behind = true;
+      }
+      t->finish_pending = 0;
+    }
+  }
+  cudaError_t le = lm_launch(k_pre, dim3(grid), dim3(T), 0, s, true, t->kp, a);
   if (le != cudaSuccess) return lm_fail((int)le, "lm_task_pre_step: %s", cudaGetErrorString(le));
+  if (finish_behind) {
+    PostArgs f;
+    memset(&f, 0, sizeof(f));
+    f.buf = *buf; f.partials = t->partials; f.ticket = t->tickets + 1; f.tile_offsets = t->tile_offsets; f.scan_base = t->scan_base;
+    f.tile_counts = t->tile_counts;
+    KernelParams kpf = t->kp;
+    kpf.d.scan_per = (d.num_tiles + FINISH_THREADS - 1) / FINISH_THREADS;
+    k_post_finish<<<1, FINISH_THREADS, 0, s>>>(kpf, f);
+  }
   return lm_check_launch("lm_task_pre_step");
 }
 
@@ -1439,7 +1523,7 @@ int lm_task_post_step(LmTask* t, const LmRobotViews* loco, const LmRobotViews* m
   if (mani) a.mani = *mani;
   a.env_pos = env_pos; a.buf = *buf; a.partials = t->partials; a.ticket = t->tickets + 1; a.tile_offsets = t->tile_offsets;
   a.parity = t->parity; a.clamp_observations = t->clamp_observations; a.timeline = t->timeline;
-  a.scan_base = t->scan_base; a.inline_finish = t->inline_finish;
+  a.scan_base = t->scan_base; a.inline_finish = t->inline_finish; a.tile_counts = t->tile_counts;
   if (t->has_pd) {
     a.pd_targets = t->pd.targets; a.pd_last_targets = t->pd.last_targets; a.pd_target_obs_scale = t->pd.target_obs_scale;
     if (t->pd.carry_post_state) { a.pd_joint_pos = t->pd.joint_pos; a.pd_joint_vel = t->pd.joint_vel; }
@@ -1452,30 +1536,46 @@ int lm_task_post_step(LmTask* t, const LmRobotViews* loco, const LmRobotViews* m
     if (le != cudaSuccess) return lm_fail((int)le, "lm_task_post_step: %s", cudaGetErrorString(le));
   }
   if (!t->inline_finish && !t->defer_finish) k_post_finish<<<1, FINISH_THREADS, 0, (cudaStream_t)stream>>>(t->kp, a);
+  // (a second post step before the pass of the first one ran overwrites its partial sums: that step's contribution to extras /
+  //  counters is dropped, as documented for the deferred mode)
+  if (t->defer_finish) t->finish_pending = 1;
   t->scan_valid = 1;
   return lm_check_launch("lm_task_post_step");
 }
 
-// Deferred finish pass: lm_task_post_step then only publishes the per-tile partial sums, and the pass that turns them into extras /
-// counters / the next step's reset scan is launched by the caller — e.g. on a second stream next to the policy forward, ahead of
-// the next lm_task_pre_step (which needs the scan).  The post kernel sheds its serial tail (one CTA reading every tile's partials).
+// Deferred finish pass: lm_task_post_step then only publishes the per-tile partial sums and reset counts — the post kernel sheds its
+// serial tail (one CTA reading every tile's partials: 2.6 of 17.5 us at 65,536 envs).  The pass that turns them into extras /
+// counters runs as ONE extra CTA of the next lm_task_pre_step's launch, next to the reset bodies (which take their rank base from
+// the per-tile counts directly), or — when extras / counters are wanted before that, e.g. at a rollout boundary — through
+// lm_task_post_finish.  Until one of the two has run, `extras`, `counters` and `num_reset` describe the step before.
 int lm_task_set_defer_finish(LmTask* t, int on) {
   if (!t) return lm_fail(LM_ERR_BAD_ARG, "lm_task_set_defer_finish: task is NULL");
+  if (t->finish_pending) return lm_fail(LM_ERR_BAD_ARG, "lm_task_set_defer_finish: a deferred finish pass is pending (lm_task_post_finish first)");
   t->defer_finish = on != 0;
   t->inline_finish = (t->kp.d.num_tiles <= INLINE_FINISH_MAX_TILES) && !t->defer_finish;
-  const int threads = t->inline_finish ? T : FINISH_THREADS;
+  // deferred: the pass runs with T threads inside k_pre (<= 1024 tiles); the stand-alone kernel gets its own scan_per at launch
+  const int threads = (t->inline_finish || t->defer_finish) ? T : FINISH_THREADS;
   t->kp.d.scan_per = (t->kp.d.num_tiles + threads - 1) / threads;
   t->scan_valid = 0;                  // the layout of tile_offsets / scan_base depends on scan_per
   return LM_OK;
 }
 
+// Runs the deferred finish pass now (a no-op on the device when the last post step's pass already ran).
 int lm_task_post_finish(LmTask* t, const LmTaskBuffers* buf, void* stream) {
   if (!t || !buf) return lm_fail(LM_ERR_BAD_ARG, "lm_task_post_finish: NULL argument");
   if (!t->defer_finish) return lm_fail(LM_ERR_BAD_ARG, "lm_task_post_finish: the task runs its finish pass itself (lm_task_set_defer_finish)");
+  // (launched even when the host-side flag says nothing is pending: under CUDA-graph replay the flag does not follow the device,
+  //  and the pass acts at most once per post step by itself)
   PostArgs a;
   memset(&a, 0, sizeof(a));
   a.buf = *buf; a.partials = t->partials; a.ticket = t->tickets + 1; a.tile_offsets = t->tile_offsets; a.scan_base = t->scan_base;
-  k_post_finish<<<1, FINISH_THREADS, 0, (cudaStream_t)stream>>>(t->kp, a);
+  a.tile_counts = t->tile_counts;
+  KernelParams kpf = t->kp;
+  kpf.d.scan_per = (t->kp.d.num_tiles + FINISH_THREADS - 1) / FINISH_THREADS;
+  k_post_finish<<<1, FINISH_THREADS, 0, (cudaStream_t)stream>>>(kpf, a);
+  t->finish_pending = 0;
+  // the stand-alone pass left tile_offsets / scan_base in ITS layout: the next pre step must not mix them with the 128-thread one
+  // (it takes its rank bases from the per-tile counts, which are layout-free)
   return lm_check_launch("lm_task_post_finish");
 }
 

@@ -366,13 +366,14 @@ class LocoManipulationTask:
         self._keep = (env_ids, uniforms)
 
     def set_defer_finish(self, on: bool = True) -> None:
-        """``on``: ``post_physics_step`` leaves the finish pass (extras, success counters, the reset scan the next ``pre_physics_step``
-        consumes) to :meth:`post_finish`, which may be launched on another stream — next to the policy forward — instead of as the
-        serial tail of the post kernel."""
+        """``on``: ``post_physics_step`` only publishes per-tile partial sums and reset counts; extras, success counters and
+        ``num_reset`` are produced by one extra CTA inside the NEXT ``pre_physics_step``'s launch (beside the reset bodies) instead of
+        as the serial tail of the post kernel, or by :meth:`post_finish` when they are wanted earlier (rollout boundaries, logging)."""
         _lib.check(self._lib.lm_task_set_defer_finish(self._handle, int(bool(on))), "lm_task_set_defer_finish")
         self._defer_finish = bool(on)
 
     def post_finish(self) -> None:
+        """Run the deferred finish pass now (acts at most once per post step)."""
         _lib.check(self._lib.lm_task_post_finish(self._handle, C.byref(self._buffers), self._stream()), "lm_task_post_finish")
 
     def post_physics_step(self):

@@ -47,6 +47,8 @@ def test_bench_pipeline_65536_graph_replay_matches_port(monkeypatch):
         stats["err"][name] = max(stats["err"].get(name, 0.0), assert_close(name, got, ref, **kw))
 
     def track(i, t):
+        if pipe.defer_finish:
+            pipe.task.post_finish()        # extras / counters of post(t) now (the captured pre launches carry the pass too: it acts once)
         torch.cuda.synchronize()
         # ---- post(t)
         p.scene = scenes_cpu[i]
@@ -103,7 +105,7 @@ def test_bench_default_pipeline_65536_graph_replay_matches_port():
     pipe = bench.Pipeline("cotrain64k", dev, rank=0)
     cfg, n = pipe.cfg, pipe.n
     S = bench.STATE_SETS
-    assert n == 65536 and pipe.task._fuse_obs_clamp and not pipe.use_sink and not pipe.overlap_pre
+    assert n == 65536 and pipe.task._fuse_obs_clamp and not pipe.use_sink and not pipe.overlap_pre and pipe.defer_finish
     scenes_cpu = []
     for i in range(S):
         sc = synthetic.SyntheticScene(cfg, n, seed=42)
@@ -115,6 +117,8 @@ def test_bench_default_pipeline_65536_graph_replay_matches_port():
     actions = {"a": pipe.actions.detach().cpu().clone()}
 
     def track(i, t):
+        if pipe.defer_finish:
+            pipe.task.post_finish()        # extras / counters of post(t) now (the captured pre launches carry the pass too: it acts once)
         torch.cuda.synchronize()
         p.pre_physics_step(torch.clamp(actions["a"], -1.0, 1.0), unis[i])      # the adapter's clamp (vec_env_rlgames.py:60)
         prev = scenes_cpu[(i - 1) % S] if t > 0 else scenes_cpu[0]             # the views that were live during pre_physics_step
@@ -323,3 +327,48 @@ def test_take_action_position_and_effort_modes(mode):
         p.post_physics_step(); task.post_physics_step()
         assert_close(f"step {t} obs", task.obs_buf, p.obs_buf)
         assert torch.equal(task.reset_buf.cpu(), p.reset_buf)
+
+
+@pytest.mark.parametrize("n", [258, 8192, 262144])
+def test_deferred_finish_matches_inline(n):
+    """lm_task_set_defer_finish: the finish pass of post(t) as an extra CTA of pre(t+1) (<= 1,024 tiles) or the stand-alone kernel behind
+    it (2,048 tiles), the reset ranks taken from the per-tile counts — against the default mode (last-CTA tail inside the post kernel)
+    on the same inputs: every buffer bit-identical after each pre step, extras / counters / num_reset bit-identical once the pass ran
+    (also when lm_task_post_finish runs it early and the next pre launch carries it again)."""
+    from locomanipulationrl_b200.tasks.base import LocoManipulationTask
+    cfg = configs.get_task_config("JointLocomanipulationVertical")
+    tasks, scenes = [], []
+    for defer in (False, True):
+        sc = synthetic.SyntheticScene(cfg, n, device="cuda:0", seed=3)
+        t = LocoManipulationTask(cfg, n, scene=sc, device="cuda:0", seed=3)
+        if defer:
+            t.set_defer_finish(True)
+        tasks.append(t); scenes.append(sc)
+    acts, unis = rollout_inputs(n, 9, seed=21)
+    ref, dfr = tasks
+    fields = ("obs_buf", "rew_buf", "reset_buf", "progress_buf", "successes", "consecutive_successes", "goal_reset_buf", "goal_quaternions")
+    for t in range(9):
+        st = scenes[0].generate(t)
+        for task, sc in zip(tasks, scenes):
+            task.pre_physics_step(acts[t].cuda(), unis[t].cuda())
+        torch.cuda.synchronize()
+        # the pass of post(t-1) has run inside (or behind) this pre launch
+        if t > 0:
+            assert torch.equal(dfr._extras_buf, ref._extras_buf) and torch.equal(dfr._counters, ref._counters), f"step {t}: extras / counters"
+            assert torch.equal(dfr.num_reset_buf, ref.num_reset_buf), f"step {t}: num_reset"
+            k = int(ref.num_reset_buf[0])
+            assert torch.equal(dfr.reset_env_ids()[:k], ref.reset_env_ids()[:k]), f"step {t}: reset id list"
+        for f in fields:
+            assert torch.equal(getattr(dfr, f), getattr(ref, f)), f"step {t}: {f} after pre"
+        for grp in ("loco", "mani"):
+            for k_, v in getattr(scenes[0], grp).items():
+                assert torch.equal(getattr(scenes[1], grp)[k_], v), f"step {t}: scene.{grp}.{k_} after pre"
+        for task, sc in zip(tasks, scenes):
+            sc.load(st)
+            task.post_physics_step()
+        if t % 3 == 2:                      # an early finish (rollout boundary): the next pre launch carries the pass again and must not act twice
+            dfr.post_finish()
+            torch.cuda.synchronize()
+            assert torch.equal(dfr._extras_buf, ref._extras_buf) and torch.equal(dfr._counters, ref._counters), f"step {t}: early finish"
+        for f in ("obs_buf", "rew_buf", "reset_buf", "progress_buf"):
+            assert torch.equal(getattr(dfr, f), getattr(ref, f)), f"step {t}: {f} after post"
