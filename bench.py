@@ -261,21 +261,25 @@ class Pipeline:
         # kernels of liblm_b200.so per step: k_pre, k_post_lean, policy forward (k_reset_count only runs when reset_buf was
         # written from outside); the gnn_gae workload adds k_rollout_write every step and lm_gae once per HORIZON steps
         self.launches_per_step = 3
-        # Default chain: pre -> post -> policy with the post kernel's finish pass (extras, counters) deferred into one extra CTA of the
-        # next pre launch (LM_BENCH_INLINE_FINISH=1: the last-CTA tail inside the post kernel, the library's default mode).
-        # Other variants, measured on B200 at 65,536 envs and OFF by default because none beat the plain chain:
-        #   LM_BENCH_SINK=1          action half of pre_physics_step folded into the MLP head epilogue (LmActionSink)
-        #   + LM_BENCH_OVERLAP=1     reset half of the next pre_physics_step on a second stream next to the policy forward
-        #   + LM_BENCH_EARLY_RESET=1 reset half ahead of the policy forward on the same stream
-        self.use_sink = bool(os.environ.get("LM_BENCH_SINK")) and self.w["policy"] == "mlp"
-        self.early_reset = bool(os.environ.get("LM_BENCH_EARLY_RESET"))
-        self.overlap_pre = self.use_sink and (bool(os.environ.get("LM_BENCH_OVERLAP")) or self.early_reset)
-        self.side = torch.cuda.Stream(device=device)
+        # Default chain (MLP workloads): post -> policy -> reset half of the next pre, where
+        #   * the action half of pre_physics_step (adapter clamp, current_actions, take_action) is done by the MLP head epilogue
+        #     (LmActionSink; LM_BENCH_NO_SINK=1: the actions go through k_pre),
+        #   * the reset half, which needs nothing from the policy kernel, is released beside it by programmatic dependent launch and
+        #     only completes after it (lm_task_set_early_reset; LM_BENCH_NO_EARLY=1: it runs behind the policy kernel),
+        #   * the post kernel's finish pass (extras, counters) is one extra CTA of that launch (lm_task_set_defer_finish;
+        #     LM_BENCH_INLINE_FINISH=1: the last-CTA tail inside the post kernel, the library's default mode).
+        # Measured and dropped in round 2: the reset half on a second stream with an event join (+0.3 us), the reset half
+        # in front of the policy kernel on the same stream (+1.6 us), the finish pass as a kernel on a second stream (+4.5 us).
+        self.use_sink = self.w["policy"] == "mlp" and not os.environ.get("LM_BENCH_NO_SINK")
+        self.early_reset = self.use_sink and not os.environ.get("LM_BENCH_NO_EARLY")
         self.graph_parity = None
         self.defer_finish = not bool(os.environ.get("LM_BENCH_INLINE_FINISH"))
         if self.defer_finish:
             self.task.set_defer_finish(True)
-        if self.overlap_pre:                             # prime: the first step's pre_physics_step (later ones ride next to the policy forward)
+        if self.early_reset:
+            self.task.set_early_reset(True)
+            # step order post(t) -> policy(t) -> pre(t+1), so that the policy kernel and the reset half it overlaps sit in the same
+            # captured graph; prime with the first step's pre_physics_step
             self.task.pre_physics_step(self.actions, self.uniforms[0])
         if self.w["policy"] == "gnn":
             from locomanipulationrl_b200.rollout import RolloutBuffer, RunningMeanStd
@@ -289,25 +293,11 @@ class Pipeline:
 
     def step_eager(self, i, t=0):
         task = self.task
-        if self.overlap_pre:
-            # MLP workload with the action sink: the head epilogue delivers action = mean into the task, so the only thing left of the
-            # NEXT pre_physics_step is its reset half, which depends on this post step alone: it runs on a second stream next to the
-            # policy forward (the persistent MLP CTAs leave room for its 128-thread CTAs on every SM) and joins before the next step.
+        if self.early_reset:
             task.set_up_scene(self.scenes[i])           # "physics": the next state set becomes the live views
             task.post_physics_step()
-            cur = torch.cuda.current_stream()
-            sink = task.action_sink()
-            if self.early_reset:
-                # same stream, reset half first: the policy kernel's prologue (117 KB of weights per CTA, TMEM allocation) then
-                # overlaps it through programmatic dependent launch
-                task.pre_physics_step(None, self.uniforms[(i + 1) % STATE_SETS])
-                self.policy(task.obs_buf, norm_mean=self.norm_mean, norm_inv_std=self.norm_inv_std, out=(self.mu, self.value), sink=sink)
-                return
-            self.side.wait_stream(cur)
-            with torch.cuda.stream(self.side):
-                task.pre_physics_step(None, self.uniforms[(i + 1) % STATE_SETS])
-            self.policy(task.obs_buf, norm_mean=self.norm_mean, norm_inv_std=self.norm_inv_std, out=(self.mu, self.value), sink=sink)
-            cur.wait_stream(self.side)
+            self.policy(task.obs_buf, norm_mean=self.norm_mean, norm_inv_std=self.norm_inv_std, out=(self.mu, self.value), sink=task.action_sink())
+            task.pre_physics_step(None, self.uniforms[(i + 1) % STATE_SETS])     # reset half, released beside the policy kernel
             return
         # action sink (default): the kernel that produced the actions (MLP head epilogue / rollout writer) already delivered them into
         # the task's buffers (clamp, current_actions, joint targets), so pre_physics_step runs its reset half only
@@ -335,10 +325,13 @@ class Pipeline:
         self.rollout.write(k, task.obs_buf, self.mu, self.value, self.log_std, task.rew_buf, task.reset_buf, noise=None,
                            actions_out=self.actions, obs_stats=self.obs_stats, sink=task.action_sink() if self.use_sink else None)
 
-    def capture(self, after_step=None):
-        """One CUDA graph per state set (parity of the action ring alternates, STATE_SETS is even).  ``after_step(i)``: called after
-        each eager warm-up step (tests/test_bench_shapes_gpu.py tracks the oracle through them)."""
-        assert STATE_SETS % 2 == 0
+    def capture(self, after_step=None, steps_per_graph=1):
+        """CUDA graphs of the step loop.  ``steps_per_graph`` = 1: one graph per state set (parity of the action ring alternates,
+        STATE_SETS is even); = STATE_SETS: ONE graph holding a whole rotation of the state sets, replayed by the first step of every
+        rotation (bench.py's default: the programmatic-dependent-launch chain then also spans the step boundaries, which a graph launch
+        per step cuts).  ``after_step(i)``: called after each eager warm-up step (tests/test_bench_shapes_gpu.py tracks the oracle
+        through them)."""
+        assert STATE_SETS % 2 == 0 and steps_per_graph in (1, STATE_SETS)
         if self.w["policy"] != "mlp":
             return                                      # the GAE cadence needs a host-side counter: stay eager
         side = torch.cuda.Stream(device=self.device)
@@ -350,20 +343,26 @@ class Pipeline:
                     after_step(i)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        self.graphs, self.graph_parity = [], []
-        for i in range(STATE_SETS):
+        self.graphs, self.graph_parity, self.steps_per_graph = [], [], steps_per_graph
+        for i in range(0, STATE_SETS, steps_per_graph):
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                self.step_eager(i)
+                for j in range(steps_per_graph):
+                    self.step_eager(i + j)
             self.graphs.append(g)
             self.graph_parity.append(self.lib.lm_task_step_parity(self.task._handle))
         torch.cuda.synchronize()
 
     def step(self, t):
+        """Step t of the loop.  With a whole rotation per graph the first step of a rotation launches all of it (callers step in whole
+        rotations: the rollout horizons are multiples of STATE_SETS)."""
         if self.graphs is not None:
-            self.graphs[t % STATE_SETS].replay()
-            # replays skip the host side of pre_physics_step: keep the handle's ring parity in step for host-side readers
-            self.lib.lm_task_set_step_parity(self.task._handle, self.graph_parity[t % STATE_SETS])
+            spg = self.steps_per_graph
+            if t % spg == 0:
+                k = (t % STATE_SETS) // spg
+                self.graphs[k].replay()
+                # replays skip the host side of pre_physics_step: keep the handle's ring parity in step for host-side readers
+                self.lib.lm_task_set_step_parity(self.task._handle, self.graph_parity[k])
         else:
             self.step_eager(t % STATE_SETS, t)
 
@@ -450,8 +449,9 @@ def cuda_arm(args):
         torch.cuda.synchronize()
 
     if not args.no_graphs:
-        pipe.capture()
-    for t in range(max(args.warmup, 3)):
+        assert HORIZON_MLP % STATE_SETS == 0
+        pipe.capture(steps_per_graph=1 if os.environ.get("LM_BENCH_GRAPH_PER_STEP") else STATE_SETS)
+    for t in range(-(-max(args.warmup, 3) // STATE_SETS) * STATE_SETS):     # whole rotations of the state sets
         pipe.step(t)
     for _ in range(2):      # NCCL connects lazily at the first collective of each size: keep that out of the timed region
         comm()
@@ -522,6 +522,8 @@ def cuda_arm(args):
     if rank == 0 and not args.no_kernel_times:
         task = pipe.task
         iters = max(12, min(args.steps, 60))
+        if pipe.early_reset:
+            task.set_early_reset(False)       # the sequences timed below put pre right behind post: outside the early-reset contract
 
         def post_only(i):
             task.set_up_scene(pipe.scenes[i % STATE_SETS])
@@ -664,15 +666,14 @@ def cuda_arm(args):
     if rank == 0:
         clocks = sampler.summary()
         line = {"metric": "env-steps/s (obs+reward+PD+reset+policy)", "value": value, "unit": "env-steps/s", "n_gpus": world,
-                "steps": steps_timed, "steps_requested": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / steps_timed,
+                "steps": steps_timed, "steps_requested": args.steps, "warmup": -(-max(args.warmup, 3) // STATE_SETS) * STATE_SETS, "ms_per_step": ms_total / steps_timed,
                 "timed_region_s": ms_total * 1e-3, "collectives_in_timed_region": collectives, "collective_us": comm_us,
                 "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32 task math, bf16 x bf16 -> f32 policy GEMMs",
                 "data": "synthetic",
                 "config": bench_config(pipe.w, world),
                 "run": {"cuda_graphs": pipe.graphs is not None, "action_sink": pipe.use_sink,
-                           "pre_reset_overlaps_policy": pipe.overlap_pre and not pipe.early_reset, "post_finish_deferred": pipe.defer_finish,
-                           "early_reset": pipe.early_reset, "comm": (f"one stat + gradient-arena all-reduce (58,651 fp32) every {horizon} steps, "
+                           "post_finish_deferred": pipe.defer_finish, "early_reset": pipe.early_reset, "comm": (f"one stat + gradient-arena all-reduce (58,651 fp32) every {horizon} steps, "
                                     + ("one-shot NVLink peer-memory kernel (lm_comm_allreduce)" if peer is not None else "NCCL all_reduce")
                                     + f", {args.comm_stream} stream, CUDA graph") if world > 1 else "none",
                            "timed": f"{reps} rollout horizons of {horizon} steps"},

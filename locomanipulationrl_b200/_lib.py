@@ -134,6 +134,7 @@ SYMBOLS = {
     "lm_task_step_parity": (C.c_int, [_vp]),
     "lm_task_set_step_parity": (C.c_int, [_vp, C.c_int]),
     "lm_task_set_defer_finish": (C.c_int, [_vp, C.c_int]),
+    "lm_task_set_early_reset": (C.c_int, [_vp, C.c_int]),
     "lm_task_post_finish": (C.c_int, [_vp, C.POINTER(LmTaskBuffers), _vp]),
     "lm_task_set_clamp_observations": (C.c_int, [_vp, C.c_int]),
     "lm_task_invalidate_reset_scan": (C.c_int, [_vp]),

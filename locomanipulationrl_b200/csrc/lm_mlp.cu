@@ -223,8 +223,15 @@ __device__ __forceinline__ void epilogue_head(const Args& a, uint32_t tmem_acc, 
   }
 }
 
+// The inference instantiation is compiled under a 672-thread bound, i.e. for at most 80 registers (it is launched with 544 threads):
+// registers are allocated in units of four warps, so the 17-warp CTA then leaves room for one 128-thread CTA of another kernel on
+// the SM — the reset half of the next pre_physics_step, which runs beside this kernel (lm_task_set_early_reset).  At 96 registers
+// the kernel alone is 0.7 us faster (17.4 vs 18.1 us at 65,536 envs) but nothing fits beside it: 42.9 vs 37.6 us per env step.
+#ifndef LM_MLP_LAUNCH_BOUND
+#define LM_MLP_LAUNCH_BOUND 672
+#endif
 template <bool kSave, bool kStamp = false>
-__global__ void __launch_bounds__(THREADS, 1) k_mlp_forward(const Args a) {
+__global__ void __launch_bounds__(kSave ? THREADS : LM_MLP_LAUNCH_BOUND, 1) k_mlp_forward(const Args a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   // mbarriers.  count 1: bar_w (weight TMA), bar_acc* (tcgen05.commit: accumulator complete).  count 16 (one arrive per epilogue
   // warp): bar_a0 (A0 operand written), bar_act1[s] / bar_act2[s] / bar_act3 (K chunk s of the next layer's A operand written; for
@@ -242,7 +249,6 @@ __global__ void __launch_bounds__(THREADS, 1) k_mlp_forward(const Args a) {
   const float* bias3 = bias2 + D2;
   const float* biash = bias3 + D3;
 
-  pdl_launch_dependents();
   if (tid == 0) {
     mbar_init(&bar_w, 1); mbar_init(&bar_a0, E_WARPS);
     mbar_init(&bar_acc1, 1); mbar_init(&bar_acc2, 1); mbar_init(&bar_acc3, 1); mbar_init(&bar_acch, 1);
@@ -339,6 +345,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_mlp_forward(const Args a) {
     }
     ObsRegs regs;
     pdl_wait();                                            // the observations are the predecessor kernel's output
+    // Dependents are released only now, i.e. once the producer of the observations (the post step) has completed: a dependent that
+    // needs nothing from THIS kernel (lm_task_set_early_reset: the reset half of the next pre step) may then run beside it.
+    pdl_launch_dependents();
     if (n_loc > 0) {
       obs_fetch(a, tile0, tid, regs);
 #pragma unroll

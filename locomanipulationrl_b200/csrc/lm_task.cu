@@ -741,24 +741,15 @@ __global__ void __launch_bounds__(FINISH_THREADS) k_post_finish(const KernelPara
 // K_pre: (1) reset mask -> rank -> compacted ascending id list (the `nonzero()` of QPC:206); (2) clamp + stash
 // actions, take_action.  The reset bodies themselves run in k_reset_apply over the compacted list, so the ~3 % of
 // envs that reset do not drag every warp through the (double-precision) goal resampling path.
-__global__ void __launch_bounds__(T) k_pre(const KernelParams kp, const PreArgs a) {
-  pdl_launch_dependents();
-  pdl_wait();
+// one tile of pre_physics_step (shared by k_pre: one CTA per tile, and k_pre_early: resident CTAs walking the tiles)
+__device__ __forceinline__ void pre_tile(const KernelParams& kp, const PreArgs& a, const int tile_idx, int* warp_base, int* base_part, int* list) {
   const LmTaskParams& P = kp.p;
-  if (blockIdx.x == (unsigned)kp.d.num_tiles) {         // the extra CTA of a deferred finish: extras / counters of the previous post step
-    __shared__ FinishSmem fs;
-    finish_tail<T, true>(kp, a, fs);
-    return;
-  }
-  const Tile tl = tile_of(kp, blockIdx.x);
+  const Tile tl = tile_of(kp, tile_idx);
   const int r = threadIdx.x;
   const int N = P.num_envs;
   float* ring_cur = a.buf.actions_ring + (size_t)a.parity * N * LM_NUM_ACT;
   const LmRobotViews& V = tl.is_mani ? a.mani : a.loco;
 
-  __shared__ int warp_base[T / 32];
-  __shared__ int base_part[T / 32];
-  __shared__ int list[T];
   const int e = tl.e0 + r, hr = tl.hr0 + r;
   // ---- every independent load first: the reset flag, this tile's rank base and the thread's three action chunks are all
   //      in flight before anything waits (the reset bodies below are a long dependent chain on a few lanes)
@@ -766,13 +757,13 @@ __global__ void __launch_bounds__(T) k_pre(const KernelParams kp, const PreArgs 
   if (r < tl.n) flag64 = a.buf.reset_buf[e];
   int tile_base = 0;
   if (a.tile_counts == nullptr) {
-    tile_base = a.scan_base[blockIdx.x / kp.d.scan_per] + a.tile_offsets[blockIdx.x];
+    tile_base = a.scan_base[tile_idx / kp.d.scan_per] + a.tile_offsets[tile_idx];
   } else {
-    // rank base from the dense per-tile reset counts of the last post step: tiles [0, blockIdx.x), four per 128-bit load
+    // rank base from the dense per-tile reset counts of the last post step: the tiles before this one, four per 128-bit load
     const int4* c4 = reinterpret_cast<const int4*>(a.tile_counts);
-    for (int i = r; 4 * i < (int)blockIdx.x; i += T) {
+    for (int i = r; 4 * i < tile_idx; i += T) {
       const int4 c = __ldcg(c4 + i);
-      const int t0 = 4 * i, lim = (int)blockIdx.x;
+      const int t0 = 4 * i, lim = tile_idx;
       tile_base += c.x + (t0 + 1 < lim ? c.y : 0) + (t0 + 2 < lim ? c.z : 0) + (t0 + 3 < lim ? c.w : 0);
     }
   }
@@ -849,12 +840,12 @@ __global__ void __launch_bounds__(T) k_pre(const KernelParams kp, const PreArgs 
     count += warp_base[w];
   }
   if (a.tile_counts != nullptr && r == 0) {             // num_reset, which the inline finish pass writes otherwise
-    if ((int)blockIdx.x == kp.d.num_tiles - 1) {
+    if (tile_idx == kp.d.num_tiles - 1) {
       a.buf.num_reset[0] = tile_base + count;
       if (P.kind == LM_KIND_LOCO) a.buf.num_reset[1] = tile_base + count;
       if (P.kind == LM_KIND_MANI) a.buf.num_reset[1] = 0;
     }
-    if (P.kind == LM_KIND_COTRAIN && (int)blockIdx.x == kp.d.tiles_per_half) a.buf.num_reset[1] = tile_base;   // resets in the locomotion half
+    if (P.kind == LM_KIND_COTRAIN && tile_idx == kp.d.tiles_per_half) a.buf.num_reset[1] = tile_base;   // resets in the locomotion half
   }
   if (count == 0) return;
   if (flag) list[local_rank] = r;
@@ -869,6 +860,120 @@ __global__ void __launch_bounds__(T) k_pre(const KernelParams kp, const PreArgs 
       reset_one_env(kp, a, V, ring_last, tl.is_mani, tl.e0 + lr, tl.hr0 + lr, tile_base + (idx >> 1), idx & 1);
     }
   }
+}
+
+__global__ void __launch_bounds__(T) k_pre(const KernelParams kp, const PreArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ int warp_base[T / 32];
+  __shared__ int base_part[T / 32];
+  __shared__ int list[T];
+  if (blockIdx.x == (unsigned)kp.d.num_tiles) {         // the extra CTA of a deferred finish: extras / counters of the previous post step
+    __shared__ FinishSmem fs;
+    finish_tail<T, true>(kp, a, fs);
+    return;
+  }
+  pre_tile(kp, a, (int)blockIdx.x, warp_base, base_part, list);
+}
+
+// The reset half of pre_physics_step (actions == NULL: they arrive through an LmActionSink) for lm_task_set_early_reset: nothing in
+// it depends on the kernel launched before it — the policy forward, which only READS the post step's outputs and delivers the
+// actions — so under programmatic dependent launch the whole half runs NEXT TO that kernel instead of behind it.  The grid has at
+// most one CTA per SM (128 threads: fits beside the policy kernel's 544-thread CTA when that kernel is built for <= 80 registers —
+// registers are allocated in units of four warps), so every CTA is resident at once; each CTA takes up to four tiles per pass: all
+// their flags and rank bases are fetched together and all their reset bodies run side by side on the CTA's lanes, one dependent
+// chain instead of one per tile.  Only the very last instruction waits for the predecessor, so that this grid's completion — which
+// releases the next post step — still implies the predecessor's.  Precondition (documented at lm_task_set_early_reset): the
+// predecessor triggers its dependents only after its own dependency wait, i.e. after the post step has completed (k_mlp_forward
+// does).
+constexpr int EARLY_TILES = 4;
+__global__ void __launch_bounds__(T) k_pre_early(const KernelParams kp, const PreArgs a, const int tile_ctas) {
+  pdl_launch_dependents();
+  const LmTaskParams& P = kp.p;
+  __shared__ int warp_cnt[EARLY_TILES][T / 32];
+  __shared__ int base_part[EARLY_TILES][T / 32];
+  __shared__ int list[EARLY_TILES][T];
+  if ((int)blockIdx.x == tile_ctas) {                   // the extra CTA of a deferred finish
+    __shared__ FinishSmem fs;
+    finish_tail<T, true>(kp, a, fs);
+  } else {
+    const int r = threadIdx.x, lane = r & 31, warp = r >> 5, nt = kp.d.num_tiles;
+    float* ring_last = a.buf.actions_ring + (size_t)(a.parity ^ 1) * P.num_envs * LM_NUM_ACT;
+    for (int first = blockIdx.x; first < nt; first += EARLY_TILES * tile_ctas) {
+      Tile tl[EARLY_TILES];
+      long long flag64[EARLY_TILES];
+      int base[EARLY_TILES];
+      // ---- phase 1: every independent load of the pass first (flags, per-tile counts)
+#pragma unroll
+      for (int j = 0; j < EARLY_TILES; ++j) {
+        const int tile = first + j * tile_ctas;
+        flag64[j] = 0; base[j] = 0;
+        if (tile >= nt) continue;
+        tl[j] = tile_of(kp, tile);
+        if (r < tl[j].n) flag64[j] = a.buf.reset_buf[tl[j].e0 + r];
+        if (a.tile_counts == nullptr) {
+          if (r == 0) base[j] = a.scan_base[tile / kp.d.scan_per] + a.tile_offsets[tile];
+        } else {
+          const int4* c4 = reinterpret_cast<const int4*>(a.tile_counts);
+          for (int i = r; 4 * i < tile; i += T) {
+            const int4 c = __ldcg(c4 + i);
+            const int t0 = 4 * i;
+            base[j] += c.x + (t0 + 1 < tile ? c.y : 0) + (t0 + 2 < tile ? c.z : 0) + (t0 + 3 < tile ? c.w : 0);
+          }
+        }
+      }
+      unsigned bal[EARLY_TILES];
+#pragma unroll
+      for (int j = 0; j < EARLY_TILES; ++j) {
+        bal[j] = __ballot_sync(0xffffffffu, flag64[j] != 0);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) base[j] += __shfl_xor_sync(0xffffffffu, base[j], off);
+        if (lane == 0) { warp_cnt[j][warp] = __popc(bal[j]); base_part[j][warp] = base[j]; }
+      }
+      __syncthreads();
+      int count[EARLY_TILES], total = 0;
+#pragma unroll
+      for (int j = 0; j < EARLY_TILES; ++j) {
+        int local_rank = __popc(bal[j] & ((1u << lane) - 1u));
+        count[j] = 0; base[j] = 0;
+#pragma unroll
+        for (int w = 0; w < T / 32; ++w) {
+          if (w < warp) local_rank += warp_cnt[j][w];
+          count[j] += warp_cnt[j][w];
+          base[j] += base_part[j][w];
+        }
+        total += count[j];
+        if (flag64[j] != 0) list[j][local_rank] = r;
+        const int tile = first + j * tile_ctas;
+        if (a.tile_counts != nullptr && r == 0 && tile < nt) {      // num_reset, which the inline finish pass writes otherwise
+          if (tile == nt - 1) {
+            a.buf.num_reset[0] = base[j] + count[j];
+            if (P.kind == LM_KIND_LOCO) a.buf.num_reset[1] = base[j] + count[j];
+            if (P.kind == LM_KIND_MANI) a.buf.num_reset[1] = 0;
+          }
+          if (P.kind == LM_KIND_COTRAIN && tile == kp.d.tiles_per_half) a.buf.num_reset[1] = base[j];
+        }
+      }
+      __syncthreads();
+      // ---- phase 2: the reset bodies of all tiles of the pass, two lanes per reset env (role 0 = goal + indicator pose, role 1 =
+      //      defaults + history), dealt round-robin over the four warps
+      const int slot = (lane << 2) | warp;
+      for (int idx = slot; idx < 2 * total; idx += T) {
+        int k = idx, j = 0;
+#pragma unroll
+        for (int jj = 0; jj < EARLY_TILES - 1; ++jj)
+          if (j == jj && k >= 2 * count[jj]) { k -= 2 * count[jj]; j = jj + 1; }
+        Tile tj = tl[0]; int bj = base[0];
+#pragma unroll
+        for (int jj = 1; jj < EARLY_TILES; ++jj)
+          if (j == jj) { tj = tl[jj]; bj = base[jj]; }
+        const int lr = list[j][k >> 1];
+        reset_one_env(kp, a, tj.is_mani ? a.mani : a.loco, ring_last, tj.is_mani, tj.e0 + lr, tj.hr0 + lr, bj + (k >> 1), k & 1);
+      }
+      __syncthreads();                                  // the shared scratch is reused by the next pass
+    }
+  }
+  pdl_wait();
 }
 
 
@@ -1242,6 +1347,7 @@ struct LmTask {
   int inline_finish;
   int defer_finish;                // the caller launches the finish pass itself (lm_task_post_finish), e.g. on a second stream
   int finish_pending;              // a deferred finish pass has not run yet
+  int early_reset;                 // lm_task_set_early_reset: the reset half of pre_step may run beside the kernel launched before it
   LmPdState pd;
   int has_pd;
   float* partials;
@@ -1481,7 +1587,15 @@ int lm_task_pre_step(LmTask* t, const LmRobotViews* loco, const LmRobotViews* ma
       t->finish_pending = 0;
     }
   }
-  cudaError_t le = lm_launch(k_pre, dim3(grid), dim3(T), 0, s, true, t->kp, a);
+  cudaError_t le;
+  if (t->early_reset && !actions && scan_was_valid) {
+    // At most one CTA per SM, each walking its tiles: every CTA of the grid is then resident beside the predecessor's CTAs (a CTA that
+    // has finished waits for the predecessor and keeps its slot, so CTAs beyond the resident set would only start when it drains).
+    const int tile_ctas = d.num_tiles < t->sm_count ? d.num_tiles : t->sm_count;
+    le = lm_launch(k_pre_early, dim3(tile_ctas + (grid > d.num_tiles ? 1 : 0)), dim3(T), 0, s, true, t->kp, a, tile_ctas);
+  } else {
+    le = lm_launch(k_pre, dim3(grid), dim3(T), 0, s, true, t->kp, a);
+  }
   if (le != cudaSuccess) return lm_fail((int)le, "lm_task_pre_step: %s", cudaGetErrorString(le));
   if (finish_behind) {
     PostArgs f;
@@ -1557,6 +1671,18 @@ int lm_task_set_defer_finish(LmTask* t, int on) {
   const int threads = (t->inline_finish || t->defer_finish) ? T : FINISH_THREADS;
   t->kp.d.scan_per = (t->kp.d.num_tiles + threads - 1) / threads;
   t->scan_valid = 0;                  // the layout of tile_offsets / scan_base depends on scan_per
+  return LM_OK;
+}
+
+// Early reset (opt-in pipelining, with an action sink): lm_task_pre_step(actions == NULL) — the reset half only — no longer waits for
+// the kernel launched before it on the stream; under programmatic dependent launch it runs beside that kernel and merely completes
+// after it.  Contract: that kernel (a) does not write anything the reset half reads or writes — the policy forward with a sink
+// writes the action ring's NEXT slot and the joint targets, the reset half the scene rows, goals, flags and the ring's LAST slot —
+// and (b) triggers its dependents only after its own dependency wait, so that the post step whose flags the reset half reads has
+// completed (lm_mlp_forward_sink does; any kernel without griddepcontrol instructions is trivially safe: no overlap then).
+int lm_task_set_early_reset(LmTask* t, int on) {
+  if (!t) return lm_fail(LM_ERR_BAD_ARG, "lm_task_set_early_reset: task is NULL");
+  t->early_reset = on != 0;
   return LM_OK;
 }
 

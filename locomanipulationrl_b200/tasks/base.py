@@ -372,6 +372,11 @@ class LocoManipulationTask:
         _lib.check(self._lib.lm_task_set_defer_finish(self._handle, int(bool(on))), "lm_task_set_defer_finish")
         self._defer_finish = bool(on)
 
+    def set_early_reset(self, on: bool = True) -> None:
+        """With an action sink: ``pre_physics_step(None, uniforms)`` (the reset half) runs beside the kernel launched before it — the
+        policy forward delivering the actions — instead of behind it (see ``lm_task_set_early_reset`` for the contract)."""
+        _lib.check(self._lib.lm_task_set_early_reset(self._handle, int(bool(on))), "lm_task_set_early_reset")
+
     def post_finish(self) -> None:
         """Run the deferred finish pass now (acts at most once per post step)."""
         _lib.check(self._lib.lm_task_post_finish(self._handle, C.byref(self._buffers), self._stream()), "lm_task_post_finish")

@@ -18,21 +18,20 @@ def _tracker(task, port, scene_cpu, cfg, n):
     return ro
 
 
-def test_bench_pipeline_65536_graph_replay_matches_port(monkeypatch):
-    """BASELINE configs[2] in bench.py's sink / second-stream variant (LM_BENCH_SINK=1 LM_BENCH_OVERLAP=1; the default pipeline is
-    the next test): JointLocomanipulationVertical, 65,536 envs, fuse_obs_clamp, six rotating
-    state sets, action = policy mean delivered through the action sink, the reset half of the next pre_physics_step running next to
-    the policy forward on a second stream, one CUDA graph per state set — tracked by the oracle port for the six eager warm-up
-    steps and eight replayed ones.  One pipeline step = post(t) -> {policy(t) || pre(t+1)}; the port runs the same calls in order."""
+def test_bench_default_pipeline_65536_graph_replay_matches_port():
+    """BASELINE configs[2] exactly as bench.py times it by default: JointLocomanipulationVertical, 65,536 envs, fuse_obs_clamp, six
+    rotating state sets, action = policy mean delivered through the action sink (the action half of pre_physics_step inside the MLP head
+    epilogue), the reset half of the next pre_physics_step released beside the policy kernel by programmatic dependent launch
+    (lm_task_set_early_reset), the post kernel's finish pass deferred into that launch, one CUDA graph per state set — tracked by the
+    oracle port for the six eager warm-up steps and eight replayed ones.  One pipeline step = post(t) -> policy(t) || pre(t+1); the
+    port runs the same calls in order."""
     import bench
     from oracle import port
-    monkeypatch.setenv("LM_BENCH_SINK", "1")
-    monkeypatch.setenv("LM_BENCH_OVERLAP", "1")
     dev = torch.device("cuda:0")
     pipe = bench.Pipeline("cotrain64k", dev, rank=0)
     cfg, n, task = pipe.cfg, pipe.n, pipe.task
     S = bench.STATE_SETS
-    assert n == 65536 and task._fuse_obs_clamp and pipe.overlap_pre
+    assert n == 65536 and task._fuse_obs_clamp and pipe.use_sink and pipe.early_reset and pipe.defer_finish
     scenes_cpu = []
     for i in range(S):
         sc = synthetic.SyntheticScene(cfg, n, seed=42)
@@ -95,17 +94,25 @@ def test_bench_pipeline_65536_graph_replay_matches_port(monkeypatch):
     print("65,536-env graph replay max abs err:", {k.split(" ", 2)[-1]: f"{v:.2e}" for k, v in sorted(stats["err"].items())[-12:]})
 
 
-def test_bench_default_pipeline_65536_graph_replay_matches_port():
-    """BASELINE configs[2] exactly as bench.py times it by default: JointLocomanipulationVertical, 65,536 envs, fuse_obs_clamp, six
-    rotating state sets, the policy mean fed back as the next action, pre -> post -> policy captured as one CUDA graph per state
-    set — tracked by the oracle port through the six eager warm-up steps and eight replayed ones."""
+
+@pytest.mark.parametrize("variant", ["sink_late_inline", "plain"])
+def test_bench_pipeline_65536_graph_replay_matches_port(variant, monkeypatch):
+    """bench.py's conservative pipelines (step order pre -> post -> policy) at the same shape: sink_late_inline = action sink only, reset
+    half behind the policy kernel, finish pass inside the post kernel (LM_BENCH_NO_EARLY, LM_BENCH_INLINE_FINISH); plain = actions
+    through k_pre (LM_BENCH_NO_SINK), deferred finish."""
     import bench
     from oracle import port
+    if variant == "sink_late_inline":
+        monkeypatch.setenv("LM_BENCH_NO_EARLY", "1")
+        monkeypatch.setenv("LM_BENCH_INLINE_FINISH", "1")
+    if variant == "plain":
+        monkeypatch.setenv("LM_BENCH_NO_SINK", "1")
     dev = torch.device("cuda:0")
     pipe = bench.Pipeline("cotrain64k", dev, rank=0)
     cfg, n = pipe.cfg, pipe.n
     S = bench.STATE_SETS
-    assert n == 65536 and pipe.task._fuse_obs_clamp and not pipe.use_sink and not pipe.overlap_pre and pipe.defer_finish
+    assert n == 65536 and pipe.task._fuse_obs_clamp
+    assert (pipe.use_sink, pipe.early_reset, pipe.defer_finish) == {"sink_late_inline": (True, False, False), "plain": (False, False, True)}[variant]
     scenes_cpu = []
     for i in range(S):
         sc = synthetic.SyntheticScene(cfg, n, seed=42)
@@ -143,7 +150,7 @@ def test_bench_default_pipeline_65536_graph_replay_matches_port():
         pipe.step(t)
         track(t % S, t)
     assert ro.exempt_events == 0, f"{ro.exempt_events} near-threshold mask exemptions"
-    print("65,536-env default pipeline, graph replay, max abs err:", {k: f"{v:.2e}" for k, v in ro.max_err.items()})
+    print(f"65,536-env pipeline ({variant}), graph replay, max abs err:", {k: f"{v:.2e}" for k, v in ro.max_err.items()})
 
 
 @pytest.mark.parametrize("name,n", [("JointLocomanipulationVertical", 4096), ("QuadrupedManipulatePlate", 1000), ("QuadrupedPoseControl", 130)])
@@ -372,3 +379,34 @@ def test_deferred_finish_matches_inline(n):
             assert torch.equal(dfr._extras_buf, ref._extras_buf) and torch.equal(dfr._counters, ref._counters), f"step {t}: early finish"
         for f in ("obs_buf", "rew_buf", "reset_buf", "progress_buf"):
             assert torch.equal(getattr(dfr, f), getattr(ref, f)), f"step {t}: {f} after post"
+
+
+def test_bench_whole_rotation_graph_equals_per_step_graphs():
+    """bench.py replays ONE graph holding a whole rotation of the six state sets (the PDL chain then spans the step boundaries); the
+    per-step graphs are what the port tracks above.  Same seeds, 18 steps each: every task / policy buffer bit-identical at the
+    rotation boundaries."""
+    import bench
+    dev = torch.device("cuda:0")
+    S = bench.STATE_SETS
+    pipes = []
+    for spg in (1, S):
+        pipe = bench.Pipeline("cotrain64k", dev, rank=0)
+        pipe.capture(steps_per_graph=spg)
+        pipes.append(pipe)
+    a, b = pipes
+    assert len(a.graphs) == S and len(b.graphs) == 1
+    for rot in range(3):
+        for t in range(rot * S, (rot + 1) * S):
+            a.step(t); b.step(t)
+        for p_ in pipes:
+            p_.task.post_finish()
+        torch.cuda.synchronize()
+        for f in ("obs_buf", "rew_buf", "reset_buf", "progress_buf", "successes", "consecutive_successes", "goal_reset_buf", "goal_quaternions",
+                  "_extras_buf", "_counters", "_actions_ring", "num_reset_buf", "last_base_tip_positions", "last_joint_velocities",
+                  "targets_loco", "targets_mani"):
+            assert torch.equal(getattr(a.task, f), getattr(b.task, f)), f"rotation {rot}: {f}"
+        assert torch.equal(a.mu, b.mu) and torch.equal(a.value, b.value), f"rotation {rot}: policy outputs"
+        for i in range(S):
+            for grp in ("loco", "mani"):
+                for k, v in getattr(a.scenes[i], grp).items():
+                    assert torch.equal(getattr(b.scenes[i], grp)[k], v), f"rotation {rot}: scene[{i}].{grp}.{k}"
