@@ -183,22 +183,27 @@ __device__ __forceinline__ void obs_fetch(const Args& a, int tile, int tid, ObsR
     r.v[j] = row < rows ? ld_nc_f4(base + (size_t)(j * E_THREADS + tid) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
 }
-// float4 j of the thread: normalise / clamp, bf16, into the A0 operand (and the training forward's saved copy)
-// (`rows`: valid rows of the tile, computed once per tile by the caller; rows beyond the batch stay zero)
-__device__ __forceinline__ void obs_convert_one(const Args& a, int rows, int tid, int j, const ObsRegs& r, const float4& mean, const float4& inv_std,
-                                                bool has_norm, uint8_t* A0, uint8_t* gA0) {
-  const int c4 = tid & 15;
-  const int row = j * 32 + (tid >> 4);
-  float4 x = r.v[j];
-  if (has_norm && row < rows) {
-    x.x = fminf(fmaxf((x.x - mean.x) * inv_std.x, -a.norm_clip), a.norm_clip);
-    x.y = fminf(fmaxf((x.y - mean.y) * inv_std.y, -a.norm_clip), a.norm_clip);
-    x.z = fminf(fmaxf((x.z - mean.z) * inv_std.z, -a.norm_clip), a.norm_clip);
-    x.w = fminf(fmaxf((x.w - mean.w) * inv_std.w, -a.norm_clip), a.norm_clip);
+// One float4 of the thread's share: normalise, bf16, clamp, into the A0 operand (and the training forward's saved copy).  The clamp is
+// taken on the packed bf16 pairs — rounding is monotone, so min(bf16(x), bf16(c)) = bf16(min(x, c)) for any clip c — and `dst` is the
+// thread's precomputed A0 address of the chunk (base + j * 512 bytes), so a piece costs 15 instructions.  kGuard (training forward,
+// whose saved rows feed the weight gradients): rows beyond the batch stay zero.
+template <bool kGuard>
+__device__ __forceinline__ void obs_convert_one(float4 x, bool row_valid, const float4& mean, const float4& inv_std, uint32_t clip2, uint32_t nclip2,
+                                                bool has_norm, uint8_t* dst, uint8_t* gdst) {
+  if (has_norm) {
+    x.x = (x.x - mean.x) * inv_std.x; x.y = (x.y - mean.y) * inv_std.y;
+    x.z = (x.z - mean.z) * inv_std.z; x.w = (x.w - mean.w) * inv_std.w;
   }
-  const uint2 w = make_uint2(pack_bf16(x.x, x.y), pack_bf16(x.z, x.w));
-  *reinterpret_cast<uint2*>(A0 + elem_offset(TM, row, 4 * c4)) = w;
-  if (gA0 != nullptr) *reinterpret_cast<uint2*>(gA0 + elem_offset(TM, row, 4 * c4)) = w;
+  uint32_t lo = pack_bf16(x.x, x.y), hi = pack_bf16(x.z, x.w);
+  if (has_norm) {
+    asm("min.bf16x2 %0, %0, %1;" : "+r"(lo) : "r"(clip2));
+    asm("max.bf16x2 %0, %0, %1;" : "+r"(lo) : "r"(nclip2));
+    asm("min.bf16x2 %0, %0, %1;" : "+r"(hi) : "r"(clip2));
+    asm("max.bf16x2 %0, %0, %1;" : "+r"(hi) : "r"(nclip2));
+  }
+  if (kGuard && !row_valid) { lo = 0u; hi = 0u; }
+  *reinterpret_cast<uint2*>(dst) = make_uint2(lo, hi);
+  if (gdst != nullptr) *reinterpret_cast<uint2*>(gdst) = make_uint2(lo, hi);
 }
 
 // Head epilogue, spread over the four column-quarter warps of a lane group: quarter q reads accumulator columns [4q, 4q + 4) —
@@ -344,6 +349,9 @@ __global__ void __launch_bounds__(kSave ? THREADS : LM_MLP_LAUNCH_BOUND, 1) k_ml
       inv_std = *reinterpret_cast<const float4*>(a.norm_inv_std + 4 * (tid & 15));
     }
     ObsRegs regs;
+    // this thread's chunk of A0: row (tid / 16) + 32 j, columns 4 (tid % 16)..: byte offset of j = 0, then 512 bytes per j
+    const int a0_off = elem_offset(TM, tid >> 4, 4 * (tid & 15));
+    const uint32_t clip2 = pack_bf16(a.norm_clip, a.norm_clip), nclip2 = pack_bf16(-a.norm_clip, -a.norm_clip);
     pdl_wait();                                            // the observations are the predecessor kernel's output
     // Dependents are released only now, i.e. once the producer of the observations (the post step) has completed: a dependent that
     // needs nothing from THIS kernel (lm_task_set_early_reset: the reset half of the next pre step) may then run beside it.
@@ -351,7 +359,9 @@ __global__ void __launch_bounds__(kSave ? THREADS : LM_MLP_LAUNCH_BOUND, 1) k_ml
     if (n_loc > 0) {
       obs_fetch(a, tile0, tid, regs);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) obs_convert_one(a, min(TM, a.n - tile0 * TM), tid, j, regs, mean, inv_std, has_norm, A0, g0(tile0));
+      for (int j = 0; j < 4; ++j)
+        obs_convert_one<kSave>(regs.v[j], j * 32 + (tid >> 4) < a.n - tile0 * TM, mean, inv_std, clip2, nclip2, has_norm, A0 + a0_off + j * 512,
+                               kSave ? g0(tile0) + a0_off + j * 512 : nullptr);
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_a0);
@@ -373,7 +383,11 @@ __global__ void __launch_bounds__(kSave ? THREADS : LM_MLP_LAUNCH_BOUND, 1) k_ml
       if (st) stamp<kStamp>(a, 8 + 8 * it + 1);
       uint8_t* gA0n = more ? g0(tile + stride) : nullptr;
       const int rows_n = min(TM, a.n - (tile + stride) * TM);
-      auto obs_hook = [&](int s) { if (more) obs_convert_one(a, rows_n, tid, s, regs, mean, inv_std, has_norm, A0, gA0n); };
+      auto obs_hook = [&](int s) {
+        if (more)
+          obs_convert_one<kSave>(regs.v[s], s * 32 + (tid >> 4) < rows_n, mean, inv_std, clip2, nclip2, has_norm, A0 + a0_off + s * 512,
+                                 kSave ? gA0n + a0_off + s * 512 : nullptr);
+      };
       epilogue_hidden<4 / kPc, kPc>(tmem + ACC1_COL, bias1, A1, bar_act1, g, q, lane, g1(tile), it >= 1 ? &bar_acc3 : nullptr, ph ^ 1, obs_hook);
       if (st) stamp<kStamp>(a, 8 + 8 * it + 2);
       if (more) {
