@@ -47,8 +47,9 @@ constexpr int W2_OFF = W1_OFF + operand_bytes(D1, D0);
 constexpr int W3_OFF = W2_OFF + operand_bytes(D2, D1);
 constexpr int WH_OFF = W3_OFF + operand_bytes(D3, D2);
 constexpr int BIAS_OFF = WH_OFF + operand_bytes(DH, D3);          // fp32 biases: 256 + 128 + 64 + 16
-constexpr int BLOB_BYTES = BIAS_OFF + (D1 + D2 + D3 + DH) * 4;
-static_assert(BLOB_BYTES % 16 == 0 && W2_OFF % 16 == 0 && W3_OFF % 16 == 0 && WH_OFF % 16 == 0 && BIAS_OFF % 16 == 0, "align");
+constexpr int SBIAS_OFF = BIAS_OFF + (D1 + D2 + D3 + DH) * 4;      // log2(e) x the hidden-layer biases (inference kernel, see kScaled)
+constexpr int BLOB_BYTES = SBIAS_OFF + (D1 + D2 + D3) * 4;
+static_assert(BLOB_BYTES % 16 == 0 && W2_OFF % 16 == 0 && W3_OFF % 16 == 0 && WH_OFF % 16 == 0 && BIAS_OFF % 16 == 0 && SBIAS_OFF % 16 == 0, "align");
 
 // activation regions (bf16 A operands).  A1 [128 x 256] = four 64-column K chunks (slots) that the layer-1 epilogue produces one by
 // one and layer 2 consumes at once.  Slots 2-3 are ALIASED onto A2: A2 is only live from E2(t) until layer 3 of tile t has read
@@ -79,14 +80,21 @@ __device__ __forceinline__ void issue_ksteps(uint32_t tmem_d, uint32_t a_saddr, 
   }
 }
 
-// 16 accumulator columns [c0, c0+16) -> +bias, ELU, bf16 -> eight packed words (two 16-byte K chunks of the next A operand)
+// 16 accumulator columns [c0, c0+16) -> +bias, ELU, bf16 -> eight packed words (two 16-byte K chunks of the next A operand).
+// kScaled (the inference kernel): activations are stored multiplied by log2(e) and `bias` holds log2(e) b (lm_tc.cuh, elu_pair_scaled).
+template <bool kScaled>
 __device__ __forceinline__ void elu16(const uint32_t* acc, const float* __restrict__ bias, int c0, uint32_t (&w)[8]) {
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const float4 b = *reinterpret_cast<const float4*>(bias + c0 + 4 * k);
-    // LM_MLP_FMA_PAIRS of every 4 ELU pairs take their exponential on the FMA pipe instead of MUFU (lm_tc.cuh)
-    w[2 * k] = elu_pair_mix<LM_MLP_FMA_PAIRS>((2 * k) & 3, acc[4 * k], acc[4 * k + 1], b.x, b.y);
-    w[2 * k + 1] = elu_pair_mix<LM_MLP_FMA_PAIRS>((2 * k + 1) & 3, acc[4 * k + 2], acc[4 * k + 3], b.z, b.w);
+    if (kScaled) {
+      w[2 * k] = elu_pair_scaled(acc[4 * k], acc[4 * k + 1], b.x, b.y);
+      w[2 * k + 1] = elu_pair_scaled(acc[4 * k + 2], acc[4 * k + 3], b.z, b.w);
+    } else {
+      // LM_MLP_FMA_PAIRS of every 4 ELU pairs take their exponential on the FMA pipe instead of MUFU (lm_tc.cuh)
+      w[2 * k] = elu_pair_mix<LM_MLP_FMA_PAIRS>((2 * k) & 3, acc[4 * k], acc[4 * k + 1], b.x, b.y);
+      w[2 * k + 1] = elu_pair_mix<LM_MLP_FMA_PAIRS>((2 * k + 1) & 3, acc[4 * k + 2], acc[4 * k + 3], b.z, b.w);
+    }
   }
 }
 // `gdst` (training forward only): the same two chunks into the tile's activation blob in global memory (same layout, same offsets)
@@ -107,7 +115,7 @@ __device__ __forceinline__ void store16(const uint32_t (&w)[8], uint8_t* dst, in
 // `hook(k)` runs once per piece k before the following fence (shared-memory stores made there are published by the same fence).
 // `alias_bar`: waited before the first store into A1 slot 2 (= A2's memory, see above).
 struct NoHook { __device__ __forceinline__ void operator()(int) const {} };
-template <int kMacro, int kPieces, typename Hook = NoHook>
+template <int kMacro, int kPieces, bool kScaled, typename Hook = NoHook>
 __device__ __forceinline__ void epilogue_hidden(uint32_t tmem_acc, const float* __restrict__ bias, uint8_t* dst, uint64_t* bars, int g, int q,
                                                 int lane, uint8_t* gsave = nullptr, uint64_t* alias_bar = nullptr, uint32_t alias_parity = 0,
                                                 Hook hook = Hook()) {
@@ -120,7 +128,7 @@ __device__ __forceinline__ void epilogue_hidden(uint32_t tmem_acc, const float* 
   tmem_ld16(tbase + c0(0), a);
   tmem_wait();
   if (kN > 1) tmem_ld16(tbase + c0(1), b);
-  elu16(a, bias, c0(0), w);
+  elu16<kScaled>(a, bias, c0(0), w);
 #pragma unroll
   for (int k = 0; k < kN; ++k) {
     uint32_t* nxt = (k & 1) ? a : b;          // holds piece k + 1 (in flight or landed)
@@ -135,7 +143,7 @@ __device__ __forceinline__ void epilogue_hidden(uint32_t tmem_acc, const float* 
 #else
       if (k + 2 < kN) tmem_ld16(tbase + c0(k + 2), free_buf);
 #endif
-      elu16(nxt, bias, c0(k + 1), w);
+      elu16<kScaled>(nxt, bias, c0(k + 1), w);
     }
     hook(k);
     if (k % kPieces == kPieces - 1) {
@@ -187,12 +195,15 @@ __device__ __forceinline__ void obs_fetch(const Args& a, int tile, int tid, ObsR
 // taken on the packed bf16 pairs — rounding is monotone, so min(bf16(x), bf16(c)) = bf16(min(x, c)) for any clip c — and `dst` is the
 // thread's precomputed A0 address of the chunk (base + j * 512 bytes), so a piece costs 15 instructions.  kGuard (training forward,
 // whose saved rows feed the weight gradients): rows beyond the batch stay zero.
-template <bool kGuard>
+template <bool kGuard, bool kScaled>
 __device__ __forceinline__ void obs_convert_one(float4 x, bool row_valid, const float4& mean, const float4& inv_std, uint32_t clip2, uint32_t nclip2,
                                                 bool has_norm, uint8_t* dst, uint8_t* gdst) {
+  // kScaled: the caller folded log2(e) into inv_std and the clip bounds; without normalisation the scaling is applied here
   if (has_norm) {
     x.x = (x.x - mean.x) * inv_std.x; x.y = (x.y - mean.y) * inv_std.y;
     x.z = (x.z - mean.z) * inv_std.z; x.w = (x.w - mean.w) * inv_std.w;
+  } else if (kScaled) {
+    x.x *= 1.4426950408889634f; x.y *= 1.4426950408889634f; x.z *= 1.4426950408889634f; x.w *= 1.4426950408889634f;
   }
   uint32_t lo = pack_bf16(x.x, x.y), hi = pack_bf16(x.z, x.w);
   if (has_norm) {
@@ -209,6 +220,7 @@ __device__ __forceinline__ void obs_convert_one(float4 x, bool row_valid, const 
 // Head epilogue, spread over the four column-quarter warps of a lane group: quarter q reads accumulator columns [4q, 4q + 4) —
 // q = 0..2: four policy means -> mu (and, with an action sink, the same chunk into the task's action ring / joint targets),
 // q = 3: column 12 -> value.  Every warp does a quarter of the work instead of one warp per scheduler doing all of it.
+template <bool kScaled>
 __device__ __forceinline__ void epilogue_head(const Args& a, uint32_t tmem_acc, const float* __restrict__ biash, int tile, int g, int lane, int q) {
   uint32_t acc[4];
   tmem_ld4(tmem_acc + ((uint32_t)(g * 32) << 16) + (uint32_t)(4 * q), acc);
@@ -218,7 +230,12 @@ __device__ __forceinline__ void epilogue_head(const Args& a, uint32_t tmem_acc, 
   const int row = g * 32 + lane;
   if (row < rows) {
     const float4 b = *reinterpret_cast<const float4*>(biash + 4 * q);
-    const float4 o = make_float4(__uint_as_float(acc[0]) + b.x, __uint_as_float(acc[1]) + b.y, __uint_as_float(acc[2]) + b.z, __uint_as_float(acc[3]) + b.w);
+    // kScaled: the accumulator holds log2(e) x (W h): one FMA per output undoes the scaling and adds the bias
+    constexpr float kInv = kScaled ? 0.6931471805599453f : 1.0f;
+    const float4 o = kScaled ? make_float4(fmaf(__uint_as_float(acc[0]), kInv, b.x), fmaf(__uint_as_float(acc[1]), kInv, b.y),
+                                           fmaf(__uint_as_float(acc[2]), kInv, b.z), fmaf(__uint_as_float(acc[3]), kInv, b.w))
+                             : make_float4(__uint_as_float(acc[0]) + b.x, __uint_as_float(acc[1]) + b.y, __uint_as_float(acc[2]) + b.z,
+                                           __uint_as_float(acc[3]) + b.w);
     if (q < 3) {
       reinterpret_cast<float4*>(a.mu + (size_t)(row0 + row) * 12)[q] = o;
       if (a.has_sink) sink_store(a.sink, row0 + row, q, o);
@@ -249,10 +266,13 @@ __global__ void __launch_bounds__(kSave ? THREADS : LM_MLP_LAUNCH_BOUND, 1) k_ml
   uint8_t* A2 = smem + A2_OFF;
   uint8_t* A0 = smem + A0_OFF;
   uint8_t* A3 = smem + A3_OFF;
-  const float* bias1 = reinterpret_cast<const float*>(smem + BIAS_OFF);
+  // Inference (kScaled): hidden activations are stored multiplied by log2(e), which removes the multiply in front of every ex2
+  // (elu_pair_scaled); the training forward keeps the plain form, because its saved activations feed the backward kernels.
+  constexpr bool kScaled = !kSave;
+  const float* bias1 = reinterpret_cast<const float*>(smem + (kScaled ? SBIAS_OFF : BIAS_OFF));
   const float* bias2 = bias1 + D1;
   const float* bias3 = bias2 + D2;
-  const float* biash = bias3 + D3;
+  const float* biash = reinterpret_cast<const float*>(smem + BIAS_OFF) + D1 + D2 + D3;
 
   if (tid == 0) {
     mbar_init(&bar_w, 1); mbar_init(&bar_a0, E_WARPS);
@@ -347,11 +367,13 @@ __global__ void __launch_bounds__(kSave ? THREADS : LM_MLP_LAUNCH_BOUND, 1) k_ml
     if (has_norm) {
       mean = *reinterpret_cast<const float4*>(a.norm_mean + 4 * (tid & 15));
       inv_std = *reinterpret_cast<const float4*>(a.norm_inv_std + 4 * (tid & 15));
+      if (kScaled) { inv_std.x *= 1.4426950408889634f; inv_std.y *= 1.4426950408889634f; inv_std.z *= 1.4426950408889634f; inv_std.w *= 1.4426950408889634f; }
     }
     ObsRegs regs;
     // this thread's chunk of A0: row (tid / 16) + 32 j, columns 4 (tid % 16)..: byte offset of j = 0, then 512 bytes per j
     const int a0_off = elem_offset(TM, tid >> 4, 4 * (tid & 15));
-    const uint32_t clip2 = pack_bf16(a.norm_clip, a.norm_clip), nclip2 = pack_bf16(-a.norm_clip, -a.norm_clip);
+    const float osc = kScaled ? 1.4426950408889634f : 1.0f;
+    const uint32_t clip2 = pack_bf16(a.norm_clip * osc, a.norm_clip * osc), nclip2 = pack_bf16(-a.norm_clip * osc, -a.norm_clip * osc);
     pdl_wait();                                            // the observations are the predecessor kernel's output
     // Dependents are released only now, i.e. once the producer of the observations (the post step) has completed: a dependent that
     // needs nothing from THIS kernel (lm_task_set_early_reset: the reset half of the next pre step) may then run beside it.
@@ -360,7 +382,7 @@ __global__ void __launch_bounds__(kSave ? THREADS : LM_MLP_LAUNCH_BOUND, 1) k_ml
       obs_fetch(a, tile0, tid, regs);
 #pragma unroll
       for (int j = 0; j < 4; ++j)
-        obs_convert_one<kSave>(regs.v[j], j * 32 + (tid >> 4) < a.n - tile0 * TM, mean, inv_std, clip2, nclip2, has_norm, A0 + a0_off + j * 512,
+        obs_convert_one<kSave, kScaled>(regs.v[j], j * 32 + (tid >> 4) < a.n - tile0 * TM, mean, inv_std, clip2, nclip2, has_norm, A0 + a0_off + j * 512,
                                kSave ? g0(tile0) + a0_off + j * 512 : nullptr);
       fence_proxy_async();
       __syncwarp();
@@ -385,10 +407,10 @@ __global__ void __launch_bounds__(kSave ? THREADS : LM_MLP_LAUNCH_BOUND, 1) k_ml
       const int rows_n = min(TM, a.n - (tile + stride) * TM);
       auto obs_hook = [&](int s) {
         if (more)
-          obs_convert_one<kSave>(regs.v[s], s * 32 + (tid >> 4) < rows_n, mean, inv_std, clip2, nclip2, has_norm, A0 + a0_off + s * 512,
+          obs_convert_one<kSave, kScaled>(regs.v[s], s * 32 + (tid >> 4) < rows_n, mean, inv_std, clip2, nclip2, has_norm, A0 + a0_off + s * 512,
                                  kSave ? gA0n + a0_off + s * 512 : nullptr);
       };
-      epilogue_hidden<4 / kPc, kPc>(tmem + ACC1_COL, bias1, A1, bar_act1, g, q, lane, g1(tile), it >= 1 ? &bar_acc3 : nullptr, ph ^ 1, obs_hook);
+      epilogue_hidden<4 / kPc, kPc, kScaled>(tmem + ACC1_COL, bias1, A1, bar_act1, g, q, lane, g1(tile), it >= 1 ? &bar_acc3 : nullptr, ph ^ 1, obs_hook);
       if (st) stamp<kStamp>(a, 8 + 8 * it + 2);
       if (more) {
         if (lane == 0) mbar_arrive(&bar_a0);               // behind the last fence of E1
@@ -399,36 +421,36 @@ __global__ void __launch_bounds__(kSave ? THREADS : LM_MLP_LAUNCH_BOUND, 1) k_ml
       if (it >= 2) {
         mbar_wait(&bar_acch, ph);
         tc_fence_after();
-        epilogue_head(a, tmem + ACCH_COL, biash, tile - 2 * stride, g, lane, q);
+        epilogue_head<kScaled>(a, tmem + ACCH_COL, biash, tile - 2 * stride, g, lane, q);
       }
       // ---- E3(t-1): TMEM[128 x 64] -> A3
       if (st) stamp<kStamp>(a, 8 + 8 * it + 4);
       if (it >= 1) {
         mbar_wait(&bar_acc3, ph ^ 1);
         tc_fence_after();
-        epilogue_hidden<1, 1>(tmem + ACC3_COL, bias3, A3, bar_act3, g, q, lane, g3(tile - stride));
+        epilogue_hidden<1, 1, kScaled>(tmem + ACC3_COL, bias3, A3, bar_act3, g, q, lane, g3(tile - stride));
       }
       // ---- E2(t): TMEM[128 x 128] -> A2 (layer 3 of tile t-1 has finished reading it: bar_acc3 above)
       if (st) stamp<kStamp>(a, 8 + 8 * it + 5);
       mbar_wait(&bar_acc2, ph);
       tc_fence_after();
       if (st) stamp<kStamp>(a, 8 + 8 * it + 6);
-      epilogue_hidden<2 / kPc, kPc>(tmem + ACC2_COL, bias2, A2, bar_act2, g, q, lane, g2(tile));
+      epilogue_hidden<2 / kPc, kPc, kScaled>(tmem + ACC2_COL, bias2, A2, bar_act2, g, q, lane, g2(tile));
       if (st) stamp<kStamp>(a, 8 + 8 * it + 7);
     }
     // ---- drain: heads(n-2), E3(n-1), heads(n-1)
     if (n_loc >= 2) {
       mbar_wait(&bar_acch, n_loc & 1);
       tc_fence_after();
-      epilogue_head(a, tmem + ACCH_COL, biash, tile0 + (n_loc - 2) * stride, g, lane, q);
+      epilogue_head<kScaled>(a, tmem + ACCH_COL, biash, tile0 + (n_loc - 2) * stride, g, lane, q);
     }
     if (n_loc >= 1) {
       mbar_wait(&bar_acc3, (n_loc - 1) & 1);
       tc_fence_after();
-      epilogue_hidden<1, 1>(tmem + ACC3_COL, bias3, A3, bar_act3, g, q, lane, g3(tile0 + (n_loc - 1) * stride));
+      epilogue_hidden<1, 1, kScaled>(tmem + ACC3_COL, bias3, A3, bar_act3, g, q, lane, g3(tile0 + (n_loc - 1) * stride));
       mbar_wait(&bar_acch, (n_loc - 1) & 1);
       tc_fence_after();
-      epilogue_head(a, tmem + ACCH_COL, biash, tile0 + (n_loc - 1) * stride, g, lane, q);
+      epilogue_head<kScaled>(a, tmem + ACCH_COL, biash, tile0 + (n_loc - 1) * stride, g, lane, q);
     }
   }
   tc_fence_before();
@@ -445,6 +467,7 @@ struct PackArgs {
   uint8_t* blob;
 };
 constexpr int PK_W1 = D1 * D0, PK_W2 = PK_W1 + D2 * D1, PK_W3 = PK_W2 + D3 * D2, PK_WH = PK_W3 + DH * D3, PK_ALL = PK_WH + D1 + D2 + D3 + DH;
+constexpr float kLog2e = 1.4426950408889634f;
 __device__ __forceinline__ void pack_elem(const float* __restrict__ w, uint8_t* dst, int rows_total, int k, int i) {
   const int row = i / k, col = i - row * k;
   *reinterpret_cast<__nv_bfloat16*>(dst + elem_offset(rows_total, row, col)) = __float2bfloat16_rn(w[i]);
@@ -461,9 +484,10 @@ __global__ void k_pack_all(const PackArgs a) {
   } else if (i < PK_ALL) {
     const int j = i - PK_WH;
     float* dst = reinterpret_cast<float*>(a.blob + BIAS_OFF);
-    if (j < D1) dst[j] = a.b1[j];
-    else if (j < D1 + D2) dst[j] = a.b2[j - D1];
-    else if (j < D1 + D2 + D3) dst[j] = a.b3[j - D1 - D2];
+    float* sdst = reinterpret_cast<float*>(a.blob + SBIAS_OFF);
+    if (j < D1) { dst[j] = a.b1[j]; sdst[j] = a.b1[j] * kLog2e; }
+    else if (j < D1 + D2) { dst[j] = a.b2[j - D1]; sdst[j] = a.b2[j - D1] * kLog2e; }
+    else if (j < D1 + D2 + D3) { dst[j] = a.b3[j - D1 - D2]; sdst[j] = a.b3[j - D1 - D2] * kLog2e; }
     else if (j < D1 + D2 + D3 + 12) dst[j] = a.b_mu[j - D1 - D2 - D3];
     else dst[j] = j == D1 + D2 + D3 + 12 ? a.b_value[0] : 0.0f;
   }

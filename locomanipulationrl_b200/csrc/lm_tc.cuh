@@ -145,6 +145,22 @@ __device__ __forceinline__ uint32_t elu_pair_relu(uint32_t acc_lo, uint32_t acc_
   asm("min.bf16x2 %0, %1, %2;" : "=r"(out) : "r"(pos), "r"(neg));
   return out;
 }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c);
+// The pair in 7 instructions, for activations stored SCALED by s = log2(e): with h'' = s h as the A operand, the accumulator of the
+// unscaled weights is s (W h), so t = acc + s b IS the ex2 argument (no multiply), and the scaled output is
+// s ELU(t / s) = min(s 2^t - s, relu(t)): FADD2, 2 MUFU, FFMA2, 2 F2FP (one with relu), HMNMX2.
+__device__ __forceinline__ uint32_t elu_pair_scaled(uint32_t acc_lo, uint32_t acc_hi, float sb_lo, float sb_hi) {
+  constexpr float kS = 1.4426950408889634f;
+  const uint64_t t2 = add2(pk2u(acc_lo, acc_hi), pk2(sb_lo, sb_hi));
+  float t0, t1, r0, r1;
+  upk2(t2, t0, t1);
+  upk2(fma2(pk2(ex2_approx(t0), ex2_approx(t1)), pk2(kS, kS), pk2(-kS, -kS)), r0, r1);
+  uint32_t pos, neg, out;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(pos) : "f"(t1), "f"(t0));
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(neg) : "f"(r1), "f"(r0));
+  asm("min.bf16x2 %0, %1, %2;" : "=r"(out) : "r"(pos), "r"(neg));
+  return out;
+}
 __device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) { uint64_t r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
 
 // The same ELU pair with exp on the FMA pipe instead of MUFU (the epilogues are MUFU-bound: 16 ex2/clk/SM, so a share of

@@ -41,6 +41,33 @@ def test_mlp_forward_matches_fp32_reference(n):
     assert_close("value vs bf16 emulation", value, v_e, rtol=0, atol=2e-3)
 
 
+@pytest.mark.parametrize("n", [100, 16384, 65536 + 37])
+def test_mlp_inference_kernel_matches_fp32_reference_and_its_bf16_emulation(n):
+    """The inference instantiation (torch.no_grad: hidden activations stored as bf16(log2(e) h), biases pre-scaled, heads un-scaled in
+    their epilogue): logits within 1e-2 of stock fp32 torch, within 2e-3 of an emulation that rounds to bf16 exactly where the kernel
+    does, and within 4e-3 of the training forward (same weights, the plain formulation)."""
+    m = _mlp()
+    g = torch.Generator().manual_seed(7 * n + 1)
+    obs = (torch.randn(n, 64, generator=g) * 1.5).clamp(-5, 5).cuda()
+    s = 1.4426950408889634
+    with torch.no_grad():
+        mu, value, _ = m(obs)
+        mu_ref, value_ref, _ = m.reference_forward(obs)
+        h = (obs * s).bfloat16().float()
+        for i in (0, 2, 4):
+            t = h @ m.net[i].weight.bfloat16().float().t() + s * m.net[i].bias
+            h = (s * torch.nn.functional.elu(t / s)).bfloat16().float()
+        mu_e = (h @ m.mean_layer.weight.bfloat16().float().t()) / s + m.mean_layer.bias
+        v_e = (h @ m.value_layer.weight.bfloat16().float().t()) / s + m.value_layer.bias
+    mu_t, value_t, _ = m(obs)                       # grad enabled: the training forward
+    assert_close("mu", mu, mu_ref, rtol=0, atol=1e-2)
+    assert_close("value", value, value_ref, rtol=0, atol=1e-2)
+    assert_close("mu vs scaled bf16 emulation", mu, mu_e, rtol=0, atol=2e-3)
+    assert_close("value vs scaled bf16 emulation", value, v_e, rtol=0, atol=2e-3)
+    assert_close("mu inference vs training forward", mu, mu_t.detach(), rtol=0, atol=4e-3)
+    assert_close("value inference vs training forward", value, value_t.detach(), rtol=0, atol=4e-3)
+
+
 def test_mlp_normalisation_and_repack():
     m = _mlp(1)
     obs = torch.randn(4096, 64, device="cuda") * 3 + 0.5
