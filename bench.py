@@ -194,6 +194,13 @@ def bind_host_cores(local_rank, world):
     boxes an unbound single rank measured 0.92 ms per host-buffer step against 0.67-0.74 for the bound ranks of a 2-rank run)."""
     if not hasattr(os, "sched_setaffinity"):
         return
+    if os.environ.get("LM_BENCH_CORES"):              # experiment override, e.g. "0-7" or "4,5,6"
+        cs = []
+        for part in os.environ["LM_BENCH_CORES"].split(","):
+            lo, _, hi = part.partition("-")
+            cs += list(range(int(lo), int(hi or lo) + 1))
+        os.sched_setaffinity(0, cs)
+        return
     try:
         cores = sorted(os.sched_getaffinity(0))
         node_cores = None
@@ -387,6 +394,10 @@ def cuda_arm(args):
         raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback (use --impl reference for the CPU baseline)")
     device = torch.device(f"cuda:{local_rank}")
     torch.cuda.set_device(device)
+    # The CUDA arm needs no CPU parallelism, and an OpenMP pool left spinning behind the synthetic-state generation steals the cores
+    # the launch thread and the driver's copy threads run on: measured 0.72 -> 0.66 ms per host-buffer step on a 24-core box (what
+    # torchrun's OMP_NUM_THREADS=1 did for the multi-rank runs).  The CPU baseline sets its own thread count (run_cpu_port).
+    torch.set_num_threads(1)
     bind_host_cores(local_rank, world)
     pipe = Pipeline(args.workload, device, rank)
     n = pipe.n
