@@ -123,10 +123,22 @@ __device__ __forceinline__ void load_bias8(const float* p, float b[8]) {
 #ifndef LM_GNN_FMA_PAIRS   // of the 4 ELU pairs of a chunk, how many take the FMA-pipe exp (tuned on B200)
 #define LM_GNN_FMA_PAIRS 1
 #endif
+// Node features and edge activations are stored SCALED by log2(e) (LM_GNN_SCALED, default; lm_tc.cuh elu_pair_scaled): the tensor-core
+// blob carries log2(e) x the input-layer weights / biases and log2(e) x the graph-layer biases, the graph-layer weights are plain, so
+// every accumulator + bias is the ex2 argument itself (7 instead of 8 instructions per ELU pair); the fp32 last layer un-scales.
+#ifndef LM_GNN_SCALED
+#define LM_GNN_SCALED 1
+#endif
+constexpr float kActScale = LM_GNN_SCALED ? 1.4426950408889634f : 1.0f;
 __device__ __forceinline__ uint4 elu_chunk(const uint32_t r[8], const float b[8]) {
   constexpr int F = LM_GNN_FMA_PAIRS;
+#if LM_GNN_SCALED
+  return make_uint4(elu_pair_mix_scaled<F>(0, r[0], r[1], b[0], b[1]), elu_pair_mix_scaled<F>(1, r[2], r[3], b[2], b[3]),
+                    elu_pair_mix_scaled<F>(2, r[4], r[5], b[4], b[5]), elu_pair_mix_scaled<F>(3, r[6], r[7], b[6], b[7]));
+#else
   return make_uint4(elu_pair_mix<F>(0, r[0], r[1], b[0], b[1]), elu_pair_mix<F>(1, r[2], r[3], b[2], b[3]),
                     elu_pair_mix<F>(2, r[4], r[5], b[4], b[5]), elu_pair_mix<F>(3, r[6], r[7], b[6], b[7]));
+#endif
 }
 __device__ __forceinline__ uint4 pack_chunk(const float v[8]) {
   return make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
@@ -138,7 +150,7 @@ __device__ __forceinline__ void max8(uint32_t a[8], const uint32_t b[8]) {
 // fp32 ELU of 8 channels (last layer: the heads read fp32, not the bf16 operand)
 __device__ __forceinline__ void elu8(const uint32_t r[8], const float b[8], float v[8]) {
 #pragma unroll
-  for (int c = 0; c < 8; ++c) v[c] = elu(__uint_as_float(r[c]) + b[c]);
+  for (int c = 0; c < 8; ++c) v[c] = elu((__uint_as_float(r[c]) + b[c]) * (1.0f / kActScale));   // accumulator and bias carry the activation scale
 }
 
 // E1 of one leg: stage-1 accumulators (6 slots) -> z operands.  taddr = this thread's lane group / column quarter in slot 0 of the set.
@@ -460,15 +472,15 @@ __global__ void k_pack_w(const float* __restrict__ w, uint8_t* __restrict__ dst,
   *reinterpret_cast<__nv_bfloat16*>(dst + elem_offset(H, r, k)) = __float2bfloat16_rn(w[(size_t)r * ld + col0 + k]);
 }
 // nn.Linear W [32, K] -> W^T [K][32] fp32
-__global__ void k_pack_wt(const float* __restrict__ w, float* __restrict__ dst, int K) {
+__global__ void k_pack_wt(const float* __restrict__ w, float* __restrict__ dst, int K, float scale) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= H * K) return;
   const int c = i / K, k = i - c * K;
-  dst[k * H + c] = w[i];
+  dst[k * H + c] = w[i] * scale;
 }
-__global__ void k_copy(const float* __restrict__ src, float* __restrict__ dst, int n) {
+__global__ void k_copy(const float* __restrict__ src, float* __restrict__ dst, int n, float scale) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) dst[i] = src[i];
+  if (i < n) dst[i] = src[i] * scale;
 }
 
 }  // namespace gnn_tc
@@ -495,21 +507,22 @@ int lm_gnn_tc_pack(LmGnn* g, const float* const* w, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   uint8_t* B = g->tc_blob;
   float* Fp = reinterpret_cast<float*>(B + F_OFF);
-  k_pack_wt<<<(H * 16 + 127) / 128, 128, 0, s>>>(w[0], Fp + F_WIN1, 16);
-  k_copy<<<1, 32, 0, s>>>(w[1], Fp + F_BIN1, H);
-  k_pack_wt<<<1, 128, 0, s>>>(w[2], Fp + F_WIN2, 4);
-  k_copy<<<1, 32, 0, s>>>(w[3], Fp + F_BIN2, H);
+  const float sc = kActScale;      // activations (and therefore these fp32 parameters) carry the activation scale, see elu_chunk
+  k_pack_wt<<<(H * 16 + 127) / 128, 128, 0, s>>>(w[0], Fp + F_WIN1, 16, sc);
+  k_copy<<<1, 32, 0, s>>>(w[1], Fp + F_BIN1, H, sc);
+  k_pack_wt<<<1, 128, 0, s>>>(w[2], Fp + F_WIN2, 4, sc);
+  k_copy<<<1, 32, 0, s>>>(w[3], Fp + F_BIN2, H, sc);
   for (int l = 0; l < 3; ++l) {
     k_pack_w<<<(H * H + 127) / 128, 128, 0, s>>>(w[4 + 4 * l], B + WL_OFF + (3 * l + 0) * WB, 2 * H, 0);   // W1a: columns of h_i (target)
     k_pack_w<<<(H * H + 127) / 128, 128, 0, s>>>(w[4 + 4 * l], B + WL_OFF + (3 * l + 1) * WB, 2 * H, H);   // W1b: columns of h_j (source)
-    k_copy<<<1, 32, 0, s>>>(w[5 + 4 * l], Fp + F_BL + l * 2 * H, H);
+    k_copy<<<1, 32, 0, s>>>(w[5 + 4 * l], Fp + F_BL + l * 2 * H, H, sc);
     k_pack_w<<<(H * H + 127) / 128, 128, 0, s>>>(w[6 + 4 * l], B + WL_OFF + (3 * l + 2) * WB, H, 0);
-    k_copy<<<1, 32, 0, s>>>(w[7 + 4 * l], Fp + F_BL + l * 2 * H + H, H);
+    k_copy<<<1, 32, 0, s>>>(w[7 + 4 * l], Fp + F_BL + l * 2 * H + H, H, sc);
   }
-  k_copy<<<1, 32, 0, s>>>(w[16], Fp + F_WACT, H);
-  k_copy<<<1, 32, 0, s>>>(w[17], Fp + F_BHEAD, 1);
-  k_copy<<<1, 32, 0, s>>>(w[18], Fp + F_WVAL, H);
-  k_copy<<<1, 32, 0, s>>>(w[19], Fp + F_BHEAD + 1, 1);
+  k_copy<<<1, 32, 0, s>>>(w[16], Fp + F_WACT, H, 1.0f);
+  k_copy<<<1, 32, 0, s>>>(w[17], Fp + F_BHEAD, 1, 1.0f);
+  k_copy<<<1, 32, 0, s>>>(w[18], Fp + F_WVAL, H, 1.0f);
+  k_copy<<<1, 32, 0, s>>>(w[19], Fp + F_BHEAD + 1, 1, 1.0f);
   g->tc_fresh_pack = true;
   return lm_check_launch("lm_gnn_pack (tensor-core blob)");
 }

@@ -189,6 +189,32 @@ __device__ __forceinline__ uint32_t elu_pair_fma(uint32_t acc_lo, uint32_t acc_h
   upk2(add2(pk2(e0, e1), pk2(-1.0f, -1.0f)), y0, y1);
   return pack_bf16(fmaxf(x0, y0), fmaxf(x1, y1));
 }
+// elu_pair_fma for activations stored scaled by log2(e) (see elu_pair_scaled): t = acc + s b is the exponent itself
+__device__ __forceinline__ uint32_t elu_pair_fma_scaled(uint32_t acc_lo, uint32_t acc_hi, float sb_lo, float sb_hi) {
+  constexpr float kMagic = 12582912.0f - 64.0f, kS = 1.4426950408889634f;
+  const uint64_t t2 = add2(pk2u(acc_lo, acc_hi), pk2(sb_lo, sb_hi));
+  float t0, t1;
+  upk2(t2, t0, t1);
+  const uint64_t s2 = pk2(__saturatef(fmaf(t0, 1.0f / 64.0f, 1.0f)), __saturatef(fmaf(t1, 1.0f / 64.0f, 1.0f)));
+  const uint64_t k64 = pk2(64.0f, 64.0f);
+  const uint64_t r2 = fma2(s2, k64, pk2(kMagic, kMagic));
+  const uint64_t f2 = fma2(s2, k64, fma2(r2, pk2(-1.0f, -1.0f), pk2(kMagic, kMagic)));     // 64 s - n
+  uint64_t p2 = fma2(f2, pk2(0.05500871f, 0.05500871f), pk2(0.24221068f, 0.24221068f));
+  p2 = fma2(p2, f2, pk2(0.69328292f, 0.69328292f));
+  p2 = fma2(p2, f2, pk2(1.0f, 1.0f));
+  float r0, r1, p0, p1;
+  upk2(r2, r0, r1);
+  upk2(p2, p0, p1);
+  const float e0 = __uint_as_float((__float_as_uint(r0) << 23) + __float_as_uint(p0));
+  const float e1 = __uint_as_float((__float_as_uint(r1) << 23) + __float_as_uint(p1));
+  float y0, y1;
+  upk2(fma2(pk2(e0, e1), pk2(kS, kS), pk2(-kS, -kS)), y0, y1);
+  return pack_bf16(fmaxf(t0, y0), fmaxf(t1, y1));
+}
+template <int kFma>
+__device__ __forceinline__ uint32_t elu_pair_mix_scaled(int i, uint32_t acc_lo, uint32_t acc_hi, float sb_lo, float sb_hi) {
+  return i < kFma ? elu_pair_fma_scaled(acc_lo, acc_hi, sb_lo, sb_hi) : elu_pair_scaled(acc_lo, acc_hi, sb_lo, sb_hi);
+}
 // pair `i` of a group of four: the first kFma pairs go to the FMA pipe
 template <int kFma>
 __device__ __forceinline__ uint32_t elu_pair_mix(int i, uint32_t acc_lo, uint32_t acc_hi, float b_lo, float b_hi) {
