@@ -689,7 +689,7 @@ def cuda_arm(args):
                                     + f", {args.comm_stream} stream, CUDA graph") if world > 1 else "none",
                            "timed": f"{reps} rollout horizons of {horizon} steps"},
                 "gpu_launches": pipe.launches_per_step * steps_timed + (steps_timed // HORIZON if pipe.w["policy"] == "gnn" else 0)
-                                + (collectives if peer is not None else 0), "clocks": clocks, "e2e": e2e, "cpu_baseline": cpu, "train": train}
+                                + (collectives if peer is not None else 0) + (reps if pipe.defer_finish else 0), "clocks": clocks, "e2e": e2e, "cpu_baseline": cpu, "train": train}
         line.update(line_extra)
         emit(line)
     if world > 1:
