@@ -220,7 +220,8 @@ typedef struct LmActionSink {
 int lm_task_set_defer_finish(LmTask* task, int on);
 /* Early reset (opt-in pipelining, needs an action sink): lm_task_pre_step(actions == NULL) then runs BESIDE the kernel launched
  * before it on the stream (programmatic dependent launch; it completes after that kernel).  That kernel must not touch what the
- * reset half reads / writes and must trigger its dependents only after its own dependency wait (lm_mlp_forward_sink qualifies). */
+ * reset half reads / writes and must trigger its dependents only after its own dependency wait (lm_mlp_forward_sink qualifies;
+ * lm_rollout_write does NOT: it reads reset_buf as the step's dones, which the reset half clears). */
 int lm_task_set_early_reset(LmTask* task, int on);
 int lm_task_post_finish(LmTask* task, const LmTaskBuffers* buf, void* stream);
 int lm_task_set_step_parity(LmTask* task, int parity);   /* after replaying a captured step: the ring slot (lm_task_step_parity at capture) it used */
