@@ -277,8 +277,10 @@ __device__ __forceinline__ long long globaltimer_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
+// (compiled into the kStamp instantiation of k_post_lean only, which is launched while a timeline buffer is registered)
+template <bool kStamp>
 __device__ __forceinline__ void stamp(const PostArgs& a, int k) {
-  if (a.timeline != nullptr && threadIdx.x == 0) a.timeline[(size_t)blockIdx.x * 8 + k] = globaltimer_ns();
+  if (kStamp && a.timeline != nullptr && threadIdx.x == 0) a.timeline[(size_t)blockIdx.x * 8 + k] = globaltimer_ns();
 }
 __device__ __forceinline__ void stamp_at(const PostArgs& a, int k) {   // caller picks the thread
   if (a.timeline != nullptr) a.timeline[(size_t)blockIdx.x * 8 + k] = globaltimer_ns();
@@ -1033,6 +1035,7 @@ struct ObsToStage {
   }
 };
 
+template <bool kStamp>
 __global__ void __launch_bounds__(T, 4) k_post_lean(const KernelParams kp, const PostArgs a) {
   extern __shared__ __align__(128) float sm[];
   __shared__ uint64_t bar;
@@ -1047,7 +1050,7 @@ __global__ void __launch_bounds__(T, 4) k_post_lean(const KernelParams kp, const
   const int n = tl.n, h0 = tl.hr0, e0 = tl.e0;
 
   pdl_launch_dependents();
-  stamp(a, 0);
+  stamp<kStamp>(a, 0);
   if (r == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
   __syncthreads();
   pdl_wait();
@@ -1082,9 +1085,9 @@ __global__ void __launch_bounds__(T, 4) k_post_lean(const KernelParams kp, const
     ld12(ring_last + (size_t)e * 12, last);
     ld12(a.buf.last_joint_vel + (size_t)e * 12, last_jv);
   }
-  stamp(a, 1);
+  stamp<kStamp>(a, 1);
   if (st.use_tma) mbar_wait(&bar, 0); else __syncthreads();
-  stamp(a, 2);
+  stamp<kStamp>(a, 2);
   if (kp.d.dof_identity) {
     ld12(sm + LeanSmem::kDofPos + rr * 20, jp);
     ld12(sm + LeanSmem::kDofVel + rr * 20, jv);
@@ -1137,9 +1140,9 @@ __global__ void __launch_bounds__(T, 4) k_post_lean(const KernelParams kp, const
       if (row < rows_here) obs_g[row * 16 + c] = v;
     }
   }
-  stamp(a, 3);
+  stamp<kStamp>(a, 3);
   finish_join<T>(kp, a, fs);
-  stamp(a, 4);
+  stamp<kStamp>(a, 4);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1458,7 +1461,8 @@ LmTask* lm_task_create(const LmTaskParams* params, int device) {
   if (!ok) { lm_set_error("lm_task_create: cudaMalloc failed"); lm_task_destroy(t); return nullptr; }
   cudaMemset(t->tickets, 0, sizeof(unsigned int) * 4);
   cudaMemset(t->scan_base, 0, sizeof(int32_t) * FINISH_THREADS);
-  err = cudaFuncSetAttribute(k_post_lean, cudaFuncAttributeMaxDynamicSharedMemorySize, LeanSmem::kBytes);
+  err = cudaFuncSetAttribute(k_post_lean<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LeanSmem::kBytes);
+  if (err == cudaSuccess) err = cudaFuncSetAttribute(k_post_lean<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LeanSmem::kBytes);
   if (err == cudaSuccess) err = cudaFuncSetAttribute(k_post, cudaFuncAttributeMaxDynamicSharedMemorySize, PostSmem::kBytes);
   if (err != cudaSuccess) { lm_set_error("cudaFuncSetAttribute(k_post): %s", cudaGetErrorString(err)); lm_task_destroy(t); return nullptr; }
   return t;
@@ -1646,7 +1650,9 @@ int lm_task_post_step(LmTask* t, const LmRobotViews* loco, const LmRobotViews* m
     k_post<<<t->kp.d.num_tiles, T, PostSmem::kBytes, (cudaStream_t)stream>>>(t->kp, a);
   else
   {
-    cudaError_t le = lm_launch(k_post_lean, dim3(t->kp.d.num_tiles), dim3(T), LeanSmem::kBytes, (cudaStream_t)stream, true, t->kp, a);
+    cudaError_t le = a.timeline != nullptr
+                         ? lm_launch(k_post_lean<true>, dim3(t->kp.d.num_tiles), dim3(T), LeanSmem::kBytes, (cudaStream_t)stream, true, t->kp, a)
+                         : lm_launch(k_post_lean<false>, dim3(t->kp.d.num_tiles), dim3(T), LeanSmem::kBytes, (cudaStream_t)stream, true, t->kp, a);
     if (le != cudaSuccess) return lm_fail((int)le, "lm_task_post_step: %s", cudaGetErrorString(le));
   }
   if (!t->inline_finish && !t->defer_finish) k_post_finish<<<1, FINISH_THREADS, 0, (cudaStream_t)stream>>>(t->kp, a);
