@@ -327,7 +327,21 @@ __global__ void __launch_bounds__(THREADS, 1) k_rms_update(const float* __restri
     for (int k = 0; k < 4; ++k) shift[k] = (float)st.mean[4 * quad + k];
     const size_t rows_per_pass = gstride / q;       // threads [0, rows_per_pass * q) are active
     if (gtid < rows_per_pass * q) {
-      for (size_t row = gtid / q; row < (size_t)n; row += rows_per_pass) {
+      // four rows (128-bit loads) in flight per thread, accumulated in row order (the sums are those of the one-load loop, bit for
+      // bit; with one load in flight the kernel ran at 0.27 of the HBM rate: 57.7 us per 393,216 x 64 minibatch)
+      size_t row = gtid / q;
+      for (; row + 3 * rows_per_pass < (size_t)n; row += 4 * rows_per_pass) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = ld_nc_f4(x + ((row + u * rows_per_pass) * q + quad) * 4);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float d[4] = {v[u].x - shift[0], v[u].y - shift[1], v[u].z - shift[2], v[u].w - shift[3]};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) { s1[k] += d[k]; s2[k] = fmaf(d[k], d[k], s2[k]); }
+        }
+      }
+      for (; row < (size_t)n; row += rows_per_pass) {
         const float4 v = ld_nc_f4(x + (row * q + quad) * 4);
         const float d[4] = {v.x - shift[0], v.y - shift[1], v.z - shift[2], v.w - shift[3]};
 #pragma unroll
