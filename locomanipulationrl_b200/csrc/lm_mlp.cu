@@ -88,8 +88,8 @@ __device__ __forceinline__ void elu16(const uint32_t* acc, const float* __restri
   for (int k = 0; k < 4; ++k) {
     const float4 b = *reinterpret_cast<const float4*>(bias + c0 + 4 * k);
     if (kScaled) {
-      w[2 * k] = elu_pair_scaled(acc[4 * k], acc[4 * k + 1], b.x, b.y);
-      w[2 * k + 1] = elu_pair_scaled(acc[4 * k + 2], acc[4 * k + 3], b.z, b.w);
+      w[2 * k] = elu_pair_mix_scaled<LM_MLP_FMA_PAIRS>((2 * k) & 3, acc[4 * k], acc[4 * k + 1], b.x, b.y);
+      w[2 * k + 1] = elu_pair_mix_scaled<LM_MLP_FMA_PAIRS>((2 * k + 1) & 3, acc[4 * k + 2], acc[4 * k + 3], b.z, b.w);
     } else {
       // LM_MLP_FMA_PAIRS of every 4 ELU pairs take their exponential on the FMA pipe instead of MUFU (lm_tc.cuh)
       w[2 * k] = elu_pair_mix<LM_MLP_FMA_PAIRS>((2 * k) & 3, acc[4 * k], acc[4 * k + 1], b.x, b.y);
