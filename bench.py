@@ -820,9 +820,13 @@ def e2e_arm(pipe, args, world, device, rank=0, readback_obs=False, shards=None):
     n = pipe.n
     mlp = pipe.w["policy"] == "mlp"
     shards = shards or args.e2e_shards
+    sizes = None
+    if os.environ.get("LM_BENCH_E2E_SPLIT") and shards == 2:          # e.g. "0.75": the first shard's share of the envs (multiples of 256)
+        first = int(round(n * float(os.environ["LM_BENCH_E2E_SPLIT"]) / 256.0)) * 256
+        sizes = [first, n - first]
     stepper = ShardedHostStepper(pipe.cfg, n, pipe.policy, shards=shards, device=device, seed=1000 * rank + 42,
                                  env_id_offset=rank * n, norm_mean=pipe.norm_mean if mlp else None,
-                                 norm_inv_std=pipe.norm_inv_std if mlp else None, readback_obs=readback_obs)
+                                 norm_inv_std=pipe.norm_inv_std if mlp else None, readback_obs=readback_obs, shard_sizes=sizes)
     sets = []                                     # STATE_SETS x shards pinned host states (> L2, and never the same twice in a row)
     for i in range(STATE_SETS):
         sets.append([s.scene.pack_host(s.scene.generate(i)) for s in stepper.shards])

@@ -58,15 +58,23 @@ class _Shard:
 class ShardedHostStepper:
     def __init__(self, cfg: TaskConfig, num_envs: int, policy, shards: int = 4, device="cuda:0", seed: int = 42,
                  env_id_offset: int = 0, norm_mean: Optional[torch.Tensor] = None, norm_inv_std: Optional[torch.Tensor] = None,
-                 readback_obs: bool = True, copy_stream: bool = True):
-        if num_envs % shards or (num_envs // shards) % 2:
-            raise _lib.LmError("num_envs must split into an even number of envs per shard")
+                 readback_obs: bool = True, copy_stream: bool = True, shard_sizes: Optional[List[int]] = None):
+        """``shard_sizes``: unequal shards (each an even number of envs, summing to ``num_envs``).  The step ends with the LAST shard's
+        kernels and read-back, which nothing overlaps: a small last shard shortens that tail."""
+        if shard_sizes is None:
+            if num_envs % shards or (num_envs // shards) % 2:
+                raise _lib.LmError("num_envs must split into an even number of envs per shard")
+            shard_sizes = [num_envs // shards] * shards
+        if sum(shard_sizes) != num_envs or any(s <= 0 or s % 2 for s in shard_sizes):
+            raise _lib.LmError("shard_sizes must be positive even numbers summing to num_envs")
+        shards = len(shard_sizes)
         self.lib = _lib.load()
         self.cfg, self.policy, self.device = cfg, policy, torch.device(device)
         self.norm_mean, self.norm_inv_std = norm_mean, norm_inv_std
-        n = num_envs // shards
         self.readback_obs = bool(readback_obs)
-        self.shards: List[_Shard] = [_Shard(cfg, n, self.device, seed + 17 * k, env_id_offset + k * n, self.readback_obs) for k in range(shards)]
+        offs = [sum(shard_sizes[:k]) for k in range(shards)]
+        self.shards: List[_Shard] = [_Shard(cfg, shard_sizes[k], self.device, seed + 17 * k, env_id_offset + offs[k], self.readback_obs)
+                                     for k in range(shards)]
         self.parity = 0
         # one copy stream for every shard's physics state (see the module docstring); a single shard needs none
         self.h2d_stream = torch.cuda.Stream(device=self.device) if (copy_stream and shards > 1) else None
