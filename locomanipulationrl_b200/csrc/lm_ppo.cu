@@ -155,12 +155,12 @@ __global__ void __launch_bounds__(ADAM_THREADS) k_adam_step(float* __restrict__ 
   __shared__ float s_coef, s_lr;
   const int tid = threadIdx.x;
   double ss = 0.0;
-  for (int i0 = tid; i0 < n; i0 += 8 * ADAM_THREADS) {          // 8 independent loads in flight per thread
-    float gv[8];
+  for (int i0 = tid; i0 < n; i0 += 16 * ADAM_THREADS) {         // 16 independent loads in flight per thread (one CTA: latency-bound)
+    float gv[16];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) { const int i = i0 + u * ADAM_THREADS; gv[u] = i < n ? g[i] * grad_scale : 0.0f; }
+    for (int u = 0; u < 16; ++u) { const int i = i0 + u * ADAM_THREADS; gv[u] = i < n ? g[i] * grad_scale : 0.0f; }
 #pragma unroll
-    for (int u = 0; u < 8; ++u) ss += (double)gv[u] * (double)gv[u];
+    for (int u = 0; u < 16; ++u) ss += (double)gv[u] * (double)gv[u];
   }
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
@@ -191,15 +191,15 @@ __global__ void __launch_bounds__(ADAM_THREADS) k_adam_step(float* __restrict__ 
   __syncthreads();
   const float coef = s_coef * grad_scale;
   const float step_size = s_lr / bc1;
-  for (int i0 = tid; i0 < n; i0 += 4 * ADAM_THREADS) {          // 16 independent loads in flight per thread
-    float gv[4], pv[4], mv[4], vv[4];
+  for (int i0 = tid; i0 < n; i0 += 8 * ADAM_THREADS) {          // 32 independent loads in flight per thread
+    float gv[8], pv[8], mv[8], vv[8];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < 8; ++u) {
       const int i = i0 + u * ADAM_THREADS;
       if (i < n) { gv[u] = g[i]; pv[u] = p[i]; mv[u] = m[i]; vv[u] = v[i]; }
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < 8; ++u) {
       const int i = i0 + u * ADAM_THREADS;
       if (i >= n) continue;
       float gi = gv[u] * coef;
