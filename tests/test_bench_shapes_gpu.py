@@ -410,3 +410,50 @@ def test_bench_whole_rotation_graph_equals_per_step_graphs():
             for grp in ("loco", "mani"):
                 for k, v in getattr(a.scenes[i], grp).items():
                     assert torch.equal(getattr(b.scenes[i], grp)[k], v), f"rotation {rot}: scene[{i}].{grp}.{k}"
+
+
+@pytest.mark.parametrize("n", [258, 4096, 20000, 80000])
+def test_early_reset_equals_late_reset(n):
+    """lm_task_set_early_reset (+ deferred finish): the reset half of pre_physics_step as k_pre_early — at most one CTA per SM, up to
+    four tiles per pass (80,000 envs = 626 tiles: two passes; 20,000: 158 tiles on 148 CTAs; 258: ragged two-tile halves) — released
+    beside the policy kernel, against the same loop with the reset half behind it.  Every task buffer and the scene rows bit-identical
+    after every step."""
+    from locomanipulationrl_b200.policy.mlp import MlpActorCritic
+    from locomanipulationrl_b200.tasks.base import LocoManipulationTask
+    cfg = configs.get_task_config("JointLocomanipulationVertical")
+    torch.manual_seed(5)
+    policy = MlpActorCritic(device="cuda:0")
+    with torch.no_grad():
+        policy.mean_layer.weight.mul_(20.0)
+    tasks, scenes, outs = [], [], []
+    for early in (False, True):
+        sc = synthetic.SyntheticScene(cfg, n, device="cuda:0", seed=8)
+        t = LocoManipulationTask(cfg, n, scene=sc, device="cuda:0", seed=8)
+        if early:
+            t.set_defer_finish(True)
+            t.set_early_reset(True)
+        tasks.append(t); scenes.append(sc)
+        outs.append((torch.zeros(n, 12, device="cuda"), torch.zeros(n, 1, device="cuda")))
+    _, unis = rollout_inputs(n, 10, seed=17)
+    for task in tasks:
+        task.pre_physics_step(torch.zeros(n, 12, device="cuda"), unis[0].cuda())
+    fields = ("obs_buf", "rew_buf", "reset_buf", "progress_buf", "successes", "consecutive_successes", "goal_reset_buf", "goal_quaternions",
+              "_actions_ring", "last_base_tip_positions", "last_joint_velocities", "targets_loco", "targets_mani", "num_reset_buf")
+    with torch.no_grad():
+        for t in range(9):
+            st = scenes[0].generate(t)
+            for task, sc, (mu, v) in zip(tasks, scenes, outs):
+                sc.load(st)
+                task.post_physics_step()
+                policy(task.obs_buf, out=(mu, v), sink=task.action_sink())
+                task.pre_physics_step(None, unis[t + 1].cuda())
+            tasks[1].post_finish()
+            torch.cuda.synchronize()
+            for f in fields + ("_extras_buf", "_counters"):
+                assert torch.equal(getattr(tasks[0], f), getattr(tasks[1], f)), f"step {t}: {f}"
+            k = int(tasks[0].num_reset_buf[0])
+            assert torch.equal(tasks[0].reset_env_ids()[:k], tasks[1].reset_env_ids()[:k]), f"step {t}: reset id list"
+            assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]), f"step {t}: policy outputs"
+            for grp in ("loco", "mani"):
+                for k_, v_ in getattr(scenes[0], grp).items():
+                    assert torch.equal(getattr(scenes[1], grp)[k_], v_), f"step {t}: scene.{grp}.{k_}"
