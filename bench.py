@@ -338,7 +338,7 @@ class Pipeline:
         rotation (bench.py's default: the programmatic-dependent-launch chain then also spans the step boundaries, which a graph launch
         per step cuts).  ``after_step(i)``: called after each eager warm-up step (tests/test_bench_shapes_gpu.py tracks the oracle
         through them)."""
-        assert STATE_SETS % 2 == 0 and steps_per_graph in (1, STATE_SETS)
+        assert STATE_SETS % 2 == 0 and (steps_per_graph == 1 or steps_per_graph % STATE_SETS == 0)
         if self.w["policy"] != "mlp":
             return                                      # the GAE cadence needs a host-side counter: stay eager
         side = torch.cuda.Stream(device=self.device)
@@ -355,7 +355,7 @@ class Pipeline:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 for j in range(steps_per_graph):
-                    self.step_eager(i + j)
+                    self.step_eager((i + j) % STATE_SETS)
             self.graphs.append(g)
             self.graph_parity.append(self.lib.lm_task_step_parity(self.task._handle))
         torch.cuda.synchronize()
@@ -366,7 +366,7 @@ class Pipeline:
         if self.graphs is not None:
             spg = self.steps_per_graph
             if t % spg == 0:
-                k = (t % STATE_SETS) // spg
+                k = (t % STATE_SETS) // spg if spg <= STATE_SETS else 0
                 self.graphs[k].replay()
                 # replays skip the host side of pre_physics_step: keep the handle's ring parity in step for host-side readers
                 self.lib.lm_task_set_step_parity(self.task._handle, self.graph_parity[k])
@@ -461,8 +461,14 @@ def cuda_arm(args):
 
     if not args.no_graphs:
         assert HORIZON_MLP % STATE_SETS == 0
-        pipe.capture(steps_per_graph=1 if os.environ.get("LM_BENCH_GRAPH_PER_STEP") else STATE_SETS)
-    for t in range(-(-max(args.warmup, 3) // STATE_SETS) * STATE_SETS):     # whole rotations of the state sets
+        # one graph per rollout horizon (48 steps = 8 rotations of the state sets); LM_BENCH_GRAPH_STEPS: 1 or a multiple of STATE_SETS
+        spg = int(os.environ.get("LM_BENCH_GRAPH_STEPS", "1" if os.environ.get("LM_BENCH_GRAPH_PER_STEP") else str(HORIZON_MLP)))
+        assert HORIZON_MLP % spg == 0
+        pipe.capture(steps_per_graph=spg)
+    wq = getattr(pipe, "steps_per_graph", 1) if pipe.graphs is not None else 1
+    wq = max(wq, STATE_SETS)
+    warm_steps = -(-max(args.warmup, 3) // wq) * wq                        # whole graphs / rotations of the state sets
+    for t in range(warm_steps):
         pipe.step(t)
     for _ in range(2):      # NCCL connects lazily at the first collective of each size: keep that out of the timed region
         comm()
@@ -677,7 +683,7 @@ def cuda_arm(args):
     if rank == 0:
         clocks = sampler.summary()
         line = {"metric": "env-steps/s (obs+reward+PD+reset+policy)", "value": value, "unit": "env-steps/s", "n_gpus": world,
-                "steps": steps_timed, "steps_requested": args.steps, "warmup": -(-max(args.warmup, 3) // STATE_SETS) * STATE_SETS, "ms_per_step": ms_total / steps_timed,
+                "steps": steps_timed, "steps_requested": args.steps, "warmup": warm_steps, "ms_per_step": ms_total / steps_timed,
                 "timed_region_s": ms_total * 1e-3, "collectives_in_timed_region": collectives, "collective_us": comm_us,
                 "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32 task math, bf16 x bf16 -> f32 policy GEMMs",

@@ -381,22 +381,23 @@ def test_deferred_finish_matches_inline(n):
             assert torch.equal(getattr(dfr, f), getattr(ref, f)), f"step {t}: {f} after post"
 
 
-def test_bench_whole_rotation_graph_equals_per_step_graphs():
-    """bench.py replays ONE graph holding a whole rotation of the six state sets (the PDL chain then spans the step boundaries); the
-    per-step graphs are what the port tracks above.  Same seeds, 18 steps each: every task / policy buffer bit-identical at the
-    rotation boundaries."""
+@pytest.mark.parametrize("spg", [6, 48])
+def test_bench_multi_step_graph_equals_per_step_graphs(spg):
+    """bench.py replays ONE graph holding a whole rollout horizon (48 steps = 8 rotations of the six state sets; the PDL chain then
+    spans the step boundaries); the per-step graphs are what the port tracks above.  Same seeds: every task / policy buffer
+    bit-identical at the graph boundaries."""
     import bench
     dev = torch.device("cuda:0")
     S = bench.STATE_SETS
     pipes = []
-    for spg in (1, S):
+    for k in (1, spg):
         pipe = bench.Pipeline("cotrain64k", dev, rank=0)
-        pipe.capture(steps_per_graph=spg)
+        pipe.capture(steps_per_graph=k)
         pipes.append(pipe)
     a, b = pipes
     assert len(a.graphs) == S and len(b.graphs) == 1
-    for rot in range(3):
-        for t in range(rot * S, (rot + 1) * S):
+    for rot in range(3 if spg == S else 2):
+        for t in range(rot * spg, (rot + 1) * spg):
             a.step(t); b.step(t)
         for p_ in pipes:
             p_.task.post_finish()
