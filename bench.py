@@ -229,7 +229,8 @@ def bind_host_cores(local_rank, world):
 
 
 class Pipeline:
-    """Device-resident step loop: S state sets, one CUDA graph per set (pre + post + policy = 3 launches)."""
+    """Device-resident step loop: S rotating state sets, post + policy + pre = 3 launches per step, captured as one CUDA graph per
+    rollout horizon (see capture())."""
 
     def __init__(self, workload, device, rank):
         from locomanipulationrl_b200 import _lib, configs, synthetic
