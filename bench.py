@@ -837,6 +837,14 @@ def e2e_arm(pipe, args, world, device, rank=0, readback_obs=False, shards=None):
     sets = []                                     # STATE_SETS x shards pinned host states (> L2, and never the same twice in a row)
     for i in range(STATE_SETS):
         sets.append([s.scene.pack_host(s.scene.generate(i)) for s in stepper.shards])
+    if os.environ.get("LM_BENCH_WC"):             # experiment: write-combined pinned memory for the state on its way to the device
+        from locomanipulationrl_b200._lib import HostBuffer
+        for per_shard in sets:
+            for hs in per_shard:
+                for grp in list(hs):
+                    hb = HostBuffer(hs[grp].numel(), write_combined=True)
+                    hb.tensor.copy_(hs[grp].view(-1))
+                    hs[grp] = hb
     g = torch.Generator().manual_seed(11 + rank)
     for s in stepper.shards:
         s.uniforms_host.copy_(torch.rand(s.n, 3, generator=g))

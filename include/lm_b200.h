@@ -598,6 +598,10 @@ int lm_task_step_host_async(LmTask* task, const LmRobotViews* loco, const LmRobo
 int lm_task_step_host_policy_async(LmTask* task, const LmRobotViews* loco, const LmRobotViews* mani, const float* env_pos,
                                    const LmTaskBuffers* buf, const LmHostStep* io, const LmHostPolicy* policy, void* stream);
 int lm_stream_synchronize(void* stream);
+/* Page-locked host memory for the host-buffer entries (cudaHostAlloc).  write_combined != 0: cudaHostAllocWriteCombined — for
+ * buffers the host only WRITES (the physics state on its way to the device): PCIe reads then bypass the CPU caches. */
+void* lm_host_alloc(int64_t bytes, int32_t write_combined);
+void lm_host_free(void* p);
 
 #ifdef __cplusplus
 }

@@ -204,6 +204,8 @@ SYMBOLS = {
     "lm_task_step_host_policy_async": (C.c_int, [_vp, C.POINTER(LmRobotViews), C.POINTER(LmRobotViews), _vp, C.POINTER(LmTaskBuffers), C.POINTER(LmHostStep),
                                                  C.POINTER(LmHostPolicy), _vp]),
     "lm_stream_synchronize": (C.c_int, [_vp]),
+    "lm_host_alloc": (_vp, [_i64, _i32]),
+    "lm_host_free": (None, [_vp]),
 }
 
 # LM_B200_LIB: load another build of the same library (kernel experiments); there is still no fallback
@@ -316,3 +318,31 @@ def task_params(cfg: TaskConfig, num_envs: int, clamp_actions: bool = True, dof_
         p.loco_default_quaternion[i] = cfg.loco_default_quaternion[i]
         p.mani_default_quaternion[i] = cfg.mani_default_quaternion[i]
     return p
+
+
+class HostBuffer:
+    """Page-locked host memory from the library (``lm_host_alloc``), viewed as a CPU float32 tensor.  ``write_combined``: for
+    buffers the host only writes (physics state on its way to the device)."""
+
+    def __init__(self, numel: int, write_combined: bool = False):
+        import torch
+        self._lib = load()
+        self.ptr = self._lib.lm_host_alloc(int(numel) * 4, int(bool(write_combined)))
+        if not self.ptr:
+            raise LmError("lm_host_alloc failed: " + self._lib.lm_last_error().decode())
+        self._raw = (C.c_float * int(numel)).from_address(self.ptr)
+        self.tensor = torch.frombuffer(self._raw, dtype=torch.float32)
+
+    def data_ptr(self) -> int:
+        return self.ptr
+
+    def numel(self) -> int:
+        return self.tensor.numel()
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                self._lib.lm_host_free(self.ptr)
+                self.ptr = None
+        except Exception:
+            pass

@@ -1804,6 +1804,14 @@ int lm_task_step_host_policy_async(LmTask* t, const LmRobotViews* loco, const Lm
   return e == cudaSuccess ? LM_OK : lm_fail((int)e, "lm_task_step_host_policy_async: %s", cudaGetErrorString(e));
 }
 
+void* lm_host_alloc(int64_t bytes, int32_t write_combined) {
+  void* p = nullptr;
+  cudaError_t e = cudaHostAlloc(&p, (size_t)bytes, write_combined ? cudaHostAllocWriteCombined : cudaHostAllocDefault);
+  if (e != cudaSuccess) { lm_set_error("lm_host_alloc: %s", cudaGetErrorString(e)); return nullptr; }
+  return p;
+}
+void lm_host_free(void* p) { if (p) cudaFreeHost(p); }
+
 int lm_stream_synchronize(void* stream) {
   cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
   return e == cudaSuccess ? LM_OK : lm_fail((int)e, "lm_stream_synchronize: %s", cudaGetErrorString(e));
